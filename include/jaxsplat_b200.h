@@ -1,0 +1,106 @@
+/* jaxsplat_b200 -- C ABI of the B200-native (sm_100a) splatting hot path.
+ *
+ * Drop-in boundary for yklcs/jaxsplat's native layer.  Each entry point names the reference
+ * interface it replaces (paths relative to the reference repository root).  Plain C types only:
+ * no torch / pybind / C++ types cross this boundary, nothing here ever throws, and every call
+ * enqueues work on the caller's stream only.
+ *
+ * The four jsb200_{project,rasterize}_{fwd,bwd} functions are XLA GPU custom-call targets
+ * (legacy "API_VERSION_ORIGINAL/STATUS_RETURNING"-compatible signature) and take exactly the
+ * operand-then-result buffer lists of the reference:
+ *
+ *   project_fwd    in : mean3ds(N,3) scales(N,3) quats(N,4) viewmat(4,4)
+ *                  out: cov3ds(N,6) xys(N,2) depths(N) radii(N)i32 conics(N,3) compensation(N)
+ *                       num_tiles_hit(N)i32 cum_tiles_hit(N)i32
+ *   project_bwd    in : mean3ds scales quats viewmat cov3ds xys radii conics compensation
+ *                       v_compensation(N) v_xy(N,2) v_depth(N) v_conic(N,3)
+ *                  out: v_mean3d(N,3) v_scale(N,3) v_quat(N,4) v_cov2d(N,3) v_cov3d(N,6)
+ *   rasterize_fwd  in : colors(N,3) opacities(N) background(3) xys depths radii conics
+ *                       cum_tiles_hit
+ *                  out: final_Ts(H,W) final_idx(H,W)i32 out_img(H,W,3)
+ *   rasterize_bwd  in : colors opacities background xys depths radii conics cum_tiles_hit
+ *                       final_Ts final_idx v_out_img(H,W,3) v_out_img_alpha(H,W)
+ *                  out: v_colors(N,3) v_opacity(N) v_xy(N,2) v_xy_abs(N,2) v_conic(N,3)
+ *
+ * All arrays are C-contiguous float32 unless marked i32.  Results arrive uninitialised and are
+ * fully written by the call.  `opaque` is the 80-byte descriptor from jsb200_make_descriptor.
+ */
+#ifndef JAXSPLAT_B200_H_
+#define JAXSPLAT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st *jsb200_stream_t; /* == cudaStream_t */
+
+#if defined(__GNUC__)
+#define JSB200_API __attribute__((visibility("default")))
+#else
+#define JSB200_API
+#endif
+
+#define JSB200_DESCRIPTOR_BYTES 80
+
+/* replaces ops::project::fwd::xla   (lib/ops.h:45-53, lib/ops.cu:12-61; registered by
+ * lib/ffi.cu:6 as "project_fwd") */
+JSB200_API void jsb200_project_fwd(jsb200_stream_t stream, void **buffers, const char *opaque,
+                        size_t opaque_len);
+/* replaces ops::project::bwd::xla   (lib/ops.h:58-66, lib/ops.cu:63-105; "project_bwd") */
+JSB200_API void jsb200_project_bwd(jsb200_stream_t stream, void **buffers, const char *opaque,
+                        size_t opaque_len);
+/* replaces ops::rasterize::fwd::xla (lib/ops.h:71-79, lib/ops.cu:107-170; "rasterize_fwd") */
+JSB200_API void jsb200_rasterize_fwd(jsb200_stream_t stream, void **buffers, const char *opaque,
+                          size_t opaque_len);
+/* replaces ops::rasterize::bwd::xla (lib/ops.h:84-92, lib/ops.cu:172-235; "rasterize_bwd") */
+JSB200_API void jsb200_rasterize_bwd(jsb200_stream_t stream, void **buffers, const char *opaque,
+                          size_t opaque_len);
+
+/* replaces make_descriptor (lib/ffi.cu:15-52): fills out[80] with the reference-compatible
+ * descriptor (img_shape is given as H, W like the Python API).  Returns 0 on success. */
+JSB200_API int jsb200_make_descriptor(unsigned num_points, unsigned img_h, unsigned img_w, float fx, float fy,
+                           float cx, float cy, float glob_scale, float clip_thresh,
+                           unsigned block_width, char *out);
+
+/* replaces ops::sort_and_bin (lib/ops.h:31-41, lib/ops.cu:645-793): binning only; writes the
+ * depth-sorted gaussian ids (num_intersects i32) and tile_bins (tiles x int2) to device buffers.
+ * Returns 0 on success. */
+JSB200_API int jsb200_sort_and_bin(jsb200_stream_t stream, const char *opaque, size_t opaque_len,
+                        unsigned num_intersects, const float *xys, const float *depths,
+                        const int *radii, const int *cum_tiles_hit, int *gaussian_ids_sorted,
+                        int *tile_bins);
+
+/* replaces ops::cumsum (lib/ops.h:24-29, lib/ops.cu:607-643): inclusive int32 prefix sum. */
+JSB200_API int jsb200_cumsum(jsb200_stream_t stream, const int *input, int *output, int num_items);
+
+/* Error channel (the reference throws std::runtime_error through the C frame,
+ * lib/common.h:11-23).  Returns the sticky error text of the calling thread's last failing call,
+ * or NULL; jsb200_clear_error resets it.  Error state is also mirrored process-wide so a host
+ * framework thread can poll it: jsb200_error_count(). */
+JSB200_API const char *jsb200_last_error(void);
+JSB200_API void jsb200_clear_error(void);
+JSB200_API unsigned long long jsb200_error_count(void);
+
+/* Test / measurement hooks (no reference equivalent). */
+/* key: "cull" (1 default; 0 disables the conservative warp-rectangle pre-filter),
+ *      "cache" (1 default; 0 forces rasterize_bwd to re-bin instead of reusing the forward's) */
+JSB200_API int jsb200_set_option(const char *key, int value);
+/* Copies the binning produced by the most recent rasterize/sort_and_bin call on `stream` into
+ * caller device buffers (any may be NULL): ids_sorted[num_intersects] i32, tile_bins[tiles] int2,
+ * keys64_sorted[num_intersects] i64 = (tile << 32 | depth bits) as the reference sorts them.
+ * Returns num_intersects, or -1 on error. */
+JSB200_API long long jsb200_debug_binning(jsb200_stream_t stream, const float *depths, int *ids_sorted,
+                               int *tile_bins, long long *keys64_sorted);
+/* counters since load: [0] rasterize_fwd calls, [1] rasterize_bwd calls, [2] binning runs,
+ * [3] binning cache hits, [4] last num_intersects, [5] workspace bytes, [6] kernel launches */
+JSB200_API void jsb200_get_stats(unsigned long long *out7);
+/* releases every workspace (all devices/streams). */
+JSB200_API void jsb200_release(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JAXSPLAT_B200_H_ */

@@ -1,0 +1,101 @@
+"""ctypes loader for the C-ABI library ``lib/libjaxsplat_b200.so`` (include/jaxsplat_b200.h).
+
+There is deliberately NO fallback: if the CUDA library has not been built the import of any
+compute entry point fails loudly (``python -c "import __graft_entry__ as g; g.build()"`` or
+``make -C jaxsplat_b200/csrc`` builds it in-tree).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libjaxsplat_b200.so")
+
+# every symbol include/jaxsplat_b200.h declares
+EXPORTS = (
+    "jsb200_project_fwd",
+    "jsb200_project_bwd",
+    "jsb200_rasterize_fwd",
+    "jsb200_rasterize_bwd",
+    "jsb200_make_descriptor",
+    "jsb200_sort_and_bin",
+    "jsb200_cumsum",
+    "jsb200_last_error",
+    "jsb200_clear_error",
+    "jsb200_error_count",
+    "jsb200_set_option",
+    "jsb200_debug_binning",
+    "jsb200_get_stats",
+    "jsb200_release",
+)
+
+_lib = None
+
+
+class NativeLibraryMissing(ImportError):
+    pass
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NativeLibraryMissing(
+            f"{LIB_PATH} not found: build it with `make -C jaxsplat_b200/csrc` "
+            "(or __graft_entry__.build()). jaxsplat_b200 has no CPU or PyTorch fallback."
+        )
+    L = ctypes.CDLL(LIB_PATH)
+    vp, cp, sz, u, i, f = (ctypes.c_void_p, ctypes.c_char_p, ctypes.c_size_t, ctypes.c_uint,
+                           ctypes.c_int, ctypes.c_float)
+    for name in ("jsb200_project_fwd", "jsb200_project_bwd", "jsb200_rasterize_fwd",
+                 "jsb200_rasterize_bwd"):
+        fn = getattr(L, name)
+        fn.argtypes = [vp, ctypes.POINTER(vp), cp, sz]
+        fn.restype = None
+    L.jsb200_make_descriptor.argtypes = [u, u, u, f, f, f, f, f, f, u, ctypes.c_char_p]
+    L.jsb200_make_descriptor.restype = i
+    L.jsb200_sort_and_bin.argtypes = [vp, cp, sz, u, vp, vp, vp, vp, vp, vp]
+    L.jsb200_sort_and_bin.restype = i
+    L.jsb200_cumsum.argtypes = [vp, vp, vp, i]
+    L.jsb200_cumsum.restype = i
+    L.jsb200_last_error.argtypes = []
+    L.jsb200_last_error.restype = ctypes.c_char_p
+    L.jsb200_clear_error.argtypes = []
+    L.jsb200_clear_error.restype = None
+    L.jsb200_error_count.argtypes = []
+    L.jsb200_error_count.restype = ctypes.c_ulonglong
+    L.jsb200_set_option.argtypes = [cp, i]
+    L.jsb200_set_option.restype = i
+    L.jsb200_debug_binning.argtypes = [vp, vp, vp, vp, vp]
+    L.jsb200_debug_binning.restype = ctypes.c_longlong
+    L.jsb200_get_stats.argtypes = [ctypes.POINTER(ctypes.c_ulonglong)]
+    L.jsb200_get_stats.restype = None
+    L.jsb200_release.argtypes = []
+    L.jsb200_release.restype = None
+    _lib = L
+    return L
+
+
+def check_error(where: str) -> None:
+    """Raise if the calling thread's last native call recorded an error."""
+    L = lib()
+    msg = L.jsb200_last_error()
+    if msg:
+        text = msg.decode("utf-8", "replace")
+        L.jsb200_clear_error()
+        raise RuntimeError(f"jaxsplat_b200 {where}: {text}")
+
+
+def stats() -> dict:
+    out = (ctypes.c_ulonglong * 7)()
+    lib().jsb200_get_stats(out)
+    keys = ("rasterize_fwd_calls", "rasterize_bwd_calls", "binning_runs", "binning_cache_hits",
+            "last_num_intersects", "workspace_bytes", "kernel_launches")
+    return dict(zip(keys, [int(x) for x in out]))
+
+
+def set_option(key: str, value: int) -> None:
+    if lib().jsb200_set_option(key.encode(), int(value)) != 0:
+        check_error("set_option")

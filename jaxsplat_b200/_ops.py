@@ -1,0 +1,127 @@
+"""The four primitives (``project_fwd/bwd``, ``rasterize_fwd/bwd``) on torch CUDA tensors.
+
+Shapes, dtypes and operand/result orders follow the reference's abstract-eval contracts
+(jaxsplat/_project/abstract.py:7-22,57-77 and jaxsplat/_rasterize/abstract.py:7-24,62-85) and
+its buffer unpacking (lib/ops.cu:237-605).  ``table`` selects the native library that executes
+the call; by default ours.  Result buffers are allocated uninitialised (optionally poisoned),
+exactly what XLA hands a custom call.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _ffi
+
+_POISON = False
+
+
+def poison_outputs(enable: bool) -> None:
+    """Test hook: pre-fill result buffers with NaN / 0x7f7f7f7f like an adversarial XLA."""
+    global _POISON
+    _POISON = bool(enable)
+
+
+def _out(shape, dtype, device):
+    t = torch.empty(shape, dtype=dtype, device=device)
+    if _POISON:
+        if dtype.is_floating_point:
+            t.fill_(float("nan"))
+        else:
+            t.fill_(0x7F7F7F7F)
+    return t
+
+
+def _f32(t: torch.Tensor, shape, name: str) -> torch.Tensor:
+    if t.dtype != torch.float32 or tuple(t.shape) != tuple(shape):
+        raise TypeError(f"{name}: expected float32{tuple(shape)}, got {t.dtype}{tuple(t.shape)}")
+    return t.contiguous()
+
+
+def _i32(t: torch.Tensor, shape, name: str) -> torch.Tensor:
+    if t.dtype != torch.int32 or tuple(t.shape) != tuple(shape):
+        raise TypeError(f"{name}: expected int32{tuple(shape)}, got {t.dtype}{tuple(t.shape)}")
+    return t.contiguous()
+
+
+def _desc(table, num_points, img_shape, f, c, glob_scale, clip_thresh, block_width) -> bytes:
+    return table.make_descriptor(num_points, tuple(img_shape), tuple(f), tuple(c), glob_scale,
+                                 clip_thresh, block_width)
+
+
+def project_fwd(mean3ds, scales, quats, viewmat, *, num_points, img_shape, f, c, glob_scale,
+                clip_thresh, block_width, table: Optional[_ffi.CustomCallTable] = None):
+    table = table or _ffi.native_table()
+    n, dev = num_points, mean3ds.device
+    ins = [_f32(mean3ds, (n, 3), "mean3ds"), _f32(scales, (n, 3), "scales"),
+           _f32(quats, (n, 4), "quats"), _f32(viewmat, (4, 4), "viewmat")]
+    outs = [_out((n, 6), torch.float32, dev), _out((n, 2), torch.float32, dev),
+            _out((n, 1), torch.float32, dev), _out((n, 1), torch.int32, dev),
+            _out((n, 3), torch.float32, dev), _out((n, 1), torch.float32, dev),
+            _out((n, 1), torch.int32, dev), _out((n, 1), torch.int32, dev)]
+    table.call("project_fwd", ins, outs,
+               _desc(table, n, img_shape, f, c, glob_scale, clip_thresh, block_width))
+    # (cov3ds, xys, depths, radii, conics, compensation, num_tiles_hit, cum_tiles_hit)
+    return tuple(outs)
+
+
+def project_bwd(mean3ds, scales, quats, viewmat, cov3ds, xys, radii, conics, compensation,
+                v_compensation, v_xy, v_depth, v_conic, *, num_points, img_shape, f, c, glob_scale,
+                clip_thresh, block_width, table: Optional[_ffi.CustomCallTable] = None):
+    table = table or _ffi.native_table()
+    n, dev = num_points, mean3ds.device
+    ins = [_f32(mean3ds, (n, 3), "mean3ds"), _f32(scales, (n, 3), "scales"),
+           _f32(quats, (n, 4), "quats"), _f32(viewmat, (4, 4), "viewmat"),
+           _f32(cov3ds, (n, 6), "cov3ds"), _f32(xys, (n, 2), "xys"), _i32(radii, (n, 1), "radii"),
+           _f32(conics, (n, 3), "conics"), _f32(compensation, (n, 1), "compensation"),
+           _f32(v_compensation, (n, 1), "v_compensation"), _f32(v_xy, (n, 2), "v_xy"),
+           _f32(v_depth, (n, 1), "v_depth"), _f32(v_conic, (n, 3), "v_conic")]
+    outs = [_out((n, 3), torch.float32, dev), _out((n, 3), torch.float32, dev),
+            _out((n, 4), torch.float32, dev), _out((n, 3), torch.float32, dev),
+            _out((n, 6), torch.float32, dev)]
+    table.call("project_bwd", ins, outs,
+               _desc(table, n, img_shape, f, c, glob_scale, clip_thresh, block_width))
+    # (v_mean3d, v_scale, v_quat, v_cov2d, v_cov3d)
+    return tuple(outs)
+
+
+def rasterize_fwd(colors, opacities, background, xys, depths, radii, conics, cum_tiles_hit, *,
+                  num_points, img_shape, block_width,
+                  table: Optional[_ffi.CustomCallTable] = None):
+    table = table or _ffi.native_table()
+    n, dev = num_points, colors.device
+    H, W = img_shape
+    ins = [_f32(colors, (n, 3), "colors"), _f32(opacities, (n, 1), "opacities"),
+           _f32(background, (3,), "background"), _f32(xys, (n, 2), "xys"),
+           _f32(depths, (n, 1), "depths"), _i32(radii, (n, 1), "radii"),
+           _f32(conics, (n, 3), "conics"), _i32(cum_tiles_hit, (n, 1), "cum_tiles_hit")]
+    outs = [_out((H, W, 1), torch.float32, dev), _out((H, W, 1), torch.int32, dev),
+            _out((H, W, 3), torch.float32, dev)]
+    # the reference's rasterize lowerings pass zeros for f, c, glob_scale, clip_thresh
+    # (jaxsplat/_rasterize/lowering.py:28-36)
+    table.call("rasterize_fwd", ins, outs,
+               _desc(table, n, img_shape, (0.0, 0.0), (0.0, 0.0), 0.0, 0.0, block_width))
+    # (final_Ts, final_idx, img)
+    return tuple(outs)
+
+
+def rasterize_bwd(colors, opacities, background, xys, depths, radii, conics, cum_tiles_hit,
+                  final_Ts, final_idx, v_img, v_img_alpha, *, num_points, img_shape, block_width,
+                  table: Optional[_ffi.CustomCallTable] = None):
+    table = table or _ffi.native_table()
+    n, dev = num_points, colors.device
+    H, W = img_shape
+    ins = [_f32(colors, (n, 3), "colors"), _f32(opacities, (n, 1), "opacities"),
+           _f32(background, (3,), "background"), _f32(xys, (n, 2), "xys"),
+           _f32(depths, (n, 1), "depths"), _i32(radii, (n, 1), "radii"),
+           _f32(conics, (n, 3), "conics"), _i32(cum_tiles_hit, (n, 1), "cum_tiles_hit"),
+           _f32(final_Ts, (H, W, 1), "final_Ts"), _i32(final_idx, (H, W, 1), "final_idx"),
+           _f32(v_img, (H, W, 3), "v_img"), _f32(v_img_alpha, (H, W, 1), "v_img_alpha")]
+    outs = [_out((n, 3), torch.float32, dev), _out((n, 1), torch.float32, dev),
+            _out((n, 2), torch.float32, dev), _out((n, 2), torch.float32, dev),
+            _out((n, 3), torch.float32, dev)]
+    table.call("rasterize_bwd", ins, outs,
+               _desc(table, n, img_shape, (0.0, 0.0), (0.0, 0.0), 0.0, 0.0, block_width))
+    # (v_colors, v_opacity, v_xy, v_xy_abs, v_conic)
+    return tuple(outs)

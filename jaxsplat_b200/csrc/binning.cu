@@ -1,0 +1,291 @@
+// Intersect emission and tile binning for sm_100a.
+//
+// Behavioural spec: reference lib/kernels/forward.cu:135-179 (map_gaussian_to_intersects),
+// :184-208 (get_tile_bin_edges) and lib/ops.cu:645-793 (sort_and_bin): the sorted list is the
+// stable ascending order of keys (tile_id << 32 | depth_bits) over all (Gaussian, covered tile)
+// pairs, emitted Gaussian-major, row-major inside each tile box.
+//
+// Design (not a port).  The reference sorts I 64-bit keys with 6 radix passes.  The same total
+// order is obtained here with far less traffic by splitting the key:
+//   1. sort the N Gaussians once by depth bits (stable, ties keep index order)        [N-scale]
+//   2. emit (tile id, gaussian id) pairs in that depth order, offsets from a fused scan
+//   3. one stable LSD sort of the I pairs on the ceil(log2 T) live tile bits only      [I-scale]
+// Stability of step 3 preserves the depth-then-index order inside every tile, i.e. exactly the
+// reference's (tile, depth, index) order, with 2-byte keys and 2 passes instead of 8-byte keys
+// and 6 passes.
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace jsb {
+namespace {
+
+constexpr int BT = 256;
+
+__device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
+    x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull;
+    x ^= x >> 27; x *= 0x94d049bb133111ebull;
+    x ^= x >> 31;
+    return x;
+}
+
+__global__ void __launch_bounds__(BT)
+bin_prep_kernel(const BinParams p, const float2 *__restrict__ xys,
+                const float *__restrict__ depths, const int *__restrict__ radii,
+                const float *__restrict__ conics, const float *__restrict__ opacities,
+                const float *__restrict__ colors, SplatRecord *__restrict__ records,
+                unsigned *__restrict__ depth_keys, unsigned *__restrict__ ids,
+                unsigned *__restrict__ tile_counts, unsigned long long *__restrict__ fingerprint) {
+    __shared__ __align__(16) float s_buf[BT * 6];
+    const int tid = threadIdx.x;
+    const long long base = (long long)blockIdx.x * BT;
+    const long long g = base + tid;
+    const long long n = p.num_points;
+    float *s_conic = s_buf, *s_color = s_buf + BT * 3;
+    const bool pack = conics != nullptr;  // sort_and_bin-only callers pass no appearance data
+    if (pack) {
+        slab_load<3, BT>(s_conic, conics, base * 3, n * 3);
+        slab_load<3, BT>(s_color, colors, base * 3, n * 3);
+    }
+    __syncthreads();
+    unsigned long long h = 0;
+    unsigned cnt = 0;
+    if (g < n) {
+        const float2 xy = __ldg(xys + g);
+        const float depth = __ldg(depths + g);
+        const int radius = __ldg(radii + g);
+        float opac = 0.f, cx = 0.f, cy = 0.f, cz = 0.f, r = 0.f, gr = 0.f, b = 0.f;
+        if (pack) {
+            opac = __ldg(opacities + g);
+            cx = s_conic[tid * 3]; cy = s_conic[tid * 3 + 1]; cz = s_conic[tid * 3 + 2];
+            r = s_color[tid * 3]; gr = s_color[tid * 3 + 1]; b = s_color[tid * 3 + 2];
+            SplatRecord rec;
+            rec.q0 = make_float4(xy.x, xy.y, opac, cx);
+            rec.q1 = make_float4(cy, cz, r, gr);
+            rec.q2 = make_float4(b, 0.f, 0.f, 0.f);
+            records[g] = rec;
+        }
+        unsigned key = 0xFFFFFFFFu;
+        if (radius > 0) {
+            unsigned x0, x1, y0, y1;
+            tile_bbox(xy.x, xy.y, (float)radius, p.block_width_f, p.tiles_x, p.tiles_y, x0, x1,
+                      y0, y1);
+            cnt = (x1 - x0) * (y1 - y0);
+            key = __float_as_uint(depth);
+        }
+        depth_keys[g] = key;
+        ids[g] = (unsigned)g;
+        tile_counts[g] = cnt;
+        // order-independent fingerprint of everything the cached binning depends on
+        unsigned long long a = ((unsigned long long)__float_as_uint(xy.x) << 32) | __float_as_uint(xy.y);
+        unsigned long long c = ((unsigned long long)__float_as_uint(depth) << 32) | (unsigned)radius;
+        unsigned long long d = ((unsigned long long)__float_as_uint(cx) << 32) | __float_as_uint(cy);
+        unsigned long long e = ((unsigned long long)__float_as_uint(cz) << 32) | __float_as_uint(opac);
+        unsigned long long f = ((unsigned long long)__float_as_uint(r) << 32) | __float_as_uint(gr);
+        h = mix64(a + 0x9e3779b97f4a7c15ull * (unsigned long long)(g + 1));
+        h = mix64(h ^ c);
+        h = mix64(h ^ d);
+        h = mix64(h ^ e);
+        h = mix64(h ^ f);
+        h = mix64(h ^ __float_as_uint(b));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        h += __shfl_xor_sync(0xffffffffu, h, o);
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    }
+    if ((tid & 31) == 0) {
+        if (h) atomicAdd(fingerprint, h);
+        if (cnt) atomicAdd(fingerprint + 1, (unsigned long long)cnt);  // total intersections
+    }
+}
+
+// inclusive int32 prefix sum, single pass (reference ops.cu:607-643 uses cub::DeviceScan)
+constexpr int SC_ITEMS = 4;
+__global__ void __launch_bounds__(BT)
+inclusive_scan_kernel(const int *__restrict__ in, int *__restrict__ out, unsigned n,
+                      unsigned long long *__restrict__ chain, unsigned *__restrict__ ticket,
+                      int *__restrict__ err) {
+    __shared__ unsigned s_ws[BT / 32 + 1];
+    __shared__ unsigned s_bid, s_prefix;
+    const int tid = threadIdx.x;
+    if (tid == 0) s_bid = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const unsigned bid = s_bid;
+    const unsigned long long first = (unsigned long long)bid * (BT * SC_ITEMS) + (unsigned)tid * SC_ITEMS;
+    unsigned v[SC_ITEMS], sum = 0;
+#pragma unroll
+    for (int i = 0; i < SC_ITEMS; ++i) {
+        v[i] = (first + i < n) ? (unsigned)in[first + i] : 0u;
+        sum += v[i];
+    }
+    unsigned total;
+    unsigned run = cta_exclusive_scan<BT>(sum, &total, s_ws);
+    if (tid < 32) {
+        unsigned pre = chain_exclusive_prefix(chain, (int)bid, total, err);
+        if (tid == 0) s_prefix = pre;
+    }
+    __syncthreads();
+    run += s_prefix;
+#pragma unroll
+    for (int i = 0; i < SC_ITEMS; ++i) {
+        run += v[i];
+        if (first + i < n) out[first + i] = (int)run;
+    }
+}
+
+template <typename TileKey>
+__global__ void __launch_bounds__(BT)
+emit_kernel(const BinParams p, const unsigned *__restrict__ order,
+            const unsigned *__restrict__ tile_counts, const float2 *__restrict__ xys,
+            const int *__restrict__ radii, TileKey *__restrict__ keys,
+            unsigned *__restrict__ vals, unsigned long long *__restrict__ chain,
+            unsigned *__restrict__ ticket, int *__restrict__ err) {
+    __shared__ unsigned s_off[BT + 1];
+    __shared__ unsigned s_tile0[BT];   // first tile id of the box
+    __shared__ unsigned s_w[BT];       // box width in tiles
+    __shared__ unsigned s_g[BT];
+    __shared__ unsigned s_ws[BT / 32 + 1];
+    __shared__ unsigned s_bid, s_prefix;
+    const int tid = threadIdx.x;
+    if (tid == 0) s_bid = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const unsigned bid = s_bid;
+    const long long pos = (long long)bid * BT + tid;
+    unsigned cnt = 0;
+    if (pos < (long long)p.num_points) {
+        const unsigned g = order[pos];
+        cnt = tile_counts[g];
+        s_g[tid] = g;
+        if (cnt) {
+            const float2 xy = __ldg(xys + g);
+            const int radius = __ldg(radii + g);
+            unsigned x0, x1, y0, y1;
+            tile_bbox(xy.x, xy.y, (float)radius, p.block_width_f, p.tiles_x, p.tiles_y, x0, x1,
+                      y0, y1);
+            s_tile0[tid] = y0 * p.tiles_x + x0;
+            s_w[tid] = x1 - x0;
+        }
+    }
+    unsigned total;
+    const unsigned excl = cta_exclusive_scan<BT>(cnt, &total, s_ws);
+    s_off[tid] = excl;
+    if (tid == 0) s_off[BT] = total;
+    if (tid < 32) {
+        unsigned pre = chain_exclusive_prefix(chain, (int)bid, total, err);
+        if (tid == 0) s_prefix = pre;
+    }
+    __syncthreads();
+    const unsigned long long out0 = s_prefix;
+    for (unsigned k = tid; k < total; k += BT) {
+        // last t with s_off[t] <= k
+        int lo = 0, hi = BT;  // invariant: s_off[lo] <= k < s_off[hi]
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+            int mid = (lo + hi) >> 1;
+            if (s_off[mid] <= k) lo = mid; else hi = mid;
+        }
+        const unsigned j = k - s_off[lo];
+        const unsigned w = s_w[lo];
+        const unsigned row = j / w;
+        const unsigned col = j - row * w;
+        keys[out0 + k] = (TileKey)(s_tile0[lo] + row * p.tiles_x + col);
+        vals[out0 + k] = s_g[lo];
+    }
+}
+
+template <typename TileKey>
+__global__ void __launch_bounds__(256)
+bin_edges_kernel(const TileKey *__restrict__ keys, unsigned n, int2 *__restrict__ bins) {
+    const unsigned i = blockIdx.x * 256u + threadIdx.x;
+    if (i >= n) return;
+    const unsigned cur = keys[i];
+    if (i == 0) bins[cur].x = 0;
+    if (i == n - 1) bins[cur].y = (int)n;
+    if (i == 0) return;
+    const unsigned prev = keys[i - 1];
+    if (prev != cur) {
+        bins[prev].y = (int)i;
+        bins[cur].x = (int)i;
+    }
+}
+
+__global__ void rebuild_keys64_kernel(const int2 *__restrict__ bins, unsigned num_tiles,
+                                      const unsigned *__restrict__ ids,
+                                      const float *__restrict__ depths,
+                                      long long *__restrict__ keys64) {
+    const unsigned t = blockIdx.x;
+    if (t >= num_tiles) return;
+    const int2 r = bins[t];
+    for (int k = r.x + (int)threadIdx.x; k < r.y; k += (int)blockDim.x) {
+        const long long d = (long long)(int)__float_as_uint(depths[ids[k]]);
+        keys64[k] = ((long long)t << 32) | d;
+    }
+}
+
+}  // namespace
+
+int launch_inclusive_scan_i32(cudaStream_t stream, const int *in, int *out, unsigned n,
+                              unsigned long long *chain, unsigned *ticket, int *err) {
+    if (n == 0) return 0;
+    inclusive_scan_kernel<<<ceil_div(n, BT * SC_ITEMS), BT, 0, stream>>>(in, out, n, chain, ticket, err);
+    JSB_CUDA_OK(cudaGetLastError());
+    note_launch();
+    return 0;
+}
+
+int launch_bin_prep(cudaStream_t stream, const BinParams &p, const float *xys,
+                    const float *depths, const int *radii, const float *conics,
+                    const float *opacities, const float *colors, SplatRecord *records,
+                    unsigned *depth_keys, unsigned *ids, unsigned *tile_counts,
+                    unsigned long long *fingerprint) {
+    if (p.num_points == 0) return 0;
+    bin_prep_kernel<<<ceil_div(p.num_points, BT), BT, 0, stream>>>(
+        p, reinterpret_cast<const float2 *>(xys), depths, radii, conics, opacities, colors,
+        records, depth_keys, ids, tile_counts, fingerprint);
+    JSB_CUDA_OK(cudaGetLastError());
+    note_launch();
+    return 0;
+}
+
+template <typename TileKey>
+int launch_emit(cudaStream_t stream, const BinParams &p, const unsigned *order,
+                const unsigned *tile_counts, const float *xys, const int *radii, TileKey *keys,
+                unsigned *vals, unsigned long long *chain, unsigned *ticket, int *err) {
+    if (p.num_points == 0) return 0;
+    emit_kernel<TileKey><<<ceil_div(p.num_points, BT), BT, 0, stream>>>(
+        p, order, tile_counts, reinterpret_cast<const float2 *>(xys), radii, keys, vals, chain,
+        ticket, err);
+    JSB_CUDA_OK(cudaGetLastError());
+    note_launch();
+    return 0;
+}
+template int launch_emit<uint16_t>(cudaStream_t, const BinParams &, const unsigned *,
+                                   const unsigned *, const float *, const int *, uint16_t *,
+                                   unsigned *, unsigned long long *, unsigned *, int *);
+template int launch_emit<uint32_t>(cudaStream_t, const BinParams &, const unsigned *,
+                                   const unsigned *, const float *, const int *, uint32_t *,
+                                   unsigned *, unsigned long long *, unsigned *, int *);
+
+template <typename TileKey>
+int launch_bin_edges(cudaStream_t stream, const TileKey *sorted_keys, unsigned n,
+                     int2 *tile_bins) {
+    if (n == 0) return 0;
+    bin_edges_kernel<TileKey><<<ceil_div(n, 256), 256, 0, stream>>>(sorted_keys, n, tile_bins);
+    JSB_CUDA_OK(cudaGetLastError());
+    note_launch();
+    return 0;
+}
+template int launch_bin_edges<uint16_t>(cudaStream_t, const uint16_t *, unsigned, int2 *);
+template int launch_bin_edges<uint32_t>(cudaStream_t, const uint32_t *, unsigned, int2 *);
+
+int launch_rebuild_keys64(cudaStream_t stream, const int2 *tile_bins, unsigned num_tiles,
+                          const unsigned *ids_sorted, const float *depths, long long *keys64) {
+    if (num_tiles == 0) return 0;
+    rebuild_keys64_kernel<<<num_tiles, 128, 0, stream>>>(tile_bins, num_tiles, ids_sorted, depths,
+                                                         keys64);
+    JSB_CUDA_OK(cudaGetLastError());
+    note_launch();
+    return 0;
+}
+
+}  // namespace jsb

@@ -1,0 +1,566 @@
+// C-ABI layer + host orchestration.  Replaces the reference's lib/ffi.cu and lib/ops.cu.
+//
+// Differences from the reference orchestration (lib/ops.cu) that matter for speed:
+//   * persistent, grow-only workspace per (device, stream) -- no cudaMalloc/cudaFree/
+//     cudaMallocAsync in steady state (the reference does 9+9+4+4 per fwd+bwd);
+//   * exactly one host sync per rasterize call (the intersection count and the input fingerprint
+//     arrive together in pinned memory); project_fwd/bwd never block the host;
+//   * outputs are written in full by the kernels: the only memsets left are the gradient
+//     accumulators of rasterize_bwd and a few KB of scan/sort bookkeeping;
+//   * rasterize_bwd reuses the forward's binning (sorted ids + tile bins) when a 64-bit
+//     fingerprint of its inputs matches -- the reference emits, sorts and bins twice.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+
+#include "../../include/jaxsplat_b200.h"
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace jsb {
+
+// ---- error channel ----------------------------------------------------------------------------
+static thread_local std::string t_error;
+static thread_local bool t_has_error = false;
+static std::atomic<unsigned long long> g_error_count{0};
+static std::atomic<unsigned long long> g_stats[7];
+
+void set_error(const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    t_error = buf;
+    t_has_error = true;
+    g_error_count.fetch_add(1);
+    fprintf(stderr, "[jaxsplat_b200] error: %s\n", buf);
+}
+void note_launch(int n) { g_stats[6].fetch_add((unsigned long long)n); }
+
+extern bool g_disable_cull;
+static bool g_disable_cache = false;
+
+// ---- workspace --------------------------------------------------------------------------------
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+struct Ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::mutex mu;
+    // N-scale
+    DevBuf records, dkeys_a, dkeys_b, ids_a, ids_b, counts, sort_n_scratch, chain;
+    // I-scale
+    DevBuf tkeys_a, tkeys_b, tvals_a, tvals_b, sort_i_scratch;
+    DevBuf bins, small;  // small: [fingerprint u64][total u64][err int x4][tickets u32 x8]
+    unsigned long long *h_pinned = nullptr;  // [fingerprint][total][err...]
+    // binning cache
+    bool cache_valid = false;
+    unsigned long long cache_fp = 0;
+    unsigned cache_n = 0, cache_tiles = 0, cache_bw = 0, cache_tiles_x = 0;
+    unsigned long long cache_I = 0;
+    unsigned *cache_ids = nullptr;  // points into tvals_a or tvals_b
+    size_t total_bytes = 0;
+
+    int ensure(DevBuf &b, size_t bytes) {
+        if (bytes <= b.cap) return 0;
+        size_t want = bytes + bytes / 4 + 256;
+        if (b.p) {
+            JSB_CUDA_OK(cudaStreamSynchronize(stream));
+            JSB_CUDA_OK(cudaFree(b.p));
+            total_bytes -= b.cap;
+            b.p = nullptr;
+            b.cap = 0;
+            cache_valid = false;
+        }
+        JSB_CUDA_OK(cudaMalloc(&b.p, want));
+        b.cap = want;
+        total_bytes += want;
+        g_stats[5].store(total_bytes);
+        return 0;
+    }
+    void release() {
+        DevBuf *all[] = {&records, &dkeys_a, &dkeys_b, &ids_a, &ids_b, &counts, &sort_n_scratch,
+                         &chain, &tkeys_a, &tkeys_b, &tvals_a, &tvals_b, &sort_i_scratch, &bins,
+                         &small};
+        for (DevBuf *b : all) {
+            if (b->p) cudaFree(b->p);
+            b->p = nullptr;
+            b->cap = 0;
+        }
+        if (h_pinned) cudaFreeHost(h_pinned);
+        h_pinned = nullptr;
+        cache_valid = false;
+        total_bytes = 0;
+    }
+};
+
+static std::mutex g_ctx_mu;
+static std::map<std::pair<int, cudaStream_t>, std::unique_ptr<Ctx>> g_ctx;
+
+static Ctx *get_ctx(cudaStream_t stream) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) {
+        set_error("cudaGetDevice failed");
+        return nullptr;
+    }
+    std::lock_guard<std::mutex> lk(g_ctx_mu);
+    auto key = std::make_pair(dev, stream);
+    auto it = g_ctx.find(key);
+    if (it != g_ctx.end()) return it->second.get();
+    auto c = std::make_unique<Ctx>();
+    c->device = dev;
+    c->stream = stream;
+    Ctx *raw = c.get();
+    g_ctx[key] = std::move(c);
+    return raw;
+}
+
+static const Descriptor *unpack(const char *opaque, size_t len) {
+    if (len != sizeof(Descriptor) || opaque == nullptr) {
+        set_error("invalid opaque descriptor size %zu (expected %zu)", len, sizeof(Descriptor));
+        return nullptr;
+    }
+    return reinterpret_cast<const Descriptor *>(opaque);
+}
+
+static int tile_bits(unsigned tiles) {
+    int b = 1;
+    while ((1ull << b) < tiles) ++b;
+    return b;
+}
+
+constexpr int SM_FP = 0, SM_TOTAL = 1;       // u64 slots in `small`
+constexpr int SM_ERR_WORD = 4;               // int slots start (byte 16)
+constexpr int SM_TICKET_WORD = 8;            // u32 tickets start (byte 32)
+constexpr size_t SMALL_BYTES = 64;
+
+// ---- binning -----------------------------------------------------------------------------------
+// Runs prep (+fingerprint, +total) and returns after the single host sync with *I and *fp set.
+static int bin_prepare(Ctx &c, const Descriptor &d, const float *xys, const float *depths,
+                       const int *radii, const float *conics, const float *opac,
+                       const float *colors, unsigned long long *I, unsigned long long *fp) {
+    const unsigned n = d.num_points;
+    cudaStream_t s = c.stream;
+    if (!c.h_pinned) JSB_CUDA_OK(cudaHostAlloc((void **)&c.h_pinned, SMALL_BYTES, cudaHostAllocDefault));
+    if (!c.small.p) {
+        if (c.ensure(c.small, SMALL_BYTES)) return 1;
+        JSB_CUDA_OK(cudaMemsetAsync(c.small.p, 0, SMALL_BYTES, s));
+    }
+    *I = 0;
+    *fp = 0;
+    if (n == 0) return 0;
+    if (c.ensure(c.records, (size_t)n * sizeof(SplatRecord))) return 1;
+    if (c.ensure(c.dkeys_a, (size_t)n * 4) || c.ensure(c.dkeys_b, (size_t)n * 4)) return 1;
+    if (c.ensure(c.ids_a, (size_t)n * 4) || c.ensure(c.ids_b, (size_t)n * 4)) return 1;
+    if (c.ensure(c.counts, (size_t)n * 4)) return 1;
+    // zero fingerprint/total (bytes 0..16) and tickets (32..64); the error words (16..32) are
+    // sticky so that a device-side failure of the PREVIOUS call is seen at this call's sync
+    JSB_CUDA_OK(cudaMemsetAsync(c.small.p, 0, 16, s));
+    JSB_CUDA_OK(cudaMemsetAsync((char *)c.small.p + 32, 0, 32, s));
+    BinParams bp{n, (float)(int)d.block_width, d.tiles_x, d.tiles_y};
+    unsigned long long *small64 = (unsigned long long *)c.small.p;
+    if (launch_bin_prep(s, bp, xys, depths, radii, conics, opac, colors,
+                        (SplatRecord *)c.records.p, (unsigned *)c.dkeys_a.p, (unsigned *)c.ids_a.p,
+                        (unsigned *)c.counts.p, small64))
+        return 1;
+    JSB_CUDA_OK(cudaMemcpyAsync(c.h_pinned, c.small.p, 32, cudaMemcpyDeviceToHost, s));
+    JSB_CUDA_OK(cudaStreamSynchronize(s));
+    *fp = c.h_pinned[SM_FP];
+    *I = c.h_pinned[SM_TOTAL];
+    const int *e = (const int *)c.h_pinned + SM_ERR_WORD;
+    if (e[0] | e[1] | e[2] | e[3]) {
+        set_error("device-side look-back spin limit tripped in an earlier call (flags %d %d %d %d)",
+                  e[0], e[1], e[2], e[3]);
+        JSB_CUDA_OK(cudaMemsetAsync((char *)c.small.p + 16, 0, 16, s));
+        return 1;
+    }
+    return 0;
+}
+
+template <typename TileKey>
+static int bin_sort_t(Ctx &c, const Descriptor &d, const float *xys, const int *radii,
+                      unsigned long long I) {
+    const unsigned n = d.num_points;
+    cudaStream_t s = c.stream;
+    const unsigned tiles = d.tiles_x * d.tiles_y;
+    int *err = (int *)c.small.p + SM_ERR_WORD;
+    unsigned *tickets = (unsigned *)c.small.p + SM_TICKET_WORD;
+    // 1. depth order of the Gaussians (N-scale, 32-bit keys)
+    if (c.ensure(c.sort_n_scratch, radix_scratch_bytes(n, 32))) return 1;
+    bool in_b = false;
+    if (radix_sort_pairs<uint32_t>(s, (uint32_t *)c.dkeys_a.p, (uint32_t *)c.dkeys_b.p,
+                                   (unsigned *)c.ids_a.p, (unsigned *)c.ids_b.p, n, 32,
+                                   c.sort_n_scratch.p, err, &in_b))
+        return 1;
+    const unsigned *order = (const unsigned *)(in_b ? c.ids_b.p : c.ids_a.p);
+    // 2. emit (tile, id) pairs in depth order
+    if (c.ensure(c.tkeys_a, (size_t)I * sizeof(TileKey)) || c.ensure(c.tkeys_b, (size_t)I * sizeof(TileKey)))
+        return 1;
+    if (c.ensure(c.tvals_a, (size_t)I * 4) || c.ensure(c.tvals_b, (size_t)I * 4)) return 1;
+    const size_t chain_bytes = (size_t)ceil_div(n, 256) * 8;
+    if (c.ensure(c.chain, chain_bytes)) return 1;
+    JSB_CUDA_OK(cudaMemsetAsync(c.chain.p, 0, chain_bytes, s));
+    BinParams bp{n, (float)(int)d.block_width, d.tiles_x, d.tiles_y};
+    if (launch_emit<TileKey>(s, bp, order, (const unsigned *)c.counts.p, xys, radii,
+                             (TileKey *)c.tkeys_a.p, (unsigned *)c.tvals_a.p,
+                             (unsigned long long *)c.chain.p, tickets, err))
+        return 1;
+    // 3. stable sort on the live tile bits
+    const int bits = tile_bits(tiles);
+    if (c.ensure(c.sort_i_scratch, radix_scratch_bytes((unsigned)I, bits))) return 1;
+    if (radix_sort_pairs<TileKey>(s, (TileKey *)c.tkeys_a.p, (TileKey *)c.tkeys_b.p,
+                                  (unsigned *)c.tvals_a.p, (unsigned *)c.tvals_b.p, (unsigned)I,
+                                  bits, c.sort_i_scratch.p, err, &in_b))
+        return 1;
+    // 4. tile bins
+    if (c.ensure(c.bins, (size_t)tiles * sizeof(int2))) return 1;
+    JSB_CUDA_OK(cudaMemsetAsync(c.bins.p, 0, (size_t)tiles * sizeof(int2), s));
+    if (launch_bin_edges<TileKey>(s, (const TileKey *)(in_b ? c.tkeys_b.p : c.tkeys_a.p),
+                                  (unsigned)I, (int2 *)c.bins.p))
+        return 1;
+    c.cache_ids = (unsigned *)(in_b ? c.tvals_b.p : c.tvals_a.p);
+    return 0;
+}
+
+static int bin_sort(Ctx &c, const Descriptor &d, const float *xys, const int *radii,
+                    unsigned long long I, unsigned long long fp) {
+    if (I >= (1ull << 30)) {
+        set_error("num_intersects=%llu exceeds the supported 2^30", I);
+        return 1;
+    }
+    const unsigned tiles = d.tiles_x * d.tiles_y;
+    c.cache_valid = false;
+    int rc = tiles <= 65536 ? bin_sort_t<uint16_t>(c, d, xys, radii, I)
+                            : bin_sort_t<uint32_t>(c, d, xys, radii, I);
+    if (rc) return rc;
+    c.cache_valid = true;
+    c.cache_fp = fp;
+    c.cache_n = d.num_points;
+    c.cache_tiles = tiles;
+    c.cache_tiles_x = d.tiles_x;
+    c.cache_bw = d.block_width;
+    c.cache_I = I;
+    g_stats[2].fetch_add(1);
+    g_stats[4].store(I);
+    return 0;
+}
+
+static bool cache_hit(const Ctx &c, const Descriptor &d, unsigned long long I,
+                      unsigned long long fp) {
+    return !g_disable_cache && c.cache_valid && c.cache_fp == fp && c.cache_I == I &&
+           c.cache_n == d.num_points && c.cache_tiles == d.tiles_x * d.tiles_y &&
+           c.cache_tiles_x == d.tiles_x && c.cache_bw == d.block_width;
+}
+
+// ---- op bodies ---------------------------------------------------------------------------------
+static int project_fwd_impl(cudaStream_t stream, void **buf, const Descriptor &d) {
+    Ctx *c = get_ctx(stream);
+    if (!c) return 1;
+    std::lock_guard<std::mutex> lk(c->mu);
+    const unsigned n = d.num_points;
+    if (n == 0) return 0;
+    if (d.block_width == 0) { set_error("block_width must be > 0"); return 1; }
+    ProjectFwdParams p;
+    p.num_points = n;
+    p.glob_scale = d.glob_scale;
+    p.fx = d.fx; p.fy = d.fy; p.cx = d.cx; p.cy = d.cy;
+    p.tan_fovx = (float)(0.5 * (double)d.img_w / (double)d.fx);
+    p.tan_fovy = (float)(0.5 * (double)d.img_h / (double)d.fy);
+    p.clip_thresh = d.clip_thresh;
+    p.block_width_f = (float)(int)d.block_width;
+    p.tiles_x = d.tiles_x; p.tiles_y = d.tiles_y;
+    const size_t chain_bytes = (size_t)ceil_div(n, 256) * 8 + 64;
+    if (c->ensure(c->chain, chain_bytes)) return 1;
+    JSB_CUDA_OK(cudaMemsetAsync(c->chain.p, 0, chain_bytes, stream));
+    unsigned long long *chain = (unsigned long long *)c->chain.p;
+    unsigned *ticket = (unsigned *)((char *)c->chain.p + chain_bytes - 64);
+    if (!c->small.p) {
+        if (c->ensure(c->small, SMALL_BYTES)) return 1;
+        JSB_CUDA_OK(cudaMemsetAsync(c->small.p, 0, SMALL_BYTES, stream));
+    }
+    int *err = (int *)c->small.p + SM_ERR_WORD + 3;
+    return launch_project_fwd(stream, p, (const float *)buf[0], (const float *)buf[1],
+                              (const float *)buf[2], (const float *)buf[3], (float *)buf[4],
+                              (float *)buf[5], (float *)buf[6], (int *)buf[7], (float *)buf[8],
+                              (float *)buf[9], (int *)buf[10], (int *)buf[11], chain, ticket, err);
+}
+
+static int project_bwd_impl(cudaStream_t stream, void **buf, const Descriptor &d) {
+    if (d.num_points == 0) return 0;
+    ProjectBwdParams p{d.num_points, d.glob_scale, d.fx, d.fy};
+    // in: 0 mean3ds 1 scales 2 quats 3 viewmat 4 cov3ds 5 xys 6 radii 7 conics 8 compensation
+    //     9 v_compensation 10 v_xy 11 v_depth 12 v_conic ; out: 13 v_mean3d 14 v_scale 15 v_quat
+    //     16 v_cov2d 17 v_cov3d
+    return launch_project_bwd(stream, p, (const float *)buf[0], (const float *)buf[1],
+                              (const float *)buf[2], (const float *)buf[3], (const float *)buf[4],
+                              (const int *)buf[6], (const float *)buf[7], (const float *)buf[8],
+                              (const float *)buf[9], (const float *)buf[10],
+                              (const float *)buf[11], (const float *)buf[12], (float *)buf[13],
+                              (float *)buf[14], (float *)buf[15], (float *)buf[16],
+                              (float *)buf[17]);
+}
+
+static RasterParams raster_params(const Descriptor &d) {
+    RasterParams rp;
+    rp.img_w = d.img_w; rp.img_h = d.img_h;
+    rp.tiles_x = d.tiles_x; rp.tiles_y = d.tiles_y;
+    rp.block_width = d.block_width;
+    return rp;
+}
+
+static int check_raster_desc(const Descriptor &d) {
+    if (d.block_width == 0 || d.block_width > 16) {
+        set_error("block_width=%u unsupported (1..16)", d.block_width);
+        return 1;
+    }
+    if (d.tiles_x != ceil_div(d.img_w, d.block_width) || d.tiles_y != ceil_div(d.img_h, d.block_width)) {
+        set_error("descriptor tile grid %ux%u inconsistent with image %ux%u / block %u", d.tiles_x,
+                  d.tiles_y, d.img_w, d.img_h, d.block_width);
+        return 1;
+    }
+    return 0;
+}
+
+static int rasterize_fwd_impl(cudaStream_t stream, void **buf, const Descriptor &d) {
+    // in: 0 colors 1 opacities 2 background 3 xys 4 depths 5 radii 6 conics 7 cum_tiles_hit
+    // out: 8 final_Ts 9 final_idx 10 out_img
+    if (check_raster_desc(d)) return 1;
+    Ctx *c = get_ctx(stream);
+    if (!c) return 1;
+    std::lock_guard<std::mutex> lk(c->mu);
+    g_stats[0].fetch_add(1);
+    const RasterParams rp = raster_params(d);
+    unsigned long long I = 0, fp = 0;
+    if (bin_prepare(*c, d, (const float *)buf[3], (const float *)buf[4], (const int *)buf[5],
+                    (const float *)buf[6], (const float *)buf[1], (const float *)buf[0], &I, &fp))
+        return 1;
+    if (I == 0) {
+        c->cache_valid = false;
+        g_stats[4].store(0);
+        return launch_fill_background(stream, rp, (const float *)buf[2], (float *)buf[8],
+                                      (int *)buf[9], (float *)buf[10]);
+    }
+    if (cache_hit(*c, d, I, fp)) {
+        g_stats[3].fetch_add(1);
+    } else if (bin_sort(*c, d, (const float *)buf[3], (const int *)buf[5], I, fp)) {
+        return 1;
+    }
+    return launch_raster_fwd(stream, rp, c->cache_ids, (const int2 *)c->bins.p,
+                             (const SplatRecord *)c->records.p, (const float *)buf[2],
+                             (float *)buf[8], (int *)buf[9], (float *)buf[10]);
+}
+
+static int rasterize_bwd_impl(cudaStream_t stream, void **buf, const Descriptor &d) {
+    // in: 0 colors 1 opacities 2 background 3 xys 4 depths 5 radii 6 conics 7 cum_tiles_hit
+    //     8 final_Ts 9 final_idx 10 v_out_img 11 v_out_img_alpha
+    // out: 12 v_colors 13 v_opacity 14 v_xy 15 v_xy_abs 16 v_conic
+    if (check_raster_desc(d)) return 1;
+    Ctx *c = get_ctx(stream);
+    if (!c) return 1;
+    std::lock_guard<std::mutex> lk(c->mu);
+    g_stats[1].fetch_add(1);
+    const size_t n = d.num_points;
+    if (n == 0) return 0;
+    JSB_CUDA_OK(cudaMemsetAsync(buf[12], 0, n * 3 * 4, stream));
+    JSB_CUDA_OK(cudaMemsetAsync(buf[13], 0, n * 4, stream));
+    JSB_CUDA_OK(cudaMemsetAsync(buf[14], 0, n * 2 * 4, stream));
+    JSB_CUDA_OK(cudaMemsetAsync(buf[15], 0, n * 2 * 4, stream));
+    JSB_CUDA_OK(cudaMemsetAsync(buf[16], 0, n * 3 * 4, stream));
+    unsigned long long I = 0, fp = 0;
+    if (bin_prepare(*c, d, (const float *)buf[3], (const float *)buf[4], (const int *)buf[5],
+                    (const float *)buf[6], (const float *)buf[1], (const float *)buf[0], &I, &fp))
+        return 1;
+    if (I == 0) return 0;
+    if (cache_hit(*c, d, I, fp)) {
+        g_stats[3].fetch_add(1);
+    } else if (bin_sort(*c, d, (const float *)buf[3], (const int *)buf[5], I, fp)) {
+        return 1;
+    }
+    return launch_raster_bwd(stream, raster_params(d), c->cache_ids, (const int2 *)c->bins.p,
+                             (const SplatRecord *)c->records.p, (const float *)buf[2],
+                             (const float *)buf[8], (const int *)buf[9], (const float *)buf[10],
+                             (const float *)buf[11], (float *)buf[14], (float *)buf[15],
+                             (float *)buf[16], (float *)buf[12], (float *)buf[13]);
+}
+
+template <typename F>
+static void guarded(const char *name, cudaStream_t stream, void **buffers, const char *opaque,
+                    size_t len, F body) {
+    try {
+        const Descriptor *d = unpack(opaque, len);
+        if (!d) return;
+        if (!buffers) { set_error("%s: null buffer list", name); return; }
+        Descriptor local;
+        memcpy(&local, d, sizeof local);  // opaque may be unaligned
+        body(stream, buffers, local);
+    } catch (const std::exception &e) {
+        set_error("%s: %s", name, e.what());
+    } catch (...) {
+        set_error("%s: unknown exception", name);
+    }
+}
+
+}  // namespace jsb
+
+// ================================================================================================
+extern "C" {
+
+void jsb200_project_fwd(jsb200_stream_t stream, void **buffers, const char *opaque, size_t len) {
+    jsb::guarded("project_fwd", (cudaStream_t)stream, buffers, opaque, len, jsb::project_fwd_impl);
+}
+void jsb200_project_bwd(jsb200_stream_t stream, void **buffers, const char *opaque, size_t len) {
+    jsb::guarded("project_bwd", (cudaStream_t)stream, buffers, opaque, len, jsb::project_bwd_impl);
+}
+void jsb200_rasterize_fwd(jsb200_stream_t stream, void **buffers, const char *opaque, size_t len) {
+    jsb::guarded("rasterize_fwd", (cudaStream_t)stream, buffers, opaque, len,
+                 jsb::rasterize_fwd_impl);
+}
+void jsb200_rasterize_bwd(jsb200_stream_t stream, void **buffers, const char *opaque, size_t len) {
+    jsb::guarded("rasterize_bwd", (cudaStream_t)stream, buffers, opaque, len,
+                 jsb::rasterize_bwd_impl);
+}
+
+int jsb200_make_descriptor(unsigned num_points, unsigned img_h, unsigned img_w, float fx, float fy,
+                           float cx, float cy, float glob_scale, float clip_thresh,
+                           unsigned block_width, char *out) {
+    if (!out || block_width == 0) {
+        jsb::set_error("make_descriptor: bad arguments");
+        return 1;
+    }
+    jsb::Descriptor d;
+    memset(&d, 0, sizeof d);
+    d.num_points = num_points;
+    d.img_w = img_w; d.img_h = img_h; d.img_d = 1;
+    d.fx = fx; d.fy = fy; d.cx = cx; d.cy = cy;
+    d.glob_scale = glob_scale;
+    d.clip_thresh = clip_thresh;
+    d.block_width = block_width;
+    d.block_dim_1d = block_width * block_width;
+    d.grid_dim_1d = (num_points + d.block_dim_1d - 1) / d.block_dim_1d;
+    d.tiles_x = (img_w + block_width - 1) / block_width;
+    d.tiles_y = (img_h + block_width - 1) / block_width;
+    d.tiles_z = 1;
+    d.bdx = block_width; d.bdy = block_width; d.bdz = 1;
+    memcpy(out, &d, sizeof d);
+    return 0;
+}
+
+int jsb200_sort_and_bin(jsb200_stream_t stream_, const char *opaque, size_t len,
+                        unsigned num_intersects, const float *xys, const float *depths,
+                        const int *radii, const int *cum_tiles_hit, int *gaussian_ids_sorted,
+                        int *tile_bins) {
+    (void)cum_tiles_hit;
+    (void)num_intersects;  // recomputed on device; the caller's value only sizes its buffers
+    try {
+        cudaStream_t stream = (cudaStream_t)stream_;
+        const jsb::Descriptor *dp = jsb::unpack(opaque, len);
+        if (!dp) return 1;
+        jsb::Descriptor d;
+        memcpy(&d, dp, sizeof d);
+        if (jsb::check_raster_desc(d)) return 1;
+        jsb::Ctx *c = jsb::get_ctx(stream);
+        if (!c) return 1;
+        std::lock_guard<std::mutex> lk(c->mu);
+        unsigned long long I = 0, fp = 0;
+        if (jsb::bin_prepare(*c, d, xys, depths, radii, nullptr, nullptr, nullptr, &I, &fp)) return 1;
+        const unsigned tiles = d.tiles_x * d.tiles_y;
+        if (I != num_intersects) {
+            jsb::set_error("sort_and_bin: caller num_intersects=%u but inputs imply %llu",
+                           num_intersects, I);
+            return 1;
+        }
+        if (I == 0) {
+            JSB_CUDA_OK(cudaMemsetAsync(tile_bins, 0, (size_t)tiles * 8, stream));
+            return 0;
+        }
+        if (jsb::bin_sort(*c, d, xys, radii, I, fp)) return 1;
+        c->cache_valid = false;  // records were not packed: never reuse for rasterisation
+        JSB_CUDA_OK(cudaMemcpyAsync(gaussian_ids_sorted, c->cache_ids, (size_t)I * 4,
+                                    cudaMemcpyDeviceToDevice, stream));
+        JSB_CUDA_OK(cudaMemcpyAsync(tile_bins, c->bins.p, (size_t)tiles * 8,
+                                    cudaMemcpyDeviceToDevice, stream));
+        return 0;
+    } catch (...) {
+        jsb::set_error("sort_and_bin: exception");
+        return 1;
+    }
+}
+
+int jsb200_cumsum(jsb200_stream_t stream_, const int *input, int *output, int num_items) {
+    try {
+        cudaStream_t stream = (cudaStream_t)stream_;
+        if (num_items <= 0) return 0;
+        jsb::Ctx *c = jsb::get_ctx(stream);
+        if (!c) return 1;
+        std::lock_guard<std::mutex> lk(c->mu);
+        const size_t chain_bytes = (size_t)jsb::ceil_div((unsigned)num_items, 1024) * 8 + 64;
+        if (c->ensure(c->chain, chain_bytes)) return 1;
+        JSB_CUDA_OK(cudaMemsetAsync(c->chain.p, 0, chain_bytes, stream));
+        unsigned *ticket = (unsigned *)((char *)c->chain.p + chain_bytes - 64);
+        return jsb::launch_inclusive_scan_i32(stream, input, output, (unsigned)num_items,
+                                              (unsigned long long *)c->chain.p, ticket,
+                                              (int *)(ticket + 4));
+    } catch (...) {
+        jsb::set_error("cumsum: exception");
+        return 1;
+    }
+}
+
+const char *jsb200_last_error(void) { return jsb::t_has_error ? jsb::t_error.c_str() : nullptr; }
+void jsb200_clear_error(void) { jsb::t_has_error = false; jsb::t_error.clear(); }
+unsigned long long jsb200_error_count(void) { return jsb::g_error_count.load(); }
+
+int jsb200_set_option(const char *key, int value) {
+    if (!key) return 1;
+    if (!strcmp(key, "cull")) { jsb::g_disable_cull = (value == 0); return 0; }
+    if (!strcmp(key, "cache")) { jsb::g_disable_cache = (value == 0); return 0; }
+    jsb::set_error("set_option: unknown key '%s'", key);
+    return 1;
+}
+
+long long jsb200_debug_binning(jsb200_stream_t stream_, const float *depths, int *ids_sorted,
+                               int *tile_bins, long long *keys64_sorted) {
+    try {
+        cudaStream_t stream = (cudaStream_t)stream_;
+        jsb::Ctx *c = jsb::get_ctx(stream);
+        if (!c) return -1;
+        std::lock_guard<std::mutex> lk(c->mu);
+        if (!c->cache_valid) { jsb::set_error("debug_binning: no binning cached on this stream"); return -1; }
+        const size_t I = c->cache_I;
+        if (ids_sorted && cudaMemcpyAsync(ids_sorted, c->cache_ids, I * 4, cudaMemcpyDeviceToDevice, stream) != cudaSuccess) return -1;
+        if (tile_bins && cudaMemcpyAsync(tile_bins, c->bins.p, (size_t)c->cache_tiles * 8, cudaMemcpyDeviceToDevice, stream) != cudaSuccess) return -1;
+        if (keys64_sorted) {
+            if (!depths) { jsb::set_error("debug_binning: keys64 needs depths"); return -1; }
+            if (jsb::launch_rebuild_keys64(stream, (const int2 *)c->bins.p, c->cache_tiles, c->cache_ids, depths, keys64_sorted)) return -1;
+        }
+        return (long long)I;
+    } catch (...) {
+        return -1;
+    }
+}
+
+void jsb200_get_stats(unsigned long long *out7) {
+    if (!out7) return;
+    for (int i = 0; i < 7; ++i) out7[i] = jsb::g_stats[i].load();
+}
+
+void jsb200_release(void) {
+    std::lock_guard<std::mutex> lk(jsb::g_ctx_mu);
+    for (auto &kv : jsb::g_ctx) {
+        std::lock_guard<std::mutex> lk2(kv.second->mu);
+        cudaSetDevice(kv.second->device);
+        kv.second->release();
+    }
+    jsb::g_ctx.clear();
+}
+
+}  // extern "C"

@@ -1,0 +1,298 @@
+// Tile rasteriser, backward, for sm_100a.
+//
+// Behavioural spec: reference lib/kernels/backward.cu:153-343 (rasterize_bwd): per tile, replay
+// the sorted list back to front starting from each pixel's final_idx / final_Ts, un-composite T,
+// and accumulate d(loss)/d{colour, opacity, conic, xy, |xy|} per Gaussian.  Alpha is clamped at
+// 0.99 here (0.999 in the forward) and the clamp is treated as identity.
+//
+// Design (not a port):
+//   * same CTA/warp-rectangle layout, staging and conservative culling as raster_fwd.cu, so a
+//     warp only replays Gaussians that can reach its 8x4 pixels;
+//   * the CTA starts at the batch holding the largest final_idx of the tile instead of the end
+//     of the tile's list;
+//   * the 11 per-pixel partial gradients are reduced across the warp with a halving butterfly
+//     (16 shuffles: after each exchange a lane keeps half of the slots) instead of 11 full
+//     butterflies (55 shuffles), and the 11 totals end up in 11 different lanes which issue ONE
+//     predicated RED.ADD.F32 instruction instead of 11 serial ones from lane 0.
+#include "common.cuh"
+#include "kernels.cuh"
+#include "raster_cull.cuh"
+
+namespace jsb {
+namespace {
+
+constexpr int RB = 256;
+
+// Halving butterfly: on entry every lane holds 16 slots; on exit lane L holds in the return
+// value the warp-wide sum of slot (L >> 1).
+__device__ __forceinline__ float warp_reduce_16slots(float (&v)[16], int lane) {
+    {
+        const bool hi = lane & 16;
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+            const float send = hi ? v[s] : v[s + 8];
+            const float keep = hi ? v[s + 8] : v[s];
+            v[s] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
+    }
+    {
+        const bool hi = lane & 8;
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            const float send = hi ? v[s] : v[s + 4];
+            const float keep = hi ? v[s + 4] : v[s];
+            v[s] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+    }
+    {
+        const bool hi = lane & 4;
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            const float send = hi ? v[s] : v[s + 2];
+            const float keep = hi ? v[s + 2] : v[s];
+            v[s] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+    }
+    {
+        const bool hi = lane & 2;
+        const float send = hi ? v[0] : v[1];
+        const float keep = hi ? v[1] : v[0];
+        v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+    return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
+struct PixelGrad {
+    float v[11];  // rgb(3) conic(3) xy(2) xy_abs(2) opacity(1)
+};
+
+// per-pixel gradient of one valid (pixel, Gaussian) pair; updates T and the colour buffer
+__device__ __forceinline__ void pair_grad(float alpha, float vis, float opac, float dx, float dy,
+                                          float cx, float cy, float cz, float r, float g, float b,
+                                          const float3 v_out, float v_out_alpha, float T_final,
+                                          const float3 bg, float &T, float3 &buf, float *o) {
+    const float ra = frcp(fsub(1.f, alpha));
+    T = T * ra;
+    const float fac = alpha * T;
+    o[0] = v_out.x * fac;
+    o[1] = v_out.y * fac;
+    o[2] = v_out.z * fac;
+    float va = v_out.x * (T * r - buf.x * ra);
+    va = fmaf(v_out.y, T * g - buf.y * ra, va);
+    va = fmaf(v_out.z, T * b - buf.z * ra, va);
+    va = fmaf(v_out_alpha, T_final * ra, va);
+    const float nb = ra * (-T_final);
+    va = fmaf(v_out.x, nb * bg.x, va);
+    va = fmaf(v_out.y, nb * bg.y, va);
+    va = fmaf(v_out.z, nb * bg.z, va);
+    buf.x = fmaf(fac, r, buf.x);
+    buf.y = fmaf(fac, g, buf.y);
+    buf.z = fmaf(fac, b, buf.z);
+    const float v_sigma = (vis * (-opac)) * va;
+    const float hs = v_sigma * 0.5f;
+    o[3] = dx * (dx * hs);
+    o[4] = dy * (dx * v_sigma);
+    o[5] = dy * (dy * hs);
+    o[6] = fmaf(dy, cy, dx * cx) * v_sigma;
+    o[7] = fmaf(dy, cz, dx * cy) * v_sigma;
+    o[8] = fabsf(o[6]);
+    o[9] = fabsf(o[7]);
+    o[10] = vis * va;
+}
+
+template <bool CULL>
+__global__ void __launch_bounds__(RB)
+raster_bwd16_kernel(const RasterParams p, const unsigned *__restrict__ ids_sorted,
+                    const int2 *__restrict__ tile_bins, const SplatRecord *__restrict__ records,
+                    const float *__restrict__ background, const float *__restrict__ final_Ts,
+                    const int *__restrict__ final_idx, const float *__restrict__ v_out_img,
+                    const float *__restrict__ v_out_alpha_img, float *__restrict__ v_xy,
+                    float *__restrict__ v_xy_abs, float *__restrict__ v_conic,
+                    float *__restrict__ v_colors, float *__restrict__ v_opacity) {
+    __shared__ float4 sA[RB];
+    __shared__ float4 sB[RB];
+    __shared__ float sC[RB];
+    __shared__ unsigned sId[RB];
+    __shared__ unsigned char sMask[RB];
+    __shared__ int s_max[RB / 32];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned tile = blockIdx.x;
+    const unsigned tile_y = tile / p.tiles_x, tile_x = tile - tile_y * p.tiles_x;
+    const unsigned j = tile_x * 16 + (warp & 1) * kRectW + (lane & 7);
+    const unsigned i = tile_y * 16 + (warp >> 1) * kRectH + (lane >> 3);
+    const float px = (float)j + 0.5f, py = (float)i + 0.5f;
+    const bool inside = (i < p.img_h) && (j < p.img_w);
+    const int2 range = tile_bins[tile];
+
+    float T_final = 1.f, v_oa = 0.f;
+    float3 v_out = make_float3(0.f, 0.f, 0.f);
+    int bin_final = -1;
+    if (inside) {
+        const size_t pix = (size_t)i * p.img_w + j;
+        T_final = final_Ts[pix];
+        bin_final = final_idx[pix];
+        v_out = make_float3(v_out_img[pix * 3], v_out_img[pix * 3 + 1], v_out_img[pix * 3 + 2]);
+        v_oa = v_out_alpha_img[pix];
+    }
+    const float3 bg = make_float3(__ldg(background), __ldg(background + 1), __ldg(background + 2));
+    float T = T_final;
+    float3 buf = make_float3(0.f, 0.f, 0.f);
+
+    // largest final index of the warp and of the tile
+    int wmax = bin_final;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+    if (lane == 0) s_max[warp] = wmax;
+    __syncthreads();
+    int tmax = s_max[0];
+#pragma unroll
+    for (int w = 1; w < RB / 32; ++w) tmax = max(tmax, s_max[w]);
+    const int top = min(range.y - 1, tmax);
+    if (top < range.x) return;  // nothing in this tile was composited (uniform across the CTA)
+    const int num_batches = (top - range.x + RB) / RB;
+    const float tile_x0 = (float)(tile_x * 16), tile_y0 = (float)(tile_y * 16);
+
+    // lane L (even, L/2 < 11) owns output slot L/2 of the reduced gradient
+    const int slot = lane >> 1;
+    float *out_base;
+    int out_stride;
+    if (slot < 3) { out_base = v_colors + slot; out_stride = 3; }
+    else if (slot < 6) { out_base = v_conic + (slot - 3); out_stride = 3; }
+    else if (slot < 8) { out_base = v_xy + (slot - 6); out_stride = 2; }
+    else if (slot < 10) { out_base = v_xy_abs + (slot - 8); out_stride = 2; }
+    else { out_base = v_opacity; out_stride = 1; }
+    const bool writer = ((lane & 1) == 0) && slot < 11;
+
+    for (int b = 0; b < num_batches; ++b) {
+        if (b) __syncthreads();
+        const int batch_end = top - RB * b;  // slot t holds sorted index batch_end - t
+        const int idx = batch_end - tid;
+        unsigned mask = 0;
+        if (idx >= range.x) {
+            const unsigned g = ids_sorted[idx];
+            const float4 q0 = __ldg(&records[g].q0);
+            const float4 q1 = __ldg(&records[g].q1);
+            const float4 q2 = __ldg(&records[g].q2);
+            sA[tid] = q0;
+            sB[tid] = q1;
+            sC[tid] = q2.x;
+            sId[tid] = g;
+            mask = CULL ? cull_mask16(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, tile_x0, tile_y0) : 0xFFu;
+        }
+        sMask[tid] = (unsigned char)mask;
+        __syncthreads();
+
+#pragma unroll 1
+        for (int k = 0; k < RB / 32; ++k) {
+            // entries newer than the warp's largest final index cannot be valid for any lane
+            if (batch_end - (k * 32 + 31) > wmax) continue;
+            const unsigned m = sMask[k * 32 + lane];
+            unsigned bits = __ballot_sync(0xffffffffu, (m >> warp) & 1u);
+            while (bits) {
+                const int t = k * 32 + __ffs(bits) - 1;
+                bits &= bits - 1;
+                const float4 a = sA[t];
+                const float4 bq = sB[t];
+                const float dx = fsub(a.x, px), dy = fsub(a.y, py);
+                const float sigma = conic_sigma(a.w, bq.x, bq.y, dx, dy);
+                const float vis = ex2_approx(fmul(sigma, kNegLog2e));
+                const float alpha = fminf(fmul(a.z, vis), 0.99f);
+                const bool valid = inside && (batch_end - t <= bin_final) && !(sigma < 0.f) &&
+                                   !(alpha < kAlphaMin);
+                if (!__any_sync(0xffffffffu, valid)) continue;
+                float v[16];
+#pragma unroll
+                for (int s = 0; s < 16; ++s) v[s] = 0.f;
+                if (valid)
+                    pair_grad(alpha, vis, a.z, dx, dy, a.w, bq.x, bq.y, bq.z, bq.w, sC[t], v_out,
+                              v_oa, T_final, bg, T, buf, v);
+                const float total = warp_reduce_16slots(v, lane);
+                if (writer) atomicAdd(out_base + (size_t)sId[t] * out_stride, total);
+            }
+        }
+    }
+}
+
+// any block_width: one thread per pixel, per-thread atomics (semantics only, not tuned)
+__global__ void raster_bwd_generic_kernel(
+    const RasterParams p, const unsigned *__restrict__ ids_sorted,
+    const int2 *__restrict__ tile_bins, const SplatRecord *__restrict__ records,
+    const float *__restrict__ background, const float *__restrict__ final_Ts,
+    const int *__restrict__ final_idx, const float *__restrict__ v_out_img,
+    const float *__restrict__ v_out_alpha_img, float *__restrict__ v_xy,
+    float *__restrict__ v_xy_abs, float *__restrict__ v_conic, float *__restrict__ v_colors,
+    float *__restrict__ v_opacity) {
+    const unsigned tile = blockIdx.y * p.tiles_x + blockIdx.x;
+    const unsigned i = blockIdx.y * blockDim.y + threadIdx.y;
+    const unsigned j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (!(i < p.img_h && j < p.img_w)) return;
+    const float px = (float)j + 0.5f, py = (float)i + 0.5f;
+    const int2 range = tile_bins[tile];
+    const size_t pix = (size_t)i * p.img_w + j;
+    const float T_final = final_Ts[pix];
+    const int bin_final = final_idx[pix];
+    const float3 v_out = make_float3(v_out_img[pix * 3], v_out_img[pix * 3 + 1], v_out_img[pix * 3 + 2]);
+    const float v_oa = v_out_alpha_img[pix];
+    const float3 bg = make_float3(__ldg(background), __ldg(background + 1), __ldg(background + 2));
+    float T = T_final;
+    float3 buf = make_float3(0.f, 0.f, 0.f);
+    for (int idx = min(range.y - 1, bin_final); idx >= range.x; --idx) {
+        const unsigned g = ids_sorted[idx];
+        const float4 a = __ldg(&records[g].q0);
+        const float4 bq = __ldg(&records[g].q1);
+        const float cb = __ldg(&records[g].q2).x;
+        const float dx = fsub(a.x, px), dy = fsub(a.y, py);
+        const float sigma = conic_sigma(a.w, bq.x, bq.y, dx, dy);
+        const float vis = ex2_approx(fmul(sigma, kNegLog2e));
+        const float alpha = fminf(fmul(a.z, vis), 0.99f);
+        if (sigma < 0.f || alpha < kAlphaMin) continue;
+        float o[11];
+        pair_grad(alpha, vis, a.z, dx, dy, a.w, bq.x, bq.y, bq.z, bq.w, cb, v_out, v_oa, T_final,
+                  bg, T, buf, o);
+        atomicAdd(v_colors + 3 * (size_t)g + 0, o[0]);
+        atomicAdd(v_colors + 3 * (size_t)g + 1, o[1]);
+        atomicAdd(v_colors + 3 * (size_t)g + 2, o[2]);
+        atomicAdd(v_conic + 3 * (size_t)g + 0, o[3]);
+        atomicAdd(v_conic + 3 * (size_t)g + 1, o[4]);
+        atomicAdd(v_conic + 3 * (size_t)g + 2, o[5]);
+        atomicAdd(v_xy + 2 * (size_t)g + 0, o[6]);
+        atomicAdd(v_xy + 2 * (size_t)g + 1, o[7]);
+        atomicAdd(v_xy_abs + 2 * (size_t)g + 0, o[8]);
+        atomicAdd(v_xy_abs + 2 * (size_t)g + 1, o[9]);
+        atomicAdd(v_opacity + g, o[10]);
+    }
+}
+
+}  // namespace
+
+extern bool g_disable_cull;
+
+int launch_raster_bwd(cudaStream_t stream, const RasterParams &p, const unsigned *ids_sorted,
+                      const int2 *tile_bins, const SplatRecord *records, const float *background,
+                      const float *final_Ts, const int *final_idx, const float *v_out,
+                      const float *v_out_alpha, float *v_xy, float *v_xy_abs, float *v_conic,
+                      float *v_colors, float *v_opacity) {
+    const unsigned tiles = p.tiles_x * p.tiles_y;
+    if (tiles == 0) return 0;
+    if (p.block_width == 16) {
+        if (g_disable_cull)
+            raster_bwd16_kernel<false><<<tiles, RB, 0, stream>>>(
+                p, ids_sorted, tile_bins, records, background, final_Ts, final_idx, v_out,
+                v_out_alpha, v_xy, v_xy_abs, v_conic, v_colors, v_opacity);
+        else
+            raster_bwd16_kernel<true><<<tiles, RB, 0, stream>>>(
+                p, ids_sorted, tile_bins, records, background, final_Ts, final_idx, v_out,
+                v_out_alpha, v_xy, v_xy_abs, v_conic, v_colors, v_opacity);
+    } else {
+        dim3 grid(p.tiles_x, p.tiles_y), block(p.block_width, p.block_width);
+        raster_bwd_generic_kernel<<<grid, block, 0, stream>>>(
+            p, ids_sorted, tile_bins, records, background, final_Ts, final_idx, v_out, v_out_alpha,
+            v_xy, v_xy_abs, v_conic, v_colors, v_opacity);
+    }
+    JSB_CUDA_OK(cudaGetLastError());
+    note_launch();
+    return 0;
+}
+
+}  // namespace jsb

@@ -1,0 +1,243 @@
+// Tile rasteriser, forward, for sm_100a.
+//
+// Behavioural spec: reference lib/kernels/forward.cu:339-462 (rasterize_fwd): per 16x16-pixel
+// tile, walk the tile's depth-sorted Gaussians front to back; per pixel evaluate sigma, alpha,
+// skip if sigma<0 or alpha<1/255, stop the pixel when next_T <= 1e-4 (that Gaussian is NOT
+// composited), accumulate colour, record final T and the global sorted index of the last
+// composited Gaussian.  Every decision is evaluated in the reference's compiled rounding order
+// (common.cuh), so final_idx is bit-exact and the image is bit-identical.
+//
+// Design (not a port):
+//   * one CTA = one tile; its 8 warps own 8x4-pixel rectangles (not 16x2 rows) so a warp's
+//     footprint is compact;
+//   * batches of 256 Gaussians are staged once per CTA from the packed 48-byte SplatRecord table
+//     with 16-byte loads; the staging thread also computes a conservative 8-bit mask saying which
+//     warp rectangles the Gaussian can reach (raster_cull.cuh);
+//   * each warp turns the masks into a 256-bit register bitmap with 8 ballots and only visits
+//     its own candidates (find-first-set walk): pairs that cannot pass the alpha test are never
+//     evaluated, which is where most of the reference's issue slots go;
+//   * per candidate the warp does 1 LDS.128 + 1 LDS.64 (broadcast) instead of 6 scalar LDS, and
+//     colours come from shared memory instead of three dependent global loads;
+//   * warps retire independently (ballot on `done`), the CTA retires on __syncthreads_count.
+#include "common.cuh"
+#include "kernels.cuh"
+#include "raster_cull.cuh"
+
+namespace jsb {
+namespace {
+
+constexpr int RB = 256;  // batch size == threads per CTA
+
+template <bool CULL>
+__global__ void __launch_bounds__(RB)
+raster_fwd16_kernel(const RasterParams p, const unsigned *__restrict__ ids_sorted,
+                    const int2 *__restrict__ tile_bins, const SplatRecord *__restrict__ records,
+                    const float *__restrict__ background, float *__restrict__ final_Ts,
+                    int *__restrict__ final_idx, float *__restrict__ out_img) {
+    __shared__ float4 sA[RB];        // x, y, opac, conic.x
+    __shared__ float4 sB[RB];        // conic.y, conic.z, r, g
+    __shared__ float sC[RB];         // b
+    __shared__ unsigned char sMask[RB];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned tile = blockIdx.x;
+    const unsigned tile_y = tile / p.tiles_x, tile_x = tile - tile_y * p.tiles_x;
+    const unsigned j = tile_x * 16 + (warp & 1) * kRectW + (lane & 7);   // pixel column
+    const unsigned i = tile_y * 16 + (warp >> 1) * kRectH + (lane >> 3); // pixel row
+    const float px = (float)j + 0.5f, py = (float)i + 0.5f;
+    const bool inside = (i < p.img_h) && (j < p.img_w);
+    bool done = !inside;
+
+    const int2 range = tile_bins[tile];
+    const int num_batches = (range.y - range.x + RB - 1) / RB;
+    const float tile_x0 = (float)(tile_x * 16), tile_y0 = (float)(tile_y * 16);
+
+    float T = 1.f;
+    int cur_idx = 0;
+    float acc_r = 0.f, acc_g = 0.f, acc_b = 0.f;
+
+    for (int b = 0; b < num_batches; ++b) {
+        // also the barrier that protects the previous batch's shared data
+        if (__syncthreads_count(done) >= RB) break;
+        const int batch_start = range.x + RB * b;
+        const int idx = batch_start + tid;
+        unsigned mask = 0;
+        if (idx < range.y) {
+            const unsigned g = ids_sorted[idx];
+            const float4 q0 = __ldg(&records[g].q0);
+            const float4 q1 = __ldg(&records[g].q1);
+            const float4 q2 = __ldg(&records[g].q2);
+            sA[tid] = q0;
+            sB[tid] = q1;
+            sC[tid] = q2.x;
+            mask = CULL ? cull_mask16(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, tile_x0, tile_y0) : 0xFFu;
+        }
+        sMask[tid] = (unsigned char)mask;
+        __syncthreads();
+
+        bool warp_done = __all_sync(0xffffffffu, done);
+#pragma unroll
+        for (int k = 0; k < RB / 32; ++k) {
+            if (warp_done) continue;
+            const unsigned m = sMask[k * 32 + lane];
+            unsigned bits = __ballot_sync(0xffffffffu, (m >> warp) & 1u);
+            while (bits) {
+                const int t = k * 32 + __ffs(bits) - 1;
+                bits &= bits - 1;
+                const float4 a = sA[t];
+                const float2 cyz = *reinterpret_cast<const float2 *>(&sB[t]);
+                const float dx = fsub(a.x, px), dy = fsub(a.y, py);
+                const float sigma = conic_sigma(a.w, cyz.x, cyz.y, dx, dy);
+                const float vis_e = ex2_approx(fmul(sigma, kNegLog2e));
+                const float alpha = fminf(fmul(a.z, vis_e), 0.999f);
+                if (!done && !(sigma < 0.f) && !(alpha < kAlphaMin)) {
+                    const float next_T = fmul(T, fsub(1.f, alpha));
+                    if (next_T <= kTmin) {
+                        done = true;  // this Gaussian is not composited
+                    } else {
+                        const float vis = fmul(T, alpha);
+                        const float2 rg = *reinterpret_cast<const float2 *>(&sB[t].z);
+                        acc_r = ffma(vis, rg.x, acc_r);
+                        acc_g = ffma(vis, rg.y, acc_g);
+                        acc_b = ffma(vis, sC[t], acc_b);
+                        T = next_T;
+                        cur_idx = batch_start + t;
+                    }
+                }
+            }
+            warp_done = __all_sync(0xffffffffu, done);
+        }
+    }
+
+    if (inside) {
+        const size_t pix = (size_t)i * p.img_w + j;
+        final_Ts[pix] = T;
+        final_idx[pix] = cur_idx;
+        const float bg0 = __ldg(background), bg1 = __ldg(background + 1), bg2 = __ldg(background + 2);
+        out_img[pix * 3 + 0] = ffma(T, bg0, acc_r);
+        out_img[pix * 3 + 1] = ffma(T, bg1, acc_g);
+        out_img[pix * 3 + 2] = ffma(T, bg2, acc_b);
+    }
+}
+
+// Any block_width in [1,16]: one CTA of bw*bw threads per tile, thread (ty,tx) = pixel, same
+// staging, no culling.  Semantics only; block_size 16 is the tuned case.
+__global__ void raster_fwd_generic_kernel(const RasterParams p,
+                                          const unsigned *__restrict__ ids_sorted,
+                                          const int2 *__restrict__ tile_bins,
+                                          const SplatRecord *__restrict__ records,
+                                          const float *__restrict__ background,
+                                          float *__restrict__ final_Ts,
+                                          int *__restrict__ final_idx,
+                                          float *__restrict__ out_img) {
+    __shared__ float4 sA[RB];
+    __shared__ float4 sB[RB];
+    __shared__ float sC[RB];
+    const int bs = blockDim.x * blockDim.y;
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    const unsigned tile = blockIdx.y * p.tiles_x + blockIdx.x;
+    const unsigned i = blockIdx.y * blockDim.y + threadIdx.y;
+    const unsigned j = blockIdx.x * blockDim.x + threadIdx.x;
+    const float px = (float)j + 0.5f, py = (float)i + 0.5f;
+    const bool inside = (i < p.img_h) && (j < p.img_w);
+    bool done = !inside;
+    const int2 range = tile_bins[tile];
+    const int num_batches = (range.y - range.x + bs - 1) / bs;
+    float T = 1.f;
+    int cur_idx = 0;
+    float acc_r = 0.f, acc_g = 0.f, acc_b = 0.f;
+    for (int b = 0; b < num_batches; ++b) {
+        if (__syncthreads_count(done) >= bs) break;
+        const int batch_start = range.x + bs * b;
+        const int idx = batch_start + tid;
+        if (idx < range.y) {
+            const unsigned g = ids_sorted[idx];
+            sA[tid] = __ldg(&records[g].q0);
+            sB[tid] = __ldg(&records[g].q1);
+            sC[tid] = __ldg(&records[g].q2).x;
+        }
+        __syncthreads();
+        const int batch_size = min(bs, range.y - batch_start);
+        for (int t = 0; t < batch_size && !done; ++t) {
+            const float4 a = sA[t];
+            const float4 bq = sB[t];
+            const float dx = fsub(a.x, px), dy = fsub(a.y, py);
+            const float sigma = conic_sigma(a.w, bq.x, bq.y, dx, dy);
+            const float alpha = fminf(fmul(a.z, ex2_approx(fmul(sigma, kNegLog2e))), 0.999f);
+            if (sigma < 0.f || alpha < kAlphaMin) continue;
+            const float next_T = fmul(T, fsub(1.f, alpha));
+            if (next_T <= kTmin) { done = true; break; }
+            const float vis = fmul(T, alpha);
+            acc_r = ffma(vis, bq.z, acc_r);
+            acc_g = ffma(vis, bq.w, acc_g);
+            acc_b = ffma(vis, sC[t], acc_b);
+            T = next_T;
+            cur_idx = batch_start + t;
+        }
+    }
+    if (inside) {
+        const size_t pix = (size_t)i * p.img_w + j;
+        final_Ts[pix] = T;
+        final_idx[pix] = cur_idx;
+        out_img[pix * 3 + 0] = ffma(T, __ldg(background), acc_r);
+        out_img[pix * 3 + 1] = ffma(T, __ldg(background + 1), acc_g);
+        out_img[pix * 3 + 2] = ffma(T, __ldg(background + 2), acc_b);
+    }
+}
+
+__global__ void fill_background_kernel(const float *__restrict__ background, size_t pixels,
+                                       float *__restrict__ final_Ts, int *__restrict__ final_idx,
+                                       float *__restrict__ out_img) {
+    const float bg0 = __ldg(background), bg1 = __ldg(background + 1), bg2 = __ldg(background + 2);
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < pixels;
+         i += (size_t)gridDim.x * blockDim.x) {
+        final_Ts[i] = 0.f;
+        final_idx[i] = 0;
+        out_img[i * 3] = bg0;
+        out_img[i * 3 + 1] = bg1;
+        out_img[i * 3 + 2] = bg2;
+    }
+}
+
+}  // namespace
+
+bool g_disable_cull = false;  // test hook (capi: jsb200_set_option)
+
+int launch_raster_fwd(cudaStream_t stream, const RasterParams &p, const unsigned *ids_sorted,
+                      const int2 *tile_bins, const SplatRecord *records, const float *background,
+                      float *final_Ts, int *final_idx, float *out_img) {
+    const unsigned tiles = p.tiles_x * p.tiles_y;
+    if (tiles == 0) return 0;
+    if (p.block_width == 16) {
+        if (g_disable_cull)
+            raster_fwd16_kernel<false><<<tiles, RB, 0, stream>>>(p, ids_sorted, tile_bins, records,
+                                                                 background, final_Ts, final_idx,
+                                                                 out_img);
+        else
+            raster_fwd16_kernel<true><<<tiles, RB, 0, stream>>>(p, ids_sorted, tile_bins, records,
+                                                                background, final_Ts, final_idx,
+                                                                out_img);
+    } else {
+        dim3 grid(p.tiles_x, p.tiles_y), block(p.block_width, p.block_width);
+        raster_fwd_generic_kernel<<<grid, block, 0, stream>>>(p, ids_sorted, tile_bins, records,
+                                                              background, final_Ts, final_idx,
+                                                              out_img);
+    }
+    JSB_CUDA_OK(cudaGetLastError());
+    note_launch();
+    return 0;
+}
+
+int launch_fill_background(cudaStream_t stream, const RasterParams &p, const float *background,
+                           float *final_Ts, int *final_idx, float *out_img) {
+    const size_t pixels = (size_t)p.img_w * p.img_h;
+    if (pixels == 0) return 0;
+    const unsigned blocks = (unsigned)((pixels + 255) / 256 < 148 * 8 ? (pixels + 255) / 256 : 148 * 8);
+    fill_background_kernel<<<blocks, 256, 0, stream>>>(background, pixels, final_Ts, final_idx,
+                                                       out_img);
+    JSB_CUDA_OK(cudaGetLastError());
+    note_launch();
+    return 0;
+}
+
+}  // namespace jsb
