@@ -54,26 +54,26 @@ __device__ __forceinline__ ProjOut project_one(float mx, float my, float mz, flo
 
     // R(q), q = (w,x,y,z)   (helpers.h:140-153)
     const float w = q.x, x = q.y, y = q.z, z = q.w;
+    // ptxas contracts the reference's products into the sums below (read from its sm_100a SASS):
+    // the six off-diagonal terms are single FMAs, the diagonal ones keep one separate add.
+    const float yz = fmul(y, z), wz = fmul(w, z), wy = fmul(w, y);
     const float yy = fmul(y, y), zz = fmul(z, z);
-    float t0 = fadd(yy, zz);
+    float t0 = ffma(w, x, yz);
+    const float r12 = fadd(t0, t0);          // 2(wx + yz)
+    t0 = ffma(-w, x, yz);
+    const float r21 = fadd(t0, t0);          // 2(yz - wx)
+    t0 = ffma(x, y, wz);
+    const float r01 = fadd(t0, t0);          // 2(xy + wz)   column 0, row 1
+    t0 = ffma(x, z, -wy);
+    const float r02 = fadd(t0, t0);          // 2(xz - wy)
+    t0 = ffma(x, y, -wz);
+    const float r10 = fadd(t0, t0);          // 2(xy - wz)
+    t0 = ffma(x, z, wy);
+    const float r20 = fadd(t0, t0);          // 2(xz + wy)
+    t0 = fadd(yy, zz);
     const float r00 = fsub(1.f, fadd(t0, t0));
-    const float xy = fmul(x, y), wz = fmul(w, z);
-    t0 = fadd(xy, wz);
-    const float r01 = fadd(t0, t0);  // column 0, row 1
-    const float xz = fmul(x, z), wy = fmul(w, y);
-    t0 = fsub(xz, wy);
-    const float r02 = fadd(t0, t0);
-    t0 = fsub(xy, wz);
-    const float r10 = fadd(t0, t0);
     t0 = ffma(x, x, zz);
     const float r11 = fsub(1.f, fadd(t0, t0));
-    const float yz = fmul(y, z), wx = fmul(w, x);
-    t0 = fadd(wx, yz);
-    const float r12 = fadd(t0, t0);
-    t0 = fadd(wy, xz);
-    const float r20 = fadd(t0, t0);
-    t0 = fsub(yz, wx);
-    const float r21 = fadd(t0, t0);
     t0 = ffma(x, x, yy);
     const float r22 = fsub(1.f, fadd(t0, t0));
 
@@ -118,19 +118,19 @@ __device__ __forceinline__ ProjOut project_one(float mx, float my, float mz, flo
     const float c01 = ffma(T0z, u12, ffma(T0x, u10, fmul(T0y, u11)));
     const float c11 = ffma(T1z, u12, ffma(T1x, u10, fmul(T1y, u11)));
     const float c01sq = fmul(c01, c01);
-    const float det_orig = fsub(fmul(c00, c11), c01sq);
+    const float det_orig = ffma(c00, c11, -c01sq);  // contracted in the reference SASS
     const float A = fadd(c00, 0.3f), B = fadd(c11, 0.3f);
-    const float det = fsub(fmul(A, B), c01sq);
+    const float det = ffma(A, B, -c01sq);           // contracted
     const float comp_sq = fmaxf(fdiv(det_orig, det), 0.f);
     if (det == 0.f) return o;  // compute_cov2d_bounds failed: only cov3d was written
 
     // conic + 3-sigma radius   (helpers.h:34-57)
     const float inv = frcp(det);
     o.conic.x = fmul(B, inv);
-    o.conic.y = fmul(inv, -c01);
+    o.conic.y = fmul(c01, -inv);
     o.conic.z = fmul(A, inv);
     const float bb = fmul(fadd(A, B), 0.5f);
-    const float sq = fsqrt(fmaxf(fsub(fmul(bb, bb), det), 0.1f));
+    const float sq = fsqrt(fmaxf(ffma(bb, bb, -det), 0.1f));  // contracted
     const float lam = fmaxf(fadd(bb, sq), fsub(bb, sq));
     const float radius = ceilf(fmul(fsqrt(lam), 3.f));
 

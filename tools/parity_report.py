@@ -14,7 +14,9 @@ from jaxsplat_b200 import _ffi, _lib, _ops, synthetic  # noqa: E402
 from oracle import ref_cuda  # noqa: E402
 
 
-def run_pipeline(scene, table, target=None):
+def run_pipeline(scene, table, target=None, feed=None):
+    """feed: outputs of another implementation; when given, every op consumes THOSE as inputs
+    (op-level parity) instead of its own upstream results (end-to-end parity)."""
     n = scene.means3d.shape[0]
     kw = dict(num_points=n, img_shape=scene.img_shape, f=scene.f, c=scene.c,
               glob_scale=scene.glob_scale, clip_thresh=scene.clip_thresh,
@@ -24,23 +26,24 @@ def run_pipeline(scene, table, target=None):
     (out["cov3ds"], out["xys"], out["depths"], out["radii"], out["conics"], out["compensation"],
      out["num_tiles_hit"], out["cum_tiles_hit"]) = _ops.project_fwd(
         scene.means3d, scene.scales, scene.quats, scene.viewmat, table=table, **kw)
+    src = feed if feed is not None else out
     out["final_Ts"], out["final_idx"], out["img"] = _ops.rasterize_fwd(
-        scene.colors, scene.opacities, scene.background, out["xys"], out["depths"], out["radii"],
-        out["conics"], out["cum_tiles_hit"], table=table, **rkw)
+        scene.colors, scene.opacities, scene.background, src["xys"], src["depths"], src["radii"],
+        src["conics"], src["cum_tiles_hit"], table=table, **rkw)
     H, W = scene.img_shape
     if target is None:
         target = torch.zeros((H, W, 3), device=scene.means3d.device)
-    v_img = (2.0 / (H * W * 3)) * (out["img"] - target)
+    v_img = (2.0 / (H * W * 3)) * (src["img"] - target)
     v_alpha = torch.zeros((H, W, 1), device=v_img.device)
     (out["v_colors"], out["v_opacity"], out["v_xy"], out["v_xy_abs"], out["v_conic"]) = \
-        _ops.rasterize_bwd(scene.colors, scene.opacities, scene.background, out["xys"],
-                           out["depths"], out["radii"], out["conics"], out["cum_tiles_hit"],
-                           out["final_Ts"], out["final_idx"], v_img, v_alpha, table=table, **rkw)
+        _ops.rasterize_bwd(scene.colors, scene.opacities, scene.background, src["xys"],
+                           src["depths"], src["radii"], src["conics"], src["cum_tiles_hit"],
+                           src["final_Ts"], src["final_idx"], v_img, v_alpha, table=table, **rkw)
     zeros = torch.zeros((n, 1), device=v_img.device)
     (out["v_mean3d"], out["v_scale"], out["v_quat"], out["v_cov2d"], out["v_cov3d"]) = \
-        _ops.project_bwd(scene.means3d, scene.scales, scene.quats, scene.viewmat, out["cov3ds"],
-                         out["xys"], out["radii"], out["conics"], out["compensation"], zeros,
-                         out["v_xy"], zeros.clone(), out["v_conic"], table=table, **kw)
+        _ops.project_bwd(scene.means3d, scene.scales, scene.quats, scene.viewmat, src["cov3ds"],
+                         src["xys"], src["radii"], src["conics"], src["compensation"], zeros,
+                         src["v_xy"], zeros.clone(), src["v_conic"], table=table, **kw)
     return out
 
 
@@ -102,6 +105,11 @@ def main():
             ints = {"radii", "num_tiles_hit", "cum_tiles_hit", "final_idx"}
             for k in mine:
                 rows.append(compare(mine[k], theirs[k], k, k in ints))
+            oplevel = run_pipeline(scene, ours, target, feed=theirs)
+            torch.cuda.synchronize()
+            for k in oplevel:
+                r = compare(oplevel[k], theirs[k], "op:" + k, k in ints)
+                rows.append(r)
             # sorted ids + bins
             desc = ref.make_descriptor(entry["N"], scene.img_shape, (0, 0), (0, 0), 0.0, 0.0,
                                        scene.block_size)
