@@ -28,6 +28,8 @@ __device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
     return x;
 }
 
+// WRITE=false: fingerprint + intersection count only (rasterize_bwd validating the forward's cache)
+template <bool WRITE>
 __global__ void __launch_bounds__(BT)
 bin_prep_kernel(const BinParams p, const float2 *__restrict__ xys,
                 const float *__restrict__ depths, const int *__restrict__ radii,
@@ -58,11 +60,13 @@ bin_prep_kernel(const BinParams p, const float2 *__restrict__ xys,
             opac = __ldg(opacities + g);
             cx = s_conic[tid * 3]; cy = s_conic[tid * 3 + 1]; cz = s_conic[tid * 3 + 2];
             r = s_color[tid * 3]; gr = s_color[tid * 3 + 1]; b = s_color[tid * 3 + 2];
-            SplatRecord rec;
-            rec.q0 = make_float4(xy.x, xy.y, opac, cx);
-            rec.q1 = make_float4(cy, cz, r, gr);
-            rec.q2 = make_float4(b, 0.f, 0.f, 0.f);
-            records[g] = rec;
+            if (WRITE) {
+                SplatRecord rec;
+                rec.q0 = make_float4(xy.x, xy.y, opac, cx);
+                rec.q1 = make_float4(cy, cz, r, gr);
+                rec.q2 = make_float4(b, 0.f, 0.f, 0.f);
+                records[g] = rec;
+            }
         }
         unsigned key = 0xFFFFFFFFu;
         if (radius > 0) {
@@ -72,9 +76,11 @@ bin_prep_kernel(const BinParams p, const float2 *__restrict__ xys,
             cnt = (x1 - x0) * (y1 - y0);
             key = __float_as_uint(depth);
         }
-        depth_keys[g] = key;
-        ids[g] = (unsigned)g;
-        tile_counts[g] = cnt;
+        if (WRITE) {
+            depth_keys[g] = key;
+            ids[g] = (unsigned)g;
+            tile_counts[g] = cnt;
+        }
         // order-independent fingerprint of everything the cached binning depends on
         unsigned long long a = ((unsigned long long)__float_as_uint(xy.x) << 32) | __float_as_uint(xy.y);
         unsigned long long c = ((unsigned long long)__float_as_uint(depth) << 32) | (unsigned)radius;
@@ -237,11 +243,16 @@ int launch_bin_prep(cudaStream_t stream, const BinParams &p, const float *xys,
                     const float *depths, const int *radii, const float *conics,
                     const float *opacities, const float *colors, SplatRecord *records,
                     unsigned *depth_keys, unsigned *ids, unsigned *tile_counts,
-                    unsigned long long *fingerprint) {
+                    unsigned long long *fingerprint, bool write) {
     if (p.num_points == 0) return 0;
-    bin_prep_kernel<<<ceil_div(p.num_points, BT), BT, 0, stream>>>(
-        p, reinterpret_cast<const float2 *>(xys), depths, radii, conics, opacities, colors,
-        records, depth_keys, ids, tile_counts, fingerprint);
+    if (write)
+        bin_prep_kernel<true><<<ceil_div(p.num_points, BT), BT, 0, stream>>>(
+            p, reinterpret_cast<const float2 *>(xys), depths, radii, conics, opacities, colors,
+            records, depth_keys, ids, tile_counts, fingerprint);
+    else
+        bin_prep_kernel<false><<<ceil_div(p.num_points, BT), BT, 0, stream>>>(
+            p, reinterpret_cast<const float2 *>(xys), depths, radii, conics, opacities, colors,
+            records, depth_keys, ids, tile_counts, fingerprint);
     JSB_CUDA_OK(cudaGetLastError());
     note_launch();
     return 0;

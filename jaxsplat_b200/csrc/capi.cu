@@ -64,6 +64,7 @@ struct Ctx {
     unsigned long long *h_pinned = nullptr;  // [fingerprint][total][err...]
     // binning cache
     bool cache_valid = false;
+    bool cache_has_records = false;  // false after a sort_and_bin-only call (no appearance data)
     unsigned long long cache_fp = 0;
     unsigned cache_n = 0, cache_tiles = 0, cache_bw = 0, cache_tiles_x = 0;
     unsigned long long cache_I = 0;
@@ -147,7 +148,8 @@ constexpr size_t SMALL_BYTES = 64;
 // Runs prep (+fingerprint, +total) and returns after the single host sync with *I and *fp set.
 static int bin_prepare(Ctx &c, const Descriptor &d, const float *xys, const float *depths,
                        const int *radii, const float *conics, const float *opac,
-                       const float *colors, unsigned long long *I, unsigned long long *fp) {
+                       const float *colors, unsigned long long *I, unsigned long long *fp,
+                       bool write = true) {
     const unsigned n = d.num_points;
     cudaStream_t s = c.stream;
     if (!c.h_pinned) JSB_CUDA_OK(cudaHostAlloc((void **)&c.h_pinned, SMALL_BYTES, cudaHostAllocDefault));
@@ -170,7 +172,7 @@ static int bin_prepare(Ctx &c, const Descriptor &d, const float *xys, const floa
     unsigned long long *small64 = (unsigned long long *)c.small.p;
     if (launch_bin_prep(s, bp, xys, depths, radii, conics, opac, colors,
                         (SplatRecord *)c.records.p, (unsigned *)c.dkeys_a.p, (unsigned *)c.ids_a.p,
-                        (unsigned *)c.counts.p, small64))
+                        (unsigned *)c.counts.p, small64, write))
         return 1;
     JSB_CUDA_OK(cudaMemcpyAsync(c.h_pinned, c.small.p, 32, cudaMemcpyDeviceToHost, s));
     JSB_CUDA_OK(cudaStreamSynchronize(s));
@@ -239,6 +241,7 @@ static int bin_sort(Ctx &c, const Descriptor &d, const float *xys, const int *ra
     }
     const unsigned tiles = d.tiles_x * d.tiles_y;
     c.cache_valid = false;
+    c.cache_has_records = false;
     int rc = tiles <= 65536 ? bin_sort_t<uint16_t>(c, d, xys, radii, I)
                             : bin_sort_t<uint32_t>(c, d, xys, radii, I);
     if (rc) return rc;
@@ -256,7 +259,7 @@ static int bin_sort(Ctx &c, const Descriptor &d, const float *xys, const int *ra
 
 static bool cache_hit(const Ctx &c, const Descriptor &d, unsigned long long I,
                       unsigned long long fp) {
-    return !g_disable_cache && c.cache_valid && c.cache_fp == fp && c.cache_I == I &&
+    return !g_disable_cache && c.cache_valid && c.cache_has_records && c.cache_fp == fp && c.cache_I == I &&
            c.cache_n == d.num_points && c.cache_tiles == d.tiles_x * d.tiles_y &&
            c.cache_tiles_x == d.tiles_x && c.cache_bw == d.block_width;
 }
@@ -349,11 +352,10 @@ static int rasterize_fwd_impl(cudaStream_t stream, void **buf, const Descriptor 
         return launch_fill_background(stream, rp, (const float *)buf[2], (float *)buf[8],
                                       (int *)buf[9], (float *)buf[10]);
     }
-    if (cache_hit(*c, d, I, fp)) {
-        g_stats[3].fetch_add(1);
-    } else if (bin_sort(*c, d, (const float *)buf[3], (const int *)buf[5], I, fp)) {
-        return 1;
-    }
+    // the forward always bins afresh (a training loop changes the parameters every step); only
+    // the matching backward may reuse this result
+    if (bin_sort(*c, d, (const float *)buf[3], (const int *)buf[5], I, fp)) return 1;
+    c->cache_has_records = true;
     return launch_raster_fwd(stream, rp, c->cache_ids, (const int2 *)c->bins.p,
                              (const SplatRecord *)c->records.p, (const float *)buf[2],
                              (float *)buf[8], (int *)buf[9], (float *)buf[10]);
@@ -376,14 +378,21 @@ static int rasterize_bwd_impl(cudaStream_t stream, void **buf, const Descriptor 
     JSB_CUDA_OK(cudaMemsetAsync(buf[15], 0, n * 2 * 4, stream));
     JSB_CUDA_OK(cudaMemsetAsync(buf[16], 0, n * 3 * 4, stream));
     unsigned long long I = 0, fp = 0;
+    // fingerprint-only pass first: if it matches the forward's binning nothing else is rebuilt
     if (bin_prepare(*c, d, (const float *)buf[3], (const float *)buf[4], (const int *)buf[5],
-                    (const float *)buf[6], (const float *)buf[1], (const float *)buf[0], &I, &fp))
+                    (const float *)buf[6], (const float *)buf[1], (const float *)buf[0], &I, &fp,
+                    /*write=*/false))
         return 1;
     if (I == 0) return 0;
     if (cache_hit(*c, d, I, fp)) {
         g_stats[3].fetch_add(1);
-    } else if (bin_sort(*c, d, (const float *)buf[3], (const int *)buf[5], I, fp)) {
-        return 1;
+    } else {
+        if (bin_prepare(*c, d, (const float *)buf[3], (const float *)buf[4], (const int *)buf[5],
+                        (const float *)buf[6], (const float *)buf[1], (const float *)buf[0], &I,
+                        &fp, /*write=*/true))
+            return 1;
+        if (bin_sort(*c, d, (const float *)buf[3], (const int *)buf[5], I, fp)) return 1;
+        c->cache_has_records = true;
     }
     return launch_raster_bwd(stream, raster_params(d), c->cache_ids, (const int2 *)c->bins.p,
                              (const SplatRecord *)c->records.p, (const float *)buf[2],
@@ -483,7 +492,7 @@ int jsb200_sort_and_bin(jsb200_stream_t stream_, const char *opaque, size_t len,
             return 0;
         }
         if (jsb::bin_sort(*c, d, xys, radii, I, fp)) return 1;
-        c->cache_valid = false;  // records were not packed: never reuse for rasterisation
+        c->cache_has_records = false;  // records were not packed: never reuse for rasterisation
         JSB_CUDA_OK(cudaMemcpyAsync(gaussian_ids_sorted, c->cache_ids, (size_t)I * 4,
                                     cudaMemcpyDeviceToDevice, stream));
         JSB_CUDA_OK(cudaMemcpyAsync(tile_bins, c->bins.p, (size_t)tiles * 8,

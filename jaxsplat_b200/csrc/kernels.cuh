@@ -54,7 +54,7 @@ int launch_bin_prep(cudaStream_t stream, const BinParams &p, const float *xys,
                     const float *depths, const int *radii, const float *conics,
                     const float *opacities, const float *colors, SplatRecord *records,
                     unsigned *depth_keys, unsigned *ids, unsigned *tile_counts,
-                    unsigned long long *fingerprint);
+                    unsigned long long *fingerprint, bool write = true);
 
 // inclusive int32 prefix sum (chain: ceil(n/1024) u64 zeroed, ticket zeroed)
 int launch_inclusive_scan_i32(cudaStream_t stream, const int *in, int *out, unsigned n,
