@@ -86,7 +86,8 @@ JSB200_API unsigned long long jsb200_error_count(void);
 
 /* Test / measurement hooks (no reference equivalent). */
 /* key: "cull" (1 default; 0 disables the conservative warp-rectangle pre-filter),
- *      "cache" (1 default; 0 forces rasterize_bwd to re-bin instead of reusing the forward's) */
+ *      "cache" (1 default; 0 forces rasterize_bwd to re-bin instead of reusing the forward's),
+ *      "timing" (0 default; 1 brackets every stage with CUDA events, see jsb200_get_stage_times) */
 JSB200_API int jsb200_set_option(const char *key, int value);
 /* Copies the binning produced by the most recent rasterize/sort_and_bin call on `stream` into
  * caller device buffers (any may be NULL): ids_sorted[num_intersects] i32, tile_bins[tiles] int2,
@@ -94,6 +95,12 @@ JSB200_API int jsb200_set_option(const char *key, int value);
  * Returns num_intersects, or -1 on error. */
 JSB200_API long long jsb200_debug_binning(jsb200_stream_t stream, const float *depths, int *ids_sorted,
                                int *tile_bins, long long *keys64_sorted);
+/* Per-stage device time, measured with CUDA events on `stream` while option "timing" is 1.
+ * Synchronises the stream.  Stage order: project_fwd, bin_prep, depth_sort, emit, tile_sort,
+ * bin_edges, raster_fwd, raster_bwd, project_bwd.  ms_out9 / calls_out9 receive accumulated
+ * milliseconds and span counts; reset != 0 clears the accumulators.  Returns 0 on success. */
+JSB200_API int jsb200_get_stage_times(jsb200_stream_t stream, double *ms_out9,
+                                      unsigned long long *calls_out9, int reset);
 /* counters since load: [0] rasterize_fwd calls, [1] rasterize_bwd calls, [2] binning runs,
  * [3] binning cache hits, [4] last num_intersects, [5] workspace bytes, [6] kernel launches */
 JSB200_API void jsb200_get_stats(unsigned long long *out7);

@@ -26,6 +26,7 @@ EXPORTS = (
     "jsb200_error_count",
     "jsb200_set_option",
     "jsb200_debug_binning",
+    "jsb200_get_stage_times",
     "jsb200_get_stats",
     "jsb200_release",
 )
@@ -70,6 +71,9 @@ def lib() -> ctypes.CDLL:
     L.jsb200_set_option.restype = i
     L.jsb200_debug_binning.argtypes = [vp, vp, vp, vp, vp]
     L.jsb200_debug_binning.restype = ctypes.c_longlong
+    L.jsb200_get_stage_times.argtypes = [vp, ctypes.POINTER(ctypes.c_double),
+                                         ctypes.POINTER(ctypes.c_ulonglong), i]
+    L.jsb200_get_stage_times.restype = i
     L.jsb200_get_stats.argtypes = [ctypes.POINTER(ctypes.c_ulonglong)]
     L.jsb200_get_stats.restype = None
     L.jsb200_release.argtypes = []
@@ -99,3 +103,16 @@ def stats() -> dict:
 def set_option(key: str, value: int) -> None:
     if lib().jsb200_set_option(key.encode(), int(value)) != 0:
         check_error("set_option")
+
+
+STAGES = ("project_fwd", "bin_prep", "depth_sort", "emit", "tile_sort", "bin_edges", "raster_fwd",
+          "raster_bwd", "project_bwd")
+
+
+def stage_times(stream: int, reset: bool = True) -> dict:
+    """accumulated per-stage device milliseconds / span counts (option "timing" must be on)"""
+    ms = (ctypes.c_double * 9)()
+    calls = (ctypes.c_ulonglong * 9)()
+    if lib().jsb200_get_stage_times(ctypes.c_void_p(stream), ms, calls, int(reset)) != 0:
+        check_error("get_stage_times")
+    return {k: dict(ms=float(ms[i]), calls=int(calls[i])) for i, k in enumerate(STAGES)}

@@ -17,6 +17,7 @@
 #include <memory>
 #include <mutex>
 #include <string>
+#include <vector>
 
 #include "../../include/jaxsplat_b200.h"
 #include "common.cuh"
@@ -46,6 +47,33 @@ void note_launch(int n) { g_stats[6].fetch_add((unsigned long long)n); }
 extern bool g_disable_cull;
 static bool g_disable_cache = false;
 
+// ---- optional per-stage device timing (jsb200_set_option("timing", 1)) -------------------------
+enum Stage { ST_PROJECT_FWD, ST_BIN_PREP, ST_DEPTH_SORT, ST_EMIT, ST_TILE_SORT, ST_BIN_EDGES,
+             ST_RASTER_FWD, ST_RASTER_BWD, ST_PROJECT_BWD, ST_COUNT };
+static bool g_timing = false;
+struct StageTimes {
+    std::vector<cudaEvent_t> pool;
+    struct Span { int stage; cudaEvent_t a, b; };
+    std::vector<Span> pending;
+    double ms[ST_COUNT] = {0};
+    unsigned long long calls[ST_COUNT] = {0};
+    cudaEvent_t get() {
+        if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+        cudaEvent_t e = nullptr;
+        cudaEventCreate(&e);
+        return e;
+    }
+    void drain() {  // caller has synchronised the stream
+        for (auto &sp : pending) {
+            float t = 0.f;
+            if (cudaEventElapsedTime(&t, sp.a, sp.b) == cudaSuccess) { ms[sp.stage] += t; calls[sp.stage]++; }
+            pool.push_back(sp.a);
+            pool.push_back(sp.b);
+        }
+        pending.clear();
+    }
+};
+
 // ---- workspace --------------------------------------------------------------------------------
 struct DevBuf {
     void *p = nullptr;
@@ -70,6 +98,7 @@ struct Ctx {
     unsigned long long cache_I = 0;
     unsigned *cache_ids = nullptr;  // points into tvals_a or tvals_b
     size_t total_bytes = 0;
+    StageTimes times;
 
     int ensure(DevBuf &b, size_t bytes) {
         if (bytes <= b.cap) return 0;
@@ -101,6 +130,23 @@ struct Ctx {
         h_pinned = nullptr;
         cache_valid = false;
         total_bytes = 0;
+    }
+};
+
+// records a (begin,end) event pair around a stage when timing is on; otherwise free
+struct StageScope {
+    Ctx *c;
+    int stage;
+    cudaEvent_t a = nullptr;
+    StageScope(Ctx *c_, int st) : c(g_timing ? c_ : nullptr), stage(st) {
+        if (c) { a = c->times.get(); cudaEventRecord(a, c->stream); }
+    }
+    ~StageScope() {
+        if (c) {
+            cudaEvent_t b = c->times.get();
+            cudaEventRecord(b, c->stream);
+            c->times.pending.push_back({stage, a, b});
+        }
     }
 };
 
@@ -170,10 +216,13 @@ static int bin_prepare(Ctx &c, const Descriptor &d, const float *xys, const floa
     JSB_CUDA_OK(cudaMemsetAsync((char *)c.small.p + 32, 0, 32, s));
     BinParams bp{n, (float)(int)d.block_width, d.tiles_x, d.tiles_y};
     unsigned long long *small64 = (unsigned long long *)c.small.p;
+    {
+    StageScope ss(&c, ST_BIN_PREP);
     if (launch_bin_prep(s, bp, xys, depths, radii, conics, opac, colors,
                         (SplatRecord *)c.records.p, (unsigned *)c.dkeys_a.p, (unsigned *)c.ids_a.p,
                         (unsigned *)c.counts.p, small64, write))
         return 1;
+    }
     JSB_CUDA_OK(cudaMemcpyAsync(c.h_pinned, c.small.p, 32, cudaMemcpyDeviceToHost, s));
     JSB_CUDA_OK(cudaStreamSynchronize(s));
     *fp = c.h_pinned[SM_FP];
@@ -199,10 +248,13 @@ static int bin_sort_t(Ctx &c, const Descriptor &d, const float *xys, const int *
     // 1. depth order of the Gaussians (N-scale, 32-bit keys)
     if (c.ensure(c.sort_n_scratch, radix_scratch_bytes(n, 32))) return 1;
     bool in_b = false;
+    {
+    StageScope ss(&c, ST_DEPTH_SORT);
     if (radix_sort_pairs<uint32_t>(s, (uint32_t *)c.dkeys_a.p, (uint32_t *)c.dkeys_b.p,
                                    (unsigned *)c.ids_a.p, (unsigned *)c.ids_b.p, n, 32,
                                    c.sort_n_scratch.p, err, &in_b))
         return 1;
+    }
     const unsigned *order = (const unsigned *)(in_b ? c.ids_b.p : c.ids_a.p);
     // 2. emit (tile, id) pairs in depth order
     if (c.ensure(c.tkeys_a, (size_t)I * sizeof(TileKey)) || c.ensure(c.tkeys_b, (size_t)I * sizeof(TileKey)))
@@ -210,21 +262,28 @@ static int bin_sort_t(Ctx &c, const Descriptor &d, const float *xys, const int *
     if (c.ensure(c.tvals_a, (size_t)I * 4) || c.ensure(c.tvals_b, (size_t)I * 4)) return 1;
     const size_t chain_bytes = (size_t)ceil_div(n, 256) * 8;
     if (c.ensure(c.chain, chain_bytes)) return 1;
-    JSB_CUDA_OK(cudaMemsetAsync(c.chain.p, 0, chain_bytes, s));
     BinParams bp{n, (float)(int)d.block_width, d.tiles_x, d.tiles_y};
+    {
+    StageScope ss(&c, ST_EMIT);
+    JSB_CUDA_OK(cudaMemsetAsync(c.chain.p, 0, chain_bytes, s));
     if (launch_emit<TileKey>(s, bp, order, (const unsigned *)c.counts.p, xys, radii,
                              (TileKey *)c.tkeys_a.p, (unsigned *)c.tvals_a.p,
                              (unsigned long long *)c.chain.p, tickets, err))
         return 1;
+    }
     // 3. stable sort on the live tile bits
     const int bits = tile_bits(tiles);
     if (c.ensure(c.sort_i_scratch, radix_scratch_bytes((unsigned)I, bits))) return 1;
+    {
+    StageScope ss(&c, ST_TILE_SORT);
     if (radix_sort_pairs<TileKey>(s, (TileKey *)c.tkeys_a.p, (TileKey *)c.tkeys_b.p,
                                   (unsigned *)c.tvals_a.p, (unsigned *)c.tvals_b.p, (unsigned)I,
                                   bits, c.sort_i_scratch.p, err, &in_b))
         return 1;
+    }
     // 4. tile bins
     if (c.ensure(c.bins, (size_t)tiles * sizeof(int2))) return 1;
+    StageScope ss(&c, ST_BIN_EDGES);
     JSB_CUDA_OK(cudaMemsetAsync(c.bins.p, 0, (size_t)tiles * sizeof(int2), s));
     if (launch_bin_edges<TileKey>(s, (const TileKey *)(in_b ? c.tkeys_b.p : c.tkeys_a.p),
                                   (unsigned)I, (int2 *)c.bins.p))
@@ -291,6 +350,7 @@ static int project_fwd_impl(cudaStream_t stream, void **buf, const Descriptor &d
         JSB_CUDA_OK(cudaMemsetAsync(c->small.p, 0, SMALL_BYTES, stream));
     }
     int *err = (int *)c->small.p + SM_ERR_WORD + 3;
+    StageScope ss(c, ST_PROJECT_FWD);
     return launch_project_fwd(stream, p, (const float *)buf[0], (const float *)buf[1],
                               (const float *)buf[2], (const float *)buf[3], (float *)buf[4],
                               (float *)buf[5], (float *)buf[6], (int *)buf[7], (float *)buf[8],
@@ -299,6 +359,10 @@ static int project_fwd_impl(cudaStream_t stream, void **buf, const Descriptor &d
 
 static int project_bwd_impl(cudaStream_t stream, void **buf, const Descriptor &d) {
     if (d.num_points == 0) return 0;
+    Ctx *c = get_ctx(stream);
+    if (!c) return 1;
+    std::lock_guard<std::mutex> lk(c->mu);
+    StageScope ss(c, ST_PROJECT_BWD);
     ProjectBwdParams p{d.num_points, d.glob_scale, d.fx, d.fy};
     // in: 0 mean3ds 1 scales 2 quats 3 viewmat 4 cov3ds 5 xys 6 radii 7 conics 8 compensation
     //     9 v_compensation 10 v_xy 11 v_depth 12 v_conic ; out: 13 v_mean3d 14 v_scale 15 v_quat
@@ -356,6 +420,7 @@ static int rasterize_fwd_impl(cudaStream_t stream, void **buf, const Descriptor 
     // the matching backward may reuse this result
     if (bin_sort(*c, d, (const float *)buf[3], (const int *)buf[5], I, fp)) return 1;
     c->cache_has_records = true;
+    StageScope ss(c, ST_RASTER_FWD);
     return launch_raster_fwd(stream, rp, c->cache_ids, (const int2 *)c->bins.p,
                              (const SplatRecord *)c->records.p, (const float *)buf[2],
                              (float *)buf[8], (int *)buf[9], (float *)buf[10]);
@@ -394,6 +459,7 @@ static int rasterize_bwd_impl(cudaStream_t stream, void **buf, const Descriptor 
         if (bin_sort(*c, d, (const float *)buf[3], (const int *)buf[5], I, fp)) return 1;
         c->cache_has_records = true;
     }
+    StageScope ss(c, ST_RASTER_BWD);
     return launch_raster_bwd(stream, raster_params(d), c->cache_ids, (const int2 *)c->bins.p,
                              (const SplatRecord *)c->records.p, (const float *)buf[2],
                              (const float *)buf[8], (const int *)buf[9], (const float *)buf[10],
@@ -532,6 +598,7 @@ int jsb200_set_option(const char *key, int value) {
     if (!key) return 1;
     if (!strcmp(key, "cull")) { jsb::g_disable_cull = (value == 0); return 0; }
     if (!strcmp(key, "cache")) { jsb::g_disable_cache = (value == 0); return 0; }
+    if (!strcmp(key, "timing")) { jsb::g_timing = (value != 0); return 0; }
     jsb::set_error("set_option: unknown key '%s'", key);
     return 1;
 }
@@ -554,6 +621,27 @@ long long jsb200_debug_binning(jsb200_stream_t stream_, const float *depths, int
         return (long long)I;
     } catch (...) {
         return -1;
+    }
+}
+
+int jsb200_get_stage_times(jsb200_stream_t stream_, double *ms_out9, unsigned long long *calls_out9,
+                           int reset) {
+    try {
+        cudaStream_t stream = (cudaStream_t)stream_;
+        jsb::Ctx *c = jsb::get_ctx(stream);
+        if (!c) return 1;
+        std::lock_guard<std::mutex> lk(c->mu);
+        JSB_CUDA_OK(cudaStreamSynchronize(stream));
+        c->times.drain();
+        for (int i = 0; i < jsb::ST_COUNT; ++i) {
+            if (ms_out9) ms_out9[i] = c->times.ms[i];
+            if (calls_out9) calls_out9[i] = c->times.calls[i];
+            if (reset) { c->times.ms[i] = 0; c->times.calls[i] = 0; }
+        }
+        return 0;
+    } catch (...) {
+        jsb::set_error("get_stage_times: exception");
+        return 1;
     }
 }
 

@@ -1,0 +1,123 @@
+"""CPU: the C-ABI library loads, exports every symbol include/jaxsplat_b200.h declares, and the
+host-side logic (descriptor layout, registrations, argument validation, synthetic scenes) works
+without a GPU.  No compute entry point is called here."""
+import ctypes
+import os
+import re
+import struct
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, load_golden
+from jaxsplat_b200 import _ffi, _lib, _ops, synthetic
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "jaxsplat_b200.h")).read()
+    return sorted(set(re.findall(r"\b(jsb200_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = _lib.lib()
+    declared = _declared_symbols()
+    assert len(declared) >= 14
+    for name in declared:
+        assert hasattr(L, name), name
+    assert sorted(_lib.EXPORTS) == declared
+
+
+def test_descriptor_layout_matches_reference_bytes():
+    """the reference's own make_descriptor output (stored in the golden fixtures) equals ours
+    except for its 4 uninitialised pad bytes, which we zero"""
+    for name in ("g_small16", "g_small8", "g_inside16"):
+        g = load_golden(name)
+        n = g["in_means3d"].shape[0]
+        ours = _ffi.make_descriptor(n, g["kw"]["img_shape"], g["kw"]["f"], g["kw"]["c"],
+                                    g["kw"]["glob_scale"], g["kw"]["clip_thresh"],
+                                    g["kw"]["block_width"])
+        ref = g["descriptor"].tobytes()
+        assert len(ours) == 80 and len(ref) == 80
+        assert ours[:76] == ref[:76]
+        assert ours[76:] == b"\0\0\0\0"
+
+
+def test_descriptor_fields():
+    d = _ffi.make_descriptor(1000, (1080, 1920), (960.0, 540.0), (959.5, 539.5), 1.5, 0.01, 16)
+    (n, w, h, one, fx, fy, cx, cy, gs, clip, bw, g1, b1, tx, ty, tz, bx, by, bz,
+     pad) = struct.unpack("<4I4f2f3I3I3II", d)
+    assert (n, w, h, one) == (1000, 1920, 1080, 1)
+    assert (fx, fy, cx, cy) == (960.0, 540.0, 959.5, 539.5)
+    assert gs == 1.5 and abs(clip - 0.01) < 1e-9
+    assert (bw, g1, b1) == (16, 4, 256)
+    assert (tx, ty, tz) == (120, 68, 1) and (bx, by, bz) == (16, 16, 1) and pad == 0
+
+
+def test_registrations_are_xla_capsules():
+    regs = _ffi.registrations()
+    assert sorted(regs) == ["project_bwd", "project_fwd", "rasterize_bwd", "rasterize_fwd"]
+    L = _lib.lib()
+    for name, cap in regs.items():
+        ptr = _ffi.capsule_pointer(cap)  # raises if the capsule name is not xla._CUSTOM_CALL_TARGET
+        assert ptr == ctypes.cast(getattr(L, "jsb200_" + name), ctypes.c_void_p).value
+
+
+def test_bad_opaque_is_an_error_not_a_crash():
+    L = _lib.lib()
+    L.jsb200_clear_error()
+    before = L.jsb200_error_count()
+    bufs = (ctypes.c_void_p * 1)(None)
+    L.jsb200_project_fwd(None, bufs, b"x" * 10, 10)  # wrong descriptor size (reference: throws)
+    assert L.jsb200_error_count() == before + 1
+    assert b"descriptor" in L.jsb200_last_error()
+    with pytest.raises(RuntimeError):
+        _lib.check_error("project_fwd")
+    assert L.jsb200_last_error() is None
+
+
+def test_unknown_option_rejected():
+    with pytest.raises(RuntimeError):
+        _lib.set_option("no_such_option", 1)
+
+
+def test_ops_validate_shapes_before_touching_the_gpu():
+    n = 8
+    z = torch.zeros
+    with pytest.raises(TypeError):
+        _ops.project_fwd(z(n, 3), z(n, 3), z(n, 3), z(4, 4), num_points=n, img_shape=(32, 32),
+                         f=(16, 16), c=(16, 16), glob_scale=1.0, clip_thresh=0.01, block_width=16)
+    with pytest.raises(TypeError):
+        _ops.rasterize_fwd(z(n, 3), z(n, 1), z(3), z(n, 2), z(n, 1), z(n, 1), z(n, 3),
+                           z(n, 1, dtype=torch.int32), num_points=n, img_shape=(32, 32),
+                           block_width=16)  # radii must be int32
+    with pytest.raises(ValueError):  # CPU tensors are refused: there is no CPU path
+        _ops.project_fwd(z(n, 3), z(n, 3), z(n, 4), z(4, 4), num_points=n, img_shape=(32, 32),
+                         f=(16, 16), c=(16, 16), glob_scale=1.0, clip_thresh=0.01, block_width=16)
+
+
+def test_synthetic_scenes_are_deterministic():
+    a = synthetic.make_config("C1")
+    b = synthetic.make_config("C1")
+    assert torch.equal(a.means3d, b.means3d) and torch.equal(a.quats, b.quats)
+    assert a.means3d.shape == (10_000, 3) and a.img_shape == (256, 256)
+    c2 = synthetic.make_config("C2", num_points=1000)
+    assert c2.means3d.shape == (1000, 3) and c2.img_shape == (512, 512)
+    assert torch.allclose(c2.quats.norm(dim=1), torch.ones(1000), atol=1e-6)
+    cams = synthetic.ring_cameras(4)
+    for v in cams:
+        R = v[:3, :3].double()
+        assert torch.allclose(R @ R.T, torch.eye(3, dtype=torch.float64), atol=1e-6)
+        # the origin is in front of the camera at distance ~8
+        assert 7.5 < float(v[2, 3]) < 8.6
+
+
+def test_product_never_imports_the_oracle():
+    """the oracle is test infrastructure: nothing under jaxsplat_b200/ may reference it"""
+    pkg = os.path.join(ROOT, "jaxsplat_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text, f
+                assert "liboracle" not in text and "oracle/" not in text, f

@@ -1,0 +1,153 @@
+"""GPU: the public API (render/project/rasterize + autograd), size-independent properties at the
+BASELINE.json full sizes, and parity with the live reference CUDA library when it is present
+(oracle/_ref travels to the GPU box; it does not exist in a fresh checkout)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import grad_close
+import gpu_util as G
+import jaxsplat_b200 as jsb
+from jaxsplat_b200 import _ffi, synthetic
+from oracle import ref_cuda
+
+pytestmark = pytest.mark.gpu
+
+
+def _render_loss_and_grads(scene, target):
+    sc = scene.to(G.DEV)
+    params = [p.clone().requires_grad_(True) for p in sc.params()]
+    img = jsb.render(*params, **sc.render_kwargs())
+    loss = ((img - target) ** 2).mean()
+    loss.backward()
+    return img.detach(), float(loss), [p.grad for p in params]
+
+
+def test_render_autograd_matches_manual_op_chain():
+    s = synthetic.make_config("C1")
+    H, W = s.img_shape
+    target = torch.rand((H, W, 3), generator=torch.Generator().manual_seed(0)).to(G.DEV)
+    img, loss, grads = _render_loss_and_grads(s, target)
+    inp = G.scene_inputs(s)
+    kw, rkw = G.scene_kw(s)
+    P = G.project_fwd(inp, kw)
+    R = G.rasterize_fwd(inp, P, rkw)
+    assert torch.equal(R["img"], img)
+    v_img = (2.0 / (H * W * 3)) * (R["img"] - target)
+    B = G.rasterize_bwd(inp, P, R, v_img.contiguous(), torch.zeros((H, W, 1), device=G.DEV), rkw)
+    z = torch.zeros((10000, 1), device=G.DEV)
+    Gd = G.project_bwd(inp, P, z, B["v_xy"], z.clone(), B["v_conic"], kw)
+    manual = [Gd["v_mean3d"], Gd["v_scale"], Gd["v_quat"], B["v_colors"], B["v_opacity"]]
+    for a, b in zip(grads, manual):
+        ok, err, scale = grad_close(G.npy(a), G.npy(b), rel=2e-5)
+        assert ok, (err, scale)
+
+
+def test_directional_derivative():
+    """<grad, d> vs central finite difference of the rendered loss (float32 kernels: 3% tol)"""
+    s = synthetic.benchmark_scene(400, (64, 64), scale_max=0.5, seed=9)
+    target = torch.rand((64, 64, 3), generator=torch.Generator().manual_seed(1)).to(G.DEV)
+    _, _, grads = _render_loss_and_grads(s, target)
+    sc = s.to(G.DEV)
+    gen = torch.Generator().manual_seed(2)
+    for which in (0, 1, 3, 4):  # means, scales, colors, opacities (quats need renormalisation)
+        d = torch.randn(sc.params()[which].shape, generator=gen).to(G.DEV)
+        eps = 1e-3
+        vals = []
+        for sgn in (+1, -1):
+            ps = [p.clone() for p in sc.params()]
+            ps[which] = ps[which] + sgn * eps * d
+            img = jsb.render(*ps, **sc.render_kwargs())
+            vals.append(float(((img.double() - target.double()) ** 2).mean()))
+        fd = (vals[0] - vals[1]) / (2 * eps)
+        an = float((grads[which].double() * d.double()).sum())
+        assert abs(fd - an) <= 3e-2 * max(abs(fd), abs(an)) + 1e-7, (which, fd, an)
+
+
+def test_project_and_rasterize_public_signatures():
+    s = synthetic.make_config("C1").to(G.DEV)
+    xys, depths, radii, conics, nth, cth = jsb.project(
+        s.means3d, s.scales, s.quats, s.viewmat, img_shape=s.img_shape, f=s.f, c=s.c,
+        glob_scale=1.0, clip_thresh=0.01, block_width=16)
+    assert xys.shape == (10000, 2) and depths.shape == (10000, 1) and radii.dtype == torch.int32
+    assert conics.shape == (10000, 3) and nth.shape == (10000, 1) and cth.shape == (10000, 1)
+    img = jsb.rasterize(s.colors, s.opacities, s.background, xys, depths, radii, conics, cth,
+                        img_shape=s.img_shape, block_width=16)
+    assert img.shape == (256, 256, 3) and img.dtype == torch.float32
+    assert torch.equal(img, jsb.render(*s.params(), **s.render_kwargs()))
+
+
+@pytest.mark.parametrize("cfg", ["C3"])
+def test_full_size_properties(cfg):
+    """BASELINE.json full size: properties that need no oracle run"""
+    s = synthetic.make_config(cfg)
+    inp = G.scene_inputs(s)
+    kw, rkw = G.scene_kw(s)
+    H, W = s.img_shape
+    P = G.project_fwd(inp, kw)
+    nth, cth = P["num_tiles_hit"].long().view(-1), P["cum_tiles_hit"].long().view(-1)
+    assert torch.equal(torch.cumsum(nth, 0), cth)                    # scan == checksum of counts
+    assert bool(((P["radii"].view(-1) > 0) == (nth > 0)).all())
+    I = int(cth[-1])
+    R = G.rasterize_fwd(inp, P, rkw)
+    R2 = G.rasterize_fwd(inp, P, rkw)
+    assert torch.equal(R["img"], R2["img"]) and torch.equal(R["final_idx"], R2["final_idx"])  # deterministic
+    tiles = ((W + 15) // 16) * ((H + 15) // 16)
+    got, ids, bins, keys = G.debug_binning(I, tiles, depths=P["depths"])
+    assert got == I
+    assert bool((keys[1:] >= keys[:-1]).all())                        # sortedness
+    cnt = (bins[:, 1] - bins[:, 0]).long()
+    assert int(cnt.sum()) == I and bool((cnt >= 0).all())             # bins partition [0, I)
+    assert torch.equal(torch.bincount(ids.long(), minlength=nth.numel()), nth)  # every pair once
+    tile_of_key = (keys >> 32)
+    nz = cnt > 0
+    assert torch.equal(torch.bincount(tile_of_key, minlength=tiles)[nz], cnt[nz])
+    fi = R["final_idx"].view(-1).long()
+    assert int(fi.max()) < I and int(fi.min()) >= 0
+    assert float(R["final_Ts"].min()) > 0 and float(R["final_Ts"].max()) <= 1
+    # backward is linear in the cotangent
+    v = torch.rand((H, W, 3), generator=torch.Generator().manual_seed(4)).to(G.DEV) * 1e-6
+    va = torch.zeros((H, W, 1), device=G.DEV)
+    B1 = G.rasterize_bwd(inp, P, R, v, va, rkw)
+    B2 = G.rasterize_bwd(inp, P, R, 2 * v, va, rkw)
+    for k in ("v_colors", "v_opacity", "v_xy", "v_conic"):
+        ok, err, scale = grad_close(G.npy(B2[k]), 2 * G.npy(B1[k]), rel=2e-5)
+        assert ok, (k, err, scale)
+
+
+@pytest.mark.skipif(not ref_cuda.available(), reason="oracle/_ref (reference CUDA build) not present")
+@pytest.mark.parametrize("cfg", ["C2", "C3"])
+def test_live_reference_parity(cfg):
+    s = synthetic.make_config(cfg)
+    inp = G.scene_inputs(s)
+    kw, rkw = G.scene_kw(s)
+    H, W = s.img_shape
+    ref = ref_cuda.table()
+    Pr, Po = G.project_fwd(inp, kw, table=ref), G.project_fwd(inp, kw)
+    for k in Pr:
+        if Pr[k].dtype == torch.int32:
+            assert torch.equal(Pr[k], Po[k]), k
+        else:
+            assert G.bits_equal(G.npy(Pr[k]), G.npy(Po[k])) == 0, k
+    Rr, Ro = G.rasterize_fwd(inp, Pr, rkw, table=ref), G.rasterize_fwd(inp, Pr, rkw)
+    assert torch.equal(Rr["final_idx"], Ro["final_idx"])
+    assert float((Rr["img"] - Ro["img"]).abs().max()) <= 1e-5
+    assert G.bits_equal(G.npy(Rr["img"]), G.npy(Ro["img"])) == 0
+    I = int(Pr["cum_tiles_hit"][-1])
+    desc = ref.make_descriptor(s.means3d.shape[0], s.img_shape, (0, 0), (0, 0), 0.0, 0.0, 16)
+    rid, rbins = ref_cuda.sort_and_bin(desc, I, Pr["xys"], Pr["depths"], Pr["radii"], Pr["cum_tiles_hit"])
+    got, ids, bins, _ = G.debug_binning(I, rbins.shape[0])
+    assert got == I and torch.equal(ids, rid) and torch.equal(bins, rbins)
+    target = torch.rand((H, W, 3), generator=torch.Generator().manual_seed(3)).to(G.DEV)
+    v_img = ((2.0 / (H * W * 3)) * (Rr["img"] - target)).contiguous()
+    va = torch.zeros((H, W, 1), device=G.DEV)
+    Br, Bo = G.rasterize_bwd(inp, Pr, Rr, v_img, va, rkw, table=ref), G.rasterize_bwd(inp, Pr, Rr, v_img, va, rkw)
+    for k in Br:
+        ok, err, scale = grad_close(G.npy(Bo[k]), G.npy(Br[k]), rel=1e-4)
+        assert ok, (k, err, scale)
+    z = torch.zeros((s.means3d.shape[0], 1), device=G.DEV)
+    Gr = G.project_bwd(inp, Pr, z, Br["v_xy"], z.clone(), Br["v_conic"], kw, table=ref)
+    Go = G.project_bwd(inp, Pr, z, Br["v_xy"], z.clone(), Br["v_conic"], kw)
+    for k in Gr:
+        ok, err, scale = grad_close(G.npy(Go[k]), G.npy(Gr[k]), rel=1e-4)
+        assert ok, (k, err, scale)

@@ -1,0 +1,245 @@
+"""GPU: CUDA path vs the CPU oracle on seeded scenes the oracle finishes in seconds, plus the
+edge cases the domain has (empty frames, ragged sizes, culled Gaussians, every block size) and
+the library's own invariants (culling and caching never change a result)."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import grad_close
+import gpu_util as G
+from jaxsplat_b200 import _lib, _ops, synthetic
+from oracle import cpu
+
+pytestmark = pytest.mark.gpu
+
+
+def _full_gpu(inp, kw, rkw, target, v_alpha=None):
+    P = G.project_fwd(inp, kw)
+    R = G.rasterize_fwd(inp, P, rkw)
+    H, W = rkw["img_shape"]
+    v_img = ((2.0 / (H * W * 3)) * (R["img"] - G.t(target))).contiguous()
+    va = torch.zeros((H, W, 1), device=G.DEV) if v_alpha is None else G.t(v_alpha)
+    B = G.rasterize_bwd(inp, P, R, v_img, va, rkw)
+    n = inp["means3d"].shape[0]
+    z = torch.zeros((n, 1), device=G.DEV)
+    Gd = G.project_bwd(inp, P, z, B["v_xy"], z.clone(), B["v_conic"], kw)
+    out = {}
+    for d in (P, R, B, Gd):
+        out.update({k: G.npy(v) for k, v in d.items()})
+    out["v_img"] = G.npy(v_img)
+    return out
+
+
+def _check_vs_oracle(scene, seed=5):
+    inp = G.scene_inputs(scene)
+    kw, rkw = G.scene_kw(scene)
+    H, W = scene.img_shape
+    target = np.random.RandomState(seed).rand(H, W, 3).astype(np.float32)
+    gpu = _full_gpu(inp, kw, rkw, target)
+    # --- projection: bit-exact
+    P = cpu.project_fwd(inp["means3d"], inp["scales"], inp["quats"], inp["viewmat"], **kw)
+    for k in ("radii", "num_tiles_hit", "cum_tiles_hit"):
+        assert np.array_equal(P[k], gpu[k]), k
+    for k in ("cov3ds", "xys", "depths", "conics", "compensation"):
+        assert G.bits_equal(P[k], gpu[k]) == 0, k
+    # --- binning: bit-exact
+    b = cpu.sort_and_bin(P["xys"], P["depths"], P["radii"], P["cum_tiles_hit"], **rkw)
+    I = b["num_intersects"]
+    if I:
+        # the last rasterize call on the stream was the backward: same cached binning
+        got, ids, bins, keys = G.debug_binning(I, b["tile_bins"].shape[0], depths=G.t(P["depths"]))
+        assert got == I
+        assert np.array_equal(G.npy(ids), b["ids_sorted"])
+        assert np.array_equal(G.npy(bins), b["tile_bins"])
+        assert np.array_equal(G.npy(keys), b["keys_sorted"])
+    # --- rasteriser forward (oracle uses exp2f, GPU MUFU.EX2: bounded decision flips)
+    R = cpu.rasterize_fwd(inp["colors"], inp["opacities"], inp["background"], P["xys"],
+                          P["depths"], P["radii"], P["conics"], P["cum_tiles_hit"], binning=b, **rkw)
+    same = (R["final_idx"] == gpu["final_idx"])[..., 0]
+    assert 1.0 - same.mean() <= 2e-3
+    assert np.abs(R["img"][same] - gpu["img"][same]).max(initial=0) <= 1e-5
+    # --- backward, op level: feed the GPU's own forward results to the oracle
+    B = cpu.rasterize_bwd(inp["colors"], inp["opacities"], inp["background"], P["xys"],
+                          P["depths"], P["radii"], P["conics"], P["cum_tiles_hit"],
+                          gpu["final_Ts"], gpu["final_idx"], gpu["v_img"],
+                          np.zeros((H, W, 1), np.float32), binning=b, **rkw)
+    for k in ("v_colors", "v_opacity", "v_xy", "v_xy_abs", "v_conic"):
+        ok, err, scale = grad_close(gpu[k], B[k], rel=1e-4)
+        assert ok, (k, err, scale)
+    n = inp["means3d"].shape[0]
+    z = np.zeros((n, 1), np.float32)
+    Gd = cpu.project_bwd(inp["means3d"], inp["scales"], inp["quats"], inp["viewmat"], P["cov3ds"],
+                         P["xys"], P["radii"], P["conics"], P["compensation"], z, gpu["v_xy"], z,
+                         gpu["v_conic"], **kw)
+    for k in ("v_mean3d", "v_scale", "v_quat", "v_cov2d", "v_cov3d"):
+        ok, err, scale = grad_close(gpu[k], Gd[k], rel=1e-4)
+        assert ok, (k, err, scale)
+    return gpu
+
+
+def test_config1_vs_oracle():
+    _check_vs_oracle(synthetic.make_config("C1"))
+
+
+def test_config2_vs_oracle():
+    _check_vs_oracle(synthetic.make_config("C2"))
+
+
+@pytest.mark.parametrize("bw", [2, 4, 8, 16])
+def test_block_sizes_vs_oracle(bw):
+    s = synthetic.benchmark_scene(1200, (50, 70), scale_max=0.3, seed=21 + bw)
+    s.block_size = bw
+    _check_vs_oracle(s)
+
+
+@pytest.mark.parametrize("n", [1, 255, 256, 257, 4097])
+def test_ragged_counts(n):
+    _check_vs_oracle(synthetic.benchmark_scene(n, (33, 47), scale_max=0.4, seed=n))
+
+
+def test_single_gaussian_on_axis_closed_form():
+    """one isotropic Gaussian on the optical axis: xy = c, conic = 1/(f^2 s^2/z^2 + 0.3) I"""
+    s = synthetic.benchmark_scene(1, (64, 64), seed=0)
+    s.means3d[:] = 0
+    s.scales[:] = 0.2
+    s.quats[:] = torch.tensor([1.0, 0, 0, 0])
+    inp = G.scene_inputs(s)
+    kw, rkw = G.scene_kw(s)
+    P = G.project_fwd(inp, kw)
+    z, f = 8.0, 32.0
+    var = (f * 0.2 / z) ** 2 + 0.3
+    assert np.allclose(G.npy(P["xys"])[0], [32.0, 32.0], atol=1e-4)
+    assert np.allclose(G.npy(P["conics"])[0], [1 / var, 0, 1 / var], rtol=1e-5, atol=1e-7)
+    assert int(P["radii"][0]) == int(np.ceil(3 * np.sqrt(var)))
+    assert float(P["depths"][0]) == 8.0
+
+
+def test_empty_frame():
+    """all Gaussians behind the camera -> image = background, final_Ts = 0, zero grads (Q5)"""
+    s = synthetic.benchmark_scene(500, (40, 56), seed=3)
+    s.viewmat = synthetic._viewmat_identity(-30.0)
+    s.background = torch.tensor([0.25, 0.5, 0.75])
+    inp = G.scene_inputs(s)
+    kw, rkw = G.scene_kw(s)
+    _ops.poison_outputs(True)
+    try:
+        out = _full_gpu(inp, kw, rkw, np.zeros((40, 56, 3), np.float32))
+    finally:
+        _ops.poison_outputs(False)
+    assert not out["radii"].any() and not out["cum_tiles_hit"].any() and not out["cov3ds"].any()
+    assert np.array_equal(out["img"], np.broadcast_to(inp["background"], (40, 56, 3)))
+    assert not out["final_Ts"].any() and not out["final_idx"].any()
+    for k in ("v_colors", "v_opacity", "v_xy", "v_xy_abs", "v_conic", "v_mean3d", "v_scale", "v_quat"):
+        assert not out[k].any(), k
+
+
+def _adversarial_scene():
+    """thin, long, diagonal splats + tiny/huge opacities: the hard cases for the conservative
+    warp-rectangle pre-filter"""
+    g = torch.Generator().manual_seed(77)
+    n = 6000
+    s = synthetic.benchmark_scene(n, (160, 208), scale_max=0.3, seed=78)
+    s.scales[:, 0] = torch.rand(n, generator=g) * 1.5 + 0.05      # long axis
+    s.scales[:, 1] = torch.rand(n, generator=g) * 0.004 + 0.0002  # needle thin
+    s.scales[:, 2] = torch.rand(n, generator=g) * 0.004 + 0.0002
+    s.opacities[: n // 3] = torch.rand((n // 3, 1), generator=g) * 0.01  # around the 1/255 cut
+    s.opacities[n // 3: n // 2] = 1.0
+    return s
+
+
+@pytest.mark.parametrize("scene_fn", [_adversarial_scene, lambda: synthetic.make_config("C2", num_points=30000)])
+def test_culling_never_changes_a_bit(scene_fn):
+    s = scene_fn()
+    inp = G.scene_inputs(s)
+    kw, rkw = G.scene_kw(s)
+    H, W = s.img_shape
+    target = np.random.RandomState(1).rand(H, W, 3).astype(np.float32)
+    try:
+        _lib.set_option("cull", 1)
+        a = _full_gpu(inp, kw, rkw, target)
+        _lib.set_option("cull", 0)
+        b = _full_gpu(inp, kw, rkw, target)
+    finally:
+        _lib.set_option("cull", 1)
+    for k in ("final_idx",):
+        assert np.array_equal(a[k], b[k]), k
+    for k in ("final_Ts", "img"):
+        assert G.bits_equal(a[k], b[k]) == 0, k
+    for k in ("v_colors", "v_opacity", "v_xy", "v_xy_abs", "v_conic"):
+        ok, err, scale = grad_close(a[k], b[k], rel=2e-5)
+        assert ok, (k, err, scale)
+
+
+def test_adversarial_scene_vs_oracle():
+    _check_vs_oracle(_adversarial_scene())
+
+
+def test_backward_cache_on_off_identical_binning():
+    s = synthetic.make_config("C1")
+    inp = G.scene_inputs(s)
+    kw, rkw = G.scene_kw(s)
+    target = np.zeros((256, 256, 3), np.float32)
+    before = _lib.stats()
+    a = _full_gpu(inp, kw, rkw, target)
+    mid = _lib.stats()
+    assert mid["binning_cache_hits"] == before["binning_cache_hits"] + 1  # bwd reused the fwd sort
+    assert mid["binning_runs"] == before["binning_runs"] + 1
+    try:
+        _lib.set_option("cache", 0)
+        b = _full_gpu(inp, kw, rkw, target)
+    finally:
+        _lib.set_option("cache", 1)
+    after = _lib.stats()
+    assert after["binning_runs"] == mid["binning_runs"] + 2  # fwd and bwd both binned
+    for k in ("v_colors", "v_opacity", "v_xy", "v_conic", "v_mean3d"):
+        ok, err, scale = grad_close(a[k], b[k], rel=2e-5)
+        assert ok, (k, err, scale)
+
+
+def test_backward_rebins_when_inputs_changed():
+    """a backward whose inputs do not match the cached forward must not reuse its binning"""
+    s1 = synthetic.benchmark_scene(3000, (64, 64), seed=1)
+    s2 = synthetic.benchmark_scene(3000, (64, 64), seed=2)
+    kw, rkw = G.scene_kw(s1)
+    i1, i2 = G.scene_inputs(s1), G.scene_inputs(s2)
+    P1, P2 = G.project_fwd(i1, kw), G.project_fwd(i2, kw)
+    R1 = G.rasterize_fwd(i1, P1, rkw)
+    R2 = G.rasterize_fwd(i2, P2, rkw)          # cache now holds scene 2
+    v = torch.ones((64, 64, 3), device=G.DEV) * 1e-3
+    va = torch.zeros((64, 64, 1), device=G.DEV)
+    B1 = G.rasterize_bwd(i1, P1, R1, v, va, rkw)  # must re-bin for scene 1
+    ref = cpu.rasterize_bwd(i1["colors"], i1["opacities"], i1["background"], G.npy(P1["xys"]),
+                            G.npy(P1["depths"]), G.npy(P1["radii"]), G.npy(P1["conics"]),
+                            G.npy(P1["cum_tiles_hit"]), G.npy(R1["final_Ts"]),
+                            G.npy(R1["final_idx"]), G.npy(v), G.npy(va), **rkw)
+    for k in ("v_colors", "v_opacity", "v_xy", "v_conic"):
+        ok, err, scale = grad_close(G.npy(B1[k]), ref[k], rel=1e-4)
+        assert ok, (k, err, scale)
+
+
+def test_cumsum_and_sort_and_bin_entry_points():
+    L = _lib.lib()
+    x = torch.randint(0, 50, (100_003,), dtype=torch.int32, device=G.DEV)
+    y = torch.empty_like(x)
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    assert L.jsb200_cumsum(st, x.data_ptr(), y.data_ptr(), x.numel()) == 0
+    assert torch.equal(y, torch.cumsum(x, 0).to(torch.int32))
+    s = synthetic.make_config("C1")
+    inp = G.scene_inputs(s)
+    kw, rkw = G.scene_kw(s)
+    P = G.project_fwd(inp, kw)
+    I = int(P["cum_tiles_hit"][-1])
+    from jaxsplat_b200 import _ffi
+    desc = _ffi.make_descriptor(10000, s.img_shape, (0, 0), (0, 0), 0, 0, 16)
+    ids = torch.empty(I, dtype=torch.int32, device=G.DEV)
+    bins = torch.empty((256, 2), dtype=torch.int32, device=G.DEV)
+    rc = L.jsb200_sort_and_bin(st, desc, 80, I, P["xys"].data_ptr(), P["depths"].data_ptr(),
+                               P["radii"].data_ptr(), P["cum_tiles_hit"].data_ptr(),
+                               ids.data_ptr(), bins.data_ptr())
+    assert rc == 0
+    torch.cuda.synchronize()
+    b = cpu.sort_and_bin(G.npy(P["xys"]), G.npy(P["depths"]), G.npy(P["radii"]),
+                         G.npy(P["cum_tiles_hit"]), **rkw)
+    assert np.array_equal(G.npy(ids), b["ids_sorted"]) and np.array_equal(G.npy(bins), b["tile_bins"])
