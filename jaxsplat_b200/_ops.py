@@ -15,6 +15,18 @@ import torch
 from . import _ffi
 
 _POISON = False
+_DEFAULT_TABLE = None
+
+
+def set_default_table(table) -> None:
+    """Benchmark/test hook: run the public API on another library exposing the same four
+    custom-call targets (the reference's capsules).  None restores this package's own library."""
+    global _DEFAULT_TABLE
+    _DEFAULT_TABLE = table
+
+
+def _resolve(table):
+    return table or _DEFAULT_TABLE or _ffi.native_table()
 
 
 def poison_outputs(enable: bool) -> None:
@@ -52,7 +64,7 @@ def _desc(table, num_points, img_shape, f, c, glob_scale, clip_thresh, block_wid
 
 def project_fwd(mean3ds, scales, quats, viewmat, *, num_points, img_shape, f, c, glob_scale,
                 clip_thresh, block_width, table: Optional[_ffi.CustomCallTable] = None):
-    table = table or _ffi.native_table()
+    table = _resolve(table)
     n, dev = num_points, mean3ds.device
     ins = [_f32(mean3ds, (n, 3), "mean3ds"), _f32(scales, (n, 3), "scales"),
            _f32(quats, (n, 4), "quats"), _f32(viewmat, (4, 4), "viewmat")]
@@ -69,7 +81,7 @@ def project_fwd(mean3ds, scales, quats, viewmat, *, num_points, img_shape, f, c,
 def project_bwd(mean3ds, scales, quats, viewmat, cov3ds, xys, radii, conics, compensation,
                 v_compensation, v_xy, v_depth, v_conic, *, num_points, img_shape, f, c, glob_scale,
                 clip_thresh, block_width, table: Optional[_ffi.CustomCallTable] = None):
-    table = table or _ffi.native_table()
+    table = _resolve(table)
     n, dev = num_points, mean3ds.device
     ins = [_f32(mean3ds, (n, 3), "mean3ds"), _f32(scales, (n, 3), "scales"),
            _f32(quats, (n, 4), "quats"), _f32(viewmat, (4, 4), "viewmat"),
@@ -89,7 +101,7 @@ def project_bwd(mean3ds, scales, quats, viewmat, cov3ds, xys, radii, conics, com
 def rasterize_fwd(colors, opacities, background, xys, depths, radii, conics, cum_tiles_hit, *,
                   num_points, img_shape, block_width,
                   table: Optional[_ffi.CustomCallTable] = None):
-    table = table or _ffi.native_table()
+    table = _resolve(table)
     n, dev = num_points, colors.device
     H, W = img_shape
     ins = [_f32(colors, (n, 3), "colors"), _f32(opacities, (n, 1), "opacities"),
@@ -109,7 +121,7 @@ def rasterize_fwd(colors, opacities, background, xys, depths, radii, conics, cum
 def rasterize_bwd(colors, opacities, background, xys, depths, radii, conics, cum_tiles_hit,
                   final_Ts, final_idx, v_img, v_img_alpha, *, num_points, img_shape, block_width,
                   table: Optional[_ffi.CustomCallTable] = None):
-    table = table or _ffi.native_table()
+    table = _resolve(table)
     n, dev = num_points, colors.device
     H, W = img_shape
     ins = [_f32(colors, (n, 3), "colors"), _f32(opacities, (n, 1), "opacities"),

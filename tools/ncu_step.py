@@ -1,0 +1,22 @@
+"""a few fwd+bwd steps of a BASELINE config through the public API, for ncu captures"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import jaxsplat_b200 as jsb  # noqa: E402
+from jaxsplat_b200 import synthetic  # noqa: E402
+
+cfg = sys.argv[1] if len(sys.argv) > 1 else "C3"
+steps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+sc = synthetic.make_config(cfg).to("cuda:0")
+H, W = sc.img_shape
+target = torch.rand((H, W, 3), generator=torch.Generator().manual_seed(1)).to("cuda:0")
+params = [p.clone().requires_grad_(True) for p in sc.params()]
+for _ in range(steps):
+    for p in params:
+        p.grad = None
+    img = jsb.render(*params, **sc.render_kwargs())
+    ((img - target) ** 2).mean().backward()
+torch.cuda.synchronize()
