@@ -49,7 +49,6 @@ bin_prep_kernel(const BinParams p, const float2 *__restrict__ xys,
         slab_load<3, BT>(s_color, colors, base * 3, n * 3);
     }
     __syncthreads();
-    unsigned long long h = 0;
     unsigned cnt = 0;
     if (g < n) {
         const float2 xy = __ldg(xys + g);
@@ -81,28 +80,45 @@ bin_prep_kernel(const BinParams p, const float2 *__restrict__ xys,
             ids[g] = (unsigned)g;
             tile_counts[g] = cnt;
         }
-        // order-independent fingerprint of everything the cached binning depends on
-        unsigned long long a = ((unsigned long long)__float_as_uint(xy.x) << 32) | __float_as_uint(xy.y);
-        unsigned long long c = ((unsigned long long)__float_as_uint(depth) << 32) | (unsigned)radius;
-        unsigned long long d = ((unsigned long long)__float_as_uint(cx) << 32) | __float_as_uint(cy);
-        unsigned long long e = ((unsigned long long)__float_as_uint(cz) << 32) | __float_as_uint(opac);
-        unsigned long long f = ((unsigned long long)__float_as_uint(r) << 32) | __float_as_uint(gr);
-        h = mix64(a + 0x9e3779b97f4a7c15ull * (unsigned long long)(g + 1));
-        h = mix64(h ^ c);
-        h = mix64(h ^ d);
-        h = mix64(h ^ e);
-        h = mix64(h ^ f);
-        h = mix64(h ^ __float_as_uint(b));
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        h += __shfl_xor_sync(0xffffffffu, h, o);
-        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if ((tid & 31) == 0 && cnt) atomicAdd(fingerprint + 1, (unsigned long long)cnt);  // total intersections
+}
+
+// Order-independent 64-bit fingerprint of up to 6 word arrays (sum of per-word hashes keyed by
+// array id and word index).  Pure streaming read with 16-byte loads: rasterize_bwd uses it to
+// prove that its inputs are byte-identical to the forward's before reusing the cached binning.
+struct FpArrays {
+    const unsigned *ptr[6];
+    unsigned long long words[6];
+};
+__device__ __forceinline__ unsigned long long fp_word(unsigned a, unsigned long long i, unsigned v) {
+    return mix64((unsigned long long)v * 0x9e3779b97f4a7c15ull + (i + ((unsigned long long)(a + 1) << 40)));
+}
+__global__ void __launch_bounds__(256) fingerprint_kernel(const FpArrays A, unsigned long long *out) {
+    unsigned long long h = 0;
+    const unsigned long long tid = blockIdx.x * 256ull + threadIdx.x, nthr = gridDim.x * 256ull;
+#pragma unroll 1
+    for (int a = 0; a < 6; ++a) {
+        const unsigned *p = A.ptr[a];
+        if (!p) continue;
+        const unsigned long long nw = A.words[a];
+        if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+            const unsigned long long nv = nw >> 2;
+            for (unsigned long long v = tid; v < nv; v += nthr) {
+                const uint4 q = __ldg(reinterpret_cast<const uint4 *>(p) + v);
+                h += fp_word(a, 4 * v, q.x) + fp_word(a, 4 * v + 1, q.y) + fp_word(a, 4 * v + 2, q.z) +
+                     fp_word(a, 4 * v + 3, q.w);
+            }
+            for (unsigned long long i = (nv << 2) + tid; i < nw; i += nthr) h += fp_word(a, i, __ldg(p + i));
+        } else {
+            for (unsigned long long i = tid; i < nw; i += nthr) h += fp_word(a, i, __ldg(p + i));
+        }
     }
-    if ((tid & 31) == 0) {
-        if (h) atomicAdd(fingerprint, h);
-        if (cnt) atomicAdd(fingerprint + 1, (unsigned long long)cnt);  // total intersections
-    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) h += __shfl_xor_sync(0xffffffffu, h, o);
+    if ((threadIdx.x & 31) == 0 && h) atomicAdd(out, h);
 }
 
 // inclusive int32 prefix sum, single pass (reference ops.cu:607-643 uses cub::DeviceScan)
@@ -181,37 +197,104 @@ emit_kernel(const BinParams p, const unsigned *__restrict__ order,
         if (tid == 0) s_prefix = pre;
     }
     __syncthreads();
-    const unsigned long long out0 = s_prefix;
-    for (unsigned k = tid; k < total; k += BT) {
-        // last t with s_off[t] <= k
-        int lo = 0, hi = BT;  // invariant: s_off[lo] <= k < s_off[hi]
+    // Output: every thread owns 8-element chunks aligned in GLOBAL index space, so full chunks
+    // leave as 16-byte vector stores; inside a chunk the (gaussian, row, col) cursor is advanced
+    // incrementally (one binary search + one division per chunk instead of per element).
+    const unsigned long long g_begin = s_prefix, g_end = g_begin + total;
+    const unsigned long long first_chunk = g_begin >> 3;
+    const unsigned num_chunks = (unsigned)(((g_end + 7) >> 3) - first_chunk);
+    for (unsigned c = tid; c < num_chunks; c += BT) {
+        const unsigned long long cg = (first_chunk + c) << 3;
+        const unsigned kb = cg > g_begin ? (unsigned)(cg - g_begin) : 0u;
+        const unsigned ke = (cg + 8 < g_end) ? (unsigned)(cg + 8 - g_begin) : total;
+        if (kb >= ke) continue;
+        int lo = 0, hi = BT;  // invariant: s_off[lo] <= kb < s_off[hi]
 #pragma unroll
-        for (int s = 0; s < 8; ++s) {
-            int mid = (lo + hi) >> 1;
-            if (s_off[mid] <= k) lo = mid; else hi = mid;
+        for (int st = 0; st < 8; ++st) {
+            const int mid = (lo + hi) >> 1;
+            if (s_off[mid] <= kb) lo = mid; else hi = mid;
         }
-        const unsigned j = k - s_off[lo];
-        const unsigned w = s_w[lo];
+        unsigned next_off = s_off[lo + 1];
+        unsigned w = s_w[lo], g = s_g[lo];
+        const unsigned j = kb - s_off[lo];
         const unsigned row = j / w;
-        const unsigned col = j - row * w;
-        keys[out0 + k] = (TileKey)(s_tile0[lo] + row * p.tiles_x + col);
-        vals[out0 + k] = s_g[lo];
+        unsigned col = j - row * w;
+        unsigned tile = s_tile0[lo] + row * p.tiles_x + col;
+        TileKey kk[8];
+        unsigned vv[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const unsigned k = kb + e;
+            if (k < ke) {
+                if (k >= next_off) {
+                    do { ++lo; next_off = s_off[lo + 1]; } while (k >= next_off);
+                    w = s_w[lo]; g = s_g[lo]; tile = s_tile0[lo]; col = 0;
+                }
+                kk[e] = (TileKey)tile;
+                vv[e] = g;
+                ++col; ++tile;
+                if (col == w) { col = 0; tile += p.tiles_x - w; }
+            }
+        }
+        const bool full = (cg >= g_begin) && (ke - kb == 8);
+        if (full) {
+            if (sizeof(TileKey) == 2) {
+                uint4 pk;
+                pk.x = (unsigned)kk[0] | ((unsigned)kk[1] << 16);
+                pk.y = (unsigned)kk[2] | ((unsigned)kk[3] << 16);
+                pk.z = (unsigned)kk[4] | ((unsigned)kk[5] << 16);
+                pk.w = (unsigned)kk[6] | ((unsigned)kk[7] << 16);
+                *reinterpret_cast<uint4 *>(keys + cg) = pk;
+            } else {
+                *reinterpret_cast<uint4 *>(keys + cg) = make_uint4(kk[0], kk[1], kk[2], kk[3]);
+                *reinterpret_cast<uint4 *>(keys + cg + 4) = make_uint4(kk[4], kk[5], kk[6], kk[7]);
+            }
+            *reinterpret_cast<uint4 *>(vals + cg) = make_uint4(vv[0], vv[1], vv[2], vv[3]);
+            *reinterpret_cast<uint4 *>(vals + cg + 4) = make_uint4(vv[4], vv[5], vv[6], vv[7]);
+        } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+                if (kb + e < ke) {
+                    keys[g_begin + kb + e] = kk[e];
+                    vals[g_begin + kb + e] = vv[e];
+                }
+        }
     }
 }
 
+// 8 sorted keys per thread (one 16-byte load for uint16 keys) + the key just before them
 template <typename TileKey>
 __global__ void __launch_bounds__(256)
 bin_edges_kernel(const TileKey *__restrict__ keys, unsigned n, int2 *__restrict__ bins) {
-    const unsigned i = blockIdx.x * 256u + threadIdx.x;
-    if (i >= n) return;
-    const unsigned cur = keys[i];
-    if (i == 0) bins[cur].x = 0;
-    if (i == n - 1) bins[cur].y = (int)n;
-    if (i == 0) return;
-    const unsigned prev = keys[i - 1];
-    if (prev != cur) {
-        bins[prev].y = (int)i;
-        bins[cur].x = (int)i;
+    const unsigned base = (blockIdx.x * 256u + threadIdx.x) * 8u;
+    if (base >= n) return;
+    unsigned k[8];
+    const unsigned m = min(8u, n - base);
+    if (m == 8) {
+        if (sizeof(TileKey) == 2) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(keys + base));
+            k[0] = v.x & 0xffffu; k[1] = v.x >> 16; k[2] = v.y & 0xffffu; k[3] = v.y >> 16;
+            k[4] = v.z & 0xffffu; k[5] = v.z >> 16; k[6] = v.w & 0xffffu; k[7] = v.w >> 16;
+        } else {
+            const uint4 v0 = __ldg(reinterpret_cast<const uint4 *>(keys + base));
+            const uint4 v1 = __ldg(reinterpret_cast<const uint4 *>(keys + base + 4));
+            k[0] = v0.x; k[1] = v0.y; k[2] = v0.z; k[3] = v0.w;
+            k[4] = v1.x; k[5] = v1.y; k[6] = v1.z; k[7] = v1.w;
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) k[e] = (unsigned)e < m ? (unsigned)keys[base + e] : 0u;
+    }
+    unsigned prev = base ? (unsigned)keys[base - 1] : 0xffffffffu;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        if ((unsigned)e < m) {
+            const unsigned i = base + e, cur = k[e];
+            if (i == 0) bins[cur].x = 0;
+            else if (prev != cur) { bins[prev].y = (int)i; bins[cur].x = (int)i; }
+            if (i == n - 1) bins[cur].y = (int)n;
+            prev = cur;
+        }
     }
 }
 
@@ -234,6 +317,23 @@ int launch_inclusive_scan_i32(cudaStream_t stream, const int *in, int *out, unsi
                               unsigned long long *chain, unsigned *ticket, int *err) {
     if (n == 0) return 0;
     inclusive_scan_kernel<<<ceil_div(n, BT * SC_ITEMS), BT, 0, stream>>>(in, out, n, chain, ticket, err);
+    JSB_CUDA_OK(cudaGetLastError());
+    note_launch();
+    return 0;
+}
+
+int launch_fingerprint(cudaStream_t stream, unsigned n, const float *xys, const float *depths,
+                       const int *radii, const float *conics, const float *opacities,
+                       const float *colors, unsigned long long *out) {
+    if (n == 0) return 0;
+    FpArrays A;
+    const void *ptrs[6] = {xys, depths, radii, conics, opacities, colors};
+    const unsigned long long words[6] = {2ull * n, n, n, 3ull * n, n, 3ull * n};
+    for (int a = 0; a < 6; ++a) {
+        A.ptr[a] = reinterpret_cast<const unsigned *>(ptrs[a]);
+        A.words[a] = words[a];
+    }
+    fingerprint_kernel<<<148 * 8, 256, 0, stream>>>(A, out);
     JSB_CUDA_OK(cudaGetLastError());
     note_launch();
     return 0;
@@ -281,7 +381,7 @@ template <typename TileKey>
 int launch_bin_edges(cudaStream_t stream, const TileKey *sorted_keys, unsigned n,
                      int2 *tile_bins) {
     if (n == 0) return 0;
-    bin_edges_kernel<TileKey><<<ceil_div(n, 256), 256, 0, stream>>>(sorted_keys, n, tile_bins);
+    bin_edges_kernel<TileKey><<<ceil_div(n, 256 * 8), 256, 0, stream>>>(sorted_keys, n, tile_bins);
     JSB_CUDA_OK(cudaGetLastError());
     note_launch();
     return 0;

@@ -218,10 +218,11 @@ static int bin_prepare(Ctx &c, const Descriptor &d, const float *xys, const floa
     unsigned long long *small64 = (unsigned long long *)c.small.p;
     {
     StageScope ss(&c, ST_BIN_PREP);
-    if (launch_bin_prep(s, bp, xys, depths, radii, conics, opac, colors,
-                        (SplatRecord *)c.records.p, (unsigned *)c.dkeys_a.p, (unsigned *)c.ids_a.p,
-                        (unsigned *)c.counts.p, small64, write))
+    if (write && launch_bin_prep(s, bp, xys, depths, radii, conics, opac, colors,
+                                 (SplatRecord *)c.records.p, (unsigned *)c.dkeys_a.p,
+                                 (unsigned *)c.ids_a.p, (unsigned *)c.counts.p, small64, true))
         return 1;
+    if (launch_fingerprint(s, n, xys, depths, radii, conics, opac, colors, small64)) return 1;
     }
     JSB_CUDA_OK(cudaMemcpyAsync(c.h_pinned, c.small.p, 32, cudaMemcpyDeviceToHost, s));
     JSB_CUDA_OK(cudaStreamSynchronize(s));
@@ -448,14 +449,15 @@ static int rasterize_bwd_impl(cudaStream_t stream, void **buf, const Descriptor 
                     (const float *)buf[6], (const float *)buf[1], (const float *)buf[0], &I, &fp,
                     /*write=*/false))
         return 1;
-    if (I == 0) return 0;
-    if (cache_hit(*c, d, I, fp)) {
+    // (a fingerprint-only pass does not recount intersections: the fingerprint covers them)
+    if (cache_hit(*c, d, c->cache_I, fp)) {
         g_stats[3].fetch_add(1);
     } else {
         if (bin_prepare(*c, d, (const float *)buf[3], (const float *)buf[4], (const int *)buf[5],
                         (const float *)buf[6], (const float *)buf[1], (const float *)buf[0], &I,
                         &fp, /*write=*/true))
             return 1;
+        if (I == 0) return 0;
         if (bin_sort(*c, d, (const float *)buf[3], (const int *)buf[5], I, fp)) return 1;
         c->cache_has_records = true;
     }

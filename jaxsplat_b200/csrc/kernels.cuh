@@ -56,6 +56,11 @@ int launch_bin_prep(cudaStream_t stream, const BinParams &p, const float *xys,
                     unsigned *depth_keys, unsigned *ids, unsigned *tile_counts,
                     unsigned long long *fingerprint, bool write = true);
 
+// *out += order-independent 64-bit hash of every rasterizer input word (null arrays skipped)
+int launch_fingerprint(cudaStream_t stream, unsigned n, const float *xys, const float *depths,
+                       const int *radii, const float *conics, const float *opacities,
+                       const float *colors, unsigned long long *out);
+
 // inclusive int32 prefix sum (chain: ceil(n/1024) u64 zeroed, ticket zeroed)
 int launch_inclusive_scan_i32(cudaStream_t stream, const int *in, int *out, unsigned n,
                               unsigned long long *chain, unsigned *ticket, int *err);

@@ -10,10 +10,13 @@
 //     warp only replays Gaussians that can reach its 8x4 pixels;
 //   * the CTA starts at the batch holding the largest final_idx of the tile instead of the end
 //     of the tile's list;
-//   * the 11 per-pixel partial gradients are reduced across the warp with a halving butterfly
-//     (16 shuffles: after each exchange a lane keeps half of the slots) instead of 11 full
-//     butterflies (55 shuffles), and the 11 totals end up in 11 different lanes which issue ONE
-//     predicated RED.ADD.F32 instruction instead of 11 serial ones from lane 0.
+//   * the 11 per-pixel partial gradients are reduced across the warp through a per-warp shared
+//     transpose (11 conflict-free STS, then 22 lanes each sum half a row with 4 LDS.128 + 15 FADD,
+//     one shuffle joins the halves) instead of 11 full butterflies (55 SHFL + 55 FADD); the 11
+//     totals end up in 11 different lanes which issue ONE predicated RED.ADD.F32 instruction
+//     instead of 11 serial ones from lane 0;
+//   * invalid lanes are not branched around: their alpha and visibility are forced to 0, which
+//     makes every partial exactly 0 and leaves T and the colour buffer unchanged.
 #include "common.cuh"
 #include "kernels.cuh"
 #include "raster_cull.cuh"
@@ -22,56 +25,21 @@ namespace jsb {
 namespace {
 
 constexpr int RB = 256;
-
-// Halving butterfly: on entry every lane holds 16 slots; on exit lane L holds in the return
-// value the warp-wide sum of slot (L >> 1).
-__device__ __forceinline__ float warp_reduce_16slots(float (&v)[16], int lane) {
-    {
-        const bool hi = lane & 16;
-#pragma unroll
-        for (int s = 0; s < 8; ++s) {
-            const float send = hi ? v[s] : v[s + 8];
-            const float keep = hi ? v[s + 8] : v[s];
-            v[s] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-        }
-    }
-    {
-        const bool hi = lane & 8;
-#pragma unroll
-        for (int s = 0; s < 4; ++s) {
-            const float send = hi ? v[s] : v[s + 4];
-            const float keep = hi ? v[s + 4] : v[s];
-            v[s] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-        }
-    }
-    {
-        const bool hi = lane & 4;
-#pragma unroll
-        for (int s = 0; s < 2; ++s) {
-            const float send = hi ? v[s] : v[s + 2];
-            const float keep = hi ? v[s + 2] : v[s];
-            v[s] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-        }
-    }
-    {
-        const bool hi = lane & 2;
-        const float send = hi ? v[0] : v[1];
-        const float keep = hi ? v[1] : v[0];
-        v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-    }
-    return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
-}
+constexpr int RED_STRIDE = 36;  // floats per transposed row: 16-byte phases of LDS.128 conflict-free
 
 struct PixelGrad {
     float v[11];  // rgb(3) conic(3) xy(2) xy_abs(2) opacity(1)
 };
 
 // per-pixel gradient of one valid (pixel, Gaussian) pair; updates T and the colour buffer
-__device__ __forceinline__ void pair_grad(float alpha, float vis, float opac, float dx, float dy,
+__device__ __forceinline__ void pair_grad(bool valid, float alpha, float vis, float opac, float dx, float dy,
                                           float cx, float cy, float cz, float r, float g, float b,
                                           const float3 v_out, float v_out_alpha, float T_final,
                                           const float3 bg, float &T, float3 &buf, float *o) {
-    const float ra = frcp(fsub(1.f, alpha));
+    // invalid lanes: alpha = vis = 0 and ra = 1 make every partial exactly 0 and keep T / buf
+    alpha = valid ? alpha : 0.f;
+    vis = valid ? vis : 0.f;
+    const float ra = valid ? __fdividef(1.f, 1.f - alpha) : 1.f;  // gradient path: approx rcp is enough
     T = T * ra;
     const float fac = alpha * T;
     o[0] = v_out.x * fac;
@@ -101,7 +69,7 @@ __device__ __forceinline__ void pair_grad(float alpha, float vis, float opac, fl
 }
 
 template <bool CULL>
-__global__ void __launch_bounds__(RB)
+__global__ void __launch_bounds__(RB, 4)
 raster_bwd16_kernel(const RasterParams p, const unsigned *__restrict__ ids_sorted,
                     const int2 *__restrict__ tile_bins, const SplatRecord *__restrict__ records,
                     const float *__restrict__ background, const float *__restrict__ final_Ts,
@@ -115,8 +83,10 @@ raster_bwd16_kernel(const RasterParams p, const unsigned *__restrict__ ids_sorte
     __shared__ unsigned sId[RB];
     __shared__ unsigned char sMask[RB];
     __shared__ int s_max[RB / 32];
+    __shared__ __align__(16) float sRed[(RB / 32) * 11 * RED_STRIDE];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float *red = sRed + warp * 11 * RED_STRIDE;
     const unsigned tile = blockIdx.x;
     const unsigned tile_y = tile / p.tiles_x, tile_x = tile - tile_y * p.tiles_x;
     const unsigned j = tile_x * 16 + (warp & 1) * kRectW + (lane & 7);
@@ -201,13 +171,22 @@ raster_bwd16_kernel(const RasterParams p, const unsigned *__restrict__ ids_sorte
                 const bool valid = inside && (batch_end - t <= bin_final) && !(sigma < 0.f) &&
                                    !(alpha < kAlphaMin);
                 if (!__any_sync(0xffffffffu, valid)) continue;
-                float v[16];
+                float v[11];
+                pair_grad(valid, alpha, vis, a.z, dx, dy, a.w, bq.x, bq.y, bq.z, bq.w, sC[t], v_out,
+                          v_oa, T_final, bg, T, buf, v);
+                // transpose through shared memory: row k = value k of the 32 lanes
+                __syncwarp();
 #pragma unroll
-                for (int s = 0; s < 16; ++s) v[s] = 0.f;
-                if (valid)
-                    pair_grad(alpha, vis, a.z, dx, dy, a.w, bq.x, bq.y, bq.z, bq.w, sC[t], v_out,
-                              v_oa, T_final, bg, T, buf, v);
-                const float total = warp_reduce_16slots(v, lane);
+                for (int k = 0; k < 11; ++k) red[k * RED_STRIDE + lane] = v[k];
+                __syncwarp();
+                float total = 0.f;
+                if (lane < 22) {
+                    const float4 *row = reinterpret_cast<const float4 *>(red + (lane >> 1) * RED_STRIDE + (lane & 1) * 16);
+                    const float4 p0 = row[0], p1 = row[1], p2 = row[2], p3 = row[3];
+                    total = ((p0.x + p0.y) + (p0.z + p0.w)) + ((p1.x + p1.y) + (p1.z + p1.w)) +
+                            (((p2.x + p2.y) + (p2.z + p2.w)) + ((p3.x + p3.y) + (p3.z + p3.w)));
+                }
+                total += __shfl_xor_sync(0xffffffffu, total, 1);
                 if (writer) atomicAdd(out_base + (size_t)sId[t] * out_stride, total);
             }
         }
@@ -248,8 +227,8 @@ __global__ void raster_bwd_generic_kernel(
         const float alpha = fminf(fmul(a.z, vis), 0.99f);
         if (sigma < 0.f || alpha < kAlphaMin) continue;
         float o[11];
-        pair_grad(alpha, vis, a.z, dx, dy, a.w, bq.x, bq.y, bq.z, bq.w, cb, v_out, v_oa, T_final,
-                  bg, T, buf, o);
+        pair_grad(true, alpha, vis, a.z, dx, dy, a.w, bq.x, bq.y, bq.z, bq.w, cb, v_out, v_oa,
+                  T_final, bg, T, buf, o);
         atomicAdd(v_colors + 3 * (size_t)g + 0, o[0]);
         atomicAdd(v_colors + 3 * (size_t)g + 1, o[1]);
         atomicAdd(v_colors + 3 * (size_t)g + 2, o[2]);
