@@ -108,8 +108,12 @@ __global__ void __launch_bounds__(256) fingerprint_kernel(const FpArrays A, unsi
             const unsigned long long nv = nw >> 2;
             for (unsigned long long v = tid; v < nv; v += nthr) {
                 const uint4 q = __ldg(reinterpret_cast<const uint4 *>(p) + v);
-                h += fp_word(a, 4 * v, q.x) + fp_word(a, 4 * v + 1, q.y) + fp_word(a, 4 * v + 2, q.z) +
-                     fp_word(a, 4 * v + 3, q.w);
+                const unsigned long long lo = ((unsigned long long)q.y << 32) | q.x;
+                const unsigned long long hi = ((unsigned long long)q.w << 32) | q.z;
+                // one avalanche per 16 bytes (a different, equally valid hash than the word path:
+                // a fwd/bwd pair only has to agree when both see the same alignment)
+                h += mix64((lo * 0x9e3779b97f4a7c15ull) ^ (hi * 0xc2b2ae3d27d4eb4full + v) ^
+                           ((unsigned long long)(a + 1) << 56));
             }
             for (unsigned long long i = (nv << 2) + tid; i < nw; i += nthr) h += fp_word(a, i, __ldg(p + i));
         } else {
@@ -155,23 +159,70 @@ inclusive_scan_kernel(const int *__restrict__ in, int *__restrict__ out, unsigne
     }
 }
 
+// per-CTA number of (tile, Gaussian) pairs of 256 depth-ordered Gaussians
+__global__ void __launch_bounds__(BT)
+emit_count_kernel(unsigned n, const unsigned *__restrict__ order,
+                  const unsigned *__restrict__ tile_counts, unsigned *__restrict__ block_totals) {
+    __shared__ unsigned s_w[BT / 32];
+    const long long pos = (long long)blockIdx.x * BT + threadIdx.x;
+    unsigned c = pos < (long long)n ? tile_counts[order[pos]] : 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned t = 0;
+#pragma unroll
+        for (int w = 0; w < BT / 32; ++w) t += s_w[w];
+        block_totals[blockIdx.x] = t;
+    }
+}
+
+// in-place exclusive scan of the CTA totals: a single CTA walks them 1024 at a time
+__global__ void __launch_bounds__(1024) scan_totals_kernel(unsigned *__restrict__ totals, unsigned nb) {
+    __shared__ unsigned s_ws[1024 / 32 + 1];
+    unsigned carry = 0;
+    for (unsigned b = 0; b < nb; b += 1024) {
+        const unsigned i = b + threadIdx.x;
+        const unsigned v = i < nb ? totals[i] : 0u;
+        unsigned total;
+        const unsigned e = cta_exclusive_scan<1024>(v, &total, s_ws);
+        if (i < nb) totals[i] = carry + e;
+        carry += total;
+        __syncthreads();
+    }
+}
+
+// cum[i] += prefix[i / per_block]   (per_block is a multiple of 4: one int4 never straddles)
+__global__ void __launch_bounds__(256)
+add_block_prefix_kernel(int *__restrict__ cum, const unsigned *__restrict__ prefix, unsigned n,
+                        unsigned per_block) {
+    const unsigned v = blockIdx.x * 256u + threadIdx.x;
+    const unsigned i = v * 4u;
+    if (i >= n) return;
+    const int add = (int)prefix[i / per_block];
+    if (i + 4 <= n && (reinterpret_cast<uintptr_t>(cum) & 15) == 0) {
+        int4 q = reinterpret_cast<int4 *>(cum)[v];
+        q.x += add; q.y += add; q.z += add; q.w += add;
+        reinterpret_cast<int4 *>(cum)[v] = q;
+    } else {
+        for (unsigned k = i; k < n && k < i + 4; ++k) cum[k] += add;
+    }
+}
+
 template <typename TileKey>
 __global__ void __launch_bounds__(BT)
 emit_kernel(const BinParams p, const unsigned *__restrict__ order,
             const unsigned *__restrict__ tile_counts, const float2 *__restrict__ xys,
             const int *__restrict__ radii, TileKey *__restrict__ keys,
-            unsigned *__restrict__ vals, unsigned long long *__restrict__ chain,
-            unsigned *__restrict__ ticket, int *__restrict__ err) {
+            unsigned *__restrict__ vals, const unsigned *__restrict__ block_prefix) {
     __shared__ unsigned s_off[BT + 1];
     __shared__ unsigned s_tile0[BT];   // first tile id of the box
     __shared__ unsigned s_w[BT];       // box width in tiles
     __shared__ unsigned s_g[BT];
     __shared__ unsigned s_ws[BT / 32 + 1];
-    __shared__ unsigned s_bid, s_prefix;
     const int tid = threadIdx.x;
-    if (tid == 0) s_bid = atomicAdd(ticket, 1u);
-    __syncthreads();
-    const unsigned bid = s_bid;
+    const unsigned bid = blockIdx.x;
     const long long pos = (long long)bid * BT + tid;
     unsigned cnt = 0;
     if (pos < (long long)p.num_points) {
@@ -192,15 +243,11 @@ emit_kernel(const BinParams p, const unsigned *__restrict__ order,
     const unsigned excl = cta_exclusive_scan<BT>(cnt, &total, s_ws);
     s_off[tid] = excl;
     if (tid == 0) s_off[BT] = total;
-    if (tid < 32) {
-        unsigned pre = chain_exclusive_prefix(chain, (int)bid, total, err);
-        if (tid == 0) s_prefix = pre;
-    }
     __syncthreads();
     // Output: every thread owns 8-element chunks aligned in GLOBAL index space, so full chunks
     // leave as 16-byte vector stores; inside a chunk the (gaussian, row, col) cursor is advanced
     // incrementally (one binary search + one division per chunk instead of per element).
-    const unsigned long long g_begin = s_prefix, g_end = g_begin + total;
+    const unsigned long long g_begin = block_prefix[bid], g_end = g_begin + total;
     const unsigned long long first_chunk = g_begin >> 3;
     const unsigned num_chunks = (unsigned)(((g_end + 7) >> 3) - first_chunk);
     for (unsigned c = tid; c < num_chunks; c += BT) {
@@ -361,21 +408,43 @@ int launch_bin_prep(cudaStream_t stream, const BinParams &p, const float *xys,
 template <typename TileKey>
 int launch_emit(cudaStream_t stream, const BinParams &p, const unsigned *order,
                 const unsigned *tile_counts, const float *xys, const int *radii, TileKey *keys,
-                unsigned *vals, unsigned long long *chain, unsigned *ticket, int *err) {
+                unsigned *vals, unsigned *block_totals) {
     if (p.num_points == 0) return 0;
-    emit_kernel<TileKey><<<ceil_div(p.num_points, BT), BT, 0, stream>>>(
-        p, order, tile_counts, reinterpret_cast<const float2 *>(xys), radii, keys, vals, chain,
-        ticket, err);
+    const unsigned blocks = ceil_div(p.num_points, BT);
+    emit_count_kernel<<<blocks, BT, 0, stream>>>(p.num_points, order, tile_counts, block_totals);
+    JSB_CUDA_OK(cudaGetLastError());
+    note_launch();
+    if (launch_scan_totals(stream, block_totals, blocks)) return 1;
+    emit_kernel<TileKey><<<blocks, BT, 0, stream>>>(
+        p, order, tile_counts, reinterpret_cast<const float2 *>(xys), radii, keys, vals,
+        block_totals);
+    JSB_CUDA_OK(cudaGetLastError());
+    note_launch();
+    return 0;
+}
+
+int launch_scan_totals(cudaStream_t stream, unsigned *totals, unsigned nb) {
+    if (nb == 0) return 0;
+    scan_totals_kernel<<<1, 1024, 0, stream>>>(totals, nb);
+    JSB_CUDA_OK(cudaGetLastError());
+    note_launch();
+    return 0;
+}
+
+int launch_add_block_prefix(cudaStream_t stream, int *cum, const unsigned *prefix, unsigned n,
+                            unsigned per_block) {
+    if (n == 0) return 0;
+    add_block_prefix_kernel<<<ceil_div(ceil_div(n, 4), 256), 256, 0, stream>>>(cum, prefix, n, per_block);
     JSB_CUDA_OK(cudaGetLastError());
     note_launch();
     return 0;
 }
 template int launch_emit<uint16_t>(cudaStream_t, const BinParams &, const unsigned *,
                                    const unsigned *, const float *, const int *, uint16_t *,
-                                   unsigned *, unsigned long long *, unsigned *, int *);
+                                   unsigned *, unsigned *);
 template int launch_emit<uint32_t>(cudaStream_t, const BinParams &, const unsigned *,
                                    const unsigned *, const float *, const int *, uint32_t *,
-                                   unsigned *, unsigned long long *, unsigned *, int *);
+                                   unsigned *, unsigned *);
 
 template <typename TileKey>
 int launch_bin_edges(cudaStream_t stream, const TileKey *sorted_keys, unsigned n,

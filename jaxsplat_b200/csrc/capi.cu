@@ -245,7 +245,6 @@ static int bin_sort_t(Ctx &c, const Descriptor &d, const float *xys, const int *
     cudaStream_t s = c.stream;
     const unsigned tiles = d.tiles_x * d.tiles_y;
     int *err = (int *)c.small.p + SM_ERR_WORD;
-    unsigned *tickets = (unsigned *)c.small.p + SM_TICKET_WORD;
     // 1. depth order of the Gaussians (N-scale, 32-bit keys)
     if (c.ensure(c.sort_n_scratch, radix_scratch_bytes(n, 32))) return 1;
     bool in_b = false;
@@ -266,10 +265,9 @@ static int bin_sort_t(Ctx &c, const Descriptor &d, const float *xys, const int *
     BinParams bp{n, (float)(int)d.block_width, d.tiles_x, d.tiles_y};
     {
     StageScope ss(&c, ST_EMIT);
-    JSB_CUDA_OK(cudaMemsetAsync(c.chain.p, 0, chain_bytes, s));
     if (launch_emit<TileKey>(s, bp, order, (const unsigned *)c.counts.p, xys, radii,
                              (TileKey *)c.tkeys_a.p, (unsigned *)c.tvals_a.p,
-                             (unsigned long long *)c.chain.p, tickets, err))
+                             (unsigned *)c.chain.p))
         return 1;
     }
     // 3. stable sort on the live tile bits
@@ -343,19 +341,12 @@ static int project_fwd_impl(cudaStream_t stream, void **buf, const Descriptor &d
     p.tiles_x = d.tiles_x; p.tiles_y = d.tiles_y;
     const size_t chain_bytes = (size_t)ceil_div(n, 256) * 8 + 64;
     if (c->ensure(c->chain, chain_bytes)) return 1;
-    JSB_CUDA_OK(cudaMemsetAsync(c->chain.p, 0, chain_bytes, stream));
-    unsigned long long *chain = (unsigned long long *)c->chain.p;
-    unsigned *ticket = (unsigned *)((char *)c->chain.p + chain_bytes - 64);
-    if (!c->small.p) {
-        if (c->ensure(c->small, SMALL_BYTES)) return 1;
-        JSB_CUDA_OK(cudaMemsetAsync(c->small.p, 0, SMALL_BYTES, stream));
-    }
-    int *err = (int *)c->small.p + SM_ERR_WORD + 3;
     StageScope ss(c, ST_PROJECT_FWD);
     return launch_project_fwd(stream, p, (const float *)buf[0], (const float *)buf[1],
                               (const float *)buf[2], (const float *)buf[3], (float *)buf[4],
                               (float *)buf[5], (float *)buf[6], (int *)buf[7], (float *)buf[8],
-                              (float *)buf[9], (int *)buf[10], (int *)buf[11], chain, ticket, err);
+                              (float *)buf[9], (int *)buf[10], (int *)buf[11],
+                              (unsigned *)c->chain.p);
 }
 
 static int project_bwd_impl(cudaStream_t stream, void **buf, const Descriptor &d) {

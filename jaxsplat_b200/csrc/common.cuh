@@ -153,8 +153,14 @@ __device__ __forceinline__ void st_status(unsigned long long *p, unsigned long l
 }
 
 // Called by the first warp of a CTA that owns chain position `pos`.  Publishes the CTA's
-// aggregate, walks predecessors 32 at a time, publishes the inclusive prefix and returns the
-// exclusive prefix (valid in every lane).  `err` is set if the spin bound trips.
+// aggregate, walks predecessors and returns the exclusive prefix (valid in every lane), then
+// publishes the inclusive prefix.  `err` is set if the spin bound trips.
+//
+// Every CTA of a wave reaches this point at about the same time, so the nearest predecessor that
+// already holds an INCLUSIVE prefix is roughly "number of resident CTAs" positions back; the walk
+// is a chain of L2 round trips, so each round inspects a window of 32 x kChainWindow = 256
+// predecessors (8 independent loads per lane in flight) instead of 32.
+constexpr int kChainWindow = 1;  // wider windows measured slower on B200 (status polling traffic)
 __device__ __forceinline__ unsigned chain_exclusive_prefix(unsigned long long *status, int pos,
                                                            unsigned aggregate, int *err) {
     const int lane = threadIdx.x & 31;
@@ -164,24 +170,51 @@ __device__ __forceinline__ unsigned chain_exclusive_prefix(unsigned long long *s
     }
     if (lane == 0) st_status(status + pos, kFlagAggregate | aggregate);
     unsigned exclusive = 0;
-    int j = pos - 1;
+    int j = pos - 1;  // nearest predecessor of this round's window
     while (true) {
-        int idx = j - lane;
-        unsigned long long w = kFlagInclusive;  // positions before the chain start: prefix 0
+        // lane owns distances lane*W .. lane*W+W-1 from j (nearest first)
+        unsigned long long w[kChainWindow];
+        const int first = j - lane * kChainWindow;
+#pragma unroll
+        for (int u = 0; u < kChainWindow; ++u)
+            w[u] = (first - u >= 0) ? ld_status(status + (first - u)) : kFlagInclusive;
         int spins = 0;
-        if (idx >= 0) {
-            w = ld_status(status + idx);
-            while ((w >> 32) == 0) {
-                if (++spins > kSpinLimit) { *err = 1; w = kFlagInclusive; break; }
-                __nanosleep(20);
-                w = ld_status(status + idx);
+        bool pending = true;
+        while (pending) {
+            pending = false;
+#pragma unroll
+            for (int u = 0; u < kChainWindow; ++u) {
+                if ((w[u] >> 32) == 0) {
+                    w[u] = ld_status(status + (first - u));
+                    pending = pending || ((w[u] >> 32) == 0);
+                }
+            }
+            if (pending) {
+                if (++spins > kSpinLimit) {
+                    *err = 1;
+#pragma unroll
+                    for (int u = 0; u < kChainWindow; ++u)
+                        if ((w[u] >> 32) == 0) w[u] = kFlagInclusive;
+                    pending = false;
+                } else {
+                    __nanosleep(32);
+                }
             }
         }
-        unsigned incl = __ballot_sync(0xffffffffu, (w >> 32) == 2);
-        unsigned v = (unsigned)w;
+        // per-lane: sum up to and including the nearest inclusive entry
+        unsigned v = 0;
+        bool has_incl = false;
+#pragma unroll
+        for (int u = 0; u < kChainWindow; ++u) {
+            if (!has_incl) {
+                v += (unsigned)w[u];
+                has_incl = (w[u] >> 32) == 2;
+            }
+        }
+        const unsigned incl = __ballot_sync(0xffffffffu, has_incl);
         if (incl) {
-            int first = __ffs(incl) - 1;
-            if (lane > first) v = 0;
+            const int firstl = __ffs(incl) - 1;
+            if (lane > firstl) v = 0;
         }
         v += __shfl_xor_sync(0xffffffffu, v, 16);
         v += __shfl_xor_sync(0xffffffffu, v, 8);
@@ -190,7 +223,7 @@ __device__ __forceinline__ unsigned chain_exclusive_prefix(unsigned long long *s
         v += __shfl_xor_sync(0xffffffffu, v, 1);
         exclusive += v;
         if (incl) break;
-        j -= 32;
+        j -= 32 * kChainWindow;
     }
     if (lane == 0) st_status(status + pos, kFlagInclusive | (unsigned)(exclusive + aggregate));
     return exclusive;

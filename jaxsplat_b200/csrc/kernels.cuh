@@ -25,7 +25,7 @@ int launch_project_fwd(cudaStream_t stream, const ProjectFwdParams &p, const flo
                        const float *scales, const float *quats, const float *viewmat,
                        float *cov3ds, float *xys, float *depths, int *radii, float *conics,
                        float *compensation, int *num_tiles_hit, int *cum_tiles_hit,
-                       unsigned long long *chain, unsigned *ticket, int *err);
+                       unsigned *block_totals /* ceil(N/256) scratch words */);
 
 int launch_project_bwd(cudaStream_t stream, const ProjectBwdParams &p, const float *means3d,
                        const float *scales, const float *quats, const float *viewmat,
@@ -65,13 +65,18 @@ int launch_fingerprint(cudaStream_t stream, unsigned n, const float *xys, const 
 int launch_inclusive_scan_i32(cudaStream_t stream, const int *in, int *out, unsigned n,
                               unsigned long long *chain, unsigned *ticket, int *err);
 
+// in-place exclusive scan of nb CTA totals (single CTA), and cum[i] += totals[i / per_block]
+int launch_scan_totals(cudaStream_t stream, unsigned *totals, unsigned nb);
+int launch_add_block_prefix(cudaStream_t stream, int *cum, const unsigned *prefix, unsigned n,
+                            unsigned per_block);
+
 // emit: for Gaussians in depth order, write (tile id, gaussian id) for every covered tile,
-// row-major inside the box (reference forward.cu:135-179), at the running offset obtained by
-// a chained scan fused into the same launch.  TileKey is uint16_t (<= 65536 tiles) or uint32_t.
+// row-major inside the box (reference forward.cu:135-179); the per-CTA output offsets come from
+// a count kernel + a scan of the CTA totals (no chained look-back, see project.cu).  TileKey is uint16_t (<= 65536 tiles) or uint32_t.
 template <typename TileKey>
 int launch_emit(cudaStream_t stream, const BinParams &p, const unsigned *order,
                 const unsigned *tile_counts, const float *xys, const int *radii, TileKey *keys,
-                unsigned *vals, unsigned long long *chain, unsigned *ticket, int *err);
+                unsigned *vals, unsigned *block_totals /* ceil(N/256) scratch words */);
 
 // tile_bins[t] = (first, one-past-last) index of tile t in the sorted list; tiles without
 // intersections stay (0,0) (reference forward.cu:184-208 + memset ops.cu:482-488).

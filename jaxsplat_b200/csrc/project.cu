@@ -5,8 +5,10 @@
 // lib/ops.cu:607-643 (cumsum); backward: backward.cu:345-570, helpers.h:60-98,131-192.
 // Design (not a port): one CTA owns a 256-Gaussian slab, moves the AoS operands with 16-byte
 // coalesced transactions through shared memory, writes EVERY output element (no pre-zeroing
-// memsets) and produces cum_tiles_hit in the same launch with a chained look-back scan, so
-// num_tiles_hit never round-trips through HBM and no CUB temp allocation exists.
+// memsets) and computes the CTA-local part of cum_tiles_hit in the same launch; two tiny kernels
+// (scan of the CTA totals, add prefix) finish the scan.  A single-launch chained look-back scan
+// was measured slower on B200: ~half of the kernel's stall samples sat on the look-back wait,
+// because these CTAs live only a few microseconds.  No CUB, no temp allocation.
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -158,15 +160,11 @@ project_fwd_kernel(const ProjectFwdParams p, const float *__restrict__ means3d,
                    float2 *__restrict__ xys, float *__restrict__ depths, int *__restrict__ radii,
                    float *__restrict__ conics, float *__restrict__ compensation,
                    int *__restrict__ num_tiles_hit, int *__restrict__ cum_tiles_hit,
-                   unsigned long long *__restrict__ chain, unsigned *__restrict__ ticket,
-                   int *__restrict__ err) {
+                   unsigned *__restrict__ block_totals) {
     __shared__ __align__(16) float s_buf[PT * 9];
     __shared__ unsigned s_ws[PT / 32 + 1];
-    __shared__ unsigned s_bid, s_prefix;
     const int tid = threadIdx.x;
-    if (tid == 0) s_bid = atomicAdd(ticket, 1u);  // chain position == slab id (launch-order safe)
-    __syncthreads();
-    const unsigned bid = s_bid;
+    const unsigned bid = blockIdx.x;
     const long long base = (long long)bid * PT;
     const long long idx = base + tid;
     const long long n = p.num_points;
@@ -186,10 +184,7 @@ project_fwd_kernel(const ProjectFwdParams p, const float *__restrict__ means3d,
     }
     unsigned total;
     const unsigned excl = cta_exclusive_scan<PT>((unsigned)o.tiles, &total, s_ws);  // syncs
-    if (tid < 32) {
-        unsigned pre = chain_exclusive_prefix(chain, (int)bid, total, err);
-        if (tid == 0) s_prefix = pre;
-    }
+    if (tid == 0) block_totals[bid] = total;
     // stage AoS outputs (inputs are dead after the syncs inside the scan)
     float *s_cov = s_buf, *s_conic = s_buf + PT * 6;
     if (live) {
@@ -203,9 +198,10 @@ project_fwd_kernel(const ProjectFwdParams p, const float *__restrict__ means3d,
         radii[idx] = o.radius;
         compensation[idx] = o.comp;
         num_tiles_hit[idx] = o.tiles;
+        // CTA-local inclusive count; add_block_prefix_kernel adds the scanned CTA totals
+        cum_tiles_hit[idx] = (int)(excl + (unsigned)o.tiles);
     }
     __syncthreads();
-    if (live) cum_tiles_hit[idx] = (int)(s_prefix + excl + (unsigned)o.tiles);
     slab_store<6, PT>(s_cov, cov3ds, base * 6, n * 6);
     slab_store<3, PT>(s_conic, conics, base * 3, n * 3);
 }
@@ -404,16 +400,18 @@ int launch_project_fwd(cudaStream_t stream, const ProjectFwdParams &p, const flo
                        const float *scales, const float *quats, const float *viewmat,
                        float *cov3ds, float *xys, float *depths, int *radii, float *conics,
                        float *compensation, int *num_tiles_hit, int *cum_tiles_hit,
-                       unsigned long long *chain, unsigned *ticket, int *err) {
+                       unsigned *block_totals) {
     if (p.num_points == 0) return 0;
     const unsigned blocks = ceil_div(p.num_points, PT);
     project_fwd_kernel<<<blocks, PT, 0, stream>>>(
         p, means3d, scales, reinterpret_cast<const float4 *>(quats), viewmat, cov3ds,
         reinterpret_cast<float2 *>(xys), depths, radii, conics, compensation, num_tiles_hit,
-        cum_tiles_hit, chain, ticket, err);
+        cum_tiles_hit, block_totals);
     JSB_CUDA_OK(cudaGetLastError());
     note_launch();
-    return 0;
+    // cum_tiles_hit = CTA-local inclusive counts + exclusive scan of the CTA totals
+    if (launch_scan_totals(stream, block_totals, blocks)) return 1;
+    return launch_add_block_prefix(stream, cum_tiles_hit, block_totals, p.num_points, PT);
 }
 
 int launch_project_bwd(cudaStream_t stream, const ProjectBwdParams &p, const float *means3d,

@@ -85,13 +85,17 @@ __global__ void __launch_bounds__(256) radix_hist_scan_kernel(unsigned *__restri
 }
 
 // ---- one onesweep pass ------------------------------------------------------------------------
-template <typename KeyT, int RS_ITEMS>
+// CHAIN = true : onesweep (tile order from a ticket, cross-tile digit offsets by chained look-back)
+// CHAIN = false: downsweep of the upsweep/scan/downsweep variant: `status` holds, digit-major
+//                [256][tiles], the row-exclusive tile offsets and `gbase` the 256 row totals; no
+//                inter-CTA dependency, no spinning.
+template <typename KeyT, int RS_ITEMS, bool CHAIN>
 __global__ void __launch_bounds__(RS_THREADS)
 onesweep_pass_kernel(const KeyT *__restrict__ keys_in, const unsigned *__restrict__ vals_in,
                      KeyT *__restrict__ keys_out, unsigned *__restrict__ vals_out, unsigned n,
-                     int shift, const unsigned *__restrict__ gbase /*[256] exclusive*/,
-                     unsigned *__restrict__ status /*[tiles][256]*/,
-                     unsigned *__restrict__ ticket, int *__restrict__ err) {
+                     int shift, int live_bits, const unsigned *__restrict__ gbase /*[256]*/,
+                     unsigned *__restrict__ status, unsigned *__restrict__ ticket,
+                     int *__restrict__ err) {
     __shared__ unsigned s_whist[RS_WARPS * RADIX];  // per-warp digit counts -> exclusive over warps
     __shared__ unsigned s_binstart[RADIX];          // exclusive scan of the CTA histogram
     __shared__ unsigned s_goff[RADIX];              // global offset minus s_binstart (wraps)
@@ -102,10 +106,10 @@ onesweep_pass_kernel(const KeyT *__restrict__ keys_in, const unsigned *__restric
     __shared__ unsigned s_vals[RS_TILE];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+    if (CHAIN && tid == 0) s_tile = atomicAdd(ticket, 1u);
     for (int i = tid; i < RS_WARPS * RADIX; i += RS_THREADS) s_whist[i] = 0;
     __syncthreads();
-    const unsigned tile = s_tile;
+    const unsigned tile = CHAIN ? s_tile : blockIdx.x;
     const unsigned tile_base = tile * (unsigned)RS_TILE;
     const unsigned count = min((unsigned)RS_TILE, n - tile_base);
 
@@ -121,14 +125,25 @@ onesweep_pass_kernel(const KeyT *__restrict__ keys_in, const unsigned *__restric
         val[i] = (o < count) ? vals_in[tile_base + o] : 0u;
     }
 
-    // stable ranking inside the warp's chunk: memory order == (item, lane) order
+    // stable ranking inside the warp's chunk: memory order == (item, lane) order.
+    // Peers (lanes holding the same digit) come from one ballot per live digit bit: the native
+    // MATCH.ANY is data dependent on B200 -- ~2x slower when all 32 lanes differ, which is the
+    // common case for the low byte of consecutive tile ids (measured: 184 vs 101 us per pass).
     unsigned *wh = s_whist + warp * RADIX;
     const unsigned lt_mask = (1u << lane) - 1u;
 #pragma unroll
     for (int i = 0; i < RS_ITEMS; ++i) {
         const bool valid = (wbase + i * 32) < count;
         const unsigned d = valid ? (((unsigned)key[i] >> shift) & 255u) : 256u;
-        const unsigned peers = __match_any_sync(0xffffffffu, d);
+        unsigned peers = __ballot_sync(0xffffffffu, valid);
+        peers = valid ? peers : ~peers;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            if (b < live_bits) {
+                const unsigned m = __ballot_sync(0xffffffffu, (d >> b) & 1u);
+                peers &= ((d >> b) & 1u) ? m : ~m;
+            }
+        }
         const unsigned lower = peers & lt_mask;
         unsigned pre = 0;
         if (valid) pre = wh[d];
@@ -150,25 +165,31 @@ onesweep_pass_kernel(const KeyT *__restrict__ keys_in, const unsigned *__restric
     unsigned total;
     const unsigned binstart = cta_exclusive_scan<RS_THREADS>(cta_count, &total, s_ws);
     s_binstart[tid] = binstart;
-    {
+    if (!CHAIN) {
+        // digit base = exclusive scan of the row totals; tile offset precomputed by scan_rows
+        unsigned tot2;
+        const unsigned dbase = cta_exclusive_scan<RS_THREADS>(gbase[tid], &tot2, s_ws);
+        s_goff[tid] = dbase + status[(size_t)tid * gridDim.x + tile] - binstart;
+    } else {
         unsigned *st = status + (size_t)tile * RADIX + tid;
         unsigned excl = 0;
         if (tile == 0) {
             st_relaxed(st, ST_INC | cta_count);
         } else {
             st_relaxed(st, ST_AGG | cta_count);
-            // walk predecessors, 4 status loads in flight per step (the walk is a chain of L2
-            // round trips; speculative loads of older tiles cost nothing and cut it 4x)
+            // walk predecessors, LB status loads in flight per step (the walk is a chain of L2
+            // round trips; speculative loads of older tiles cost nothing and cut it LB-fold)
+            constexpr int LB = 4;
             int j = (int)tile - 1;
             int spins = 0;
             bool done = false;
             while (!done) {
-                unsigned w[4];
+                unsigned w[LB];
 #pragma unroll
-                for (int u = 0; u < 4; ++u)
+                for (int u = 0; u < LB; ++u)
                     w[u] = (j - u >= 0) ? ld_relaxed(status + (size_t)(j - u) * RADIX + tid) : ST_INC;
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < LB; ++u) {
                     if (done) break;
                     const unsigned f = w[u] & ~ST_MASK;
                     if (f == 0) {  // not published yet: retry from this tile
@@ -208,6 +229,59 @@ onesweep_pass_kernel(const KeyT *__restrict__ keys_in, const unsigned *__restric
     }
 }
 
+// ---- chain-free variant: per-tile digit histograms + row scan ---------------------------------
+template <typename KeyT>
+__global__ void __launch_bounds__(256)
+upsweep_kernel(const KeyT *__restrict__ keys, unsigned n, int shift,
+               unsigned *__restrict__ tile_hist /*[256][tiles]*/) {
+    __shared__ unsigned s_h[RADIX];
+    constexpr int TILE = RS_THREADS * 16;
+    constexpr int PER = 16 / sizeof(KeyT);
+    s_h[threadIdx.x] = 0;
+    __syncthreads();
+    const unsigned tile = blockIdx.x;
+    const unsigned base = tile * (unsigned)TILE;
+    const unsigned count = min((unsigned)TILE, n - base);
+    const KeyT *src = keys + base;  // base is a multiple of 4096 keys: 16-byte aligned
+    const unsigned nvec = count / PER;
+    for (unsigned v = threadIdx.x; v < nvec; v += 256) {
+        const uint4 q = __ldg(reinterpret_cast<const uint4 *>(src) + v);
+        unsigned k[PER];
+        if (sizeof(KeyT) == 2) {
+            k[0] = q.x & 0xffffu; k[1] = q.x >> 16; k[2 % PER] = q.y & 0xffffu; k[3 % PER] = q.y >> 16;
+            k[4 % PER] = q.z & 0xffffu; k[5 % PER] = q.z >> 16; k[6 % PER] = q.w & 0xffffu; k[7 % PER] = q.w >> 16;
+        } else {
+            k[0] = q.x; k[1] = q.y; k[2] = q.z; k[3] = q.w;
+        }
+#pragma unroll
+        for (int e = 0; e < PER; ++e) atomicAdd(&s_h[(k[e] >> shift) & 255u], 1u);
+    }
+    for (unsigned i = nvec * PER + threadIdx.x; i < count; i += 256)
+        atomicAdd(&s_h[((unsigned)src[i] >> shift) & 255u], 1u);
+    __syncthreads();
+    tile_hist[(size_t)threadIdx.x * gridDim.x + tile] = s_h[threadIdx.x];
+}
+
+// one CTA per digit: exclusive scan of its row of per-tile counts in place, row total out.
+// Each thread owns a contiguous chunk (serial sum, one CTA scan of the chunk sums, serial write).
+__global__ void __launch_bounds__(256)
+scan_rows_kernel(unsigned *__restrict__ tile_hist, unsigned tiles, unsigned *__restrict__ row_totals) {
+    __shared__ unsigned s_ws[256 / 32 + 1];
+    unsigned *row = tile_hist + (size_t)blockIdx.x * tiles;
+    const unsigned per = (tiles + 255u) / 256u;
+    const unsigned b0 = min(tiles, threadIdx.x * per), b1 = min(tiles, b0 + per);
+    unsigned sum = 0;
+    for (unsigned i = b0; i < b1; ++i) sum += row[i];
+    unsigned total;
+    unsigned run = cta_exclusive_scan<256>(sum, &total, s_ws);
+    for (unsigned i = b0; i < b1; ++i) {
+        const unsigned v = row[i];
+        row[i] = run;
+        run += v;
+    }
+    if (threadIdx.x == 0) row_totals[blockIdx.x] = total;
+}
+
 inline int items_for(unsigned n) { (void)n; return 16; }  // 4/thread measured slower even at N=1M
 inline unsigned num_tiles_of(unsigned n) { return ceil_div(n, (unsigned)(RS_THREADS * items_for(n))); }
 inline int passes_of(int bits) { return (bits + 7) / 8; }
@@ -216,8 +290,13 @@ inline int passes_of(int bits) { return (bits + 7) / 8; }
 
 // scratch layout: [ghist: MAX_PASSES*256 u32][tickets: MAX_PASSES u32 (padded to 16)]
 //                 [status: passes * tiles * 256 u32]
+// n at or above this uses upsweep/scan/downsweep (no inter-CTA spinning); below it the sort is
+// latency bound either way and the single-kernel-per-pass onesweep wins on launch count
+constexpr unsigned kChainFreeMin = 1u << 21;
+
 size_t radix_scratch_bytes(unsigned n, int bits) {
     const size_t head = (MAX_PASSES * RADIX + 16) * sizeof(unsigned);
+    if (n >= kChainFreeMin) return head + (size_t)num_tiles_of(n) * RADIX * sizeof(unsigned);
     return head + (size_t)passes_of(bits) * num_tiles_of(n) * RADIX * sizeof(unsigned);
 }
 
@@ -240,6 +319,27 @@ int radix_sort_pairs(cudaStream_t stream, KeyT *keys_a, KeyT *keys_b, unsigned *
     unsigned *ghist = reinterpret_cast<unsigned *>(scratch);
     unsigned *tickets = ghist + MAX_PASSES * RADIX;
     unsigned *status = tickets + 16;
+    if (n >= kChainFreeMin) {
+        // upsweep (per-tile digit counts) -> row scan -> downsweep; scratch needs no zeroing
+        KeyT *kin = keys_a, *kout = keys_b;
+        unsigned *vin = vals_a, *vout = vals_b;
+        unsigned *row_totals = ghist;
+        for (int ps = 0; ps < passes; ++ps) {
+            upsweep_kernel<KeyT><<<tiles, 256, 0, stream>>>(kin, n, 8 * ps, status);
+            JSB_CUDA_OK(cudaGetLastError());
+            scan_rows_kernel<<<RADIX, 256, 0, stream>>>(status, tiles, row_totals);
+            JSB_CUDA_OK(cudaGetLastError());
+            onesweep_pass_kernel<KeyT, 16, false><<<tiles, RS_THREADS, 0, stream>>>(
+                kin, vin, kout, vout, n, 8 * ps, min(8, bits - 8 * ps), row_totals, status, nullptr,
+                err);
+            JSB_CUDA_OK(cudaGetLastError());
+            note_launch(3);
+            KeyT *tk = kin; kin = kout; kout = tk;
+            unsigned *tv = vin; vin = vout; vout = tv;
+            *result_in_b = !*result_in_b;
+        }
+        return 0;
+    }
     JSB_CUDA_OK(cudaMemsetAsync(scratch, 0, radix_scratch_bytes(n, bits), stream));
     const unsigned hist_blocks = min(ceil_div(n, 256u * 32u), 148u * 8u);
     radix_hist_kernel<KeyT><<<hist_blocks, 256, 0, stream>>>(keys_a, n, passes, ghist);
@@ -252,12 +352,12 @@ int radix_sort_pairs(cudaStream_t stream, KeyT *keys_a, KeyT *keys_b, unsigned *
     unsigned *vin = vals_a, *vout = vals_b;
     for (int ps = 0; ps < passes; ++ps) {
         if (items_for(n) == 16)
-            onesweep_pass_kernel<KeyT, 16><<<tiles, RS_THREADS, 0, stream>>>(
-                kin, vin, kout, vout, n, 8 * ps, ghist + ps * RADIX,
+            onesweep_pass_kernel<KeyT, 16, true><<<tiles, RS_THREADS, 0, stream>>>(
+                kin, vin, kout, vout, n, 8 * ps, min(8, bits - 8 * ps), ghist + ps * RADIX,
                 status + (size_t)ps * tiles * RADIX, tickets + ps, err);
         else
-            onesweep_pass_kernel<KeyT, 4><<<tiles, RS_THREADS, 0, stream>>>(
-                kin, vin, kout, vout, n, 8 * ps, ghist + ps * RADIX,
+            onesweep_pass_kernel<KeyT, 4, true><<<tiles, RS_THREADS, 0, stream>>>(
+                kin, vin, kout, vout, n, 8 * ps, min(8, bits - 8 * ps), ghist + ps * RADIX,
                 status + (size_t)ps * tiles * RADIX, tickets + ps, err);
         JSB_CUDA_OK(cudaGetLastError());
     note_launch();

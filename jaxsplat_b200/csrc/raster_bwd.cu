@@ -39,7 +39,9 @@ __device__ __forceinline__ void pair_grad(bool valid, float alpha, float vis, fl
     // invalid lanes: alpha = vis = 0 and ra = 1 make every partial exactly 0 and keep T / buf
     alpha = valid ? alpha : 0.f;
     vis = valid ? vis : 0.f;
-    const float ra = valid ? __fdividef(1.f, 1.f - alpha) : 1.f;  // gradient path: approx rcp is enough
+    float ra;  // gradient path: MUFU.RCP (1 ulp) is enough; 1-alpha is in [0.01, 1]
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ra) : "f"(1.f - alpha));
+    ra = valid ? ra : 1.f;
     T = T * ra;
     const float fac = alpha * T;
     o[0] = v_out.x * fac;
@@ -69,7 +71,7 @@ __device__ __forceinline__ void pair_grad(bool valid, float alpha, float vis, fl
 }
 
 template <bool CULL>
-__global__ void __launch_bounds__(RB, 4)
+__global__ void __launch_bounds__(RB, 3)
 raster_bwd16_kernel(const RasterParams p, const unsigned *__restrict__ ids_sorted,
                     const int2 *__restrict__ tile_bins, const SplatRecord *__restrict__ records,
                     const float *__restrict__ background, const float *__restrict__ final_Ts,
@@ -187,7 +189,7 @@ raster_bwd16_kernel(const RasterParams p, const unsigned *__restrict__ ids_sorte
                             (((p2.x + p2.y) + (p2.z + p2.w)) + ((p3.x + p3.y) + (p3.z + p3.w)));
                 }
                 total += __shfl_xor_sync(0xffffffffu, total, 1);
-                if (writer) atomicAdd(out_base + (size_t)sId[t] * out_stride, total);
+                if (writer) atomicAdd(out_base + sId[t] * (unsigned)out_stride, total);
             }
         }
     }
