@@ -65,6 +65,13 @@ JSB200_API int jsb200_make_descriptor(unsigned num_points, unsigned img_h, unsig
                            float cx, float cy, float glob_scale, float clip_thresh,
                            unsigned block_width, char *out);
 
+/* Extension (no reference equivalent): restricts the rasterize calls that use this descriptor to
+ * the tile rows [tile_row_begin, tile_row_end) -- screen-tile-row sharding of one large frame
+ * across GPUs with the Gaussians replicated.  Stored in the descriptor's 4 pad bytes; a band of 0
+ * (what make_descriptor writes) means the full frame.  Only pixels of the band are written;
+ * final_idx then indexes the band's own sorted list.  Returns 0 on success. */
+JSB200_API int jsb200_set_descriptor_band(char *desc80, unsigned tile_row_begin, unsigned tile_row_end);
+
 /* replaces ops::sort_and_bin (lib/ops.h:31-41, lib/ops.cu:645-793): binning only; writes the
  * depth-sorted gaussian ids (num_intersects i32) and tile_bins (tiles x int2) to device buffers.
  * Returns 0 on success. */

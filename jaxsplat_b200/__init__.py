@@ -13,18 +13,20 @@ from ._rasterize import rasterize
 
 
 def render(means3d, scales, quats, colors, opacities, *, viewmat, background, img_shape, f, c,
-           glob_scale, clip_thresh, block_size=16):
+           glob_scale, clip_thresh, block_size=16, tile_rows=None):
     """Renders 3D Gaussians to a 2D image differentiably (reference jaxsplat/__init__.py:6-70).
 
     means3d (N,3), scales (N,3), quats (N,4) normalised (w,x,y,z), colors (N,3), opacities (N,1);
     viewmat (4,4) row-major world->camera, background (3,), img_shape (H,W), f (fx,fy),
     c (cx,cy).  Differentiable w.r.t. the five positional arrays.  Returns (H,W,3) float32.
+    tile_rows=(begin, end) (extension, default None = reference behaviour) renders only that band
+    of tile rows -- the unit of screen-tile-row sharding across GPUs (multiview.tile_row_bands).
     """
     (xys, depths, radii, conics, _num_tiles_hit, cum_tiles_hit) = project(
         means3d, scales, quats, viewmat, img_shape=img_shape, f=f, c=c, glob_scale=glob_scale,
         clip_thresh=clip_thresh, block_width=block_size)
     return rasterize(colors, opacities, background, xys, depths, radii, conics, cum_tiles_hit,
-                     img_shape=img_shape, block_width=block_size)
+                     img_shape=img_shape, block_width=block_size, tile_rows=tile_rows)
 
 
 __all__ = ["render", "project", "rasterize"]

@@ -35,6 +35,15 @@ def make_descriptor(num_points: int, img_shape, f, c, glob_scale: float, clip_th
     return buf.raw
 
 
+def with_band(descriptor: bytes, tile_row_begin: int, tile_row_end: int) -> bytes:
+    """Extension: restrict a rasterize descriptor to tile rows [begin, end) (screen-tile-row
+    sharding; include/jaxsplat_b200.h: jsb200_set_descriptor_band)."""
+    buf = ctypes.create_string_buffer(descriptor, 80)
+    if _lib.lib().jsb200_set_descriptor_band(buf, int(tile_row_begin), int(tile_row_end)) != 0:
+        _lib.check_error("set_descriptor_band")
+    return buf.raw
+
+
 def registrations() -> Dict[str, object]:
     """reference lib/ffi.cu:4-13: name -> PyCapsule("xla._CUSTOM_CALL_TARGET")."""
     L = _lib.lib()

@@ -19,6 +19,7 @@ EXPORTS = (
     "jsb200_rasterize_fwd",
     "jsb200_rasterize_bwd",
     "jsb200_make_descriptor",
+    "jsb200_set_descriptor_band",
     "jsb200_sort_and_bin",
     "jsb200_cumsum",
     "jsb200_last_error",
@@ -57,6 +58,8 @@ def lib() -> ctypes.CDLL:
         fn.restype = None
     L.jsb200_make_descriptor.argtypes = [u, u, u, f, f, f, f, f, f, u, ctypes.c_char_p]
     L.jsb200_make_descriptor.restype = i
+    L.jsb200_set_descriptor_band.argtypes = [ctypes.c_char_p, u, u]
+    L.jsb200_set_descriptor_band.restype = i
     L.jsb200_sort_and_bin.argtypes = [vp, cp, sz, u, vp, vp, vp, vp, vp, vp]
     L.jsb200_sort_and_bin.restype = i
     L.jsb200_cumsum.argtypes = [vp, vp, vp, i]

@@ -98,8 +98,17 @@ def project_bwd(mean3ds, scales, quats, viewmat, cov3ds, xys, radii, conics, com
     return tuple(outs)
 
 
+def _raster_desc(table, n, img_shape, block_width, band):
+    # the reference's rasterize lowerings pass zeros for f, c, glob_scale, clip_thresh
+    # (jaxsplat/_rasterize/lowering.py:28-36)
+    d = _desc(table, n, img_shape, (0.0, 0.0), (0.0, 0.0), 0.0, 0.0, block_width)
+    if band is not None:
+        d = _ffi.with_band(d, band[0], band[1])  # extension, this library only
+    return d
+
+
 def rasterize_fwd(colors, opacities, background, xys, depths, radii, conics, cum_tiles_hit, *,
-                  num_points, img_shape, block_width,
+                  num_points, img_shape, block_width, band=None, out=None,
                   table: Optional[_ffi.CustomCallTable] = None):
     table = _resolve(table)
     n, dev = num_points, colors.device
@@ -108,19 +117,18 @@ def rasterize_fwd(colors, opacities, background, xys, depths, radii, conics, cum
            _f32(background, (3,), "background"), _f32(xys, (n, 2), "xys"),
            _f32(depths, (n, 1), "depths"), _i32(radii, (n, 1), "radii"),
            _f32(conics, (n, 3), "conics"), _i32(cum_tiles_hit, (n, 1), "cum_tiles_hit")]
-    outs = [_out((H, W, 1), torch.float32, dev), _out((H, W, 1), torch.int32, dev),
-            _out((H, W, 3), torch.float32, dev)]
-    # the reference's rasterize lowerings pass zeros for f, c, glob_scale, clip_thresh
-    # (jaxsplat/_rasterize/lowering.py:28-36)
-    table.call("rasterize_fwd", ins, outs,
-               _desc(table, n, img_shape, (0.0, 0.0), (0.0, 0.0), 0.0, 0.0, block_width))
+    # `out`: caller-provided (final_Ts, final_idx, img) so several tile-row bands can fill one frame
+    outs = list(out) if out is not None else [
+        _out((H, W, 1), torch.float32, dev), _out((H, W, 1), torch.int32, dev),
+        _out((H, W, 3), torch.float32, dev)]
+    table.call("rasterize_fwd", ins, outs, _raster_desc(table, n, img_shape, block_width, band))
     # (final_Ts, final_idx, img)
     return tuple(outs)
 
 
 def rasterize_bwd(colors, opacities, background, xys, depths, radii, conics, cum_tiles_hit,
                   final_Ts, final_idx, v_img, v_img_alpha, *, num_points, img_shape, block_width,
-                  table: Optional[_ffi.CustomCallTable] = None):
+                  band=None, table: Optional[_ffi.CustomCallTable] = None):
     table = _resolve(table)
     n, dev = num_points, colors.device
     H, W = img_shape
@@ -133,7 +141,6 @@ def rasterize_bwd(colors, opacities, background, xys, depths, radii, conics, cum
     outs = [_out((n, 3), torch.float32, dev), _out((n, 1), torch.float32, dev),
             _out((n, 2), torch.float32, dev), _out((n, 2), torch.float32, dev),
             _out((n, 3), torch.float32, dev)]
-    table.call("rasterize_bwd", ins, outs,
-               _desc(table, n, img_shape, (0.0, 0.0), (0.0, 0.0), 0.0, 0.0, block_width))
+    table.call("rasterize_bwd", ins, outs, _raster_desc(table, n, img_shape, block_width, band))
     # (v_colors, v_opacity, v_xy, v_xy_abs, v_conic)
     return tuple(outs)

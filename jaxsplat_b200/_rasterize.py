@@ -7,7 +7,7 @@ opacities, xys, conics), ``None`` for (background, depths, radii, cum_tiles_hit)
 from __future__ import annotations
 
 from dataclasses import dataclass
-from typing import Tuple
+from typing import Optional, Tuple
 
 import torch
 
@@ -20,10 +20,11 @@ class RasterizeDescriptor:
     num_points: int
     img_shape: Tuple[int, int]
     block_width: int
+    band: Optional[Tuple[int, int]] = None  # extension: tile rows [begin, end) owned by this call
 
     def kwargs(self):
         return dict(num_points=self.num_points, img_shape=self.img_shape,
-                    block_width=self.block_width)
+                    block_width=self.block_width, band=self.band)
 
 
 class _Rasterize(torch.autograd.Function):
@@ -55,10 +56,14 @@ class _Rasterize(torch.autograd.Function):
 
 
 def rasterize(colors, opacities, background, xys, depths, radii, conics, cum_tiles_hit, *,
-              img_shape, block_width):
-    """Rasterizes projected Gaussians; returns the (H, W, 3) image."""
+              img_shape, block_width, tile_rows=None):
+    """Rasterizes projected Gaussians; returns the (H, W, 3) image.
+
+    tile_rows=(begin, end) is an extension for screen-tile-row sharding: only those tile rows are
+    rasterised (and differentiated); pixels outside the band are left unwritten."""
     desc = RasterizeDescriptor(num_points=colors.shape[0], img_shape=tuple(img_shape),
-                               block_width=int(block_width))
+                               block_width=int(block_width),
+                               band=None if tile_rows is None else (int(tile_rows[0]), int(tile_rows[1])))
     img, _img_alpha = _Rasterize.apply(desc, colors, opacities, background, xys, depths, radii,
                                        conics, cum_tiles_hit)
     return img

@@ -72,7 +72,9 @@ bin_prep_kernel(const BinParams p, const float2 *__restrict__ xys,
             unsigned x0, x1, y0, y1;
             tile_bbox(xy.x, xy.y, (float)radius, p.block_width_f, p.tiles_x, p.tiles_y, x0, x1,
                       y0, y1);
-            cnt = (x1 - x0) * (y1 - y0);
+            y0 = max(y0, p.band_y0);
+            y1 = min(y1, p.band_y1);
+            cnt = y1 > y0 ? (x1 - x0) * (y1 - y0) : 0u;
             key = __float_as_uint(depth);
         }
         if (WRITE) {
@@ -235,6 +237,7 @@ emit_kernel(const BinParams p, const unsigned *__restrict__ order,
             unsigned x0, x1, y0, y1;
             tile_bbox(xy.x, xy.y, (float)radius, p.block_width_f, p.tiles_x, p.tiles_y, x0, x1,
                       y0, y1);
+            y0 = max(y0, p.band_y0);  // cnt > 0 guarantees a non-empty clamped box
             s_tile0[tid] = y0 * p.tiles_x + x0;
             s_w[tid] = x1 - x0;
         }

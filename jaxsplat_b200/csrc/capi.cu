@@ -94,7 +94,7 @@ struct Ctx {
     bool cache_valid = false;
     bool cache_has_records = false;  // false after a sort_and_bin-only call (no appearance data)
     unsigned long long cache_fp = 0;
-    unsigned cache_n = 0, cache_tiles = 0, cache_bw = 0, cache_tiles_x = 0;
+    unsigned cache_n = 0, cache_tiles = 0, cache_bw = 0, cache_tiles_x = 0, cache_band = 0;
     unsigned long long cache_I = 0;
     unsigned *cache_ids = nullptr;  // points into tvals_a or tvals_b
     size_t total_bytes = 0;
@@ -179,6 +179,18 @@ static const Descriptor *unpack(const char *opaque, size_t len) {
     return reinterpret_cast<const Descriptor *>(opaque);
 }
 
+// Screen-tile-row band carried in the descriptor's 4 pad bytes (an extension: the reference
+// leaves them uninitialised): low 16 bits = first tile row, high 16 bits = one past the last.
+// 0 means the full frame, which is what every reference-compatible descriptor holds.
+static void band_of(const Descriptor &d, unsigned *y0, unsigned *y1) {
+    *y0 = 0;
+    *y1 = d.tiles_y;
+    if (d.pad != 0) {
+        *y0 = d.pad & 0xffffu;
+        *y1 = d.pad >> 16;
+    }
+}
+
 static int tile_bits(unsigned tiles) {
     int b = 1;
     while ((1ull << b) < tiles) ++b;
@@ -214,7 +226,8 @@ static int bin_prepare(Ctx &c, const Descriptor &d, const float *xys, const floa
     // sticky so that a device-side failure of the PREVIOUS call is seen at this call's sync
     JSB_CUDA_OK(cudaMemsetAsync(c.small.p, 0, 16, s));
     JSB_CUDA_OK(cudaMemsetAsync((char *)c.small.p + 32, 0, 32, s));
-    BinParams bp{n, (float)(int)d.block_width, d.tiles_x, d.tiles_y};
+    BinParams bp{n, (float)(int)d.block_width, d.tiles_x, d.tiles_y, 0, 0};
+    band_of(d, &bp.band_y0, &bp.band_y1);
     unsigned long long *small64 = (unsigned long long *)c.small.p;
     {
     StageScope ss(&c, ST_BIN_PREP);
@@ -262,7 +275,8 @@ static int bin_sort_t(Ctx &c, const Descriptor &d, const float *xys, const int *
     if (c.ensure(c.tvals_a, (size_t)I * 4) || c.ensure(c.tvals_b, (size_t)I * 4)) return 1;
     const size_t chain_bytes = (size_t)ceil_div(n, 256) * 8;
     if (c.ensure(c.chain, chain_bytes)) return 1;
-    BinParams bp{n, (float)(int)d.block_width, d.tiles_x, d.tiles_y};
+    BinParams bp{n, (float)(int)d.block_width, d.tiles_x, d.tiles_y, 0, 0};
+    band_of(d, &bp.band_y0, &bp.band_y1);
     {
     StageScope ss(&c, ST_EMIT);
     if (launch_emit<TileKey>(s, bp, order, (const unsigned *)c.counts.p, xys, radii,
@@ -309,6 +323,7 @@ static int bin_sort(Ctx &c, const Descriptor &d, const float *xys, const int *ra
     c.cache_tiles = tiles;
     c.cache_tiles_x = d.tiles_x;
     c.cache_bw = d.block_width;
+    c.cache_band = d.pad;
     c.cache_I = I;
     g_stats[2].fetch_add(1);
     g_stats[4].store(I);
@@ -319,7 +334,7 @@ static bool cache_hit(const Ctx &c, const Descriptor &d, unsigned long long I,
                       unsigned long long fp) {
     return !g_disable_cache && c.cache_valid && c.cache_has_records && c.cache_fp == fp && c.cache_I == I &&
            c.cache_n == d.num_points && c.cache_tiles == d.tiles_x * d.tiles_y &&
-           c.cache_tiles_x == d.tiles_x && c.cache_bw == d.block_width;
+           c.cache_tiles_x == d.tiles_x && c.cache_bw == d.block_width && c.cache_band == d.pad;
 }
 
 // ---- op bodies ---------------------------------------------------------------------------------
@@ -373,6 +388,7 @@ static RasterParams raster_params(const Descriptor &d) {
     rp.img_w = d.img_w; rp.img_h = d.img_h;
     rp.tiles_x = d.tiles_x; rp.tiles_y = d.tiles_y;
     rp.block_width = d.block_width;
+    band_of(d, &rp.band_y0, &rp.band_y1);
     return rp;
 }
 
@@ -384,6 +400,12 @@ static int check_raster_desc(const Descriptor &d) {
     if (d.tiles_x != ceil_div(d.img_w, d.block_width) || d.tiles_y != ceil_div(d.img_h, d.block_width)) {
         set_error("descriptor tile grid %ux%u inconsistent with image %ux%u / block %u", d.tiles_x,
                   d.tiles_y, d.img_w, d.img_h, d.block_width);
+        return 1;
+    }
+    unsigned y0, y1;
+    band_of(d, &y0, &y1);
+    if (y0 >= y1 || y1 > d.tiles_y) {
+        set_error("descriptor tile-row band [%u,%u) invalid for %u tile rows", y0, y1, d.tiles_y);
         return 1;
     }
     return 0;
@@ -519,6 +541,16 @@ int jsb200_make_descriptor(unsigned num_points, unsigned img_h, unsigned img_w, 
     d.tiles_z = 1;
     d.bdx = block_width; d.bdy = block_width; d.bdz = 1;
     memcpy(out, &d, sizeof d);
+    return 0;
+}
+
+int jsb200_set_descriptor_band(char *desc, unsigned tile_row_begin, unsigned tile_row_end) {
+    if (!desc || tile_row_begin >= tile_row_end || tile_row_end > 0xffffu) {
+        jsb::set_error("set_descriptor_band: invalid band [%u,%u)", tile_row_begin, tile_row_end);
+        return 1;
+    }
+    const unsigned v = (tile_row_begin & 0xffffu) | (tile_row_end << 16);
+    memcpy(desc + 76, &v, 4);
     return 0;
 }
 

@@ -45,6 +45,7 @@ struct BinParams {
     unsigned num_points;
     float block_width_f;
     unsigned tiles_x, tiles_y;
+    unsigned band_y0, band_y1;  // tile rows [band_y0, band_y1) this call owns (full frame: 0, tiles_y)
 };
 
 // prep: pack records, depth keys (0xFFFFFFFF for radii<=0), per-Gaussian tile counts,
@@ -102,6 +103,7 @@ struct RasterParams {
     unsigned img_w, img_h;
     unsigned tiles_x, tiles_y;
     unsigned block_width;
+    unsigned band_y0, band_y1;  // tile rows rasterised by this call (screen-tile-row sharding)
 };
 
 int launch_raster_fwd(cudaStream_t stream, const RasterParams &p, const unsigned *ids_sorted,

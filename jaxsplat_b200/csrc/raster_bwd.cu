@@ -71,7 +71,7 @@ __device__ __forceinline__ void pair_grad(bool valid, float alpha, float vis, fl
 }
 
 template <bool CULL>
-__global__ void __launch_bounds__(RB, 3)
+__global__ void __launch_bounds__(RB, 4)
 raster_bwd16_kernel(const RasterParams p, const unsigned *__restrict__ ids_sorted,
                     const int2 *__restrict__ tile_bins, const SplatRecord *__restrict__ records,
                     const float *__restrict__ background, const float *__restrict__ final_Ts,
@@ -89,7 +89,7 @@ raster_bwd16_kernel(const RasterParams p, const unsigned *__restrict__ ids_sorte
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     float *red = sRed + warp * 11 * RED_STRIDE;
-    const unsigned tile = blockIdx.x;
+    const unsigned tile = p.band_y0 * p.tiles_x + blockIdx.x;
     const unsigned tile_y = tile / p.tiles_x, tile_x = tile - tile_y * p.tiles_x;
     const unsigned j = tile_x * 16 + (warp & 1) * kRectW + (lane & 7);
     const unsigned i = tile_y * 16 + (warp >> 1) * kRectH + (lane >> 3);
@@ -204,8 +204,8 @@ __global__ void raster_bwd_generic_kernel(
     const float *__restrict__ v_out_alpha_img, float *__restrict__ v_xy,
     float *__restrict__ v_xy_abs, float *__restrict__ v_conic, float *__restrict__ v_colors,
     float *__restrict__ v_opacity) {
-    const unsigned tile = blockIdx.y * p.tiles_x + blockIdx.x;
-    const unsigned i = blockIdx.y * blockDim.y + threadIdx.y;
+    const unsigned tile = (blockIdx.y + p.band_y0) * p.tiles_x + blockIdx.x;
+    const unsigned i = (blockIdx.y + p.band_y0) * blockDim.y + threadIdx.y;
     const unsigned j = blockIdx.x * blockDim.x + threadIdx.x;
     if (!(i < p.img_h && j < p.img_w)) return;
     const float px = (float)j + 0.5f, py = (float)i + 0.5f;
@@ -254,7 +254,7 @@ int launch_raster_bwd(cudaStream_t stream, const RasterParams &p, const unsigned
                       const float *final_Ts, const int *final_idx, const float *v_out,
                       const float *v_out_alpha, float *v_xy, float *v_xy_abs, float *v_conic,
                       float *v_colors, float *v_opacity) {
-    const unsigned tiles = p.tiles_x * p.tiles_y;
+    const unsigned tiles = p.tiles_x * (p.band_y1 - p.band_y0);
     if (tiles == 0) return 0;
     if (p.block_width == 16) {
         if (g_disable_cull)
@@ -266,7 +266,7 @@ int launch_raster_bwd(cudaStream_t stream, const RasterParams &p, const unsigned
                 p, ids_sorted, tile_bins, records, background, final_Ts, final_idx, v_out,
                 v_out_alpha, v_xy, v_xy_abs, v_conic, v_colors, v_opacity);
     } else {
-        dim3 grid(p.tiles_x, p.tiles_y), block(p.block_width, p.block_width);
+        dim3 grid(p.tiles_x, p.band_y1 - p.band_y0), block(p.block_width, p.block_width);
         raster_bwd_generic_kernel<<<grid, block, 0, stream>>>(
             p, ids_sorted, tile_bins, records, background, final_Ts, final_idx, v_out, v_out_alpha,
             v_xy, v_xy_abs, v_conic, v_colors, v_opacity);

@@ -29,7 +29,7 @@ namespace {
 constexpr int RB = 256;  // batch size == threads per CTA
 
 template <bool CULL>
-__global__ void __launch_bounds__(RB)
+__global__ void __launch_bounds__(RB, 5)
 raster_fwd16_kernel(const RasterParams p, const unsigned *__restrict__ ids_sorted,
                     const int2 *__restrict__ tile_bins, const SplatRecord *__restrict__ records,
                     const float *__restrict__ background, float *__restrict__ final_Ts,
@@ -40,7 +40,7 @@ raster_fwd16_kernel(const RasterParams p, const unsigned *__restrict__ ids_sorte
     __shared__ unsigned char sMask[RB];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const unsigned tile = blockIdx.x;
+    const unsigned tile = p.band_y0 * p.tiles_x + blockIdx.x;
     const unsigned tile_y = tile / p.tiles_x, tile_x = tile - tile_y * p.tiles_x;
     const unsigned j = tile_x * 16 + (warp & 1) * kRectW + (lane & 7);   // pixel column
     const unsigned i = tile_y * 16 + (warp >> 1) * kRectH + (lane >> 3); // pixel row
@@ -135,8 +135,8 @@ __global__ void raster_fwd_generic_kernel(const RasterParams p,
     __shared__ float sC[RB];
     const int bs = blockDim.x * blockDim.y;
     const int tid = threadIdx.y * blockDim.x + threadIdx.x;
-    const unsigned tile = blockIdx.y * p.tiles_x + blockIdx.x;
-    const unsigned i = blockIdx.y * blockDim.y + threadIdx.y;
+    const unsigned tile = (blockIdx.y + p.band_y0) * p.tiles_x + blockIdx.x;
+    const unsigned i = (blockIdx.y + p.band_y0) * blockDim.y + threadIdx.y;
     const unsigned j = blockIdx.x * blockDim.x + threadIdx.x;
     const float px = (float)j + 0.5f, py = (float)i + 0.5f;
     const bool inside = (i < p.img_h) && (j < p.img_w);
@@ -185,11 +185,11 @@ __global__ void raster_fwd_generic_kernel(const RasterParams p,
     }
 }
 
-__global__ void fill_background_kernel(const float *__restrict__ background, size_t pixels,
-                                       float *__restrict__ final_Ts, int *__restrict__ final_idx,
-                                       float *__restrict__ out_img) {
+__global__ void fill_background_kernel(const float *__restrict__ background, size_t first,
+                                       size_t pixels, float *__restrict__ final_Ts,
+                                       int *__restrict__ final_idx, float *__restrict__ out_img) {
     const float bg0 = __ldg(background), bg1 = __ldg(background + 1), bg2 = __ldg(background + 2);
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < pixels;
+    for (size_t i = first + blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < first + pixels;
          i += (size_t)gridDim.x * blockDim.x) {
         final_Ts[i] = 0.f;
         final_idx[i] = 0;
@@ -206,7 +206,7 @@ bool g_disable_cull = false;  // test hook (capi: jsb200_set_option)
 int launch_raster_fwd(cudaStream_t stream, const RasterParams &p, const unsigned *ids_sorted,
                       const int2 *tile_bins, const SplatRecord *records, const float *background,
                       float *final_Ts, int *final_idx, float *out_img) {
-    const unsigned tiles = p.tiles_x * p.tiles_y;
+    const unsigned tiles = p.tiles_x * (p.band_y1 - p.band_y0);
     if (tiles == 0) return 0;
     if (p.block_width == 16) {
         if (g_disable_cull)
@@ -218,7 +218,7 @@ int launch_raster_fwd(cudaStream_t stream, const RasterParams &p, const unsigned
                                                                 background, final_Ts, final_idx,
                                                                 out_img);
     } else {
-        dim3 grid(p.tiles_x, p.tiles_y), block(p.block_width, p.block_width);
+        dim3 grid(p.tiles_x, p.band_y1 - p.band_y0), block(p.block_width, p.block_width);
         raster_fwd_generic_kernel<<<grid, block, 0, stream>>>(p, ids_sorted, tile_bins, records,
                                                               background, final_Ts, final_idx,
                                                               out_img);
@@ -230,11 +230,13 @@ int launch_raster_fwd(cudaStream_t stream, const RasterParams &p, const unsigned
 
 int launch_fill_background(cudaStream_t stream, const RasterParams &p, const float *background,
                            float *final_Ts, int *final_idx, float *out_img) {
-    const size_t pixels = (size_t)p.img_w * p.img_h;
-    if (pixels == 0) return 0;
+    const size_t row0 = (size_t)p.band_y0 * p.block_width;
+    const size_t row1 = min((size_t)p.img_h, (size_t)p.band_y1 * p.block_width);
+    if (row1 <= row0 || p.img_w == 0) return 0;
+    const size_t first = row0 * p.img_w, pixels = (row1 - row0) * p.img_w;
     const unsigned blocks = (unsigned)((pixels + 255) / 256 < 148 * 8 ? (pixels + 255) / 256 : 148 * 8);
-    fill_background_kernel<<<blocks, 256, 0, stream>>>(background, pixels, final_Ts, final_idx,
-                                                       out_img);
+    fill_background_kernel<<<blocks, 256, 0, stream>>>(background, first, pixels, final_Ts,
+                                                       final_idx, out_img);
     JSB_CUDA_OK(cudaGetLastError());
     note_launch();
     return 0;

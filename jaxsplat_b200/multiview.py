@@ -18,6 +18,30 @@ def shard_views(num_views: int, rank: int, world: int) -> List[int]:
     return list(range(rank, num_views, world))
 
 
+def tile_row_bands(tiles_y: int, world: int, weights=None) -> List[tuple]:
+    """Screen-tile-row sharding of ONE large frame (BASELINE config 5): contiguous
+    bands of tile rows, one per rank, Gaussians replicated.  `weights` (per tile row, e.g. the
+    number of intersections in that row) balances the bands by work instead of by rows."""
+    if weights is None:
+        weights = [1.0] * tiles_y
+    total = float(sum(weights))
+    bands, start, acc = [], 0, 0.0
+    for r in range(world):
+        target = total * (r + 1) / world
+        end = start
+        while end < tiles_y and (acc + weights[end] <= target + 1e-9 or end == start):
+            acc += weights[end]
+            end += 1
+        # leave at least one row for every remaining rank
+        end = min(end, tiles_y - (world - 1 - r))
+        if r == world - 1:
+            end = tiles_y
+        end = max(end, start + 1) if start < tiles_y else start
+        bands.append((start, end))
+        start = end
+    return bands
+
+
 class FlatParams:
     """the five parameter arrays as views into one flat buffer, with their gradients as views
     into a second flat buffer so the reduction is a single collective call"""

@@ -121,3 +121,12 @@ def test_product_never_imports_the_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text, f
                 assert "liboracle" not in text and "oracle/" not in text, f
+
+
+def test_descriptor_band_extension():
+    d = _ffi.make_descriptor(10, (1080, 1920), (1.0, 1.0), (0.0, 0.0), 1.0, 0.01, 16)
+    b = _ffi.with_band(d, 17, 34)
+    assert b[:76] == d[:76]
+    assert struct.unpack("<I", b[76:])[0] == (17 | (34 << 16))
+    with pytest.raises(RuntimeError):
+        _ffi.with_band(d, 5, 5)

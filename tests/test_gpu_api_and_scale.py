@@ -158,3 +158,32 @@ def test_live_reference_parity(cfg):
     for k in Gr:
         ok, err, scale = grad_close(G.npy(Go[k]), G.npy(Gr[k]), rel=1e-4)
         assert ok, (k, err, scale)
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_tile_row_bands_reproduce_the_full_frame(world):
+    """screen-tile-row sharding: the union of the bands is the full image bit for bit, and the
+    band gradients sum to the full-frame gradient"""
+    from jaxsplat_b200 import multiview
+    s = synthetic.make_config("C2", num_points=40000)
+    sc = s.to(G.DEV)
+    H, W = s.img_shape
+    target = torch.rand((H, W, 3), generator=torch.Generator().manual_seed(7)).to(G.DEV)
+    full_img, _, full_grads = _render_loss_and_grads(s, target)
+    tiles_y = (H + 15) // 16
+    img = torch.full((H, W, 3), float("nan"), device=G.DEV)
+    acc = [torch.zeros_like(p) for p in sc.params()]
+    for (r0, r1) in multiview.tile_row_bands(tiles_y, world):
+        params = [p.clone().requires_grad_(True) for p in sc.params()]
+        band_img = jsb.render(*params, tile_rows=(r0, r1), **sc.render_kwargs())
+        y0, y1 = r0 * 16, min(H, r1 * 16)
+        img[y0:y1] = band_img[y0:y1].detach()
+        # the loss of the full frame restricted to this band (same normalisation)
+        loss = ((band_img[y0:y1] - target[y0:y1]) ** 2).sum() / (H * W * 3)
+        loss.backward()
+        for a, p in zip(acc, params):
+            a += p.grad
+    assert torch.equal(img, full_img)
+    for a, g in zip(acc, full_grads):  # different float summation order: stated gradient tolerance
+        ok, err, scale = grad_close(G.npy(a), G.npy(g), rel=1e-4)
+        assert ok, (err, scale)

@@ -71,3 +71,19 @@ def test_two_rank_gradient_equals_single_process(tmp_path):
     # gradient views alias the flat buffer
     for g, p in zip(flat.grads(), flat.params):
         assert g.data_ptr() == p.grad.data_ptr()
+
+
+def test_tile_row_bands_partition():
+    for tiles_y in (1, 7, 68, 135):
+        for world in (1, 2, 3, 8):
+            if world > tiles_y:
+                continue
+            bands = multiview.tile_row_bands(tiles_y, world)
+            assert len(bands) == world and bands[0][0] == 0 and bands[-1][1] == tiles_y
+            for (a0, a1), (b0, b1) in zip(bands, bands[1:]):
+                assert a1 == b0 and a1 > a0
+            assert bands[-1][1] > bands[-1][0]
+    w = [1] * 20
+    w[3] = 50
+    bands = multiview.tile_row_bands(20, 4, weights=w)
+    assert bands[0][0] == 0 and bands[-1][1] == 20 and all(b > a for a, b in bands)
