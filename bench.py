@@ -95,14 +95,14 @@ class ClockSampler:
 
 def algorithmic_bytes(stage, N, I, P, T):
     """DESIGN.md 'algorithmic bytes per unit' (SURVEY.md 8d), per launch of the stage"""
-    tile_passes = 2 if T > 256 else 1
+    G = min(148 * 6, max(1, (I + 2047) // 2048))  # chunks of the counting distribution
     return {
         "project_fwd": N * 108,
-        "bin_prep": N * (44 + 48 + 12),
+        "bin_prep": N * (44 + 48 + 4 + 4 + 8),
         "depth_sort": N * (4 + 4 * 2 * 8),
-        "emit": N * 20 + I * 6,
-        "tile_sort": I * (2 + tile_passes * 2 * 6),
-        "bin_edges": I * 2 + T * 8,
+        "emit": N * (4 + 8 + 16 + 16) + I * 6,
+        "tile_offsets": I * 2 + 5 * G * T * 4 + T * 8,
+        "tile_scatter": I * (6 + 4) + G * T * 4,
         "raster_fwd": P * 20 + I * 52,
         "raster_bwd": P * 24 + I * (4 + 40 + 44),
         "project_bwd": N * 188,

@@ -103,8 +103,8 @@ JSB200_API int jsb200_set_option(const char *key, int value);
 JSB200_API long long jsb200_debug_binning(jsb200_stream_t stream, const float *depths, int *ids_sorted,
                                int *tile_bins, long long *keys64_sorted);
 /* Per-stage device time, measured with CUDA events on `stream` while option "timing" is 1.
- * Synchronises the stream.  Stage order: project_fwd, bin_prep, depth_sort, emit, tile_sort,
- * bin_edges, raster_fwd, raster_bwd, project_bwd.  ms_out9 / calls_out9 receive accumulated
+ * Synchronises the stream.  Stage order: project_fwd, bin_prep, depth_sort, emit, tile_scatter,
+ * tile_offsets, raster_fwd, raster_bwd, project_bwd.  ms_out9 / calls_out9 receive accumulated
  * milliseconds and span counts; reset != 0 clears the accumulators.  Returns 0 on success. */
 JSB200_API int jsb200_get_stage_times(jsb200_stream_t stream, double *ms_out9,
                                       unsigned long long *calls_out9, int reset);

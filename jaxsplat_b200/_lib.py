@@ -108,7 +108,7 @@ def set_option(key: str, value: int) -> None:
         check_error("set_option")
 
 
-STAGES = ("project_fwd", "bin_prep", "depth_sort", "emit", "tile_sort", "bin_edges", "raster_fwd",
+STAGES = ("project_fwd", "bin_prep", "depth_sort", "emit", "tile_scatter", "tile_offsets", "raster_fwd",
           "raster_bwd", "project_bwd")
 
 

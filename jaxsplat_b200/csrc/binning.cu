@@ -36,7 +36,7 @@ bin_prep_kernel(const BinParams p, const float2 *__restrict__ xys,
                 const float *__restrict__ conics, const float *__restrict__ opacities,
                 const float *__restrict__ colors, SplatRecord *__restrict__ records,
                 unsigned *__restrict__ depth_keys, unsigned *__restrict__ ids,
-                unsigned *__restrict__ tile_counts, unsigned long long *__restrict__ fingerprint) {
+                uint2 *__restrict__ box_by_id, unsigned long long *__restrict__ fingerprint) {
     __shared__ __align__(16) float s_buf[BT * 6];
     const int tid = threadIdx.x;
     const long long base = (long long)blockIdx.x * BT;
@@ -68,19 +68,23 @@ bin_prep_kernel(const BinParams p, const float2 *__restrict__ xys,
             }
         }
         unsigned key = 0xFFFFFFFFu;
+        uint2 box = make_uint2(0u, 0u);  // {x0 | y0 << 16, width | height << 16}, band-clamped
         if (radius > 0) {
             unsigned x0, x1, y0, y1;
             tile_bbox(xy.x, xy.y, (float)radius, p.block_width_f, p.tiles_x, p.tiles_y, x0, x1,
                       y0, y1);
             y0 = max(y0, p.band_y0);
             y1 = min(y1, p.band_y1);
-            cnt = y1 > y0 ? (x1 - x0) * (y1 - y0) : 0u;
+            if (y1 > y0 && x1 > x0) {
+                cnt = (x1 - x0) * (y1 - y0);
+                box = make_uint2(x0 | (y0 << 16), (x1 - x0) | ((y1 - y0) << 16));
+            }
             key = __float_as_uint(depth);
         }
         if (WRITE) {
             depth_keys[g] = key;
             ids[g] = (unsigned)g;
-            tile_counts[g] = cnt;
+            box_by_id[g] = box;
         }
     }
 #pragma unroll
@@ -161,25 +165,6 @@ inclusive_scan_kernel(const int *__restrict__ in, int *__restrict__ out, unsigne
     }
 }
 
-// per-CTA number of (tile, Gaussian) pairs of 256 depth-ordered Gaussians
-__global__ void __launch_bounds__(BT)
-emit_count_kernel(unsigned n, const unsigned *__restrict__ order,
-                  const unsigned *__restrict__ tile_counts, unsigned *__restrict__ block_totals) {
-    __shared__ unsigned s_w[BT / 32];
-    const long long pos = (long long)blockIdx.x * BT + threadIdx.x;
-    unsigned c = pos < (long long)n ? tile_counts[order[pos]] : 0u;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = c;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        unsigned t = 0;
-#pragma unroll
-        for (int w = 0; w < BT / 32; ++w) t += s_w[w];
-        block_totals[blockIdx.x] = t;
-    }
-}
-
 // in-place exclusive scan of the CTA totals: a single CTA walks them 1024 at a time
 __global__ void __launch_bounds__(1024) scan_totals_kernel(unsigned *__restrict__ totals, unsigned nb) {
     __shared__ unsigned s_ws[1024 / 32 + 1];
@@ -209,142 +194,6 @@ add_block_prefix_kernel(int *__restrict__ cum, const unsigned *__restrict__ pref
         reinterpret_cast<int4 *>(cum)[v] = q;
     } else {
         for (unsigned k = i; k < n && k < i + 4; ++k) cum[k] += add;
-    }
-}
-
-template <typename TileKey>
-__global__ void __launch_bounds__(BT)
-emit_kernel(const BinParams p, const unsigned *__restrict__ order,
-            const unsigned *__restrict__ tile_counts, const float2 *__restrict__ xys,
-            const int *__restrict__ radii, TileKey *__restrict__ keys,
-            unsigned *__restrict__ vals, const unsigned *__restrict__ block_prefix) {
-    __shared__ unsigned s_off[BT + 1];
-    __shared__ unsigned s_tile0[BT];   // first tile id of the box
-    __shared__ unsigned s_w[BT];       // box width in tiles
-    __shared__ unsigned s_g[BT];
-    __shared__ unsigned s_ws[BT / 32 + 1];
-    const int tid = threadIdx.x;
-    const unsigned bid = blockIdx.x;
-    const long long pos = (long long)bid * BT + tid;
-    unsigned cnt = 0;
-    if (pos < (long long)p.num_points) {
-        const unsigned g = order[pos];
-        cnt = tile_counts[g];
-        s_g[tid] = g;
-        if (cnt) {
-            const float2 xy = __ldg(xys + g);
-            const int radius = __ldg(radii + g);
-            unsigned x0, x1, y0, y1;
-            tile_bbox(xy.x, xy.y, (float)radius, p.block_width_f, p.tiles_x, p.tiles_y, x0, x1,
-                      y0, y1);
-            y0 = max(y0, p.band_y0);  // cnt > 0 guarantees a non-empty clamped box
-            s_tile0[tid] = y0 * p.tiles_x + x0;
-            s_w[tid] = x1 - x0;
-        }
-    }
-    unsigned total;
-    const unsigned excl = cta_exclusive_scan<BT>(cnt, &total, s_ws);
-    s_off[tid] = excl;
-    if (tid == 0) s_off[BT] = total;
-    __syncthreads();
-    // Output: every thread owns 8-element chunks aligned in GLOBAL index space, so full chunks
-    // leave as 16-byte vector stores; inside a chunk the (gaussian, row, col) cursor is advanced
-    // incrementally (one binary search + one division per chunk instead of per element).
-    const unsigned long long g_begin = block_prefix[bid], g_end = g_begin + total;
-    const unsigned long long first_chunk = g_begin >> 3;
-    const unsigned num_chunks = (unsigned)(((g_end + 7) >> 3) - first_chunk);
-    for (unsigned c = tid; c < num_chunks; c += BT) {
-        const unsigned long long cg = (first_chunk + c) << 3;
-        const unsigned kb = cg > g_begin ? (unsigned)(cg - g_begin) : 0u;
-        const unsigned ke = (cg + 8 < g_end) ? (unsigned)(cg + 8 - g_begin) : total;
-        if (kb >= ke) continue;
-        int lo = 0, hi = BT;  // invariant: s_off[lo] <= kb < s_off[hi]
-#pragma unroll
-        for (int st = 0; st < 8; ++st) {
-            const int mid = (lo + hi) >> 1;
-            if (s_off[mid] <= kb) lo = mid; else hi = mid;
-        }
-        unsigned next_off = s_off[lo + 1];
-        unsigned w = s_w[lo], g = s_g[lo];
-        const unsigned j = kb - s_off[lo];
-        const unsigned row = j / w;
-        unsigned col = j - row * w;
-        unsigned tile = s_tile0[lo] + row * p.tiles_x + col;
-        TileKey kk[8];
-        unsigned vv[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const unsigned k = kb + e;
-            if (k < ke) {
-                if (k >= next_off) {
-                    do { ++lo; next_off = s_off[lo + 1]; } while (k >= next_off);
-                    w = s_w[lo]; g = s_g[lo]; tile = s_tile0[lo]; col = 0;
-                }
-                kk[e] = (TileKey)tile;
-                vv[e] = g;
-                ++col; ++tile;
-                if (col == w) { col = 0; tile += p.tiles_x - w; }
-            }
-        }
-        const bool full = (cg >= g_begin) && (ke - kb == 8);
-        if (full) {
-            if (sizeof(TileKey) == 2) {
-                uint4 pk;
-                pk.x = (unsigned)kk[0] | ((unsigned)kk[1] << 16);
-                pk.y = (unsigned)kk[2] | ((unsigned)kk[3] << 16);
-                pk.z = (unsigned)kk[4] | ((unsigned)kk[5] << 16);
-                pk.w = (unsigned)kk[6] | ((unsigned)kk[7] << 16);
-                *reinterpret_cast<uint4 *>(keys + cg) = pk;
-            } else {
-                *reinterpret_cast<uint4 *>(keys + cg) = make_uint4(kk[0], kk[1], kk[2], kk[3]);
-                *reinterpret_cast<uint4 *>(keys + cg + 4) = make_uint4(kk[4], kk[5], kk[6], kk[7]);
-            }
-            *reinterpret_cast<uint4 *>(vals + cg) = make_uint4(vv[0], vv[1], vv[2], vv[3]);
-            *reinterpret_cast<uint4 *>(vals + cg + 4) = make_uint4(vv[4], vv[5], vv[6], vv[7]);
-        } else {
-#pragma unroll
-            for (int e = 0; e < 8; ++e)
-                if (kb + e < ke) {
-                    keys[g_begin + kb + e] = kk[e];
-                    vals[g_begin + kb + e] = vv[e];
-                }
-        }
-    }
-}
-
-// 8 sorted keys per thread (one 16-byte load for uint16 keys) + the key just before them
-template <typename TileKey>
-__global__ void __launch_bounds__(256)
-bin_edges_kernel(const TileKey *__restrict__ keys, unsigned n, int2 *__restrict__ bins) {
-    const unsigned base = (blockIdx.x * 256u + threadIdx.x) * 8u;
-    if (base >= n) return;
-    unsigned k[8];
-    const unsigned m = min(8u, n - base);
-    if (m == 8) {
-        if (sizeof(TileKey) == 2) {
-            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(keys + base));
-            k[0] = v.x & 0xffffu; k[1] = v.x >> 16; k[2] = v.y & 0xffffu; k[3] = v.y >> 16;
-            k[4] = v.z & 0xffffu; k[5] = v.z >> 16; k[6] = v.w & 0xffffu; k[7] = v.w >> 16;
-        } else {
-            const uint4 v0 = __ldg(reinterpret_cast<const uint4 *>(keys + base));
-            const uint4 v1 = __ldg(reinterpret_cast<const uint4 *>(keys + base + 4));
-            k[0] = v0.x; k[1] = v0.y; k[2] = v0.z; k[3] = v0.w;
-            k[4] = v1.x; k[5] = v1.y; k[6] = v1.z; k[7] = v1.w;
-        }
-    } else {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) k[e] = (unsigned)e < m ? (unsigned)keys[base + e] : 0u;
-    }
-    unsigned prev = base ? (unsigned)keys[base - 1] : 0xffffffffu;
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-        if ((unsigned)e < m) {
-            const unsigned i = base + e, cur = k[e];
-            if (i == 0) bins[cur].x = 0;
-            else if (prev != cur) { bins[prev].y = (int)i; bins[cur].x = (int)i; }
-            if (i == n - 1) bins[cur].y = (int)n;
-            prev = cur;
-        }
     }
 }
 
@@ -392,35 +241,17 @@ int launch_fingerprint(cudaStream_t stream, unsigned n, const float *xys, const 
 int launch_bin_prep(cudaStream_t stream, const BinParams &p, const float *xys,
                     const float *depths, const int *radii, const float *conics,
                     const float *opacities, const float *colors, SplatRecord *records,
-                    unsigned *depth_keys, unsigned *ids, unsigned *tile_counts,
+                    unsigned *depth_keys, unsigned *ids, uint2 *box_by_id,
                     unsigned long long *fingerprint, bool write) {
     if (p.num_points == 0) return 0;
     if (write)
         bin_prep_kernel<true><<<ceil_div(p.num_points, BT), BT, 0, stream>>>(
             p, reinterpret_cast<const float2 *>(xys), depths, radii, conics, opacities, colors,
-            records, depth_keys, ids, tile_counts, fingerprint);
+            records, depth_keys, ids, box_by_id, fingerprint);
     else
         bin_prep_kernel<false><<<ceil_div(p.num_points, BT), BT, 0, stream>>>(
             p, reinterpret_cast<const float2 *>(xys), depths, radii, conics, opacities, colors,
-            records, depth_keys, ids, tile_counts, fingerprint);
-    JSB_CUDA_OK(cudaGetLastError());
-    note_launch();
-    return 0;
-}
-
-template <typename TileKey>
-int launch_emit(cudaStream_t stream, const BinParams &p, const unsigned *order,
-                const unsigned *tile_counts, const float *xys, const int *radii, TileKey *keys,
-                unsigned *vals, unsigned *block_totals) {
-    if (p.num_points == 0) return 0;
-    const unsigned blocks = ceil_div(p.num_points, BT);
-    emit_count_kernel<<<blocks, BT, 0, stream>>>(p.num_points, order, tile_counts, block_totals);
-    JSB_CUDA_OK(cudaGetLastError());
-    note_launch();
-    if (launch_scan_totals(stream, block_totals, blocks)) return 1;
-    emit_kernel<TileKey><<<blocks, BT, 0, stream>>>(
-        p, order, tile_counts, reinterpret_cast<const float2 *>(xys), radii, keys, vals,
-        block_totals);
+            records, depth_keys, ids, box_by_id, fingerprint);
     JSB_CUDA_OK(cudaGetLastError());
     note_launch();
     return 0;
@@ -442,25 +273,6 @@ int launch_add_block_prefix(cudaStream_t stream, int *cum, const unsigned *prefi
     note_launch();
     return 0;
 }
-template int launch_emit<uint16_t>(cudaStream_t, const BinParams &, const unsigned *,
-                                   const unsigned *, const float *, const int *, uint16_t *,
-                                   unsigned *, unsigned *);
-template int launch_emit<uint32_t>(cudaStream_t, const BinParams &, const unsigned *,
-                                   const unsigned *, const float *, const int *, uint32_t *,
-                                   unsigned *, unsigned *);
-
-template <typename TileKey>
-int launch_bin_edges(cudaStream_t stream, const TileKey *sorted_keys, unsigned n,
-                     int2 *tile_bins) {
-    if (n == 0) return 0;
-    bin_edges_kernel<TileKey><<<ceil_div(n, 256 * 8), 256, 0, stream>>>(sorted_keys, n, tile_bins);
-    JSB_CUDA_OK(cudaGetLastError());
-    note_launch();
-    return 0;
-}
-template int launch_bin_edges<uint16_t>(cudaStream_t, const uint16_t *, unsigned, int2 *);
-template int launch_bin_edges<uint32_t>(cudaStream_t, const uint32_t *, unsigned, int2 *);
-
 int launch_rebuild_keys64(cudaStream_t stream, const int2 *tile_bins, unsigned num_tiles,
                           const unsigned *ids_sorted, const float *depths, long long *keys64) {
     if (num_tiles == 0) return 0;

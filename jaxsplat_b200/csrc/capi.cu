@@ -85,9 +85,9 @@ struct Ctx {
     cudaStream_t stream = nullptr;
     std::mutex mu;
     // N-scale
-    DevBuf records, dkeys_a, dkeys_b, ids_a, ids_b, counts, sort_n_scratch, chain;
+    DevBuf records, dkeys_a, dkeys_b, ids_a, ids_b, box_by_id, boxes, sort_n_scratch, chain;
     // I-scale
-    DevBuf tkeys_a, tkeys_b, tvals_a, tvals_b, sort_i_scratch;
+    DevBuf tile_keys, tile_vals, tile_ids, tile_scratch;
     DevBuf bins, small;  // small: [fingerprint u64][total u64][err int x4][tickets u32 x8]
     unsigned long long *h_pinned = nullptr;  // [fingerprint][total][err...]
     // binning cache
@@ -96,7 +96,7 @@ struct Ctx {
     unsigned long long cache_fp = 0;
     unsigned cache_n = 0, cache_tiles = 0, cache_bw = 0, cache_tiles_x = 0, cache_band = 0;
     unsigned long long cache_I = 0;
-    unsigned *cache_ids = nullptr;  // points into tvals_a or tvals_b
+    unsigned *cache_ids = nullptr;  // points into tile_ids
     size_t total_bytes = 0;
     StageTimes times;
 
@@ -118,9 +118,9 @@ struct Ctx {
         return 0;
     }
     void release() {
-        DevBuf *all[] = {&records, &dkeys_a, &dkeys_b, &ids_a, &ids_b, &counts, &sort_n_scratch,
-                         &chain, &tkeys_a, &tkeys_b, &tvals_a, &tvals_b, &sort_i_scratch, &bins,
-                         &small};
+        DevBuf *all[] = {&records, &dkeys_a, &dkeys_b, &ids_a, &ids_b, &box_by_id, &boxes,
+                         &sort_n_scratch, &chain, &tile_keys, &tile_vals, &tile_ids, &tile_scratch,
+                         &bins, &small};
         for (DevBuf *b : all) {
             if (b->p) cudaFree(b->p);
             b->p = nullptr;
@@ -221,7 +221,7 @@ static int bin_prepare(Ctx &c, const Descriptor &d, const float *xys, const floa
     if (c.ensure(c.records, (size_t)n * sizeof(SplatRecord))) return 1;
     if (c.ensure(c.dkeys_a, (size_t)n * 4) || c.ensure(c.dkeys_b, (size_t)n * 4)) return 1;
     if (c.ensure(c.ids_a, (size_t)n * 4) || c.ensure(c.ids_b, (size_t)n * 4)) return 1;
-    if (c.ensure(c.counts, (size_t)n * 4)) return 1;
+    if (c.ensure(c.box_by_id, (size_t)n * sizeof(uint2))) return 1;
     // zero fingerprint/total (bytes 0..16) and tickets (32..64); the error words (16..32) are
     // sticky so that a device-side failure of the PREVIOUS call is seen at this call's sync
     JSB_CUDA_OK(cudaMemsetAsync(c.small.p, 0, 16, s));
@@ -233,7 +233,7 @@ static int bin_prepare(Ctx &c, const Descriptor &d, const float *xys, const floa
     StageScope ss(&c, ST_BIN_PREP);
     if (write && launch_bin_prep(s, bp, xys, depths, radii, conics, opac, colors,
                                  (SplatRecord *)c.records.p, (unsigned *)c.dkeys_a.p,
-                                 (unsigned *)c.ids_a.p, (unsigned *)c.counts.p, small64, true))
+                                 (unsigned *)c.ids_a.p, (uint2 *)c.box_by_id.p, small64, true))
         return 1;
     if (launch_fingerprint(s, n, xys, depths, radii, conics, opac, colors, small64)) return 1;
     }
@@ -252,8 +252,7 @@ static int bin_prepare(Ctx &c, const Descriptor &d, const float *xys, const floa
 }
 
 template <typename TileKey>
-static int bin_sort_t(Ctx &c, const Descriptor &d, const float *xys, const int *radii,
-                      unsigned long long I) {
+static int bin_sort_impl(Ctx &c, const Descriptor &d, unsigned long long I) {
     const unsigned n = d.num_points;
     cudaStream_t s = c.stream;
     const unsigned tiles = d.tiles_x * d.tiles_y;
@@ -269,44 +268,44 @@ static int bin_sort_t(Ctx &c, const Descriptor &d, const float *xys, const int *
         return 1;
     }
     const unsigned *order = (const unsigned *)(in_b ? c.ids_b.p : c.ids_a.p);
-    // 2. emit (tile, id) pairs in depth order
-    if (c.ensure(c.tkeys_a, (size_t)I * sizeof(TileKey)) || c.ensure(c.tkeys_b, (size_t)I * sizeof(TileKey)))
-        return 1;
-    if (c.ensure(c.tvals_a, (size_t)I * 4) || c.ensure(c.tvals_b, (size_t)I * 4)) return 1;
-    const size_t chain_bytes = (size_t)ceil_div(n, 256) * 8;
-    if (c.ensure(c.chain, chain_bytes)) return 1;
     BinParams bp{n, (float)(int)d.block_width, d.tiles_x, d.tiles_y, 0, 0};
     band_of(d, &bp.band_y0, &bp.band_y1);
+    const unsigned chunks = tile_lists_chunks(I);
+    if (c.ensure(c.boxes, (size_t)n * sizeof(uint4))) return 1;
+    if (c.ensure(c.chain, (size_t)ceil_div(n, 256) * 8 + 64)) return 1;
+    if (c.ensure(c.tile_keys, (size_t)I * sizeof(TileKey) + 16)) return 1;
+    if (c.ensure(c.tile_vals, (size_t)I * 4 + 16) || c.ensure(c.tile_ids, (size_t)I * 4)) return 1;
+    if (c.ensure(c.tile_scratch, tile_lists_scratch_words(bp, chunks) * sizeof(unsigned))) return 1;
+    if (c.ensure(c.bins, (size_t)tiles * sizeof(int2))) return 1;
+    // 2. (tile, id) pairs in depth order
     {
     StageScope ss(&c, ST_EMIT);
-    if (launch_emit<TileKey>(s, bp, order, (const unsigned *)c.counts.p, xys, radii,
-                             (TileKey *)c.tkeys_a.p, (unsigned *)c.tvals_a.p,
-                             (unsigned *)c.chain.p))
+    if (launch_box_gather(s, n, order, (const uint2 *)c.box_by_id.p, (uint4 *)c.boxes.p,
+                          (unsigned *)c.chain.p))
+        return 1;
+    if (launch_emit<TileKey>(s, bp, (const uint4 *)c.boxes.p, (unsigned *)c.chain.p,
+                             (TileKey *)c.tile_keys.p, (unsigned *)c.tile_vals.p))
         return 1;
     }
-    // 3. stable sort on the live tile bits
-    const int bits = tile_bits(tiles);
-    if (c.ensure(c.sort_i_scratch, radix_scratch_bytes((unsigned)I, bits))) return 1;
+    // 3. per-(chunk, tile) counts -> run offsets and tile bins
     {
-    StageScope ss(&c, ST_TILE_SORT);
-    if (radix_sort_pairs<TileKey>(s, (TileKey *)c.tkeys_a.p, (TileKey *)c.tkeys_b.p,
-                                  (unsigned *)c.tvals_a.p, (unsigned *)c.tvals_b.p, (unsigned)I,
-                                  bits, c.sort_i_scratch.p, err, &in_b))
-        return 1;
-    }
-    // 4. tile bins
-    if (c.ensure(c.bins, (size_t)tiles * sizeof(int2))) return 1;
     StageScope ss(&c, ST_BIN_EDGES);
     JSB_CUDA_OK(cudaMemsetAsync(c.bins.p, 0, (size_t)tiles * sizeof(int2), s));
-    if (launch_bin_edges<TileKey>(s, (const TileKey *)(in_b ? c.tkeys_b.p : c.tkeys_a.p),
-                                  (unsigned)I, (int2 *)c.bins.p))
+    if (launch_tile_offsets<TileKey>(s, bp, chunks, I, (const TileKey *)c.tile_keys.p,
+                                     (unsigned *)c.tile_scratch.p, (int2 *)c.bins.p))
         return 1;
-    c.cache_ids = (unsigned *)(in_b ? c.tvals_b.p : c.tvals_a.p);
+    }
+    // 4. ids into their per-tile runs, in depth order
+    StageScope ss(&c, ST_TILE_SORT);
+    if (launch_tile_scatter<TileKey>(s, bp, chunks, I, (const TileKey *)c.tile_keys.p,
+                                     (const unsigned *)c.tile_vals.p,
+                                     (const unsigned *)c.tile_scratch.p, (unsigned *)c.tile_ids.p))
+        return 1;
+    c.cache_ids = (unsigned *)c.tile_ids.p;
     return 0;
 }
 
-static int bin_sort(Ctx &c, const Descriptor &d, const float *xys, const int *radii,
-                    unsigned long long I, unsigned long long fp) {
+static int bin_sort(Ctx &c, const Descriptor &d, unsigned long long I, unsigned long long fp) {
     if (I >= (1ull << 30)) {
         set_error("num_intersects=%llu exceeds the supported 2^30", I);
         return 1;
@@ -314,8 +313,7 @@ static int bin_sort(Ctx &c, const Descriptor &d, const float *xys, const int *ra
     const unsigned tiles = d.tiles_x * d.tiles_y;
     c.cache_valid = false;
     c.cache_has_records = false;
-    int rc = tiles <= 65536 ? bin_sort_t<uint16_t>(c, d, xys, radii, I)
-                            : bin_sort_t<uint32_t>(c, d, xys, radii, I);
+    int rc = tiles <= 65536 ? bin_sort_impl<uint16_t>(c, d, I) : bin_sort_impl<uint32_t>(c, d, I);
     if (rc) return rc;
     c.cache_valid = true;
     c.cache_fp = fp;
@@ -402,6 +400,10 @@ static int check_raster_desc(const Descriptor &d) {
                   d.tiles_y, d.img_w, d.img_h, d.block_width);
         return 1;
     }
+    if (d.tiles_x > 8192u || d.tiles_y > 65535u) {
+        set_error("tile grid %ux%u exceeds the supported 8192 x 65535", d.tiles_x, d.tiles_y);
+        return 1;
+    }
     unsigned y0, y1;
     band_of(d, &y0, &y1);
     if (y0 >= y1 || y1 > d.tiles_y) {
@@ -432,7 +434,7 @@ static int rasterize_fwd_impl(cudaStream_t stream, void **buf, const Descriptor 
     }
     // the forward always bins afresh (a training loop changes the parameters every step); only
     // the matching backward may reuse this result
-    if (bin_sort(*c, d, (const float *)buf[3], (const int *)buf[5], I, fp)) return 1;
+    if (bin_sort(*c, d, I, fp)) return 1;
     c->cache_has_records = true;
     StageScope ss(c, ST_RASTER_FWD);
     return launch_raster_fwd(stream, rp, c->cache_ids, (const int2 *)c->bins.p,
@@ -471,7 +473,7 @@ static int rasterize_bwd_impl(cudaStream_t stream, void **buf, const Descriptor 
                         &fp, /*write=*/true))
             return 1;
         if (I == 0) return 0;
-        if (bin_sort(*c, d, (const float *)buf[3], (const int *)buf[5], I, fp)) return 1;
+        if (bin_sort(*c, d, I, fp)) return 1;
         c->cache_has_records = true;
     }
     StageScope ss(c, ST_RASTER_BWD);
@@ -582,7 +584,7 @@ int jsb200_sort_and_bin(jsb200_stream_t stream_, const char *opaque, size_t len,
             JSB_CUDA_OK(cudaMemsetAsync(tile_bins, 0, (size_t)tiles * 8, stream));
             return 0;
         }
-        if (jsb::bin_sort(*c, d, xys, radii, I, fp)) return 1;
+        if (jsb::bin_sort(*c, d, I, fp)) return 1;
         c->cache_has_records = false;  // records were not packed: never reuse for rasterisation
         JSB_CUDA_OK(cudaMemcpyAsync(gaussian_ids_sorted, c->cache_ids, (size_t)I * 4,
                                     cudaMemcpyDeviceToDevice, stream));

@@ -48,13 +48,13 @@ struct BinParams {
     unsigned band_y0, band_y1;  // tile rows [band_y0, band_y1) this call owns (full frame: 0, tiles_y)
 };
 
-// prep: pack records, depth keys (0xFFFFFFFF for radii<=0), per-Gaussian tile counts,
-// identity ids; fingerprint[0] += 64-bit hash of every input, fingerprint[1] += tile count
+// prep: pack records, depth keys (0xFFFFFFFF for radii<=0), per-Gaussian band-clamped tile boxes
+// {x0 | y0 << 16, width | height << 16}, identity ids; fingerprint[0] += 64-bit hash of every input, fingerprint[1] += tile count
 // (= num_intersects).  conics == nullptr skips the record packing (sort_and_bin-only callers).
 int launch_bin_prep(cudaStream_t stream, const BinParams &p, const float *xys,
                     const float *depths, const int *radii, const float *conics,
                     const float *opacities, const float *colors, SplatRecord *records,
-                    unsigned *depth_keys, unsigned *ids, unsigned *tile_counts,
+                    unsigned *depth_keys, unsigned *ids, uint2 *box_by_id,
                     unsigned long long *fingerprint, bool write = true);
 
 // *out += order-independent 64-bit hash of every rasterizer input word (null arrays skipped)
@@ -71,18 +71,32 @@ int launch_scan_totals(cudaStream_t stream, unsigned *totals, unsigned nb);
 int launch_add_block_prefix(cudaStream_t stream, int *cum, const unsigned *prefix, unsigned n,
                             unsigned per_block);
 
-// emit: for Gaussians in depth order, write (tile id, gaussian id) for every covered tile,
-// row-major inside the box (reference forward.cu:135-179); the per-CTA output offsets come from
-// a count kernel + a scan of the CTA totals (no chained look-back, see project.cu).  TileKey is uint16_t (<= 65536 tiles) or uint32_t.
+// ---- per-tile lists (tile_lists.cu) ----------------------------------------------------------
+// boxes[i] = {id, x0|y0<<16, w|h<<16, tiles} of the i-th Gaussian in depth order; block_totals[b] =
+// tiles of depth positions [256 b, 256 b + 256)
+int launch_box_gather(cudaStream_t stream, unsigned n, const unsigned *order, const uint2 *box_by_id,
+                      uint4 *boxes, unsigned *block_totals /* ceil(N/256) words */);
+// (tile id, gaussian id) pairs in depth order, row-major inside each box (the reference's
+// map_gaussian_to_intersects order, forward.cu:135-179, for depth-sorted Gaussians).
+// block_totals is scanned in place.  TileKey is uint16_t (<= 65536 tiles) or uint32_t.
 template <typename TileKey>
-int launch_emit(cudaStream_t stream, const BinParams &p, const unsigned *order,
-                const unsigned *tile_counts, const float *xys, const int *radii, TileKey *keys,
-                unsigned *vals, unsigned *block_totals /* ceil(N/256) scratch words */);
-
-// tile_bins[t] = (first, one-past-last) index of tile t in the sorted list; tiles without
-// intersections stay (0,0) (reference forward.cu:184-208 + memset ops.cu:482-488).
+int launch_emit(cudaStream_t stream, const BinParams &p, const uint4 *boxes,
+                unsigned *block_totals, TileKey *keys, unsigned *vals);
+// number of single-warp chunks the depth-ordered pairs are cut into
+unsigned tile_lists_chunks(unsigned long long num_intersects);
+size_t tile_lists_scratch_words(const BinParams &p, unsigned chunks);
+// count + offsets: fills the (chunk, tile) run starts in `scratch` and tile_bins of the band's
+// tiles ((0,0) for tiles without intersections, reference forward.cu:184-208 + ops.cu:482-488)
 template <typename TileKey>
-int launch_bin_edges(cudaStream_t stream, const TileKey *sorted_keys, unsigned n, int2 *tile_bins);
+int launch_tile_offsets(cudaStream_t stream, const BinParams &p, unsigned chunks,
+                        unsigned long long num_intersects, const TileKey *keys, unsigned *scratch,
+                        int2 *tile_bins);
+// scatter: ids_sorted = per-tile (depth, index)-ordered Gaussian ids, tiles in tile-id order --
+// the value array of the reference's sorted (tile<<32|depth, id) pairs (ops.cu:722-757)
+template <typename TileKey>
+int launch_tile_scatter(cudaStream_t stream, const BinParams &p, unsigned chunks,
+                        unsigned long long num_intersects, const TileKey *keys,
+                        const unsigned *vals, const unsigned *scratch, unsigned *ids_sorted);
 
 // optional debug/parity helper: rebuild the reference's sorted 64-bit keys (tile<<32 | depth bits)
 int launch_rebuild_keys64(cudaStream_t stream, const int2 *tile_bins, unsigned num_tiles,
