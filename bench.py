@@ -111,6 +111,10 @@ def algorithmic_bytes(stage, N, I, P, T):
 
 def main():
     args = parse()
+    # the contract is ONE JSON line on stdout: libraries that chat on fd 1 (NCCL prints its
+    # version banner there) are pointed at stderr, the JSON goes to the saved descriptor
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -132,7 +136,8 @@ def main():
     if args.impl == "reference":
         from oracle import ref_cuda
         if not ref_cuda.available():
-            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/_jaxsplat*.so not built"}))
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/_jaxsplat*.so not built"}),
+                  file=real_stdout, flush=True)
             return
         _ops.set_default_table(ref_cuda.table())
 
@@ -309,7 +314,7 @@ def main():
                                "sample": f"{reps} full fwd+bwd views of the same {args.config} workload "
                                          f"(oracle/oracle.c, OpenMP, {dt / reps:.2f} s/view); the reference "
                                          "itself has no CPU path"}
-    print(json.dumps(out))
+    print(json.dumps(out), file=real_stdout, flush=True)
     if use_dist:
         dist.destroy_process_group()
 

@@ -38,7 +38,11 @@ bin_prep_kernel(const BinParams p, const float2 *__restrict__ xys,
                 unsigned *__restrict__ depth_keys, unsigned *__restrict__ ids,
                 uint2 *__restrict__ box_by_id, unsigned long long *__restrict__ fingerprint) {
     __shared__ __align__(16) float s_buf[BT * 6];
+    __shared__ unsigned s_strip[kMaxStrips];
     const int tid = threadIdx.x;
+    const unsigned nstrips = ceil_div(p.band_y1 - p.band_y0, p.strip_rows);
+    if (WRITE && nstrips > 1)
+        for (unsigned i = tid; i < nstrips; i += BT) s_strip[i] = 0u;
     const long long base = (long long)blockIdx.x * BT;
     const long long g = base + tid;
     const long long n = p.num_points;
@@ -78,6 +82,14 @@ bin_prep_kernel(const BinParams p, const float2 *__restrict__ xys,
             if (y1 > y0 && x1 > x0) {
                 cnt = (x1 - x0) * (y1 - y0);
                 box = make_uint2(x0 | (y0 << 16), (x1 - x0) | ((y1 - y0) << 16));
+                if (WRITE && nstrips > 1) {  // tiles per strip (the strips are binned one by one)
+                    for (unsigned st = (y0 - p.band_y0) / p.strip_rows; st < nstrips; ++st) {
+                        const unsigned r0 = p.band_y0 + st * p.strip_rows;
+                        if (r0 >= y1) break;
+                        const unsigned rows = min(y1, r0 + p.strip_rows) - max(y0, r0);
+                        atomicAdd(&s_strip[st], (x1 - x0) * rows);
+                    }
+                }
             }
             key = __float_as_uint(depth);
         }
@@ -90,6 +102,11 @@ bin_prep_kernel(const BinParams p, const float2 *__restrict__ xys,
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
     if ((tid & 31) == 0 && cnt) atomicAdd(fingerprint + 1, (unsigned long long)cnt);  // total intersections
+    if (WRITE && nstrips > 1) {
+        __syncthreads();
+        for (unsigned i = tid; i < nstrips; i += BT)
+            if (s_strip[i]) atomicAdd(fingerprint + 8 + i, (unsigned long long)s_strip[i]);
+    }
 }
 
 // Order-independent 64-bit fingerprint of up to 6 word arrays (sum of per-word hashes keyed by

@@ -9,6 +9,7 @@
 //     accumulators of rasterize_bwd and a few KB of scan/sort bookkeeping;
 //   * rasterize_bwd reuses the forward's binning (sorted ids + tile bins) when a 64-bit
 //     fingerprint of its inputs matches -- the reference emits, sorts and bins twice.
+#include <algorithm>
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
@@ -191,6 +192,15 @@ static void band_of(const Descriptor &d, unsigned *y0, unsigned *y1) {
     }
 }
 
+static BinParams bin_params(const Descriptor &d) {
+    BinParams bp{d.num_points, (float)(int)d.block_width, d.tiles_x, d.tiles_y, 0, 0, 1};
+    band_of(d, &bp.band_y0, &bp.band_y1);
+    bp.strip_rows = tile_strip_rows(d.tiles_x);
+    if (bp.strip_rows == 0) bp.strip_rows = 1;  // (rejected by check_raster_desc)
+    if (bp.strip_rows > bp.band_y1 - bp.band_y0) bp.strip_rows = bp.band_y1 - bp.band_y0;
+    return bp;
+}
+
 static int tile_bits(unsigned tiles) {
     int b = 1;
     while ((1ull << b) < tiles) ++b;
@@ -200,7 +210,8 @@ static int tile_bits(unsigned tiles) {
 constexpr int SM_FP = 0, SM_TOTAL = 1;       // u64 slots in `small`
 constexpr int SM_ERR_WORD = 4;               // int slots start (byte 16)
 constexpr int SM_TICKET_WORD = 8;            // u32 tickets start (byte 32)
-constexpr size_t SMALL_BYTES = 64;
+constexpr int SM_STRIP = 8;                  // u64 per-strip intersection counts start (byte 64)
+constexpr size_t SMALL_BYTES = 64 + 8 * kMaxStrips;
 
 // ---- binning -----------------------------------------------------------------------------------
 // Runs prep (+fingerprint, +total) and returns after the single host sync with *I and *fp set.
@@ -226,8 +237,9 @@ static int bin_prepare(Ctx &c, const Descriptor &d, const float *xys, const floa
     // sticky so that a device-side failure of the PREVIOUS call is seen at this call's sync
     JSB_CUDA_OK(cudaMemsetAsync(c.small.p, 0, 16, s));
     JSB_CUDA_OK(cudaMemsetAsync((char *)c.small.p + 32, 0, 32, s));
-    BinParams bp{n, (float)(int)d.block_width, d.tiles_x, d.tiles_y, 0, 0};
-    band_of(d, &bp.band_y0, &bp.band_y1);
+    const BinParams bp = bin_params(d);
+    const unsigned nstrips = ceil_div(bp.band_y1 - bp.band_y0, bp.strip_rows);
+    if (nstrips > 1) JSB_CUDA_OK(cudaMemsetAsync((char *)c.small.p + 64, 0, 8 * nstrips, s));
     unsigned long long *small64 = (unsigned long long *)c.small.p;
     {
     StageScope ss(&c, ST_BIN_PREP);
@@ -237,7 +249,8 @@ static int bin_prepare(Ctx &c, const Descriptor &d, const float *xys, const floa
         return 1;
     if (launch_fingerprint(s, n, xys, depths, radii, conics, opac, colors, small64)) return 1;
     }
-    JSB_CUDA_OK(cudaMemcpyAsync(c.h_pinned, c.small.p, 32, cudaMemcpyDeviceToHost, s));
+    JSB_CUDA_OK(cudaMemcpyAsync(c.h_pinned, c.small.p, nstrips > 1 ? 64 + 8 * nstrips : 32,
+                                cudaMemcpyDeviceToHost, s));
     JSB_CUDA_OK(cudaStreamSynchronize(s));
     *fp = c.h_pinned[SM_FP];
     *I = c.h_pinned[SM_TOTAL];
@@ -268,39 +281,65 @@ static int bin_sort_impl(Ctx &c, const Descriptor &d, unsigned long long I) {
         return 1;
     }
     const unsigned *order = (const unsigned *)(in_b ? c.ids_b.p : c.ids_a.p);
-    BinParams bp{n, (float)(int)d.block_width, d.tiles_x, d.tiles_y, 0, 0};
-    band_of(d, &bp.band_y0, &bp.band_y1);
-    const unsigned chunks = tile_lists_chunks(I);
+    // The band is binned strip by strip (<= 8192 tiles each: the scatter keeps one cursor per
+    // tile in shared memory); tile ids are row-major, so the strips' lists simply concatenate.
+    const BinParams bp = bin_params(d);
+    const unsigned nstrips = ceil_div(bp.band_y1 - bp.band_y0, bp.strip_rows);
+    unsigned long long max_strip = I;
+    if (nstrips > 1) {
+        max_strip = 0;
+        for (unsigned st = 0; st < nstrips; ++st)
+            max_strip = std::max(max_strip, c.h_pinned[SM_STRIP + st]);
+    }
+    BinParams widest = bp;
+    widest.band_y1 = bp.band_y0 + bp.strip_rows;
     if (c.ensure(c.boxes, (size_t)n * sizeof(uint4))) return 1;
     if (c.ensure(c.chain, (size_t)ceil_div(n, 256) * 8 + 64)) return 1;
-    if (c.ensure(c.tile_keys, (size_t)I * sizeof(TileKey) + 16)) return 1;
-    if (c.ensure(c.tile_vals, (size_t)I * 4 + 16) || c.ensure(c.tile_ids, (size_t)I * 4)) return 1;
-    if (c.ensure(c.tile_scratch, tile_lists_scratch_words(bp, chunks) * sizeof(unsigned))) return 1;
+    if (c.ensure(c.tile_keys, (size_t)max_strip * sizeof(TileKey) + 16)) return 1;
+    if (c.ensure(c.tile_vals, (size_t)max_strip * 4 + 16) || c.ensure(c.tile_ids, (size_t)I * 4)) return 1;
+    if (c.ensure(c.tile_scratch,
+                 tile_lists_scratch_words(widest, tile_lists_chunks(max_strip)) * sizeof(unsigned)))
+        return 1;
     if (c.ensure(c.bins, (size_t)tiles * sizeof(int2))) return 1;
-    // 2. (tile, id) pairs in depth order
-    {
-    StageScope ss(&c, ST_EMIT);
-    if (launch_box_gather(s, n, order, (const uint2 *)c.box_by_id.p, (uint4 *)c.boxes.p,
-                          (unsigned *)c.chain.p))
-        return 1;
-    if (launch_emit<TileKey>(s, bp, (const uint4 *)c.boxes.p, (unsigned *)c.chain.p,
-                             (TileKey *)c.tile_keys.p, (unsigned *)c.tile_vals.p))
-        return 1;
-    }
-    // 3. per-(chunk, tile) counts -> run offsets and tile bins
-    {
-    StageScope ss(&c, ST_BIN_EDGES);
     JSB_CUDA_OK(cudaMemsetAsync(c.bins.p, 0, (size_t)tiles * sizeof(int2), s));
-    if (launch_tile_offsets<TileKey>(s, bp, chunks, I, (const TileKey *)c.tile_keys.p,
-                                     (unsigned *)c.tile_scratch.p, (int2 *)c.bins.p))
+    unsigned long long done = 0;
+    for (unsigned st = 0; st < nstrips; ++st) {
+        const unsigned long long Is = nstrips > 1 ? c.h_pinned[SM_STRIP + st] : I;
+        if (Is == 0) continue;
+        BinParams sp = bp;
+        sp.band_y0 = bp.band_y0 + st * bp.strip_rows;
+        sp.band_y1 = std::min(bp.band_y1, sp.band_y0 + bp.strip_rows);
+        const unsigned chunks = tile_lists_chunks(Is);
+        // 2. (tile, id) pairs of the strip in depth order
+        {
+        StageScope ss(&c, ST_EMIT);
+        if (launch_box_gather(s, n, order, (const uint2 *)c.box_by_id.p, sp.band_y0, sp.band_y1,
+                              (uint4 *)c.boxes.p, (unsigned *)c.chain.p))
+            return 1;
+        if (launch_emit<TileKey>(s, sp, (const uint4 *)c.boxes.p, (unsigned *)c.chain.p,
+                                 (TileKey *)c.tile_keys.p, (unsigned *)c.tile_vals.p))
+            return 1;
+        }
+        // 3. per-(chunk, tile) counts -> run offsets and tile bins
+        {
+        StageScope ss(&c, ST_BIN_EDGES);
+        if (launch_tile_offsets<TileKey>(s, sp, chunks, Is, done, (const TileKey *)c.tile_keys.p,
+                                         (unsigned *)c.tile_scratch.p, (int2 *)c.bins.p))
+            return 1;
+        }
+        // 4. ids into their per-tile runs, in depth order
+        StageScope ss(&c, ST_TILE_SORT);
+        if (launch_tile_scatter<TileKey>(s, sp, chunks, Is, (const TileKey *)c.tile_keys.p,
+                                         (const unsigned *)c.tile_vals.p,
+                                         (const unsigned *)c.tile_scratch.p,
+                                         (unsigned *)c.tile_ids.p))
+            return 1;
+        done += Is;
+    }
+    if (done != I) {
+        set_error("strip intersection counts sum to %llu, expected %llu", done, I);
         return 1;
     }
-    // 4. ids into their per-tile runs, in depth order
-    StageScope ss(&c, ST_TILE_SORT);
-    if (launch_tile_scatter<TileKey>(s, bp, chunks, I, (const TileKey *)c.tile_keys.p,
-                                     (const unsigned *)c.tile_vals.p,
-                                     (const unsigned *)c.tile_scratch.p, (unsigned *)c.tile_ids.p))
-        return 1;
     c.cache_ids = (unsigned *)c.tile_ids.p;
     return 0;
 }
@@ -400,8 +439,10 @@ static int check_raster_desc(const Descriptor &d) {
                   d.tiles_y, d.img_w, d.img_h, d.block_width);
         return 1;
     }
-    if (d.tiles_x > 8192u || d.tiles_y > 65535u) {
-        set_error("tile grid %ux%u exceeds the supported 8192 x 65535", d.tiles_x, d.tiles_y);
+    if (d.tiles_x > 8192u || d.tiles_y > 65535u ||
+        ceil_div(d.tiles_y, std::max(1u, tile_strip_rows(d.tiles_x))) > kMaxStrips) {
+        set_error("tile grid %ux%u exceeds the supported size (<= 8192 wide, <= 65535 high, <= %u "
+                  "strips of 8192 tiles)", d.tiles_x, d.tiles_y, kMaxStrips);
         return 1;
     }
     unsigned y0, y1;

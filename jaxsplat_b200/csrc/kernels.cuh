@@ -46,7 +46,12 @@ struct BinParams {
     float block_width_f;
     unsigned tiles_x, tiles_y;
     unsigned band_y0, band_y1;  // tile rows [band_y0, band_y1) this call owns (full frame: 0, tiles_y)
+    unsigned strip_rows;        // the band is binned in strips of this many tile rows (tile_lists.cu)
 };
+
+constexpr unsigned kMaxStrips = 256;
+// tile rows per strip such that one strip holds at most 8192 tiles (0 if a single row does not fit)
+unsigned tile_strip_rows(unsigned tiles_x);
 
 // prep: pack records, depth keys (0xFFFFFFFF for radii<=0), per-Gaussian band-clamped tile boxes
 // {x0 | y0 << 16, width | height << 16}, identity ids; fingerprint[0] += 64-bit hash of every input, fingerprint[1] += tile count
@@ -74,8 +79,10 @@ int launch_add_block_prefix(cudaStream_t stream, int *cum, const unsigned *prefi
 // ---- per-tile lists (tile_lists.cu) ----------------------------------------------------------
 // boxes[i] = {id, x0|y0<<16, w|h<<16, tiles} of the i-th Gaussian in depth order; block_totals[b] =
 // tiles of depth positions [256 b, 256 b + 256)
+// (boxes clamped to tile rows [row0, row1))
 int launch_box_gather(cudaStream_t stream, unsigned n, const unsigned *order, const uint2 *box_by_id,
-                      uint4 *boxes, unsigned *block_totals /* ceil(N/256) words */);
+                      unsigned row0, unsigned row1, uint4 *boxes,
+                      unsigned *block_totals /* ceil(N/256) words */);
 // (tile id, gaussian id) pairs in depth order, row-major inside each box (the reference's
 // map_gaussian_to_intersects order, forward.cu:135-179, for depth-sorted Gaussians).
 // block_totals is scanned in place.  TileKey is uint16_t (<= 65536 tiles) or uint32_t.
@@ -85,12 +92,12 @@ int launch_emit(cudaStream_t stream, const BinParams &p, const uint4 *boxes,
 // number of single-warp chunks the depth-ordered pairs are cut into
 unsigned tile_lists_chunks(unsigned long long num_intersects);
 size_t tile_lists_scratch_words(const BinParams &p, unsigned chunks);
-// count + offsets: fills the (chunk, tile) run starts in `scratch` and tile_bins of the band's
-// tiles ((0,0) for tiles without intersections, reference forward.cu:184-208 + ops.cu:482-488)
+// count + offsets: fills the (chunk, tile) run starts in `scratch` (absolute: list_offset is the
+// position of the band's first pair in the whole list) and tile_bins of the band's tiles ((0,0) for tiles without intersections, reference forward.cu:184-208 + ops.cu:482-488)
 template <typename TileKey>
 int launch_tile_offsets(cudaStream_t stream, const BinParams &p, unsigned chunks,
-                        unsigned long long num_intersects, const TileKey *keys, unsigned *scratch,
-                        int2 *tile_bins);
+                        unsigned long long num_intersects, unsigned long long list_offset,
+                        const TileKey *keys, unsigned *scratch, int2 *tile_bins);
 // scatter: ids_sorted = per-tile (depth, index)-ordered Gaussian ids, tiles in tile-id order --
 // the value array of the reference's sorted (tile<<32|depth, id) pairs (ops.cu:722-757)
 template <typename TileKey>

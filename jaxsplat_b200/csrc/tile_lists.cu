@@ -49,15 +49,19 @@ struct WalkParams {
 // ---- step 1: boxes in depth order + per-256 totals ---------------------------------------------
 __global__ void __launch_bounds__(256)
 box_gather_kernel(unsigned n, const unsigned *__restrict__ order, const uint2 *__restrict__ box_by_id,
-                  uint4 *__restrict__ boxes, unsigned *__restrict__ block_totals) {
+                  unsigned row0, unsigned row1, uint4 *__restrict__ boxes,
+                  unsigned *__restrict__ block_totals) {
     __shared__ unsigned s_w[8];
     const long long pos = (long long)blockIdx.x * 256 + threadIdx.x;
     unsigned c = 0;
     if (pos < (long long)n) {
         const unsigned g = order[pos];
         const uint2 b = __ldg(box_by_id + g);
-        c = (b.y & 0xffffu) * (b.y >> 16);
-        boxes[pos] = make_uint4(g, b.x, b.y, c);
+        const unsigned w = b.y & 0xffffu, y0 = b.x >> 16;
+        const unsigned ya = max(y0, row0), yb = min(y0 + (b.y >> 16), row1);
+        const unsigned h = yb > ya ? yb - ya : 0u;
+        c = w * h;
+        boxes[pos] = make_uint4(g, (b.x & 0xffffu) | (ya << 16), h ? (w | (h << 16)) : 0u, c);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
@@ -332,14 +336,14 @@ group_scan_kernel(unsigned band_tiles, unsigned stride, unsigned *__restrict__ g
 // tile_base = exclusive scan of tile_totals (in place, scan_totals_kernel).
 __global__ void __launch_bounds__(256)
 hist_apply_kernel(const WalkParams p, unsigned group_size, const unsigned *__restrict__ group_hist,
-                  const unsigned *__restrict__ tile_base, unsigned total,
+                  const unsigned *__restrict__ tile_base, unsigned total, unsigned list_offset,
                   unsigned *__restrict__ hist, int2 *__restrict__ tile_bins) {
     const unsigned t = blockIdx.x * 256u + threadIdx.x;
     if (t >= p.band_tiles) return;
     const unsigned g = blockIdx.y;
-    const unsigned base = tile_base[t];
+    const unsigned base = list_offset + tile_base[t];
     if (g == 0) {
-        const unsigned end = (t + 1 < p.band_tiles) ? tile_base[t + 1] : total;
+        const unsigned end = list_offset + ((t + 1 < p.band_tiles) ? tile_base[t + 1] : total);
         // tiles without intersections stay (0,0) like the reference's memset + edge detection
         tile_bins[(size_t)p.band_y0 * p.tiles_x + t] =
             end > base ? make_int2((int)base, (int)end) : make_int2(0, 0);
@@ -398,10 +402,13 @@ size_t tile_lists_scratch_words(const BinParams &p, unsigned chunks) {
     return ((size_t)chunks + TL_GROUPS + 1) * w.stride + 16;
 }
 
+unsigned tile_strip_rows(unsigned tiles_x) { return tiles_x ? (unsigned)TL_TCAP / tiles_x : 0u; }
+
 int launch_box_gather(cudaStream_t stream, unsigned n, const unsigned *order, const uint2 *box_by_id,
-                      uint4 *boxes, unsigned *block_totals) {
+                      unsigned row0, unsigned row1, uint4 *boxes, unsigned *block_totals) {
     if (n == 0) return 0;
-    box_gather_kernel<<<ceil_div(n, 256u), 256, 0, stream>>>(n, order, box_by_id, boxes, block_totals);
+    box_gather_kernel<<<ceil_div(n, 256u), 256, 0, stream>>>(n, order, box_by_id, row0, row1, boxes,
+                                                            block_totals);
     JSB_CUDA_OK(cudaGetLastError());
     note_launch();
     return 0;
@@ -421,8 +428,8 @@ int launch_emit(cudaStream_t stream, const BinParams &p, const uint4 *boxes,
 
 template <typename TileKey>
 int launch_tile_offsets(cudaStream_t stream, const BinParams &p, unsigned chunks,
-                        unsigned long long num_intersects, const TileKey *keys, unsigned *scratch,
-                        int2 *tile_bins) {
+                        unsigned long long num_intersects, unsigned long long list_offset,
+                        const TileKey *keys, unsigned *scratch, int2 *tile_bins) {
     if (p.num_points == 0 || p.band_y1 <= p.band_y0) return 0;
     if (p.tiles_x > (unsigned)TL_TCAP) {
         set_error("tile grid %u tiles wide exceeds the supported %d", p.tiles_x, TL_TCAP);
@@ -446,7 +453,8 @@ int launch_tile_offsets(cudaStream_t stream, const BinParams &p, unsigned chunks
     note_launch(3);
     if (launch_scan_totals(stream, tile_totals, w.band_tiles)) return 1;
     hist_apply_kernel<<<dim3(tile_blocks, TL_GROUPS), 256, 0, stream>>>(
-        w, group_size, group_hist, tile_totals, (unsigned)num_intersects, hist, tile_bins);
+        w, group_size, group_hist, tile_totals, (unsigned)num_intersects, (unsigned)list_offset, hist,
+        tile_bins);
     JSB_CUDA_OK(cudaGetLastError());
     note_launch();
     return 0;
@@ -471,7 +479,8 @@ int launch_tile_scatter(cudaStream_t stream, const BinParams &p, unsigned chunks
     template int launch_emit<K>(cudaStream_t, const BinParams &, const uint4 *, unsigned *, K *,   \
                                 unsigned *);                                                       \
     template int launch_tile_offsets<K>(cudaStream_t, const BinParams &, unsigned,                 \
-                                        unsigned long long, const K *, unsigned *, int2 *);        \
+                                        unsigned long long, unsigned long long, const K *,         \
+                                        unsigned *, int2 *);                                       \
     template int launch_tile_scatter<K>(cudaStream_t, const BinParams &, unsigned,                 \
                                         unsigned long long, const K *, const unsigned *,           \
                                         const unsigned *, unsigned *);

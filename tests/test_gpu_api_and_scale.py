@@ -160,6 +160,41 @@ def test_live_reference_parity(cfg):
         assert ok, (k, err, scale)
 
 
+def test_tile_grid_wider_than_one_strip():
+    """> 8192 tiles: the counting distribution works in row strips (tile_lists.cu); the list must
+    still be the stable (tile, depth, index) order -- properties, plus the reference when built"""
+    s = synthetic.benchmark_scene(40000, (960, 1280), scale_max=0.25, seed=11)
+    s.block_size = 8
+    inp = G.scene_inputs(s)
+    kw, rkw = G.scene_kw(s)
+    H, W = s.img_shape
+    tiles = ((W + 7) // 8) * ((H + 7) // 8)
+    assert tiles > 2 * 8192
+    P = G.project_fwd(inp, kw)
+    nth = P["num_tiles_hit"].long().view(-1)
+    I = int(P["cum_tiles_hit"][-1])
+    R = G.rasterize_fwd(inp, P, rkw)
+    got, ids, bins, keys = G.debug_binning(I, tiles, depths=P["depths"])
+    assert got == I
+    assert bool((keys[1:] >= keys[:-1]).all())
+    cnt = (bins[:, 1] - bins[:, 0]).long()
+    assert int(cnt.sum()) == I and bool((cnt >= 0).all())
+    assert torch.equal(torch.bincount(ids.long(), minlength=nth.numel()), nth)
+    nz = cnt > 0
+    assert torch.equal(torch.bincount(keys >> 32, minlength=tiles)[nz], cnt[nz])
+    # equal keys (same tile, same depth bits) must keep index order: stability
+    same = keys[1:] == keys[:-1]
+    assert bool((ids[1:][same] > ids[:-1][same]).all())
+    if ref_cuda.available():
+        ref = ref_cuda.table()
+        Rr = G.rasterize_fwd(inp, P, rkw, table=ref)
+        assert torch.equal(Rr["final_idx"], R["final_idx"])
+        assert G.bits_equal(G.npy(Rr["img"]), G.npy(R["img"])) == 0
+        desc = ref.make_descriptor(s.means3d.shape[0], s.img_shape, (0, 0), (0, 0), 0.0, 0.0, 8)
+        rid, rbins = ref_cuda.sort_and_bin(desc, I, P["xys"], P["depths"], P["radii"], P["cum_tiles_hit"])
+        assert torch.equal(ids, rid) and torch.equal(bins, rbins)
+
+
 @pytest.mark.parametrize("world", [2, 3])
 def test_tile_row_bands_reproduce_the_full_frame(world):
     """screen-tile-row sharding: the union of the bands is the full image bit for bit, and the
