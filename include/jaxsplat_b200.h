@@ -114,6 +114,19 @@ JSB200_API void jsb200_get_stats(unsigned long long *out7);
 /* releases every workspace (all devices/streams). */
 JSB200_API void jsb200_release(void);
 
+/* ---- multi-GPU (no reference equivalent: yklcs/jaxsplat is single-device) ----
+ * In-place sum of n_floats floats across the `world` ranks of one NVSwitch node, in ONE kernel:
+ * every rank's buffer is the same symmetric allocation, mapped peer-to-peer (peer_bases[r] = rank
+ * r's buffer as seen from this rank) and at a multicast address (multicast_base).  Rank r reduces
+ * slice r inside the switch (multimem.ld_reduce) and broadcasts it (multimem.st).  The 16-byte
+ * aligned block of >= 256 bytes at flags_offset_bytes (beyond the data, zero-initialised once)
+ * holds the cross-GPU arrive/depart flags; `epoch` must grow by one per call, starting at 1.
+ * n_floats must be a multiple of 4.  Returns 0 on success. */
+JSB200_API int jsb200_multimem_allreduce_f32(jsb200_stream_t stream, void *multicast_base,
+                                             void *const *peer_bases, size_t n_floats,
+                                             size_t flags_offset_bytes, int rank, int world,
+                                             unsigned epoch);
+
 #ifdef __cplusplus
 }
 #endif

@@ -30,6 +30,7 @@ EXPORTS = (
     "jsb200_get_stage_times",
     "jsb200_get_stats",
     "jsb200_release",
+    "jsb200_multimem_allreduce_f32",
 )
 
 _lib = None
@@ -81,6 +82,8 @@ def lib() -> ctypes.CDLL:
     L.jsb200_get_stats.restype = None
     L.jsb200_release.argtypes = []
     L.jsb200_release.restype = None
+    L.jsb200_multimem_allreduce_f32.argtypes = [vp, vp, ctypes.POINTER(vp), sz, sz, i, i, u]
+    L.jsb200_multimem_allreduce_f32.restype = i
     _lib = L
     return L
 

@@ -42,15 +42,78 @@ def tile_row_bands(tiles_y: int, world: int, weights=None) -> List[tuple]:
     return bands
 
 
+class SwitchReducedBuffer:
+    """A flat float32 buffer that every rank of a node allocates symmetrically and that is summed
+    across ranks IN the NVSwitch by one native kernel (csrc/collective.cu:
+    multimem.ld_reduce + multimem.st, barriers inside the kernel) instead of an NCCL call.
+
+    torch's symmetric-memory allocator is only the plumbing (allocation, handle exchange,
+    multicast mapping).  Where the node has no multicast-capable switch (or a single rank) the
+    buffer is an ordinary tensor and ``all_reduce`` is ``torch.distributed.all_reduce``:
+    ``self.mode`` says which ("nvls-multimem" / "nccl" / "gloo" / "single")."""
+
+    FLAG_BYTES = 4096
+
+    def __init__(self, numel: int, device, group=None):
+        self.numel = int(numel)
+        self.mode = "single"
+        self._epoch = 0
+        self._hdl = None
+        distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+        if distributed:
+            self.mode = dist.get_backend(group)
+        self._group = group
+        padded = (self.numel + 3) // 4 * 4
+        if distributed and torch.device(device).type == "cuda" and self.mode == "nccl":
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                g = group if group is not None else dist.group.WORLD
+                raw = symm_mem.empty(padded + self.FLAG_BYTES // 4, dtype=torch.float32, device=device)
+                hdl = symm_mem.rendezvous(raw, g.group_name)
+                if hdl.multicast_ptr and hdl.world_size <= 16:
+                    raw.zero_()
+                    hdl.barrier(channel=0)
+                    self._raw, self._hdl = raw, hdl
+                    self._padded = padded
+                    self.tensor = raw[:self.numel]
+                    self.mode = "nvls-multimem"
+            except Exception:  # no symmetric memory / multicast on this system: NCCL it is
+                self._hdl = None
+        if self._hdl is None:
+            self.tensor = torch.zeros(self.numel, dtype=torch.float32, device=device)
+
+    def all_reduce(self):
+        """in-place sum over the ranks, enqueued on the current stream"""
+        if self.mode == "single":
+            return
+        if self._hdl is None:
+            dist.all_reduce(self.tensor, group=self._group)
+            return
+        import ctypes
+
+        from . import _lib
+        hdl, raw = self._hdl, self._raw
+        delta = raw.data_ptr() - int(hdl.buffer_ptrs[hdl.rank])
+        peers = (ctypes.c_void_p * hdl.world_size)(*[int(p) + delta for p in hdl.buffer_ptrs])
+        self._epoch += 1
+        rc = _lib.lib().jsb200_multimem_allreduce_f32(
+            ctypes.c_void_p(torch.cuda.current_stream().cuda_stream),
+            ctypes.c_void_p(int(hdl.multicast_ptr) + delta), peers, self._padded,
+            self._padded * 4, hdl.rank, hdl.world_size, self._epoch)
+        if rc != 0:
+            _lib.check_error("multimem_allreduce")
+
+
 class FlatParams:
     """the five parameter arrays as views into one flat buffer, with their gradients as views
     into a second flat buffer so the reduction is a single collective call"""
 
-    def __init__(self, params: Sequence[torch.Tensor]):
+    def __init__(self, params: Sequence[torch.Tensor], group=None):
         self.shapes = [tuple(p.shape) for p in params]
         self.sizes = [p.numel() for p in params]
         self.flat = torch.cat([p.detach().reshape(-1) for p in params]).contiguous()
-        self.grad = torch.zeros_like(self.flat)
+        self.reducer = SwitchReducedBuffer(self.flat.numel(), self.flat.device, group)
+        self.grad = self.reducer.tensor
         self.params, off = [], 0
         for shape, sz in zip(self.shapes, self.sizes):
             q = self.flat[off:off + sz].view(shape).requires_grad_(True)
@@ -81,6 +144,6 @@ def multiview_step(flat: FlatParams, views: Sequence, targets: Sequence[torch.Te
         loss.backward()
         total = total + loss.detach()
     if reduce and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-        dist.all_reduce(flat.grad)
+        flat.reducer.all_reduce()
         dist.all_reduce(total)
     return total

@@ -222,3 +222,17 @@ def test_tile_row_bands_reproduce_the_full_frame(world):
     for a, g in zip(acc, full_grads):  # different float summation order: stated gradient tolerance
         ok, err, scale = grad_close(G.npy(a), G.npy(g), rel=1e-4)
         assert ok, (err, scale)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs on one NVSwitch node")
+def test_in_switch_allreduce_two_ranks():
+    """csrc/collective.cu under torchrun: bit-equal to NCCL on integer data, close on random"""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29541",
+                        os.path.join(root, "tools", "allreduce_check.py"), "100000"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
