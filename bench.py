@@ -309,6 +309,13 @@ def main():
         out["impl"] = "reference"
         out["config"]["reference"] = "unmodified yklcs/jaxsplat lib/*.cu built for sm_100a (oracle/_ref), same harness"
         out["gpu_launches"] = None
+        # the reference has no CPU implementation of this path (its kernels are CUDA-only): this arm
+        # is its own CUDA library on the same B200; the host-core timing is the `cpu_baseline` of
+        # the default arm (oracle/oracle.c)
+        out["cpu_baseline"] = {"value": value, "unit": "views/s", "cores": 0, "kind": "reference",
+                               "sample": f"{args.steps} full fwd+bwd views of {args.config} through the "
+                                         "unmodified reference CUDA kernels on this GPU (no host-core "
+                                         "compute: the reference has no CPU path)"}
     if stages is not None:
         peaks = {}
         try:
