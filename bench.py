@@ -93,16 +93,21 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def algorithmic_bytes(stage, N, I, P, T):
-    """DESIGN.md 'algorithmic bytes per unit' (SURVEY.md 8d), per launch of the stage"""
-    G = min(148 * 6, max(1, (I + 2047) // 2048))  # chunks of the counting distribution
+def algorithmic_bytes(stage, N, I, P, T, rows=0, tiles_x=120):
+    """DESIGN.md 'algorithmic bytes per unit' (SURVEY.md 8d), per launch of the stage.
+    rows = row entries (sum of tile-box heights) of the two-level list distribution."""
+    k2 = 256 if rows == 0 or I == 0 else max(32, min(256, (1792 * 3 * rows // (4 * I)) & ~31))
+    chunks = rows // k2 + (T // max(tiles_x, 1))  # level-2 chunks (upper bound the grid uses)
     return {
         "project_fwd": N * 108,
         "bin_prep": N * (44 + 48 + 4 + 4 + 8),
         "depth_sort": N * (4 + 4 * 2 * 8),
-        "emit": N * (4 + 8 + 16 + 16) + I * 6,
-        "tile_offsets": I * 2 + 5 * G * T * 4 + T * 8,
-        "tile_scatter": I * (6 + 4) + G * T * 4,
+        # level 1: order + box gathered twice (count, scatter), one 8-byte entry per covered row
+        "emit": N * (4 + 8) * 2 + rows * 8,
+        # level-2 counts: entries read once, count matrix written, scanned in place, tile bins
+        "tile_offsets": rows * 8 + 3 * chunks * tiles_x * 4 + T * (4 + 8),
+        # level-2 scatter: entries + run starts read, every id written once
+        "tile_scatter": rows * 8 + chunks * tiles_x * 4 + I * 4,
         "raster_fwd": P * 20 + I * 52,
         "raster_bwd": P * 24 + I * (4 + 40 + 44),
         "project_bwd": N * 188,
@@ -153,26 +158,27 @@ def main():
     target = target_host.to(dev)
     kw = sc.render_kwargs()
 
-    # parameters are views into one flat buffer so the gradient all-reduce is a single call:
-    # the in-switch multimem kernel (csrc/collective.cu) where the node has NVLS, else NCCL
+    # A/B switches for profiling runs (defaults are the product configuration)
+    if args.impl == "ours":
+        if os.environ.get("JSB_ROWCOL") == "0":
+            _lib.set_option("rowcol", 0)
+        if os.environ.get("JSB_FUSED") == "0":
+            jsb.set_fused_render(False)
+    # N > 1: the five gradients are packed into one flat symmetric buffer so the all-reduce is a
+    # single call: the in-switch multimem kernel (csrc/collective.cu) where the node has NVLS
     from jaxsplat_b200.multiview import SwitchReducedBuffer
-    sizes = [p.numel() for p in sc.params()]
-    flat_p = torch.cat([p.reshape(-1) for p in sc.params()]).contiguous()
+    flat_n = sum(p.numel() for p in sc.params())
     if use_dist and os.environ.get("JSB_BENCH_NCCL") == "1":
         reducer = None
-        flat_g = torch.zeros_like(flat_p)
+        flat_g = torch.zeros(flat_n, dtype=torch.float32, device=dev)
     else:
-        reducer = SwitchReducedBuffer(flat_p.numel(), dev) if use_dist else None
-        flat_g = reducer.tensor if reducer is not None else torch.zeros_like(flat_p)
-    params, off = [], 0
-    for p, sz in zip(sc.params(), sizes):
-        q = flat_p[off:off + sz].view(p.shape).requires_grad_(True)
-        q.grad = flat_g[off:off + sz].view(p.shape)
-        params.append(q)
-        off += sz
+        reducer = SwitchReducedBuffer(flat_n, dev) if use_dist else None
+        flat_g = reducer.tensor if reducer is not None else None
+    params = [p.clone().requires_grad_(True) for p in sc.params()]
 
     def step(view, tgt):
-        flat_g.zero_()
+        for q in params:
+            q.grad = None  # optimizer.zero_grad(set_to_none=True): no memset, no accumulate pass
         k = dict(kw)
         k["viewmat"] = view
         img = jsb.render(*params, **k)
@@ -182,6 +188,9 @@ def main():
         loss = (diff * diff).mean()
         img.backward(gradient=diff * (2.0 / diff.numel()))
         if use_dist:
+            # the five parameter gradients packed into the one flat (symmetric) buffer, summed
+            # over the ranks in a single call
+            torch.cat([q.grad.reshape(-1) for q in params], out=flat_g)
             if reducer is not None:
                 reducer.all_reduce()
             else:
@@ -289,6 +298,7 @@ def main():
         return
 
     I = _lib.stats()["last_num_intersects"] if args.impl == "ours" else None
+    rows = _lib.stats()["last_row_entries"] if args.impl == "ours" else 0
     T = ((W + 15) // 16) * ((H + 15) // 16)
     out = {
         "metric": METRIC, "value": value, "unit": "views/s", "n_gpus": world if args.impl == "ours" else 1,
@@ -330,7 +340,7 @@ def main():
             if v["calls"] == 0:
                 continue
             ms = v["ms"] / v["calls"]
-            b = algorithmic_bytes(k, N, I, P, T)
+            b = algorithmic_bytes(k, N, I, P, T, rows, (W + 15) // 16)
             per_stage[k] = {"ms_per_launch": ms, "launches_per_step": v["calls"] / args.steps,
                             "algorithmic_bytes": b, "gbs": b / (ms * 1e-3) / 1e9,
                             "hbm_frac": b / (ms * 1e-3) / 1e9 / peak}

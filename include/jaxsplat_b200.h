@@ -59,6 +59,27 @@ JSB200_API void jsb200_rasterize_fwd(jsb200_stream_t stream, void **buffers, con
 JSB200_API void jsb200_rasterize_bwd(jsb200_stream_t stream, void **buffers, const char *opaque,
                           size_t opaque_len);
 
+/* Fused render (no single reference entry point: replaces the chain
+ * jaxsplat/__init__.py:54-70 = project (lib/ops.cu:12-61) then rasterize (lib/ops.cu:107-170) and,
+ * for the backward, rasterize_bwd (lib/ops.cu:172-235) then project_bwd (lib/ops.cu:63-105)).
+ *   render_fwd  in : means3d scales quats viewmat colors opacities background
+ *               out: cov3ds xys depths radii conics compensation num_tiles_hit cum_tiles_hit
+ *                    final_Ts final_idx out_img          (the two ops' results, same layouts)
+ *   render_bwd  in : means3d scales quats viewmat colors opacities background cov3ds xys depths
+ *                    radii conics compensation cum_tiles_hit final_Ts final_idx v_out_img
+ *                    v_out_img_alpha
+ *               out: v_mean3d v_scale v_quat v_colors v_opacity | v_xy v_xy_abs v_conic v_cov2d
+ *                    v_cov3d                              (the last five: intermediate cotangents)
+ * `opaque` is a full descriptor (f, c, glob_scale, clip_thresh set).  *token_out identifies the
+ * binning this forward left in the per-(device, stream) workspace (0 = none); a render_bwd given
+ * that token reuses it without any check or host synchronisation if no other binning ran on the
+ * stream in between, and rebuilds it otherwise.  Results are bit-identical to the four-call
+ * chain.  Return 0 on success. */
+JSB200_API int jsb200_render_fwd(jsb200_stream_t stream, void **buffers, const char *opaque,
+                                 size_t opaque_len, unsigned long long *token_out);
+JSB200_API int jsb200_render_bwd(jsb200_stream_t stream, void **buffers, const char *opaque,
+                                 size_t opaque_len, unsigned long long token);
+
 /* replaces make_descriptor (lib/ffi.cu:15-52): fills out[80] with the reference-compatible
  * descriptor (img_shape is given as H, W like the Python API).  Returns 0 on success. */
 JSB200_API int jsb200_make_descriptor(unsigned num_points, unsigned img_h, unsigned img_w, float fx, float fy,
@@ -94,6 +115,8 @@ JSB200_API unsigned long long jsb200_error_count(void);
 /* Test / measurement hooks (no reference equivalent). */
 /* key: "cull" (1 default; 0 disables the conservative warp-rectangle pre-filter),
  *      "cache" (1 default; 0 forces rasterize_bwd to re-bin instead of reusing the forward's),
+ *      "rowcol" (1 default; 0 builds the per-tile lists with the older counting distribution of
+ *               tile_lists.cu instead of the two-level row/column distribution),
  *      "timing" (0 default; 1 brackets every stage with CUDA events, see jsb200_get_stage_times) */
 JSB200_API int jsb200_set_option(const char *key, int value);
 /* Copies the binning produced by the most recent rasterize/sort_and_bin call on `stream` into
@@ -109,8 +132,9 @@ JSB200_API long long jsb200_debug_binning(jsb200_stream_t stream, const float *d
 JSB200_API int jsb200_get_stage_times(jsb200_stream_t stream, double *ms_out9,
                                       unsigned long long *calls_out9, int reset);
 /* counters since load: [0] rasterize_fwd calls, [1] rasterize_bwd calls, [2] binning runs,
- * [3] binning cache hits, [4] last num_intersects, [5] workspace bytes, [6] kernel launches */
-JSB200_API void jsb200_get_stats(unsigned long long *out7);
+ * [3] binning cache hits, [4] last num_intersects, [5] workspace bytes, [6] kernel launches,
+ * [7] last row-entry count (sum of tile-box heights) */
+JSB200_API void jsb200_get_stats(unsigned long long *out8);
 /* releases every workspace (all devices/streams). */
 JSB200_API void jsb200_release(void);
 

@@ -8,8 +8,20 @@ in ``jaxsplat_b200.jax_binding`` and is import-guarded).  All compute runs in
 ``lib/libjaxsplat_b200.so`` through the C ABI of ``include/jaxsplat_b200.h``; there is no
 fallback path.
 """
+from . import _ops
 from ._project import project
 from ._rasterize import rasterize
+from ._render import render_fused
+
+_FUSED = True
+
+
+def set_fused_render(enable: bool) -> None:
+    """``render`` runs as one fused native call per direction (default) or, when disabled, as the
+    reference's two-op chain ``project`` -> ``rasterize`` (identical results either way)."""
+    global _FUSED
+    _FUSED = bool(enable)
+
 
 
 def render(means3d, scales, quats, colors, opacities, *, viewmat, background, img_shape, f, c,
@@ -22,6 +34,11 @@ def render(means3d, scales, quats, colors, opacities, *, viewmat, background, im
     tile_rows=(begin, end) (extension, default None = reference behaviour) renders only that band
     of tile rows -- the unit of screen-tile-row sharding across GPUs (multiview.tile_row_bands).
     """
+    if _FUSED and _ops._DEFAULT_TABLE is None:  # (another library's table: the plain op chain)
+        return render_fused(means3d, scales, quats, colors, opacities, viewmat=viewmat,
+                            background=background, img_shape=img_shape, f=f, c=c,
+                            glob_scale=glob_scale, clip_thresh=clip_thresh, block_size=block_size,
+                            tile_rows=tile_rows)
     (xys, depths, radii, conics, _num_tiles_hit, cum_tiles_hit) = project(
         means3d, scales, quats, viewmat, img_shape=img_shape, f=f, c=c, glob_scale=glob_scale,
         clip_thresh=clip_thresh, block_width=block_size)
@@ -29,4 +46,4 @@ def render(means3d, scales, quats, colors, opacities, *, viewmat, background, im
                      img_shape=img_shape, block_width=block_size, tile_rows=tile_rows)
 
 
-__all__ = ["render", "project", "rasterize"]
+__all__ = ["render", "project", "rasterize", "set_fused_render"]

@@ -18,6 +18,8 @@ EXPORTS = (
     "jsb200_project_bwd",
     "jsb200_rasterize_fwd",
     "jsb200_rasterize_bwd",
+    "jsb200_render_fwd",
+    "jsb200_render_bwd",
     "jsb200_make_descriptor",
     "jsb200_set_descriptor_band",
     "jsb200_sort_and_bin",
@@ -57,6 +59,10 @@ def lib() -> ctypes.CDLL:
         fn = getattr(L, name)
         fn.argtypes = [vp, ctypes.POINTER(vp), cp, sz]
         fn.restype = None
+    L.jsb200_render_fwd.argtypes = [vp, ctypes.POINTER(vp), cp, sz, ctypes.POINTER(ctypes.c_ulonglong)]
+    L.jsb200_render_fwd.restype = i
+    L.jsb200_render_bwd.argtypes = [vp, ctypes.POINTER(vp), cp, sz, ctypes.c_ulonglong]
+    L.jsb200_render_bwd.restype = i
     L.jsb200_make_descriptor.argtypes = [u, u, u, f, f, f, f, f, f, u, ctypes.c_char_p]
     L.jsb200_make_descriptor.restype = i
     L.jsb200_set_descriptor_band.argtypes = [ctypes.c_char_p, u, u]
@@ -99,10 +105,10 @@ def check_error(where: str) -> None:
 
 
 def stats() -> dict:
-    out = (ctypes.c_ulonglong * 7)()
+    out = (ctypes.c_ulonglong * 8)()
     lib().jsb200_get_stats(out)
     keys = ("rasterize_fwd_calls", "rasterize_bwd_calls", "binning_runs", "binning_cache_hits",
-            "last_num_intersects", "workspace_bytes", "kernel_launches")
+            "last_num_intersects", "workspace_bytes", "kernel_launches", "last_row_entries")
     return dict(zip(keys, [int(x) for x in out]))
 
 

@@ -144,3 +144,80 @@ def rasterize_bwd(colors, opacities, background, xys, depths, radii, conics, cum
     table.call("rasterize_bwd", ins, outs, _raster_desc(table, n, img_shape, block_width, band))
     # (v_colors, v_opacity, v_xy, v_xy_abs, v_conic)
     return tuple(outs)
+
+
+# ---- fused render: this library only, through include/jaxsplat_b200.h ------------
+def _call_native(fn_name, tensors, opaque, *extra):
+    import ctypes
+
+    from . import _lib
+    for t in tensors:
+        if not t.is_cuda or not t.is_contiguous():
+            raise ValueError(f"{fn_name}: every buffer must be a contiguous CUDA tensor")
+    bufs = (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    rc = getattr(_lib.lib(), fn_name)(stream, bufs, opaque, len(opaque), *extra)
+    if rc != 0:
+        _lib.check_error(fn_name)
+        raise RuntimeError(f"{fn_name} failed")
+    _lib.check_error(fn_name)
+
+
+def render_fwd(mean3ds, scales, quats, viewmat, colors, opacities, background, *, num_points,
+               img_shape, f, c, glob_scale, clip_thresh, block_width, band=None):
+    """project_fwd + binning + rasterize_fwd in one native call (jsb200_render_fwd).  Returns
+    ((cov3ds, xys, depths, radii, conics, compensation, num_tiles_hit, cum_tiles_hit, final_Ts,
+    final_idx, img), token); outputs are bit-identical to the two-op chain."""
+    import ctypes
+
+    n, dev = num_points, mean3ds.device
+    H, W = img_shape
+    ins = [_f32(mean3ds, (n, 3), "mean3ds"), _f32(scales, (n, 3), "scales"),
+           _f32(quats, (n, 4), "quats"), _f32(viewmat, (4, 4), "viewmat"),
+           _f32(colors, (n, 3), "colors"), _f32(opacities, (n, 1), "opacities"),
+           _f32(background, (3,), "background")]
+    outs = [_out((n, 6), torch.float32, dev), _out((n, 2), torch.float32, dev),
+            _out((n, 1), torch.float32, dev), _out((n, 1), torch.int32, dev),
+            _out((n, 3), torch.float32, dev), _out((n, 1), torch.float32, dev),
+            _out((n, 1), torch.int32, dev), _out((n, 1), torch.int32, dev),
+            _out((H, W, 1), torch.float32, dev), _out((H, W, 1), torch.int32, dev),
+            _out((H, W, 3), torch.float32, dev)]
+    d = _ffi.make_descriptor(n, tuple(img_shape), tuple(f), tuple(c), glob_scale, clip_thresh,
+                             block_width)
+    if band is not None:
+        d = _ffi.with_band(d, band[0], band[1])
+    token = ctypes.c_ulonglong(0)
+    _call_native("jsb200_render_fwd", ins + outs, d, ctypes.byref(token))
+    return tuple(outs), int(token.value)
+
+
+def render_bwd(mean3ds, scales, quats, viewmat, colors, opacities, background, cov3ds, xys, depths,
+               radii, conics, compensation, cum_tiles_hit, final_Ts, final_idx, v_img, v_img_alpha,
+               *, token, num_points, img_shape, f, c, glob_scale, clip_thresh, block_width,
+               band=None):
+    """rasterize_bwd + project_bwd in one native call (jsb200_render_bwd).  Returns
+    (v_mean3d, v_scale, v_quat, v_colors, v_opacity, v_xy, v_xy_abs, v_conic, v_cov2d, v_cov3d)."""
+    import ctypes
+
+    n, dev = num_points, mean3ds.device
+    H, W = img_shape
+    ins = [_f32(mean3ds, (n, 3), "mean3ds"), _f32(scales, (n, 3), "scales"),
+           _f32(quats, (n, 4), "quats"), _f32(viewmat, (4, 4), "viewmat"),
+           _f32(colors, (n, 3), "colors"), _f32(opacities, (n, 1), "opacities"),
+           _f32(background, (3,), "background"), _f32(cov3ds, (n, 6), "cov3ds"),
+           _f32(xys, (n, 2), "xys"), _f32(depths, (n, 1), "depths"), _i32(radii, (n, 1), "radii"),
+           _f32(conics, (n, 3), "conics"), _f32(compensation, (n, 1), "compensation"),
+           _i32(cum_tiles_hit, (n, 1), "cum_tiles_hit"), _f32(final_Ts, (H, W, 1), "final_Ts"),
+           _i32(final_idx, (H, W, 1), "final_idx"), _f32(v_img, (H, W, 3), "v_img"),
+           _f32(v_img_alpha, (H, W, 1), "v_img_alpha")]
+    outs = [_out((n, 3), torch.float32, dev), _out((n, 3), torch.float32, dev),
+            _out((n, 4), torch.float32, dev), _out((n, 3), torch.float32, dev),
+            _out((n, 1), torch.float32, dev), _out((n, 2), torch.float32, dev),
+            _out((n, 2), torch.float32, dev), _out((n, 3), torch.float32, dev),
+            _out((n, 3), torch.float32, dev), _out((n, 6), torch.float32, dev)]
+    d = _ffi.make_descriptor(n, tuple(img_shape), tuple(f), tuple(c), glob_scale, clip_thresh,
+                             block_width)
+    if band is not None:
+        d = _ffi.with_band(d, band[0], band[1])
+    _call_native("jsb200_render_bwd", ins + outs, d, ctypes.c_ulonglong(int(token)))
+    return tuple(outs)

@@ -1,0 +1,49 @@
+"""Fused ``render``: one native call forward, one backward.
+
+Same values and gradients as ``project`` followed by ``rasterize`` (reference
+jaxsplat/__init__.py:54-70), without the intermediate autograd nodes: the forward keeps the
+projected arrays and the sorted lists on the device, the backward reuses the forward's binning
+through a token (no fingerprint pass, no host synchronisation) and feeds v_xy / v_conic straight
+into the projection VJP (the round trip of reference _rasterize/__init__.py:187 ->
+_project/__init__.py:170-198).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _ops
+from ._project import ProjectDescriptor
+
+
+class _Render(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, desc: ProjectDescriptor, band, means3d, scales, quats, colors, opacities,
+                viewmat, background):
+        (cov3ds, xys, depths, radii, conics, compensation, _num_tiles_hit, cum_tiles_hit, final_Ts,
+         final_idx, img), token = _ops.render_fwd(means3d, scales, quats, viewmat, colors,
+                                                  opacities, background, band=band, **desc.kwargs())
+        ctx.desc, ctx.band, ctx.token = desc, band, token
+        ctx.save_for_backward(means3d, scales, quats, viewmat, colors, opacities, background,
+                              cov3ds, xys, depths, radii, conics, compensation, cum_tiles_hit,
+                              final_Ts, final_idx)
+        return img
+
+    @staticmethod
+    def backward(ctx, v_img):
+        saved = ctx.saved_tensors
+        H, W = ctx.desc.img_shape
+        v_alpha = torch.zeros((H, W, 1), dtype=torch.float32, device=v_img.device)
+        (v_mean3d, v_scale, v_quat, v_colors, v_opacity, *_rest) = _ops.render_bwd(
+            *saved, v_img.contiguous(), v_alpha, token=ctx.token, band=ctx.band,
+            **ctx.desc.kwargs())
+        return None, None, v_mean3d, v_scale, v_quat, v_colors, v_opacity, None, None
+
+
+def render_fused(means3d, scales, quats, colors, opacities, *, viewmat, background, img_shape, f, c,
+                 glob_scale, clip_thresh, block_size=16, tile_rows=None):
+    desc = ProjectDescriptor(num_points=means3d.shape[0], img_shape=tuple(img_shape),
+                             f=(float(f[0]), float(f[1])), c=(float(c[0]), float(c[1])),
+                             glob_scale=float(glob_scale), clip_thresh=float(clip_thresh),
+                             block_width=int(block_size))
+    band = None if tile_rows is None else (int(tile_rows[0]), int(tile_rows[1]))
+    return _Render.apply(desc, band, means3d, scales, quats, colors, opacities, viewmat, background)

@@ -53,7 +53,7 @@ bin_prep_kernel(const BinParams p, const float2 *__restrict__ xys,
         slab_load<3, BT>(s_color, colors, base * 3, n * 3);
     }
     __syncthreads();
-    unsigned cnt = 0;
+    unsigned cnt = 0, cnt_rows = 0;
     if (g < n) {
         const float2 xy = __ldg(xys + g);
         const float depth = __ldg(depths + g);
@@ -81,6 +81,7 @@ bin_prep_kernel(const BinParams p, const float2 *__restrict__ xys,
             y1 = min(y1, p.band_y1);
             if (y1 > y0 && x1 > x0) {
                 cnt = (x1 - x0) * (y1 - y0);
+                cnt_rows = y1 - y0;
                 box = make_uint2(x0 | (y0 << 16), (x1 - x0) | ((y1 - y0) << 16));
                 if (WRITE && nstrips > 1) {  // tiles per strip (the strips are binned one by one)
                     for (unsigned st = (y0 - p.band_y0) / p.strip_rows; st < nstrips; ++st) {
@@ -100,8 +101,15 @@ bin_prep_kernel(const BinParams p, const float2 *__restrict__ xys,
         }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-    if ((tid & 31) == 0 && cnt) atomicAdd(fingerprint + 1, (unsigned long long)cnt);  // total intersections
+    for (int o = 16; o > 0; o >>= 1) {
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        cnt_rows += __shfl_xor_sync(0xffffffffu, cnt_rows, o);
+    }
+    if ((tid & 31) == 0 && cnt) {
+        atomicAdd(fingerprint + 1, (unsigned long long)cnt);  // total intersections
+        // sum of box heights = row entries of the two-level distribution (rowcol_lists.cu)
+        if (WRITE) atomicAdd(fingerprint + 4, (unsigned long long)cnt_rows);
+    }
     if (WRITE && nstrips > 1) {
         __syncthreads();
         for (unsigned i = tid; i < nstrips; i += BT)

@@ -30,7 +30,7 @@ namespace jsb {
 static thread_local std::string t_error;
 static thread_local bool t_has_error = false;
 static std::atomic<unsigned long long> g_error_count{0};
-static std::atomic<unsigned long long> g_stats[7];
+static std::atomic<unsigned long long> g_stats[8];
 
 void set_error(const char *fmt, ...) {
     char buf[1024];
@@ -47,6 +47,7 @@ void note_launch(int n) { g_stats[6].fetch_add((unsigned long long)n); }
 
 extern bool g_disable_cull;
 static bool g_disable_cache = false;
+static bool g_disable_rowcol = false;
 
 // ---- optional per-stage device timing (jsb200_set_option("timing", 1)) -------------------------
 enum Stage { ST_PROJECT_FWD, ST_BIN_PREP, ST_DEPTH_SORT, ST_EMIT, ST_TILE_SORT, ST_BIN_EDGES,
@@ -91,12 +92,18 @@ struct Ctx {
     DevBuf tile_keys, tile_vals, tile_ids, tile_scratch;
     DevBuf bins, small;  // small: [fingerprint u64][total u64][err int x4][tickets u32 x8]
     unsigned long long *h_pinned = nullptr;  // [fingerprint][total][err...]
+    cudaEvent_t ev_ready = nullptr;          // recorded after the D2H of `small`
+    bool order_in_b = false;                 // where the depth-sorted ids of the last prep are
+    unsigned long long last_rows = 0;        // sum of box heights of the last prep (row entries)
     // binning cache
     bool cache_valid = false;
     bool cache_has_records = false;  // false after a sort_and_bin-only call (no appearance data)
     unsigned long long cache_fp = 0;
     unsigned cache_n = 0, cache_tiles = 0, cache_bw = 0, cache_tiles_x = 0, cache_band = 0;
     unsigned long long cache_I = 0;
+    bool cache_fp_known = false;             // false when the binning came from the fused render
+    unsigned long long generation = 0;       // bumped by every binning run on this context
+    unsigned long long cache_token = 0;      // generation of the cached binning (fused render)
     unsigned *cache_ids = nullptr;  // points into tile_ids
     size_t total_bytes = 0;
     StageTimes times;
@@ -129,6 +136,8 @@ struct Ctx {
         }
         if (h_pinned) cudaFreeHost(h_pinned);
         h_pinned = nullptr;
+        if (ev_ready) cudaEventDestroy(ev_ready);
+        ev_ready = nullptr;
         cache_valid = false;
         total_bytes = 0;
     }
@@ -208,32 +217,34 @@ static int tile_bits(unsigned tiles) {
 }
 
 constexpr int SM_FP = 0, SM_TOTAL = 1;       // u64 slots in `small`
+constexpr int SM_ROWS = 4;                   // u64 slot: sum of box heights (row entries)
 constexpr int SM_ERR_WORD = 4;               // int slots start (byte 16)
 constexpr int SM_TICKET_WORD = 8;            // u32 tickets start (byte 32)
 constexpr int SM_STRIP = 8;                  // u64 per-strip intersection counts start (byte 64)
 constexpr size_t SMALL_BYTES = 64 + 8 * kMaxStrips;
 
 // ---- binning -----------------------------------------------------------------------------------
-// Runs prep (+fingerprint, +total) and returns after the single host sync with *I and *fp set.
-static int bin_prepare(Ctx &c, const Descriptor &d, const float *xys, const float *depths,
-                       const int *radii, const float *conics, const float *opac,
-                       const float *colors, unsigned long long *I, unsigned long long *fp,
-                       bool write = true) {
+// Enqueues prep (+fingerprint, +totals) and the D2H of the 64 control bytes, records ev_ready and
+// -- for a writing prep -- keeps the GPU busy with the N-scale depth sort, which does not depend
+// on the intersection count, so the host's wake-up after bin_prepare_wait() costs no GPU idle time.
+static int bin_prepare_enqueue(Ctx &c, const Descriptor &d, const float *xys, const float *depths,
+                               const int *radii, const float *conics, const float *opac,
+                               const float *colors, bool write = true, bool fingerprint = true) {
     const unsigned n = d.num_points;
     cudaStream_t s = c.stream;
     if (!c.h_pinned) JSB_CUDA_OK(cudaHostAlloc((void **)&c.h_pinned, SMALL_BYTES, cudaHostAllocDefault));
+    if (!c.ev_ready) JSB_CUDA_OK(cudaEventCreateWithFlags(&c.ev_ready, cudaEventDisableTiming));
     if (!c.small.p) {
         if (c.ensure(c.small, SMALL_BYTES)) return 1;
         JSB_CUDA_OK(cudaMemsetAsync(c.small.p, 0, SMALL_BYTES, s));
     }
-    *I = 0;
-    *fp = 0;
     if (n == 0) return 0;
     if (c.ensure(c.records, (size_t)n * sizeof(SplatRecord))) return 1;
     if (c.ensure(c.dkeys_a, (size_t)n * 4) || c.ensure(c.dkeys_b, (size_t)n * 4)) return 1;
     if (c.ensure(c.ids_a, (size_t)n * 4) || c.ensure(c.ids_b, (size_t)n * 4)) return 1;
     if (c.ensure(c.box_by_id, (size_t)n * sizeof(uint2))) return 1;
-    // zero fingerprint/total (bytes 0..16) and tickets (32..64); the error words (16..32) are
+    if (write && c.ensure(c.sort_n_scratch, radix_scratch_bytes(n, 32))) return 1;
+    // zero fingerprint/total (bytes 0..16) and the counters at 32..64; the error words (16..32) are
     // sticky so that a device-side failure of the PREVIOUS call is seen at this call's sync
     JSB_CUDA_OK(cudaMemsetAsync(c.small.p, 0, 16, s));
     JSB_CUDA_OK(cudaMemsetAsync((char *)c.small.p + 32, 0, 32, s));
@@ -247,21 +258,52 @@ static int bin_prepare(Ctx &c, const Descriptor &d, const float *xys, const floa
                                  (SplatRecord *)c.records.p, (unsigned *)c.dkeys_a.p,
                                  (unsigned *)c.ids_a.p, (uint2 *)c.box_by_id.p, small64, true))
         return 1;
-    if (launch_fingerprint(s, n, xys, depths, radii, conics, opac, colors, small64)) return 1;
+    if (fingerprint && launch_fingerprint(s, n, xys, depths, radii, conics, opac, colors, small64))
+        return 1;
     }
-    JSB_CUDA_OK(cudaMemcpyAsync(c.h_pinned, c.small.p, nstrips > 1 ? 64 + 8 * nstrips : 32,
+    JSB_CUDA_OK(cudaMemcpyAsync(c.h_pinned, c.small.p, 64 + (nstrips > 1 ? 8 * nstrips : 0),
                                 cudaMemcpyDeviceToHost, s));
-    JSB_CUDA_OK(cudaStreamSynchronize(s));
+    JSB_CUDA_OK(cudaEventRecord(c.ev_ready, s));
+    if (write) {
+        // depth order of the Gaussians (N-scale, 32-bit keys): independent of the counts
+        StageScope ss(&c, ST_DEPTH_SORT);
+        bool in_b = false;
+        if (radix_sort_pairs<uint32_t>(s, (uint32_t *)c.dkeys_a.p, (uint32_t *)c.dkeys_b.p,
+                                       (unsigned *)c.ids_a.p, (unsigned *)c.ids_b.p, n, 32,
+                                       c.sort_n_scratch.p, (int *)c.small.p + SM_ERR_WORD, &in_b))
+            return 1;
+        c.order_in_b = in_b;
+    }
+    return 0;
+}
+
+// Blocks the host until the control bytes of the last bin_prepare_enqueue have arrived.
+static int bin_prepare_wait(Ctx &c, const Descriptor &d, unsigned long long *I,
+                            unsigned long long *fp) {
+    *I = 0;
+    *fp = 0;
+    c.last_rows = 0;
+    if (d.num_points == 0) return 0;
+    JSB_CUDA_OK(cudaEventSynchronize(c.ev_ready));
     *fp = c.h_pinned[SM_FP];
     *I = c.h_pinned[SM_TOTAL];
+    c.last_rows = c.h_pinned[SM_ROWS];
     const int *e = (const int *)c.h_pinned + SM_ERR_WORD;
     if (e[0] | e[1] | e[2] | e[3]) {
         set_error("device-side look-back spin limit tripped in an earlier call (flags %d %d %d %d)",
                   e[0], e[1], e[2], e[3]);
-        JSB_CUDA_OK(cudaMemsetAsync((char *)c.small.p + 16, 0, 16, s));
+        JSB_CUDA_OK(cudaMemsetAsync((char *)c.small.p + 16, 0, 16, c.stream));
         return 1;
     }
     return 0;
+}
+
+static int bin_prepare(Ctx &c, const Descriptor &d, const float *xys, const float *depths,
+                       const int *radii, const float *conics, const float *opac,
+                       const float *colors, unsigned long long *I, unsigned long long *fp,
+                       bool write = true) {
+    if (bin_prepare_enqueue(c, d, xys, depths, radii, conics, opac, colors, write)) return 1;
+    return bin_prepare_wait(c, d, I, fp);
 }
 
 template <typename TileKey>
@@ -269,18 +311,28 @@ static int bin_sort_impl(Ctx &c, const Descriptor &d, unsigned long long I) {
     const unsigned n = d.num_points;
     cudaStream_t s = c.stream;
     const unsigned tiles = d.tiles_x * d.tiles_y;
-    int *err = (int *)c.small.p + SM_ERR_WORD;
-    // 1. depth order of the Gaussians (N-scale, 32-bit keys)
-    if (c.ensure(c.sort_n_scratch, radix_scratch_bytes(n, 32))) return 1;
-    bool in_b = false;
-    {
-    StageScope ss(&c, ST_DEPTH_SORT);
-    if (radix_sort_pairs<uint32_t>(s, (uint32_t *)c.dkeys_a.p, (uint32_t *)c.dkeys_b.p,
-                                   (unsigned *)c.ids_a.p, (unsigned *)c.ids_b.p, n, 32,
-                                   c.sort_n_scratch.p, err, &in_b))
-        return 1;
+    // 1. the depth order of the Gaussians was enqueued by bin_prepare_enqueue
+    const unsigned *order = (const unsigned *)(c.order_in_b ? c.ids_b.p : c.ids_a.p);
+    if (c.ensure(c.bins, (size_t)tiles * sizeof(int2))) return 1;
+    if (!g_disable_rowcol && rowcol_supported(bin_params(d))) {
+        // two-level in-order distribution (rowcol_lists.cu): rows, then tiles of each row
+        const BinParams bp = bin_params(d);
+        const unsigned long long rows = c.last_rows;
+        if (c.ensure(c.tile_ids, (size_t)I * 4)) return 1;
+        if (c.ensure(c.tile_scratch, rowcol_scratch_bytes(bp, rows, I))) return 1;
+        if ((bp.band_y1 - bp.band_y0) != d.tiles_y)
+            JSB_CUDA_OK(cudaMemsetAsync(c.bins.p, 0, (size_t)tiles * sizeof(int2), s));
+        const Stage stage_of[3] = {ST_EMIT, ST_BIN_EDGES, ST_TILE_SORT};
+        for (int phase = 0; phase < 3; ++phase) {
+            StageScope ss(&c, stage_of[phase]);
+            if (launch_rowcol_lists(s, bp, order, (const uint2 *)c.box_by_id.p, rows, I,
+                                    (unsigned *)c.tile_scratch.p, (unsigned *)c.tile_ids.p,
+                                    (int2 *)c.bins.p, phase))
+                return 1;
+        }
+        c.cache_ids = (unsigned *)c.tile_ids.p;
+        return 0;
     }
-    const unsigned *order = (const unsigned *)(in_b ? c.ids_b.p : c.ids_a.p);
     // The band is binned strip by strip (<= 8192 tiles each: the scatter keeps one cursor per
     // tile in shared memory); tile ids are row-major, so the strips' lists simply concatenate.
     const BinParams bp = bin_params(d);
@@ -300,7 +352,6 @@ static int bin_sort_impl(Ctx &c, const Descriptor &d, unsigned long long I) {
     if (c.ensure(c.tile_scratch,
                  tile_lists_scratch_words(widest, tile_lists_chunks(max_strip)) * sizeof(unsigned)))
         return 1;
-    if (c.ensure(c.bins, (size_t)tiles * sizeof(int2))) return 1;
     JSB_CUDA_OK(cudaMemsetAsync(c.bins.p, 0, (size_t)tiles * sizeof(int2), s));
     unsigned long long done = 0;
     for (unsigned st = 0; st < nstrips; ++st) {
@@ -355,6 +406,8 @@ static int bin_sort(Ctx &c, const Descriptor &d, unsigned long long I, unsigned 
     int rc = tiles <= 65536 ? bin_sort_impl<uint16_t>(c, d, I) : bin_sort_impl<uint32_t>(c, d, I);
     if (rc) return rc;
     c.cache_valid = true;
+    c.cache_fp_known = true;
+    c.cache_token = ++c.generation;
     c.cache_fp = fp;
     c.cache_n = d.num_points;
     c.cache_tiles = tiles;
@@ -364,12 +417,14 @@ static int bin_sort(Ctx &c, const Descriptor &d, unsigned long long I, unsigned 
     c.cache_I = I;
     g_stats[2].fetch_add(1);
     g_stats[4].store(I);
+    g_stats[7].store(c.last_rows);
     return 0;
 }
 
 static bool cache_hit(const Ctx &c, const Descriptor &d, unsigned long long I,
                       unsigned long long fp) {
-    return !g_disable_cache && c.cache_valid && c.cache_has_records && c.cache_fp == fp && c.cache_I == I &&
+    return !g_disable_cache && c.cache_valid && c.cache_has_records && c.cache_fp_known &&
+           c.cache_fp == fp && c.cache_I == I &&
            c.cache_n == d.num_points && c.cache_tiles == d.tiles_x * d.tiles_y &&
            c.cache_tiles_x == d.tiles_x && c.cache_bw == d.block_width && c.cache_band == d.pad;
 }
@@ -494,17 +549,19 @@ static int rasterize_bwd_impl(cudaStream_t stream, void **buf, const Descriptor 
     g_stats[1].fetch_add(1);
     const size_t n = d.num_points;
     if (n == 0) return 0;
+    unsigned long long I = 0, fp = 0;
+    // fingerprint-only pass first: if it matches the forward's binning nothing else is rebuilt;
+    // the gradient accumulators are cleared while its result travels to the host
+    if (bin_prepare_enqueue(*c, d, (const float *)buf[3], (const float *)buf[4], (const int *)buf[5],
+                            (const float *)buf[6], (const float *)buf[1], (const float *)buf[0],
+                            /*write=*/false))
+        return 1;
     JSB_CUDA_OK(cudaMemsetAsync(buf[12], 0, n * 3 * 4, stream));
     JSB_CUDA_OK(cudaMemsetAsync(buf[13], 0, n * 4, stream));
     JSB_CUDA_OK(cudaMemsetAsync(buf[14], 0, n * 2 * 4, stream));
     JSB_CUDA_OK(cudaMemsetAsync(buf[15], 0, n * 2 * 4, stream));
     JSB_CUDA_OK(cudaMemsetAsync(buf[16], 0, n * 3 * 4, stream));
-    unsigned long long I = 0, fp = 0;
-    // fingerprint-only pass first: if it matches the forward's binning nothing else is rebuilt
-    if (bin_prepare(*c, d, (const float *)buf[3], (const float *)buf[4], (const int *)buf[5],
-                    (const float *)buf[6], (const float *)buf[1], (const float *)buf[0], &I, &fp,
-                    /*write=*/false))
-        return 1;
+    if (bin_prepare_wait(*c, d, &I, &fp)) return 1;
     // (a fingerprint-only pass does not recount intersections: the fingerprint covers them)
     if (cache_hit(*c, d, c->cache_I, fp)) {
         g_stats[3].fetch_add(1);
@@ -523,6 +580,105 @@ static int rasterize_bwd_impl(cudaStream_t stream, void **buf, const Descriptor 
                              (const float *)buf[8], (const int *)buf[9], (const float *)buf[10],
                              (const float *)buf[11], (float *)buf[14], (float *)buf[15],
                              (float *)buf[16], (float *)buf[12], (float *)buf[13]);
+}
+
+// ---- fused render ---------------------------------------------------------------
+// project_fwd + binning + rasterize_fwd in one call.  The binning is tagged with a host-side
+// token instead of a fingerprint: render_bwd presented with the same token knows that no other
+// binning ran on this context since, so it needs neither the fingerprint pass nor a host sync.
+static int render_fwd_impl(cudaStream_t stream, void **buf, const Descriptor &d,
+                           unsigned long long *token) {
+    // in : 0 means3d 1 scales 2 quats 3 viewmat 4 colors 5 opacities 6 background
+    // out: 7 cov3ds 8 xys 9 depths 10 radii 11 conics 12 compensation 13 num_tiles_hit
+    //      14 cum_tiles_hit 15 final_Ts 16 final_idx 17 out_img
+    if (token) *token = 0;
+    if (check_raster_desc(d)) return 1;
+    void *pbuf[12] = {buf[0], buf[1], buf[2], buf[3], buf[7], buf[8], buf[9], buf[10], buf[11],
+                      buf[12], buf[13], buf[14]};
+    if (project_fwd_impl(stream, pbuf, d)) return 1;
+    Ctx *c = get_ctx(stream);
+    if (!c) return 1;
+    std::lock_guard<std::mutex> lk(c->mu);
+    g_stats[0].fetch_add(1);
+    const RasterParams rp = raster_params(d);
+    unsigned long long I = 0, fp = 0;
+    if (bin_prepare_enqueue(*c, d, (const float *)buf[8], (const float *)buf[9], (const int *)buf[10],
+                            (const float *)buf[11], (const float *)buf[5], (const float *)buf[4],
+                            /*write=*/true, /*fingerprint=*/false))
+        return 1;
+    if (bin_prepare_wait(*c, d, &I, &fp)) return 1;
+    if (I == 0) {
+        c->cache_valid = false;
+        g_stats[4].store(0);
+        return launch_fill_background(stream, rp, (const float *)buf[6], (float *)buf[15],
+                                      (int *)buf[16], (float *)buf[17]);
+    }
+    if (bin_sort(*c, d, I, 0)) return 1;
+    c->cache_has_records = true;
+    c->cache_fp_known = false;  // never matches a fingerprint: only the token proves identity
+    if (token) *token = c->cache_token;
+    StageScope ss(c, ST_RASTER_FWD);
+    return launch_raster_fwd(stream, rp, c->cache_ids, (const int2 *)c->bins.p,
+                             (const SplatRecord *)c->records.p, (const float *)buf[6],
+                             (float *)buf[15], (int *)buf[16], (float *)buf[17]);
+}
+
+static int render_bwd_impl(cudaStream_t stream, void **buf, const Descriptor &d,
+                           unsigned long long token) {
+    // in : 0 means3d 1 scales 2 quats 3 viewmat 4 colors 5 opacities 6 background 7 cov3ds 8 xys
+    //      9 depths 10 radii 11 conics 12 compensation 13 cum_tiles_hit 14 final_Ts 15 final_idx
+    //      16 v_out_img 17 v_out_img_alpha
+    // out: 18 v_mean3d 19 v_scale 20 v_quat 21 v_colors 22 v_opacity
+    //      23 v_xy 24 v_xy_abs 25 v_conic 26 v_cov2d 27 v_cov3d   (intermediate cotangents)
+    if (check_raster_desc(d)) return 1;
+    const size_t n = d.num_points;
+    if (n == 0) return 0;
+    {
+    Ctx *c = get_ctx(stream);
+    if (!c) return 1;
+    std::lock_guard<std::mutex> lk(c->mu);
+    g_stats[1].fetch_add(1);
+    JSB_CUDA_OK(cudaMemsetAsync(buf[21], 0, n * 3 * 4, stream));
+    JSB_CUDA_OK(cudaMemsetAsync(buf[22], 0, n * 4, stream));
+    JSB_CUDA_OK(cudaMemsetAsync(buf[23], 0, n * 2 * 4, stream));
+    JSB_CUDA_OK(cudaMemsetAsync(buf[24], 0, n * 2 * 4, stream));
+    JSB_CUDA_OK(cudaMemsetAsync(buf[25], 0, n * 3 * 4, stream));
+    const bool hit = !g_disable_cache && token != 0 && c->cache_valid && c->cache_has_records &&
+                     c->cache_token == token && c->cache_n == d.num_points &&
+                     c->cache_tiles == d.tiles_x * d.tiles_y && c->cache_tiles_x == d.tiles_x &&
+                     c->cache_bw == d.block_width && c->cache_band == d.pad;
+    bool empty = false;
+    if (hit) {
+        g_stats[3].fetch_add(1);
+    } else {
+        unsigned long long I = 0, fp = 0;
+        if (bin_prepare_enqueue(*c, d, (const float *)buf[8], (const float *)buf[9],
+                                (const int *)buf[10], (const float *)buf[11], (const float *)buf[5],
+                                (const float *)buf[4], /*write=*/true, /*fingerprint=*/false))
+            return 1;
+        if (bin_prepare_wait(*c, d, &I, &fp)) return 1;
+        if (I == 0) {
+            empty = true;  // rasterizer gradients stay zero; project_bwd still runs on them
+        } else {
+            if (bin_sort(*c, d, I, 0)) return 1;
+            c->cache_has_records = true;
+            c->cache_fp_known = false;
+        }
+    }
+    if (!empty) {
+        StageScope ss(c, ST_RASTER_BWD);
+        if (launch_raster_bwd(stream, raster_params(d), c->cache_ids, (const int2 *)c->bins.p,
+                              (const SplatRecord *)c->records.p, (const float *)buf[6],
+                              (const float *)buf[14], (const int *)buf[15], (const float *)buf[16],
+                              (const float *)buf[17], (float *)buf[23], (float *)buf[24],
+                              (float *)buf[25], (float *)buf[21], (float *)buf[22]))
+            return 1;
+    }
+    }
+    // project_bwd with zero cotangents for depth and compensation (render uses neither)
+    void *pbuf[18] = {buf[0], buf[1], buf[2], buf[3], buf[7], buf[8], buf[10], buf[11], buf[12],
+                      nullptr, buf[23], nullptr, buf[25], buf[18], buf[19], buf[20], buf[26], buf[27]};
+    return project_bwd_impl(stream, pbuf, d);
 }
 
 template <typename F>
@@ -560,6 +716,36 @@ void jsb200_rasterize_fwd(jsb200_stream_t stream, void **buffers, const char *op
 void jsb200_rasterize_bwd(jsb200_stream_t stream, void **buffers, const char *opaque, size_t len) {
     jsb::guarded("rasterize_bwd", (cudaStream_t)stream, buffers, opaque, len,
                  jsb::rasterize_bwd_impl);
+}
+
+int jsb200_render_fwd(jsb200_stream_t stream, void **buffers, const char *opaque, size_t len,
+                      unsigned long long *token_out) {
+    try {
+        const jsb::Descriptor *dp = jsb::unpack(opaque, len);
+        if (!dp) return 1;
+        if (!buffers) { jsb::set_error("render_fwd: null buffer list"); return 1; }
+        jsb::Descriptor d;
+        memcpy(&d, dp, sizeof d);
+        return jsb::render_fwd_impl((cudaStream_t)stream, buffers, d, token_out);
+    } catch (...) {
+        jsb::set_error("render_fwd: exception");
+        return 1;
+    }
+}
+
+int jsb200_render_bwd(jsb200_stream_t stream, void **buffers, const char *opaque, size_t len,
+                      unsigned long long token) {
+    try {
+        const jsb::Descriptor *dp = jsb::unpack(opaque, len);
+        if (!dp) return 1;
+        if (!buffers) { jsb::set_error("render_bwd: null buffer list"); return 1; }
+        jsb::Descriptor d;
+        memcpy(&d, dp, sizeof d);
+        return jsb::render_bwd_impl((cudaStream_t)stream, buffers, d, token);
+    } catch (...) {
+        jsb::set_error("render_bwd: exception");
+        return 1;
+    }
 }
 
 int jsb200_make_descriptor(unsigned num_points, unsigned img_h, unsigned img_w, float fx, float fy,
@@ -666,6 +852,7 @@ int jsb200_set_option(const char *key, int value) {
     if (!key) return 1;
     if (!strcmp(key, "cull")) { jsb::g_disable_cull = (value == 0); return 0; }
     if (!strcmp(key, "cache")) { jsb::g_disable_cache = (value == 0); return 0; }
+    if (!strcmp(key, "rowcol")) { jsb::g_disable_rowcol = (value == 0); return 0; }
     if (!strcmp(key, "timing")) { jsb::g_timing = (value != 0); return 0; }
     jsb::set_error("set_option: unknown key '%s'", key);
     return 1;
@@ -713,9 +900,9 @@ int jsb200_get_stage_times(jsb200_stream_t stream_, double *ms_out9, unsigned lo
     }
 }
 
-void jsb200_get_stats(unsigned long long *out7) {
-    if (!out7) return;
-    for (int i = 0; i < 7; ++i) out7[i] = jsb::g_stats[i].load();
+void jsb200_get_stats(unsigned long long *out8) {
+    if (!out8) return;
+    for (int i = 0; i < 8; ++i) out8[i] = jsb::g_stats[i].load();
 }
 
 void jsb200_release(void) {

@@ -105,6 +105,18 @@ int launch_tile_scatter(cudaStream_t stream, const BinParams &p, unsigned chunks
                         unsigned long long num_intersects, const TileKey *keys,
                         const unsigned *vals, const unsigned *scratch, unsigned *ids_sorted);
 
+// ---- per-tile lists, two-level row/column distribution (rowcol_lists.cu) ----------------------
+// Same result as box_gather + emit + tile_offsets + tile_scatter for bands of <= 256 tile rows
+// and <= 512 tiles per row.  row_entries = sum of the band-clamped box heights (bin_prep counts
+// it), phase 0 = row lists, 1 = run starts + tile_bins of the band, 2 = ids_sorted.
+bool rowcol_supported(const BinParams &p);
+size_t rowcol_scratch_bytes(const BinParams &p, unsigned long long row_entries,
+                            unsigned long long num_intersects);
+int launch_rowcol_lists(cudaStream_t stream, const BinParams &p, const unsigned *order,
+                        const uint2 *box_by_id, unsigned long long row_entries,
+                        unsigned long long num_intersects, unsigned *scratch, unsigned *ids_sorted,
+                        int2 *tile_bins, int phase);
+
 // optional debug/parity helper: rebuild the reference's sorted 64-bit keys (tile<<32 | depth bits)
 int launch_rebuild_keys64(cudaStream_t stream, const int2 *tile_bins, unsigned num_tiles,
                           const unsigned *ids_sorted, const float *depths, long long *keys64);

@@ -279,7 +279,7 @@ project_bwd_kernel(const ProjectBwdParams p, const float *__restrict__ means3d,
         float vm_x = v[0] * vvx + v[4] * vvy + v[8] * vvz;
         float vm_y = v[1] * vvx + v[5] * vvy + v[9] * vvz;
         float vm_z = v[2] * vvx + v[6] * vvy + v[10] * vvz;
-        const float vz = v_depth[idx];
+        const float vz = v_depth ? v_depth[idx] : 0.f;  // null = zero cotangent (fused render)
         vm_x += v[8] * vz;
         vm_y += v[9] * vz;
         vm_z += v[10] * vz;
@@ -299,7 +299,7 @@ project_bwd_kernel(const ProjectBwdParams p, const float *__restrict__ means3d,
         float vc_x = S00, vc_y = S10 + S01, vc_z = S11;
         // cov2d_to_compensation_vjp (helpers.h:73-87): the reference evaluates this in FP64
         {
-            const float comp = compensation[idx], vcomp = v_compensation[idx];
+            const float comp = compensation[idx], vcomp = v_compensation ? v_compensation[idx] : 0.f;
             const float inv_det = cx * cz - cy * cy;
             const float om = 1 - comp * comp;
             const float vs = (float)((double)vcomp * 0.5 / ((double)comp + 1e-6));

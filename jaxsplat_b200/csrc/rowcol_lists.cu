@@ -1,0 +1,522 @@
+// Per-tile depth-ordered Gaussian lists for sm_100a by a two-level in-order distribution:
+// Gaussians -> tile rows -> tiles.  Nothing I-scale is ever written except the final list.
+//
+// Behavioural spec (same as tile_lists.cu): reference lib/kernels/forward.cu:135-179
+// (map_gaussian_to_intersects), lib/ops.cu:722-757 (SortPairs on tile<<32|depth) and
+// forward.cu:184-208 (get_tile_bin_edges): per tile, the ids of the Gaussians whose tile box
+// covers it in ascending (depth bits, index) order, tiles concatenated in tile-id order, plus
+// every tile's (first, one-past-last) range.
+//
+// Design (not a port).  The Gaussians arrive in (depth, index) order.  A tile's list is the
+// subsequence of that order whose boxes cover it, so the list is a *distribution*, not a sort:
+//   level 1  each Gaussian drops one 8-byte entry {id, x0 | w << 16} into every tile ROW of its
+//            box: R row lists, each still in depth order (sum of box heights entries -- about
+//            a quarter of the intersections);
+//   level 2  each row entry drops its id into the tiles x0 .. x0+w-1 of that row.
+// Both levels are the same single-warp kernel: a chunk of <= 256 items is walked IN ORDER by one
+// warp (lanes = the bins an item covers, so one item never conflicts with itself and the order of
+// every bin's run is the item order by construction), the ids land in a shared-memory staging
+// area laid out bin by bin, and the staged chunk leaves as full coalesced runs -- the previous
+// design (tile_lists.cu) issued one 4-byte partial-sector write per intersection and was bound by
+// the L2's partial-write rate.  Run starts come from per-(chunk, bin) counts (difference arrays
+// in shared memory) and a column scan; the count matrices are (chunks x rows) and
+// (row chunks x tile columns): a few MB instead of the (chunks x tiles) matrix of tile_lists.cu.
+// HBM traffic per intersection: the 4-byte id, once.  Per row entry: 8 B written, 8 B read twice.
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace jsb {
+namespace {
+
+constexpr int RC_ITEMS = 256;    // items per chunk (8 register groups of 32)
+constexpr int RC_STAGE1 = 1280;  // staged 8-byte row entries per level-1 chunk
+constexpr int RC_STAGE2 = 1792;  // staged 4-byte ids per level-2 chunk
+
+struct RcParams {
+    unsigned n;          // Gaussians
+    unsigned rows;       // R: tile rows of the band
+    unsigned cols;       // X: tiles per row
+    unsigned band_y0;    // first tile row of the band
+    unsigned k1;         // depth positions per level-1 chunk (multiple of 32, <= 256)
+    unsigned k2;         // row entries per level-2 chunk (multiple of 32, <= 256)
+    unsigned n1;         // level-1 chunks = ceil(n / k1)
+    unsigned n1s;        // row stride of the level-1 count matrix (n1 rounded up to 4)
+    unsigned n2max;      // upper bound of the level-2 chunk count
+};
+
+// word offsets inside the scratch buffer
+struct RcLayout {
+    size_t l1m;         // [rows][n1s]   level-1 counts -> exclusive prefix per row
+    size_t row_tot;     // [rows]
+    size_t row_start;   // [rows + 1]
+    size_t chunk_base;  // [rows + 1]
+    size_t chunk_row;   // [n2max]
+    size_t tile_cnt;    // [rows * cols] -> exclusive scan (tile bases)
+    size_t m;           // [n2max][cols] level-2 counts -> exclusive prefix per (row, col)
+    size_t entries;     // uint2 [entries] (8-byte aligned)
+    size_t end;
+};
+
+__host__ __device__ inline size_t up4(size_t v) { return (v + 3) & ~(size_t)3; }
+
+static RcLayout rc_layout(const RcParams &p, unsigned long long row_entries) {
+    RcLayout L;
+    size_t o = 0;
+    L.l1m = o;        o += up4((size_t)p.rows * p.n1s);
+    L.row_tot = o;    o += up4(p.rows);
+    L.row_start = o;  o += up4(p.rows + 1);
+    L.chunk_base = o; o += up4(p.rows + 1);
+    L.chunk_row = o;  o += up4(p.n2max);
+    L.tile_cnt = o;   o += up4((size_t)p.rows * p.cols + 1);
+    L.m = o;          o += up4((size_t)p.n2max * p.cols);
+    L.entries = o;    o += up4(2 * (size_t)row_entries + 4);
+    L.end = o;
+    return L;
+}
+
+__device__ __forceinline__ unsigned warp_inclusive_scan(unsigned v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
+    }
+    return v;
+}
+
+// band-clamped box of the Gaussian at depth position `pos`: rows relative to the band
+__device__ __forceinline__ bool load_box(const RcParams &p, unsigned pos,
+                                         const unsigned *__restrict__ order,
+                                         const uint2 *__restrict__ box_by_id, unsigned &g,
+                                         unsigned &y0, unsigned &h, unsigned &xw) {
+    g = 0; y0 = 0; h = 0; xw = 0;
+    if (pos >= p.n) return false;
+    g = order[pos];
+    const uint2 b = __ldg(box_by_id + g);
+    const unsigned w = b.y & 0xffffu;
+    h = b.y >> 16;
+    if (w == 0 || h == 0) { h = 0; return false; }
+    y0 = (b.x >> 16) - p.band_y0;
+    xw = (b.x & 0xffffu) | (w << 16);
+    return true;
+}
+
+// ---- level 1 counts: rows covered by each chunk of k1 depth positions ----------------------------
+__global__ void __launch_bounds__(256)
+rc_row_count_kernel(const RcParams p, const unsigned *__restrict__ order,
+                    const uint2 *__restrict__ box_by_id, unsigned *__restrict__ l1m) {
+    __shared__ unsigned s_diff[256 + 1];
+    __shared__ unsigned s_ws[256 / 32 + 1];
+    const unsigned tid = threadIdx.x, chunk = blockIdx.x;
+    for (unsigned i = tid; i <= 256; i += 256) s_diff[i] = 0u;
+    __syncthreads();
+    if (tid < p.k1) {
+        unsigned g, y0, h, xw;
+        if (load_box(p, chunk * p.k1 + tid, order, box_by_id, g, y0, h, xw)) {
+            atomicAdd(&s_diff[y0], 1u);
+            atomicAdd(&s_diff[y0 + h], 0xffffffffu);  // -1 (mod 2^32)
+        }
+    }
+    __syncthreads();
+    const unsigned d = tid < p.rows ? s_diff[tid] : 0u;
+    unsigned total;
+    const unsigned excl = cta_exclusive_scan<256>(d, &total, s_ws);
+    if (tid < p.rows) l1m[(size_t)tid * p.n1s + chunk] = excl + d;  // entries of this chunk in row tid
+}
+
+// ---- in-place exclusive scan of every row of the level-1 matrix ----------------------------------
+__global__ void __launch_bounds__(1024)
+rc_row_scan_kernel(const RcParams p, unsigned *__restrict__ l1m, unsigned *__restrict__ row_tot) {
+    __shared__ unsigned s_ws[1024 / 32 + 1];
+    unsigned *row = l1m + (size_t)blockIdx.x * p.n1s;
+    unsigned carry = 0;
+    for (unsigned b = 0; b < p.n1; b += 1024) {
+        const unsigned i = b + threadIdx.x;
+        const unsigned v = i < p.n1 ? row[i] : 0u;
+        unsigned total;
+        const unsigned e = cta_exclusive_scan<1024>(v, &total, s_ws);
+        if (i < p.n1) row[i] = carry + e;
+        carry += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) row_tot[blockIdx.x] = carry;
+}
+
+// ---- row starts and level-2 chunk bases (rows <= 256: one CTA) -----------------------------------
+__global__ void __launch_bounds__(256)
+rc_row_meta_kernel(const RcParams p, const unsigned *__restrict__ row_tot,
+                   unsigned *__restrict__ row_start, unsigned *__restrict__ chunk_base) {
+    __shared__ unsigned s_ws[256 / 32 + 1];
+    const unsigned tid = threadIdx.x;
+    const unsigned n = tid < p.rows ? row_tot[tid] : 0u;
+    unsigned total;
+    unsigned e = cta_exclusive_scan<256>(n, &total, s_ws);
+    if (tid < p.rows) row_start[tid] = e;
+    if (tid == 0) row_start[p.rows] = total;
+    __syncthreads();
+    const unsigned c = (n + p.k2 - 1) / p.k2;
+    e = cta_exclusive_scan<256>(c, &total, s_ws);
+    if (tid < p.rows) chunk_base[tid] = e;
+    if (tid == 0) chunk_base[p.rows] = total;
+}
+
+// ---- row of every level-2 chunk ------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+rc_chunk_rows_kernel(const RcParams p, const unsigned *__restrict__ chunk_base,
+                     unsigned *__restrict__ chunk_row) {
+    __shared__ unsigned s_base[256 + 1];
+    for (unsigned i = threadIdx.x; i <= p.rows; i += 256) s_base[i] = chunk_base[i];
+    __syncthreads();
+    const unsigned c = blockIdx.x * 256u + threadIdx.x;
+    if (c >= s_base[p.rows]) return;
+    unsigned lo = 0, hi = p.rows;  // invariant: s_base[lo] <= c < s_base[hi]
+    while (hi - lo > 1) {
+        const unsigned mid = (lo + hi) >> 1;
+        if (s_base[mid] <= c) lo = mid; else hi = mid;
+    }
+    chunk_row[c] = lo;
+}
+
+// ---- level 2 counts: tile columns covered by each chunk of k2 row entries -------------------------
+__global__ void __launch_bounds__(256)
+rc_col_count_kernel(const RcParams p, const unsigned *__restrict__ row_start,
+                    const unsigned *__restrict__ chunk_base, const unsigned *__restrict__ chunk_row,
+                    const uint2 *__restrict__ entries, unsigned *__restrict__ m) {
+    __shared__ unsigned s_diff[512 + 2];
+    __shared__ unsigned s_ws[256 / 32 + 1];
+    const unsigned tid = threadIdx.x, c = blockIdx.x;
+    if (c >= chunk_base[p.rows]) return;
+    for (unsigned i = tid; i < 512 + 2; i += 256) s_diff[i] = 0u;
+    __syncthreads();
+    const unsigned r = chunk_row[c];
+    const unsigned ebeg = row_start[r] + (c - chunk_base[r]) * p.k2;
+    const unsigned eend = min(row_start[r + 1], ebeg + p.k2);
+    if (ebeg + tid < eend) {
+        const unsigned xw = entries[ebeg + tid].y;
+        const unsigned x0 = xw & 0xffffu, w = xw >> 16;
+        atomicAdd(&s_diff[x0], 1u);
+        atomicAdd(&s_diff[x0 + w], 0xffffffffu);
+    }
+    __syncthreads();
+    const unsigned d0 = s_diff[2 * tid], d1 = s_diff[2 * tid + 1];
+    unsigned total;
+    const unsigned excl = cta_exclusive_scan<256>(d0 + d1, &total, s_ws);
+    const unsigned c0 = excl + d0, c1 = c0 + d1;
+    unsigned *mrow = m + (size_t)c * p.cols;
+    if (2 * tid < p.cols) mrow[2 * tid] = c0;
+    if (2 * tid + 1 < p.cols) mrow[2 * tid + 1] = c1;
+}
+
+// ---- per (row, column): exclusive scan over the row's chunks in place; tile totals out ------------
+__global__ void __launch_bounds__(256)
+rc_col_scan_kernel(const RcParams p, const unsigned *__restrict__ chunk_base,
+                   unsigned *__restrict__ m, unsigned *__restrict__ tile_cnt) {
+    __shared__ unsigned s_part[8][32];
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned r = blockIdx.y, col = blockIdx.x * 32u + lane;
+    const unsigned cb = chunk_base[r], ce = chunk_base[r + 1];
+    const unsigned per = (ce - cb + 7) / 8;
+    const unsigned c0 = min(ce, cb + warp * per), c1 = min(ce, c0 + per);
+    const bool live = col < p.cols;
+    unsigned sum = 0;
+    if (live) {
+#pragma unroll 4
+        for (unsigned c = c0; c < c1; ++c) sum += m[(size_t)c * p.cols + col];
+    }
+    s_part[warp][lane] = sum;
+    __syncthreads();
+    unsigned run = 0, total = 0;
+#pragma unroll
+    for (unsigned w = 0; w < 8; ++w) {
+        const unsigned v = s_part[w][lane];
+        if (w < warp) run += v;
+        total += v;
+    }
+    if (live) {
+        constexpr int U = 4;
+        for (unsigned c = c0; c < c1; c += U) {
+            unsigned v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) v[u] = (c + u < c1) ? m[(size_t)(c + u) * p.cols + col] : 0u;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (c + u < c1) m[(size_t)(c + u) * p.cols + col] = run;
+                run += v[u];
+            }
+        }
+        if (warp == 0) tile_cnt[(size_t)r * p.cols + col] = total;
+    }
+}
+
+// ---- tile bins from the scanned tile counts --------------------------------------------------------
+__global__ void __launch_bounds__(256)
+rc_tile_bins_kernel(const RcParams p, const unsigned *__restrict__ tile_base, unsigned total,
+                    int2 *__restrict__ tile_bins) {
+    const unsigned t = blockIdx.x * 256u + threadIdx.x;
+    const unsigned nt = p.rows * p.cols;
+    if (t >= nt) return;
+    const unsigned base = tile_base[t];
+    const unsigned end = (t + 1 < nt) ? tile_base[t + 1] : total;
+    // tiles without intersections stay (0,0) like the reference's memset + edge detection
+    tile_bins[(size_t)p.band_y0 * p.cols + t] =
+        end > base ? make_int2((int)base, (int)end) : make_int2(0, 0);
+}
+
+// ---- the in-order staged distribution of one chunk (both levels) -----------------------------------
+// Items live in registers: group q (0..7), lane l = item 32 q + l of the chunk, covering bins
+// [lo, lo + len) with payload `pay`; len == 0 marks an absent item.  Shared memory (per warp):
+//   s_off[nb + 1]  start of each bin's run inside the chunk (exclusive prefix of the bin counts)
+//   s_cur[nb]      next free slot of each bin's run
+//   s_gbase[nb]    global index of the first element of the (chunk, bin) run
+//   s_stage/s_bin  staged payloads and their bins, laid out run by run
+// Slots beyond the staging capacity go straight to global memory (correct, just slower).
+template <typename Payload> struct Shfl;
+template <> struct Shfl<unsigned> {
+    static __device__ __forceinline__ unsigned get(unsigned v, int src) {
+        return __shfl_sync(0xffffffffu, v, src);
+    }
+};
+template <> struct Shfl<uint2> {
+    static __device__ __forceinline__ uint2 get(uint2 v, int src) {
+        return make_uint2(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src));
+    }
+};
+
+template <typename Payload, int STAGE>
+__device__ __forceinline__ void distribute_counts(const unsigned (&lo)[8], const unsigned (&len)[8],
+                                                  unsigned nb, unsigned *s_off, unsigned *s_cur,
+                                                  unsigned &pairs) {
+    const int lane = threadIdx.x;
+    for (unsigned i = lane; i <= nb; i += 32) s_off[i] = 0u;
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        if (len[q]) {
+            atomicAdd(&s_off[lo[q]], 1u);
+            atomicAdd(&s_off[lo[q] + len[q]], 0xffffffffu);
+        }
+    }
+    __syncwarp();
+    unsigned carry_c = 0, carry_o = 0;
+    for (unsigned base = 0; base < nb; base += 32) {
+        const unsigned i = base + lane;
+        const unsigned d = i < nb ? s_off[i] : 0u;
+        unsigned c = warp_inclusive_scan(d, lane) + carry_c;  // items covering bin i
+        carry_c = __shfl_sync(0xffffffffu, c, 31);
+        if (i >= nb) c = 0u;
+        const unsigned s = warp_inclusive_scan(c, lane);
+        const unsigned excl = s - c + carry_o;
+        carry_o += __shfl_sync(0xffffffffu, s, 31);
+        __syncwarp();
+        if (i < nb) { s_off[i] = excl; s_cur[i] = excl; }
+    }
+    pairs = carry_o;
+    __syncwarp();
+}
+
+template <typename Payload, int STAGE>
+__device__ __forceinline__ void distribute_place(const unsigned (&lo)[8], const unsigned (&len)[8],
+                                                 const Payload (&pay)[8], unsigned pairs,
+                                                 const unsigned *s_off, unsigned *s_cur,
+                                                 const unsigned *s_gbase, Payload *s_stage,
+                                                 unsigned short *s_bin, Payload *__restrict__ out) {
+    const unsigned lane = threadIdx.x;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        unsigned live = __ballot_sync(0xffffffffu, len[q] != 0u);
+        while (live) {
+            const int e = __ffs(live) - 1;
+            live &= live - 1;
+            const unsigned lo_e = __shfl_sync(0xffffffffu, lo[q], e);
+            const unsigned len_e = __shfl_sync(0xffffffffu, len[q], e);
+            const Payload pay_e = Shfl<Payload>::get(pay[q], e);
+            for (unsigned l = lane; l < len_e; l += 32) {
+                const unsigned b = lo_e + l;
+                const unsigned slot = s_cur[b];
+                s_cur[b] = slot + 1u;
+                if (slot < (unsigned)STAGE) {
+                    s_stage[slot] = pay_e;
+                    s_bin[slot] = (unsigned short)b;
+                } else {
+                    out[s_gbase[b] + (slot - s_off[b])] = pay_e;
+                }
+            }
+            __syncwarp();
+        }
+    }
+    const unsigned staged = min(pairs, (unsigned)STAGE);
+    for (unsigned s = lane; s < staged; s += 32) {
+        const unsigned b = s_bin[s];
+        out[s_gbase[b] + (s - s_off[b])] = s_stage[s];
+    }
+}
+
+// ---- level 1: Gaussians (depth order) -> row lists ------------------------------------------------
+__global__ void __launch_bounds__(32)
+rc_row_scatter_kernel(const RcParams p, const unsigned *__restrict__ order,
+                      const uint2 *__restrict__ box_by_id, const unsigned *__restrict__ l1m,
+                      const unsigned *__restrict__ row_start, uint2 *__restrict__ entries) {
+    extern __shared__ __align__(16) unsigned char rc_smem[];
+    const unsigned nbp = (p.rows + 1 + 31) & ~31u;
+    uint2 *s_stage = reinterpret_cast<uint2 *>(rc_smem);
+    unsigned *s_off = reinterpret_cast<unsigned *>(rc_smem + (size_t)RC_STAGE1 * 8);
+    unsigned *s_cur = s_off + nbp;
+    unsigned *s_gbase = s_cur + nbp;
+    unsigned short *s_bin = reinterpret_cast<unsigned short *>(s_gbase + nbp);
+    const unsigned lane = threadIdx.x, chunk = blockIdx.x;
+    unsigned lo[8], len[8];
+    uint2 pay[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        unsigned g, y0, h, xw;
+        const unsigned item = q * 32 + lane;
+        const bool ok = item < p.k1 && load_box(p, chunk * p.k1 + item, order, box_by_id, g, y0, h, xw);
+        lo[q] = ok ? y0 : 0u;
+        len[q] = ok ? h : 0u;
+        pay[q] = make_uint2(g, xw);
+    }
+    unsigned pairs;
+    distribute_counts<uint2, RC_STAGE1>(lo, len, p.rows, s_off, s_cur, pairs);
+    if (pairs == 0) return;  // warp-uniform
+    for (unsigned r = lane; r < p.rows; r += 32)
+        s_gbase[r] = row_start[r] + l1m[(size_t)r * p.n1s + chunk];
+    __syncwarp();
+    distribute_place<uint2, RC_STAGE1>(lo, len, pay, pairs, s_off, s_cur, s_gbase, s_stage, s_bin,
+                                       entries);
+}
+
+// ---- level 2: row entries -> per-tile id lists -----------------------------------------------------
+__global__ void __launch_bounds__(32)
+rc_col_scatter_kernel(const RcParams p, const unsigned *__restrict__ row_start,
+                      const unsigned *__restrict__ chunk_base,
+                      const unsigned *__restrict__ chunk_row, const uint2 *__restrict__ entries,
+                      const unsigned *__restrict__ m, const unsigned *__restrict__ tile_base,
+                      unsigned *__restrict__ out_ids) {
+    extern __shared__ __align__(16) unsigned char rc_smem[];
+    const unsigned nbp = (p.cols + 1 + 31) & ~31u;
+    unsigned *s_stage = reinterpret_cast<unsigned *>(rc_smem);
+    unsigned *s_off = s_stage + RC_STAGE2;
+    unsigned *s_cur = s_off + nbp;
+    unsigned *s_gbase = s_cur + nbp;
+    unsigned short *s_bin = reinterpret_cast<unsigned short *>(s_gbase + nbp);
+    const unsigned lane = threadIdx.x, c = blockIdx.x;
+    if (c >= chunk_base[p.rows]) return;
+    const unsigned r = chunk_row[c];
+    const unsigned ebeg = row_start[r] + (c - chunk_base[r]) * p.k2;
+    const unsigned eend = min(row_start[r + 1], ebeg + p.k2);
+    unsigned lo[8], len[8], pay[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const unsigned e = ebeg + q * 32 + lane;
+        uint2 v = make_uint2(0u, 0u);
+        if (q * 32 + lane < p.k2 && e < eend) v = entries[e];
+        pay[q] = v.x;
+        lo[q] = v.y & 0xffffu;
+        len[q] = v.y >> 16;
+    }
+    unsigned pairs;
+    distribute_counts<unsigned, RC_STAGE2>(lo, len, p.cols, s_off, s_cur, pairs);
+    if (pairs == 0) return;
+    const unsigned *mrow = m + (size_t)c * p.cols;
+    const unsigned *tb = tile_base + (size_t)r * p.cols;
+    for (unsigned x = lane; x < p.cols; x += 32) s_gbase[x] = tb[x] + mrow[x];
+    __syncwarp();
+    distribute_place<unsigned, RC_STAGE2>(lo, len, pay, pairs, s_off, s_cur, s_gbase, s_stage, s_bin,
+                                          out_ids);
+}
+
+static unsigned pick_items(unsigned long long produced, unsigned long long items, unsigned stage) {
+    // items per chunk such that the expected output of a chunk fills ~3/4 of the staging area
+    if (produced == 0 || items == 0) return RC_ITEMS;
+    unsigned long long k = (unsigned long long)stage * 3ull * items / (4ull * produced);
+    k &= ~31ull;
+    if (k < 32) k = 32;
+    if (k > (unsigned)RC_ITEMS) k = RC_ITEMS;
+    return (unsigned)k;
+}
+
+static RcParams rc_params(const BinParams &bp, unsigned long long row_entries,
+                          unsigned long long num_intersects) {
+    RcParams p;
+    p.n = bp.num_points;
+    p.rows = bp.band_y1 - bp.band_y0;
+    p.cols = bp.tiles_x;
+    p.band_y0 = bp.band_y0;
+    p.k1 = pick_items(row_entries, bp.num_points, RC_STAGE1);
+    p.k2 = pick_items(num_intersects, row_entries, RC_STAGE2);
+    p.n1 = ceil_div(p.n, p.k1);
+    p.n1s = (p.n1 + 3u) & ~3u;
+    p.n2max = (unsigned)(row_entries / p.k2) + p.rows;
+    return p;
+}
+
+}  // namespace
+
+bool rowcol_supported(const BinParams &bp) {
+    return bp.band_y1 > bp.band_y0 && bp.band_y1 - bp.band_y0 <= 256u && bp.tiles_x <= 512u;
+}
+
+size_t rowcol_scratch_bytes(const BinParams &bp, unsigned long long row_entries,
+                            unsigned long long num_intersects) {
+    const RcParams p = rc_params(bp, row_entries, num_intersects);
+    return rc_layout(p, row_entries).end * sizeof(unsigned);
+}
+
+int launch_rowcol_lists(cudaStream_t stream, const BinParams &bp, const unsigned *order,
+                        const uint2 *box_by_id, unsigned long long row_entries,
+                        unsigned long long num_intersects, unsigned *scratch, unsigned *ids_sorted,
+                        int2 *tile_bins, int phase) {
+    if (bp.num_points == 0 || num_intersects == 0) return 0;
+    if (!rowcol_supported(bp)) {
+        set_error("rowcol_lists: band of %u rows x %u tiles not supported", bp.band_y1 - bp.band_y0,
+                  bp.tiles_x);
+        return 1;
+    }
+    if (row_entries >= (1ull << 31) || num_intersects >= (1ull << 31)) {
+        set_error("rowcol_lists: %llu row entries / %llu intersections exceed 2^31", row_entries,
+                  num_intersects);
+        return 1;
+    }
+    const RcParams p = rc_params(bp, row_entries, num_intersects);
+    const RcLayout L = rc_layout(p, row_entries);
+    unsigned *l1m = scratch + L.l1m, *row_tot = scratch + L.row_tot;
+    unsigned *row_start = scratch + L.row_start, *chunk_base = scratch + L.chunk_base;
+    unsigned *chunk_row = scratch + L.chunk_row, *tile_cnt = scratch + L.tile_cnt;
+    unsigned *m = scratch + L.m;
+    uint2 *entries = reinterpret_cast<uint2 *>(scratch + L.entries);
+    const unsigned nbp1 = (p.rows + 1 + 31) & ~31u, nbp2 = (p.cols + 1 + 31) & ~31u;
+    const size_t smem1 = (size_t)RC_STAGE1 * 8 + 3 * (size_t)nbp1 * 4 + (size_t)RC_STAGE1 * 2;
+    const size_t smem2 = (size_t)RC_STAGE2 * 4 + 3 * (size_t)nbp2 * 4 + (size_t)RC_STAGE2 * 2;
+
+    if (phase == 0) {  // level 1: row lists
+        rc_row_count_kernel<<<p.n1, 256, 0, stream>>>(p, order, box_by_id, l1m);
+        JSB_CUDA_OK(cudaGetLastError());
+        rc_row_scan_kernel<<<p.rows, 1024, 0, stream>>>(p, l1m, row_tot);
+        JSB_CUDA_OK(cudaGetLastError());
+        rc_row_meta_kernel<<<1, 256, 0, stream>>>(p, row_tot, row_start, chunk_base);
+        JSB_CUDA_OK(cudaGetLastError());
+        rc_chunk_rows_kernel<<<ceil_div(p.n2max, 256u), 256, 0, stream>>>(p, chunk_base, chunk_row);
+        JSB_CUDA_OK(cudaGetLastError());
+        rc_row_scatter_kernel<<<p.n1, 32, smem1, stream>>>(p, order, box_by_id, l1m, row_start, entries);
+        JSB_CUDA_OK(cudaGetLastError());
+        note_launch(5);
+    } else if (phase == 1) {  // level 2 run starts and tile bins
+        rc_col_count_kernel<<<p.n2max, 256, 0, stream>>>(p, row_start, chunk_base, chunk_row, entries, m);
+        JSB_CUDA_OK(cudaGetLastError());
+        rc_col_scan_kernel<<<dim3(ceil_div(p.cols, 32u), p.rows), 256, 0, stream>>>(p, chunk_base, m, tile_cnt);
+        JSB_CUDA_OK(cudaGetLastError());
+        note_launch(2);
+        if (launch_scan_totals(stream, tile_cnt, p.rows * p.cols)) return 1;
+        rc_tile_bins_kernel<<<ceil_div(p.rows * p.cols, 256u), 256, 0, stream>>>(
+            p, tile_cnt, (unsigned)num_intersects, tile_bins);
+        JSB_CUDA_OK(cudaGetLastError());
+        note_launch();
+    } else {  // level 2: the lists
+        rc_col_scatter_kernel<<<p.n2max, 32, smem2, stream>>>(p, row_start, chunk_base, chunk_row,
+                                                              entries, m, tile_cnt, ids_sorted);
+        JSB_CUDA_OK(cudaGetLastError());
+        note_launch();
+    }
+    return 0;
+}
+
+}  // namespace jsb

@@ -236,3 +236,70 @@ def test_in_switch_allreduce_two_ranks():
                         os.path.join(root, "tools", "allreduce_check.py"), "100000"],
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def _grads_of(scene, target, fused):
+    jsb.set_fused_render(fused)
+    try:
+        return _render_loss_and_grads(scene, target)
+    finally:
+        jsb.set_fused_render(True)
+
+
+@pytest.mark.parametrize("scene_fn", [lambda: synthetic.make_config("C1"),
+                                      lambda: synthetic.make_config("C2", num_points=40000),
+                                      lambda: synthetic.benchmark_scene(0 + 513, (40, 72), seed=2)])
+def test_fused_render_equals_the_two_op_chain(scene_fn):
+    """jsb200_render_fwd/bwd (one call per direction) vs project -> rasterize through autograd"""
+    s = scene_fn()
+    H, W = s.img_shape
+    target = torch.rand((H, W, 3), generator=torch.Generator().manual_seed(3)).to(G.DEV)
+    img_f, loss_f, g_f = _grads_of(s, target, True)
+    img_c, loss_c, g_c = _grads_of(s, target, False)
+    assert torch.equal(img_f, img_c)
+    assert loss_f == loss_c
+    for a, b in zip(g_f, g_c):  # same kernels, same inputs: only atomic-order noise
+        ok, err, scale = grad_close(G.npy(a), G.npy(b), rel=2e-5)
+        assert ok, (err, scale)
+
+
+def test_fused_backward_reuses_the_forward_binning_without_a_sync_and_rebins_when_stale():
+    from jaxsplat_b200 import _lib
+    s1 = synthetic.benchmark_scene(3000, (64, 96), seed=1).to(G.DEV)
+    s2 = synthetic.benchmark_scene(3000, (64, 96), seed=2).to(G.DEV)
+    t = torch.rand((64, 96, 3), generator=torch.Generator().manual_seed(5)).to(G.DEV)
+
+    def fwd(sc):
+        ps = [p.clone().requires_grad_(True) for p in sc.params()]
+        return ps, jsb.render(*ps, **sc.render_kwargs())
+
+    # fresh forward -> backward: the token matches, no binning run is added
+    before = _lib.stats()
+    p1, img1 = fwd(s1)
+    ((img1 - t) ** 2).mean().backward()
+    mid = _lib.stats()
+    assert mid["binning_runs"] == before["binning_runs"] + 1
+    assert mid["binning_cache_hits"] == before["binning_cache_hits"] + 1
+    ref = [p.grad.clone() for p in p1]
+    # two forwards, then the backward of the FIRST: its token is stale, the library must re-bin
+    p1, img1 = fwd(s1)
+    _p2, _img2 = fwd(s2)
+    ((img1 - t) ** 2).mean().backward()
+    after = _lib.stats()
+    assert after["binning_runs"] == mid["binning_runs"] + 3
+    assert after["binning_cache_hits"] == mid["binning_cache_hits"]
+    for p, r in zip(p1, ref):
+        ok, err, scale = grad_close(G.npy(p.grad), G.npy(r), rel=2e-5)
+        assert ok, (err, scale)
+
+
+def test_fused_render_empty_frame():
+    s = synthetic.benchmark_scene(100, (32, 48), seed=3)
+    s.means3d[:, 2] = -20.0  # everything behind the camera
+    sc = s.to(G.DEV)
+    ps = [p.clone().requires_grad_(True) for p in sc.params()]
+    img = jsb.render(*ps, **sc.render_kwargs())
+    assert torch.equal(img, sc.background.expand(32, 48, 3))
+    img.sum().backward()
+    for p in ps:
+        assert torch.count_nonzero(p.grad) == 0

@@ -246,3 +246,53 @@ def test_cumsum_and_sort_and_bin_entry_points():
     b = cpu.sort_and_bin(G.npy(P["xys"]), G.npy(P["depths"]), G.npy(P["radii"]),
                          G.npy(P["cum_tiles_hit"]), **rkw)
     assert np.array_equal(G.npy(ids), b["ids_sorted"]) and np.array_equal(G.npy(bins), b["tile_bins"])
+
+
+def _binning_of(scene, band=None):
+    """sorted ids + tile bins the library builds for `scene` (forward rasterisation only)"""
+    inp = G.scene_inputs(scene)
+    kw, rkw = G.scene_kw(scene)
+    P = G.project_fwd(inp, kw)
+    n = inp["colors"].shape[0]
+    outs = _ops.rasterize_fwd(G.t(inp["colors"]), G.t(inp["opacities"]), G.t(inp["background"]),
+                              P["xys"], P["depths"], P["radii"], P["conics"], P["cum_tiles_hit"],
+                              num_points=n, band=band, **rkw)
+    I = _lib.stats()["last_num_intersects"]
+    H, W = scene.img_shape
+    bw = scene.block_size
+    tiles = ((W + bw - 1) // bw) * ((H + bw - 1) // bw)
+    got, ids, bins, _ = G.debug_binning(I, tiles)
+    return I, G.npy(ids), G.npy(bins), [G.npy(o) for o in outs]
+
+
+@pytest.mark.parametrize("case", ["C1", "wide_boxes", "bw8", "ragged", "band", "tall_boxes"])
+def test_row_column_lists_equal_the_counting_distribution(case):
+    """the two list builders (rowcol_lists.cu, tile_lists.cu) must agree bit for bit"""
+    band = None
+    if case == "C1":
+        s = synthetic.make_config("C1")
+    elif case == "wide_boxes":   # many tiles per Gaussian: staging overflow + small chunks
+        s = synthetic.benchmark_scene(20000, (272, 400), scale_max=1.5, seed=9)
+    elif case == "bw8":
+        s = synthetic.benchmark_scene(30000, (200, 312), scale_max=0.3, seed=4)
+        s.block_size = 8
+    elif case == "ragged":
+        s = synthetic.benchmark_scene(777, (90, 50), scale_max=0.4, seed=6)
+    elif case == "band":
+        s = synthetic.benchmark_scene(20000, (320, 256), scale_max=0.4, seed=8)
+        band = (5, 13)
+    else:  # tall boxes: more row entries per chunk than the level-1 staging area holds
+        s = synthetic.benchmark_scene(4000, (1024, 64), scale_max=2.0, seed=10)
+    try:
+        _lib.set_option("rowcol", 1)
+        Ia, ids_a, bins_a, outs_a = _binning_of(s, band)
+        _lib.set_option("rowcol", 0)
+        Ib, ids_b, bins_b, outs_b = _binning_of(s, band)
+    finally:
+        _lib.set_option("rowcol", 1)
+    assert Ia == Ib and Ia > 0
+    assert np.array_equal(bins_a, bins_b)
+    assert np.array_equal(ids_a, ids_b)
+    if band is None:
+        for a, b in zip(outs_a, outs_b):
+            assert np.array_equal(a, b)
