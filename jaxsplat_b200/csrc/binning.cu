@@ -105,10 +105,20 @@ bin_prep_kernel(const BinParams p, const float2 *__restrict__ xys,
         cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
         cnt_rows += __shfl_xor_sync(0xffffffffu, cnt_rows, o);
     }
-    if ((tid & 31) == 0 && cnt) {
-        atomicAdd(fingerprint + 1, (unsigned long long)cnt);  // total intersections
-        // sum of box heights = row entries of the two-level distribution (rowcol_lists.cu)
-        if (WRITE) atomicAdd(fingerprint + 4, (unsigned long long)cnt_rows);
+    // one pair of global atomics per CTA (they all hit the same two words: per-warp atomics
+    // serialise in the L2 and were the kernel's critical path)
+    __shared__ unsigned s_tot[BT / 32][2];
+    if ((tid & 31) == 0) { s_tot[tid >> 5][0] = cnt; s_tot[tid >> 5][1] = cnt_rows; }
+    __syncthreads();
+    if (tid == 0) {
+        unsigned long long t0 = 0, t1 = 0;
+#pragma unroll
+        for (int w = 0; w < BT / 32; ++w) { t0 += s_tot[w][0]; t1 += s_tot[w][1]; }
+        if (t0) {
+            atomicAdd(fingerprint + 1, t0);  // total intersections
+            // sum of box heights = row entries of the two-level distribution (rowcol_lists.cu)
+            if (WRITE) atomicAdd(fingerprint + 4, t1);
+        }
     }
     if (WRITE && nstrips > 1) {
         __syncthreads();
@@ -153,7 +163,15 @@ __global__ void __launch_bounds__(256) fingerprint_kernel(const FpArrays A, unsi
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) h += __shfl_xor_sync(0xffffffffu, h, o);
-    if ((threadIdx.x & 31) == 0 && h) atomicAdd(out, h);
+    __shared__ unsigned long long s_h[8];
+    if ((threadIdx.x & 31) == 0) s_h[threadIdx.x >> 5] = h;
+    __syncthreads();
+    if (threadIdx.x == 0) {  // one same-address atomic per CTA
+        unsigned long long t = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += s_h[w];
+        if (t) atomicAdd(out, t);
+    }
 }
 
 // inclusive int32 prefix sum, single pass (reference ops.cu:607-643 uses cub::DeviceScan)

@@ -13,10 +13,11 @@
 //            box: R row lists, each still in depth order (sum of box heights entries -- about
 //            a quarter of the intersections);
 //   level 2  each row entry drops its id into the tiles x0 .. x0+w-1 of that row.
-// Both levels are the same single-warp kernel: a chunk of <= 256 items is walked IN ORDER by one
-// warp (lanes = the bins an item covers, so one item never conflicts with itself and the order of
-// every bin's run is the item order by construction), the ids land in a shared-memory staging
-// area laid out bin by bin, and the staged chunk leaves as full coalesced runs -- the previous
+// Both levels are the same single-warp kernel: a chunk of <= 256 items is placed 32 items at a
+// time; inside a group the rank of an item in each bin it covers comes from a per-bin lane mask
+// (popc of the lower lanes = item order), between groups from shared-memory cursors, so every
+// bin's run is in item order by construction.  The ids land in a shared-memory staging area laid
+// out bin by bin, and the staged chunk leaves as full coalesced runs -- the previous
 // design (tile_lists.cu) issued one 4-byte partial-sector write per intersection and was bound by
 // the L2's partial-write rate.  Run starts come from per-(chunk, bin) counts (difference arrays
 // in shared memory) and a column scan; the count matrices are (chunks x rows) and
@@ -266,6 +267,7 @@ rc_tile_bins_kernel(const RcParams p, const unsigned *__restrict__ tile_base, un
 // [lo, lo + len) with payload `pay`; len == 0 marks an absent item.  Shared memory (per warp):
 //   s_off[nb + 1]  start of each bin's run inside the chunk (exclusive prefix of the bin counts)
 //   s_cur[nb]      next free slot of each bin's run
+//   s_mask[nb]     lanes of the current 32-item group covering each bin
 //   s_gbase[nb]    global index of the first element of the (chunk, bin) run
 //   s_stage/s_bin  staged payloads and their bins, laid out run by run
 // Slots beyond the staging capacity go straight to global memory (correct, just slower).
@@ -284,9 +286,9 @@ template <> struct Shfl<uint2> {
 template <typename Payload, int STAGE>
 __device__ __forceinline__ void distribute_counts(const unsigned (&lo)[8], const unsigned (&len)[8],
                                                   unsigned nb, unsigned *s_off, unsigned *s_cur,
-                                                  unsigned &pairs) {
+                                                  unsigned *s_mask, unsigned &pairs) {
     const int lane = threadIdx.x;
-    for (unsigned i = lane; i <= nb; i += 32) s_off[i] = 0u;
+    for (unsigned i = lane; i <= nb; i += 32) { s_off[i] = 0u; s_mask[i] = 0u; }
     __syncwarp();
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
@@ -313,35 +315,45 @@ __device__ __forceinline__ void distribute_counts(const unsigned (&lo)[8], const
     __syncwarp();
 }
 
+// Placement, 32 items at a time, order-preserving without walking the items one by one: every
+// lane ORs its lane bit into a coverage mask of each bin it covers; the rank of item `lane` inside
+// bin b among the 32 items is then popc(mask[b] & lanes_below) -- exactly the item order -- and
+// the highest covering lane advances the bin's cursor by popc(mask[b]) and clears the mask.
 template <typename Payload, int STAGE>
 __device__ __forceinline__ void distribute_place(const unsigned (&lo)[8], const unsigned (&len)[8],
                                                  const Payload (&pay)[8], unsigned pairs,
                                                  const unsigned *s_off, unsigned *s_cur,
-                                                 const unsigned *s_gbase, Payload *s_stage,
-                                                 unsigned short *s_bin, Payload *__restrict__ out) {
+                                                 unsigned *s_mask, const unsigned *s_gbase,
+                                                 Payload *s_stage, unsigned short *s_bin,
+                                                 Payload *__restrict__ out) {
     const unsigned lane = threadIdx.x;
+    const unsigned below = (1u << lane) - 1u, mine = 1u << lane;
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-        unsigned live = __ballot_sync(0xffffffffu, len[q] != 0u);
-        while (live) {
-            const int e = __ffs(live) - 1;
-            live &= live - 1;
-            const unsigned lo_e = __shfl_sync(0xffffffffu, lo[q], e);
-            const unsigned len_e = __shfl_sync(0xffffffffu, len[q], e);
-            const Payload pay_e = Shfl<Payload>::get(pay[q], e);
-            for (unsigned l = lane; l < len_e; l += 32) {
-                const unsigned b = lo_e + l;
-                const unsigned slot = s_cur[b];
-                s_cur[b] = slot + 1u;
-                if (slot < (unsigned)STAGE) {
-                    s_stage[slot] = pay_e;
-                    s_bin[slot] = (unsigned short)b;
-                } else {
-                    out[s_gbase[b] + (slot - s_off[b])] = pay_e;
-                }
+        const unsigned mylo = lo[q], mylen = len[q];
+        if (__ballot_sync(0xffffffffu, mylen != 0u) == 0u) continue;  // warp-uniform
+        for (unsigned k = 0; k < mylen; ++k) atomicOr(&s_mask[mylo + k], mine);
+        __syncwarp();
+        for (unsigned k = 0; k < mylen; ++k) {
+            const unsigned b = mylo + k;
+            const unsigned slot = s_cur[b] + __popc(s_mask[b] & below);
+            if (slot < (unsigned)STAGE) {
+                s_stage[slot] = pay[q];
+                s_bin[slot] = (unsigned short)b;
+            } else {
+                out[s_gbase[b] + (slot - s_off[b])] = pay[q];
             }
-            __syncwarp();
         }
+        __syncwarp();
+        for (unsigned k = 0; k < mylen; ++k) {
+            const unsigned b = mylo + k;
+            const unsigned m = s_mask[b];
+            if ((m >> lane) == 1u) {  // highest covering lane (a cleared mask reads 0: no-op)
+                s_cur[b] += __popc(m);
+                s_mask[b] = 0u;
+            }
+        }
+        __syncwarp();
     }
     const unsigned staged = min(pairs, (unsigned)STAGE);
     for (unsigned s = lane; s < staged; s += 32) {
@@ -361,7 +373,8 @@ rc_row_scatter_kernel(const RcParams p, const unsigned *__restrict__ order,
     unsigned *s_off = reinterpret_cast<unsigned *>(rc_smem + (size_t)RC_STAGE1 * 8);
     unsigned *s_cur = s_off + nbp;
     unsigned *s_gbase = s_cur + nbp;
-    unsigned short *s_bin = reinterpret_cast<unsigned short *>(s_gbase + nbp);
+    unsigned *s_mask = s_gbase + nbp;
+    unsigned short *s_bin = reinterpret_cast<unsigned short *>(s_mask + nbp);
     const unsigned lane = threadIdx.x, chunk = blockIdx.x;
     unsigned lo[8], len[8];
     uint2 pay[8];
@@ -375,12 +388,12 @@ rc_row_scatter_kernel(const RcParams p, const unsigned *__restrict__ order,
         pay[q] = make_uint2(g, xw);
     }
     unsigned pairs;
-    distribute_counts<uint2, RC_STAGE1>(lo, len, p.rows, s_off, s_cur, pairs);
+    distribute_counts<uint2, RC_STAGE1>(lo, len, p.rows, s_off, s_cur, s_mask, pairs);
     if (pairs == 0) return;  // warp-uniform
     for (unsigned r = lane; r < p.rows; r += 32)
         s_gbase[r] = row_start[r] + l1m[(size_t)r * p.n1s + chunk];
     __syncwarp();
-    distribute_place<uint2, RC_STAGE1>(lo, len, pay, pairs, s_off, s_cur, s_gbase, s_stage, s_bin,
+    distribute_place<uint2, RC_STAGE1>(lo, len, pay, pairs, s_off, s_cur, s_mask, s_gbase, s_stage, s_bin,
                                        entries);
 }
 
@@ -397,7 +410,8 @@ rc_col_scatter_kernel(const RcParams p, const unsigned *__restrict__ row_start,
     unsigned *s_off = s_stage + RC_STAGE2;
     unsigned *s_cur = s_off + nbp;
     unsigned *s_gbase = s_cur + nbp;
-    unsigned short *s_bin = reinterpret_cast<unsigned short *>(s_gbase + nbp);
+    unsigned *s_mask = s_gbase + nbp;
+    unsigned short *s_bin = reinterpret_cast<unsigned short *>(s_mask + nbp);
     const unsigned lane = threadIdx.x, c = blockIdx.x;
     if (c >= chunk_base[p.rows]) return;
     const unsigned r = chunk_row[c];
@@ -414,13 +428,13 @@ rc_col_scatter_kernel(const RcParams p, const unsigned *__restrict__ row_start,
         len[q] = v.y >> 16;
     }
     unsigned pairs;
-    distribute_counts<unsigned, RC_STAGE2>(lo, len, p.cols, s_off, s_cur, pairs);
+    distribute_counts<unsigned, RC_STAGE2>(lo, len, p.cols, s_off, s_cur, s_mask, pairs);
     if (pairs == 0) return;
     const unsigned *mrow = m + (size_t)c * p.cols;
     const unsigned *tb = tile_base + (size_t)r * p.cols;
     for (unsigned x = lane; x < p.cols; x += 32) s_gbase[x] = tb[x] + mrow[x];
     __syncwarp();
-    distribute_place<unsigned, RC_STAGE2>(lo, len, pay, pairs, s_off, s_cur, s_gbase, s_stage, s_bin,
+    distribute_place<unsigned, RC_STAGE2>(lo, len, pay, pairs, s_off, s_cur, s_mask, s_gbase, s_stage, s_bin,
                                           out_ids);
 }
 
@@ -484,8 +498,8 @@ int launch_rowcol_lists(cudaStream_t stream, const BinParams &bp, const unsigned
     unsigned *m = scratch + L.m;
     uint2 *entries = reinterpret_cast<uint2 *>(scratch + L.entries);
     const unsigned nbp1 = (p.rows + 1 + 31) & ~31u, nbp2 = (p.cols + 1 + 31) & ~31u;
-    const size_t smem1 = (size_t)RC_STAGE1 * 8 + 3 * (size_t)nbp1 * 4 + (size_t)RC_STAGE1 * 2;
-    const size_t smem2 = (size_t)RC_STAGE2 * 4 + 3 * (size_t)nbp2 * 4 + (size_t)RC_STAGE2 * 2;
+    const size_t smem1 = (size_t)RC_STAGE1 * 8 + 4 * (size_t)nbp1 * 4 + (size_t)RC_STAGE1 * 2;
+    const size_t smem2 = (size_t)RC_STAGE2 * 4 + 4 * (size_t)nbp2 * 4 + (size_t)RC_STAGE2 * 2;
 
     if (phase == 0) {  // level 1: row lists
         rc_row_count_kernel<<<p.n1, 256, 0, stream>>>(p, order, box_by_id, l1m);

@@ -259,7 +259,7 @@ def test_fused_render_equals_the_two_op_chain(scene_fn):
     assert torch.equal(img_f, img_c)
     assert loss_f == loss_c
     for a, b in zip(g_f, g_c):  # same kernels, same inputs: only atomic-order noise
-        ok, err, scale = grad_close(G.npy(a), G.npy(b), rel=2e-5)
+        ok, err, scale = grad_close(G.npy(a), G.npy(b), rel=1e-4)
         assert ok, (err, scale)
 
 
@@ -289,7 +289,7 @@ def test_fused_backward_reuses_the_forward_binning_without_a_sync_and_rebins_whe
     assert after["binning_runs"] == mid["binning_runs"] + 3
     assert after["binning_cache_hits"] == mid["binning_cache_hits"]
     for p, r in zip(p1, ref):
-        ok, err, scale = grad_close(G.npy(p.grad), G.npy(r), rel=2e-5)
+        ok, err, scale = grad_close(G.npy(p.grad), G.npy(r), rel=1e-4)
         assert ok, (err, scale)
 
 
