@@ -96,7 +96,7 @@ class ClockSampler:
 def algorithmic_bytes(stage, N, I, P, T, rows=0, tiles_x=120):
     """DESIGN.md 'algorithmic bytes per unit' (SURVEY.md 8d), per launch of the stage.
     rows = row entries (sum of tile-box heights) of the two-level list distribution."""
-    k2 = 256 if rows == 0 or I == 0 else max(32, min(256, (1792 * 3 * rows // (4 * I)) & ~31))
+    k2 = 256 if rows == 0 or I == 0 else max(32, min(256, (1536 * 3 * rows // (4 * I)) & ~31))
     chunks = rows // k2 + (T // max(tiles_x, 1))  # level-2 chunks (upper bound the grid uses)
     return {
         "project_fwd": N * 108,

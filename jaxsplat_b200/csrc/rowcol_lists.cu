@@ -13,10 +13,10 @@
 //            box: R row lists, each still in depth order (sum of box heights entries -- about
 //            a quarter of the intersections);
 //   level 2  each row entry drops its id into the tiles x0 .. x0+w-1 of that row.
-// Both levels are the same single-warp kernel: a chunk of <= 256 items is placed 32 items at a
-// time; inside a group the rank of an item in each bin it covers comes from a per-bin lane mask
-// (popc of the lower lanes = item order), between groups from shared-memory cursors, so every
-// bin's run is in item order by construction.  The ids land in a shared-memory staging area laid
+// Both levels are the same single-warp kernel: a chunk of <= 256 items is ranked all at once --
+// the rank of an item in each bin it covers comes from per-bin lane masks (popc of the earlier
+// groups' masks + popc of the lower lanes of its own group = item order), so every bin's run is
+// in item order by construction, with no serial walk over the items.  The ids land in a shared-memory staging area laid
 // out bin by bin, and the staged chunk leaves as full coalesced runs -- the previous
 // design (tile_lists.cu) issued one 4-byte partial-sector write per intersection and was bound by
 // the L2's partial-write rate.  Run starts come from per-(chunk, bin) counts (difference arrays
@@ -30,8 +30,8 @@ namespace jsb {
 namespace {
 
 constexpr int RC_ITEMS = 256;    // items per chunk (8 register groups of 32)
-constexpr int RC_STAGE1 = 1280;  // staged 8-byte row entries per level-1 chunk
-constexpr int RC_STAGE2 = 1792;  // staged 4-byte ids per level-2 chunk
+constexpr int RC_STAGE1 = 1024;  // staged 8-byte row entries per level-1 chunk
+constexpr int RC_STAGE2 = 1536;  // staged 4-byte ids per level-2 chunk
 
 struct RcParams {
     unsigned n;          // Gaussians
@@ -264,101 +264,96 @@ rc_tile_bins_kernel(const RcParams p, const unsigned *__restrict__ tile_base, un
 
 // ---- the in-order staged distribution of one chunk (both levels) -----------------------------------
 // Items live in registers: group q (0..7), lane l = item 32 q + l of the chunk, covering bins
-// [lo, lo + len) with payload `pay`; len == 0 marks an absent item.  Shared memory (per warp):
-//   s_off[nb + 1]  start of each bin's run inside the chunk (exclusive prefix of the bin counts)
-//   s_cur[nb]      next free slot of each bin's run
-//   s_mask[nb]     lanes of the current 32-item group covering each bin
-//   s_gbase[nb]    global index of the first element of the (chunk, bin) run
-//   s_stage/s_bin  staged payloads and their bins, laid out run by run
-// Slots beyond the staging capacity go straight to global memory (correct, just slower).
-template <typename Payload> struct Shfl;
-template <> struct Shfl<unsigned> {
-    static __device__ __forceinline__ unsigned get(unsigned v, int src) {
-        return __shfl_sync(0xffffffffu, v, src);
+// [lo, lo + len) with payload `pay`; len == 0 marks an absent item.  Order-preserving placement
+// without walking the items one by one:
+//   1. every item ORs its lane bit into mask[q][b] of each bin b it covers;
+//   2. per bin: pre[q][b] = items of groups < q covering b, count[b] = all of them; an exclusive
+//      scan of count over the bins lays the chunk's output out bin by bin (off[b]);
+//   3. item (q, lane) owns slot off[b] + pre[q][b] + popc(mask[q][b] & lower lanes) of bin b --
+//      its rank in item order -- and drops its payload there: into the shared staging area, or
+//      straight to global memory for slots beyond the staging capacity (correct, just slower);
+//   4. the staged slots leave in slot order = run by run, as coalesced stores.
+// Shared memory per warp (nbp = bins + 1 rounded up to 32):
+//   mask u32[8][nbp] | off u32[nbp] | gbase u32[nbp] | stage Payload[STAGE] | pre u16[8][nbp] |
+//   bin u16[STAGE]
+template <typename Payload, int STAGE>
+struct DistSmem {
+    Payload *stage;
+    unsigned *mask, *off, *gbase;
+    unsigned short *pre, *bin;
+    unsigned nbp;
+    __device__ __forceinline__ DistSmem(unsigned char *base, unsigned nb) {
+        nbp = (nb + 1 + 31) & ~31u;
+        stage = reinterpret_cast<Payload *>(base);
+        mask = reinterpret_cast<unsigned *>(base + (size_t)STAGE * sizeof(Payload));
+        off = mask + 8 * nbp;
+        gbase = off + nbp;
+        pre = reinterpret_cast<unsigned short *>(gbase + nbp);
+        bin = pre + 8 * nbp;
     }
-};
-template <> struct Shfl<uint2> {
-    static __device__ __forceinline__ uint2 get(uint2 v, int src) {
-        return make_uint2(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src));
+    static size_t bytes(unsigned nb) {
+        const size_t nbp = (nb + 1 + 31) & ~31u;
+        return (size_t)STAGE * sizeof(Payload) + 10 * nbp * 4 + 8 * nbp * 2 + (size_t)STAGE * 2;
     }
 };
 
+// steps 1 + 2; returns the number of (item, bin) pairs of the chunk (warp-uniform)
 template <typename Payload, int STAGE>
-__device__ __forceinline__ void distribute_counts(const unsigned (&lo)[8], const unsigned (&len)[8],
-                                                  unsigned nb, unsigned *s_off, unsigned *s_cur,
-                                                  unsigned *s_mask, unsigned &pairs) {
-    const int lane = threadIdx.x;
-    for (unsigned i = lane; i <= nb; i += 32) { s_off[i] = 0u; s_mask[i] = 0u; }
+__device__ __forceinline__ unsigned distribute_rank(const unsigned (&lo)[8], const unsigned (&len)[8],
+                                                    unsigned nb, const DistSmem<Payload, STAGE> &S) {
+    const unsigned lane = threadIdx.x, mine = 1u << lane, nbp = S.nbp;
+    uint4 *mz = reinterpret_cast<uint4 *>(S.mask);
+    for (unsigned i = lane; i < 2 * nbp; i += 32) mz[i] = make_uint4(0u, 0u, 0u, 0u);
     __syncwarp();
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-        if (len[q]) {
-            atomicAdd(&s_off[lo[q]], 1u);
-            atomicAdd(&s_off[lo[q] + len[q]], 0xffffffffu);
-        }
-    }
+    for (int q = 0; q < 8; ++q)
+        for (unsigned k = 0; k < len[q]; ++k) atomicOr(&S.mask[q * nbp + lo[q] + k], mine);
     __syncwarp();
-    unsigned carry_c = 0, carry_o = 0;
+    unsigned carry = 0;
     for (unsigned base = 0; base < nb; base += 32) {
-        const unsigned i = base + lane;
-        const unsigned d = i < nb ? s_off[i] : 0u;
-        unsigned c = warp_inclusive_scan(d, lane) + carry_c;  // items covering bin i
-        carry_c = __shfl_sync(0xffffffffu, c, 31);
-        if (i >= nb) c = 0u;
-        const unsigned s = warp_inclusive_scan(c, lane);
-        const unsigned excl = s - c + carry_o;
-        carry_o += __shfl_sync(0xffffffffu, s, 31);
-        __syncwarp();
-        if (i < nb) { s_off[i] = excl; s_cur[i] = excl; }
+        const unsigned b = base + lane;
+        unsigned run = 0;
+        if (b < nb) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                S.pre[q * nbp + b] = (unsigned short)run;
+                run += __popc(S.mask[q * nbp + b]);
+            }
+        }
+        const unsigned incl = warp_inclusive_scan(run, lane);
+        if (b < nb) S.off[b] = incl - run + carry;
+        carry += __shfl_sync(0xffffffffu, incl, 31);
     }
-    pairs = carry_o;
     __syncwarp();
+    return carry;
 }
 
-// Placement, 32 items at a time, order-preserving without walking the items one by one: every
-// lane ORs its lane bit into a coverage mask of each bin it covers; the rank of item `lane` inside
-// bin b among the 32 items is then popc(mask[b] & lanes_below) -- exactly the item order -- and
-// the highest covering lane advances the bin's cursor by popc(mask[b]) and clears the mask.
+// steps 3 + 4 (S.gbase[b] = global index of the first element of the (chunk, bin) run)
 template <typename Payload, int STAGE>
 __device__ __forceinline__ void distribute_place(const unsigned (&lo)[8], const unsigned (&len)[8],
                                                  const Payload (&pay)[8], unsigned pairs,
-                                                 const unsigned *s_off, unsigned *s_cur,
-                                                 unsigned *s_mask, const unsigned *s_gbase,
-                                                 Payload *s_stage, unsigned short *s_bin,
+                                                 const DistSmem<Payload, STAGE> &S,
                                                  Payload *__restrict__ out) {
-    const unsigned lane = threadIdx.x;
-    const unsigned below = (1u << lane) - 1u, mine = 1u << lane;
+    const unsigned lane = threadIdx.x, below = (1u << lane) - 1u, nbp = S.nbp;
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-        const unsigned mylo = lo[q], mylen = len[q];
-        if (__ballot_sync(0xffffffffu, mylen != 0u) == 0u) continue;  // warp-uniform
-        for (unsigned k = 0; k < mylen; ++k) atomicOr(&s_mask[mylo + k], mine);
-        __syncwarp();
-        for (unsigned k = 0; k < mylen; ++k) {
-            const unsigned b = mylo + k;
-            const unsigned slot = s_cur[b] + __popc(s_mask[b] & below);
+        for (unsigned k = 0; k < len[q]; ++k) {
+            const unsigned b = lo[q] + k;
+            const unsigned rank = S.pre[q * nbp + b] + __popc(S.mask[q * nbp + b] & below);
+            const unsigned slot = S.off[b] + rank;
             if (slot < (unsigned)STAGE) {
-                s_stage[slot] = pay[q];
-                s_bin[slot] = (unsigned short)b;
+                S.stage[slot] = pay[q];
+                S.bin[slot] = (unsigned short)b;
             } else {
-                out[s_gbase[b] + (slot - s_off[b])] = pay[q];
+                out[S.gbase[b] + rank] = pay[q];
             }
         }
-        __syncwarp();
-        for (unsigned k = 0; k < mylen; ++k) {
-            const unsigned b = mylo + k;
-            const unsigned m = s_mask[b];
-            if ((m >> lane) == 1u) {  // highest covering lane (a cleared mask reads 0: no-op)
-                s_cur[b] += __popc(m);
-                s_mask[b] = 0u;
-            }
-        }
-        __syncwarp();
     }
+    __syncwarp();
     const unsigned staged = min(pairs, (unsigned)STAGE);
     for (unsigned s = lane; s < staged; s += 32) {
-        const unsigned b = s_bin[s];
-        out[s_gbase[b] + (s - s_off[b])] = s_stage[s];
+        const unsigned b = S.bin[s];
+        out[S.gbase[b] + (s - S.off[b])] = S.stage[s];
     }
 }
 
@@ -368,13 +363,7 @@ rc_row_scatter_kernel(const RcParams p, const unsigned *__restrict__ order,
                       const uint2 *__restrict__ box_by_id, const unsigned *__restrict__ l1m,
                       const unsigned *__restrict__ row_start, uint2 *__restrict__ entries) {
     extern __shared__ __align__(16) unsigned char rc_smem[];
-    const unsigned nbp = (p.rows + 1 + 31) & ~31u;
-    uint2 *s_stage = reinterpret_cast<uint2 *>(rc_smem);
-    unsigned *s_off = reinterpret_cast<unsigned *>(rc_smem + (size_t)RC_STAGE1 * 8);
-    unsigned *s_cur = s_off + nbp;
-    unsigned *s_gbase = s_cur + nbp;
-    unsigned *s_mask = s_gbase + nbp;
-    unsigned short *s_bin = reinterpret_cast<unsigned short *>(s_mask + nbp);
+    const DistSmem<uint2, RC_STAGE1> S(rc_smem, p.rows);
     const unsigned lane = threadIdx.x, chunk = blockIdx.x;
     unsigned lo[8], len[8];
     uint2 pay[8];
@@ -387,14 +376,11 @@ rc_row_scatter_kernel(const RcParams p, const unsigned *__restrict__ order,
         len[q] = ok ? h : 0u;
         pay[q] = make_uint2(g, xw);
     }
-    unsigned pairs;
-    distribute_counts<uint2, RC_STAGE1>(lo, len, p.rows, s_off, s_cur, s_mask, pairs);
-    if (pairs == 0) return;  // warp-uniform
     for (unsigned r = lane; r < p.rows; r += 32)
-        s_gbase[r] = row_start[r] + l1m[(size_t)r * p.n1s + chunk];
-    __syncwarp();
-    distribute_place<uint2, RC_STAGE1>(lo, len, pay, pairs, s_off, s_cur, s_mask, s_gbase, s_stage, s_bin,
-                                       entries);
+        S.gbase[r] = row_start[r] + l1m[(size_t)r * p.n1s + chunk];
+    const unsigned pairs = distribute_rank<uint2, RC_STAGE1>(lo, len, p.rows, S);
+    if (pairs == 0) return;  // warp-uniform
+    distribute_place<uint2, RC_STAGE1>(lo, len, pay, pairs, S, entries);
 }
 
 // ---- level 2: row entries -> per-tile id lists -----------------------------------------------------
@@ -405,13 +391,7 @@ rc_col_scatter_kernel(const RcParams p, const unsigned *__restrict__ row_start,
                       const unsigned *__restrict__ m, const unsigned *__restrict__ tile_base,
                       unsigned *__restrict__ out_ids) {
     extern __shared__ __align__(16) unsigned char rc_smem[];
-    const unsigned nbp = (p.cols + 1 + 31) & ~31u;
-    unsigned *s_stage = reinterpret_cast<unsigned *>(rc_smem);
-    unsigned *s_off = s_stage + RC_STAGE2;
-    unsigned *s_cur = s_off + nbp;
-    unsigned *s_gbase = s_cur + nbp;
-    unsigned *s_mask = s_gbase + nbp;
-    unsigned short *s_bin = reinterpret_cast<unsigned short *>(s_mask + nbp);
+    const DistSmem<unsigned, RC_STAGE2> S(rc_smem, p.cols);
     const unsigned lane = threadIdx.x, c = blockIdx.x;
     if (c >= chunk_base[p.rows]) return;
     const unsigned r = chunk_row[c];
@@ -427,15 +407,12 @@ rc_col_scatter_kernel(const RcParams p, const unsigned *__restrict__ row_start,
         lo[q] = v.y & 0xffffu;
         len[q] = v.y >> 16;
     }
-    unsigned pairs;
-    distribute_counts<unsigned, RC_STAGE2>(lo, len, p.cols, s_off, s_cur, s_mask, pairs);
-    if (pairs == 0) return;
     const unsigned *mrow = m + (size_t)c * p.cols;
     const unsigned *tb = tile_base + (size_t)r * p.cols;
-    for (unsigned x = lane; x < p.cols; x += 32) s_gbase[x] = tb[x] + mrow[x];
-    __syncwarp();
-    distribute_place<unsigned, RC_STAGE2>(lo, len, pay, pairs, s_off, s_cur, s_mask, s_gbase, s_stage, s_bin,
-                                          out_ids);
+    for (unsigned x = lane; x < p.cols; x += 32) S.gbase[x] = tb[x] + mrow[x];
+    const unsigned pairs = distribute_rank<unsigned, RC_STAGE2>(lo, len, p.cols, S);
+    if (pairs == 0) return;
+    distribute_place<unsigned, RC_STAGE2>(lo, len, pay, pairs, S, out_ids);
 }
 
 static unsigned pick_items(unsigned long long produced, unsigned long long items, unsigned stage) {
@@ -497,9 +474,8 @@ int launch_rowcol_lists(cudaStream_t stream, const BinParams &bp, const unsigned
     unsigned *chunk_row = scratch + L.chunk_row, *tile_cnt = scratch + L.tile_cnt;
     unsigned *m = scratch + L.m;
     uint2 *entries = reinterpret_cast<uint2 *>(scratch + L.entries);
-    const unsigned nbp1 = (p.rows + 1 + 31) & ~31u, nbp2 = (p.cols + 1 + 31) & ~31u;
-    const size_t smem1 = (size_t)RC_STAGE1 * 8 + 4 * (size_t)nbp1 * 4 + (size_t)RC_STAGE1 * 2;
-    const size_t smem2 = (size_t)RC_STAGE2 * 4 + 4 * (size_t)nbp2 * 4 + (size_t)RC_STAGE2 * 2;
+    const size_t smem1 = DistSmem<uint2, RC_STAGE1>::bytes(p.rows);
+    const size_t smem2 = DistSmem<unsigned, RC_STAGE2>::bytes(p.cols);
 
     if (phase == 0) {  // level 1: row lists
         rc_row_count_kernel<<<p.n1, 256, 0, stream>>>(p, order, box_by_id, l1m);
