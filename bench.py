@@ -162,6 +162,8 @@ def main():
     if args.impl == "ours":
         if os.environ.get("JSB_ROWCOL") == "0":
             _lib.set_option("rowcol", 0)
+        if os.environ.get("JSB_BWD2PX") == "0":
+            _lib.set_option("bwd2px", 0)
         if os.environ.get("JSB_FUSED") == "0":
             jsb.set_fused_render(False)
     # N > 1: the five gradients are packed into one flat symmetric buffer so the all-reduce is a

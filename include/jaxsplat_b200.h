@@ -68,8 +68,9 @@ JSB200_API void jsb200_rasterize_bwd(jsb200_stream_t stream, void **buffers, con
  *   render_bwd  in : means3d scales quats viewmat colors opacities background cov3ds xys depths
  *                    radii conics compensation cum_tiles_hit final_Ts final_idx v_out_img
  *                    v_out_img_alpha
- *               out: v_mean3d v_scale v_quat v_colors v_opacity | v_xy v_xy_abs v_conic v_cov2d
- *                    v_cov3d                              (the last five: intermediate cotangents)
+ *               out: v_mean3d v_scale v_quat v_colors v_opacity | v_xy v_conic v_cov2d v_cov3d
+ *                    (the last four: intermediate cotangents; v_xy_abs, which nothing downstream
+ *                    of rasterize_bwd reads, is not computed)
  * `opaque` is a full descriptor (f, c, glob_scale, clip_thresh set).  *token_out identifies the
  * binning this forward left in the per-(device, stream) workspace (0 = none); a render_bwd given
  * that token reuses it without any check or host synchronisation if no other binning ran on the
@@ -115,6 +116,7 @@ JSB200_API unsigned long long jsb200_error_count(void);
 /* Test / measurement hooks (no reference equivalent). */
 /* key: "cull" (1 default; 0 disables the conservative warp-rectangle pre-filter),
  *      "cache" (1 default; 0 forces rasterize_bwd to re-bin instead of reusing the forward's),
+ *      "bwd2px" (1 default; 0 runs rasterize_bwd with one pixel per thread instead of two),
  *      "rowcol" (1 default; 0 builds the per-tile lists with the older counting distribution of
  *               tile_lists.cu instead of the two-level row/column distribution),
  *      "timing" (0 default; 1 brackets every stage with CUDA events, see jsb200_get_stage_times) */

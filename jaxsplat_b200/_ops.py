@@ -196,7 +196,7 @@ def render_bwd(mean3ds, scales, quats, viewmat, colors, opacities, background, c
                *, token, num_points, img_shape, f, c, glob_scale, clip_thresh, block_width,
                band=None):
     """rasterize_bwd + project_bwd in one native call (jsb200_render_bwd).  Returns
-    (v_mean3d, v_scale, v_quat, v_colors, v_opacity, v_xy, v_xy_abs, v_conic, v_cov2d, v_cov3d)."""
+    (v_mean3d, v_scale, v_quat, v_colors, v_opacity, v_xy, v_conic, v_cov2d, v_cov3d)."""
     import ctypes
 
     n, dev = num_points, mean3ds.device
@@ -213,8 +213,8 @@ def render_bwd(mean3ds, scales, quats, viewmat, colors, opacities, background, c
     outs = [_out((n, 3), torch.float32, dev), _out((n, 3), torch.float32, dev),
             _out((n, 4), torch.float32, dev), _out((n, 3), torch.float32, dev),
             _out((n, 1), torch.float32, dev), _out((n, 2), torch.float32, dev),
-            _out((n, 2), torch.float32, dev), _out((n, 3), torch.float32, dev),
-            _out((n, 3), torch.float32, dev), _out((n, 6), torch.float32, dev)]
+            _out((n, 3), torch.float32, dev), _out((n, 3), torch.float32, dev),
+            _out((n, 6), torch.float32, dev)]
     d = _ffi.make_descriptor(n, tuple(img_shape), tuple(f), tuple(c), glob_scale, clip_thresh,
                              block_width)
     if band is not None:

@@ -46,6 +46,7 @@ void set_error(const char *fmt, ...) {
 void note_launch(int n) { g_stats[6].fetch_add((unsigned long long)n); }
 
 extern bool g_disable_cull;
+extern bool g_bwd_one_pixel;
 static bool g_disable_cache = false;
 static bool g_disable_rowcol = false;
 
@@ -90,6 +91,7 @@ struct Ctx {
     DevBuf records, dkeys_a, dkeys_b, ids_a, ids_b, box_by_id, boxes, sort_n_scratch, chain;
     // I-scale
     DevBuf tile_keys, tile_vals, tile_ids, tile_scratch;
+    DevBuf abs_scratch;
     DevBuf bins, small;  // small: [fingerprint u64][total u64][err int x4][tickets u32 x8]
     unsigned long long *h_pinned = nullptr;  // [fingerprint][total][err...]
     cudaEvent_t ev_ready = nullptr;          // recorded after the D2H of `small`
@@ -128,7 +130,7 @@ struct Ctx {
     void release() {
         DevBuf *all[] = {&records, &dkeys_a, &dkeys_b, &ids_a, &ids_b, &box_by_id, &boxes,
                          &sort_n_scratch, &chain, &tile_keys, &tile_vals, &tile_ids, &tile_scratch,
-                         &bins, &small};
+                         &bins, &small, &abs_scratch};
         for (DevBuf *b : all) {
             if (b->p) cudaFree(b->p);
             b->p = nullptr;
@@ -629,7 +631,8 @@ static int render_bwd_impl(cudaStream_t stream, void **buf, const Descriptor &d,
     //      9 depths 10 radii 11 conics 12 compensation 13 cum_tiles_hit 14 final_Ts 15 final_idx
     //      16 v_out_img 17 v_out_img_alpha
     // out: 18 v_mean3d 19 v_scale 20 v_quat 21 v_colors 22 v_opacity
-    //      23 v_xy 24 v_xy_abs 25 v_conic 26 v_cov2d 27 v_cov3d   (intermediate cotangents)
+    //      23 v_xy 24 v_conic 25 v_cov2d 26 v_cov3d   (intermediate cotangents)
+    // v_xy_abs (an output of rasterize_bwd that nothing downstream reads) is not computed
     if (check_raster_desc(d)) return 1;
     const size_t n = d.num_points;
     if (n == 0) return 0;
@@ -641,8 +644,13 @@ static int render_bwd_impl(cudaStream_t stream, void **buf, const Descriptor &d,
     JSB_CUDA_OK(cudaMemsetAsync(buf[21], 0, n * 3 * 4, stream));
     JSB_CUDA_OK(cudaMemsetAsync(buf[22], 0, n * 4, stream));
     JSB_CUDA_OK(cudaMemsetAsync(buf[23], 0, n * 2 * 4, stream));
-    JSB_CUDA_OK(cudaMemsetAsync(buf[24], 0, n * 2 * 4, stream));
-    JSB_CUDA_OK(cudaMemsetAsync(buf[25], 0, n * 3 * 4, stream));
+    JSB_CUDA_OK(cudaMemsetAsync(buf[24], 0, n * 3 * 4, stream));
+    float *v_xy_abs = nullptr;
+    if (d.block_width != 16) {  // the generic rasteriser always writes it: library scratch
+        if (c->ensure(c->abs_scratch, n * 2 * 4)) return 1;
+        JSB_CUDA_OK(cudaMemsetAsync(c->abs_scratch.p, 0, n * 2 * 4, stream));
+        v_xy_abs = (float *)c->abs_scratch.p;
+    }
     const bool hit = !g_disable_cache && token != 0 && c->cache_valid && c->cache_has_records &&
                      c->cache_token == token && c->cache_n == d.num_points &&
                      c->cache_tiles == d.tiles_x * d.tiles_y && c->cache_tiles_x == d.tiles_x &&
@@ -670,14 +678,14 @@ static int render_bwd_impl(cudaStream_t stream, void **buf, const Descriptor &d,
         if (launch_raster_bwd(stream, raster_params(d), c->cache_ids, (const int2 *)c->bins.p,
                               (const SplatRecord *)c->records.p, (const float *)buf[6],
                               (const float *)buf[14], (const int *)buf[15], (const float *)buf[16],
-                              (const float *)buf[17], (float *)buf[23], (float *)buf[24],
-                              (float *)buf[25], (float *)buf[21], (float *)buf[22]))
+                              (const float *)buf[17], (float *)buf[23], v_xy_abs,
+                              (float *)buf[24], (float *)buf[21], (float *)buf[22]))
             return 1;
     }
     }
     // project_bwd with zero cotangents for depth and compensation (render uses neither)
     void *pbuf[18] = {buf[0], buf[1], buf[2], buf[3], buf[7], buf[8], buf[10], buf[11], buf[12],
-                      nullptr, buf[23], nullptr, buf[25], buf[18], buf[19], buf[20], buf[26], buf[27]};
+                      nullptr, buf[23], nullptr, buf[24], buf[18], buf[19], buf[20], buf[25], buf[26]};
     return project_bwd_impl(stream, pbuf, d);
 }
 
@@ -852,6 +860,7 @@ int jsb200_set_option(const char *key, int value) {
     if (!key) return 1;
     if (!strcmp(key, "cull")) { jsb::g_disable_cull = (value == 0); return 0; }
     if (!strcmp(key, "cache")) { jsb::g_disable_cache = (value == 0); return 0; }
+    if (!strcmp(key, "bwd2px")) { jsb::g_bwd_one_pixel = (value == 0); return 0; }
     if (!strcmp(key, "rowcol")) { jsb::g_disable_rowcol = (value == 0); return 0; }
     if (!strcmp(key, "timing")) { jsb::g_timing = (value != 0); return 0; }
     jsb::set_error("set_option: unknown key '%s'", key);

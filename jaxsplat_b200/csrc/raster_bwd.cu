@@ -195,6 +195,215 @@ raster_bwd16_kernel(const RasterParams p, const unsigned *__restrict__ ids_sorte
     }
 }
 
+// ---- two pixels per thread -------------------------------------------------------------------
+// Same algorithm, but a CTA is 4 warps and each warp owns an 8x8 quadrant of the tile: lane l
+// replays pixels (x, y) and (x, y + 4).  The two pixels' partial gradients are added in registers
+// before the cross-lane reduction, so the transpose / 22-lane sums / RED (a third of the
+// instructions of a visit) and the candidate bookkeeping are paid once per 64 pixels instead of
+// once per 32.  ABS = false (fused render: nothing consumes v_xy_abs) drops two of the eleven rows.
+// Row order of the reduction: rgb(3) conic(3) xy(2) opacity(1) xy_abs(2).
+constexpr int RB2 = 128;
+
+template <bool ABS, bool ACC>
+__device__ __forceinline__ void pair_grad2(bool valid, float alpha, float vis, float opac, float dx,
+                                           float dy, float cx, float cy, float cz, float r, float g,
+                                           float b, const float3 v_out, float v_out_alpha,
+                                           float T_final, const float3 bg, float &T, float3 &buf,
+                                           float *o) {
+    alpha = valid ? alpha : 0.f;
+    vis = valid ? vis : 0.f;
+    float ra;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ra) : "f"(1.f - alpha));
+    ra = valid ? ra : 1.f;
+    T = T * ra;
+    const float fac = alpha * T;
+    float va = v_out.x * (T * r - buf.x * ra);
+    va = fmaf(v_out.y, T * g - buf.y * ra, va);
+    va = fmaf(v_out.z, T * b - buf.z * ra, va);
+    va = fmaf(v_out_alpha, T_final * ra, va);
+    const float nb = ra * (-T_final);
+    va = fmaf(v_out.x, nb * bg.x, va);
+    va = fmaf(v_out.y, nb * bg.y, va);
+    va = fmaf(v_out.z, nb * bg.z, va);
+    buf.x = fmaf(fac, r, buf.x);
+    buf.y = fmaf(fac, g, buf.y);
+    buf.z = fmaf(fac, b, buf.z);
+    const float v_sigma = (vis * (-opac)) * va;
+    const float hs = v_sigma * 0.5f;
+    const float gx = fmaf(dy, cy, dx * cx) * v_sigma, gy = fmaf(dy, cz, dx * cy) * v_sigma;
+    if (ACC) {
+        o[0] = fmaf(v_out.x, fac, o[0]);
+        o[1] = fmaf(v_out.y, fac, o[1]);
+        o[2] = fmaf(v_out.z, fac, o[2]);
+        o[3] = fmaf(dx, dx * hs, o[3]);
+        o[4] = fmaf(dy, dx * v_sigma, o[4]);
+        o[5] = fmaf(dy, dy * hs, o[5]);
+        o[6] += gx;
+        o[7] += gy;
+        o[8] = fmaf(vis, va, o[8]);
+        if (ABS) { o[9] += fabsf(gx); o[10] += fabsf(gy); }
+    } else {
+        o[0] = v_out.x * fac;
+        o[1] = v_out.y * fac;
+        o[2] = v_out.z * fac;
+        o[3] = dx * (dx * hs);
+        o[4] = dy * (dx * v_sigma);
+        o[5] = dy * (dy * hs);
+        o[6] = gx;
+        o[7] = gy;
+        o[8] = vis * va;
+        if (ABS) { o[9] = fabsf(gx); o[10] = fabsf(gy); }
+    }
+}
+
+template <bool CULL, bool ABS>
+__global__ void __launch_bounds__(RB2, 6)
+raster_bwd16x2_kernel(const RasterParams p, const unsigned *__restrict__ ids_sorted,
+                      const int2 *__restrict__ tile_bins, const SplatRecord *__restrict__ records,
+                      const float *__restrict__ background, const float *__restrict__ final_Ts,
+                      const int *__restrict__ final_idx, const float *__restrict__ v_out_img,
+                      const float *__restrict__ v_out_alpha_img, float *__restrict__ v_xy,
+                      float *__restrict__ v_xy_abs, float *__restrict__ v_conic,
+                      float *__restrict__ v_colors, float *__restrict__ v_opacity) {
+    constexpr int NV = ABS ? 11 : 9;
+    constexpr int BATCH = 256;  // two staged entries per thread
+    __shared__ float4 sA[BATCH];
+    __shared__ float4 sB[BATCH];
+    __shared__ float sC[BATCH];
+    __shared__ unsigned sId[BATCH];
+    __shared__ unsigned char sMask[BATCH];
+    __shared__ int s_max[RB2 / 32];
+    __shared__ __align__(16) float sRed[(RB2 / 32) * NV * RED_STRIDE];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float *red = sRed + warp * NV * RED_STRIDE;
+    const unsigned tile = p.band_y0 * p.tiles_x + blockIdx.x;
+    const unsigned tile_y = tile / p.tiles_x, tile_x = tile - tile_y * p.tiles_x;
+    const unsigned j = tile_x * 16 + (warp & 1) * 8 + (lane & 7);
+    const unsigned i0 = tile_y * 16 + (warp >> 1) * 8 + (lane >> 3), i1 = i0 + 4;
+    const float px = (float)j + 0.5f, py0 = (float)i0 + 0.5f, py1 = (float)i1 + 0.5f;
+    const bool in0 = (i0 < p.img_h) && (j < p.img_w), in1 = (i1 < p.img_h) && (j < p.img_w);
+    const int2 range = tile_bins[tile];
+    // quadrant bit inside the 8-rectangle cull mask after folding rows: (m | m >> 2) has the
+    // quadrant's two 8x4 rectangles ORed at bit (warp & 1) + 4 * (warp >> 1)
+    const int qbit = (warp & 1) + 4 * (warp >> 1);
+
+    float Tf0 = 1.f, Tf1 = 1.f, voa0 = 0.f, voa1 = 0.f;
+    float3 vo0 = make_float3(0.f, 0.f, 0.f), vo1 = vo0;
+    int bf0 = -1, bf1 = -1;
+    if (in0) {
+        const size_t pix = (size_t)i0 * p.img_w + j;
+        Tf0 = final_Ts[pix];
+        bf0 = final_idx[pix];
+        vo0 = make_float3(v_out_img[pix * 3], v_out_img[pix * 3 + 1], v_out_img[pix * 3 + 2]);
+        voa0 = v_out_alpha_img[pix];
+    }
+    if (in1) {
+        const size_t pix = (size_t)i1 * p.img_w + j;
+        Tf1 = final_Ts[pix];
+        bf1 = final_idx[pix];
+        vo1 = make_float3(v_out_img[pix * 3], v_out_img[pix * 3 + 1], v_out_img[pix * 3 + 2]);
+        voa1 = v_out_alpha_img[pix];
+    }
+    const float3 bg = make_float3(__ldg(background), __ldg(background + 1), __ldg(background + 2));
+    float T0 = Tf0, T1 = Tf1;
+    float3 buf0 = make_float3(0.f, 0.f, 0.f), buf1 = buf0;
+
+    int wmax = max(bf0, bf1);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+    if (lane == 0) s_max[warp] = wmax;
+    __syncthreads();
+    int tmax = s_max[0];
+#pragma unroll
+    for (int w = 1; w < RB2 / 32; ++w) tmax = max(tmax, s_max[w]);
+    const int top = min(range.y - 1, tmax);
+    if (top < range.x) return;  // nothing in this tile was composited (uniform across the CTA)
+    const int num_batches = (top - range.x + BATCH) / BATCH;
+    const float tile_x0 = (float)(tile_x * 16), tile_y0 = (float)(tile_y * 16);
+
+    // lane L (even, L/2 < NV) owns output row L/2 of the reduced gradient
+    const int slot = lane >> 1;
+    float *out_base;
+    int out_stride;
+    if (slot < 3) { out_base = v_colors + slot; out_stride = 3; }
+    else if (slot < 6) { out_base = v_conic + (slot - 3); out_stride = 3; }
+    else if (slot < 8) { out_base = v_xy + (slot - 6); out_stride = 2; }
+    else if (slot < 9) { out_base = v_opacity; out_stride = 1; }
+    else { out_base = v_xy_abs + (slot - 9); out_stride = 2; }
+    const bool writer = ((lane & 1) == 0) && slot < NV;
+
+    for (int b = 0; b < num_batches; ++b) {
+        if (b) __syncthreads();
+        const int batch_end = top - BATCH * b;  // slot t holds sorted index batch_end - t
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int t = tid + h * RB2;
+            const int idx = batch_end - t;
+            unsigned mask = 0;
+            if (idx >= range.x) {
+                const unsigned g = ids_sorted[idx];
+                const float4 q0 = __ldg(&records[g].q0);
+                const float4 q1 = __ldg(&records[g].q1);
+                const float4 q2 = __ldg(&records[g].q2);
+                sA[t] = q0;
+                sB[t] = q1;
+                sC[t] = q2.x;
+                sId[t] = g;
+                mask = CULL ? cull_mask16(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, tile_x0, tile_y0) : 0xFFu;
+            }
+            sMask[t] = (unsigned char)(mask | (mask >> 2));
+        }
+        __syncthreads();
+
+#pragma unroll 1
+        for (int k = 0; k < BATCH / 32; ++k) {
+            // entries newer than the warp's largest final index cannot be valid for any lane
+            if (batch_end - (k * 32 + 31) > wmax) continue;
+            const unsigned m = sMask[k * 32 + lane];
+            unsigned bits = __ballot_sync(0xffffffffu, (m >> qbit) & 1u);
+            while (bits) {
+                const int t = k * 32 + __ffs(bits) - 1;
+                bits &= bits - 1;
+                const float4 a = sA[t];
+                const float4 bq = sB[t];
+                const float dx = fsub(a.x, px);
+                const float dy0 = fsub(a.y, py0), dy1 = fsub(a.y, py1);
+                const float sg0 = conic_sigma(a.w, bq.x, bq.y, dx, dy0);
+                const float sg1 = conic_sigma(a.w, bq.x, bq.y, dx, dy1);
+                const float vis0 = ex2_approx(fmul(sg0, kNegLog2e));
+                const float vis1 = ex2_approx(fmul(sg1, kNegLog2e));
+                const float al0 = fminf(fmul(a.z, vis0), 0.99f);
+                const float al1 = fminf(fmul(a.z, vis1), 0.99f);
+                const int sidx = batch_end - t;
+                const bool ok0 = in0 && (sidx <= bf0) && !(sg0 < 0.f) && !(al0 < kAlphaMin);
+                const bool ok1 = in1 && (sidx <= bf1) && !(sg1 < 0.f) && !(al1 < kAlphaMin);
+                if (!__any_sync(0xffffffffu, ok0 || ok1)) continue;
+                float v[NV];
+                const float cb = sC[t];
+                pair_grad2<ABS, false>(ok0, al0, vis0, a.z, dx, dy0, a.w, bq.x, bq.y, bq.z, bq.w, cb,
+                                       vo0, voa0, Tf0, bg, T0, buf0, v);
+                pair_grad2<ABS, true>(ok1, al1, vis1, a.z, dx, dy1, a.w, bq.x, bq.y, bq.z, bq.w, cb,
+                                      vo1, voa1, Tf1, bg, T1, buf1, v);
+                // transpose through shared memory: row r = value r of the 32 lanes
+                __syncwarp();
+#pragma unroll
+                for (int r = 0; r < NV; ++r) red[r * RED_STRIDE + lane] = v[r];
+                __syncwarp();
+                float total = 0.f;
+                if (lane < 2 * NV) {
+                    const float4 *row = reinterpret_cast<const float4 *>(red + (lane >> 1) * RED_STRIDE + (lane & 1) * 16);
+                    const float4 p0 = row[0], p1 = row[1], p2 = row[2], p3 = row[3];
+                    total = ((p0.x + p0.y) + (p0.z + p0.w)) + ((p1.x + p1.y) + (p1.z + p1.w)) +
+                            (((p2.x + p2.y) + (p2.z + p2.w)) + ((p3.x + p3.y) + (p3.z + p3.w)));
+                }
+                total += __shfl_xor_sync(0xffffffffu, total, 1);
+                if (writer) atomicAdd(out_base + sId[t] * (unsigned)out_stride, total);
+            }
+        }
+    }
+}
+
 // any block_width: one thread per pixel, per-thread atomics (semantics only, not tuned)
 __global__ void raster_bwd_generic_kernel(
     const RasterParams p, const unsigned *__restrict__ ids_sorted,
@@ -248,7 +457,20 @@ __global__ void raster_bwd_generic_kernel(
 }  // namespace
 
 extern bool g_disable_cull;
+bool g_bwd_one_pixel = false;  // option "bwd2px" = 0: the one-pixel-per-thread kernel
 
+template <bool CULL, bool ABS>
+static void launch_x2(cudaStream_t stream, unsigned tiles, const RasterParams &p,
+                      const unsigned *ids_sorted, const int2 *tile_bins, const SplatRecord *records,
+                      const float *background, const float *final_Ts, const int *final_idx,
+                      const float *v_out, const float *v_out_alpha, float *v_xy, float *v_xy_abs,
+                      float *v_conic, float *v_colors, float *v_opacity) {
+    raster_bwd16x2_kernel<CULL, ABS><<<tiles, RB2, 0, stream>>>(
+        p, ids_sorted, tile_bins, records, background, final_Ts, final_idx, v_out, v_out_alpha, v_xy,
+        v_xy_abs, v_conic, v_colors, v_opacity);
+}
+
+// v_xy_abs == nullptr: not computed (fused render; block_width 16 only)
 int launch_raster_bwd(cudaStream_t stream, const RasterParams &p, const unsigned *ids_sorted,
                       const int2 *tile_bins, const SplatRecord *records, const float *background,
                       const float *final_Ts, const int *final_idx, const float *v_out,
@@ -256,7 +478,19 @@ int launch_raster_bwd(cudaStream_t stream, const RasterParams &p, const unsigned
                       float *v_colors, float *v_opacity) {
     const unsigned tiles = p.tiles_x * (p.band_y1 - p.band_y0);
     if (tiles == 0) return 0;
-    if (p.block_width == 16) {
+    if (p.block_width == 16 && !(g_bwd_one_pixel && v_xy_abs)) {
+        if (v_xy_abs) {
+            if (g_disable_cull)
+                launch_x2<false, true>(stream, tiles, p, ids_sorted, tile_bins, records, background, final_Ts, final_idx, v_out, v_out_alpha, v_xy, v_xy_abs, v_conic, v_colors, v_opacity);
+            else
+                launch_x2<true, true>(stream, tiles, p, ids_sorted, tile_bins, records, background, final_Ts, final_idx, v_out, v_out_alpha, v_xy, v_xy_abs, v_conic, v_colors, v_opacity);
+        } else {
+            if (g_disable_cull)
+                launch_x2<false, false>(stream, tiles, p, ids_sorted, tile_bins, records, background, final_Ts, final_idx, v_out, v_out_alpha, v_xy, v_xy_abs, v_conic, v_colors, v_opacity);
+            else
+                launch_x2<true, false>(stream, tiles, p, ids_sorted, tile_bins, records, background, final_Ts, final_idx, v_out, v_out_alpha, v_xy, v_xy_abs, v_conic, v_colors, v_opacity);
+        }
+    } else if (p.block_width == 16) {
         if (g_disable_cull)
             raster_bwd16_kernel<false><<<tiles, RB, 0, stream>>>(
                 p, ids_sorted, tile_bins, records, background, final_Ts, final_idx, v_out,
@@ -266,6 +500,10 @@ int launch_raster_bwd(cudaStream_t stream, const RasterParams &p, const unsigned
                 p, ids_sorted, tile_bins, records, background, final_Ts, final_idx, v_out,
                 v_out_alpha, v_xy, v_xy_abs, v_conic, v_colors, v_opacity);
     } else {
+        if (!v_xy_abs) {
+            set_error("raster_bwd: block_width %u needs a v_xy_abs buffer", p.block_width);
+            return 1;
+        }
         dim3 grid(p.tiles_x, p.band_y1 - p.band_y0), block(p.block_width, p.block_width);
         raster_bwd_generic_kernel<<<grid, block, 0, stream>>>(
             p, ids_sorted, tile_bins, records, background, final_Ts, final_idx, v_out, v_out_alpha,

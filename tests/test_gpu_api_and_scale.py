@@ -238,6 +238,12 @@ def test_in_switch_allreduce_two_ranks():
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 
 
+def _bw8_scene():
+    s = synthetic.benchmark_scene(5000, (100, 136), scale_max=0.3, seed=12)
+    s.block_size = 8
+    return s
+
+
 def _grads_of(scene, target, fused):
     jsb.set_fused_render(fused)
     try:
@@ -248,7 +254,8 @@ def _grads_of(scene, target, fused):
 
 @pytest.mark.parametrize("scene_fn", [lambda: synthetic.make_config("C1"),
                                       lambda: synthetic.make_config("C2", num_points=40000),
-                                      lambda: synthetic.benchmark_scene(0 + 513, (40, 72), seed=2)])
+                                      lambda: synthetic.benchmark_scene(0 + 513, (40, 72), seed=2),
+                                      lambda: _bw8_scene()])
 def test_fused_render_equals_the_two_op_chain(scene_fn):
     """jsb200_render_fwd/bwd (one call per direction) vs project -> rasterize through autograd"""
     s = scene_fn()

@@ -296,3 +296,25 @@ def test_row_column_lists_equal_the_counting_distribution(case):
     if band is None:
         for a, b in zip(outs_a, outs_b):
             assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("scene_fn", [_adversarial_scene, lambda: synthetic.make_config("C2", num_points=30000),
+                                      lambda: synthetic.benchmark_scene(9000, (200, 120), scale_max=0.2, seed=21)])
+def test_two_pixels_per_thread_backward_equals_one_pixel_per_thread(scene_fn):
+    """raster_bwd16x2_kernel (two pixels per thread, default) vs raster_bwd16_kernel"""
+    s = scene_fn()
+    inp = G.scene_inputs(s)
+    kw, rkw = G.scene_kw(s)
+    H, W = s.img_shape
+    target = np.random.RandomState(2).rand(H, W, 3).astype(np.float32)
+    v_alpha = np.random.RandomState(3).rand(H, W, 1).astype(np.float32) * 1e-3
+    try:
+        _lib.set_option("bwd2px", 1)
+        a = _full_gpu(inp, kw, rkw, target, v_alpha)
+        _lib.set_option("bwd2px", 0)
+        b = _full_gpu(inp, kw, rkw, target, v_alpha)
+    finally:
+        _lib.set_option("bwd2px", 1)
+    for k in ("v_colors", "v_opacity", "v_xy", "v_xy_abs", "v_conic"):
+        ok, err, scale = grad_close(a[k], b[k], rel=1e-4)
+        assert ok, (k, err, scale)
