@@ -108,8 +108,10 @@ def algorithmic_bytes(stage, N, I, P, T, rows=0, tiles_x=120):
         "tile_offsets": rows * 8 + 3 * chunks * tiles_x * 4 + T * (4 + 8),
         # level-2 scatter: entries + run starts read, every id written once
         "tile_scatter": rows * 8 + chunks * tiles_x * 4 + I * 4,
-        "raster_fwd": P * 20 + I * 52,
-        "raster_bwd": P * 24 + I * (4 + 40 + 44),
+        # rasterisers: compulsory HBM bytes only (pixels in/out, every record once, the id list
+        # once, every gradient word once); the per-(tile, Gaussian) staging traffic is L2 hits
+        "raster_fwd": P * 20 + N * 48 + I * 4,
+        "raster_bwd": P * 24 + N * 48 + I * 4 + N * 36,
         "project_bwd": N * 188,
     }[stage]
 
@@ -184,10 +186,11 @@ def main():
         k = dict(kw)
         k["viewmat"] = view
         img = jsb.render(*params, **k)
-        # MSE and its gradient written out by hand (3 elementwise kernels instead of the 9 that
+        # MSE and its gradient written out by hand (sub, dot, scale instead of the 9 kernels that
         # autograd launches for ((img - tgt) ** 2).mean()); the render backward is autograd's
         diff = img.detach() - tgt
-        loss = (diff * diff).mean()
+        flat = diff.view(-1)
+        loss = torch.dot(flat, flat) / flat.numel()
         img.backward(gradient=diff * (2.0 / diff.numel()))
         if use_dist:
             # the five parameter gradients packed into the one flat (symmetric) buffer, summed
@@ -356,9 +359,14 @@ def main():
         out["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": d["gbs"], "peak": peak,
                            "unit": "GB/s", "frac": d["hbm_frac"], "traffic": traffic,
                            "peak_source": which_peak,
-                           "note": "the rasterisers are SM-issue bound, not HBM bound (no dense "
-                                   "contraction, no tensor cores): see 'issue' and DESIGN.md"}
-        # issue-slot view of the rasterisers: (tile,Gaussian,pixel) pairs the reference evaluates
+                           "note": "achieved = compulsory HBM bytes of the dominant stage / its "
+                                   "device time; the rasterisers are SM-issue bound, not HBM bound "
+                                   "(no dense contraction, no tensor cores; ncu: 75-78 % issue-slot "
+                                   "utilisation, 2 % DRAM throughput): see 'issue', 'stages' and "
+                                   "DESIGN.md section 5"}
+        # issue-slot view of the rasterisers: (tile, Gaussian, pixel) pairs the REFERENCE's kernels
+        # evaluate for this frame (I * 256) per second of ours, against the issue-slot roof of
+        # evaluating every one of them (15 slots each); > 1x the roof = pairs never evaluated
         pairs = I * 256
         out["issue"] = {k: {"pairs_per_s": pairs / (per_stage[k]["ms_per_launch"] * 1e-3),
                             "roof_pairs_per_s": 148 * 128 * (clocks["sm_mhz"] or 1965.0) * 1e6 / 15.0}

@@ -71,6 +71,7 @@ JSB200_API void jsb200_rasterize_bwd(jsb200_stream_t stream, void **buffers, con
  *               out: v_mean3d v_scale v_quat v_colors v_opacity | v_xy v_conic v_cov2d v_cov3d
  *                    (the last four: intermediate cotangents; v_xy_abs, which nothing downstream
  *                    of rasterize_bwd reads, is not computed)
+ * v_out_img_alpha may be NULL (= zero cotangent; block_width 16 only).
  * `opaque` is a full descriptor (f, c, glob_scale, clip_thresh set).  *token_out identifies the
  * binning this forward left in the per-(device, stream) workspace (0 = none); a render_bwd given
  * that token reuses it without any check or host synchronisation if no other binning ran on the

@@ -152,9 +152,9 @@ def _call_native(fn_name, tensors, opaque, *extra):
 
     from . import _lib
     for t in tensors:
-        if not t.is_cuda or not t.is_contiguous():
+        if t is not None and (not t.is_cuda or not t.is_contiguous()):
             raise ValueError(f"{fn_name}: every buffer must be a contiguous CUDA tensor")
-    bufs = (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+    bufs = (ctypes.c_void_p * len(tensors))(*[None if t is None else t.data_ptr() for t in tensors])
     stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
     rc = getattr(_lib.lib(), fn_name)(stream, bufs, opaque, len(opaque), *extra)
     if rc != 0:
@@ -209,11 +209,16 @@ def render_bwd(mean3ds, scales, quats, viewmat, colors, opacities, background, c
            _f32(conics, (n, 3), "conics"), _f32(compensation, (n, 1), "compensation"),
            _i32(cum_tiles_hit, (n, 1), "cum_tiles_hit"), _f32(final_Ts, (H, W, 1), "final_Ts"),
            _i32(final_idx, (H, W, 1), "final_idx"), _f32(v_img, (H, W, 3), "v_img"),
-           _f32(v_img_alpha, (H, W, 1), "v_img_alpha")]
+           # None = zero cotangent for the alpha image (16x16 tiles only)
+           None if (v_img_alpha is None and block_width == 16) else _f32(
+               torch.zeros((H, W, 1), dtype=torch.float32, device=dev) if v_img_alpha is None
+               else v_img_alpha, (H, W, 1), "v_img_alpha")]
+    # the four atomically accumulated gradients back to back: the library clears them in one go
+    acc = _out((n, 9), torch.float32, dev).reshape(-1)
     outs = [_out((n, 3), torch.float32, dev), _out((n, 3), torch.float32, dev),
-            _out((n, 4), torch.float32, dev), _out((n, 3), torch.float32, dev),
-            _out((n, 1), torch.float32, dev), _out((n, 2), torch.float32, dev),
-            _out((n, 3), torch.float32, dev), _out((n, 3), torch.float32, dev),
+            _out((n, 4), torch.float32, dev), acc[:3 * n].view(n, 3),
+            acc[3 * n:4 * n].view(n, 1), acc[4 * n:6 * n].view(n, 2),
+            acc[6 * n:9 * n].view(n, 3), _out((n, 3), torch.float32, dev),
             _out((n, 6), torch.float32, dev)]
     d = _ffi.make_descriptor(n, tuple(img_shape), tuple(f), tuple(c), glob_scale, clip_thresh,
                              block_width)

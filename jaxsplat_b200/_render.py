@@ -31,10 +31,9 @@ class _Render(torch.autograd.Function):
     @staticmethod
     def backward(ctx, v_img):
         saved = ctx.saved_tensors
-        H, W = ctx.desc.img_shape
-        v_alpha = torch.zeros((H, W, 1), dtype=torch.float32, device=v_img.device)
+        # render() exposes no alpha image: its cotangent is identically zero (None = not read)
         (v_mean3d, v_scale, v_quat, v_colors, v_opacity, *_rest) = _ops.render_bwd(
-            *saved, v_img.contiguous(), v_alpha, token=ctx.token, band=ctx.band,
+            *saved, v_img.contiguous(), None, token=ctx.token, band=ctx.band,
             **ctx.desc.kwargs())
         return None, None, v_mean3d, v_scale, v_quat, v_colors, v_opacity, None, None
 

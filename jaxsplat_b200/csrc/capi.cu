@@ -641,11 +641,22 @@ static int render_bwd_impl(cudaStream_t stream, void **buf, const Descriptor &d,
     if (!c) return 1;
     std::lock_guard<std::mutex> lk(c->mu);
     g_stats[1].fetch_add(1);
-    JSB_CUDA_OK(cudaMemsetAsync(buf[21], 0, n * 3 * 4, stream));
-    JSB_CUDA_OK(cudaMemsetAsync(buf[22], 0, n * 4, stream));
-    JSB_CUDA_OK(cudaMemsetAsync(buf[23], 0, n * 2 * 4, stream));
-    JSB_CUDA_OK(cudaMemsetAsync(buf[24], 0, n * 3 * 4, stream));
+    // the four accumulators are cleared with one memset when the caller laid them out back to
+    // back (the torch host layer does), else one by one
+    char *g0 = (char *)buf[21];
+    if ((char *)buf[22] == g0 + n * 12 && (char *)buf[23] == g0 + n * 16 && (char *)buf[24] == g0 + n * 24) {
+        JSB_CUDA_OK(cudaMemsetAsync(g0, 0, n * 36, stream));
+    } else {
+        JSB_CUDA_OK(cudaMemsetAsync(buf[21], 0, n * 3 * 4, stream));
+        JSB_CUDA_OK(cudaMemsetAsync(buf[22], 0, n * 4, stream));
+        JSB_CUDA_OK(cudaMemsetAsync(buf[23], 0, n * 2 * 4, stream));
+        JSB_CUDA_OK(cudaMemsetAsync(buf[24], 0, n * 3 * 4, stream));
+    }
     float *v_xy_abs = nullptr;
+    if (d.block_width != 16 && !buf[17]) {
+        set_error("render_bwd: block_width %u needs a v_out_img_alpha buffer", d.block_width);
+        return 1;
+    }
     if (d.block_width != 16) {  // the generic rasteriser always writes it: library scratch
         if (c->ensure(c->abs_scratch, n * 2 * 4)) return 1;
         JSB_CUDA_OK(cudaMemsetAsync(c->abs_scratch.p, 0, n * 2 * 4, stream));

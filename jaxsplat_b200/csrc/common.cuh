@@ -84,6 +84,20 @@ __device__ __forceinline__ float conic_sigma(float cx, float cy, float cz, float
     return ffma(d, dy, s);
 }
 
+// Asynchronous global -> shared copies (LDGSTS): the rasterisers stage the NEXT batch of splat
+// records with these while the current batch is being composited.
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)),
+                 "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void *smem, const void *gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem)),
+                 "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.wait_all;" ::: "memory");
+}
+
 __host__ __device__ inline unsigned ceil_div(unsigned a, unsigned b) { return (a + b - 1) / b; }
 
 // tile box of a projected Gaussian; reference helpers.h:9-32 (get_tile_bbox -> get_bbox).

@@ -267,10 +267,10 @@ raster_bwd16x2_kernel(const RasterParams p, const unsigned *__restrict__ ids_sor
                       float *__restrict__ v_colors, float *__restrict__ v_opacity) {
     constexpr int NV = ABS ? 11 : 9;
     constexpr int BATCH = 256;  // two staged entries per thread
-    __shared__ float4 sA[BATCH];
-    __shared__ float4 sB[BATCH];
-    __shared__ float sC[BATCH];
-    __shared__ unsigned sId[BATCH];
+    __shared__ float4 sA2[2][BATCH];  // double-buffered batches (cp.async staging)
+    __shared__ float4 sB2[2][BATCH];
+    __shared__ float sC2[2][BATCH];
+    __shared__ unsigned sId2[2][BATCH];
     __shared__ unsigned char sMask[BATCH];
     __shared__ int s_max[RB2 / 32];
     __shared__ __align__(16) float sRed[(RB2 / 32) * NV * RED_STRIDE];
@@ -296,14 +296,14 @@ raster_bwd16x2_kernel(const RasterParams p, const unsigned *__restrict__ ids_sor
         Tf0 = final_Ts[pix];
         bf0 = final_idx[pix];
         vo0 = make_float3(v_out_img[pix * 3], v_out_img[pix * 3 + 1], v_out_img[pix * 3 + 2]);
-        voa0 = v_out_alpha_img[pix];
+        voa0 = v_out_alpha_img ? v_out_alpha_img[pix] : 0.f;
     }
     if (in1) {
         const size_t pix = (size_t)i1 * p.img_w + j;
         Tf1 = final_Ts[pix];
         bf1 = final_idx[pix];
         vo1 = make_float3(v_out_img[pix * 3], v_out_img[pix * 3 + 1], v_out_img[pix * 3 + 2]);
-        voa1 = v_out_alpha_img[pix];
+        voa1 = v_out_alpha_img ? v_out_alpha_img[pix] : 0.f;
     }
     const float3 bg = make_float3(__ldg(background), __ldg(background + 1), __ldg(background + 2));
     float T0 = Tf0, T1 = Tf1;
@@ -333,23 +333,45 @@ raster_bwd16x2_kernel(const RasterParams p, const unsigned *__restrict__ ids_sor
     else { out_base = v_xy_abs + (slot - 9); out_stride = 2; }
     const bool writer = ((lane & 1) == 0) && slot < NV;
 
+    // Software pipeline (as in raster_fwd.cu): records of batch b+1 by cp.async into the other
+    // buffer and sorted ids of batch b+2 into registers while batch b is replayed.
+    auto load_id = [&](int bb, int h) -> unsigned {
+        const int idx = top - BATCH * bb - (tid + h * RB2);
+        return (bb < num_batches && idx >= range.x) ? ids_sorted[idx] : 0u;
+    };
+    auto issue = [&](int bb, int h, unsigned g) {
+        const int t = tid + h * RB2;
+        if (top - BATCH * bb - t >= range.x) {
+            const SplatRecord *r = records + g;
+            cp_async16(&sA2[bb & 1][t], &r->q0);
+            cp_async16(&sB2[bb & 1][t], &r->q1);
+            cp_async4(&sC2[bb & 1][t], &r->q2);
+            sId2[bb & 1][t] = g;
+        }
+    };
+    issue(0, 0, load_id(0, 0));
+    issue(0, 1, load_id(0, 1));
+    unsigned gn0 = load_id(1, 0), gn1 = load_id(1, 1);
+
     for (int b = 0; b < num_batches; ++b) {
-        if (b) __syncthreads();
+        cp_async_wait_all();
+        __syncthreads();  // batch b landed; every warp is done with batch b-1
         const int batch_end = top - BATCH * b;  // slot t holds sorted index batch_end - t
+        const int buf = b & 1;
+        const float4 *sA = sA2[buf];
+        const float4 *sB = sB2[buf];
+        const float *sC = sC2[buf];
+        const unsigned *sId = sId2[buf];
+        if (b + 1 < num_batches) { issue(b + 1, 0, gn0); issue(b + 1, 1, gn1); }
+        gn0 = load_id(b + 2, 0);
+        gn1 = load_id(b + 2, 1);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const int t = tid + h * RB2;
-            const int idx = batch_end - t;
             unsigned mask = 0;
-            if (idx >= range.x) {
-                const unsigned g = ids_sorted[idx];
-                const float4 q0 = __ldg(&records[g].q0);
-                const float4 q1 = __ldg(&records[g].q1);
-                const float4 q2 = __ldg(&records[g].q2);
-                sA[t] = q0;
-                sB[t] = q1;
-                sC[t] = q2.x;
-                sId[t] = g;
+            if (batch_end - t >= range.x) {
+                const float4 q0 = sA[t];
+                const float2 q1 = *reinterpret_cast<const float2 *>(&sB[t]);
                 mask = CULL ? cull_mask16(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, tile_x0, tile_y0) : 0xFFu;
             }
             sMask[t] = (unsigned char)(mask | (mask >> 2));

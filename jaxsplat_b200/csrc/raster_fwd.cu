@@ -18,7 +18,10 @@
 //     evaluated, which is where most of the reference's issue slots go;
 //   * per candidate the warp does 1 LDS.128 + 1 LDS.64 (broadcast) instead of 6 scalar LDS, and
 //     colours come from shared memory instead of three dependent global loads;
-//   * warps retire independently (ballot on `done`), the CTA retires on __syncthreads_count.
+//   * warps retire independently (ballot on `done`), the CTA retires on __syncthreads_count;
+//   * the staging is software-pipelined: the records of batch b+1 arrive by cp.async (LDGSTS,
+//     double-buffered shared memory) and the sorted ids of batch b+2 by a register prefetch while
+//     batch b is composited.
 #include "common.cuh"
 #include "kernels.cuh"
 #include "raster_cull.cuh"
@@ -34,9 +37,9 @@ raster_fwd16_kernel(const RasterParams p, const unsigned *__restrict__ ids_sorte
                     const int2 *__restrict__ tile_bins, const SplatRecord *__restrict__ records,
                     const float *__restrict__ background, float *__restrict__ final_Ts,
                     int *__restrict__ final_idx, float *__restrict__ out_img) {
-    __shared__ float4 sA[RB];        // x, y, opac, conic.x
-    __shared__ float4 sB[RB];        // conic.y, conic.z, r, g
-    __shared__ float sC[RB];         // b
+    __shared__ float4 sA[2][RB];     // x, y, opac, conic.x      (double-buffered batches)
+    __shared__ float4 sB[2][RB];     // conic.y, conic.z, r, g
+    __shared__ float sC[2][RB];      // b
     __shared__ unsigned char sMask[RB];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -56,20 +59,36 @@ raster_fwd16_kernel(const RasterParams p, const unsigned *__restrict__ ids_sorte
     int cur_idx = 0;
     float acc_r = 0.f, acc_g = 0.f, acc_b = 0.f;
 
+    // Software pipeline: while batch b is composited, the records of batch b+1 travel global ->
+    // shared (cp.async) and the sorted ids of batch b+2 travel to a register, so the two dependent
+    // gathers of the staging (id, then record) are off the critical path.
+    auto issue = [&](int b, unsigned g) {  // this thread's record of batch b -> buffer b & 1
+        if (range.x + RB * b + tid < range.y) {
+            const SplatRecord *r = records + g;
+            cp_async16(&sA[b & 1][tid], &r->q0);
+            cp_async16(&sB[b & 1][tid], &r->q1);
+            cp_async4(&sC[b & 1][tid], &r->q2);
+        }
+    };
+    auto load_id = [&](int b) -> unsigned {
+        const int idx = range.x + RB * b + tid;
+        return (b < num_batches && idx < range.y) ? ids_sorted[idx] : 0u;
+    };
+    if (num_batches > 0) issue(0, load_id(0));
+    unsigned g_next = load_id(1);
+
     for (int b = 0; b < num_batches; ++b) {
-        // also the barrier that protects the previous batch's shared data
+        cp_async_wait_all();
+        // batch b has landed; also the barrier that protects the previous batch's shared data
         if (__syncthreads_count(done) >= RB) break;
         const int batch_start = range.x + RB * b;
-        const int idx = batch_start + tid;
+        const int buf = b & 1;
+        if (b + 1 < num_batches) issue(b + 1, g_next);
+        g_next = load_id(b + 2);
         unsigned mask = 0;
-        if (idx < range.y) {
-            const unsigned g = ids_sorted[idx];
-            const float4 q0 = __ldg(&records[g].q0);
-            const float4 q1 = __ldg(&records[g].q1);
-            const float4 q2 = __ldg(&records[g].q2);
-            sA[tid] = q0;
-            sB[tid] = q1;
-            sC[tid] = q2.x;
+        if (batch_start + tid < range.y) {
+            const float4 q0 = sA[buf][tid];
+            const float2 q1 = *reinterpret_cast<const float2 *>(&sB[buf][tid]);
             mask = CULL ? cull_mask16(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, tile_x0, tile_y0) : 0xFFu;
         }
         sMask[tid] = (unsigned char)mask;
@@ -84,8 +103,8 @@ raster_fwd16_kernel(const RasterParams p, const unsigned *__restrict__ ids_sorte
             while (bits) {
                 const int t = k * 32 + __ffs(bits) - 1;
                 bits &= bits - 1;
-                const float4 a = sA[t];
-                const float2 cyz = *reinterpret_cast<const float2 *>(&sB[t]);
+                const float4 a = sA[buf][t];
+                const float2 cyz = *reinterpret_cast<const float2 *>(&sB[buf][t]);
                 const float dx = fsub(a.x, px), dy = fsub(a.y, py);
                 const float sigma = conic_sigma(a.w, cyz.x, cyz.y, dx, dy);
                 const float vis_e = ex2_approx(fmul(sigma, kNegLog2e));
@@ -96,10 +115,10 @@ raster_fwd16_kernel(const RasterParams p, const unsigned *__restrict__ ids_sorte
                         done = true;  // this Gaussian is not composited
                     } else {
                         const float vis = fmul(T, alpha);
-                        const float2 rg = *reinterpret_cast<const float2 *>(&sB[t].z);
+                        const float2 rg = *reinterpret_cast<const float2 *>(&sB[buf][t].z);
                         acc_r = ffma(vis, rg.x, acc_r);
                         acc_g = ffma(vis, rg.y, acc_g);
-                        acc_b = ffma(vis, sC[t], acc_b);
+                        acc_b = ffma(vis, sC[buf][t], acc_b);
                         T = next_T;
                         cur_idx = batch_start + t;
                     }
@@ -108,6 +127,7 @@ raster_fwd16_kernel(const RasterParams p, const unsigned *__restrict__ ids_sorte
             warp_done = __all_sync(0xffffffffu, done);
         }
     }
+    cp_async_wait_all();
 
     if (inside) {
         const size_t pix = (size_t)i * p.img_w + j;
