@@ -229,9 +229,8 @@ constexpr size_t SMALL_BYTES = 64 + 8 * kMaxStrips;
 // Enqueues prep (+fingerprint, +totals) and the D2H of the 64 control bytes, records ev_ready and
 // -- for a writing prep -- keeps the GPU busy with the N-scale depth sort, which does not depend
 // on the intersection count, so the host's wake-up after bin_prepare_wait() costs no GPU idle time.
-static int bin_prepare_enqueue(Ctx &c, const Descriptor &d, const float *xys, const float *depths,
-                               const int *radii, const float *conics, const float *opac,
-                               const float *colors, bool write = true, bool fingerprint = true) {
+// ensures the N-scale buffers and zeroes the control words; returns the band parameters
+static int bin_begin(Ctx &c, const Descriptor &d, bool write) {
     const unsigned n = d.num_points;
     cudaStream_t s = c.stream;
     if (!c.h_pinned) JSB_CUDA_OK(cudaHostAlloc((void **)&c.h_pinned, SMALL_BYTES, cudaHostAllocDefault));
@@ -253,21 +252,21 @@ static int bin_prepare_enqueue(Ctx &c, const Descriptor &d, const float *xys, co
     const BinParams bp = bin_params(d);
     const unsigned nstrips = ceil_div(bp.band_y1 - bp.band_y0, bp.strip_rows);
     if (nstrips > 1) JSB_CUDA_OK(cudaMemsetAsync((char *)c.small.p + 64, 0, 8 * nstrips, s));
-    unsigned long long *small64 = (unsigned long long *)c.small.p;
-    {
-    StageScope ss(&c, ST_BIN_PREP);
-    if (write && launch_bin_prep(s, bp, xys, depths, radii, conics, opac, colors,
-                                 (SplatRecord *)c.records.p, (unsigned *)c.dkeys_a.p,
-                                 (unsigned *)c.ids_a.p, (uint2 *)c.box_by_id.p, small64, true))
-        return 1;
-    if (fingerprint && launch_fingerprint(s, n, xys, depths, radii, conics, opac, colors, small64))
-        return 1;
-    }
+    return 0;
+}
+
+// D2H of the control bytes + ev_ready, then (writing prep) the N-scale depth sort, which does not
+// depend on the intersection count: the GPU stays busy while the host waits and wakes up
+static int bin_finish_enqueue(Ctx &c, const Descriptor &d, bool write) {
+    const unsigned n = d.num_points;
+    cudaStream_t s = c.stream;
+    if (n == 0) return 0;
+    const BinParams bp = bin_params(d);
+    const unsigned nstrips = ceil_div(bp.band_y1 - bp.band_y0, bp.strip_rows);
     JSB_CUDA_OK(cudaMemcpyAsync(c.h_pinned, c.small.p, 64 + (nstrips > 1 ? 8 * nstrips : 0),
                                 cudaMemcpyDeviceToHost, s));
     JSB_CUDA_OK(cudaEventRecord(c.ev_ready, s));
     if (write) {
-        // depth order of the Gaussians (N-scale, 32-bit keys): independent of the counts
         StageScope ss(&c, ST_DEPTH_SORT);
         bool in_b = false;
         if (radix_sort_pairs<uint32_t>(s, (uint32_t *)c.dkeys_a.p, (uint32_t *)c.dkeys_b.p,
@@ -277,6 +276,28 @@ static int bin_prepare_enqueue(Ctx &c, const Descriptor &d, const float *xys, co
         c.order_in_b = in_b;
     }
     return 0;
+}
+
+// Enqueues prep (+fingerprint, +totals), the D2H of the 64 control bytes and (writing prep) the
+// depth sort; bin_prepare_wait() then blocks the host until the control bytes have arrived.
+static int bin_prepare_enqueue(Ctx &c, const Descriptor &d, const float *xys, const float *depths,
+                               const int *radii, const float *conics, const float *opac,
+                               const float *colors, bool write = true, bool fingerprint = true) {
+    if (bin_begin(c, d, write)) return 1;
+    if (d.num_points == 0) return 0;
+    const BinParams bp = bin_params(d);
+    unsigned long long *small64 = (unsigned long long *)c.small.p;
+    {
+    StageScope ss(&c, ST_BIN_PREP);
+    if (write && launch_bin_prep(c.stream, bp, xys, depths, radii, conics, opac, colors,
+                                 (SplatRecord *)c.records.p, (unsigned *)c.dkeys_a.p,
+                                 (unsigned *)c.ids_a.p, (uint2 *)c.box_by_id.p, small64, true))
+        return 1;
+    if (fingerprint && launch_fingerprint(c.stream, d.num_points, xys, depths, radii, conics, opac,
+                                          colors, small64))
+        return 1;
+    }
+    return bin_finish_enqueue(c, d, write);
 }
 
 // Blocks the host until the control bytes of the last bin_prepare_enqueue have arrived.
@@ -432,10 +453,8 @@ static bool cache_hit(const Ctx &c, const Descriptor &d, unsigned long long I,
 }
 
 // ---- op bodies ---------------------------------------------------------------------------------
-static int project_fwd_impl(cudaStream_t stream, void **buf, const Descriptor &d) {
-    Ctx *c = get_ctx(stream);
-    if (!c) return 1;
-    std::lock_guard<std::mutex> lk(c->mu);
+static int project_fwd_locked(Ctx *c, cudaStream_t stream, void **buf, const Descriptor &d,
+                              const FusedPrep *fused) {
     const unsigned n = d.num_points;
     if (n == 0) return 0;
     if (d.block_width == 0) { set_error("block_width must be > 0"); return 1; }
@@ -455,7 +474,14 @@ static int project_fwd_impl(cudaStream_t stream, void **buf, const Descriptor &d
                               (const float *)buf[2], (const float *)buf[3], (float *)buf[4],
                               (float *)buf[5], (float *)buf[6], (int *)buf[7], (float *)buf[8],
                               (float *)buf[9], (int *)buf[10], (int *)buf[11],
-                              (unsigned *)c->chain.p);
+                              (unsigned *)c->chain.p, fused);
+}
+
+static int project_fwd_impl(cudaStream_t stream, void **buf, const Descriptor &d) {
+    Ctx *c = get_ctx(stream);
+    if (!c) return 1;
+    std::lock_guard<std::mutex> lk(c->mu);
+    return project_fwd_locked(c, stream, buf, d, nullptr);
 }
 
 static int project_bwd_impl(cudaStream_t stream, void **buf, const Descriptor &d) {
@@ -597,17 +623,32 @@ static int render_fwd_impl(cudaStream_t stream, void **buf, const Descriptor &d,
     if (check_raster_desc(d)) return 1;
     void *pbuf[12] = {buf[0], buf[1], buf[2], buf[3], buf[7], buf[8], buf[9], buf[10], buf[11],
                       buf[12], buf[13], buf[14]};
-    if (project_fwd_impl(stream, pbuf, d)) return 1;
     Ctx *c = get_ctx(stream);
     if (!c) return 1;
     std::lock_guard<std::mutex> lk(c->mu);
     g_stats[0].fetch_add(1);
     const RasterParams rp = raster_params(d);
     unsigned long long I = 0, fp = 0;
-    if (bin_prepare_enqueue(*c, d, (const float *)buf[8], (const float *)buf[9], (const int *)buf[10],
-                            (const float *)buf[11], (const float *)buf[5], (const float *)buf[4],
-                            /*write=*/true, /*fingerprint=*/false))
-        return 1;
+    if (d.pad == 0 && d.num_points != 0) {
+        // full frame: the projection kernel also packs records / depth keys / tile boxes
+        if (bin_begin(*c, d, /*write=*/true)) return 1;
+        FusedPrep f;
+        f.colors = (const float *)buf[4];
+        f.opacities = (const float *)buf[5];
+        f.records = (SplatRecord *)c->records.p;
+        f.depth_keys = (unsigned *)c->dkeys_a.p;
+        f.ids = (unsigned *)c->ids_a.p;
+        f.box_by_id = (uint2 *)c->box_by_id.p;
+        f.totals = (unsigned long long *)c->small.p;
+        if (project_fwd_locked(c, stream, pbuf, d, &f)) return 1;
+        if (bin_finish_enqueue(*c, d, /*write=*/true)) return 1;
+    } else {
+        if (project_fwd_locked(c, stream, pbuf, d, nullptr)) return 1;
+        if (bin_prepare_enqueue(*c, d, (const float *)buf[8], (const float *)buf[9],
+                                (const int *)buf[10], (const float *)buf[11], (const float *)buf[5],
+                                (const float *)buf[4], /*write=*/true, /*fingerprint=*/false))
+            return 1;
+    }
     if (bin_prepare_wait(*c, d, &I, &fp)) return 1;
     if (I == 0) {
         c->cache_valid = false;

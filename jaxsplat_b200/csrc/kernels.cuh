@@ -21,11 +21,24 @@ struct ProjectBwdParams {
     float fx, fy;
 };
 
+struct SplatRecord;
+// Fused render, full-frame band: project_fwd also produces what bin_prep would (binning.cu):
+// records, depth keys (0xFFFFFFFF for radii <= 0), identity ids, tile boxes, and adds the
+// intersection / row-entry totals to totals[1] / totals[4].
+struct FusedPrep {
+    const float *colors = nullptr, *opacities = nullptr;
+    SplatRecord *records = nullptr;
+    unsigned *depth_keys = nullptr, *ids = nullptr;
+    uint2 *box_by_id = nullptr;
+    unsigned long long *totals = nullptr;
+};
+
 int launch_project_fwd(cudaStream_t stream, const ProjectFwdParams &p, const float *means3d,
                        const float *scales, const float *quats, const float *viewmat,
                        float *cov3ds, float *xys, float *depths, int *radii, float *conics,
                        float *compensation, int *num_tiles_hit, int *cum_tiles_hit,
-                       unsigned *block_totals /* ceil(N/256) scratch words */);
+                       unsigned *block_totals /* ceil(N/256) scratch words */,
+                       const FusedPrep *fused = nullptr);
 
 int launch_project_bwd(cudaStream_t stream, const ProjectBwdParams &p, const float *means3d,
                        const float *scales, const float *quats, const float *viewmat,

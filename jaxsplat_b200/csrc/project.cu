@@ -153,6 +153,11 @@ __device__ __forceinline__ ProjOut project_one(float mx, float my, float mz, flo
     return o;
 }
 
+// FUSED (fused render, full-frame band): the kernel also does bin_prep's job (binning.cu) for the
+// Gaussian it just projected -- packed rasteriser record, depth key, identity id, tile box, and
+// the per-CTA totals of intersections and row entries -- so the projected arrays are not read
+// back by a second kernel.
+template <bool FUSED>
 __global__ void __launch_bounds__(PT)
 project_fwd_kernel(const ProjectFwdParams p, const float *__restrict__ means3d,
                    const float *__restrict__ scales, const float4 *__restrict__ quats,
@@ -160,9 +165,11 @@ project_fwd_kernel(const ProjectFwdParams p, const float *__restrict__ means3d,
                    float2 *__restrict__ xys, float *__restrict__ depths, int *__restrict__ radii,
                    float *__restrict__ conics, float *__restrict__ compensation,
                    int *__restrict__ num_tiles_hit, int *__restrict__ cum_tiles_hit,
-                   unsigned *__restrict__ block_totals) {
+                   unsigned *__restrict__ block_totals, const FusedPrep f) {
     __shared__ __align__(16) float s_buf[PT * 9];
+    __shared__ __align__(16) float s_color[FUSED ? PT * 3 : 4];
     __shared__ unsigned s_ws[PT / 32 + 1];
+    __shared__ unsigned s_rows;
     const int tid = threadIdx.x;
     const unsigned bid = blockIdx.x;
     const long long base = (long long)bid * PT;
@@ -171,6 +178,10 @@ project_fwd_kernel(const ProjectFwdParams p, const float *__restrict__ means3d,
     float *s_mean = s_buf, *s_scale = s_buf + PT * 3;
     slab_load<3, PT>(s_mean, means3d, base * 3, n * 3);
     slab_load<3, PT>(s_scale, scales, base * 3, n * 3);
+    if (FUSED) {
+        slab_load<3, PT>(s_color, f.colors, base * 3, n * 3);
+        if (tid == 0) s_rows = 0u;
+    }
     __syncthreads();
 
     ProjOut o;
@@ -182,9 +193,44 @@ project_fwd_kernel(const ProjectFwdParams p, const float *__restrict__ means3d,
                         s_scale[tid * 3], s_scale[tid * 3 + 1], s_scale[tid * 3 + 2], q, viewmat,
                         p);
     }
+    if (FUSED) {
+        unsigned rows = 0;
+        if (live) {
+            SplatRecord rec;
+            rec.q0 = make_float4(o.xy.x, o.xy.y, __ldg(f.opacities + idx), o.conic.x);
+            rec.q1 = make_float4(o.conic.y, o.conic.z, s_color[tid * 3], s_color[tid * 3 + 1]);
+            rec.q2 = make_float4(s_color[tid * 3 + 2], 0.f, 0.f, 0.f);
+            f.records[idx] = rec;
+            unsigned key = 0xFFFFFFFFu;
+            uint2 box = make_uint2(0u, 0u);  // {x0 | y0 << 16, width | height << 16}
+            if (o.radius > 0) {
+                // same expression as bin_prep_kernel: box from the stored xy and integer radius
+                unsigned x0, x1, y0, y1;
+                tile_bbox(o.xy.x, o.xy.y, (float)o.radius, p.block_width_f, p.tiles_x, p.tiles_y,
+                          x0, x1, y0, y1);
+                if (y1 > y0 && x1 > x0) {
+                    rows = y1 - y0;
+                    box = make_uint2(x0 | (y0 << 16), (x1 - x0) | ((y1 - y0) << 16));
+                }
+                key = __float_as_uint(o.depth);
+            }
+            f.depth_keys[idx] = key;
+            f.ids[idx] = (unsigned)idx;
+            f.box_by_id[idx] = box;
+        }
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) rows += __shfl_xor_sync(0xffffffffu, rows, s);
+        if ((tid & 31) == 0 && rows) atomicAdd(&s_rows, rows);
+    }
     unsigned total;
     const unsigned excl = cta_exclusive_scan<PT>((unsigned)o.tiles, &total, s_ws);  // syncs
-    if (tid == 0) block_totals[bid] = total;
+    if (tid == 0) {
+        block_totals[bid] = total;
+        if (FUSED && total) {  // one pair of same-address atomics per CTA
+            atomicAdd(f.totals + 1, (unsigned long long)total);
+            atomicAdd(f.totals + 4, (unsigned long long)s_rows);
+        }
+    }
     // stage AoS outputs (inputs are dead after the syncs inside the scan)
     float *s_cov = s_buf, *s_conic = s_buf + PT * 6;
     if (live) {
@@ -400,13 +446,19 @@ int launch_project_fwd(cudaStream_t stream, const ProjectFwdParams &p, const flo
                        const float *scales, const float *quats, const float *viewmat,
                        float *cov3ds, float *xys, float *depths, int *radii, float *conics,
                        float *compensation, int *num_tiles_hit, int *cum_tiles_hit,
-                       unsigned *block_totals) {
+                       unsigned *block_totals, const FusedPrep *fused) {
     if (p.num_points == 0) return 0;
     const unsigned blocks = ceil_div(p.num_points, PT);
-    project_fwd_kernel<<<blocks, PT, 0, stream>>>(
-        p, means3d, scales, reinterpret_cast<const float4 *>(quats), viewmat, cov3ds,
-        reinterpret_cast<float2 *>(xys), depths, radii, conics, compensation, num_tiles_hit,
-        cum_tiles_hit, block_totals);
+    if (fused)
+        project_fwd_kernel<true><<<blocks, PT, 0, stream>>>(
+            p, means3d, scales, reinterpret_cast<const float4 *>(quats), viewmat, cov3ds,
+            reinterpret_cast<float2 *>(xys), depths, radii, conics, compensation, num_tiles_hit,
+            cum_tiles_hit, block_totals, *fused);
+    else
+        project_fwd_kernel<false><<<blocks, PT, 0, stream>>>(
+            p, means3d, scales, reinterpret_cast<const float4 *>(quats), viewmat, cov3ds,
+            reinterpret_cast<float2 *>(xys), depths, radii, conics, compensation, num_tiles_hit,
+            cum_tiles_hit, block_totals, FusedPrep{});
     JSB_CUDA_OK(cudaGetLastError());
     note_launch();
     // cum_tiles_hit = CTA-local inclusive counts + exclusive scan of the CTA totals
