@@ -204,12 +204,14 @@ raster_bwd16_kernel(const RasterParams p, const unsigned *__restrict__ ids_sorte
 // Row order of the reduction: rgb(3) conic(3) xy(2) opacity(1) xy_abs(2).
 constexpr int RB2 = 128;
 
+// tfc = T_final * (v_out_alpha - <v_out, background>): the two background/alpha terms of the
+// reference's v_alpha (backward.cu:283-291) are both proportional to T_final * ra, so they fold
+// into one FMA per pair with a per-pixel constant.
 template <bool ABS, bool ACC>
 __device__ __forceinline__ void pair_grad2(bool valid, float alpha, float vis, float opac, float dx,
                                            float dy, float cx, float cy, float cz, float r, float g,
-                                           float b, const float3 v_out, float v_out_alpha,
-                                           float T_final, const float3 bg, float &T, float3 &buf,
-                                           float *o) {
+                                           float b, const float3 v_out, float tfc, float &T,
+                                           float3 &buf, float *o) {
     alpha = valid ? alpha : 0.f;
     vis = valid ? vis : 0.f;
     float ra;
@@ -220,11 +222,7 @@ __device__ __forceinline__ void pair_grad2(bool valid, float alpha, float vis, f
     float va = v_out.x * (T * r - buf.x * ra);
     va = fmaf(v_out.y, T * g - buf.y * ra, va);
     va = fmaf(v_out.z, T * b - buf.z * ra, va);
-    va = fmaf(v_out_alpha, T_final * ra, va);
-    const float nb = ra * (-T_final);
-    va = fmaf(v_out.x, nb * bg.x, va);
-    va = fmaf(v_out.y, nb * bg.y, va);
-    va = fmaf(v_out.z, nb * bg.z, va);
+    va = fmaf(tfc, ra, va);
     buf.x = fmaf(fac, r, buf.x);
     buf.y = fmaf(fac, g, buf.y);
     buf.z = fmaf(fac, b, buf.z);
@@ -306,6 +304,8 @@ raster_bwd16x2_kernel(const RasterParams p, const unsigned *__restrict__ ids_sor
         voa1 = v_out_alpha_img ? v_out_alpha_img[pix] : 0.f;
     }
     const float3 bg = make_float3(__ldg(background), __ldg(background + 1), __ldg(background + 2));
+    const float tfc0 = Tf0 * (voa0 - (vo0.x * bg.x + vo0.y * bg.y + vo0.z * bg.z));
+    const float tfc1 = Tf1 * (voa1 - (vo1.x * bg.x + vo1.y * bg.y + vo1.z * bg.z));
     float T0 = Tf0, T1 = Tf1;
     float3 buf0 = make_float3(0.f, 0.f, 0.f), buf1 = buf0;
 
@@ -404,9 +404,9 @@ raster_bwd16x2_kernel(const RasterParams p, const unsigned *__restrict__ ids_sor
                 float v[NV];
                 const float cb = sC[t];
                 pair_grad2<ABS, false>(ok0, al0, vis0, a.z, dx, dy0, a.w, bq.x, bq.y, bq.z, bq.w, cb,
-                                       vo0, voa0, Tf0, bg, T0, buf0, v);
+                                       vo0, tfc0, T0, buf0, v);
                 pair_grad2<ABS, true>(ok1, al1, vis1, a.z, dx, dy1, a.w, bq.x, bq.y, bq.z, bq.w, cb,
-                                      vo1, voa1, Tf1, bg, T1, buf1, v);
+                                      vo1, tfc1, T1, buf1, v);
                 // transpose through shared memory: row r = value r of the 32 lanes
                 __syncwarp();
 #pragma unroll
