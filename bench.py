@@ -164,6 +164,8 @@ def main():
     if args.impl == "ours":
         if os.environ.get("JSB_ROWCOL") == "0":
             _lib.set_option("rowcol", 0)
+        if os.environ.get("JSB_FWD2PX") == "0":
+            _lib.set_option("fwd2px", 0)
         if os.environ.get("JSB_BWD2PX") == "0":
             _lib.set_option("bwd2px", 0)
         if os.environ.get("JSB_FUSED") == "0":

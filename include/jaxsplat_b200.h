@@ -117,7 +117,8 @@ JSB200_API unsigned long long jsb200_error_count(void);
 /* Test / measurement hooks (no reference equivalent). */
 /* key: "cull" (1 default; 0 disables the conservative warp-rectangle pre-filter),
  *      "cache" (1 default; 0 forces rasterize_bwd to re-bin instead of reusing the forward's),
- *      "bwd2px" (1 default; 0 runs rasterize_bwd with one pixel per thread instead of two),
+ *      "fwd2px" / "bwd2px" (1 default; 0 runs rasterize_fwd / rasterize_bwd with one pixel per
+ *               thread instead of two),
  *      "rowcol" (1 default; 0 builds the per-tile lists with the older counting distribution of
  *               tile_lists.cu instead of the two-level row/column distribution),
  *      "timing" (0 default; 1 brackets every stage with CUDA events, see jsb200_get_stage_times) */

@@ -140,6 +140,154 @@ raster_fwd16_kernel(const RasterParams p, const unsigned *__restrict__ ids_sorte
     }
 }
 
+// ---- two pixels per thread -------------------------------------------------------------------
+// A CTA is 4 warps and each warp owns an 8x8 quadrant of the tile: lane l composites pixels (x, y)
+// and (x, y + 4) of the quadrant.  The candidate walk, the record loads, dx and the two conic
+// products that depend only on dx are paid once per two pixels (about a third of the issue slots
+// of a visit); every per-pixel operation keeps the reference's rounding order, so the outputs
+// stay bit-identical.
+constexpr int RF2 = 128;
+
+template <bool CULL>
+__global__ void __launch_bounds__(RF2, 8)
+raster_fwd16x2_kernel(const RasterParams p, const unsigned *__restrict__ ids_sorted,
+                      const int2 *__restrict__ tile_bins, const SplatRecord *__restrict__ records,
+                      const float *__restrict__ background, float *__restrict__ final_Ts,
+                      int *__restrict__ final_idx, float *__restrict__ out_img) {
+    constexpr int BATCH = 256;  // two staged entries per thread
+    __shared__ float4 sA[2][BATCH];
+    __shared__ float4 sB[2][BATCH];
+    __shared__ float sC[2][BATCH];
+    __shared__ unsigned char sMask[BATCH];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned tile = p.band_y0 * p.tiles_x + blockIdx.x;
+    const unsigned tile_y = tile / p.tiles_x, tile_x = tile - tile_y * p.tiles_x;
+    const unsigned j = tile_x * 16 + (warp & 1) * 8 + (lane & 7);
+    const unsigned i0 = tile_y * 16 + (warp >> 1) * 8 + (lane >> 3), i1 = i0 + 4;
+    const float px = (float)j + 0.5f, py0 = (float)i0 + 0.5f, py1 = (float)i1 + 0.5f;
+    const bool in0 = (i0 < p.img_h) && (j < p.img_w), in1 = (i1 < p.img_h) && (j < p.img_w);
+    bool done0 = !in0, done1 = !in1;
+    const int qbit = (warp & 1) + 4 * (warp >> 1);  // quadrant bit of the row-folded cull mask
+
+    const int2 range = tile_bins[tile];
+    const int num_batches = (range.y - range.x + BATCH - 1) / BATCH;
+    const float tile_x0 = (float)(tile_x * 16), tile_y0 = (float)(tile_y * 16);
+
+    float T0 = 1.f, T1 = 1.f;
+    int cur0 = 0, cur1 = 0;
+    float r0 = 0.f, g0 = 0.f, b0 = 0.f, r1 = 0.f, g1 = 0.f, b1 = 0.f;
+
+    auto load_id = [&](int b, int h) -> unsigned {
+        const int idx = range.x + BATCH * b + tid + h * RF2;
+        return (b < num_batches && idx < range.y) ? ids_sorted[idx] : 0u;
+    };
+    auto issue = [&](int b, int h, unsigned g) {
+        const int t = tid + h * RF2;
+        if (range.x + BATCH * b + t < range.y) {
+            const SplatRecord *r = records + g;
+            cp_async16(&sA[b & 1][t], &r->q0);
+            cp_async16(&sB[b & 1][t], &r->q1);
+            cp_async4(&sC[b & 1][t], &r->q2);
+        }
+    };
+    if (num_batches > 0) { issue(0, 0, load_id(0, 0)); issue(0, 1, load_id(0, 1)); }
+    unsigned gn0 = load_id(1, 0), gn1 = load_id(1, 1);
+
+    for (int b = 0; b < num_batches; ++b) {
+        cp_async_wait_all();
+        if (__syncthreads_count(done0 && done1) >= RF2) break;
+        const int batch_start = range.x + BATCH * b;
+        const int buf = b & 1;
+        if (b + 1 < num_batches) { issue(b + 1, 0, gn0); issue(b + 1, 1, gn1); }
+        gn0 = load_id(b + 2, 0);
+        gn1 = load_id(b + 2, 1);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int t = tid + h * RF2;
+            unsigned mask = 0;
+            if (batch_start + t < range.y) {
+                const float4 q0 = sA[buf][t];
+                const float2 q1 = *reinterpret_cast<const float2 *>(&sB[buf][t]);
+                mask = CULL ? cull_mask16(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, tile_x0, tile_y0) : 0xFFu;
+            }
+            sMask[t] = (unsigned char)(mask | (mask >> 2));
+        }
+        __syncthreads();
+
+        bool warp_done = __all_sync(0xffffffffu, done0 && done1);
+#pragma unroll
+        for (int k = 0; k < BATCH / 32; ++k) {
+            if (warp_done) continue;
+            const unsigned m = sMask[k * 32 + lane];
+            unsigned bits = __ballot_sync(0xffffffffu, (m >> qbit) & 1u);
+            while (bits) {
+                const int t = k * 32 + __ffs(bits) - 1;
+                bits &= bits - 1;
+                const float4 a = sA[buf][t];
+                const float4 bq = sB[buf][t];
+                const float dx = fsub(a.x, px);
+                const float dy0 = fsub(a.y, py0), dy1 = fsub(a.y, py1);
+                const float sg0 = conic_sigma(a.w, bq.x, bq.y, dx, dy0);
+                const float sg1 = conic_sigma(a.w, bq.x, bq.y, dx, dy1);
+                const float al0 = fminf(fmul(a.z, ex2_approx(fmul(sg0, kNegLog2e))), 0.999f);
+                const float al1 = fminf(fmul(a.z, ex2_approx(fmul(sg1, kNegLog2e))), 0.999f);
+                const bool ok0 = !done0 && !(sg0 < 0.f) && !(al0 < kAlphaMin);
+                const bool ok1 = !done1 && !(sg1 < 0.f) && !(al1 < kAlphaMin);
+                if (ok0 || ok1) {
+                    const float cb = sC[buf][t];
+                    if (ok0) {
+                        const float next_T = fmul(T0, fsub(1.f, al0));
+                        if (next_T <= kTmin) {
+                            done0 = true;  // this Gaussian is not composited
+                        } else {
+                            const float vis = fmul(T0, al0);
+                            r0 = ffma(vis, bq.z, r0);
+                            g0 = ffma(vis, bq.w, g0);
+                            b0 = ffma(vis, cb, b0);
+                            T0 = next_T;
+                            cur0 = batch_start + t;
+                        }
+                    }
+                    if (ok1) {
+                        const float next_T = fmul(T1, fsub(1.f, al1));
+                        if (next_T <= kTmin) {
+                            done1 = true;
+                        } else {
+                            const float vis = fmul(T1, al1);
+                            r1 = ffma(vis, bq.z, r1);
+                            g1 = ffma(vis, bq.w, g1);
+                            b1 = ffma(vis, cb, b1);
+                            T1 = next_T;
+                            cur1 = batch_start + t;
+                        }
+                    }
+                }
+            }
+            warp_done = __all_sync(0xffffffffu, done0 && done1);
+        }
+    }
+    cp_async_wait_all();
+
+    const float bg0 = __ldg(background), bg1 = __ldg(background + 1), bg2 = __ldg(background + 2);
+    if (in0) {
+        const size_t pix = (size_t)i0 * p.img_w + j;
+        final_Ts[pix] = T0;
+        final_idx[pix] = cur0;
+        out_img[pix * 3 + 0] = ffma(T0, bg0, r0);
+        out_img[pix * 3 + 1] = ffma(T0, bg1, g0);
+        out_img[pix * 3 + 2] = ffma(T0, bg2, b0);
+    }
+    if (in1) {
+        const size_t pix = (size_t)i1 * p.img_w + j;
+        final_Ts[pix] = T1;
+        final_idx[pix] = cur1;
+        out_img[pix * 3 + 0] = ffma(T1, bg0, r1);
+        out_img[pix * 3 + 1] = ffma(T1, bg1, g1);
+        out_img[pix * 3 + 2] = ffma(T1, bg2, b1);
+    }
+}
+
 // Any block_width in [1,16]: one CTA of bw*bw threads per tile, thread (ty,tx) = pixel, same
 // staging, no culling.  Semantics only; block_size 16 is the tuned case.
 __global__ void raster_fwd_generic_kernel(const RasterParams p,
@@ -222,13 +370,23 @@ __global__ void fill_background_kernel(const float *__restrict__ background, siz
 }  // namespace
 
 bool g_disable_cull = false;  // test hook (capi: jsb200_set_option)
+bool g_fwd_one_pixel = false;  // option "fwd2px" = 0: the one-pixel-per-thread kernel
 
 int launch_raster_fwd(cudaStream_t stream, const RasterParams &p, const unsigned *ids_sorted,
                       const int2 *tile_bins, const SplatRecord *records, const float *background,
                       float *final_Ts, int *final_idx, float *out_img) {
     const unsigned tiles = p.tiles_x * (p.band_y1 - p.band_y0);
     if (tiles == 0) return 0;
-    if (p.block_width == 16) {
+    if (p.block_width == 16 && !g_fwd_one_pixel) {
+        if (g_disable_cull)
+            raster_fwd16x2_kernel<false><<<tiles, RF2, 0, stream>>>(p, ids_sorted, tile_bins, records,
+                                                                    background, final_Ts, final_idx,
+                                                                    out_img);
+        else
+            raster_fwd16x2_kernel<true><<<tiles, RF2, 0, stream>>>(p, ids_sorted, tile_bins, records,
+                                                                   background, final_Ts, final_idx,
+                                                                   out_img);
+    } else if (p.block_width == 16) {
         if (g_disable_cull)
             raster_fwd16_kernel<false><<<tiles, RB, 0, stream>>>(p, ids_sorted, tile_bins, records,
                                                                  background, final_Ts, final_idx,
