@@ -63,11 +63,11 @@ JSB200_API void jsb200_rasterize_bwd(jsb200_stream_t stream, void **buffers, con
  * jaxsplat/__init__.py:54-70 = project (lib/ops.cu:12-61) then rasterize (lib/ops.cu:107-170) and,
  * for the backward, rasterize_bwd (lib/ops.cu:172-235) then project_bwd (lib/ops.cu:63-105)).
  *   render_fwd  in : means3d scales quats viewmat colors opacities background
- *               out: cov3ds xys depths radii conics compensation num_tiles_hit cum_tiles_hit
- *                    final_Ts final_idx out_img          (the two ops' results, same layouts)
+ *               out: cov3ds xys depths radii conics compensation final_Ts final_idx out_img
+ *                    (the two ops' results, same layouts, minus num_tiles_hit / cum_tiles_hit,
+ *                    which nothing downstream reads)
  *   render_bwd  in : means3d scales quats viewmat colors opacities background cov3ds xys depths
- *                    radii conics compensation cum_tiles_hit final_Ts final_idx v_out_img
- *                    v_out_img_alpha
+ *                    radii conics compensation final_Ts final_idx v_out_img v_out_img_alpha
  *               out: v_mean3d v_scale v_quat v_colors v_opacity | v_xy v_conic v_cov2d v_cov3d
  *                    (the last four: intermediate cotangents; v_xy_abs, which nothing downstream
  *                    of rasterize_bwd reads, is not computed)

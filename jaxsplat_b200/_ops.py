@@ -166,8 +166,8 @@ def _call_native(fn_name, tensors, opaque, *extra):
 def render_fwd(mean3ds, scales, quats, viewmat, colors, opacities, background, *, num_points,
                img_shape, f, c, glob_scale, clip_thresh, block_width, band=None):
     """project_fwd + binning + rasterize_fwd in one native call (jsb200_render_fwd).  Returns
-    ((cov3ds, xys, depths, radii, conics, compensation, num_tiles_hit, cum_tiles_hit, final_Ts,
-    final_idx, img), token); outputs are bit-identical to the two-op chain."""
+    ((cov3ds, xys, depths, radii, conics, compensation, final_Ts, final_idx, img), token);
+    outputs are bit-identical to the two-op chain."""
     import ctypes
 
     n, dev = num_points, mean3ds.device
@@ -179,7 +179,6 @@ def render_fwd(mean3ds, scales, quats, viewmat, colors, opacities, background, *
     outs = [_out((n, 6), torch.float32, dev), _out((n, 2), torch.float32, dev),
             _out((n, 1), torch.float32, dev), _out((n, 1), torch.int32, dev),
             _out((n, 3), torch.float32, dev), _out((n, 1), torch.float32, dev),
-            _out((n, 1), torch.int32, dev), _out((n, 1), torch.int32, dev),
             _out((H, W, 1), torch.float32, dev), _out((H, W, 1), torch.int32, dev),
             _out((H, W, 3), torch.float32, dev)]
     d = _ffi.make_descriptor(n, tuple(img_shape), tuple(f), tuple(c), glob_scale, clip_thresh,
@@ -192,7 +191,7 @@ def render_fwd(mean3ds, scales, quats, viewmat, colors, opacities, background, *
 
 
 def render_bwd(mean3ds, scales, quats, viewmat, colors, opacities, background, cov3ds, xys, depths,
-               radii, conics, compensation, cum_tiles_hit, final_Ts, final_idx, v_img, v_img_alpha,
+               radii, conics, compensation, final_Ts, final_idx, v_img, v_img_alpha,
                *, token, num_points, img_shape, f, c, glob_scale, clip_thresh, block_width,
                band=None):
     """rasterize_bwd + project_bwd in one native call (jsb200_render_bwd).  Returns
@@ -207,7 +206,7 @@ def render_bwd(mean3ds, scales, quats, viewmat, colors, opacities, background, c
            _f32(background, (3,), "background"), _f32(cov3ds, (n, 6), "cov3ds"),
            _f32(xys, (n, 2), "xys"), _f32(depths, (n, 1), "depths"), _i32(radii, (n, 1), "radii"),
            _f32(conics, (n, 3), "conics"), _f32(compensation, (n, 1), "compensation"),
-           _i32(cum_tiles_hit, (n, 1), "cum_tiles_hit"), _f32(final_Ts, (H, W, 1), "final_Ts"),
+           _f32(final_Ts, (H, W, 1), "final_Ts"),
            _i32(final_idx, (H, W, 1), "final_idx"), _f32(v_img, (H, W, 3), "v_img"),
            # None = zero cotangent for the alpha image (16x16 tiles only)
            None if (v_img_alpha is None and block_width == 16) else _f32(

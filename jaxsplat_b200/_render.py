@@ -19,13 +19,13 @@ class _Render(torch.autograd.Function):
     @staticmethod
     def forward(ctx, desc: ProjectDescriptor, band, means3d, scales, quats, colors, opacities,
                 viewmat, background):
-        (cov3ds, xys, depths, radii, conics, compensation, _num_tiles_hit, cum_tiles_hit, final_Ts,
-         final_idx, img), token = _ops.render_fwd(means3d, scales, quats, viewmat, colors,
-                                                  opacities, background, band=band, **desc.kwargs())
+        (cov3ds, xys, depths, radii, conics, compensation, final_Ts, final_idx,
+         img), token = _ops.render_fwd(means3d, scales, quats, viewmat, colors, opacities,
+                                       background, band=band, **desc.kwargs())
         ctx.desc, ctx.band, ctx.token = desc, band, token
         ctx.save_for_backward(means3d, scales, quats, viewmat, colors, opacities, background,
-                              cov3ds, xys, depths, radii, conics, compensation, cum_tiles_hit,
-                              final_Ts, final_idx)
+                              cov3ds, xys, depths, radii, conics, compensation, final_Ts,
+                              final_idx)
         return img
 
     @staticmethod

@@ -618,12 +618,12 @@ static int rasterize_bwd_impl(cudaStream_t stream, void **buf, const Descriptor 
 static int render_fwd_impl(cudaStream_t stream, void **buf, const Descriptor &d,
                            unsigned long long *token) {
     // in : 0 means3d 1 scales 2 quats 3 viewmat 4 colors 5 opacities 6 background
-    // out: 7 cov3ds 8 xys 9 depths 10 radii 11 conics 12 compensation 13 num_tiles_hit
-    //      14 cum_tiles_hit 15 final_Ts 16 final_idx 17 out_img
+    // out: 7 cov3ds 8 xys 9 depths 10 radii 11 conics 12 compensation 13 final_Ts 14 final_idx
+    //      15 out_img   (num_tiles_hit / cum_tiles_hit are not produced: nothing reads them)
     if (token) *token = 0;
     if (check_raster_desc(d)) return 1;
     void *pbuf[12] = {buf[0], buf[1], buf[2], buf[3], buf[7], buf[8], buf[9], buf[10], buf[11],
-                      buf[12], buf[13], buf[14]};
+                      buf[12], nullptr, nullptr};
     Ctx *c = get_ctx(stream);
     if (!c) return 1;
     std::lock_guard<std::mutex> lk(c->mu);
@@ -654,8 +654,8 @@ static int render_fwd_impl(cudaStream_t stream, void **buf, const Descriptor &d,
     if (I == 0) {
         c->cache_valid = false;
         g_stats[4].store(0);
-        return launch_fill_background(stream, rp, (const float *)buf[6], (float *)buf[15],
-                                      (int *)buf[16], (float *)buf[17]);
+        return launch_fill_background(stream, rp, (const float *)buf[6], (float *)buf[13],
+                                      (int *)buf[14], (float *)buf[15]);
     }
     if (bin_sort(*c, d, I, 0)) return 1;
     c->cache_has_records = true;
@@ -664,16 +664,16 @@ static int render_fwd_impl(cudaStream_t stream, void **buf, const Descriptor &d,
     StageScope ss(c, ST_RASTER_FWD);
     return launch_raster_fwd(stream, rp, c->cache_ids, (const int2 *)c->bins.p,
                              (const SplatRecord *)c->records.p, (const float *)buf[6],
-                             (float *)buf[15], (int *)buf[16], (float *)buf[17]);
+                             (float *)buf[13], (int *)buf[14], (float *)buf[15]);
 }
 
 static int render_bwd_impl(cudaStream_t stream, void **buf, const Descriptor &d,
                            unsigned long long token) {
     // in : 0 means3d 1 scales 2 quats 3 viewmat 4 colors 5 opacities 6 background 7 cov3ds 8 xys
-    //      9 depths 10 radii 11 conics 12 compensation 13 cum_tiles_hit 14 final_Ts 15 final_idx
-    //      16 v_out_img 17 v_out_img_alpha
-    // out: 18 v_mean3d 19 v_scale 20 v_quat 21 v_colors 22 v_opacity
-    //      23 v_xy 24 v_conic 25 v_cov2d 26 v_cov3d   (intermediate cotangents)
+    //      9 depths 10 radii 11 conics 12 compensation 13 final_Ts 14 final_idx
+    //      15 v_out_img 16 v_out_img_alpha
+    // out: 17 v_mean3d 18 v_scale 19 v_quat 20 v_colors 21 v_opacity
+    //      22 v_xy 23 v_conic 24 v_cov2d 25 v_cov3d   (intermediate cotangents)
     // v_xy_abs (an output of rasterize_bwd that nothing downstream reads) is not computed
     if (check_raster_desc(d)) return 1;
     const size_t n = d.num_points;
@@ -685,17 +685,17 @@ static int render_bwd_impl(cudaStream_t stream, void **buf, const Descriptor &d,
     g_stats[1].fetch_add(1);
     // the four accumulators are cleared with one memset when the caller laid them out back to
     // back (the torch host layer does), else one by one
-    char *g0 = (char *)buf[21];
-    if ((char *)buf[22] == g0 + n * 12 && (char *)buf[23] == g0 + n * 16 && (char *)buf[24] == g0 + n * 24) {
+    char *g0 = (char *)buf[20];
+    if ((char *)buf[21] == g0 + n * 12 && (char *)buf[22] == g0 + n * 16 && (char *)buf[23] == g0 + n * 24) {
         JSB_CUDA_OK(cudaMemsetAsync(g0, 0, n * 36, stream));
     } else {
-        JSB_CUDA_OK(cudaMemsetAsync(buf[21], 0, n * 3 * 4, stream));
-        JSB_CUDA_OK(cudaMemsetAsync(buf[22], 0, n * 4, stream));
-        JSB_CUDA_OK(cudaMemsetAsync(buf[23], 0, n * 2 * 4, stream));
-        JSB_CUDA_OK(cudaMemsetAsync(buf[24], 0, n * 3 * 4, stream));
+        JSB_CUDA_OK(cudaMemsetAsync(buf[20], 0, n * 3 * 4, stream));
+        JSB_CUDA_OK(cudaMemsetAsync(buf[21], 0, n * 4, stream));
+        JSB_CUDA_OK(cudaMemsetAsync(buf[22], 0, n * 2 * 4, stream));
+        JSB_CUDA_OK(cudaMemsetAsync(buf[23], 0, n * 3 * 4, stream));
     }
     float *v_xy_abs = nullptr;
-    if (d.block_width != 16 && !buf[17]) {
+    if (d.block_width != 16 && !buf[16]) {
         set_error("render_bwd: block_width %u needs a v_out_img_alpha buffer", d.block_width);
         return 1;
     }
@@ -730,15 +730,15 @@ static int render_bwd_impl(cudaStream_t stream, void **buf, const Descriptor &d,
         StageScope ss(c, ST_RASTER_BWD);
         if (launch_raster_bwd(stream, raster_params(d), c->cache_ids, (const int2 *)c->bins.p,
                               (const SplatRecord *)c->records.p, (const float *)buf[6],
-                              (const float *)buf[14], (const int *)buf[15], (const float *)buf[16],
-                              (const float *)buf[17], (float *)buf[23], v_xy_abs,
-                              (float *)buf[24], (float *)buf[21], (float *)buf[22]))
+                              (const float *)buf[13], (const int *)buf[14], (const float *)buf[15],
+                              (const float *)buf[16], (float *)buf[22], v_xy_abs,
+                              (float *)buf[23], (float *)buf[20], (float *)buf[21]))
             return 1;
     }
     }
     // project_bwd with zero cotangents for depth and compensation (render uses neither)
     void *pbuf[18] = {buf[0], buf[1], buf[2], buf[3], buf[7], buf[8], buf[10], buf[11], buf[12],
-                      nullptr, buf[23], nullptr, buf[24], buf[18], buf[19], buf[20], buf[25], buf[26]};
+                      nullptr, buf[22], nullptr, buf[23], buf[17], buf[18], buf[19], buf[24], buf[25]};
     return project_bwd_impl(stream, pbuf, d);
 }
 

@@ -225,7 +225,7 @@ project_fwd_kernel(const ProjectFwdParams p, const float *__restrict__ means3d,
     unsigned total;
     const unsigned excl = cta_exclusive_scan<PT>((unsigned)o.tiles, &total, s_ws);  // syncs
     if (tid == 0) {
-        block_totals[bid] = total;
+        if (cum_tiles_hit) block_totals[bid] = total;
         if (FUSED && total) {  // one pair of same-address atomics per CTA
             atomicAdd(f.totals + 1, (unsigned long long)total);
             atomicAdd(f.totals + 4, (unsigned long long)s_rows);
@@ -243,9 +243,10 @@ project_fwd_kernel(const ProjectFwdParams p, const float *__restrict__ means3d,
         depths[idx] = o.depth;
         radii[idx] = o.radius;
         compensation[idx] = o.comp;
-        num_tiles_hit[idx] = o.tiles;
+        // (the fused render passes null: nothing downstream of it reads the tile counts)
+        if (num_tiles_hit) num_tiles_hit[idx] = o.tiles;
         // CTA-local inclusive count; add_block_prefix_kernel adds the scanned CTA totals
-        cum_tiles_hit[idx] = (int)(excl + (unsigned)o.tiles);
+        if (cum_tiles_hit) cum_tiles_hit[idx] = (int)(excl + (unsigned)o.tiles);
     }
     __syncthreads();
     slab_store<6, PT>(s_cov, cov3ds, base * 6, n * 6);
@@ -461,6 +462,7 @@ int launch_project_fwd(cudaStream_t stream, const ProjectFwdParams &p, const flo
             cum_tiles_hit, block_totals, FusedPrep{});
     JSB_CUDA_OK(cudaGetLastError());
     note_launch();
+    if (!cum_tiles_hit) return 0;
     // cum_tiles_hit = CTA-local inclusive counts + exclusive scan of the CTA totals
     if (launch_scan_totals(stream, block_totals, blocks)) return 1;
     return launch_add_block_prefix(stream, cum_tiles_hit, block_totals, p.num_points, PT);

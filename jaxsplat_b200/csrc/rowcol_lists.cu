@@ -142,39 +142,41 @@ rc_row_scan_kernel(const RcParams p, unsigned *__restrict__ l1m, unsigned *__res
     if (threadIdx.x == 0) row_tot[blockIdx.x] = carry;
 }
 
-// ---- row starts and level-2 chunk bases (rows <= 256: one CTA) -----------------------------------
+// ---- row starts, level-2 chunk bases and the row of every level-2 chunk ---------------------------
+// Every CTA rebuilds the two <= 256-entry scans from the row totals (cheaper than a launch of its
+// own); CTA 0 publishes them for the later kernels.
 __global__ void __launch_bounds__(256)
-rc_row_meta_kernel(const RcParams p, const unsigned *__restrict__ row_tot,
-                   unsigned *__restrict__ row_start, unsigned *__restrict__ chunk_base) {
+rc_chunk_rows_kernel(const RcParams p, const unsigned *__restrict__ row_tot,
+                     unsigned *__restrict__ row_start, unsigned *__restrict__ chunk_base,
+                     unsigned *__restrict__ chunk_row) {
+    __shared__ unsigned s_base[256 + 1];
     __shared__ unsigned s_ws[256 / 32 + 1];
     const unsigned tid = threadIdx.x;
     const unsigned n = tid < p.rows ? row_tot[tid] : 0u;
     unsigned total;
     unsigned e = cta_exclusive_scan<256>(n, &total, s_ws);
-    if (tid < p.rows) row_start[tid] = e;
-    if (tid == 0) row_start[p.rows] = total;
+    if (blockIdx.x == 0) {
+        if (tid < p.rows) row_start[tid] = e;
+        if (tid == 0) row_start[p.rows] = total;
+    }
     __syncthreads();
     const unsigned c = (n + p.k2 - 1) / p.k2;
     e = cta_exclusive_scan<256>(c, &total, s_ws);
-    if (tid < p.rows) chunk_base[tid] = e;
-    if (tid == 0) chunk_base[p.rows] = total;
-}
-
-// ---- row of every level-2 chunk ------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-rc_chunk_rows_kernel(const RcParams p, const unsigned *__restrict__ chunk_base,
-                     unsigned *__restrict__ chunk_row) {
-    __shared__ unsigned s_base[256 + 1];
-    for (unsigned i = threadIdx.x; i <= p.rows; i += 256) s_base[i] = chunk_base[i];
+    if (tid < p.rows) s_base[tid] = e;
+    if (tid == 0) s_base[p.rows] = total;
+    if (blockIdx.x == 0) {
+        if (tid < p.rows) chunk_base[tid] = e;
+        if (tid == 0) chunk_base[p.rows] = total;
+    }
     __syncthreads();
-    const unsigned c = blockIdx.x * 256u + threadIdx.x;
-    if (c >= s_base[p.rows]) return;
-    unsigned lo = 0, hi = p.rows;  // invariant: s_base[lo] <= c < s_base[hi]
+    const unsigned ch = blockIdx.x * 256u + tid;
+    if (ch >= s_base[p.rows]) return;
+    unsigned lo = 0, hi = p.rows;  // invariant: s_base[lo] <= ch < s_base[hi]
     while (hi - lo > 1) {
         const unsigned mid = (lo + hi) >> 1;
-        if (s_base[mid] <= c) lo = mid; else hi = mid;
+        if (s_base[mid] <= ch) lo = mid; else hi = mid;
     }
-    chunk_row[c] = lo;
+    chunk_row[ch] = lo;
 }
 
 // ---- level 2 counts: tile columns covered by each chunk of k2 row entries -------------------------
@@ -248,18 +250,27 @@ rc_col_scan_kernel(const RcParams p, const unsigned *__restrict__ chunk_base,
     }
 }
 
-// ---- tile bins from the scanned tile counts --------------------------------------------------------
-__global__ void __launch_bounds__(256)
-rc_tile_bins_kernel(const RcParams p, const unsigned *__restrict__ tile_base, unsigned total,
-                    int2 *__restrict__ tile_bins) {
-    const unsigned t = blockIdx.x * 256u + threadIdx.x;
+// ---- tile counts -> tile bases (in place) and tile bins: one CTA walks the tiles 1024 at a time ----
+__global__ void __launch_bounds__(1024)
+rc_tile_scan_bins_kernel(const RcParams p, unsigned *__restrict__ tile_cnt,
+                         int2 *__restrict__ tile_bins) {
+    __shared__ unsigned s_ws[1024 / 32 + 1];
     const unsigned nt = p.rows * p.cols;
-    if (t >= nt) return;
-    const unsigned base = tile_base[t];
-    const unsigned end = (t + 1 < nt) ? tile_base[t + 1] : total;
-    // tiles without intersections stay (0,0) like the reference's memset + edge detection
-    tile_bins[(size_t)p.band_y0 * p.cols + t] =
-        end > base ? make_int2((int)base, (int)end) : make_int2(0, 0);
+    unsigned carry = 0;
+    for (unsigned b = 0; b < nt; b += 1024) {
+        const unsigned t = b + threadIdx.x;
+        const unsigned v = t < nt ? tile_cnt[t] : 0u;
+        unsigned total;
+        const unsigned base = carry + cta_exclusive_scan<1024>(v, &total, s_ws);
+        if (t < nt) {
+            tile_cnt[t] = base;
+            // tiles without intersections stay (0,0) like the reference's memset + edge detection
+            tile_bins[(size_t)p.band_y0 * p.cols + t] =
+                v ? make_int2((int)base, (int)(base + v)) : make_int2(0, 0);
+        }
+        carry += total;
+        __syncthreads();
+    }
 }
 
 // ---- the in-order staged distribution of one chunk (both levels) -----------------------------------
@@ -482,24 +493,20 @@ int launch_rowcol_lists(cudaStream_t stream, const BinParams &bp, const unsigned
         JSB_CUDA_OK(cudaGetLastError());
         rc_row_scan_kernel<<<p.rows, 1024, 0, stream>>>(p, l1m, row_tot);
         JSB_CUDA_OK(cudaGetLastError());
-        rc_row_meta_kernel<<<1, 256, 0, stream>>>(p, row_tot, row_start, chunk_base);
-        JSB_CUDA_OK(cudaGetLastError());
-        rc_chunk_rows_kernel<<<ceil_div(p.n2max, 256u), 256, 0, stream>>>(p, chunk_base, chunk_row);
+        rc_chunk_rows_kernel<<<ceil_div(p.n2max, 256u), 256, 0, stream>>>(p, row_tot, row_start,
+                                                                          chunk_base, chunk_row);
         JSB_CUDA_OK(cudaGetLastError());
         rc_row_scatter_kernel<<<p.n1, 32, smem1, stream>>>(p, order, box_by_id, l1m, row_start, entries);
         JSB_CUDA_OK(cudaGetLastError());
-        note_launch(5);
+        note_launch(4);
     } else if (phase == 1) {  // level 2 run starts and tile bins
         rc_col_count_kernel<<<p.n2max, 256, 0, stream>>>(p, row_start, chunk_base, chunk_row, entries, m);
         JSB_CUDA_OK(cudaGetLastError());
         rc_col_scan_kernel<<<dim3(ceil_div(p.cols, 32u), p.rows), 256, 0, stream>>>(p, chunk_base, m, tile_cnt);
         JSB_CUDA_OK(cudaGetLastError());
-        note_launch(2);
-        if (launch_scan_totals(stream, tile_cnt, p.rows * p.cols)) return 1;
-        rc_tile_bins_kernel<<<ceil_div(p.rows * p.cols, 256u), 256, 0, stream>>>(
-            p, tile_cnt, (unsigned)num_intersects, tile_bins);
+        rc_tile_scan_bins_kernel<<<1, 1024, 0, stream>>>(p, tile_cnt, tile_bins);
         JSB_CUDA_OK(cudaGetLastError());
-        note_launch();
+        note_launch(3);
     } else {  // level 2: the lists
         rc_col_scatter_kernel<<<p.n2max, 32, smem2, stream>>>(p, row_start, chunk_base, chunk_row,
                                                               entries, m, tile_cnt, ids_sorted);
