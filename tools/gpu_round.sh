@@ -6,7 +6,7 @@ TAG=${1:-r01x}
 FULL=${2:-}
 OUT=gpurun_out
 mkdir -p $OUT
-KREGEX='regex:^(project_|bin_prep|fingerprint|radix_|onesweep|upsweep|scan_|box_gather|emit_|chunk_|group_|hist_apply|raster_|inclusive_scan|add_block|fill_background)'
+KREGEX='regex:^(rc_|project_|bin_prep|fingerprint|radix_|onesweep|upsweep|scan_|box_gather|emit_|chunk_|group_|hist_apply|raster_|inclusive_scan|add_block|fill_background)'
 nvidia-smi --query-gpu=name,clocks.max.sm,clocks.sm,power.limit --format=csv > $OUT/${TAG}_gpu.txt 2>&1
 nproc >> $OUT/${TAG}_gpu.txt
 timeout 900 python -m pytest tests -m gpu -x -q > $OUT/${TAG}_pytest.log 2>&1
@@ -19,7 +19,7 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --c
 if [ -n "$FULL" ]; then
   # step 1 warms (arena growth), step 2 is captured: skip the first step's launches of our kernels
   timeout 900 ncu --set full --clock-control none --import-source on -k "$KREGEX" \
-      --launch-skip 40 -c 40 -f -o $OUT/${TAG}_full python tools/ncu_step.py C3 3 \
+      --launch-skip 22 -c 22 -f -o $OUT/${TAG}_full python tools/ncu_step.py C3 3 \
       > $OUT/${TAG}_full.log 2>&1
   ncu -i $OUT/${TAG}_full.ncu-rep --page raw --csv > $OUT/${TAG}_full_raw.csv 2>/dev/null
 fi
