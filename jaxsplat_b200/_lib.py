@@ -10,7 +10,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libjaxsplat_b200.so")
+# JSB200_LIB: load another build of the same library (A/B experiments: tools/gpu_ab_builds.sh)
+LIB_PATH = os.environ.get("JSB200_LIB") or os.path.join(_HERE, "lib", "libjaxsplat_b200.so")
 
 # every symbol include/jaxsplat_b200.h declares
 EXPORTS = (

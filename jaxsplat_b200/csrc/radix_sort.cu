@@ -179,7 +179,10 @@ onesweep_pass_kernel(const KeyT *__restrict__ keys_in, const unsigned *__restric
             st_relaxed(st, ST_AGG | cta_count);
             // walk predecessors, LB status loads in flight per step (the walk is a chain of L2
             // round trips; speculative loads of older tiles cost nothing and cut it LB-fold)
-            constexpr int LB = 4;
+#ifndef JSB_RADIX_LB
+#define JSB_RADIX_LB 4
+#endif
+            constexpr int LB = JSB_RADIX_LB;
             int j = (int)tile - 1;
             int spins = 0;
             bool done = false;
@@ -282,7 +285,10 @@ scan_rows_kernel(unsigned *__restrict__ tile_hist, unsigned tiles, unsigned *__r
     if (threadIdx.x == 0) row_totals[blockIdx.x] = total;
 }
 
-inline int items_for(unsigned n) { (void)n; return 16; }  // 4/thread measured slower even at N=1M
+#ifndef JSB_RADIX_ITEMS
+#define JSB_RADIX_ITEMS 16  // 4, 8 and 32 per thread measured no faster at N = 1M (tools/gpu_ab_builds.sh)
+#endif
+inline int items_for(unsigned n) { (void)n; return JSB_RADIX_ITEMS; }
 inline unsigned num_tiles_of(unsigned n) { return ceil_div(n, (unsigned)(RS_THREADS * items_for(n))); }
 inline int passes_of(int bits) { return (bits + 7) / 8; }
 
@@ -329,7 +335,7 @@ int radix_sort_pairs(cudaStream_t stream, KeyT *keys_a, KeyT *keys_b, unsigned *
             JSB_CUDA_OK(cudaGetLastError());
             scan_rows_kernel<<<RADIX, 256, 0, stream>>>(status, tiles, row_totals);
             JSB_CUDA_OK(cudaGetLastError());
-            onesweep_pass_kernel<KeyT, 16, false><<<tiles, RS_THREADS, 0, stream>>>(
+            onesweep_pass_kernel<KeyT, JSB_RADIX_ITEMS, false><<<tiles, RS_THREADS, 0, stream>>>(
                 kin, vin, kout, vout, n, 8 * ps, min(8, bits - 8 * ps), row_totals, status, nullptr,
                 err);
             JSB_CUDA_OK(cudaGetLastError());
@@ -351,14 +357,9 @@ int radix_sort_pairs(cudaStream_t stream, KeyT *keys_a, KeyT *keys_b, unsigned *
     KeyT *kin = keys_a, *kout = keys_b;
     unsigned *vin = vals_a, *vout = vals_b;
     for (int ps = 0; ps < passes; ++ps) {
-        if (items_for(n) == 16)
-            onesweep_pass_kernel<KeyT, 16, true><<<tiles, RS_THREADS, 0, stream>>>(
-                kin, vin, kout, vout, n, 8 * ps, min(8, bits - 8 * ps), ghist + ps * RADIX,
-                status + (size_t)ps * tiles * RADIX, tickets + ps, err);
-        else
-            onesweep_pass_kernel<KeyT, 4, true><<<tiles, RS_THREADS, 0, stream>>>(
-                kin, vin, kout, vout, n, 8 * ps, min(8, bits - 8 * ps), ghist + ps * RADIX,
-                status + (size_t)ps * tiles * RADIX, tickets + ps, err);
+        onesweep_pass_kernel<KeyT, JSB_RADIX_ITEMS, true><<<tiles, RS_THREADS, 0, stream>>>(
+            kin, vin, kout, vout, n, 8 * ps, min(8, bits - 8 * ps), ghist + ps * RADIX,
+            status + (size_t)ps * tiles * RADIX, tickets + ps, err);
         JSB_CUDA_OK(cudaGetLastError());
     note_launch();
         KeyT *tk = kin; kin = kout; kout = tk;

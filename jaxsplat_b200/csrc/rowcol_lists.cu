@@ -30,8 +30,14 @@ namespace jsb {
 namespace {
 
 constexpr int RC_ITEMS = 256;    // items per chunk (8 register groups of 32)
-constexpr int RC_STAGE1 = 1024;  // staged 8-byte row entries per level-1 chunk
-constexpr int RC_STAGE2 = 1536;  // staged 4-byte ids per level-2 chunk
+#ifndef JSB_RC_STAGE1
+#define JSB_RC_STAGE1 1024
+#endif
+#ifndef JSB_RC_STAGE2
+#define JSB_RC_STAGE2 1536
+#endif
+constexpr int RC_STAGE1 = JSB_RC_STAGE1;  // staged 8-byte row entries per level-1 chunk
+constexpr int RC_STAGE2 = JSB_RC_STAGE2;  // staged 4-byte ids per level-2 chunk
 
 struct RcParams {
     unsigned n;          // Gaussians
