@@ -155,6 +155,15 @@ JSB200_API int jsb200_multimem_allreduce_f32(jsb200_stream_t stream, void *multi
                                              size_t flags_offset_bytes, int rank, int world,
                                              unsigned epoch);
 
+/* ---- optimiser step either side of the path -----------------------------------
+ * One Adam update of a flat float array in one streaming kernel; the semantics of optax.adam(lr)
+ * as used by the reference's examples/single_image.py:21-40 (b1 = 0.9, b2 = 0.999, eps = 1e-8,
+ * bias-corrected moments, no weight decay).  `step` counts from 1.  m and v are the caller's
+ * moment buffers (zero before the first step).  Returns 0 on success. */
+JSB200_API int jsb200_adam_step(jsb200_stream_t stream, float *param, const float *grad, float *m,
+                                float *v, size_t n, float lr, float b1, float b2, float eps,
+                                unsigned long long step);
+
 #ifdef __cplusplus
 }
 #endif

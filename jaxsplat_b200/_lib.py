@@ -34,6 +34,7 @@ EXPORTS = (
     "jsb200_get_stats",
     "jsb200_release",
     "jsb200_multimem_allreduce_f32",
+    "jsb200_adam_step",
 )
 
 _lib = None
@@ -91,6 +92,8 @@ def lib() -> ctypes.CDLL:
     L.jsb200_release.restype = None
     L.jsb200_multimem_allreduce_f32.argtypes = [vp, vp, ctypes.POINTER(vp), sz, sz, i, i, u]
     L.jsb200_multimem_allreduce_f32.restype = i
+    L.jsb200_adam_step.argtypes = [vp, vp, vp, vp, vp, sz, f, f, f, f, ctypes.c_ulonglong]
+    L.jsb200_adam_step.restype = i
     _lib = L
     return L
 

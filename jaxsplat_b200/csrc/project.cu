@@ -16,7 +16,10 @@ namespace jsb {
 
 namespace {
 
-constexpr int PT = 256;  // Gaussians (= threads) per CTA
+#ifndef JSB_PROJECT_THREADS
+#define JSB_PROJECT_THREADS 256
+#endif
+constexpr int PT = JSB_PROJECT_THREADS;  // Gaussians (= threads) per CTA
 
 struct ProjOut {
     float cov3d[6];

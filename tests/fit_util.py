@@ -57,17 +57,25 @@ def fit_cpu(scene, target, steps=100, lr=0.01):
     return losses
 
 
-def fit_gpu(scene, target, steps=100, lr=0.01, device="cuda:0"):
+def fit_gpu(scene, target, steps=100, lr=0.01, device="cuda:0", native_adam=False):
+    """native_adam: jaxsplat_b200.optim.Adam (one fused kernel per array) instead of torch's"""
     import torch
 
     import jaxsplat_b200 as jsb
     p = {k: torch.from_numpy(v).to(device).requires_grad_(True) for k, v in raw_params(scene).items()}
-    opt = torch.optim.Adam(list(p.values()), lr=lr)
+    if native_adam:
+        from jaxsplat_b200.optim import Adam
+        opt = Adam(list(p.values()), lr=lr)
+    else:
+        opt = torch.optim.Adam(list(p.values()), lr=lr)
     kw = scene.to(device).render_kwargs()
     tgt = torch.from_numpy(target).to(device)
     losses = []
     for _ in range(steps):
-        opt.zero_grad(set_to_none=True)
+        if native_adam:
+            opt.zero_grad()
+        else:
+            opt.zero_grad(set_to_none=True)
         q = p["quats"] / p["quats"].norm(dim=1, keepdim=True)
         img = jsb.render(p["means3d"], p["scales"], q, torch.sigmoid(p["colors"]),
                          torch.sigmoid(p["opacities"]), **kw)

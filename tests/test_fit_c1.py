@@ -33,3 +33,31 @@ def test_config1_fit_100_adam_steps_matches_oracle_run():
     for k in (1, 5, 10, 25, 50, 99):
         assert abs(gpu_losses[k] - cpu_losses[k]) <= 1e-2 * cpu_losses[k], (k, gpu_losses[k], cpu_losses[k])
     assert gpu_losses[-1] < 0.7 * gpu_losses[0]
+
+
+@pytest.mark.gpu
+def test_native_adam_matches_torch_adam():
+    import torch
+    from jaxsplat_b200.optim import Adam
+    gen = torch.Generator().manual_seed(0)
+    shapes = [(1000, 3), (1000, 4), (777, 1), (5,)]
+    a = [torch.randn(s, generator=gen).cuda().requires_grad_(True) for s in shapes]
+    b = [x.detach().clone().requires_grad_(True) for x in a]
+    oa, ob = Adam(a, lr=0.01), torch.optim.Adam(b, lr=0.01)
+    for step in range(7):
+        grads = [torch.randn(s, generator=gen).cuda() * (10.0 ** (step - 3)) for s in shapes]
+        for x, y, g in zip(a, b, grads):
+            x.grad, y.grad = g.clone(), g.clone()
+        oa.step()
+        ob.step()
+        for x, y in zip(a, b):
+            assert torch.allclose(x, y, rtol=2e-6, atol=1e-7), (step, (x - y).abs().max())
+
+
+@pytest.mark.gpu
+def test_config1_fit_with_the_native_adam_step():
+    scene, target = _c1()
+    ref = fit_util.fit_gpu(scene, target, steps=30)
+    got = fit_util.fit_gpu(scene, target, steps=30, native_adam=True)
+    for k in (0, 1, 10, 29):
+        assert abs(got[k] - ref[k]) <= 2e-3 * ref[k], (k, got[k], ref[k])
