@@ -166,8 +166,6 @@ def main():
             _lib.set_option("rowcol", 0)
         if os.environ.get("JSB_FWD2PX") == "0":
             _lib.set_option("fwd2px", 0)
-        if os.environ.get("JSB_BWD_PPT"):
-            _lib.set_option("bwd_ppt", int(os.environ["JSB_BWD_PPT"]))
         if os.environ.get("JSB_BWD2PX") == "0":
             _lib.set_option("bwd2px", 0)
         if os.environ.get("JSB_FUSED") == "0":

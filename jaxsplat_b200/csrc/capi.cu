@@ -48,7 +48,6 @@ void note_launch(int n) { g_stats[6].fetch_add((unsigned long long)n); }
 extern bool g_disable_cull;
 extern bool g_bwd_one_pixel;
 extern bool g_fwd_one_pixel;
-extern int g_bwd_ppt;
 static bool g_disable_cache = false;
 static bool g_disable_rowcol = false;
 
@@ -915,11 +914,6 @@ int jsb200_set_option(const char *key, int value) {
     if (!strcmp(key, "cull")) { jsb::g_disable_cull = (value == 0); return 0; }
     if (!strcmp(key, "cache")) { jsb::g_disable_cache = (value == 0); return 0; }
     if (!strcmp(key, "fwd2px")) { jsb::g_fwd_one_pixel = (value == 0); return 0; }
-    if (!strcmp(key, "bwd_ppt")) {
-        if (value != 2 && value != 4) { jsb::set_error("set_option: bwd_ppt must be 2 or 4"); return 1; }
-        jsb::g_bwd_ppt = value;
-        return 0;
-    }
     if (!strcmp(key, "bwd2px")) { jsb::g_bwd_one_pixel = (value == 0); return 0; }
     if (!strcmp(key, "rowcol")) { jsb::g_disable_rowcol = (value == 0); return 0; }
     if (!strcmp(key, "timing")) { jsb::g_timing = (value != 0); return 0; }

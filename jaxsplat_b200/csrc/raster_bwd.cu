@@ -202,6 +202,7 @@ raster_bwd16_kernel(const RasterParams p, const unsigned *__restrict__ ids_sorte
 // instructions of a visit) and the candidate bookkeeping are paid once per 64 pixels instead of
 // once per 32.  ABS = false (fused render: nothing consumes v_xy_abs) drops two of the eleven rows.
 // Row order of the reduction: rgb(3) conic(3) xy(2) opacity(1) xy_abs(2).
+constexpr int RB2 = 128;
 
 // tfc = T_final * (v_out_alpha - <v_out, background>): the two background/alpha terms of the
 // reference's v_alpha (backward.cu:283-291) are both proportional to T_final * ra, so they fold
@@ -253,11 +254,9 @@ __device__ __forceinline__ void pair_grad2(bool valid, float alpha, float vis, f
     }
 }
 
-// PPT pixels per thread: 2 -> 4 warps of 8x8 quadrants, 4 -> 2 warps of 8x16 half tiles (lane l
-// owns column l & 7 and rows (l >> 3) + 4 k, k < PPT, of its warp's area).
-template <bool CULL, bool ABS, int PPT>
-__global__ void __launch_bounds__(256 / PPT, PPT == 2 ? 6 : 8)
-raster_bwd16xN_kernel(const RasterParams p, const unsigned *__restrict__ ids_sorted,
+template <bool CULL, bool ABS>
+__global__ void __launch_bounds__(RB2, 6)
+raster_bwd16x2_kernel(const RasterParams p, const unsigned *__restrict__ ids_sorted,
                       const int2 *__restrict__ tile_bins, const SplatRecord *__restrict__ records,
                       const float *__restrict__ background, const float *__restrict__ final_Ts,
                       const int *__restrict__ final_idx, const float *__restrict__ v_out_img,
@@ -265,65 +264,59 @@ raster_bwd16xN_kernel(const RasterParams p, const unsigned *__restrict__ ids_sor
                       float *__restrict__ v_xy_abs, float *__restrict__ v_conic,
                       float *__restrict__ v_colors, float *__restrict__ v_opacity) {
     constexpr int NV = ABS ? 11 : 9;
-    constexpr int BATCH = 256;
-    constexpr int THREADS = 256 / PPT, WARPS = THREADS / 32;
-    constexpr int EPT = BATCH / THREADS;  // staged entries per thread
+    constexpr int BATCH = 256;  // two staged entries per thread
     __shared__ float4 sA2[2][BATCH];  // double-buffered batches (cp.async staging)
     __shared__ float4 sB2[2][BATCH];
     __shared__ float sC2[2][BATCH];
     __shared__ unsigned sId2[2][BATCH];
     __shared__ unsigned char sMask[BATCH];
-    __shared__ int s_max[WARPS];
-    __shared__ __align__(16) float sRed[WARPS * NV * RED_STRIDE];
+    __shared__ int s_max[RB2 / 32];
+    __shared__ __align__(16) float sRed[(RB2 / 32) * NV * RED_STRIDE];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     float *red = sRed + warp * NV * RED_STRIDE;
     const unsigned tile = p.band_y0 * p.tiles_x + blockIdx.x;
     const unsigned tile_y = tile / p.tiles_x, tile_x = tile - tile_y * p.tiles_x;
     const unsigned j = tile_x * 16 + (warp & 1) * 8 + (lane & 7);
-    const unsigned i_first = tile_y * 16 + (PPT == 2 ? (warp >> 1) * 8 : 0) + (lane >> 3);
-    const float px = (float)j + 0.5f;
+    const unsigned i0 = tile_y * 16 + (warp >> 1) * 8 + (lane >> 3), i1 = i0 + 4;
+    const float px = (float)j + 0.5f, py0 = (float)i0 + 0.5f, py1 = (float)i1 + 0.5f;
+    const bool in0 = (i0 < p.img_h) && (j < p.img_w), in1 = (i1 < p.img_h) && (j < p.img_w);
     const int2 range = tile_bins[tile];
-    // bit of this warp's area in the folded 8-rectangle cull mask (bit = wy * 2 + wx):
-    // PPT 2: (m | m >> 2) ORs the quadrant's two rectangles at bit wx + 4 (wy >> 1);
-    // PPT 4: (m | m >> 2 | m >> 4 | m >> 6) ORs the half tile's four rectangles at bit wx
-    const int qbit = PPT == 2 ? (warp & 1) + 4 * (warp >> 1) : (warp & 1);
+    // quadrant bit inside the 8-rectangle cull mask after folding rows: (m | m >> 2) has the
+    // quadrant's two 8x4 rectangles ORed at bit (warp & 1) + 4 * (warp >> 1)
+    const int qbit = (warp & 1) + 4 * (warp >> 1);
 
-    float py[PPT], Tfin[PPT], tfc[PPT], T[PPT];
-    float3 vo[PPT], buf[PPT];
-    int bf[PPT];
-    bool in[PPT];
-    const float3 bg = make_float3(__ldg(background), __ldg(background + 1), __ldg(background + 2));
-    int wmax = -1;
-#pragma unroll
-    for (int k = 0; k < PPT; ++k) {
-        const unsigned i = i_first + 4 * k;
-        py[k] = (float)i + 0.5f;
-        in[k] = (i < p.img_h) && (j < p.img_w);
-        Tfin[k] = 1.f;
-        float voa = 0.f;
-        vo[k] = make_float3(0.f, 0.f, 0.f);
-        bf[k] = -1;
-        if (in[k]) {
-            const size_t pix = (size_t)i * p.img_w + j;
-            Tfin[k] = final_Ts[pix];
-            bf[k] = final_idx[pix];
-            vo[k] = make_float3(v_out_img[pix * 3], v_out_img[pix * 3 + 1], v_out_img[pix * 3 + 2]);
-            voa = v_out_alpha_img ? v_out_alpha_img[pix] : 0.f;
-        }
-        tfc[k] = Tfin[k] * (voa - (vo[k].x * bg.x + vo[k].y * bg.y + vo[k].z * bg.z));
-        T[k] = Tfin[k];
-        buf[k] = make_float3(0.f, 0.f, 0.f);
-        wmax = max(wmax, bf[k]);
+    float Tf0 = 1.f, Tf1 = 1.f, voa0 = 0.f, voa1 = 0.f;
+    float3 vo0 = make_float3(0.f, 0.f, 0.f), vo1 = vo0;
+    int bf0 = -1, bf1 = -1;
+    if (in0) {
+        const size_t pix = (size_t)i0 * p.img_w + j;
+        Tf0 = final_Ts[pix];
+        bf0 = final_idx[pix];
+        vo0 = make_float3(v_out_img[pix * 3], v_out_img[pix * 3 + 1], v_out_img[pix * 3 + 2]);
+        voa0 = v_out_alpha_img ? v_out_alpha_img[pix] : 0.f;
     }
+    if (in1) {
+        const size_t pix = (size_t)i1 * p.img_w + j;
+        Tf1 = final_Ts[pix];
+        bf1 = final_idx[pix];
+        vo1 = make_float3(v_out_img[pix * 3], v_out_img[pix * 3 + 1], v_out_img[pix * 3 + 2]);
+        voa1 = v_out_alpha_img ? v_out_alpha_img[pix] : 0.f;
+    }
+    const float3 bg = make_float3(__ldg(background), __ldg(background + 1), __ldg(background + 2));
+    const float tfc0 = Tf0 * (voa0 - (vo0.x * bg.x + vo0.y * bg.y + vo0.z * bg.z));
+    const float tfc1 = Tf1 * (voa1 - (vo1.x * bg.x + vo1.y * bg.y + vo1.z * bg.z));
+    float T0 = Tf0, T1 = Tf1;
+    float3 buf0 = make_float3(0.f, 0.f, 0.f), buf1 = buf0;
 
+    int wmax = max(bf0, bf1);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
     if (lane == 0) s_max[warp] = wmax;
     __syncthreads();
     int tmax = s_max[0];
 #pragma unroll
-    for (int w = 1; w < WARPS; ++w) tmax = max(tmax, s_max[w]);
+    for (int w = 1; w < RB2 / 32; ++w) tmax = max(tmax, s_max[w]);
     const int top = min(range.y - 1, tmax);
     if (top < range.x) return;  // nothing in this tile was composited (uniform across the CTA)
     const int num_batches = (top - range.x + BATCH) / BATCH;
@@ -343,11 +336,11 @@ raster_bwd16xN_kernel(const RasterParams p, const unsigned *__restrict__ ids_sor
     // Software pipeline (as in raster_fwd.cu): records of batch b+1 by cp.async into the other
     // buffer and sorted ids of batch b+2 into registers while batch b is replayed.
     auto load_id = [&](int bb, int h) -> unsigned {
-        const int idx = top - BATCH * bb - (tid + h * THREADS);
+        const int idx = top - BATCH * bb - (tid + h * RB2);
         return (bb < num_batches && idx >= range.x) ? ids_sorted[idx] : 0u;
     };
     auto issue = [&](int bb, int h, unsigned g) {
-        const int t = tid + h * THREADS;
+        const int t = tid + h * RB2;
         if (top - BATCH * bb - t >= range.x) {
             const SplatRecord *r = records + g;
             cp_async16(&sA2[bb & 1][t], &r->q0);
@@ -356,76 +349,64 @@ raster_bwd16xN_kernel(const RasterParams p, const unsigned *__restrict__ ids_sor
             sId2[bb & 1][t] = g;
         }
     };
-    unsigned gn[EPT];
-#pragma unroll
-    for (int h = 0; h < EPT; ++h) issue(0, h, load_id(0, h));
-#pragma unroll
-    for (int h = 0; h < EPT; ++h) gn[h] = load_id(1, h);
+    issue(0, 0, load_id(0, 0));
+    issue(0, 1, load_id(0, 1));
+    unsigned gn0 = load_id(1, 0), gn1 = load_id(1, 1);
 
     for (int b = 0; b < num_batches; ++b) {
         cp_async_wait_all();
         __syncthreads();  // batch b landed; every warp is done with batch b-1
         const int batch_end = top - BATCH * b;  // slot t holds sorted index batch_end - t
-        const int bsel = b & 1;
-        const float4 *sA = sA2[bsel];
-        const float4 *sB = sB2[bsel];
-        const float *sC = sC2[bsel];
-        const unsigned *sId = sId2[bsel];
-        if (b + 1 < num_batches) {
+        const int buf = b & 1;
+        const float4 *sA = sA2[buf];
+        const float4 *sB = sB2[buf];
+        const float *sC = sC2[buf];
+        const unsigned *sId = sId2[buf];
+        if (b + 1 < num_batches) { issue(b + 1, 0, gn0); issue(b + 1, 1, gn1); }
+        gn0 = load_id(b + 2, 0);
+        gn1 = load_id(b + 2, 1);
 #pragma unroll
-            for (int h = 0; h < EPT; ++h) issue(b + 1, h, gn[h]);
-        }
-#pragma unroll
-        for (int h = 0; h < EPT; ++h) gn[h] = load_id(b + 2, h);
-#pragma unroll
-        for (int h = 0; h < EPT; ++h) {
-            const int t = tid + h * THREADS;
+        for (int h = 0; h < 2; ++h) {
+            const int t = tid + h * RB2;
             unsigned mask = 0;
             if (batch_end - t >= range.x) {
                 const float4 q0 = sA[t];
                 const float2 q1 = *reinterpret_cast<const float2 *>(&sB[t]);
                 mask = CULL ? cull_mask16(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, tile_x0, tile_y0) : 0xFFu;
             }
-            mask |= mask >> 2;
-            if (PPT == 4) mask |= mask >> 4;
-            sMask[t] = (unsigned char)mask;
+            sMask[t] = (unsigned char)(mask | (mask >> 2));
         }
         __syncthreads();
 
 #pragma unroll 1
-        for (int kk = 0; kk < BATCH / 32; ++kk) {
+        for (int k = 0; k < BATCH / 32; ++k) {
             // entries newer than the warp's largest final index cannot be valid for any lane
-            if (batch_end - (kk * 32 + 31) > wmax) continue;
-            const unsigned m = sMask[kk * 32 + lane];
+            if (batch_end - (k * 32 + 31) > wmax) continue;
+            const unsigned m = sMask[k * 32 + lane];
             unsigned bits = __ballot_sync(0xffffffffu, (m >> qbit) & 1u);
             while (bits) {
-                const int t = kk * 32 + __ffs(bits) - 1;
+                const int t = k * 32 + __ffs(bits) - 1;
                 bits &= bits - 1;
                 const float4 a = sA[t];
                 const float4 bq = sB[t];
                 const float dx = fsub(a.x, px);
+                const float dy0 = fsub(a.y, py0), dy1 = fsub(a.y, py1);
+                const float sg0 = conic_sigma(a.w, bq.x, bq.y, dx, dy0);
+                const float sg1 = conic_sigma(a.w, bq.x, bq.y, dx, dy1);
+                const float vis0 = ex2_approx(fmul(sg0, kNegLog2e));
+                const float vis1 = ex2_approx(fmul(sg1, kNegLog2e));
+                const float al0 = fminf(fmul(a.z, vis0), 0.99f);
+                const float al1 = fminf(fmul(a.z, vis1), 0.99f);
                 const int sidx = batch_end - t;
-                float dy[PPT], vis[PPT], al[PPT];
-                bool ok[PPT];
-                bool any_ok = false;
-#pragma unroll
-                for (int k = 0; k < PPT; ++k) {
-                    dy[k] = fsub(a.y, py[k]);
-                    const float sg = conic_sigma(a.w, bq.x, bq.y, dx, dy[k]);
-                    vis[k] = ex2_approx(fmul(sg, kNegLog2e));
-                    al[k] = fminf(fmul(a.z, vis[k]), 0.99f);
-                    ok[k] = in[k] && (sidx <= bf[k]) && !(sg < 0.f) && !(al[k] < kAlphaMin);
-                    any_ok = any_ok || ok[k];
-                }
-                if (!__any_sync(0xffffffffu, any_ok)) continue;
+                const bool ok0 = in0 && (sidx <= bf0) && !(sg0 < 0.f) && !(al0 < kAlphaMin);
+                const bool ok1 = in1 && (sidx <= bf1) && !(sg1 < 0.f) && !(al1 < kAlphaMin);
+                if (!__any_sync(0xffffffffu, ok0 || ok1)) continue;
                 float v[NV];
                 const float cb = sC[t];
-                pair_grad2<ABS, false>(ok[0], al[0], vis[0], a.z, dx, dy[0], a.w, bq.x, bq.y, bq.z, bq.w,
-                                       cb, vo[0], tfc[0], T[0], buf[0], v);
-#pragma unroll
-                for (int k = 1; k < PPT; ++k)
-                    pair_grad2<ABS, true>(ok[k], al[k], vis[k], a.z, dx, dy[k], a.w, bq.x, bq.y, bq.z,
-                                          bq.w, cb, vo[k], tfc[k], T[k], buf[k], v);
+                pair_grad2<ABS, false>(ok0, al0, vis0, a.z, dx, dy0, a.w, bq.x, bq.y, bq.z, bq.w, cb,
+                                       vo0, tfc0, T0, buf0, v);
+                pair_grad2<ABS, true>(ok1, al1, vis1, a.z, dx, dy1, a.w, bq.x, bq.y, bq.z, bq.w, cb,
+                                      vo1, tfc1, T1, buf1, v);
                 // transpose through shared memory: row r = value r of the 32 lanes
                 __syncwarp();
 #pragma unroll
@@ -500,22 +481,15 @@ __global__ void raster_bwd_generic_kernel(
 extern bool g_disable_cull;
 bool g_bwd_one_pixel = false;  // option "bwd2px" = 0: the one-pixel-per-thread kernel
 
-int g_bwd_ppt = 2;  // option "bwd_ppt": pixels per thread of the default backward kernel (2 or 4)
-
 template <bool CULL, bool ABS>
 static void launch_x2(cudaStream_t stream, unsigned tiles, const RasterParams &p,
                       const unsigned *ids_sorted, const int2 *tile_bins, const SplatRecord *records,
                       const float *background, const float *final_Ts, const int *final_idx,
                       const float *v_out, const float *v_out_alpha, float *v_xy, float *v_xy_abs,
                       float *v_conic, float *v_colors, float *v_opacity) {
-    if (g_bwd_ppt == 4)
-        raster_bwd16xN_kernel<CULL, ABS, 4><<<tiles, 64, 0, stream>>>(
-            p, ids_sorted, tile_bins, records, background, final_Ts, final_idx, v_out, v_out_alpha,
-            v_xy, v_xy_abs, v_conic, v_colors, v_opacity);
-    else
-        raster_bwd16xN_kernel<CULL, ABS, 2><<<tiles, 128, 0, stream>>>(
-            p, ids_sorted, tile_bins, records, background, final_Ts, final_idx, v_out, v_out_alpha,
-            v_xy, v_xy_abs, v_conic, v_colors, v_opacity);
+    raster_bwd16x2_kernel<CULL, ABS><<<tiles, RB2, 0, stream>>>(
+        p, ids_sorted, tile_bins, records, background, final_Ts, final_idx, v_out, v_out_alpha, v_xy,
+        v_xy_abs, v_conic, v_colors, v_opacity);
 }
 
 // v_xy_abs == nullptr: not computed (fused render; block_width 16 only)

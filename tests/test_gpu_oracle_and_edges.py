@@ -311,19 +311,14 @@ def test_two_pixels_per_thread_backward_equals_one_pixel_per_thread(scene_fn):
     v_alpha = np.random.RandomState(3).rand(H, W, 1).astype(np.float32) * 1e-3
     try:
         _lib.set_option("bwd2px", 1)
-        _lib.set_option("bwd_ppt", 2)
         a = _full_gpu(inp, kw, rkw, target, v_alpha)
-        _lib.set_option("bwd_ppt", 4)
-        c = _full_gpu(inp, kw, rkw, target, v_alpha)
         _lib.set_option("bwd2px", 0)
         b = _full_gpu(inp, kw, rkw, target, v_alpha)
     finally:
         _lib.set_option("bwd2px", 1)
-        _lib.set_option("bwd_ppt", 2)
     for k in ("v_colors", "v_opacity", "v_xy", "v_xy_abs", "v_conic"):
-        for got in (a, c):  # two and four pixels per thread vs one
-            ok, err, scale = grad_close(got[k], b[k], rel=1e-4)
-            assert ok, (k, err, scale)
+        ok, err, scale = grad_close(a[k], b[k], rel=1e-4)
+        assert ok, (k, err, scale)
 
 
 @pytest.mark.parametrize("scene_fn", [_adversarial_scene, lambda: synthetic.make_config("C2", num_points=30000),
