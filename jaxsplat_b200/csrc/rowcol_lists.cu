@@ -108,26 +108,41 @@ __device__ __forceinline__ bool load_box(const RcParams &p, unsigned pos,
 }
 
 // ---- level 1 counts: rows covered by each chunk of k1 depth positions ----------------------------
-__global__ void __launch_bounds__(256)
+// One warp per chunk (8 chunks per CTA, no CTA-wide barrier), 8 positions per lane.
+constexpr int RC_RC_WARPS = 8;
+__global__ void __launch_bounds__(32 * RC_RC_WARPS)
 rc_row_count_kernel(const RcParams p, const unsigned *__restrict__ order,
                     const uint2 *__restrict__ box_by_id, unsigned *__restrict__ l1m) {
-    __shared__ unsigned s_diff[256 + 1];
-    __shared__ unsigned s_ws[256 / 32 + 1];
-    const unsigned tid = threadIdx.x, chunk = blockIdx.x;
-    for (unsigned i = tid; i <= 256; i += 256) s_diff[i] = 0u;
-    __syncthreads();
-    if (tid < p.k1) {
-        unsigned g, y0, h, xw;
-        if (load_box(p, chunk * p.k1 + tid, order, box_by_id, g, y0, h, xw)) {
-            atomicAdd(&s_diff[y0], 1u);
-            atomicAdd(&s_diff[y0 + h], 0xffffffffu);  // -1 (mod 2^32)
+    __shared__ unsigned s_diff_all[RC_RC_WARPS][256 + 32];
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned *s_diff = s_diff_all[warp];
+    const unsigned chunk = blockIdx.x * RC_RC_WARPS + warp;
+    if (chunk >= p.n1) return;  // warp-uniform; no CTA barrier below
+    for (unsigned i = lane; i <= p.rows; i += 32) s_diff[i] = 0u;
+    unsigned y0[8], h[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        unsigned g, xw;
+        const unsigned item = q * 32 + lane;
+        const bool ok = item < p.k1 && load_box(p, chunk * p.k1 + item, order, box_by_id, g, y0[q], h[q], xw);
+        if (!ok) h[q] = 0u;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        if (h[q]) {
+            atomicAdd(&s_diff[y0[q]], 1u);
+            atomicAdd(&s_diff[y0[q] + h[q]], 0xffffffffu);  // -1 (mod 2^32)
         }
     }
-    __syncthreads();
-    const unsigned d = tid < p.rows ? s_diff[tid] : 0u;
-    unsigned total;
-    const unsigned excl = cta_exclusive_scan<256>(d, &total, s_ws);
-    if (tid < p.rows) l1m[(size_t)tid * p.n1s + chunk] = excl + d;  // entries of this chunk in row tid
+    __syncwarp();
+    unsigned carry = 0;
+    for (unsigned base = 0; base < p.rows; base += 32) {
+        const unsigned i = base + lane;
+        const unsigned cnt = warp_inclusive_scan(i < p.rows ? s_diff[i] : 0u, lane) + carry;
+        carry = __shfl_sync(0xffffffffu, cnt, 31);
+        if (i < p.rows) l1m[(size_t)i * p.n1s + chunk] = cnt;  // entries of this chunk in row i
+    }
 }
 
 // ---- in-place exclusive scan of every row of the level-1 matrix ----------------------------------
@@ -186,62 +201,77 @@ rc_chunk_rows_kernel(const RcParams p, const unsigned *__restrict__ row_tot,
 }
 
 // ---- level 2 counts: tile columns covered by each chunk of k2 row entries -------------------------
-__global__ void __launch_bounds__(256)
+// One warp per chunk (8 chunks per CTA, no CTA-wide barrier): difference array in the warp's own
+// shared memory, 8 entries per lane, then a prefix over the columns.
+constexpr int RC_CC_WARPS = 8;
+__global__ void __launch_bounds__(32 * RC_CC_WARPS)
 rc_col_count_kernel(const RcParams p, const unsigned *__restrict__ row_start,
                     const unsigned *__restrict__ chunk_base, const unsigned *__restrict__ chunk_row,
                     const uint2 *__restrict__ entries, unsigned *__restrict__ m) {
-    __shared__ unsigned s_diff[512 + 2];
-    __shared__ unsigned s_ws[256 / 32 + 1];
-    const unsigned tid = threadIdx.x, c = blockIdx.x;
-    if (c >= chunk_base[p.rows]) return;
-    for (unsigned i = tid; i < 512 + 2; i += 256) s_diff[i] = 0u;
-    __syncthreads();
+    __shared__ unsigned s_diff_all[RC_CC_WARPS][512 + 32];
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned *s_diff = s_diff_all[warp];
+    const unsigned c = blockIdx.x * RC_CC_WARPS + warp;
+    if (c >= chunk_base[p.rows]) return;  // warp-uniform; no CTA barrier below
+    for (unsigned i = lane; i <= p.cols; i += 32) s_diff[i] = 0u;
     const unsigned r = chunk_row[c];
     const unsigned ebeg = row_start[r] + (c - chunk_base[r]) * p.k2;
     const unsigned eend = min(row_start[r + 1], ebeg + p.k2);
-    if (ebeg + tid < eend) {
-        const unsigned xw = entries[ebeg + tid].y;
-        const unsigned x0 = xw & 0xffffu, w = xw >> 16;
-        atomicAdd(&s_diff[x0], 1u);
-        atomicAdd(&s_diff[x0 + w], 0xffffffffu);
+    unsigned xw[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const unsigned e = ebeg + q * 32 + lane;
+        xw[q] = (q * 32 + lane < p.k2 && e < eend) ? entries[e].y : 0u;
     }
-    __syncthreads();
-    const unsigned d0 = s_diff[2 * tid], d1 = s_diff[2 * tid + 1];
-    unsigned total;
-    const unsigned excl = cta_exclusive_scan<256>(d0 + d1, &total, s_ws);
-    const unsigned c0 = excl + d0, c1 = c0 + d1;
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const unsigned x0 = xw[q] & 0xffffu, w = xw[q] >> 16;
+        if (w) {
+            atomicAdd(&s_diff[x0], 1u);
+            atomicAdd(&s_diff[x0 + w], 0xffffffffu);
+        }
+    }
+    __syncwarp();
     unsigned *mrow = m + (size_t)c * p.cols;
-    if (2 * tid < p.cols) mrow[2 * tid] = c0;
-    if (2 * tid + 1 < p.cols) mrow[2 * tid + 1] = c1;
+    unsigned carry = 0;
+    for (unsigned base = 0; base < p.cols; base += 32) {
+        const unsigned i = base + lane;
+        const unsigned cnt = warp_inclusive_scan(i < p.cols ? s_diff[i] : 0u, lane) + carry;
+        carry = __shfl_sync(0xffffffffu, cnt, 31);
+        if (i < p.cols) mrow[i] = cnt;
+    }
 }
 
 // ---- per (row, column): exclusive scan over the row's chunks in place; tile totals out ------------
-__global__ void __launch_bounds__(256)
+// CTA = (row, 32 columns); its 32 warps split the row's chunks, lanes = columns.
+constexpr int RC_CS_WARPS = 32;
+__global__ void __launch_bounds__(32 * RC_CS_WARPS)
 rc_col_scan_kernel(const RcParams p, const unsigned *__restrict__ chunk_base,
                    unsigned *__restrict__ m, unsigned *__restrict__ tile_cnt) {
-    __shared__ unsigned s_part[8][32];
+    __shared__ unsigned s_part[RC_CS_WARPS][32];
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned r = blockIdx.y, col = blockIdx.x * 32u + lane;
     const unsigned cb = chunk_base[r], ce = chunk_base[r + 1];
-    const unsigned per = (ce - cb + 7) / 8;
+    const unsigned per = (ce - cb + RC_CS_WARPS - 1) / RC_CS_WARPS;
     const unsigned c0 = min(ce, cb + warp * per), c1 = min(ce, c0 + per);
     const bool live = col < p.cols;
     unsigned sum = 0;
     if (live) {
-#pragma unroll 4
+#pragma unroll 8
         for (unsigned c = c0; c < c1; ++c) sum += m[(size_t)c * p.cols + col];
     }
     s_part[warp][lane] = sum;
     __syncthreads();
     unsigned run = 0, total = 0;
 #pragma unroll
-    for (unsigned w = 0; w < 8; ++w) {
+    for (unsigned w = 0; w < RC_CS_WARPS; ++w) {
         const unsigned v = s_part[w][lane];
         if (w < warp) run += v;
         total += v;
     }
     if (live) {
-        constexpr int U = 4;
+        constexpr int U = 8;
         for (unsigned c = c0; c < c1; c += U) {
             unsigned v[U];
 #pragma unroll
@@ -495,7 +525,8 @@ int launch_rowcol_lists(cudaStream_t stream, const BinParams &bp, const unsigned
     const size_t smem2 = DistSmem<unsigned, RC_STAGE2>::bytes(p.cols);
 
     if (phase == 0) {  // level 1: row lists
-        rc_row_count_kernel<<<p.n1, 256, 0, stream>>>(p, order, box_by_id, l1m);
+        rc_row_count_kernel<<<ceil_div(p.n1, (unsigned)RC_RC_WARPS), 32 * RC_RC_WARPS, 0, stream>>>(
+            p, order, box_by_id, l1m);
         JSB_CUDA_OK(cudaGetLastError());
         rc_row_scan_kernel<<<p.rows, 1024, 0, stream>>>(p, l1m, row_tot);
         JSB_CUDA_OK(cudaGetLastError());
@@ -506,9 +537,11 @@ int launch_rowcol_lists(cudaStream_t stream, const BinParams &bp, const unsigned
         JSB_CUDA_OK(cudaGetLastError());
         note_launch(4);
     } else if (phase == 1) {  // level 2 run starts and tile bins
-        rc_col_count_kernel<<<p.n2max, 256, 0, stream>>>(p, row_start, chunk_base, chunk_row, entries, m);
+        rc_col_count_kernel<<<ceil_div(p.n2max, (unsigned)RC_CC_WARPS), 32 * RC_CC_WARPS, 0, stream>>>(
+            p, row_start, chunk_base, chunk_row, entries, m);
         JSB_CUDA_OK(cudaGetLastError());
-        rc_col_scan_kernel<<<dim3(ceil_div(p.cols, 32u), p.rows), 256, 0, stream>>>(p, chunk_base, m, tile_cnt);
+        rc_col_scan_kernel<<<dim3(ceil_div(p.cols, 32u), p.rows), 32 * RC_CS_WARPS, 0, stream>>>(
+            p, chunk_base, m, tile_cnt);
         JSB_CUDA_OK(cudaGetLastError());
         rc_tile_scan_bins_kernel<<<1, 1024, 0, stream>>>(p, tile_cnt, tile_bins);
         JSB_CUDA_OK(cudaGetLastError());
