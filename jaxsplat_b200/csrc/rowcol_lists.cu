@@ -146,21 +146,23 @@ rc_row_count_kernel(const RcParams p, const unsigned *__restrict__ order,
 }
 
 // ---- in-place exclusive scan of every row of the level-1 matrix ----------------------------------
+// One CTA per row; every thread owns a contiguous segment, so a single CTA-wide scan suffices.
 __global__ void __launch_bounds__(1024)
 rc_row_scan_kernel(const RcParams p, unsigned *__restrict__ l1m, unsigned *__restrict__ row_tot) {
     __shared__ unsigned s_ws[1024 / 32 + 1];
     unsigned *row = l1m + (size_t)blockIdx.x * p.n1s;
-    unsigned carry = 0;
-    for (unsigned b = 0; b < p.n1; b += 1024) {
-        const unsigned i = b + threadIdx.x;
-        const unsigned v = i < p.n1 ? row[i] : 0u;
-        unsigned total;
-        const unsigned e = cta_exclusive_scan<1024>(v, &total, s_ws);
-        if (i < p.n1) row[i] = carry + e;
-        carry += total;
-        __syncthreads();
+    const unsigned per = (p.n1 + 1023u) / 1024u;
+    const unsigned i0 = min(p.n1, threadIdx.x * per), i1 = min(p.n1, i0 + per);
+    unsigned sum = 0;
+    for (unsigned i = i0; i < i1; ++i) sum += row[i];
+    unsigned total;
+    unsigned run = cta_exclusive_scan<1024>(sum, &total, s_ws);
+    for (unsigned i = i0; i < i1; ++i) {
+        const unsigned v = row[i];
+        row[i] = run;
+        run += v;
     }
-    if (threadIdx.x == 0) row_tot[blockIdx.x] = carry;
+    if (threadIdx.x == 0) row_tot[blockIdx.x] = total;
 }
 
 // ---- row starts, level-2 chunk bases and the row of every level-2 chunk ---------------------------
@@ -286,26 +288,25 @@ rc_col_scan_kernel(const RcParams p, const unsigned *__restrict__ chunk_base,
     }
 }
 
-// ---- tile counts -> tile bases (in place) and tile bins: one CTA walks the tiles 1024 at a time ----
+// ---- tile counts -> tile bases (in place) and tile bins: one CTA, a contiguous segment per thread -
 __global__ void __launch_bounds__(1024)
 rc_tile_scan_bins_kernel(const RcParams p, unsigned *__restrict__ tile_cnt,
                          int2 *__restrict__ tile_bins) {
     __shared__ unsigned s_ws[1024 / 32 + 1];
     const unsigned nt = p.rows * p.cols;
-    unsigned carry = 0;
-    for (unsigned b = 0; b < nt; b += 1024) {
-        const unsigned t = b + threadIdx.x;
-        const unsigned v = t < nt ? tile_cnt[t] : 0u;
-        unsigned total;
-        const unsigned base = carry + cta_exclusive_scan<1024>(v, &total, s_ws);
-        if (t < nt) {
-            tile_cnt[t] = base;
-            // tiles without intersections stay (0,0) like the reference's memset + edge detection
-            tile_bins[(size_t)p.band_y0 * p.cols + t] =
-                v ? make_int2((int)base, (int)(base + v)) : make_int2(0, 0);
-        }
-        carry += total;
-        __syncthreads();
+    const unsigned per = (nt + 1023u) / 1024u;
+    const unsigned t0 = min(nt, threadIdx.x * per), t1 = min(nt, t0 + per);
+    unsigned sum = 0;
+    for (unsigned t = t0; t < t1; ++t) sum += tile_cnt[t];
+    unsigned total;
+    unsigned base = cta_exclusive_scan<1024>(sum, &total, s_ws);
+    for (unsigned t = t0; t < t1; ++t) {
+        const unsigned v = tile_cnt[t];
+        tile_cnt[t] = base;
+        // tiles without intersections stay (0,0) like the reference's memset + edge detection
+        tile_bins[(size_t)p.band_y0 * p.cols + t] =
+            v ? make_int2((int)base, (int)(base + v)) : make_int2(0, 0);
+        base += v;
     }
 }
 
