@@ -145,23 +145,48 @@ rc_row_count_kernel(const RcParams p, const unsigned *__restrict__ order,
     }
 }
 
-// ---- in-place exclusive scan of every row of the level-1 matrix ----------------------------------
-// One CTA per row; every thread owns a contiguous segment, so a single CTA-wide scan suffices.
+// In-place exclusive scan of n words by one CTA of 32 warps: warp w owns the contiguous slice
+// [w * per, (w + 1) * per) and walks it 32 words at a time (coalesced, loads of the next strip
+// independent of the running prefix), so the CTA synchronises only once; `each(i, base, v)` sees
+// every element's exclusive prefix and value.  Returns the total (all threads).
+template <typename F>
+__device__ __forceinline__ unsigned cta32_exclusive_scan_inplace(unsigned *data, unsigned n, F each) {
+    __shared__ unsigned s_wtot[32];
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned per = ((n + 31u) / 32u + 31u) & ~31u;  // slice length, multiple of 32
+    const unsigned i0 = min(n, warp * per), i1 = min(n, i0 + per);
+    unsigned sum = 0;
+#pragma unroll 4
+    for (unsigned i = i0 + lane; i < i1; i += 32) sum += data[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) s_wtot[warp] = sum;
+    __syncthreads();
+    unsigned run = 0, total = 0;
+#pragma unroll
+    for (unsigned w = 0; w < 32; ++w) {
+        const unsigned v = s_wtot[w];
+        if (w < warp) run += v;
+        total += v;
+    }
+    for (unsigned b0 = i0; b0 < i1; b0 += 32) {
+        const unsigned i = b0 + lane;
+        const unsigned v = i < i1 ? data[i] : 0u;
+        const unsigned incl = warp_inclusive_scan(v, lane);
+        if (i < i1) {
+            data[i] = run + incl - v;
+            each(i, run + incl - v, v);
+        }
+        run += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    return total;
+}
+
+// ---- in-place exclusive scan of every row of the level-1 matrix (one CTA per row) -----------------
 __global__ void __launch_bounds__(1024)
 rc_row_scan_kernel(const RcParams p, unsigned *__restrict__ l1m, unsigned *__restrict__ row_tot) {
-    __shared__ unsigned s_ws[1024 / 32 + 1];
     unsigned *row = l1m + (size_t)blockIdx.x * p.n1s;
-    const unsigned per = (p.n1 + 1023u) / 1024u;
-    const unsigned i0 = min(p.n1, threadIdx.x * per), i1 = min(p.n1, i0 + per);
-    unsigned sum = 0;
-    for (unsigned i = i0; i < i1; ++i) sum += row[i];
-    unsigned total;
-    unsigned run = cta_exclusive_scan<1024>(sum, &total, s_ws);
-    for (unsigned i = i0; i < i1; ++i) {
-        const unsigned v = row[i];
-        row[i] = run;
-        run += v;
-    }
+    const unsigned total = cta32_exclusive_scan_inplace(row, p.n1, [](unsigned, unsigned, unsigned) {});
     if (threadIdx.x == 0) row_tot[blockIdx.x] = total;
 }
 
@@ -288,26 +313,15 @@ rc_col_scan_kernel(const RcParams p, const unsigned *__restrict__ chunk_base,
     }
 }
 
-// ---- tile counts -> tile bases (in place) and tile bins: one CTA, a contiguous segment per thread -
+// ---- tile counts -> tile bases (in place) and tile bins (one CTA) ----------------------------------
 __global__ void __launch_bounds__(1024)
 rc_tile_scan_bins_kernel(const RcParams p, unsigned *__restrict__ tile_cnt,
                          int2 *__restrict__ tile_bins) {
-    __shared__ unsigned s_ws[1024 / 32 + 1];
-    const unsigned nt = p.rows * p.cols;
-    const unsigned per = (nt + 1023u) / 1024u;
-    const unsigned t0 = min(nt, threadIdx.x * per), t1 = min(nt, t0 + per);
-    unsigned sum = 0;
-    for (unsigned t = t0; t < t1; ++t) sum += tile_cnt[t];
-    unsigned total;
-    unsigned base = cta_exclusive_scan<1024>(sum, &total, s_ws);
-    for (unsigned t = t0; t < t1; ++t) {
-        const unsigned v = tile_cnt[t];
-        tile_cnt[t] = base;
+    int2 *bins = tile_bins + (size_t)p.band_y0 * p.cols;
+    cta32_exclusive_scan_inplace(tile_cnt, p.rows * p.cols, [bins](unsigned t, unsigned base, unsigned v) {
         // tiles without intersections stay (0,0) like the reference's memset + edge detection
-        tile_bins[(size_t)p.band_y0 * p.cols + t] =
-            v ? make_int2((int)base, (int)(base + v)) : make_int2(0, 0);
-        base += v;
-    }
+        bins[t] = v ? make_int2((int)base, (int)(base + v)) : make_int2(0, 0);
+    });
 }
 
 // ---- the in-order staged distribution of one chunk (both levels) -----------------------------------
