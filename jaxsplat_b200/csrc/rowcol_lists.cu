@@ -57,7 +57,7 @@ struct RcLayout {
     size_t row_tot;     // [rows]
     size_t row_start;   // [rows + 1]
     size_t chunk_base;  // [rows + 1]
-    size_t chunk_row;   // [n2max]
+    size_t chunk_row;   // uint4 [n2max]: {row, first entry, one past last entry, 0} of every level-2 chunk
     size_t tile_cnt;    // [rows * cols] -> exclusive scan (tile bases)
     size_t m;           // [n2max][cols] level-2 counts -> exclusive prefix per (row, col)
     size_t entries;     // uint2 [entries] (8-byte aligned)
@@ -73,7 +73,7 @@ static RcLayout rc_layout(const RcParams &p, unsigned long long row_entries) {
     L.row_tot = o;    o += up4(p.rows);
     L.row_start = o;  o += up4(p.rows + 1);
     L.chunk_base = o; o += up4(p.rows + 1);
-    L.chunk_row = o;  o += up4(p.n2max);
+    L.chunk_row = o;  o += 4 * (size_t)p.n2max;
     L.tile_cnt = o;   o += up4((size_t)p.rows * p.cols + 1);
     L.m = o;          o += up4((size_t)p.n2max * p.cols);
     L.entries = o;    o += up4(2 * (size_t)row_entries + 4);
@@ -190,19 +190,22 @@ rc_row_scan_kernel(const RcParams p, unsigned *__restrict__ l1m, unsigned *__res
     if (threadIdx.x == 0) row_tot[blockIdx.x] = total;
 }
 
-// ---- row starts, level-2 chunk bases and the row of every level-2 chunk ---------------------------
+// ---- row starts, level-2 chunk bases and {row, entry range} of every level-2 chunk ----------------
 // Every CTA rebuilds the two <= 256-entry scans from the row totals (cheaper than a launch of its
-// own); CTA 0 publishes them for the later kernels.
+// own); CTA 0 publishes them for the later kernels.  The per-chunk record spares the level-2
+// kernels a chain of three dependent global loads before they can touch their entries.
 __global__ void __launch_bounds__(256)
 rc_chunk_rows_kernel(const RcParams p, const unsigned *__restrict__ row_tot,
                      unsigned *__restrict__ row_start, unsigned *__restrict__ chunk_base,
-                     unsigned *__restrict__ chunk_row) {
-    __shared__ unsigned s_base[256 + 1];
+                     uint4 *__restrict__ chunk_info) {
+    __shared__ unsigned s_base[256 + 1], s_start[256 + 1];
     __shared__ unsigned s_ws[256 / 32 + 1];
     const unsigned tid = threadIdx.x;
     const unsigned n = tid < p.rows ? row_tot[tid] : 0u;
     unsigned total;
     unsigned e = cta_exclusive_scan<256>(n, &total, s_ws);
+    if (tid < p.rows) s_start[tid] = e;
+    if (tid == 0) s_start[p.rows] = total;
     if (blockIdx.x == 0) {
         if (tid < p.rows) row_start[tid] = e;
         if (tid == 0) row_start[p.rows] = total;
@@ -218,13 +221,18 @@ rc_chunk_rows_kernel(const RcParams p, const unsigned *__restrict__ row_tot,
     }
     __syncthreads();
     const unsigned ch = blockIdx.x * 256u + tid;
-    if (ch >= s_base[p.rows]) return;
-    unsigned lo = 0, hi = p.rows;  // invariant: s_base[lo] <= ch < s_base[hi]
-    while (hi - lo > 1) {
-        const unsigned mid = (lo + hi) >> 1;
-        if (s_base[mid] <= ch) lo = mid; else hi = mid;
+    if (ch >= p.n2max) return;
+    uint4 info = make_uint4(0u, 0u, 0u, 0u);  // chunks beyond the total: empty range
+    if (ch < s_base[p.rows]) {
+        unsigned lo = 0, hi = p.rows;  // invariant: s_base[lo] <= ch < s_base[hi]
+        while (hi - lo > 1) {
+            const unsigned mid = (lo + hi) >> 1;
+            if (s_base[mid] <= ch) lo = mid; else hi = mid;
+        }
+        const unsigned ebeg = s_start[lo] + (ch - s_base[lo]) * p.k2;
+        info = make_uint4(lo, ebeg, min(s_start[lo + 1], ebeg + p.k2), 0u);
     }
-    chunk_row[ch] = lo;
+    chunk_info[ch] = info;
 }
 
 // ---- level 2 counts: tile columns covered by each chunk of k2 row entries -------------------------
@@ -232,18 +240,17 @@ rc_chunk_rows_kernel(const RcParams p, const unsigned *__restrict__ row_tot,
 // shared memory, 8 entries per lane, then a prefix over the columns.
 constexpr int RC_CC_WARPS = 8;
 __global__ void __launch_bounds__(32 * RC_CC_WARPS)
-rc_col_count_kernel(const RcParams p, const unsigned *__restrict__ row_start,
-                    const unsigned *__restrict__ chunk_base, const unsigned *__restrict__ chunk_row,
+rc_col_count_kernel(const RcParams p, const uint4 *__restrict__ chunk_info,
                     const uint2 *__restrict__ entries, unsigned *__restrict__ m) {
     __shared__ unsigned s_diff_all[RC_CC_WARPS][512 + 32];
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned *s_diff = s_diff_all[warp];
     const unsigned c = blockIdx.x * RC_CC_WARPS + warp;
-    if (c >= chunk_base[p.rows]) return;  // warp-uniform; no CTA barrier below
+    if (c >= p.n2max) return;  // warp-uniform; no CTA barrier below
+    const uint4 info = __ldg(chunk_info + c);
+    const unsigned ebeg = info.y, eend = info.z;
+    if (ebeg >= eend) return;
     for (unsigned i = lane; i <= p.cols; i += 32) s_diff[i] = 0u;
-    const unsigned r = chunk_row[c];
-    const unsigned ebeg = row_start[r] + (c - chunk_base[r]) * p.k2;
-    const unsigned eend = min(row_start[r + 1], ebeg + p.k2);
     unsigned xw[8];
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
@@ -429,17 +436,36 @@ rc_row_scatter_kernel(const RcParams p, const unsigned *__restrict__ order,
     const unsigned lane = threadIdx.x, chunk = blockIdx.x;
     unsigned lo[8], len[8];
     uint2 pay[8];
+    unsigned gid[8];
+    bool have[8];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-        unsigned g, y0, h, xw;
-        const unsigned item = q * 32 + lane;
-        const bool ok = item < p.k1 && load_box(p, chunk * p.k1 + item, order, box_by_id, g, y0, h, xw);
-        lo[q] = ok ? y0 : 0u;
-        len[q] = ok ? h : 0u;
-        pay[q] = make_uint2(g, xw);
+    for (int q = 0; q < 8; ++q) {  // 8 independent loads of the depth order ...
+        const unsigned item = q * 32 + lane, pos = chunk * p.k1 + item;
+        have[q] = item < p.k1 && pos < p.n;
+        gid[q] = have[q] ? order[pos] : 0u;
     }
-    for (unsigned r = lane; r < p.rows; r += 32)
-        S.gbase[r] = row_start[r] + l1m[(size_t)r * p.n1s + chunk];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {  // ... then 8 independent gathers of the boxes
+        uint2 b = make_uint2(0u, 0u);
+        if (have[q]) b = __ldg(box_by_id + gid[q]);
+        const unsigned w = b.y & 0xffffu, h = b.y >> 16;
+        const bool ok = w != 0u && h != 0u;
+        lo[q] = ok ? (b.x >> 16) - p.band_y0 : 0u;
+        len[q] = ok ? h : 0u;
+        pay[q] = make_uint2(gid[q], (b.x & 0xffffu) | (w << 16));
+    }
+    // run starts of this chunk in every row: loads in flight before the dependent stores
+    unsigned gb[8];  // rows <= 256
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const unsigned r = lane + 32u * i;
+        gb[i] = r < p.rows ? __ldg(row_start + r) + __ldg(l1m + (size_t)r * p.n1s + chunk) : 0u;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const unsigned r = lane + 32u * i;
+        if (r < p.rows) S.gbase[r] = gb[i];
+    }
     const unsigned pairs = distribute_rank<uint2, RC_STAGE1>(lo, len, p.rows, S);
     if (pairs == 0) return;  // warp-uniform
     distribute_place<uint2, RC_STAGE1>(lo, len, pay, pairs, S, entries);
@@ -447,18 +473,24 @@ rc_row_scatter_kernel(const RcParams p, const unsigned *__restrict__ order,
 
 // ---- level 2: row entries -> per-tile id lists -----------------------------------------------------
 __global__ void __launch_bounds__(32)
-rc_col_scatter_kernel(const RcParams p, const unsigned *__restrict__ row_start,
-                      const unsigned *__restrict__ chunk_base,
-                      const unsigned *__restrict__ chunk_row, const uint2 *__restrict__ entries,
-                      const unsigned *__restrict__ m, const unsigned *__restrict__ tile_base,
-                      unsigned *__restrict__ out_ids) {
+rc_col_scatter_kernel(const RcParams p, const uint4 *__restrict__ chunk_info,
+                      const uint2 *__restrict__ entries, const unsigned *__restrict__ m,
+                      const unsigned *__restrict__ tile_base, unsigned *__restrict__ out_ids) {
     extern __shared__ __align__(16) unsigned char rc_smem[];
     const DistSmem<unsigned, RC_STAGE2> S(rc_smem, p.cols);
     const unsigned lane = threadIdx.x, c = blockIdx.x;
-    if (c >= chunk_base[p.rows]) return;
-    const unsigned r = chunk_row[c];
-    const unsigned ebeg = row_start[r] + (c - chunk_base[r]) * p.k2;
-    const unsigned eend = min(row_start[r + 1], ebeg + p.k2);
+    const uint4 info = __ldg(chunk_info + c);
+    const unsigned r = info.x, ebeg = info.y, eend = info.z;
+    if (ebeg >= eend) return;
+    // run starts of this chunk: all loads in flight before the first dependent store
+    const unsigned *mrow = m + (size_t)c * p.cols;
+    const unsigned *tb = tile_base + (size_t)r * p.cols;
+    unsigned gb[16];  // cols <= 512
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const unsigned x = lane + 32u * i;
+        gb[i] = x < p.cols ? __ldg(tb + x) + __ldg(mrow + x) : 0u;
+    }
     unsigned lo[8], len[8], pay[8];
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
@@ -469,9 +501,11 @@ rc_col_scatter_kernel(const RcParams p, const unsigned *__restrict__ row_start,
         lo[q] = v.y & 0xffffu;
         len[q] = v.y >> 16;
     }
-    const unsigned *mrow = m + (size_t)c * p.cols;
-    const unsigned *tb = tile_base + (size_t)r * p.cols;
-    for (unsigned x = lane; x < p.cols; x += 32) S.gbase[x] = tb[x] + mrow[x];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const unsigned x = lane + 32u * i;
+        if (x < p.cols) S.gbase[x] = gb[i];
+    }
     const unsigned pairs = distribute_rank<unsigned, RC_STAGE2>(lo, len, p.cols, S);
     if (pairs == 0) return;
     distribute_place<unsigned, RC_STAGE2>(lo, len, pay, pairs, S, out_ids);
@@ -533,7 +567,8 @@ int launch_rowcol_lists(cudaStream_t stream, const BinParams &bp, const unsigned
     const RcLayout L = rc_layout(p, row_entries);
     unsigned *l1m = scratch + L.l1m, *row_tot = scratch + L.row_tot;
     unsigned *row_start = scratch + L.row_start, *chunk_base = scratch + L.chunk_base;
-    unsigned *chunk_row = scratch + L.chunk_row, *tile_cnt = scratch + L.tile_cnt;
+    uint4 *chunk_info = reinterpret_cast<uint4 *>(scratch + L.chunk_row);
+    unsigned *tile_cnt = scratch + L.tile_cnt;
     unsigned *m = scratch + L.m;
     uint2 *entries = reinterpret_cast<uint2 *>(scratch + L.entries);
     const size_t smem1 = DistSmem<uint2, RC_STAGE1>::bytes(p.rows);
@@ -546,14 +581,14 @@ int launch_rowcol_lists(cudaStream_t stream, const BinParams &bp, const unsigned
         rc_row_scan_kernel<<<p.rows, 1024, 0, stream>>>(p, l1m, row_tot);
         JSB_CUDA_OK(cudaGetLastError());
         rc_chunk_rows_kernel<<<ceil_div(p.n2max, 256u), 256, 0, stream>>>(p, row_tot, row_start,
-                                                                          chunk_base, chunk_row);
+                                                                          chunk_base, chunk_info);
         JSB_CUDA_OK(cudaGetLastError());
         rc_row_scatter_kernel<<<p.n1, 32, smem1, stream>>>(p, order, box_by_id, l1m, row_start, entries);
         JSB_CUDA_OK(cudaGetLastError());
         note_launch(4);
     } else if (phase == 1) {  // level 2 run starts and tile bins
         rc_col_count_kernel<<<ceil_div(p.n2max, (unsigned)RC_CC_WARPS), 32 * RC_CC_WARPS, 0, stream>>>(
-            p, row_start, chunk_base, chunk_row, entries, m);
+            p, chunk_info, entries, m);
         JSB_CUDA_OK(cudaGetLastError());
         rc_col_scan_kernel<<<dim3(ceil_div(p.cols, 32u), p.rows), 32 * RC_CS_WARPS, 0, stream>>>(
             p, chunk_base, m, tile_cnt);
@@ -562,8 +597,8 @@ int launch_rowcol_lists(cudaStream_t stream, const BinParams &bp, const unsigned
         JSB_CUDA_OK(cudaGetLastError());
         note_launch(3);
     } else {  // level 2: the lists
-        rc_col_scatter_kernel<<<p.n2max, 32, smem2, stream>>>(p, row_start, chunk_base, chunk_row,
-                                                              entries, m, tile_cnt, ids_sorted);
+        rc_col_scatter_kernel<<<p.n2max, 32, smem2, stream>>>(p, chunk_info, entries, m, tile_cnt,
+                                                              ids_sorted);
         JSB_CUDA_OK(cudaGetLastError());
         note_launch();
     }
