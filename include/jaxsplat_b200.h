@@ -59,6 +59,27 @@ JSB200_API void jsb200_rasterize_fwd(jsb200_stream_t stream, void **buffers, con
 JSB200_API void jsb200_rasterize_bwd(jsb200_stream_t stream, void **buffers, const char *opaque,
                           size_t opaque_len);
 
+/* The same four targets for XLA's API_VERSION_STATUS_RETURNING custom calls (the default
+ * api_version of jaxlib.hlo_helpers.custom_call, which jaxsplat/_project/lowering.py:40-75 and
+ * jaxsplat/_rasterize/lowering.py:40-73 use): XLA passes an XlaCustomCallStatus* as a fifth
+ * argument.  The reference ignores it and throws std::runtime_error through the C frame instead
+ * (lib/common.h:11-23, lib/ffi.h:19-21); these variants report a failure through
+ * XlaCustomCallStatusSetFailure (resolved in the host process at the time of the failure) so the
+ * error surfaces as an XlaRuntimeError in Python.  Behaviour on success is identical. */
+typedef struct XlaCustomCallStatus_ jsb200_xla_status_t;
+JSB200_API void jsb200_project_fwd_status(jsb200_stream_t stream, void **buffers,
+                                          const char *opaque, size_t opaque_len,
+                                          jsb200_xla_status_t *status);
+JSB200_API void jsb200_project_bwd_status(jsb200_stream_t stream, void **buffers,
+                                          const char *opaque, size_t opaque_len,
+                                          jsb200_xla_status_t *status);
+JSB200_API void jsb200_rasterize_fwd_status(jsb200_stream_t stream, void **buffers,
+                                            const char *opaque, size_t opaque_len,
+                                            jsb200_xla_status_t *status);
+JSB200_API void jsb200_rasterize_bwd_status(jsb200_stream_t stream, void **buffers,
+                                            const char *opaque, size_t opaque_len,
+                                            jsb200_xla_status_t *status);
+
 /* Fused render (no single reference entry point: replaces the chain
  * jaxsplat/__init__.py:54-70 = project (lib/ops.cu:12-61) then rasterize (lib/ops.cu:107-170) and,
  * for the backward, rasterize_bwd (lib/ops.cu:172-235) then project_bwd (lib/ops.cu:63-105)).
@@ -81,6 +102,27 @@ JSB200_API int jsb200_render_fwd(jsb200_stream_t stream, void **buffers, const c
                                  size_t opaque_len, unsigned long long *token_out);
 JSB200_API int jsb200_render_bwd(jsb200_stream_t stream, void **buffers, const char *opaque,
                                  size_t opaque_len, unsigned long long token);
+
+/* Batched cameras (an API addition: the reference renders one camera per call,
+ * jaxsplat/__init__.py:6-70, and a multi-view step loops over it in Python).  num_views cameras of
+ * the same Gaussians in one call; per-view arrays are stacked on a leading view axis.
+ *   render_views_fwd  in : means3d scales quats viewmats(B,4,4) colors opacities background
+ *                     out: cov3ds(B,N,6) xys(B,N,2) depths(B,N) radii(B,N) conics(B,N,3)
+ *                          compensation(B,N) final_Ts(B,H,W) final_idx(B,H,W) out_img(B,H,W,3)
+ *   render_views_bwd  in : the 7 operands and 8 residual arrays above (final_Ts, final_idx last),
+ *                          v_out_img(B,H,W,3), v_out_img_alpha(B,H,W) or NULL
+ *                     out: v_mean3d v_scale v_quat v_colors v_opacity -- summed over the views
+ * View b is bit-identical to jsb200_render_fwd with viewmats[b]; the gradients equal the sum of
+ * the per-view jsb200_render_bwd results up to float summation order.  tokens_out / tokens hold
+ * num_views binning tokens (may be NULL: the backward then re-bins every view).  The binnings of
+ * the most recent "view_slots" views (jsb200_set_option, default 8) are kept for the backward.
+ * Return 0 on success. */
+JSB200_API int jsb200_render_views_fwd(jsb200_stream_t stream, void **buffers, const char *opaque,
+                                       size_t opaque_len, unsigned num_views,
+                                       unsigned long long *tokens_out);
+JSB200_API int jsb200_render_views_bwd(jsb200_stream_t stream, void **buffers, const char *opaque,
+                                       size_t opaque_len, unsigned num_views,
+                                       const unsigned long long *tokens);
 
 /* replaces make_descriptor (lib/ffi.cu:15-52): fills out[80] with the reference-compatible
  * descriptor (img_shape is given as H, W like the Python API).  Returns 0 on success. */
@@ -121,7 +163,8 @@ JSB200_API unsigned long long jsb200_error_count(void);
  *               thread instead of two),
  *      "rowcol" (1 default; 0 builds the per-tile lists with the older counting distribution of
  *               tile_lists.cu instead of the two-level row/column distribution),
- *      "timing" (0 default; 1 brackets every stage with CUDA events, see jsb200_get_stage_times) */
+ *      "timing" (0 default; 1 brackets every stage with CUDA events, see jsb200_get_stage_times),
+ *      "view_slots" (8 default; binning workspaces a batched-camera call cycles through) */
 JSB200_API int jsb200_set_option(const char *key, int value);
 /* Copies the binning produced by the most recent rasterize/sort_and_bin call on `stream` into
  * caller device buffers (any may be NULL): ids_sorted[num_intersects] i32, tile_bins[tiles] int2,

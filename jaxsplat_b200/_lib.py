@@ -19,8 +19,14 @@ EXPORTS = (
     "jsb200_project_bwd",
     "jsb200_rasterize_fwd",
     "jsb200_rasterize_bwd",
+    "jsb200_project_fwd_status",
+    "jsb200_project_bwd_status",
+    "jsb200_rasterize_fwd_status",
+    "jsb200_rasterize_bwd_status",
     "jsb200_render_fwd",
     "jsb200_render_bwd",
+    "jsb200_render_views_fwd",
+    "jsb200_render_views_bwd",
     "jsb200_make_descriptor",
     "jsb200_set_descriptor_band",
     "jsb200_sort_and_bin",
@@ -61,6 +67,17 @@ def lib() -> ctypes.CDLL:
         fn = getattr(L, name)
         fn.argtypes = [vp, ctypes.POINTER(vp), cp, sz]
         fn.restype = None
+    for name in ("jsb200_project_fwd_status", "jsb200_project_bwd_status",
+                 "jsb200_rasterize_fwd_status", "jsb200_rasterize_bwd_status"):
+        fn = getattr(L, name)
+        fn.argtypes = [vp, ctypes.POINTER(vp), cp, sz, vp]
+        fn.restype = None
+    L.jsb200_render_views_fwd.argtypes = [vp, ctypes.POINTER(vp), cp, sz, u,
+                                          ctypes.POINTER(ctypes.c_ulonglong)]
+    L.jsb200_render_views_fwd.restype = i
+    L.jsb200_render_views_bwd.argtypes = [vp, ctypes.POINTER(vp), cp, sz, u,
+                                          ctypes.POINTER(ctypes.c_ulonglong)]
+    L.jsb200_render_views_bwd.restype = i
     L.jsb200_render_fwd.argtypes = [vp, ctypes.POINTER(vp), cp, sz, ctypes.POINTER(ctypes.c_ulonglong)]
     L.jsb200_render_fwd.restype = i
     L.jsb200_render_bwd.argtypes = [vp, ctypes.POINTER(vp), cp, sz, ctypes.c_ulonglong]

@@ -225,3 +225,64 @@ def render_bwd(mean3ds, scales, quats, viewmat, colors, opacities, background, c
         d = _ffi.with_band(d, band[0], band[1])
     _call_native("jsb200_render_bwd", ins + outs, d, ctypes.c_ulonglong(int(token)))
     return tuple(outs)
+
+
+# ---- batched cameras: this library only ------------------------------------------
+def render_views_fwd(mean3ds, scales, quats, viewmats, colors, opacities, background, *,
+                     num_points, img_shape, f, c, glob_scale, clip_thresh, block_width):
+    """B cameras of the same Gaussians in one native call (jsb200_render_views_fwd).  Returns
+    ((cov3ds, xys, depths, radii, conics, compensation, final_Ts, final_idx, imgs), tokens), every
+    array with a leading view axis; view b is bit-identical to ``render_fwd`` with viewmats[b]."""
+    import ctypes
+
+    n, dev = num_points, mean3ds.device
+    H, W = img_shape
+    if viewmats.dim() != 3:
+        raise TypeError(f"viewmats: expected float32(B, 4, 4), got {tuple(viewmats.shape)}")
+    B = int(viewmats.shape[0])
+    ins = [_f32(mean3ds, (n, 3), "mean3ds"), _f32(scales, (n, 3), "scales"),
+           _f32(quats, (n, 4), "quats"), _f32(viewmats, (B, 4, 4), "viewmats"),
+           _f32(colors, (n, 3), "colors"), _f32(opacities, (n, 1), "opacities"),
+           _f32(background, (3,), "background")]
+    outs = [_out((B, n, 6), torch.float32, dev), _out((B, n, 2), torch.float32, dev),
+            _out((B, n, 1), torch.float32, dev), _out((B, n, 1), torch.int32, dev),
+            _out((B, n, 3), torch.float32, dev), _out((B, n, 1), torch.float32, dev),
+            _out((B, H, W, 1), torch.float32, dev), _out((B, H, W, 1), torch.int32, dev),
+            _out((B, H, W, 3), torch.float32, dev)]
+    d = _ffi.make_descriptor(n, tuple(img_shape), tuple(f), tuple(c), glob_scale, clip_thresh,
+                             block_width)
+    tokens = (ctypes.c_ulonglong * max(B, 1))()
+    _call_native("jsb200_render_views_fwd", ins + outs, d, ctypes.c_uint(B), tokens)
+    return tuple(outs), [int(t) for t in tokens[:B]]
+
+
+def render_views_bwd(mean3ds, scales, quats, viewmats, colors, opacities, background, cov3ds, xys,
+                     depths, radii, conics, compensation, final_Ts, final_idx, v_imgs, v_img_alphas,
+                     *, tokens, num_points, img_shape, f, c, glob_scale, clip_thresh, block_width):
+    """Backward of ``render_views_fwd`` in one native call (jsb200_render_views_bwd).  Returns
+    (v_mean3d, v_scale, v_quat, v_colors, v_opacity) summed over the views."""
+    import ctypes
+
+    n, dev = num_points, mean3ds.device
+    H, W = img_shape
+    B = int(viewmats.shape[0])
+    if v_img_alphas is None and block_width != 16:
+        v_img_alphas = torch.zeros((B, H, W, 1), dtype=torch.float32, device=dev)
+    ins = [_f32(mean3ds, (n, 3), "mean3ds"), _f32(scales, (n, 3), "scales"),
+           _f32(quats, (n, 4), "quats"), _f32(viewmats, (B, 4, 4), "viewmats"),
+           _f32(colors, (n, 3), "colors"), _f32(opacities, (n, 1), "opacities"),
+           _f32(background, (3,), "background"), _f32(cov3ds, (B, n, 6), "cov3ds"),
+           _f32(xys, (B, n, 2), "xys"), _f32(depths, (B, n, 1), "depths"),
+           _i32(radii, (B, n, 1), "radii"), _f32(conics, (B, n, 3), "conics"),
+           _f32(compensation, (B, n, 1), "compensation"),
+           _f32(final_Ts, (B, H, W, 1), "final_Ts"), _i32(final_idx, (B, H, W, 1), "final_idx"),
+           _f32(v_imgs, (B, H, W, 3), "v_imgs"),
+           None if v_img_alphas is None else _f32(v_img_alphas, (B, H, W, 1), "v_img_alphas")]
+    outs = [_out((n, 3), torch.float32, dev), _out((n, 3), torch.float32, dev),
+            _out((n, 4), torch.float32, dev), _out((n, 3), torch.float32, dev),
+            _out((n, 1), torch.float32, dev)]
+    d = _ffi.make_descriptor(n, tuple(img_shape), tuple(f), tuple(c), glob_scale, clip_thresh,
+                             block_width)
+    toks = (ctypes.c_ulonglong * max(B, 1))(*[int(t) for t in tokens])
+    _call_native("jsb200_render_views_bwd", ins + outs, d, ctypes.c_uint(B), toks)
+    return tuple(outs)

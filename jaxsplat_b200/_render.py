@@ -46,3 +46,39 @@ def render_fused(means3d, scales, quats, colors, opacities, *, viewmat, backgrou
                              block_width=int(block_size))
     band = None if tile_rows is None else (int(tile_rows[0]), int(tile_rows[1]))
     return _Render.apply(desc, band, means3d, scales, quats, colors, opacities, viewmat, background)
+
+
+class _RenderViews(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, desc: ProjectDescriptor, means3d, scales, quats, colors, opacities, viewmats,
+                background):
+        (cov3ds, xys, depths, radii, conics, compensation, final_Ts, final_idx,
+         imgs), tokens = _ops.render_views_fwd(means3d, scales, quats, viewmats, colors, opacities,
+                                               background, **desc.kwargs())
+        ctx.desc, ctx.tokens = desc, tokens
+        ctx.save_for_backward(means3d, scales, quats, viewmats, colors, opacities, background,
+                              cov3ds, xys, depths, radii, conics, compensation, final_Ts,
+                              final_idx)
+        return imgs
+
+    @staticmethod
+    def backward(ctx, v_imgs):
+        grads = _ops.render_views_bwd(*ctx.saved_tensors, v_imgs.contiguous(), None,
+                                      tokens=ctx.tokens, **ctx.desc.kwargs())
+        return (None,) + tuple(grads) + (None, None)
+
+
+def render_views(means3d, scales, quats, colors, opacities, *, viewmats, background, img_shape, f,
+                 c, glob_scale, clip_thresh, block_size=16):
+    """``render`` for a batch of cameras (an addition to the reference API, which
+    renders one camera per call: jaxsplat/__init__.py:6-70).
+
+    Same arguments as ``render`` except ``viewmats`` (B,4,4).  Returns (B,H,W,3); view b is
+    bit-identical to ``render(..., viewmat=viewmats[b])``.  Differentiable w.r.t. the five
+    positional arrays: their gradients are the sums over the views, computed in one native call.
+    """
+    desc = ProjectDescriptor(num_points=means3d.shape[0], img_shape=tuple(img_shape),
+                             f=(float(f[0]), float(f[1])), c=(float(c[0]), float(c[1])),
+                             glob_scale=float(glob_scale), clip_thresh=float(clip_thresh),
+                             block_width=int(block_size))
+    return _RenderViews.apply(desc, means3d, scales, quats, colors, opacities, viewmats, background)

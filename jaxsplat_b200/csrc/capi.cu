@@ -18,7 +18,10 @@
 #include <memory>
 #include <mutex>
 #include <string>
+#include <tuple>
 #include <vector>
+
+#include <dlfcn.h>
 
 #include "../../include/jaxsplat_b200.h"
 #include "common.cuh"
@@ -50,6 +53,7 @@ extern bool g_bwd_one_pixel;
 extern bool g_fwd_one_pixel;
 static bool g_disable_cache = false;
 static bool g_disable_rowcol = false;
+static unsigned g_view_slots = 8;  // binning workspaces a batched-camera call cycles through
 
 // ---- optional per-stage device timing (jsb200_set_option("timing", 1)) -------------------------
 enum Stage { ST_PROJECT_FWD, ST_BIN_PREP, ST_DEPTH_SORT, ST_EMIT, ST_TILE_SORT, ST_BIN_EDGES,
@@ -93,6 +97,7 @@ struct Ctx {
     // I-scale
     DevBuf tile_keys, tile_vals, tile_ids, tile_scratch;
     DevBuf abs_scratch;
+    DevBuf views_scratch;  // batched cameras: per-view cotangents + parameter-gradient staging
     DevBuf bins, small;  // small: [fingerprint u64][total u64][err int x4][tickets u32 x8]
     unsigned long long *h_pinned = nullptr;  // [fingerprint][total][err...]
     cudaEvent_t ev_ready = nullptr;          // recorded after the D2H of `small`
@@ -131,7 +136,7 @@ struct Ctx {
     void release() {
         DevBuf *all[] = {&records, &dkeys_a, &dkeys_b, &ids_a, &ids_b, &box_by_id, &boxes,
                          &sort_n_scratch, &chain, &tile_keys, &tile_vals, &tile_ids, &tile_scratch,
-                         &bins, &small, &abs_scratch};
+                         &bins, &small, &abs_scratch, &views_scratch};
         for (DevBuf *b : all) {
             if (b->p) cudaFree(b->p);
             b->p = nullptr;
@@ -164,16 +169,20 @@ struct StageScope {
 };
 
 static std::mutex g_ctx_mu;
-static std::map<std::pair<int, cudaStream_t>, std::unique_ptr<Ctx>> g_ctx;
+// One workspace per (device, stream, slot).  Slot 0 serves the single-view entry points; a
+// batched-camera call keeps the binning of view b in slot b % view_slots so that its backward
+// finds it again; kViewsSlot only holds the batched calls' own scratch (and serialises them).
+constexpr unsigned kViewsSlot = 0xffffffffu;
+static std::map<std::tuple<int, cudaStream_t, unsigned>, std::unique_ptr<Ctx>> g_ctx;
 
-static Ctx *get_ctx(cudaStream_t stream) {
+static Ctx *get_ctx(cudaStream_t stream, unsigned slot = 0) {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) {
         set_error("cudaGetDevice failed");
         return nullptr;
     }
     std::lock_guard<std::mutex> lk(g_ctx_mu);
-    auto key = std::make_pair(dev, stream);
+    auto key = std::make_tuple(dev, stream, slot);
     auto it = g_ctx.find(key);
     if (it != g_ctx.end()) return it->second.get();
     auto c = std::make_unique<Ctx>();
@@ -616,7 +625,7 @@ static int rasterize_bwd_impl(cudaStream_t stream, void **buf, const Descriptor 
 // token instead of a fingerprint: render_bwd presented with the same token knows that no other
 // binning ran on this context since, so it needs neither the fingerprint pass nor a host sync.
 static int render_fwd_impl(cudaStream_t stream, void **buf, const Descriptor &d,
-                           unsigned long long *token) {
+                           unsigned long long *token, unsigned slot = 0) {
     // in : 0 means3d 1 scales 2 quats 3 viewmat 4 colors 5 opacities 6 background
     // out: 7 cov3ds 8 xys 9 depths 10 radii 11 conics 12 compensation 13 final_Ts 14 final_idx
     //      15 out_img   (num_tiles_hit / cum_tiles_hit are not produced: nothing reads them)
@@ -624,7 +633,7 @@ static int render_fwd_impl(cudaStream_t stream, void **buf, const Descriptor &d,
     if (check_raster_desc(d)) return 1;
     void *pbuf[12] = {buf[0], buf[1], buf[2], buf[3], buf[7], buf[8], buf[9], buf[10], buf[11],
                       buf[12], nullptr, nullptr};
-    Ctx *c = get_ctx(stream);
+    Ctx *c = get_ctx(stream, slot);
     if (!c) return 1;
     std::lock_guard<std::mutex> lk(c->mu);
     g_stats[0].fetch_add(1);
@@ -667,8 +676,11 @@ static int render_fwd_impl(cudaStream_t stream, void **buf, const Descriptor &d,
                              (float *)buf[13], (int *)buf[14], (float *)buf[15]);
 }
 
+// keep_appearance: v_colors / v_opacity already hold the sum over earlier views of a batched call
+// and keep accumulating (raster_bwd only ever adds to them)
 static int render_bwd_impl(cudaStream_t stream, void **buf, const Descriptor &d,
-                           unsigned long long token) {
+                           unsigned long long token, unsigned slot = 0,
+                           bool keep_appearance = false) {
     // in : 0 means3d 1 scales 2 quats 3 viewmat 4 colors 5 opacities 6 background 7 cov3ds 8 xys
     //      9 depths 10 radii 11 conics 12 compensation 13 final_Ts 14 final_idx
     //      15 v_out_img 16 v_out_img_alpha
@@ -679,14 +691,22 @@ static int render_bwd_impl(cudaStream_t stream, void **buf, const Descriptor &d,
     const size_t n = d.num_points;
     if (n == 0) return 0;
     {
-    Ctx *c = get_ctx(stream);
+    Ctx *c = get_ctx(stream, slot);
     if (!c) return 1;
     std::lock_guard<std::mutex> lk(c->mu);
     g_stats[1].fetch_add(1);
     // the four accumulators are cleared with one memset when the caller laid them out back to
     // back (the torch host layer does), else one by one
     char *g0 = (char *)buf[20];
-    if ((char *)buf[21] == g0 + n * 12 && (char *)buf[22] == g0 + n * 16 && (char *)buf[23] == g0 + n * 24) {
+    if (keep_appearance) {
+        if ((char *)buf[23] == (char *)buf[22] + n * 8) {
+            JSB_CUDA_OK(cudaMemsetAsync(buf[22], 0, n * 20, stream));
+        } else {
+            JSB_CUDA_OK(cudaMemsetAsync(buf[22], 0, n * 2 * 4, stream));
+            JSB_CUDA_OK(cudaMemsetAsync(buf[23], 0, n * 3 * 4, stream));
+        }
+    } else if ((char *)buf[21] == g0 + n * 12 && (char *)buf[22] == g0 + n * 16 &&
+               (char *)buf[23] == g0 + n * 24) {
         JSB_CUDA_OK(cudaMemsetAsync(g0, 0, n * 36, stream));
     } else {
         JSB_CUDA_OK(cudaMemsetAsync(buf[20], 0, n * 3 * 4, stream));
@@ -742,21 +762,120 @@ static int render_bwd_impl(cudaStream_t stream, void **buf, const Descriptor &d,
     return project_bwd_impl(stream, pbuf, d);
 }
 
+
+// ---- batched cameras ------------------------------------------------------------
+// B views of the same Gaussians in one call.  View b's binning lives in workspace slot
+// b % view_slots; the backward walks the views from last to first, so for every slot the view
+// that ran last in the forward (the one whose binning is still there) comes first and hits, and
+// only views beyond the slot count re-bin (stale token).  Parameter gradients are summed over the
+// views: v_colors / v_opacity accumulate in place (raster_bwd adds atomically), v_mean3d / v_scale
+// / v_quat of every view after the first go through a staging buffer and one add kernel.
+static int render_views_fwd_impl(cudaStream_t stream, void **buf, const Descriptor &d, unsigned B,
+                                 unsigned long long *tokens) {
+    // in : 0 means3d 1 scales 2 quats 3 viewmats(B,4,4) 4 colors 5 opacities 6 background
+    // out: 7 cov3ds(B,N,6) 8 xys(B,N,2) 9 depths(B,N) 10 radii(B,N) 11 conics(B,N,3)
+    //      12 compensation(B,N) 13 final_Ts(B,H,W) 14 final_idx(B,H,W) 15 out_img(B,H,W,3)
+    if (check_raster_desc(d)) return 1;
+    Ctx *vc = get_ctx(stream, kViewsSlot);
+    if (!vc) return 1;
+    std::lock_guard<std::mutex> lk(vc->mu);
+    const size_t n = d.num_points, px = (size_t)d.img_w * d.img_h;
+    for (unsigned b = 0; b < B; ++b) {
+        void *vb[16] = {buf[0], buf[1], buf[2], (float *)buf[3] + 16 * (size_t)b, buf[4], buf[5],
+                        buf[6],
+                        (float *)buf[7] + b * n * 6, (float *)buf[8] + b * n * 2,
+                        (float *)buf[9] + b * n, (int *)buf[10] + b * n,
+                        (float *)buf[11] + b * n * 3, (float *)buf[12] + b * n,
+                        (float *)buf[13] + b * px, (int *)buf[14] + b * px,
+                        (float *)buf[15] + b * px * 3};
+        unsigned long long tok = 0;
+        if (render_fwd_impl(stream, vb, d, &tok, b % g_view_slots)) return 1;
+        if (tokens) tokens[b] = tok;
+    }
+    return 0;
+}
+
+static int render_views_bwd_impl(cudaStream_t stream, void **buf, const Descriptor &d, unsigned B,
+                                 const unsigned long long *tokens) {
+    // in : 0 means3d 1 scales 2 quats 3 viewmats 4 colors 5 opacities 6 background 7 cov3ds 8 xys
+    //      9 depths 10 radii 11 conics 12 compensation 13 final_Ts 14 final_idx (all per view, as
+    //      render_views_fwd wrote them) 15 v_out_img(B,H,W,3) 16 v_out_img_alpha(B,H,W) or NULL
+    // out: 17 v_mean3d 18 v_scale 19 v_quat 20 v_colors 21 v_opacity  (sums over the B views)
+    if (check_raster_desc(d)) return 1;
+    const size_t n = d.num_points, px = (size_t)d.img_w * d.img_h;
+    if (n == 0) return 0;
+    Ctx *vc = get_ctx(stream, kViewsSlot);
+    if (!vc) return 1;
+    std::lock_guard<std::mutex> lk(vc->mu);
+    JSB_CUDA_OK(cudaMemsetAsync(buf[20], 0, n * 3 * 4, stream));
+    JSB_CUDA_OK(cudaMemsetAsync(buf[21], 0, n * 4, stream));
+    if (B == 0) {
+        JSB_CUDA_OK(cudaMemsetAsync(buf[17], 0, n * 3 * 4, stream));
+        JSB_CUDA_OK(cudaMemsetAsync(buf[18], 0, n * 3 * 4, stream));
+        JSB_CUDA_OK(cudaMemsetAsync(buf[19], 0, n * 4 * 4, stream));
+        return 0;
+    }
+    // scratch, every array 16-byte aligned (m = n rounded up to a multiple of 4):
+    // [v_xy 2m][v_conic 3m][v_cov2d 3m][v_cov3d 6m][staged v_mean3d 3m | v_scale 3m | v_quat 4m]
+    const size_t m = (n + 3) & ~(size_t)3;
+    if (vc->ensure(vc->views_scratch, m * 24 * sizeof(float))) return 1;
+    float *sc = (float *)vc->views_scratch.p;
+    float *s_xy = sc, *s_conic = sc + 2 * m, *s_cov2d = sc + 5 * m, *s_cov3d = sc + 8 * m,
+          *s_stage = sc + 14 * m;
+    for (unsigned i = 0; i < B; ++i) {
+        const unsigned b = B - 1 - i;
+        const bool first = (i == 0);
+        void *vb[26] = {buf[0], buf[1], buf[2], (float *)buf[3] + 16 * (size_t)b, buf[4], buf[5],
+                        buf[6],
+                        (float *)buf[7] + b * n * 6, (float *)buf[8] + b * n * 2,
+                        (float *)buf[9] + b * n, (int *)buf[10] + b * n,
+                        (float *)buf[11] + b * n * 3, (float *)buf[12] + b * n,
+                        (float *)buf[13] + b * px, (int *)buf[14] + b * px,
+                        (float *)buf[15] + b * px * 3,
+                        buf[16] ? (void *)((float *)buf[16] + b * px) : nullptr,
+                        first ? buf[17] : (void *)s_stage,
+                        first ? buf[18] : (void *)(s_stage + 3 * m),
+                        first ? buf[19] : (void *)(s_stage + 6 * m),
+                        buf[20], buf[21], s_xy, s_conic, s_cov2d, s_cov3d};
+        if (render_bwd_impl(stream, vb, d, tokens ? tokens[b] : 0, b % g_view_slots,
+                            /*keep_appearance=*/true))
+            return 1;
+        if (!first && launch_accumulate_param_grads(stream, n, s_stage, s_stage + 3 * m,
+                                                    s_stage + 6 * m, (float *)buf[17],
+                                                    (float *)buf[18], (float *)buf[19]))
+            return 1;
+    }
+    return 0;
+}
+
 template <typename F>
-static void guarded(const char *name, cudaStream_t stream, void **buffers, const char *opaque,
-                    size_t len, F body) {
+static int guarded(const char *name, cudaStream_t stream, void **buffers, const char *opaque,
+                   size_t len, F body) {
     try {
         const Descriptor *d = unpack(opaque, len);
-        if (!d) return;
-        if (!buffers) { set_error("%s: null buffer list", name); return; }
+        if (!d) return 1;
+        if (!buffers) { set_error("%s: null buffer list", name); return 1; }
         Descriptor local;
         memcpy(&local, d, sizeof local);  // opaque may be unaligned
-        body(stream, buffers, local);
+        return body(stream, buffers, local);
     } catch (const std::exception &e) {
         set_error("%s: %s", name, e.what());
     } catch (...) {
         set_error("%s: unknown exception", name);
     }
+    return 1;
+}
+
+// XLA's API_VERSION_STATUS_RETURNING custom calls receive an XlaCustomCallStatus*; a failure is
+// reported through XlaCustomCallStatusSetFailure (xla/service/custom_call_status.h), which lives
+// in the host process (jaxlib), not in this library: resolved at the time of the failure.
+static void report_status(void *status, int rc) {
+    if (rc == 0 || status == nullptr) return;
+    using SetFailure = void (*)(void *, const char *, size_t);
+    SetFailure fn = reinterpret_cast<SetFailure>(dlsym(RTLD_DEFAULT, "XlaCustomCallStatusSetFailure"));
+    if (!fn) return;  // the sticky error text (jsb200_last_error) and stderr still carry it
+    const std::string msg = t_has_error ? t_error : std::string("jaxsplat_b200: custom call failed");
+    fn(status, msg.c_str(), msg.size());
 }
 
 }  // namespace jsb
@@ -777,6 +896,42 @@ void jsb200_rasterize_fwd(jsb200_stream_t stream, void **buffers, const char *op
 void jsb200_rasterize_bwd(jsb200_stream_t stream, void **buffers, const char *opaque, size_t len) {
     jsb::guarded("rasterize_bwd", (cudaStream_t)stream, buffers, opaque, len,
                  jsb::rasterize_bwd_impl);
+}
+
+void jsb200_project_fwd_status(jsb200_stream_t stream, void **buffers, const char *opaque,
+                               size_t len, jsb200_xla_status_t *status) {
+    jsb::report_status(status, jsb::guarded("project_fwd", (cudaStream_t)stream, buffers, opaque,
+                                            len, jsb::project_fwd_impl));
+}
+void jsb200_project_bwd_status(jsb200_stream_t stream, void **buffers, const char *opaque,
+                               size_t len, jsb200_xla_status_t *status) {
+    jsb::report_status(status, jsb::guarded("project_bwd", (cudaStream_t)stream, buffers, opaque,
+                                            len, jsb::project_bwd_impl));
+}
+void jsb200_rasterize_fwd_status(jsb200_stream_t stream, void **buffers, const char *opaque,
+                                 size_t len, jsb200_xla_status_t *status) {
+    jsb::report_status(status, jsb::guarded("rasterize_fwd", (cudaStream_t)stream, buffers, opaque,
+                                            len, jsb::rasterize_fwd_impl));
+}
+void jsb200_rasterize_bwd_status(jsb200_stream_t stream, void **buffers, const char *opaque,
+                                 size_t len, jsb200_xla_status_t *status) {
+    jsb::report_status(status, jsb::guarded("rasterize_bwd", (cudaStream_t)stream, buffers, opaque,
+                                            len, jsb::rasterize_bwd_impl));
+}
+
+int jsb200_render_views_fwd(jsb200_stream_t stream, void **buffers, const char *opaque, size_t len,
+                            unsigned num_views, unsigned long long *tokens_out) {
+    return jsb::guarded("render_views_fwd", (cudaStream_t)stream, buffers, opaque, len,
+                        [&](cudaStream_t s, void **b, const jsb::Descriptor &d) {
+                            return jsb::render_views_fwd_impl(s, b, d, num_views, tokens_out);
+                        });
+}
+int jsb200_render_views_bwd(jsb200_stream_t stream, void **buffers, const char *opaque, size_t len,
+                            unsigned num_views, const unsigned long long *tokens) {
+    return jsb::guarded("render_views_bwd", (cudaStream_t)stream, buffers, opaque, len,
+                        [&](cudaStream_t s, void **b, const jsb::Descriptor &d) {
+                            return jsb::render_views_bwd_impl(s, b, d, num_views, tokens);
+                        });
 }
 
 int jsb200_render_fwd(jsb200_stream_t stream, void **buffers, const char *opaque, size_t len,
@@ -917,6 +1072,11 @@ int jsb200_set_option(const char *key, int value) {
     if (!strcmp(key, "bwd2px")) { jsb::g_bwd_one_pixel = (value == 0); return 0; }
     if (!strcmp(key, "rowcol")) { jsb::g_disable_rowcol = (value == 0); return 0; }
     if (!strcmp(key, "timing")) { jsb::g_timing = (value != 0); return 0; }
+    if (!strcmp(key, "view_slots")) {
+        if (value < 1 || value > 4096) { jsb::set_error("set_option: view_slots must be 1..4096"); return 1; }
+        jsb::g_view_slots = (unsigned)value;
+        return 0;
+    }
     jsb::set_error("set_option: unknown key '%s'", key);
     return 1;
 }
@@ -946,15 +1106,30 @@ int jsb200_get_stage_times(jsb200_stream_t stream_, double *ms_out9, unsigned lo
                            int reset) {
     try {
         cudaStream_t stream = (cudaStream_t)stream_;
-        jsb::Ctx *c = jsb::get_ctx(stream);
-        if (!c) return 1;
-        std::lock_guard<std::mutex> lk(c->mu);
+        if (!jsb::get_ctx(stream)) return 1;
+        int dev = 0;
+        JSB_CUDA_OK(cudaGetDevice(&dev));
         JSB_CUDA_OK(cudaStreamSynchronize(stream));
-        c->times.drain();
         for (int i = 0; i < jsb::ST_COUNT; ++i) {
-            if (ms_out9) ms_out9[i] = c->times.ms[i];
-            if (calls_out9) calls_out9[i] = c->times.calls[i];
-            if (reset) { c->times.ms[i] = 0; c->times.calls[i] = 0; }
+            if (ms_out9) ms_out9[i] = 0;
+            if (calls_out9) calls_out9[i] = 0;
+        }
+        // every workspace slot of this (device, stream): batched-camera calls spread their views
+        std::vector<jsb::Ctx *> slots;
+        {
+            std::lock_guard<std::mutex> lk0(jsb::g_ctx_mu);
+            for (auto &kv : jsb::g_ctx)
+                if (std::get<0>(kv.first) == dev && std::get<1>(kv.first) == stream)
+                    slots.push_back(kv.second.get());
+        }
+        for (jsb::Ctx *c : slots) {
+            std::lock_guard<std::mutex> lk(c->mu);
+            c->times.drain();
+            for (int i = 0; i < jsb::ST_COUNT; ++i) {
+                if (ms_out9) ms_out9[i] += c->times.ms[i];
+                if (calls_out9) calls_out9[i] += c->times.calls[i];
+                if (reset) { c->times.ms[i] = 0; c->times.calls[i] = 0; }
+            }
         }
         return 0;
     } catch (...) {

@@ -47,6 +47,11 @@ int launch_project_bwd(cudaStream_t stream, const ProjectBwdParams &p, const flo
                        const float *v_depth, const float *v_conic, float *v_mean3d,
                        float *v_scale, float *v_quat, float *v_cov2d, float *v_cov3d);
 
+// batched cameras: v_mean3d / v_scale / v_quat += one view's staged arrays (3n / 3n / 4n floats)
+int launch_accumulate_param_grads(cudaStream_t stream, size_t n, const float *s_mean,
+                                  const float *s_scale, const float *s_quat, float *v_mean3d,
+                                  float *v_scale, float *v_quat);
+
 // ---- binning (binning.cu) -------------------------------------------------------------------
 // Per-Gaussian record gathered by the rasterisers: 3 x float4 = 48 B, one 16-B aligned line.
 //   q0 = {x, y, opacity, conic.x}   q1 = {conic.y, conic.z, r, g}   q2 = {b, 0, 0, 0}

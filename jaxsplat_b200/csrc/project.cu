@@ -444,7 +444,34 @@ project_bwd_kernel(const ProjectBwdParams p, const float *__restrict__ means3d,
     slab_store<6, PT>(s_vcov3d, v_cov3d, base * 6, n * 6);
 }
 
+// batched cameras: adds one view's staged v_mean3d (3n) / v_scale (3n) / v_quat (4n) to the sums
+__global__ void __launch_bounds__(256)
+accumulate_param_grads_kernel(const float *__restrict__ s_mean, const float *__restrict__ s_scale,
+                              const float *__restrict__ s_quat, float *__restrict__ v_mean3d,
+                              float *__restrict__ v_scale, float *__restrict__ v_quat, size_t n) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const size_t n3 = 3 * n, n6 = 6 * n, n10 = 10 * n;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n10; i += stride) {
+        if (i < n3) v_mean3d[i] += __ldg(s_mean + i);
+        else if (i < n6) v_scale[i - n3] += __ldg(s_scale + (i - n3));
+        else v_quat[i - n6] += __ldg(s_quat + (i - n6));
+    }
+}
+
 }  // namespace
+
+int launch_accumulate_param_grads(cudaStream_t stream, size_t n, const float *s_mean,
+                                  const float *s_scale, const float *s_quat, float *v_mean3d,
+                                  float *v_scale, float *v_quat) {
+    if (n == 0) return 0;
+    const size_t want = (10 * n + 255) / 256;
+    const unsigned blocks = (unsigned)(want < 148u * 16u ? want : 148u * 16u);
+    accumulate_param_grads_kernel<<<blocks, 256, 0, stream>>>(s_mean, s_scale, s_quat, v_mean3d,
+                                                              v_scale, v_quat, n);
+    JSB_CUDA_OK(cudaGetLastError());
+    note_launch();
+    return 0;
+}
 
 int launch_project_fwd(cudaStream_t stream, const ProjectFwdParams &p, const float *means3d,
                        const float *scales, const float *quats, const float *viewmat,
