@@ -50,6 +50,8 @@ void note_launch(int n) { g_stats[6].fetch_add((unsigned long long)n); }
 
 extern bool g_disable_cull;
 extern bool g_bwd_one_pixel;
+extern bool g_bwd_scalar;
+extern bool g_fwd_scalar;
 extern bool g_fwd_one_pixel;
 static bool g_disable_cache = false;
 static bool g_disable_rowcol = false;
@@ -1070,6 +1072,8 @@ int jsb200_set_option(const char *key, int value) {
     if (!strcmp(key, "cache")) { jsb::g_disable_cache = (value == 0); return 0; }
     if (!strcmp(key, "fwd2px")) { jsb::g_fwd_one_pixel = (value == 0); return 0; }
     if (!strcmp(key, "bwd2px")) { jsb::g_bwd_one_pixel = (value == 0); return 0; }
+    if (!strcmp(key, "bwdpk")) { jsb::g_bwd_scalar = (value == 0); return 0; }
+    if (!strcmp(key, "fwdpk")) { jsb::g_fwd_scalar = (value == 0); return 0; }
     if (!strcmp(key, "rowcol")) { jsb::g_disable_rowcol = (value == 0); return 0; }
     if (!strcmp(key, "timing")) { jsb::g_timing = (value != 0); return 0; }
     if (!strcmp(key, "view_slots")) {

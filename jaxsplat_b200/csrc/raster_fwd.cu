@@ -148,7 +148,7 @@ raster_fwd16_kernel(const RasterParams p, const unsigned *__restrict__ ids_sorte
 // stay bit-identical.
 constexpr int RF2 = 128;
 
-template <bool CULL>
+template <bool CULL, bool PACKED>
 __global__ void __launch_bounds__(RF2, 8)
 raster_fwd16x2_kernel(const RasterParams p, const unsigned *__restrict__ ids_sorted,
                       const int2 *__restrict__ tile_bins, const SplatRecord *__restrict__ records,
@@ -227,11 +227,32 @@ raster_fwd16x2_kernel(const RasterParams p, const unsigned *__restrict__ ids_sor
                 const float4 a = sA[buf][t];
                 const float4 bq = sB[buf][t];
                 const float dx = fsub(a.x, px);
-                const float dy0 = fsub(a.y, py0), dy1 = fsub(a.y, py1);
-                const float sg0 = conic_sigma(a.w, bq.x, bq.y, dx, dy0);
-                const float sg1 = conic_sigma(a.w, bq.x, bq.y, dx, dy1);
-                const float al0 = fminf(fmul(a.z, ex2_approx(fmul(sg0, kNegLog2e))), 0.999f);
-                const float al1 = fminf(fmul(a.z, ex2_approx(fmul(sg1, kNegLog2e))), 0.999f);
+                float sg0, sg1, al0, al1;
+                if (PACKED) {
+                    // conic_sigma (common.cuh) for both pixels at once with FMUL2 / FFMA2 / FADD2
+                    // (one issue slot, two FP32 lanes, each rounding like the scalar form), the
+                    // per-Gaussian operands as scalar broadcasts: same operation order per pixel,
+                    // so the outputs stay bit-identical to the scalar path
+                    const float2 dy2 = __fadd2_rn(make_float2(a.y, a.y), make_float2(-py0, -py1));
+                    const float ca = fmul(a.w, dx);                                   // cx dx
+                    const float ce = fmul(bq.x, dx);                                  // cy dx
+                    const float2 b2 = __fmul2_rn(make_float2(bq.y, bq.y), dy2);       // cz dy
+                    const float2 c2 = __fmul2_rn(dy2, b2);
+                    float2 s2 = __ffma2_rn(make_float2(dx, dx), make_float2(ca, ca), c2);
+                    s2 = __fmul2_rn(s2, make_float2(0.5f, 0.5f));
+                    const float2 sg2 = __ffma2_rn(make_float2(ce, ce), dy2, s2);
+                    const float2 x2 = __fmul2_rn(sg2, make_float2(kNegLog2e, kNegLog2e));
+                    const float2 ar2 = __fmul2_rn(make_float2(a.z, a.z),
+                                                  make_float2(ex2_approx(x2.x), ex2_approx(x2.y)));
+                    sg0 = sg2.x; sg1 = sg2.y;
+                    al0 = fminf(ar2.x, 0.999f); al1 = fminf(ar2.y, 0.999f);
+                } else {
+                    const float dy0 = fsub(a.y, py0), dy1 = fsub(a.y, py1);
+                    sg0 = conic_sigma(a.w, bq.x, bq.y, dx, dy0);
+                    sg1 = conic_sigma(a.w, bq.x, bq.y, dx, dy1);
+                    al0 = fminf(fmul(a.z, ex2_approx(fmul(sg0, kNegLog2e))), 0.999f);
+                    al1 = fminf(fmul(a.z, ex2_approx(fmul(sg1, kNegLog2e))), 0.999f);
+                }
                 const bool ok0 = !done0 && !(sg0 < 0.f) && !(al0 < kAlphaMin);
                 const bool ok1 = !done1 && !(sg1 < 0.f) && !(al1 < kAlphaMin);
                 if (ok0 || ok1) {
@@ -370,6 +391,7 @@ __global__ void fill_background_kernel(const float *__restrict__ background, siz
 }  // namespace
 
 bool g_disable_cull = false;  // test hook (capi: jsb200_set_option)
+bool g_fwd_scalar = false;  // option "fwdpk" = 0: scalar FP32 math in the two-pixel kernel
 bool g_fwd_one_pixel = false;  // option "fwd2px" = 0: the one-pixel-per-thread kernel
 
 int launch_raster_fwd(cudaStream_t stream, const RasterParams &p, const unsigned *ids_sorted,
@@ -378,14 +400,11 @@ int launch_raster_fwd(cudaStream_t stream, const RasterParams &p, const unsigned
     const unsigned tiles = p.tiles_x * (p.band_y1 - p.band_y0);
     if (tiles == 0) return 0;
     if (p.block_width == 16 && !g_fwd_one_pixel) {
-        if (g_disable_cull)
-            raster_fwd16x2_kernel<false><<<tiles, RF2, 0, stream>>>(p, ids_sorted, tile_bins, records,
-                                                                    background, final_Ts, final_idx,
-                                                                    out_img);
-        else
-            raster_fwd16x2_kernel<true><<<tiles, RF2, 0, stream>>>(p, ids_sorted, tile_bins, records,
-                                                                   background, final_Ts, final_idx,
-                                                                   out_img);
+#define JSB_FWD2(C, P) raster_fwd16x2_kernel<C, P><<<tiles, RF2, 0, stream>>>( \
+        p, ids_sorted, tile_bins, records, background, final_Ts, final_idx, out_img)
+        if (g_disable_cull) { if (g_fwd_scalar) JSB_FWD2(false, false); else JSB_FWD2(false, true); }
+        else { if (g_fwd_scalar) JSB_FWD2(true, false); else JSB_FWD2(true, true); }
+#undef JSB_FWD2
     } else if (p.block_width == 16) {
         if (g_disable_cull)
             raster_fwd16_kernel<false><<<tiles, RB, 0, stream>>>(p, ids_sorted, tile_bins, records,
