@@ -537,6 +537,26 @@ raster_bwd16x2p_kernel(const RasterParams p, const unsigned *__restrict__ ids_so
     issue(0, 1, load_id(0, 1));
     unsigned gn0 = load_id(1, 0), gn1 = load_id(1, 1);
 
+    // The cross-lane reduction of a visit is deferred into the NEXT visit: its shared-memory reads,
+    // adds, shuffle and RED have nothing to do with that visit's sigma / alpha arithmetic, so in
+    // one straight-line block the scheduler overlaps the two latency chains (the reduction tail
+    // held 27 % of the kernel's stall samples when it ran at the end of its own visit).
+    bool pend = false;       // `red` holds the partials of a visit that is not reduced yet
+    unsigned pend_id = 0;    // its Gaussian
+    const float4 *red_row = reinterpret_cast<const float4 *>(
+        red + min(lane >> 1, NV - 1) * RED_STRIDE + (lane & 1) * 16);
+    auto reduce_rows = [&]() -> float {
+        const float4 p0 = red_row[0], p1 = red_row[1], p2 = red_row[2], p3 = red_row[3];
+        float2 u0 = __fadd2_rn(f2(p0.x, p0.y), f2(p0.z, p0.w));
+        float2 u1 = __fadd2_rn(f2(p1.x, p1.y), f2(p1.z, p1.w));
+        float2 u2 = __fadd2_rn(f2(p2.x, p2.y), f2(p2.z, p2.w));
+        float2 u3 = __fadd2_rn(f2(p3.x, p3.y), f2(p3.z, p3.w));
+        u0 = __fadd2_rn(u0, u1);
+        u2 = __fadd2_rn(u2, u3);
+        u0 = __fadd2_rn(u0, u2);
+        return u0.x + u0.y;
+    };
+
     for (int b = 0; b < num_batches; ++b) {
         cp_async_wait_all();
         __syncthreads();  // batch b landed; every warp is done with batch b-1
@@ -573,6 +593,7 @@ raster_bwd16x2p_kernel(const RasterParams p, const unsigned *__restrict__ ids_so
                 bits &= bits - 1;
                 const float4 a = sA[t];    // {x, y, opacity, cx}
                 const float4 bq = sB[t];   // {cy, cz, r, g}
+                float total = reduce_rows();  // previous visit's partials (stale rows if !pend)
                 // conic_sigma (common.cuh) lane by lane, in the reference's operation order
                 const float dx = fsub(a.x, px);
                 const float2 dy2 = __fadd2_rn(bc(a.y), npy2);
@@ -590,6 +611,9 @@ raster_bwd16x2p_kernel(const RasterParams p, const unsigned *__restrict__ ids_so
                 const int sidx = batch_end - t;
                 const bool ok0 = in0 && (sidx <= bf0) && !(sg2.x < 0.f) && !(al0 < kAlphaMin);
                 const bool ok1 = in1 && (sidx <= bf1) && !(sg2.y < 0.f) && !(al1 < kAlphaMin);
+                total += __shfl_xor_sync(0xffffffffu, total, 1);
+                if (writer && pend) atomicAdd(out_base + pend_id * (unsigned)out_stride, total);
+                pend = false;
                 if (!__any_sync(0xffffffffu, ok0 || ok1)) continue;
 
                 // invalid pixels: alpha = opacity*vis = 0 and ra = 1 make every partial exactly 0
@@ -644,23 +668,15 @@ raster_bwd16x2p_kernel(const RasterParams p, const unsigned *__restrict__ ids_so
 #pragma unroll
                 for (int r = 0; r < NV; ++r) red[r * RED_STRIDE + lane] = v[r];
                 __syncwarp();
-                float total = 0.f;
-                if (lane < 2 * NV) {
-                    const float4 *row = reinterpret_cast<const float4 *>(red + (lane >> 1) * RED_STRIDE + (lane & 1) * 16);
-                    const float4 p0 = row[0], p1 = row[1], p2 = row[2], p3 = row[3];
-                    float2 u0 = __fadd2_rn(f2(p0.x, p0.y), f2(p0.z, p0.w));
-                    float2 u1 = __fadd2_rn(f2(p1.x, p1.y), f2(p1.z, p1.w));
-                    float2 u2 = __fadd2_rn(f2(p2.x, p2.y), f2(p2.z, p2.w));
-                    float2 u3 = __fadd2_rn(f2(p3.x, p3.y), f2(p3.z, p3.w));
-                    u0 = __fadd2_rn(u0, u1);
-                    u2 = __fadd2_rn(u2, u3);
-                    u0 = __fadd2_rn(u0, u2);
-                    total = u0.x + u0.y;
-                }
-                total += __shfl_xor_sync(0xffffffffu, total, 1);
-                if (writer) atomicAdd(out_base + sId[t] * (unsigned)out_stride, total);
+                pend = true;
+                pend_id = sId[t];
             }
         }
+    }
+    if (pend) {  // warp-uniform: the last visit of this warp
+        float total = reduce_rows();
+        total += __shfl_xor_sync(0xffffffffu, total, 1);
+        if (writer) atomicAdd(out_base + pend_id * (unsigned)out_stride, total);
     }
 }
 
