@@ -216,9 +216,6 @@ def main():
     for _ in range(max(args.warmup, 3)):
         step(sc.viewmat, target)
     barrier()
-    if args.impl == "ours":
-        _lib.set_option("timing", 1)
-        _lib.stage_times(torch.cuda.current_stream().cuda_stream, reset=True)
     launches0 = _lib.stats()["kernel_launches"] if args.impl == "ours" else 0
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -234,9 +231,18 @@ def main():
     stages = None
     launches = 0
     if args.impl == "ours":
+        launches = _lib.stats()["kernel_launches"] - launches0
+        # per-stage device times: a separate pass of the same step with the library's stage events
+        # switched on, OUTSIDE the timed region (two event records per stage would otherwise sit
+        # between the kernels of the steps being timed)
+        stage_steps = min(args.steps, 50)
+        _lib.set_option("timing", 1)
+        _lib.stage_times(torch.cuda.current_stream().cuda_stream, reset=True)
+        for _ in range(stage_steps):
+            step(sc.viewmat, target)
+        barrier()
         stages = _lib.stage_times(torch.cuda.current_stream().cuda_stream, reset=True)
         _lib.set_option("timing", 0)
-        launches = _lib.stats()["kernel_launches"] - launches0
     t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
     if use_dist:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -351,7 +357,7 @@ def main():
                 continue
             ms = v["ms"] / v["calls"]
             b = algorithmic_bytes(k, N, I, P, T, rows, (W + 15) // 16)
-            per_stage[k] = {"ms_per_launch": ms, "launches_per_step": v["calls"] / args.steps,
+            per_stage[k] = {"ms_per_launch": ms, "launches_per_step": v["calls"] / stage_steps,
                             "algorithmic_bytes": b, "gbs": b / (ms * 1e-3) / 1e9,
                             "hbm_frac": b / (ms * 1e-3) / 1e9 / peak}
         dom = max(per_stage, key=lambda k: per_stage[k]["ms_per_launch"] * per_stage[k]["launches_per_step"])
@@ -366,9 +372,10 @@ def main():
                            "peak_source": which_peak,
                            "note": "achieved = compulsory HBM bytes of the dominant stage / its "
                                    "device time; the rasterisers are SM-issue bound, not HBM bound "
-                                   "(no dense contraction, no tensor cores; ncu: 75-78 % issue-slot "
+                                   "(no dense contraction, no tensor cores; ncu: 65-73 % issue-slot "
                                    "utilisation, 2 % DRAM throughput): see 'issue', 'stages' and "
-                                   "DESIGN.md section 5"}
+                                   "DESIGN.md section 5; stage times come from a separate pass of "
+                                   "the same step with the library's stage events on"}
         # issue-slot view of the rasterisers: (tile, Gaussian, pixel) pairs the REFERENCE's kernels
         # evaluate for this frame (I * 256) per second of ours, against the issue-slot roof of
         # evaluating every one of them (15 slots each); > 1x the roof = pairs never evaluated

@@ -203,6 +203,13 @@ raster_bwd16_kernel(const RasterParams p, const unsigned *__restrict__ ids_sorte
 // once per 32.  ABS = false (fused render: nothing consumes v_xy_abs) drops two of the eleven rows.
 // Row order of the reduction: rgb(3) conic(3) xy(2) opacity(1) xy_abs(2).
 constexpr int RB2 = 128;
+// tuning knobs of the packed kernel (A/B builds: make EXTRA=-DJSB_BWD_CTAS=5 ...)
+#ifndef JSB_BWD_CTAS
+#define JSB_BWD_CTAS 6   // resident CTAs per SM the register allocation is bounded for
+#endif
+#ifndef JSB_BWD_EPT
+#define JSB_BWD_EPT 2    // staged entries per thread and batch (batch = 128 * EPT entries)
+#endif
 
 // tfc = T_final * (v_out_alpha - <v_out, background>): the two background/alpha terms of the
 // reference's v_alpha (backward.cu:283-291) are both proportional to T_final * ra, so they fold
@@ -440,7 +447,7 @@ __device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b
 __device__ __forceinline__ float2 bc(float a) { return make_float2(a, a); }
 
 template <bool CULL, bool ABS>
-__global__ void __launch_bounds__(RB2, 6)
+__global__ void __launch_bounds__(RB2, JSB_BWD_CTAS)
 raster_bwd16x2p_kernel(const RasterParams p, const unsigned *__restrict__ ids_sorted,
                        const int2 *__restrict__ tile_bins, const SplatRecord *__restrict__ records,
                        const float *__restrict__ background, const float *__restrict__ final_Ts,
@@ -449,7 +456,8 @@ raster_bwd16x2p_kernel(const RasterParams p, const unsigned *__restrict__ ids_so
                        float *__restrict__ v_xy_abs, float *__restrict__ v_conic,
                        float *__restrict__ v_colors, float *__restrict__ v_opacity) {
     constexpr int NV = ABS ? 11 : 9;
-    constexpr int BATCH = 256;  // two staged entries per thread
+    constexpr int EPT = JSB_BWD_EPT;      // staged entries per thread and batch
+    constexpr int BATCH = RB2 * EPT;
     __shared__ float4 sA2[2][BATCH];  // double-buffered batches (cp.async staging)
     __shared__ float4 sB2[2][BATCH];
     __shared__ float sC2[2][BATCH];
@@ -533,9 +541,11 @@ raster_bwd16x2p_kernel(const RasterParams p, const unsigned *__restrict__ ids_so
             sId2[bb & 1][t] = g;
         }
     };
-    issue(0, 0, load_id(0, 0));
-    issue(0, 1, load_id(0, 1));
-    unsigned gn0 = load_id(1, 0), gn1 = load_id(1, 1);
+    unsigned gn[EPT];
+#pragma unroll
+    for (int h = 0; h < EPT; ++h) issue(0, h, load_id(0, h));
+#pragma unroll
+    for (int h = 0; h < EPT; ++h) gn[h] = load_id(1, h);
 
     // The cross-lane reduction of a visit is deferred into the NEXT visit: its shared-memory reads,
     // adds, shuffle and RED have nothing to do with that visit's sigma / alpha arithmetic, so in
@@ -566,11 +576,14 @@ raster_bwd16x2p_kernel(const RasterParams p, const unsigned *__restrict__ ids_so
         const float4 *sB = sB2[buf];
         const float *sC = sC2[buf];
         const unsigned *sId = sId2[buf];
-        if (b + 1 < num_batches) { issue(b + 1, 0, gn0); issue(b + 1, 1, gn1); }
-        gn0 = load_id(b + 2, 0);
-        gn1 = load_id(b + 2, 1);
+        if (b + 1 < num_batches) {
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
+            for (int h = 0; h < EPT; ++h) issue(b + 1, h, gn[h]);
+        }
+#pragma unroll
+        for (int h = 0; h < EPT; ++h) gn[h] = load_id(b + 2, h);
+#pragma unroll
+        for (int h = 0; h < EPT; ++h) {
             const int t = tid + h * RB2;
             unsigned mask = 0;
             if (batch_end - t >= range.x) {

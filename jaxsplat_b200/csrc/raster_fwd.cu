@@ -147,14 +147,22 @@ raster_fwd16_kernel(const RasterParams p, const unsigned *__restrict__ ids_sorte
 // of a visit); every per-pixel operation keeps the reference's rounding order, so the outputs
 // stay bit-identical.
 constexpr int RF2 = 128;
+// tuning knobs (A/B builds: make EXTRA=-DJSB_FWD_CTAS=6 ...)
+#ifndef JSB_FWD_CTAS
+#define JSB_FWD_CTAS 8   // resident CTAs per SM the register allocation is bounded for
+#endif
+#ifndef JSB_FWD_EPT
+#define JSB_FWD_EPT 1    // staged entries per thread and batch (batch = 128 * EPT entries)
+#endif
 
 template <bool CULL, bool PACKED>
-__global__ void __launch_bounds__(RF2, 8)
+__global__ void __launch_bounds__(RF2, JSB_FWD_CTAS)
 raster_fwd16x2_kernel(const RasterParams p, const unsigned *__restrict__ ids_sorted,
                       const int2 *__restrict__ tile_bins, const SplatRecord *__restrict__ records,
                       const float *__restrict__ background, float *__restrict__ final_Ts,
                       int *__restrict__ final_idx, float *__restrict__ out_img) {
-    constexpr int BATCH = 256;  // two staged entries per thread
+    constexpr int EPT = JSB_FWD_EPT;      // staged entries per thread and batch
+    constexpr int BATCH = RF2 * EPT;
     __shared__ float4 sA[2][BATCH];
     __shared__ float4 sB[2][BATCH];
     __shared__ float sC[2][BATCH];
@@ -191,19 +199,27 @@ raster_fwd16x2_kernel(const RasterParams p, const unsigned *__restrict__ ids_sor
             cp_async4(&sC[b & 1][t], &r->q2);
         }
     };
-    if (num_batches > 0) { issue(0, 0, load_id(0, 0)); issue(0, 1, load_id(0, 1)); }
-    unsigned gn0 = load_id(1, 0), gn1 = load_id(1, 1);
+    unsigned gn[EPT];
+    if (num_batches > 0) {
+#pragma unroll
+        for (int h = 0; h < EPT; ++h) issue(0, h, load_id(0, h));
+    }
+#pragma unroll
+    for (int h = 0; h < EPT; ++h) gn[h] = load_id(1, h);
 
     for (int b = 0; b < num_batches; ++b) {
         cp_async_wait_all();
         if (__syncthreads_count(done0 && done1) >= RF2) break;
         const int batch_start = range.x + BATCH * b;
         const int buf = b & 1;
-        if (b + 1 < num_batches) { issue(b + 1, 0, gn0); issue(b + 1, 1, gn1); }
-        gn0 = load_id(b + 2, 0);
-        gn1 = load_id(b + 2, 1);
+        if (b + 1 < num_batches) {
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
+            for (int h = 0; h < EPT; ++h) issue(b + 1, h, gn[h]);
+        }
+#pragma unroll
+        for (int h = 0; h < EPT; ++h) gn[h] = load_id(b + 2, h);
+#pragma unroll
+        for (int h = 0; h < EPT; ++h) {
             const int t = tid + h * RF2;
             unsigned mask = 0;
             if (batch_start + t < range.y) {
