@@ -179,11 +179,23 @@ def main():
     flat_n = sum(p.numel() for p in sc.params())
     if use_dist and os.environ.get("JSB_BENCH_NCCL") == "1":
         reducer = None
-        flat_g = torch.zeros(flat_n, dtype=torch.float32, device=dev)
+        flat_raw = torch.zeros(flat_n + 5 * N, dtype=torch.float32, device=dev)
+        flat_g, flat_scratch = flat_raw[:flat_n], flat_raw[flat_n:]
     else:
-        reducer = SwitchReducedBuffer(flat_n, dev) if use_dist else None
+        reducer = SwitchReducedBuffer(flat_n, dev, scratch_numel=5 * N) if use_dist else None
         flat_g = reducer.tensor if reducer is not None else None
+        flat_scratch = reducer.scratch if reducer is not None else None
     params = [p.clone().requires_grad_(True) for p in sc.params()]
+    # the render backward writes the five parameter gradients straight into the flat buffer the
+    # all-reduce sums in place (no packing pass); checked after the first step, torch.cat otherwise
+    sink_views = None
+    if use_dist and args.impl == "ours" and os.environ.get("JSB_BENCH_NOSINK") != "1":
+        sink_views, off = [], 0
+        for q in params:
+            sink_views.append(flat_g[off:off + q.numel()].view(q.shape))
+            off += q.numel()
+        jsb.set_gradient_sink(sink_views + [flat_scratch])
+    sink_ok = [False]
 
     def step(view, tgt):
         for q in params:
@@ -198,9 +210,13 @@ def main():
         loss = torch.dot(flat, flat) / flat.numel()
         img.backward(gradient=diff * (2.0 / diff.numel()))
         if use_dist:
-            # the five parameter gradients packed into the one flat (symmetric) buffer, summed
-            # over the ranks in a single call
-            torch.cat([q.grad.reshape(-1) for q in params], out=flat_g)
+            # the five parameter gradients in the one flat (symmetric) buffer, summed over the
+            # ranks in a single call
+            if not sink_ok[0]:
+                sink_ok[0] = sink_views is not None and all(
+                    q.grad.data_ptr() == v.data_ptr() for q, v in zip(params, sink_views))
+            if not sink_ok[0]:
+                torch.cat([q.grad.reshape(-1) for q in params], out=flat_g)
             if reducer is not None:
                 reducer.all_reduce()
             else:
@@ -324,7 +340,9 @@ def main():
         "config": {"workload": f"{args.config}: {N} Gaussians (benchmark.py distribution, scales<0.1, seed 0), "
                                f"{W}x{H}, block_size 16, fwd+bwd of MSE loss, 1 view/GPU/step",
                    "num_intersects": I, "parallelism": (f"view-parallel dp{world}, gradient all-reduce: "
-                                   f"{reducer.mode if reducer is not None else 'nccl'}") if world > 1 else "single GPU",
+                                   f"{reducer.mode if reducer is not None else 'nccl'}, gradients "
+                                   f"{'written in place into' if sink_ok[0] else 'packed (torch.cat) into'} "
+                                   "the reduced buffer") if world > 1 else "single GPU",
                    "l2": "per-step working set ~0.5 GB (keys/ids ping-pong 0.2 GB, records, images, "
                          "parameters, gradients) exceeds the 126 MB L2; no explicit flush",
                    "timing": "CUDA events around exactly K steps, barrier+synchronize both sides, max over ranks"},

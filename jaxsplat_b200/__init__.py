@@ -11,7 +11,7 @@ fallback path.
 from . import _ops
 from ._project import project
 from ._rasterize import rasterize
-from ._render import render_fused, render_views
+from ._render import render_fused, render_views, set_gradient_sink
 
 _FUSED = True
 
@@ -46,4 +46,5 @@ def render(means3d, scales, quats, colors, opacities, *, viewmat, background, im
                      img_shape=img_shape, block_width=block_size, tile_rows=tile_rows)
 
 
-__all__ = ["render", "render_views", "project", "rasterize", "set_fused_render"]
+__all__ = ["render", "render_views", "project", "rasterize", "set_fused_render",
+           "set_gradient_sink"]

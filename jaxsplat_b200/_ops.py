@@ -193,9 +193,12 @@ def render_fwd(mean3ds, scales, quats, viewmat, colors, opacities, background, *
 def render_bwd(mean3ds, scales, quats, viewmat, colors, opacities, background, cov3ds, xys, depths,
                radii, conics, compensation, final_Ts, final_idx, v_img, v_img_alpha,
                *, token, num_points, img_shape, f, c, glob_scale, clip_thresh, block_width,
-               band=None):
+               band=None, grad_out=None):
     """rasterize_bwd + project_bwd in one native call (jsb200_render_bwd).  Returns
-    (v_mean3d, v_scale, v_quat, v_colors, v_opacity, v_xy, v_conic, v_cov2d, v_cov3d)."""
+    (v_mean3d, v_scale, v_quat, v_colors, v_opacity, v_xy, v_conic, v_cov2d, v_cov3d).
+    grad_out: optional caller-owned buffers for the first five results (see
+    ``jaxsplat_b200.set_gradient_sink``); a sixth tensor of 5*N floats placed right behind
+    v_opacity lets the library clear its four accumulators with one memset."""
     import ctypes
 
     n, dev = num_points, mean3ds.device
@@ -212,13 +215,23 @@ def render_bwd(mean3ds, scales, quats, viewmat, colors, opacities, background, c
            None if (v_img_alpha is None and block_width == 16) else _f32(
                torch.zeros((H, W, 1), dtype=torch.float32, device=dev) if v_img_alpha is None
                else v_img_alpha, (H, W, 1), "v_img_alpha")]
-    # the four atomically accumulated gradients back to back: the library clears them in one go
-    acc = _out((n, 9), torch.float32, dev).reshape(-1)
-    outs = [_out((n, 3), torch.float32, dev), _out((n, 3), torch.float32, dev),
-            _out((n, 4), torch.float32, dev), acc[:3 * n].view(n, 3),
-            acc[3 * n:4 * n].view(n, 1), acc[4 * n:6 * n].view(n, 2),
-            acc[6 * n:9 * n].view(n, 3), _out((n, 3), torch.float32, dev),
-            _out((n, 6), torch.float32, dev)]
+    if grad_out is not None:
+        g = [_f32(t, shape, "grad_out") for t, shape in zip(grad_out[:5], ((n, 3), (n, 3), (n, 4),
+                                                                         (n, 3), (n, 1)))]
+        tail = grad_out[5] if len(grad_out) > 5 else _out((5 * n,), torch.float32, dev)
+        tail = _f32(tail, (5 * n,), "grad_out tail")
+        # fresh view objects: autograd may then adopt them as .grad without a copy
+        outs = [t.view(t.shape) for t in g] + [tail[:2 * n].view(n, 2), tail[2 * n:].view(n, 3),
+                                                _out((n, 3), torch.float32, dev),
+                                                _out((n, 6), torch.float32, dev)]
+    else:
+        # the four atomically accumulated gradients back to back: the library clears them in one go
+        acc = _out((n, 9), torch.float32, dev).reshape(-1)
+        outs = [_out((n, 3), torch.float32, dev), _out((n, 3), torch.float32, dev),
+                _out((n, 4), torch.float32, dev), acc[:3 * n].view(n, 3),
+                acc[3 * n:4 * n].view(n, 1), acc[4 * n:6 * n].view(n, 2),
+                acc[6 * n:9 * n].view(n, 3), _out((n, 3), torch.float32, dev),
+                _out((n, 6), torch.float32, dev)]
     d = _ffi.make_descriptor(n, tuple(img_shape), tuple(f), tuple(c), glob_scale, clip_thresh,
                              block_width)
     if band is not None:

@@ -15,6 +15,23 @@ from . import _ops
 from ._project import ProjectDescriptor
 
 
+_GRAD_SINK = None
+
+
+def set_gradient_sink(buffers) -> None:
+    """Where the fused ``render`` backward writes the five parameter gradients (extension).
+
+    ``buffers`` = [v_means3d (N,3), v_scales (N,3), v_quats (N,4), v_colors (N,3), v_opacities (N,1)]
+    (+ optionally a 5*N-float scratch tensor that directly follows v_opacities in memory), typically
+    views into ONE flat buffer that a data-parallel driver all-reduces in place: the gradients then
+    never get packed or copied -- the same idea as DDP's ``gradient_as_bucket_view``.  autograd
+    adopts the returned views as ``.grad`` when ``.grad`` is None.  ``None`` restores private
+    result buffers.  One render backward per step may use the sink (a second one would overwrite
+    it); multi-view accumulation goes through ``render_views`` or ordinary ``.grad`` accumulation."""
+    global _GRAD_SINK
+    _GRAD_SINK = None if buffers is None else list(buffers)
+
+
 class _Render(torch.autograd.Function):
     @staticmethod
     def forward(ctx, desc: ProjectDescriptor, band, means3d, scales, quats, colors, opacities,
@@ -34,7 +51,7 @@ class _Render(torch.autograd.Function):
         # render() exposes no alpha image: its cotangent is identically zero (None = not read)
         (v_mean3d, v_scale, v_quat, v_colors, v_opacity, *_rest) = _ops.render_bwd(
             *saved, v_img.contiguous(), None, token=ctx.token, band=ctx.band,
-            **ctx.desc.kwargs())
+            grad_out=_GRAD_SINK, **ctx.desc.kwargs())
         return None, None, v_mean3d, v_scale, v_quat, v_colors, v_opacity, None, None
 
 

@@ -54,7 +54,11 @@ class SwitchReducedBuffer:
 
     FLAG_BYTES = 4096
 
-    def __init__(self, numel: int, device, group=None):
+    def __init__(self, numel: int, device, group=None, scratch_numel: int = 0):
+        """``scratch_numel`` floats of per-rank scratch (``self.scratch``) directly follow the
+        reduced floats in memory; they are never meaningfully reduced (see
+        ``jaxsplat_b200.set_gradient_sink``: the render backward keeps its two intermediate
+        cotangents there, so that it clears all four accumulators with one memset)."""
         self.numel = int(numel)
         self.mode = "single"
         self._epoch = 0
@@ -64,23 +68,28 @@ class SwitchReducedBuffer:
             self.mode = dist.get_backend(group)
         self._group = group
         padded = (self.numel + 3) // 4 * 4
+        total = (self.numel + int(scratch_numel) + 3) // 4 * 4   # flags start here (16-byte aligned)
         if distributed and torch.device(device).type == "cuda" and self.mode == "nccl":
             try:
                 import torch.distributed._symmetric_memory as symm_mem
                 g = group if group is not None else dist.group.WORLD
-                raw = symm_mem.empty(padded + self.FLAG_BYTES // 4, dtype=torch.float32, device=device)
+                raw = symm_mem.empty(total + self.FLAG_BYTES // 4, dtype=torch.float32, device=device)
                 hdl = symm_mem.rendezvous(raw, g.group_name)
                 if hdl.multicast_ptr and hdl.world_size <= 16:
                     raw.zero_()
                     hdl.barrier(channel=0)
                     self._raw, self._hdl = raw, hdl
                     self._padded = padded
+                    self._flags_off = total * 4
                     self.tensor = raw[:self.numel]
+                    self.scratch = raw[self.numel:self.numel + int(scratch_numel)]
                     self.mode = "nvls-multimem"
             except Exception:  # no symmetric memory / multicast on this system: NCCL it is
                 self._hdl = None
         if self._hdl is None:
-            self.tensor = torch.zeros(self.numel, dtype=torch.float32, device=device)
+            raw = torch.zeros(self.numel + int(scratch_numel), dtype=torch.float32, device=device)
+            self.tensor = raw[:self.numel]
+            self.scratch = raw[self.numel:]
 
     def all_reduce(self):
         """in-place sum over the ranks, enqueued on the current stream"""
@@ -99,7 +108,7 @@ class SwitchReducedBuffer:
         rc = _lib.lib().jsb200_multimem_allreduce_f32(
             ctypes.c_void_p(torch.cuda.current_stream().cuda_stream),
             ctypes.c_void_p(int(hdl.multicast_ptr) + delta), peers, self._padded,
-            self._padded * 4, hdl.rank, hdl.world_size, self._epoch)
+            self._flags_off, hdl.rank, hdl.world_size, self._epoch)
         if rc != 0:
             _lib.check_error("multimem_allreduce")
 

@@ -137,3 +137,45 @@ def test_status_returning_targets_compute_the_same():
     for o, k in zip(outs, ("cov3ds", "xys", "depths", "radii", "conics", "compensation",
                            "num_tiles_hit", "cum_tiles_hit")):
         assert torch.equal(o, P[k]), k
+
+
+def test_gradient_sink_receives_the_gradients_in_place():
+    """set_gradient_sink: the fused backward writes the five parameter gradients straight into
+    caller-owned views of one flat buffer (what the data-parallel driver all-reduces), autograd
+    adopts those views as .grad, and the values are those of the ordinary path"""
+    sc, _ = _scene_and_cameras(1)
+    H, W = sc.img_shape
+    n = sc.means3d.shape[0]
+    target = torch.rand((H, W, 3), generator=torch.Generator().manual_seed(6)).to(G.DEV)
+
+    def grads(sink):
+        params = [p.clone().requires_grad_(True) for p in sc.params()]
+        jsb.set_gradient_sink(sink)
+        try:
+            img = jsb.render(*params, **sc.render_kwargs())
+            ((img - target) ** 2).mean().backward()
+        finally:
+            jsb.set_gradient_sink(None)
+        return params
+
+    ref = grads(None)
+    flat = torch.full((14 * n + 5 * n,), float("nan"), device=G.DEV)
+    views, off = [], 0
+    for p in sc.params():
+        views.append(flat[off:off + p.numel()].view(p.shape))
+        off += p.numel()
+    got = grads(views + [flat[14 * n:]])
+    for p, v, r in zip(got, views, ref):
+        assert p.grad.data_ptr() == v.data_ptr()          # adopted, not copied
+        ok, err, scale = grad_close(G.npy(v), G.npy(r.grad), rel=1e-4)
+        assert ok, (err, scale)
+    assert bool(torch.isfinite(flat[:14 * n]).all())
+    # without the scratch tail the library allocates its own (same values)
+    flat2 = torch.zeros(14 * n, device=G.DEV)
+    views2, off = [], 0
+    for p in sc.params():
+        views2.append(flat2[off:off + p.numel()].view(p.shape))
+        off += p.numel()
+    grads(views2)
+    ok, err, scale = grad_close(G.npy(flat2), G.npy(flat[:14 * n]), rel=1e-4)
+    assert ok, (err, scale)

@@ -87,3 +87,15 @@ def test_tile_row_bands_partition():
     w[3] = 50
     bands = multiview.tile_row_bands(20, 4, weights=w)
     assert bands[0][0] == 0 and bands[-1][1] == 20 and all(b > a for a, b in bands)
+
+
+def test_reduced_buffer_scratch_tail_follows_the_reduced_floats():
+    """single process: the per-rank scratch of a SwitchReducedBuffer starts exactly where the
+    reduced floats end (the render backward relies on that to clear its accumulators at once)"""
+    buf = multiview.SwitchReducedBuffer(14 * 10, "cpu", scratch_numel=5 * 10)
+    assert buf.mode == "single" and buf.tensor.numel() == 140 and buf.scratch.numel() == 50
+    assert buf.scratch.data_ptr() == buf.tensor.data_ptr() + 140 * 4
+    buf.tensor.fill_(1.0)
+    buf.all_reduce()  # no-op on one rank
+    assert float(buf.tensor.sum()) == 140.0 and float(buf.scratch.abs().sum()) == 0.0
+    assert multiview.SwitchReducedBuffer(7, "cpu").scratch.numel() == 0
