@@ -296,13 +296,13 @@ def main():
         last = 0.0
         for k in range(steps):
             b = k % 2
-            if k + 1 < steps:
-                issue_copy(k + 1)
             main.wait_event(ev_copied[b])
             loss = step(view_buf[b], tgt_buf[b])
             ev_free[b].record(main)
             loss_pinned[b:b + 1].copy_(loss.detach().reshape(1), non_blocking=True)  # D2H of the result
             ev_loss[b].record(main)
+            if k + 1 < steps:
+                issue_copy(k + 1)  # after step k is enqueued: the host never delays the GPU's next kernel
             if k >= 1:
                 ev_loss[1 - b].synchronize()
                 last = float(loss_pinned[1 - b])
