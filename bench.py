@@ -417,7 +417,8 @@ def main():
                                "kind": "port",
                                "sample": f"{reps} full fwd+bwd views of the same {args.config} workload "
                                          f"(oracle/oracle.c, OpenMP, {dt / reps:.2f} s/view); the reference "
-                                         "itself has no CPU path"}
+                                         "itself has no CPU path, and BASELINE.json's pure-JAX jit oracle is "
+                                         "replaced by this C restatement because JAX cannot be installed here"}
     print(json.dumps(out), file=real_stdout, flush=True)
     if use_dist:
         dist.destroy_process_group()
