@@ -161,6 +161,8 @@ JSB200_API unsigned long long jsb200_error_count(void);
  *      "cache" (1 default; 0 forces rasterize_bwd to re-bin instead of reusing the forward's),
  *      "fwd2px" / "bwd2px" (1 default; 0 runs rasterize_fwd / rasterize_bwd with one pixel per
  *               thread instead of two),
+ *      "fwdpk" / "bwdpk" (1 default; 0 runs the two-pixel rasterisers with scalar FP32 math
+ *               instead of the packed FP32x2 instructions of sm_100),
  *      "rowcol" (1 default; 0 builds the per-tile lists with the older counting distribution of
  *               tile_lists.cu instead of the two-level row/column distribution),
  *      "timing" (0 default; 1 brackets every stage with CUDA events, see jsb200_get_stage_times),
