@@ -224,16 +224,9 @@ static BinParams bin_params(const Descriptor &d) {
     return bp;
 }
 
-static int tile_bits(unsigned tiles) {
-    int b = 1;
-    while ((1ull << b) < tiles) ++b;
-    return b;
-}
-
 constexpr int SM_FP = 0, SM_TOTAL = 1;       // u64 slots in `small`
 constexpr int SM_ROWS = 4;                   // u64 slot: sum of box heights (row entries)
 constexpr int SM_ERR_WORD = 4;               // int slots start (byte 16)
-constexpr int SM_TICKET_WORD = 8;            // u32 tickets start (byte 32)
 constexpr int SM_STRIP = 8;                  // u64 per-strip intersection counts start (byte 64)
 constexpr size_t SMALL_BYTES = 64 + 8 * kMaxStrips;
 
