@@ -120,3 +120,23 @@ def test_views_entry_points_validate_before_touching_the_gpu():
     with pytest.raises(RuntimeError):
         _lib.set_option("view_slots", 0)
     _lib.set_option("view_slots", 8)
+
+
+def test_jax_binding_is_importable_and_guarded_without_jax():
+    """the JAX host layer cannot run here (no JAX in the image) but must import, hand out the
+    same capsules as the compiled module, and fail loudly when asked to register"""
+    from jaxsplat_b200 import jax_binding as jb
+    L = _lib.lib()
+    for status in (False, True):
+        regs = jb.registrations(status_returning=status)
+        assert sorted(regs) == sorted(_ffi.TARGETS)
+        for name, cap in regs.items():
+            sym = "jsb200_" + name + ("_status" if status else "")
+            assert _ffi.capsule_pointer(cap) == ctypes.cast(getattr(L, sym), ctypes.c_void_p).value
+    d = jb.make_descriptor(7, (32, 48), (24.0, 16.0), (24.0, 16.0), 1.0, 0.01, 16)
+    assert d == _ffi.make_descriptor(7, (32, 48), (24.0, 16.0), (24.0, 16.0), 1.0, 0.01, 16)
+    if not jb.HAVE_JAX:
+        with pytest.raises(ImportError):
+            jb.register_targets()
+    for fn in ("render", "project", "rasterize"):
+        assert callable(getattr(jb, fn))
