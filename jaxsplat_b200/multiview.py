@@ -156,3 +156,25 @@ def multiview_step(flat: FlatParams, views: Sequence, targets: Sequence[torch.Te
         flat.reducer.all_reduce()
         dist.all_reduce(total)
     return total
+
+
+def band_step(flat: FlatParams, target: torch.Tensor, band: tuple, render_fn: Callable, *,
+              block_size: int = 16, reduce: bool = True):
+    """One fwd+bwd of ONE large frame sharded by screen-tile rows (BASELINE config 5):
+    this rank renders only the tile rows ``band = (begin, end)`` (``render_fn(*params,
+    tile_rows=band)`` -> (H, W, 3), e.g. ``jaxsplat_b200.render`` with its keyword arguments bound),
+    takes the full-frame MSE restricted to its rows (same normalisation, so the ranks' losses add up
+    to the full-frame loss), and the per-Gaussian gradients are summed across ranks with the one
+    flat all-reduce.  Returns the rank-local share of the loss (summed over ranks when reducing).
+    The image stays sharded: rows outside the band are not written by the band render."""
+    flat.zero_grad()
+    H, W = target.shape[0], target.shape[1]
+    y0, y1 = band[0] * block_size, min(H, band[1] * block_size)
+    img = render_fn(*flat.params, tile_rows=band)
+    loss = ((img[y0:y1] - target[y0:y1]) ** 2).sum() / float(H * W * target.shape[2])
+    loss.backward()
+    total = loss.detach().clone()
+    if reduce and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        flat.reducer.all_reduce()
+        dist.all_reduce(total)
+    return total

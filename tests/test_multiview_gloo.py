@@ -99,3 +99,46 @@ def test_reduced_buffer_scratch_tail_follows_the_reduced_floats():
     buf.all_reduce()  # no-op on one rank
     assert float(buf.tensor.sum()) == 140.0 and float(buf.scratch.abs().sum()) == 0.0
     assert multiview.SwitchReducedBuffer(7, "cpu").scratch.numel() == 0
+
+
+def _fake_band_render(means, scales, quats, colors, opac, tile_rows=None, H=48, W=8):
+    """a differentiable stand-in whose rows depend on all five arrays; like the product's band
+    render it only produces the rows of its band (the others stay zero and must not be read)"""
+    rows = torch.arange(H, dtype=torch.float32).view(H, 1, 1)
+    base = (means.sum(0) * scales.mean(0)).view(1, 1, 3) + quats[:, :3].cos().mean(0).view(1, 1, 3)
+    img = (base * (1.0 + 0.01 * rows) + (colors * opac).sum(0).view(1, 1, 3) * torch.sin(rows)).expand(H, W, 3)
+    if tile_rows is None:
+        return img
+    mask = torch.zeros((H, 1, 1))
+    mask[tile_rows[0] * 16:min(H, tile_rows[1] * 16)] = 1.0
+    return img * mask
+
+
+def _band_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ps, _, _ = _make(seed=3)
+    target = torch.rand((48, 8, 3), generator=torch.Generator().manual_seed(9))
+    flat = multiview.FlatParams(ps)
+    band = multiview.tile_row_bands(3, world)[rank]
+    loss = multiview.band_step(flat, target, band, _fake_band_render)
+    if rank == 0:
+        torch.save({"grad": flat.grad.clone(), "loss": loss}, out)
+    dist.destroy_process_group()
+
+
+def test_two_rank_band_step_equals_the_full_frame(tmp_path):
+    """screen-tile-row sharding of one frame over two gloo ranks: summed gradient and loss equal
+    the single-process full-frame values"""
+    out = str(tmp_path / "band.pt")
+    mp.spawn(_band_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    got = torch.load(out)
+    ps, _, _ = _make(seed=3)
+    target = torch.rand((48, 8, 3), generator=torch.Generator().manual_seed(9))
+    qs = [p.clone().requires_grad_(True) for p in ps]
+    full = ((_fake_band_render(*qs) - target) ** 2).mean()
+    full.backward()
+    ref = torch.cat([q.grad.reshape(-1) for q in qs])
+    assert torch.allclose(got["grad"], ref, rtol=1e-5, atol=1e-7)
+    assert abs(float(got["loss"]) - float(full)) <= 1e-6 * max(1.0, abs(float(full)))
