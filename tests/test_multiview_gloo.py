@@ -141,4 +141,5 @@ def test_two_rank_band_step_equals_the_full_frame(tmp_path):
     full.backward()
     ref = torch.cat([q.grad.reshape(-1) for q in qs])
     assert torch.allclose(got["grad"], ref, rtol=1e-5, atol=1e-7)
-    assert abs(float(got["loss"]) - float(full)) <= 1e-6 * max(1.0, abs(float(full)))
+    full_loss = float(full.detach())
+    assert abs(float(got["loss"]) - full_loss) <= 1e-6 * max(1.0, abs(full_loss))
