@@ -130,3 +130,60 @@ def test_descriptor_band_extension():
     assert struct.unpack("<I", b[76:])[0] == (17 | (34 << 16))
     with pytest.raises(RuntimeError):
         _ffi.with_band(d, 5, 5)
+
+
+def test_error_text_is_thread_local():
+    """the sticky error belongs to the calling thread (XLA drives several devices from several
+    host threads): a failure on one thread is invisible to another, the global counter sees both"""
+    import threading
+    L = _lib.lib()
+    L.jsb200_clear_error()
+    before = L.jsb200_error_count()
+    seen = {}
+
+    def worker(tag, fail):
+        L.jsb200_clear_error()
+        if fail:
+            bufs = (ctypes.c_void_p * 1)(None)
+            L.jsb200_rasterize_fwd(None, bufs, b"y" * 7, 7)
+        msg = L.jsb200_last_error()
+        seen[tag] = None if msg is None else bytes(msg)
+        L.jsb200_clear_error()
+
+    threads = [threading.Thread(target=worker, args=("bad", True)),
+               threading.Thread(target=worker, args=("good", False))]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert seen["bad"] is not None and b"descriptor" in seen["bad"]
+    assert seen["good"] is None
+    assert L.jsb200_last_error() is None            # nor on this thread
+    assert L.jsb200_error_count() == before + 1
+
+
+def test_tile_row_bands_properties():
+    """bands are contiguous, cover every tile row exactly once, are non-empty whenever there are
+    at least as many rows as ranks, and follow the weights"""
+    from hypothesis import given, settings, strategies as st
+    from jaxsplat_b200 import multiview
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.integers(1, 300), st.integers(1, 16), st.randoms(use_true_random=False))
+    def check(tiles_y, world, rnd):
+        weights = [rnd.random() * 10 + 0.01 for _ in range(tiles_y)]
+        for w in (None, weights):
+            bands = multiview.tile_row_bands(tiles_y, world, w)
+            assert len(bands) == world
+            assert bands[0][0] == 0 and bands[-1][1] == tiles_y
+            for (a0, a1), (b0, b1) in zip(bands, bands[1:]):
+                assert a1 == b0 and a0 <= a1
+            if tiles_y >= world:
+                assert all(b1 > b0 for b0, b1 in bands)
+    check()
+    # heavy rows in the middle: the band holding them is the narrowest
+    w = [1.0] * 30
+    w[14] = w[15] = 100.0
+    bands = multiview.tile_row_bands(30, 3, w)
+    widths = [b1 - b0 for b0, b1 in bands]
+    assert widths[1] == min(widths)
