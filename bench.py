@@ -122,7 +122,6 @@ def main():
     # version banner there) are pointed at stderr, the JSON goes to the saved descriptor
     real_stdout = os.fdopen(os.dup(1), "w")
     os.dup2(2, 1)
-    import numpy as np
     import torch
     import torch.distributed as dist
 
@@ -138,7 +137,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     import jaxsplat_b200 as jsb
-    from jaxsplat_b200 import _ffi, _lib, _ops, synthetic
+    from jaxsplat_b200 import _lib, _ops, synthetic
 
     if args.impl == "reference":
         from oracle import ref_cuda

@@ -6,7 +6,6 @@ import os
 import re
 import struct
 
-import numpy as np
 import pytest
 import torch
 

@@ -1,14 +1,13 @@
 """GPU: the public API (render/project/rasterize + autograd), size-independent properties at the
 BASELINE.json full sizes, and parity with the live reference CUDA library when it is present
 (oracle/_ref travels to the GPU box; it does not exist in a fresh checkout)."""
-import numpy as np
 import pytest
 import torch
 
 from conftest import grad_close
 import gpu_util as G
 import jaxsplat_b200 as jsb
-from jaxsplat_b200 import _ffi, synthetic
+from jaxsplat_b200 import synthetic
 from oracle import ref_cuda
 
 pytestmark = pytest.mark.gpu
