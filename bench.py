@@ -6,13 +6,19 @@ under torchrun for N > 1, prints ONE JSON line on rank 0.
 
 Workload (BASELINE.json configs[2]): 1M synthetic Gaussians, 1920x1080, block_size 16; one step =
 one view's render forward + backward of loss = mean((img - target)^2) w.r.t. the five parameter
-arrays, through the public API (jaxsplat_b200.render + autograd) -> the four C-ABI custom calls.
+arrays, through the public API (jaxsplat_b200.render + autograd) -> the fused C-ABI render calls.
 At N > 1 the views shard across ranks (one view per rank per step, Gaussians replicated, weak
-scaling) and the 14*N-float parameter gradient is summed with one NCCL all-reduce per step.
+scaling); the render backward writes the 14*N-float parameter gradient in place into one flat
+symmetric buffer (jaxsplat_b200.set_gradient_sink) that is summed with one all-reduce per step
+(the in-switch multimem kernel of csrc/collective.cu where the node has NVLS, NCCL otherwise).
 
-  value  : views/s, whole job, parameters/targets resident in HBM (CUDA events, max over ranks)
+  value  : views/s, whole job, parameters/targets resident in HBM (CUDA events, max over ranks);
+           the library's per-stage events are OFF during these K steps
+  stages / roofline / issue : per-stage device times from a separate pass of the same step with
+           the stage events on (outside the timed region)
   e2e    : same step, but the step's host inputs (target image + camera, pinned) are copied H2D
-           and the loss is read back D2H inside the timed region (wall clock around K steps)
+           and the loss is read back D2H inside the timed region (wall clock around K steps);
+           the copy of step k+1 runs on a copy stream under step k
   --impl reference : the UNMODIFIED reference CUDA library (oracle/_ref, built from
            /root/reference/lib by oracle/Makefile) driven through the same harness on rank 0.
 """
