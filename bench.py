@@ -342,7 +342,8 @@ def main():
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": f"{args.config}: {N} Gaussians (benchmark.py distribution, scales<0.1, seed 0), "
+        "config": {"workload": f"{args.config}: {N} Gaussians (benchmark.py distribution, "
+                               f"scales {scene.meta.get('scales', '?')}, seed 0), "
                                f"{W}x{H}, block_size 16, fwd+bwd of MSE loss, 1 view/GPU/step",
                    "num_intersects": I, "parallelism": (f"view-parallel dp{world}, gradient all-reduce: "
                                    f"{reducer.mode if reducer is not None else 'nccl'}, gradients "

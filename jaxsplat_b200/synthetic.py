@@ -91,7 +91,8 @@ def benchmark_scene(num_points: int, img_shape: Tuple[int, int], scale_max: floa
                  viewmat=_viewmat_identity(8.0) if viewmat is None else viewmat,
                  background=torch.full((3,), background, dtype=torch.float32),
                  img_shape=(H, W), f=(W / 2.0, H / 2.0), c=(W / 2.0, H / 2.0),
-                 meta=dict(seed=seed, scale_max=scale_max))
+                 meta=dict(seed=seed, scales=(f"U[0,{scale_max})" if log_uniform_scales is None else
+                                              f"log-uniform[{log_uniform_scales[0]},{log_uniform_scales[1]}]")))
 
 
 def single_image_scene(num_points: int = 10_000, img_shape=(256, 256), seed: int = 0) -> Scene:
@@ -135,6 +136,10 @@ CONFIGS = {
     "C1": dict(kind="single_image", num_points=10_000, img_shape=(256, 256)),
     "C2": dict(kind="benchmark", num_points=100_000, img_shape=(512, 512), scale_max=0.5),
     "C3": dict(kind="benchmark", num_points=1_000_000, img_shape=(1080, 1920), scale_max=0.1),
+    # C3's secondary distributions: small "trained-scene-like" splats (I ~ 2.8e6) and
+    # examples/benchmark.py's literal scales < 0.5 (I ~ 2.6e8, list-building dominated)
+    "C3s": dict(kind="benchmark", num_points=1_000_000, img_shape=(1080, 1920), scale_max=0.02),
+    "C3b": dict(kind="benchmark", num_points=1_000_000, img_shape=(1080, 1920), scale_max=0.5),
     "C4": dict(kind="benchmark", num_points=3_000_000, img_shape=(1080, 1920),
                log_uniform_scales=(0.002, 0.06)),
     "C5": dict(kind="benchmark", num_points=6_000_000, img_shape=(2160, 3840), scale_max=0.1),
