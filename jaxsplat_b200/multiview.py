@@ -42,6 +42,36 @@ def tile_row_bands(tiles_y: int, world: int, weights=None) -> List[tuple]:
     return bands
 
 
+def tile_row_weights(xys: torch.Tensor, radii: torch.Tensor, img_shape, block_size: int = 16):
+    """Intersections per screen-tile row from the public outputs of ``project`` -- the `weights`
+    of ``tile_row_bands`` ("balance bands by intersection count, not rows, using the
+    per-row histogram").  Same tile box as the reference's get_tile_bbox (helpers.h:9-32): float32
+    ``xy / bw -+ radius / bw (+ 1)``, truncated toward zero, clamped to the tile grid; Gaussians
+    with ``radii <= 0`` hit nothing (forward.cu:145).  A planning pass outside the hot path (a few
+    elementwise torch ops on whatever device the inputs live on); its sum equals
+    ``cum_tiles_hit[-1]``.  Returns a float64 tensor of ``ceil(H / block_size)`` entries."""
+    H, W = int(img_shape[0]), int(img_shape[1])
+    tiles_x, tiles_y = (W + block_size - 1) // block_size, (H + block_size - 1) // block_size
+    bw = float(block_size)
+    xy = xys.reshape(-1, 2).to(torch.float32)
+    r = radii.reshape(-1).to(torch.float32)
+    centre, tr = xy / bw, (r / bw).unsqueeze(1)
+    # out-of-range floats saturate in the reference's cvt.rzi.s32.f32; the clamp to the tile grid
+    # that follows makes a float clamp before the cast equivalent
+    big = float(max(tiles_x, tiles_y) + 1)
+    lo = torch.nan_to_num(centre - tr, nan=0.0).clamp(-1.0, big).trunc().to(torch.int64)
+    hi = torch.nan_to_num(centre + tr + 1.0, nan=0.0).clamp(-1.0, big).trunc().to(torch.int64)
+    x0, x1 = lo[:, 0].clamp(0, tiles_x), hi[:, 0].clamp(0, tiles_x)
+    y0, y1 = lo[:, 1].clamp(0, tiles_y), hi[:, 1].clamp(0, tiles_y)
+    width = (x1 - x0).clamp_min(0).to(torch.float64)
+    width = torch.where((radii.reshape(-1) > 0) & (y1 > y0), width, torch.zeros_like(width))
+    # difference array over the rows: +width at y0, -width at y1, prefix sum
+    delta = torch.zeros(tiles_y + 1, dtype=torch.float64, device=xy.device)
+    delta.index_add_(0, y0, width)
+    delta.index_add_(0, y1, -width)
+    return delta.cumsum(0)[:tiles_y]
+
+
 class SwitchReducedBuffer:
     """A flat float32 buffer that every rank of a node allocates symmetrically and that is summed
     across ranks IN the NVSwitch by one native kernel (csrc/collective.cu:

@@ -143,3 +143,64 @@ def test_two_rank_band_step_equals_the_full_frame(tmp_path):
     assert torch.allclose(got["grad"], ref, rtol=1e-5, atol=1e-7)
     full_loss = float(full.detach())
     assert abs(float(got["loss"]) - full_loss) <= 1e-6 * max(1.0, abs(full_loss))
+
+
+def test_tile_row_weights_equal_the_oracle_row_histogram():
+    """multiview.tile_row_weights (planning pass of the tile-row sharding) against the oracle:
+    per tile row, the number of intersections in the oracle's tile bins (reference
+    forward.cu:135-208 restated in oracle/oracle.c); exact integers, block sizes 16 and 8, an
+    image whose last tile row is half covered, Gaussians partly and wholly off screen"""
+    import numpy as np
+
+    from jaxsplat_b200 import synthetic
+    from oracle import cpu
+    for bw, shape, smax in ((16, (120, 200), 0.3), (8, (72, 90), 0.15), (16, (40, 64), 2.0)):
+        s = synthetic.benchmark_scene(3000, shape, scale_max=smax, seed=4)
+        P = cpu.project_fwd(s.means3d.numpy(), s.scales.numpy(), s.quats.numpy(), s.viewmat.numpy(),
+                            img_shape=shape, f=s.f, c=s.c, glob_scale=1.0, clip_thresh=0.01,
+                            block_width=bw)
+        B = cpu.sort_and_bin(P["xys"], P["depths"], P["radii"], P["cum_tiles_hit"],
+                             img_shape=shape, block_width=bw)
+        tx, ty = cpu.tiles_of(shape, bw)
+        per_tile = (B["tile_bins"][:, 1] - B["tile_bins"][:, 0]).reshape(ty, tx)
+        want = per_tile.sum(1)
+        got = multiview.tile_row_weights(torch.from_numpy(P["xys"]), torch.from_numpy(P["radii"]),
+                                         shape, bw)
+        assert got.shape == (ty,)
+        assert np.array_equal(got.numpy().astype(np.int64), want.astype(np.int64)), (bw, shape)
+        assert int(got.sum()) == int(P["cum_tiles_hit"][-1, 0]) == B["num_intersects"]
+        # and the bands built from them are balanced to within twice the heaviest row (greedy cut)
+        bands = multiview.tile_row_bands(ty, 2, weights=got.tolist())
+        loads = [float(got[a:b].sum()) for a, b in bands]
+        assert abs(loads[0] - loads[1]) <= 2.0 * float(got.max()) + 1e-9
+
+
+def _run_tool(args, nproc=1):
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable]
+    if nproc > 1:
+        cmd += ["-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
+                "--master-addr", "127.0.0.1", "--master-port", str(_free_port())]
+    cmd += [os.path.join(root, "tools", "multigpu_bench.py")] + args
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1, r.stdout  # ONE JSON line, on rank 0
+    return json.loads(lines[0])
+
+
+def test_multigpu_bench_tool_dry_run_shards_consistently():
+    """tools/multigpu_bench.py (the C4 view-batch / C5 tile-row-band lines) in its CPU dry mode
+    (gloo, stand-in renderer): a 5-view batch in chunks of 2 and a banded frame give the same
+    loss and gradient norm on one rank and on two"""
+    for mode in ("views", "bands"):
+        args = [mode, "--dry", "--steps", "1", "--warmup", "1", "--views", "5", "--chunk", "2"]
+        one = _run_tool(args)
+        two = _run_tool(args, nproc=2)
+        assert one["n_gpus"] == 1 and two["n_gpus"] == 2 and two["reduction"] == "gloo"
+        assert abs(one["loss"] - two["loss"]) <= 1e-5 * abs(one["loss"])
+        assert abs(one["grad_l2"] - two["grad_l2"]) <= 1e-5 * abs(one["grad_l2"])
+    assert two["bands"][0][0] == 0 and two["bands"][-1][1] == 3 and len(two["bands"]) == 2

@@ -1,0 +1,32 @@
+#!/bin/bash
+# Runs ON the GPU box (through gpurun, ONE GPU): everything round 1 left unmeasured, plus the
+# regression set, in one call.  usage: tools/gpu_round2_open.sh [TAG]
+#   GPU tests (incl. the packed-vs-scalar rasteriser tests added after the last round-1 GPU run),
+#   bench lines for C3 and its two secondary scale distributions (C3s, C3b), the
+#   reference arm, and the single-GPU points of the two sharded configurations (C4 views, C5 bands).
+TAG=${1:-r02a}
+OUT=gpurun_out
+mkdir -p $OUT
+nvidia-smi --query-gpu=name,clocks.max.sm,clocks.sm,power.limit --format=csv > $OUT/${TAG}_gpu.txt 2>&1
+nproc >> $OUT/${TAG}_gpu.txt
+timeout 900 python -m pytest tests -m gpu -x -q > $OUT/${TAG}_pytest.log 2>&1
+tail -3 $OUT/${TAG}_pytest.log
+timeout 600 python bench.py > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err
+timeout 300 python bench.py --impl reference --steps 30 --warmup 5 > $OUT/${TAG}_bench_reference.json 2> $OUT/${TAG}_bench_reference.err
+for C in C3s C3b; do
+  timeout 400 python bench.py --config $C --steps 50 --warmup 5 --no-cpu-baseline > $OUT/${TAG}_bench_$C.json 2> $OUT/${TAG}_bench_$C.err
+  timeout 400 python bench.py --config $C --impl reference --steps 10 --warmup 3 > $OUT/${TAG}_bench_reference_$C.json 2> $OUT/${TAG}_bench_reference_$C.err
+done
+timeout 400 python tools/multigpu_bench.py views --steps 3 --warmup 2 > $OUT/${TAG}_views_C4_1gpu.json 2> $OUT/${TAG}_views_C4_1gpu.err
+timeout 400 python tools/multigpu_bench.py bands --steps 5 --warmup 2 > $OUT/${TAG}_bands_C5_1gpu.json 2> $OUT/${TAG}_bands_C5_1gpu.err
+python - <<EOF
+import glob, json
+for f in sorted(glob.glob("${OUT}/${TAG}_*.json")):
+    try:
+        d = json.loads(open(f).read().strip().splitlines()[-1])
+        e = d.get('e2e') or {}
+        print(f, 'ms/step', round(d['ms_per_step'], 4), d.get('unit'), round(d.get('value', 0), 2),
+              'e2e', e.get('ms_per_step'))
+    except Exception as ex:
+        print(f, 'unreadable', ex)
+EOF
