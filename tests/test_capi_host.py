@@ -186,3 +186,15 @@ def test_tile_row_bands_properties():
     bands = multiview.tile_row_bands(30, 3, w)
     widths = [b1 - b0 for b0, b1 in bands]
     assert widths[1] == min(widths)
+
+
+def test_adam_rejects_host_tensors_and_mismatched_gradient_buffers():
+    """optim.Adam is CUDA-only like the rest of the product (no CPU fallback): host tensors and
+    ill-sized fixed gradient buffers are refused before anything native is called"""
+    import torch
+
+    from jaxsplat_b200.optim import Adam
+    with pytest.raises(TypeError):
+        Adam([torch.zeros(4)])
+    with pytest.raises((TypeError, ValueError)):
+        Adam([], grads=[torch.zeros(4)])

@@ -55,6 +55,36 @@ def test_native_adam_matches_torch_adam():
 
 
 @pytest.mark.gpu
+def test_flat_adam_reads_the_reduced_gradient_buffer():
+    """Adam.for_flat: one kernel over the 14*N-float FlatParams buffer, gradients read
+    from the flat all-reduced buffer in place, equals the per-array Adam on the same gradients"""
+    import torch
+    from jaxsplat_b200 import multiview
+    from jaxsplat_b200.optim import Adam
+    gen = torch.Generator().manual_seed(1)
+    n = 1003  # 3n, 6n, 10n, 13n: array boundaries that are not 16-byte aligned
+    shapes = [(n, 3), (n, 3), (n, 4), (n, 3), (n, 1)]
+    init = [torch.randn(s, generator=gen).cuda() for s in shapes]
+    flat = multiview.FlatParams(init)
+    ref = [x.clone().requires_grad_(True) for x in init]
+    of, orf = Adam.for_flat(flat, lr=0.01), Adam(ref, lr=0.01)
+    assert flat.reducer.mode == "single"
+    for step in range(5):
+        flat.zero_grad()
+        for q, y in zip(flat.params, ref):
+            g = torch.randn(q.shape, generator=gen).cuda() * (10.0 ** (step - 2))
+            q.grad.add_(g)   # what backward passes accumulate into the flat buffer's views
+            y.grad = g.clone()
+        flat.reducer.all_reduce()  # single rank: no-op
+        of.step()
+        orf.step()
+        for q, y in zip(flat.params, ref):
+            assert torch.allclose(q.detach(), y.detach(), rtol=2e-6, atol=1e-7), step
+    # the parameter views still alias the flat buffer the kernel updated
+    assert flat.params[0].data_ptr() == flat.flat.data_ptr()
+
+
+@pytest.mark.gpu
 def test_config1_fit_with_the_native_adam_step():
     scene, target = _c1()
     ref = fit_util.fit_gpu(scene, target, steps=30)
