@@ -176,6 +176,8 @@ def main():
         for key in ("bwdpk", "fwdpk"):  # packed FP32x2 rasterisers (A/B: tools/gpu_pk.sh)
             if os.environ.get("JSB_" + key.upper()) == "0":
                 _lib.set_option(key, 0)
+        if os.environ.get("JSB_SORTLIVE") == "1":  # experimental live-bit depth sort
+            _lib.set_option("sortlive", 1)
         if os.environ.get("JSB_FUSED") == "0":
             jsb.set_fused_render(False)
     # N > 1: the five gradients are packed into one flat symmetric buffer so the all-reduce is a

@@ -165,6 +165,9 @@ JSB200_API unsigned long long jsb200_error_count(void);
  *               instead of the packed FP32x2 instructions of sm_100),
  *      "rowcol" (1 default; 0 builds the per-tile lists with the older counting distribution of
  *               tile_lists.cu instead of the two-level row/column distribution),
+ *      "sortlive" (0 default; 1 = EXPERIMENTAL, written without GPU access and not yet run on
+ *               one: the depth sort takes its digits from `key - min key` and skips the passes
+ *               over the zero top bytes; same lists by construction),
  *      "timing" (0 default; 1 brackets every stage with CUDA events, see jsb200_get_stage_times),
  *      "view_slots" (8 default; binning workspaces a batched-camera call cycles through) */
 JSB200_API int jsb200_set_option(const char *key, int value);

@@ -55,6 +55,7 @@ extern bool g_fwd_scalar;
 extern bool g_fwd_one_pixel;
 static bool g_disable_cache = false;
 static bool g_disable_rowcol = false;
+static bool g_sort_live = false;  // option "sortlive": depth sort on the live bits of key - min
 static unsigned g_view_slots = 8;  // binning workspaces a batched-camera call cycles through
 
 // ---- optional per-stage device timing (jsb200_set_option("timing", 1)) -------------------------
@@ -274,9 +275,14 @@ static int bin_finish_enqueue(Ctx &c, const Descriptor &d, bool write) {
     if (write) {
         StageScope ss(&c, ST_DEPTH_SORT);
         bool in_b = false;
-        if (radix_sort_pairs<uint32_t>(s, (uint32_t *)c.dkeys_a.p, (uint32_t *)c.dkeys_b.p,
-                                       (unsigned *)c.ids_a.p, (unsigned *)c.ids_b.p, n, 32,
-                                       c.sort_n_scratch.p, (int *)c.small.p + SM_ERR_WORD, &in_b))
+        if (g_sort_live
+                ? radix_sort_depth_live(s, (uint32_t *)c.dkeys_a.p, (uint32_t *)c.dkeys_b.p,
+                                        (unsigned *)c.ids_a.p, (unsigned *)c.ids_b.p, n,
+                                        c.sort_n_scratch.p, (int *)c.small.p + SM_ERR_WORD, &in_b)
+                : radix_sort_pairs<uint32_t>(s, (uint32_t *)c.dkeys_a.p, (uint32_t *)c.dkeys_b.p,
+                                             (unsigned *)c.ids_a.p, (unsigned *)c.ids_b.p, n, 32,
+                                             c.sort_n_scratch.p, (int *)c.small.p + SM_ERR_WORD,
+                                             &in_b))
             return 1;
         c.order_in_b = in_b;
     }
@@ -1068,6 +1074,7 @@ int jsb200_set_option(const char *key, int value) {
     if (!strcmp(key, "bwdpk")) { jsb::g_bwd_scalar = (value == 0); return 0; }
     if (!strcmp(key, "fwdpk")) { jsb::g_fwd_scalar = (value == 0); return 0; }
     if (!strcmp(key, "rowcol")) { jsb::g_disable_rowcol = (value == 0); return 0; }
+    if (!strcmp(key, "sortlive")) { jsb::g_sort_live = (value != 0); return 0; }
     if (!strcmp(key, "timing")) { jsb::g_timing = (value != 0); return 0; }
     if (!strcmp(key, "view_slots")) {
         if (value < 1 || value > 4096) { jsb::set_error("set_option: view_slots must be 1..4096"); return 1; }

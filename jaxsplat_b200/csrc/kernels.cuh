@@ -149,6 +149,12 @@ int radix_sort_pairs(cudaStream_t stream, KeyT *keys_a, KeyT *keys_b, unsigned *
                      unsigned *vals_b, unsigned n, int bits, void *scratch, int *err,
                      bool *result_in_b);
 
+// Depth order on the live key bits (option "sortlive", off by default): same order of the values
+// as radix_sort_pairs<uint32_t>(bits = 32) for every key != 0xFFFFFFFF; identity passes over the
+// zero top bytes of `key - min` only copy the values.  Same scratch; key buffers are scratch after.
+int radix_sort_depth_live(cudaStream_t stream, uint32_t *keys_a, uint32_t *keys_b, unsigned *vals_a,
+                          unsigned *vals_b, unsigned n, void *scratch, int *err, bool *result_in_b);
+
 // ---- rasterisers (raster_fwd.cu / raster_bwd.cu) --------------------------------------------
 struct RasterParams {
     unsigned img_w, img_h;
