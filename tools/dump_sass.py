@@ -14,7 +14,7 @@ OUT = sys.argv[2] if len(sys.argv) > 2 else os.path.join(ROOT, "profiles", "sass
 PREFER = {"raster_fwd16x2_kernel": "ILb1ELb1E", "raster_bwd16x2p_kernel": "ILb1ELb0E",
           "raster_bwd16x2_kernel": "ILb1ELb0E", "raster_fwd16_kernel": "ILb1E",
           "raster_bwd16_kernel": "ILb1E", "project_fwd_kernel": "ILb1E",
-          "onesweep_pass_kernel": "IjLi16ELb1ELi0E", "radix_hist_kernel": "IjE"}
+          "onesweep_pass_kernel": "IjLi16ELb1ELi0E", "radix_hist_kernel": "IjE", "upsweep_kernel": "IjE"}
 
 
 def main():
