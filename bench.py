@@ -176,6 +176,8 @@ def main():
         for key in ("bwdpk", "fwdpk"):  # packed FP32x2 rasterisers (A/B: tools/gpu_pk.sh)
             if os.environ.get("JSB_" + key.upper()) == "0":
                 _lib.set_option(key, 0)
+        if os.environ.get("JSB_FWD1BAR") == "1":  # experimental one-barrier forward rasteriser
+            _lib.set_option("fwd1bar", 1)
         if os.environ.get("JSB_SORTLIVE") == "1":  # experimental live-bit depth sort
             _lib.set_option("sortlive", 1)
         if os.environ.get("JSB_FUSED") == "0":

@@ -433,3 +433,31 @@ def test_live_bit_depth_sort_builds_the_same_lists(case):
     if band is None:
         for a, b in zip(outs_a, outs_b):
             assert np.array_equal(a, b)
+
+
+@_experimental
+@pytest.mark.parametrize("scene_fn", [_adversarial_scene, lambda: synthetic.make_config("C2", num_points=30000),
+                                      lambda: synthetic.benchmark_scene(9000, (200, 120), scale_max=0.2, seed=21),
+                                      lambda: synthetic.benchmark_scene(60, (40, 40), scale_max=0.3, seed=3),
+                                      lambda: synthetic.make_config("C1")])
+def test_one_barrier_forward_is_bit_identical(scene_fn):
+    """option "fwd1bar": raster_fwd16x2s_kernel (cull masks of batch b+1 computed after the walk of
+    batch b, one CTA barrier per batch) against the default two-barrier kernel: same arithmetic in
+    the same order, so not a bit may differ -- with and without culling"""
+    s = scene_fn()
+    inp = G.scene_inputs(s)
+    kw, rkw = G.scene_kw(s)
+    P = G.project_fwd(inp, kw)
+    for cull in (1, 0):
+        try:
+            _lib.set_option("cull", cull)
+            _lib.set_option("fwd1bar", 1)
+            a = G.rasterize_fwd(inp, P, rkw)
+            _lib.set_option("fwd1bar", 0)
+            b = G.rasterize_fwd(inp, P, rkw)
+        finally:
+            _lib.set_option("fwd1bar", 0)
+            _lib.set_option("cull", 1)
+        assert torch.equal(a["final_idx"], b["final_idx"])
+        assert torch.equal(a["final_Ts"].view(torch.int32), b["final_Ts"].view(torch.int32))
+        assert torch.equal(a["img"].view(torch.int32), b["img"].view(torch.int32))
