@@ -178,6 +178,8 @@ def main():
                 _lib.set_option(key, 0)
         if os.environ.get("JSB_FWD1BAR") == "1":  # experimental one-barrier forward rasteriser
             _lib.set_option("fwd1bar", 1)
+        if os.environ.get("JSB_BWD1BAR") == "1":  # experimental one-barrier backward rasteriser
+            _lib.set_option("bwd1bar", 1)
         if os.environ.get("JSB_SORTLIVE") == "1":  # experimental live-bit depth sort
             _lib.set_option("sortlive", 1)
         if os.environ.get("JSB_FUSED") == "0":

@@ -168,8 +168,9 @@ JSB200_API unsigned long long jsb200_error_count(void);
  *      "sortlive" (0 default; 1 = EXPERIMENTAL, written without GPU access and not yet run on
  *               one: the depth sort takes its digits from `key - min key` and skips the passes
  *               over the zero top bytes; same lists by construction),
- *      "fwd1bar" (0 default; 1 = EXPERIMENTAL, not yet run on a GPU: the two-pixel forward
- *               rasteriser with one CTA barrier per batch instead of two; same arithmetic),
+ *      "fwd1bar" / "bwd1bar" (0 default; 1 = EXPERIMENTAL, not yet run on a GPU: the two-pixel
+ *               forward / packed backward rasteriser with one CTA barrier per batch instead of
+ *               two; same arithmetic),
  *      "timing" (0 default; 1 brackets every stage with CUDA events, see jsb200_get_stage_times),
  *      "view_slots" (8 default; binning workspaces a batched-camera call cycles through) */
 JSB200_API int jsb200_set_option(const char *key, int value);

@@ -54,6 +54,7 @@ extern bool g_bwd_scalar;
 extern bool g_fwd_scalar;
 extern bool g_fwd_one_pixel;
 extern bool g_fwd_one_barrier;
+extern bool g_bwd_one_barrier;
 static bool g_disable_cache = false;
 static bool g_disable_rowcol = false;
 static bool g_sort_live = false;  // option "sortlive": depth sort on the live bits of key - min
@@ -1077,6 +1078,7 @@ int jsb200_set_option(const char *key, int value) {
     if (!strcmp(key, "rowcol")) { jsb::g_disable_rowcol = (value == 0); return 0; }
     if (!strcmp(key, "sortlive")) { jsb::g_sort_live = (value != 0); return 0; }
     if (!strcmp(key, "fwd1bar")) { jsb::g_fwd_one_barrier = (value != 0); return 0; }
+    if (!strcmp(key, "bwd1bar")) { jsb::g_bwd_one_barrier = (value != 0); return 0; }
     if (!strcmp(key, "timing")) { jsb::g_timing = (value != 0); return 0; }
     if (!strcmp(key, "view_slots")) {
         if (value < 1 || value > 4096) { jsb::set_error("set_option: view_slots must be 1..4096"); return 1; }

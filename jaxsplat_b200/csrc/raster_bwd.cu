@@ -693,6 +693,272 @@ raster_bwd16x2p_kernel(const RasterParams p, const unsigned *__restrict__ ids_so
     }
 }
 
+// ---- packed two-pixel backward, ONE CTA barrier per batch (option "bwd1bar", experimental) ----
+// raster_bwd16x2p_kernel with the staging re-ordered like raster_fwd16x2s_kernel (raster_fwd.cu):
+// the cull masks of batch b+1 are computed by each thread right after it has walked batch b, and
+// a single barrier then means both "batch b is free" and "batch b+1 is visible".  Shared memory
+// is one struct per buffer.  The walk and all arithmetic are the default kernel's text.
+template <bool CULL, bool ABS>
+__global__ void __launch_bounds__(RB2, JSB_BWD_CTAS)
+raster_bwd16x2ps_kernel(const RasterParams p, const unsigned *__restrict__ ids_sorted,
+                       const int2 *__restrict__ tile_bins, const SplatRecord *__restrict__ records,
+                       const float *__restrict__ background, const float *__restrict__ final_Ts,
+                       const int *__restrict__ final_idx, const float *__restrict__ v_out_img,
+                       const float *__restrict__ v_out_alpha_img, float *__restrict__ v_xy,
+                       float *__restrict__ v_xy_abs, float *__restrict__ v_conic,
+                       float *__restrict__ v_colors, float *__restrict__ v_opacity) {
+    constexpr int NV = ABS ? 11 : 9;
+    constexpr int EPT = JSB_BWD_EPT;      // staged entries per thread and batch
+    constexpr int BATCH = RB2 * EPT;
+    // one struct per buffer: every shared address of a batch is one base register + a constant
+    struct Stage {
+        float4 A[BATCH];          // x, y, opac, conic.x      (cp.async staging)
+        float4 B[BATCH];          // conic.y, conic.z, r, g
+        float C[BATCH];           // b
+        unsigned Id[BATCH];       // Gaussian id
+        unsigned char M[BATCH];   // quadrant cull mask
+    };
+    __shared__ Stage st[2];
+    __shared__ int s_max[RB2 / 32];
+    __shared__ __align__(16) float sRed[(RB2 / 32) * NV * RED_STRIDE];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float *red = sRed + warp * NV * RED_STRIDE;
+    const unsigned tile = p.band_y0 * p.tiles_x + blockIdx.x;
+    const unsigned tile_y = tile / p.tiles_x, tile_x = tile - tile_y * p.tiles_x;
+    const unsigned j = tile_x * 16 + (warp & 1) * 8 + (lane & 7);
+    const unsigned i0 = tile_y * 16 + (warp >> 1) * 8 + (lane >> 3), i1 = i0 + 4;
+    const float px = (float)j + 0.5f, py0 = (float)i0 + 0.5f, py1 = (float)i1 + 0.5f;
+    const bool in0 = (i0 < p.img_h) && (j < p.img_w), in1 = (i1 < p.img_h) && (j < p.img_w);
+    const int2 range = tile_bins[tile];
+    const int qbit = (warp & 1) + 4 * (warp >> 1);
+
+    float Tf0 = 1.f, Tf1 = 1.f, voa0 = 0.f, voa1 = 0.f;
+    float3 vo0 = make_float3(0.f, 0.f, 0.f), vo1 = vo0;
+    int bf0 = -1, bf1 = -1;
+    if (in0) {
+        const size_t pix = (size_t)i0 * p.img_w + j;
+        Tf0 = final_Ts[pix];
+        bf0 = final_idx[pix];
+        vo0 = make_float3(v_out_img[pix * 3], v_out_img[pix * 3 + 1], v_out_img[pix * 3 + 2]);
+        voa0 = v_out_alpha_img ? v_out_alpha_img[pix] : 0.f;
+    }
+    if (in1) {
+        const size_t pix = (size_t)i1 * p.img_w + j;
+        Tf1 = final_Ts[pix];
+        bf1 = final_idx[pix];
+        vo1 = make_float3(v_out_img[pix * 3], v_out_img[pix * 3 + 1], v_out_img[pix * 3 + 2]);
+        voa1 = v_out_alpha_img ? v_out_alpha_img[pix] : 0.f;
+    }
+    const float3 bg = make_float3(__ldg(background), __ldg(background + 1), __ldg(background + 2));
+    // per-pixel constants as {pixel 0, pixel 1} pairs
+    const float2 tfc2 = f2(Tf0 * (voa0 - (vo0.x * bg.x + vo0.y * bg.y + vo0.z * bg.z)),
+                           Tf1 * (voa1 - (vo1.x * bg.x + vo1.y * bg.y + vo1.z * bg.z)));
+    const float2 vox2 = f2(vo0.x, vo1.x), voy2 = f2(vo0.y, vo1.y), voz2 = f2(vo0.z, vo1.z);
+    const float2 nvox2 = f2(-vo0.x, -vo1.x), nvoy2 = f2(-vo0.y, -vo1.y), nvoz2 = f2(-vo0.z, -vo1.z);
+    const float2 npy2 = f2(-py0, -py1);
+    float2 T2 = f2(Tf0, Tf1);
+    float2 bufx2 = f2(0.f, 0.f), bufy2 = bufx2, bufz2 = bufx2;
+
+    int wmax = max(bf0, bf1);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+    if (lane == 0) s_max[warp] = wmax;
+    __syncthreads();
+    int tmax = s_max[0];
+#pragma unroll
+    for (int w = 1; w < RB2 / 32; ++w) tmax = max(tmax, s_max[w]);
+    const int top = min(range.y - 1, tmax);
+    if (top < range.x) return;  // nothing in this tile was composited (uniform across the CTA)
+    const int num_batches = (top - range.x + BATCH) / BATCH;
+    const float tile_x0 = (float)(tile_x * 16), tile_y0 = (float)(tile_y * 16);
+
+    const int slot = lane >> 1;
+    float *out_base;
+    int out_stride;
+    if (slot < 3) { out_base = v_colors + slot; out_stride = 3; }
+    else if (slot < 6) { out_base = v_conic + (slot - 3); out_stride = 3; }
+    else if (slot < 8) { out_base = v_xy + (slot - 6); out_stride = 2; }
+    else if (slot < 9) { out_base = v_opacity; out_stride = 1; }
+    else { out_base = v_xy_abs + (slot - 9); out_stride = 2; }
+    const bool writer = ((lane & 1) == 0) && slot < NV;
+
+    auto load_id = [&](int bb, int h) -> unsigned {
+        const int idx = top - BATCH * bb - (tid + h * RB2);
+        return (bb < num_batches && idx >= range.x) ? ids_sorted[idx] : 0u;
+    };
+    auto issue = [&](int bb, int h, unsigned g) {
+        const int t = tid + h * RB2;
+        if (top - BATCH * bb - t >= range.x) {
+            const SplatRecord *r = records + g;
+            cp_async16(&st[bb & 1].A[t], &r->q0);
+            cp_async16(&st[bb & 1].B[t], &r->q1);
+            cp_async4(&st[bb & 1].C[t], &r->q2);
+            st[bb & 1].Id[t] = g;
+        }
+    };
+    // cull masks of this thread's entries of batch bb (its own cp.async data has been waited for)
+    auto stage_mask = [&](int bb) {
+#pragma unroll
+        for (int h = 0; h < EPT; ++h) {
+            const int t = tid + h * RB2;
+            unsigned mask = 0;
+            if (top - BATCH * bb - t >= range.x) {
+                const float4 q0 = st[bb & 1].A[t];
+                const float2 q1 = *reinterpret_cast<const float2 *>(&st[bb & 1].B[t]);
+                mask = CULL ? cull_mask16(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, tile_x0, tile_y0) : 0xFFu;
+            }
+            st[bb & 1].M[t] = (unsigned char)(mask | (mask >> 2));
+        }
+    };
+    unsigned gn[EPT];
+#pragma unroll
+    for (int h = 0; h < EPT; ++h) issue(0, h, load_id(0, h));
+#pragma unroll
+    for (int h = 0; h < EPT; ++h) gn[h] = load_id(1, h);
+    cp_async_wait_all();
+    stage_mask(0);
+    __syncthreads();  // records, ids and masks of batch 0 are visible
+    if (1 < num_batches) {
+#pragma unroll
+        for (int h = 0; h < EPT; ++h) issue(1, h, gn[h]);
+    }
+#pragma unroll
+    for (int h = 0; h < EPT; ++h) gn[h] = load_id(2, h);
+
+    // The cross-lane reduction of a visit is deferred into the NEXT visit: its shared-memory reads,
+    // adds, shuffle and RED have nothing to do with that visit's sigma / alpha arithmetic, so in
+    // one straight-line block the scheduler overlaps the two latency chains (the reduction tail
+    // held 27 % of the kernel's stall samples when it ran at the end of its own visit).
+    bool pend = false;       // `red` holds the partials of a visit that is not reduced yet
+    unsigned pend_id = 0;    // its Gaussian
+    const float4 *red_row = reinterpret_cast<const float4 *>(
+        red + min(lane >> 1, NV - 1) * RED_STRIDE + (lane & 1) * 16);
+    auto reduce_rows = [&]() -> float {
+        const float4 p0 = red_row[0], p1 = red_row[1], p2 = red_row[2], p3 = red_row[3];
+        float2 u0 = __fadd2_rn(f2(p0.x, p0.y), f2(p0.z, p0.w));
+        float2 u1 = __fadd2_rn(f2(p1.x, p1.y), f2(p1.z, p1.w));
+        float2 u2 = __fadd2_rn(f2(p2.x, p2.y), f2(p2.z, p2.w));
+        float2 u3 = __fadd2_rn(f2(p3.x, p3.y), f2(p3.z, p3.w));
+        u0 = __fadd2_rn(u0, u1);
+        u2 = __fadd2_rn(u2, u3);
+        u0 = __fadd2_rn(u0, u2);
+        return u0.x + u0.y;
+    };
+
+    for (int b = 0; b < num_batches; ++b) {
+        const int batch_end = top - BATCH * b;  // slot t holds sorted index batch_end - t
+        const Stage &S = st[b & 1];
+#pragma unroll 1
+        for (int k = 0; k < BATCH / 32; ++k) {
+            // entries newer than the warp's largest final index cannot be valid for any lane
+            if (batch_end - (k * 32 + 31) > wmax) continue;
+            const unsigned m = S.M[k * 32 + lane];
+            unsigned bits = __ballot_sync(0xffffffffu, (m >> qbit) & 1u);
+            while (bits) {
+                const int t = k * 32 + __ffs(bits) - 1;
+                bits &= bits - 1;
+                const float4 a = S.A[t];    // {x, y, opacity, cx}
+                const float4 bq = S.B[t];   // {cy, cz, r, g}
+                float total = reduce_rows();  // previous visit's partials (stale rows if !pend)
+                // conic_sigma (common.cuh) lane by lane, in the reference's operation order
+                const float dx = fsub(a.x, px);
+                const float2 dy2 = __fadd2_rn(bc(a.y), npy2);
+                const float ca = fmul(a.w, dx);                        // cx dx
+                const float ce = fmul(bq.x, dx);                       // cy dx
+                const float2 b2 = __fmul2_rn(bc(bq.y), dy2);           // cz dy
+                const float2 c2 = __fmul2_rn(dy2, b2);
+                float2 s2 = __ffma2_rn(bc(dx), bc(ca), c2);
+                s2 = __fmul2_rn(s2, bc(0.5f));
+                const float2 sg2 = __ffma2_rn(bc(ce), dy2, s2);
+                const float2 x2 = __fmul2_rn(sg2, bc(kNegLog2e));
+                const float vis0 = ex2_approx(x2.x), vis1 = ex2_approx(x2.y);
+                const float2 ar2 = __fmul2_rn(bc(a.z), f2(vis0, vis1));  // opacity * vis
+                const float al0 = fminf(ar2.x, 0.99f), al1 = fminf(ar2.y, 0.99f);
+                const int sidx = batch_end - t;
+                const bool ok0 = in0 && (sidx <= bf0) && !(sg2.x < 0.f) && !(al0 < kAlphaMin);
+                const bool ok1 = in1 && (sidx <= bf1) && !(sg2.y < 0.f) && !(al1 < kAlphaMin);
+                total += __shfl_xor_sync(0xffffffffu, total, 1);
+                if (writer && pend) atomicAdd(out_base + pend_id * (unsigned)out_stride, total);
+                pend = false;
+                if (!__any_sync(0xffffffffu, ok0 || ok1)) continue;
+
+                // invalid pixels: alpha = opacity*vis = 0 and ra = 1 make every partial exactly 0
+                // and leave T and the colour buffer unchanged
+                const float2 al2 = f2(ok0 ? al0 : 0.f, ok1 ? al1 : 0.f);
+                const float2 av2 = f2(ok0 ? ar2.x : 0.f, ok1 ? ar2.y : 0.f);   // opacity * vis
+                const float2 vis2 = f2(ok0 ? vis0 : 0.f, ok1 ? vis1 : 0.f);
+                const float2 om2 = __ffma2_rn(al2, bc(-1.f), bc(1.f));         // 1 - alpha
+                float r0, r1;
+                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(om2.x));
+                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(om2.y));
+                const float2 ra2 = f2(ok0 ? r0 : 1.f, ok1 ? r1 : 1.f);
+                const float cb = S.C[t];
+                T2 = __fmul2_rn(T2, ra2);
+                const float2 fac2 = __fmul2_rn(al2, T2);
+                // v_alpha = sum_c v_out_c (T c_c - buf_c ra) + tfc ra
+                //         = T <v_out, c> + ra (tfc - <v_out, buf>)
+                float2 P2 = __fmul2_rn(vox2, bc(bq.z));
+                P2 = __ffma2_rn(voy2, bc(bq.w), P2);
+                P2 = __ffma2_rn(voz2, bc(cb), P2);
+                float2 Q2 = __ffma2_rn(nvox2, bufx2, tfc2);
+                Q2 = __ffma2_rn(nvoy2, bufy2, Q2);
+                Q2 = __ffma2_rn(nvoz2, bufz2, Q2);
+                const float2 va2 = __ffma2_rn(ra2, Q2, __fmul2_rn(T2, P2));
+                bufx2 = __ffma2_rn(fac2, bc(bq.z), bufx2);
+                bufy2 = __ffma2_rn(fac2, bc(bq.w), bufy2);
+                bufz2 = __ffma2_rn(fac2, bc(cb), bufz2);
+                // v_sigma = -opacity vis v_alpha
+                const float2 pv2 = __fmul2_rn(av2, va2);
+                const float2 vs2 = __fmul2_rn(pv2, bc(-1.f));
+                const float2 hs2 = __fmul2_rn(pv2, bc(-0.5f));
+                const float2 dxv2 = __fmul2_rn(bc(dx), vs2);    // dx v_sigma
+                float2 o2[9];
+                o2[0] = __fmul2_rn(vox2, fac2);
+                o2[1] = __fmul2_rn(voy2, fac2);
+                o2[2] = __fmul2_rn(voz2, fac2);
+                o2[3] = __fmul2_rn(bc(dx * dx), hs2);
+                o2[4] = __fmul2_rn(dy2, dxv2);
+                o2[5] = __fmul2_rn(dy2, __fmul2_rn(dy2, hs2));
+                o2[6] = __ffma2_rn(__fmul2_rn(dy2, bc(bq.x)), vs2, __fmul2_rn(bc(ca), vs2));  // (cx dx + cy dy) v_sigma
+                o2[7] = __fmul2_rn(__fadd2_rn(bc(ce), b2), vs2);                               // (cy dx + cz dy) v_sigma
+                o2[8] = __fmul2_rn(vis2, va2);
+                float v[NV];
+#pragma unroll
+                for (int r = 0; r < 9; ++r) v[r] = o2[r].x + o2[r].y;
+                if (ABS) {
+                    v[9] = fabsf(o2[6].x) + fabsf(o2[6].y);
+                    v[10] = fabsf(o2[7].x) + fabsf(o2[7].y);
+                }
+                // transpose through shared memory: row r = value r of the 32 lanes
+                __syncwarp();
+#pragma unroll
+                for (int r = 0; r < NV; ++r) red[r * RED_STRIDE + lane] = v[r];
+                __syncwarp();
+                pend = true;
+                pend_id = S.Id[t];
+            }
+        }
+        if (b + 1 >= num_batches) break;
+        // this thread's entries of batch b+1 have landed: their masks; then the ONE barrier of the
+        // batch -- every warp is done with batch b (its buffers are free) and batch b+1 is visible
+        cp_async_wait_all();
+        stage_mask(b + 1);
+        __syncthreads();
+        if (b + 2 < num_batches) {
+#pragma unroll
+            for (int h = 0; h < EPT; ++h) issue(b + 2, h, gn[h]);
+        }
+#pragma unroll
+        for (int h = 0; h < EPT; ++h) gn[h] = load_id(b + 3, h);
+    }
+    if (pend) {  // warp-uniform: the last visit of this warp
+        float total = reduce_rows();
+        total += __shfl_xor_sync(0xffffffffu, total, 1);
+        if (writer) atomicAdd(out_base + pend_id * (unsigned)out_stride, total);
+    }
+}
+
 // any block_width: one thread per pixel, per-thread atomics (semantics only, not tuned)
 __global__ void raster_bwd_generic_kernel(
     const RasterParams p, const unsigned *__restrict__ ids_sorted,
@@ -748,6 +1014,7 @@ __global__ void raster_bwd_generic_kernel(
 extern bool g_disable_cull;
 bool g_bwd_one_pixel = false;  // option "bwd2px" = 0: the one-pixel-per-thread kernel
 bool g_bwd_scalar = false;     // option "bwdpk" = 0: the two-pixel kernel with scalar FP32 math
+bool g_bwd_one_barrier = false;  // option "bwd1bar" = 1 (experimental): one barrier per batch
 
 template <bool CULL, bool ABS>
 static void launch_x2(cudaStream_t stream, unsigned tiles, const RasterParams &p,
@@ -755,7 +1022,11 @@ static void launch_x2(cudaStream_t stream, unsigned tiles, const RasterParams &p
                       const float *background, const float *final_Ts, const int *final_idx,
                       const float *v_out, const float *v_out_alpha, float *v_xy, float *v_xy_abs,
                       float *v_conic, float *v_colors, float *v_opacity) {
-    if (g_bwd_scalar)
+    if (g_bwd_one_barrier && !g_bwd_scalar)
+        raster_bwd16x2ps_kernel<CULL, ABS><<<tiles, RB2, 0, stream>>>(
+            p, ids_sorted, tile_bins, records, background, final_Ts, final_idx, v_out, v_out_alpha,
+            v_xy, v_xy_abs, v_conic, v_colors, v_opacity);
+    else if (g_bwd_scalar)
         raster_bwd16x2_kernel<CULL, ABS><<<tiles, RB2, 0, stream>>>(
             p, ids_sorted, tile_bins, records, background, final_Ts, final_idx, v_out, v_out_alpha,
             v_xy, v_xy_abs, v_conic, v_colors, v_opacity);

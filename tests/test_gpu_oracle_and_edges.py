@@ -461,3 +461,29 @@ def test_one_barrier_forward_is_bit_identical(scene_fn):
         assert torch.equal(a["final_idx"], b["final_idx"])
         assert torch.equal(a["final_Ts"].view(torch.int32), b["final_Ts"].view(torch.int32))
         assert torch.equal(a["img"].view(torch.int32), b["img"].view(torch.int32))
+
+
+@_experimental
+@pytest.mark.parametrize("scene_fn", [_adversarial_scene, lambda: synthetic.make_config("C2", num_points=30000),
+                                      lambda: synthetic.benchmark_scene(9000, (200, 120), scale_max=0.2, seed=21),
+                                      lambda: synthetic.benchmark_scene(60, (40, 40), scale_max=0.3, seed=3)])
+def test_one_barrier_backward_equals_the_default_kernel(scene_fn):
+    """option "bwd1bar": raster_bwd16x2ps_kernel (one CTA barrier per batch) against the default
+    packed kernel: the same visits with the same arithmetic, so the only difference left is the
+    order in which the atomics of different tiles land (the reference's own run-to-run noise)"""
+    s = scene_fn()
+    inp = G.scene_inputs(s)
+    kw, rkw = G.scene_kw(s)
+    H, W = s.img_shape
+    target = np.random.RandomState(2).rand(H, W, 3).astype(np.float32)
+    v_alpha = np.random.RandomState(3).rand(H, W, 1).astype(np.float32) * 1e-3
+    try:
+        _lib.set_option("bwd1bar", 1)
+        a = _full_gpu(inp, kw, rkw, target, v_alpha)
+        _lib.set_option("bwd1bar", 0)
+        b = _full_gpu(inp, kw, rkw, target, v_alpha)
+    finally:
+        _lib.set_option("bwd1bar", 0)
+    for k in ("v_colors", "v_opacity", "v_xy", "v_xy_abs", "v_conic"):
+        ok, err, scale = grad_close(a[k], b[k], rel=2e-5)
+        assert ok, (k, err, scale)

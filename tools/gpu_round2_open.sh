@@ -18,6 +18,7 @@ JSB_EXPERIMENTAL=1 timeout 300 python -m pytest tests -m gpu -q -k "live_bit or 
 tail -3 $OUT/${TAG}_pytest_sortlive.log
 JSB_SORTLIVE=1 timeout 300 python bench.py --steps 100 --warmup 10 --no-cpu-baseline > $OUT/${TAG}_bench_sortlive.json 2> $OUT/${TAG}_bench_sortlive.err
 JSB_FWD1BAR=1 timeout 300 python bench.py --steps 100 --warmup 10 --no-cpu-baseline > $OUT/${TAG}_bench_fwd1bar.json 2> $OUT/${TAG}_bench_fwd1bar.err
+JSB_BWD1BAR=1 timeout 300 python bench.py --steps 100 --warmup 10 --no-cpu-baseline > $OUT/${TAG}_bench_bwd1bar.json 2> $OUT/${TAG}_bench_bwd1bar.err
 for C in C3s C3b; do
   timeout 400 python bench.py --config $C --steps 50 --warmup 5 --no-cpu-baseline > $OUT/${TAG}_bench_$C.json 2> $OUT/${TAG}_bench_$C.err
   timeout 400 python bench.py --config $C --impl reference --steps 10 --warmup 3 > $OUT/${TAG}_bench_reference_$C.json 2> $OUT/${TAG}_bench_reference_$C.err
