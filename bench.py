@@ -19,6 +19,8 @@ symmetric buffer (jaxsplat_b200.set_gradient_sink) that is summed with one all-r
   e2e    : same step, but the step's host inputs (target image + camera, pinned) are copied H2D
            and the loss is read back D2H inside the timed region (wall clock around K steps);
            the copy of step k+1 runs on a copy stream under step k
+  JSB_BENCH_OVERLAP=1 (N > 1, experimental, off by default): the appearance gradients' share of
+           the all-reduce runs on a side stream under the projection backward
   --impl reference : the UNMODIFIED reference CUDA library (oracle/_ref, built from
            /root/reference/lib by oracle/Makefile) driven through the same harness on rank 0.
 """
@@ -207,6 +209,18 @@ def main():
             off += q.numel()
         jsb.set_gradient_sink(sink_views + [flat_scratch])
     sink_ok = [False]
+    # EXPERIMENTAL (JSB_BENCH_OVERLAP=1, written without GPU access, not yet run on GPUs): the
+    # appearance gradients (colors + opacities: the last 4N of the 14N floats) are final when the
+    # rasteriser backward ends, so their share of the all-reduce runs on a side stream under the
+    # projection backward; the library records `ev_app` between its two backward kernels
+    overlap = (use_dist and reducer is not None and sink_views is not None
+               and os.environ.get("JSB_BENCH_OVERLAP") == "1" and N % 4 == 0)
+    if overlap:
+        side = torch.cuda.Stream(device=dev)
+        ev_app, ev_side = torch.cuda.Event(), torch.cuda.Event()
+        ev_app.record()   # materialises the CUDA handle
+        ev_side.record()
+        _lib.set_raster_bwd_event(ev_app)
 
     def step(view, tgt):
         for q in params:
@@ -228,7 +242,15 @@ def main():
                     q.grad.data_ptr() == v.data_ptr() for q, v in zip(params, sink_views))
             if not sink_ok[0]:
                 torch.cat([q.grad.reshape(-1) for q in params], out=flat_g)
-            if reducer is not None:
+            if overlap and sink_ok[0]:
+                main = torch.cuda.current_stream()
+                side.wait_event(ev_app)          # recorded inside the backward, after raster_bwd
+                with torch.cuda.stream(side):
+                    reducer.all_reduce_range(10 * N, 4 * N, channel=1)
+                    ev_side.record(side)
+                reducer.all_reduce_range(0, 10 * N, channel=0)   # after project_bwd, main stream
+                main.wait_event(ev_side)         # the step ends when both halves are reduced
+            elif reducer is not None:
                 reducer.all_reduce()
             else:
                 dist.all_reduce(flat_g)
@@ -354,7 +376,9 @@ def main():
                    "num_intersects": I, "parallelism": (f"view-parallel dp{world}, gradient all-reduce: "
                                    f"{reducer.mode if reducer is not None else 'nccl'}, gradients "
                                    f"{'written in place into' if sink_ok[0] else 'packed (torch.cat) into'} "
-                                   "the reduced buffer") if world > 1 else "single GPU",
+                                   "the reduced buffer"
+                                   + (", appearance gradients reduced on a side stream under project_bwd"
+                                      if world > 1 and overlap else "")) if world > 1 else "single GPU",
                    "l2": "per-step working set ~0.5 GB (keys/ids ping-pong 0.2 GB, records, images, "
                          "parameters, gradients) exceeds the 126 MB L2; no explicit flush",
                    "timing": "CUDA events around exactly K steps, barrier+synchronize both sides, max over ranks"},

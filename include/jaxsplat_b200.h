@@ -193,6 +193,13 @@ JSB200_API void jsb200_get_stats(unsigned long long *out8);
 /* releases every workspace (all devices/streams). */
 JSB200_API void jsb200_release(void);
 
+/* Registers a CUDA event (cudaEvent_t, or NULL to clear) that jsb200_render_bwd records on its
+ * stream between its two kernels, i.e. at the point where v_colors and v_opacity are final and
+ * only the projection backward is left: a data-parallel driver can wait on it from a second stream
+ * and reduce those two gradients across GPUs while the projection backward still runs.
+ * Process-wide (one process drives one GPU); the batched-camera calls do not record it. */
+JSB200_API int jsb200_set_raster_bwd_event(void *cuda_event);
+
 /* ---- multi-GPU (no reference equivalent: yklcs/jaxsplat is single-device) ----
  * In-place sum of n_floats floats across the `world` ranks of one NVSwitch node, in ONE kernel:
  * every rank's buffer is the same symmetric allocation, mapped peer-to-peer (peer_bases[r] = rank

@@ -58,6 +58,9 @@ extern bool g_bwd_one_barrier;
 static bool g_disable_cache = false;
 static bool g_disable_rowcol = false;
 static bool g_sort_live = false;  // option "sortlive": depth sort on the live bits of key - min
+// jsb200_set_raster_bwd_event: recorded by the fused render backward between its two kernels
+// (process-wide: autograd runs the backward on its own thread, so not thread-local)
+static std::atomic<cudaEvent_t> g_raster_bwd_event{nullptr};
 static unsigned g_view_slots = 8;  // binning workspaces a batched-camera call cycles through
 
 // ---- optional per-stage device timing (jsb200_set_option("timing", 1)) -------------------------
@@ -759,6 +762,11 @@ static int render_bwd_impl(cudaStream_t stream, void **buf, const Descriptor &d,
             return 1;
     }
     }
+    // v_colors / v_opacity are final from here on (project_bwd only produces the other three): a
+    // data-parallel driver may start reducing them on another stream under project_bwd
+    if (slot == 0 && !keep_appearance) {
+        if (cudaEvent_t ev = g_raster_bwd_event.load()) JSB_CUDA_OK(cudaEventRecord(ev, stream));
+    }
     // project_bwd with zero cotangents for depth and compensation (render uses neither)
     void *pbuf[18] = {buf[0], buf[1], buf[2], buf[3], buf[7], buf[8], buf[10], buf[11], buf[12],
                       nullptr, buf[22], nullptr, buf[23], buf[17], buf[18], buf[19], buf[24], buf[25]};
@@ -1066,6 +1074,11 @@ int jsb200_cumsum(jsb200_stream_t stream_, const int *input, int *output, int nu
 const char *jsb200_last_error(void) { return jsb::t_has_error ? jsb::t_error.c_str() : nullptr; }
 void jsb200_clear_error(void) { jsb::t_has_error = false; jsb::t_error.clear(); }
 unsigned long long jsb200_error_count(void) { return jsb::g_error_count.load(); }
+
+int jsb200_set_raster_bwd_event(void *cuda_event) {
+    jsb::g_raster_bwd_event.store((cudaEvent_t)cuda_event);
+    return 0;
+}
 
 int jsb200_set_option(const char *key, int value) {
     if (!key) return 1;
