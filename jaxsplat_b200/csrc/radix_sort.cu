@@ -135,10 +135,15 @@ radix_hist_live_kernel(const unsigned *__restrict__ keys, unsigned n,
     __syncthreads();
     unsigned kmin, span;
     live_range(mm, kmin, span);
+    // identity passes need no histogram -- and theirs would be the worst one to build: every key
+    // increments the same shared-memory word (bin 0)
+    int live_passes = 0;
+    while (live_passes < MAX_PASSES && (span >> (8 * live_passes)) != 0u) ++live_passes;
     auto count = [&](unsigned k) {
         const unsigned r = live_rebase(k, kmin, span);
 #pragma unroll
-        for (int ps = 0; ps < MAX_PASSES; ++ps) atomicAdd(&s_h[ps * RADIX + ((r >> (8 * ps)) & 255u)], 1u);
+        for (int ps = 0; ps < MAX_PASSES; ++ps)
+            if (ps < live_passes) atomicAdd(&s_h[ps * RADIX + ((r >> (8 * ps)) & 255u)], 1u);
     };
     const unsigned nvec = n / 4;
     const unsigned stride = gridDim.x * 256u;
