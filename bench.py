@@ -222,6 +222,12 @@ def main():
         ev_side.record()
         _lib.set_raster_bwd_event(ev_app)
 
+    # JSB_BENCH_NATIVE_LOSS=1 (experimental, not yet run on a GPU, off by default): the MSE and its
+    # cotangent from one kernel of the library (csrc/loss.cu) instead of three torch kernels
+    native_loss = args.impl == "ours" and os.environ.get("JSB_BENCH_NATIVE_LOSS") == "1"
+    if native_loss:
+        from jaxsplat_b200 import losses
+
     def step(view, tgt):
         for q in params:
             q.grad = None  # optimizer.zero_grad(set_to_none=True): no memset, no accumulate pass
@@ -230,10 +236,14 @@ def main():
         img = jsb.render(*params, **k)
         # MSE and its gradient written out by hand (sub, dot, scale instead of the 9 kernels that
         # autograd launches for ((img - tgt) ** 2).mean()); the render backward is autograd's
-        diff = img.detach() - tgt
-        flat = diff.view(-1)
-        loss = torch.dot(flat, flat) / flat.numel()
-        img.backward(gradient=diff * (2.0 / diff.numel()))
+        if native_loss:  # (EXPERIMENTAL switch: loss + cotangent in one native kernel)
+            loss, v_img = losses.mse_loss_and_grad(img.detach(), tgt)
+            img.backward(gradient=v_img)
+        else:
+            diff = img.detach() - tgt
+            flat = diff.view(-1)
+            loss = torch.dot(flat, flat) / flat.numel()
+            img.backward(gradient=diff * (2.0 / diff.numel()))
         if use_dist:
             # the five parameter gradients in the one flat (symmetric) buffer, summed over the
             # ranks in a single call

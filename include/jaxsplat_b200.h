@@ -222,6 +222,14 @@ JSB200_API int jsb200_adam_step(jsb200_stream_t stream, float *param, const floa
                                 float *v, size_t n, float lr, float b1, float b2, float eps,
                                 unsigned long long step);
 
+/* Mean-squared-error loss and its gradient in one streaming kernel (the loss of the reference's
+ * examples/single_image.py:21-30 and of the benchmark metric: mean((img - target)^2)):
+ * v_img[i] = (img[i] - target[i]) * scale (pass scale = 2 / n for d loss / d img), and
+ * *loss = sum_i (img[i] - target[i])^2 / n (device float, cleared inside; summed with one atomic
+ * per CTA, so its last bits depend on the order in which the CTAs finish).  Returns 0 on success. */
+JSB200_API int jsb200_mse_loss_grad(jsb200_stream_t stream, const float *img, const float *target,
+                                    size_t n, float scale, float *v_img, float *loss);
+
 #ifdef __cplusplus
 }
 #endif

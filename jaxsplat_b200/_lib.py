@@ -42,6 +42,7 @@ EXPORTS = (
     "jsb200_set_raster_bwd_event",
     "jsb200_multimem_allreduce_f32",
     "jsb200_adam_step",
+    "jsb200_mse_loss_grad",
 )
 
 _lib = None
@@ -114,6 +115,8 @@ def lib() -> ctypes.CDLL:
     L.jsb200_multimem_allreduce_f32.restype = i
     L.jsb200_adam_step.argtypes = [vp, vp, vp, vp, vp, sz, f, f, f, f, ctypes.c_ulonglong]
     L.jsb200_adam_step.restype = i
+    L.jsb200_mse_loss_grad.argtypes = [vp, vp, vp, sz, f, vp, vp]
+    L.jsb200_mse_loss_grad.restype = i
     _lib = L
     return L
 

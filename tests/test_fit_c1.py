@@ -91,3 +91,25 @@ def test_config1_fit_with_the_native_adam_step():
     got = fit_util.fit_gpu(scene, target, steps=30, native_adam=True)
     for k in (0, 1, 10, 29):
         assert abs(got[k] - ref[k]) <= 2e-3 * ref[k], (k, got[k], ref[k])
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(__import__("os").environ.get("JSB_EXPERIMENTAL") != "1",
+                    reason="experimental kernel, not yet verified on a GPU")
+def test_native_mse_loss_and_gradient_match_torch():
+    """losses.mse_loss_and_grad (one kernel) against the eager expressions: the cotangent bit for
+    bit, the loss to float tolerance; sizes that are and are not multiples of 4, a misaligned view"""
+    import torch
+    from jaxsplat_b200.losses import mse_loss_and_grad
+    gen = torch.Generator().manual_seed(5)
+    for shape, off in (((1080, 1920, 3), 0), ((37, 53, 3), 0), ((5,), 0), ((64, 64, 3), 1)):
+        n = 1
+        for d in shape:
+            n *= d
+        a = torch.rand(n + off, generator=gen).cuda()[off:].view(shape)
+        b = torch.rand(n + off, generator=gen).cuda()[off:].view(shape)
+        loss, v = mse_loss_and_grad(a, b)
+        diff = a - b
+        assert torch.equal(v, diff * (2.0 / diff.numel()))
+        ref = float((diff.double() ** 2).mean())
+        assert abs(float(loss) - ref) <= 1e-5 * ref

@@ -14,10 +14,11 @@ tail -3 $OUT/${TAG}_pytest.log
 timeout 600 python bench.py > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err
 timeout 300 python bench.py --impl reference --steps 30 --warmup 5 > $OUT/${TAG}_bench_reference.json 2> $OUT/${TAG}_bench_reference.err
 # the experimental options (written without a GPU): their parity tests, then the A/B lines
-JSB_EXPERIMENTAL=1 timeout 300 python -m pytest tests -m gpu -q -k "live_bit or one_barrier or raster_bwd_event" > $OUT/${TAG}_pytest_sortlive.log 2>&1
+JSB_EXPERIMENTAL=1 timeout 300 python -m pytest tests -m gpu -q -k "live_bit or one_barrier or raster_bwd_event or native_mse" > $OUT/${TAG}_pytest_sortlive.log 2>&1
 tail -3 $OUT/${TAG}_pytest_sortlive.log
 JSB_SORTLIVE=1 timeout 300 python bench.py --steps 100 --warmup 10 --no-cpu-baseline > $OUT/${TAG}_bench_sortlive.json 2> $OUT/${TAG}_bench_sortlive.err
 JSB_FWD1BAR=1 timeout 300 python bench.py --steps 100 --warmup 10 --no-cpu-baseline > $OUT/${TAG}_bench_fwd1bar.json 2> $OUT/${TAG}_bench_fwd1bar.err
+JSB_BENCH_NATIVE_LOSS=1 timeout 300 python bench.py --steps 100 --warmup 10 --no-cpu-baseline > $OUT/${TAG}_bench_nativeloss.json 2> $OUT/${TAG}_bench_nativeloss.err
 JSB_BWD1BAR=1 timeout 300 python bench.py --steps 100 --warmup 10 --no-cpu-baseline > $OUT/${TAG}_bench_bwd1bar.json 2> $OUT/${TAG}_bench_bwd1bar.err
 for C in C3s C3b; do
   timeout 400 python bench.py --config $C --steps 50 --warmup 5 --no-cpu-baseline > $OUT/${TAG}_bench_$C.json 2> $OUT/${TAG}_bench_$C.err
