@@ -24,6 +24,11 @@ for C in C3s C3b; do
   timeout 400 python bench.py --config $C --steps 50 --warmup 5 --no-cpu-baseline > $OUT/${TAG}_bench_$C.json 2> $OUT/${TAG}_bench_$C.err
   timeout 400 python bench.py --config $C --impl reference --steps 10 --warmup 3 > $OUT/${TAG}_bench_reference_$C.json 2> $OUT/${TAG}_bench_reference_$C.err
 done
+# reference kernel-time baseline: launch list of the reference arm's C3 step
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file $OUT/${TAG}_reference_launches_C3.csv python bench.py --impl reference --steps 2 --warmup 1 > $OUT/${TAG}_reference_ncu.log 2>&1
+# depth sort vs CUB on the same keys
+timeout 120 tools/microbench/depth_sort_vs_cub 1000000 200 > $OUT/${TAG}_depth_sort_vs_cub.json 2> $OUT/${TAG}_depth_sort_vs_cub.err
+timeout 120 tools/microbench/depth_sort_vs_cub 3000000 100 >> $OUT/${TAG}_depth_sort_vs_cub.json 2>> $OUT/${TAG}_depth_sort_vs_cub.err
 timeout 400 python tools/multigpu_bench.py views --steps 3 --warmup 2 > $OUT/${TAG}_views_C4_1gpu.json 2> $OUT/${TAG}_views_C4_1gpu.err
 timeout 400 python tools/multigpu_bench.py bands --steps 5 --warmup 2 > $OUT/${TAG}_bands_C5_1gpu.json 2> $OUT/${TAG}_bands_C5_1gpu.err
 python - <<EOF
