@@ -14,7 +14,7 @@ symmetric buffer (jaxsplat_b200.set_gradient_sink) that is summed with one all-r
 
   value  : views/s, whole job, parameters/targets resident in HBM (CUDA events, max over ranks);
            the library's per-stage events are OFF during these K steps
-  stages / roofline / issue : per-stage device times from a separate pass of the same step with
+  stages / roofline / pairs : per-stage device times from a separate pass of the same step with
            the stage events on (outside the timed region)
   e2e    : same step, but the step's host inputs (target image + camera, pinned) are copied H2D
            and the loss is read back D2H inside the timed region (wall clock around K steps);
@@ -28,7 +28,6 @@ import argparse
 import json
 import os
 import statistics
-import subprocess
 import sys
 import threading
 import time
@@ -51,54 +50,77 @@ def parse():
 
 
 class ClockSampler:
-    """samples nvidia-smi clocks / throttle reasons while the timed region runs"""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """Samples SM clock / throttle reasons in-process through NVML every few milliseconds from a
+    thread that runs from before the warm-up to after the timed region; `mark()` brackets the timed
+    region so that the reported median is taken under load (nvidia-smi -lms 100 saw 0-2 samples of
+    a 170 ms region)."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
+               0x4: "sw_power_cap"}
 
-    def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+    def __init__(self, torch_device, period_s=0.004):
+        self.samples, self.marks, self.stop_flag, self.thread = [], [], False, None
+        self.period, self.err, self.h, self.nv = period_s, None, None, None
+        try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            try:
+                uuid = "GPU-" + str(torch.cuda.get_device_properties(torch_device).uuid)
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+            except Exception:
+                vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+                idx = torch_device.index or 0
+                if vis:
+                    idx = int(vis.split(",")[idx])
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception as ex:  # no NVML: report it, never fail the bench
+            self.err = f"{type(ex).__name__}: {ex}"
+
+    def _run(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                mhz = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    reasons = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    reasons = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.samples.append((time.perf_counter(), mhz, reasons))
+            except Exception as ex:
+                self.err = f"{type(ex).__name__}: {ex}"
+                return
+            time.sleep(self.period)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms",
-                 "100", "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
-                text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+        if self.h is not None:
+            self.thread = threading.Thread(target=self._run, daemon=True)
             self.thread.start()
-        except Exception:
-            self.proc = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+    def mark(self):
+        self.marks.append(time.perf_counter())
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            parts = [p.strip() for p in ln.split(",")]
-            if len(parts) < 9:
-                continue
-            try:
-                sm.append(float(parts[1]))
-                mx.append(float(parts[2]))
-            except ValueError:
-                continue
-            for name, val in zip(names, parts[5:9]):
-                if val.lower().startswith("active"):
+        self.stop_flag = True
+        if self.thread:
+            self.thread.join(timeout=1.0)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [self.err or "no NVML samples"],
+                    "samples": 0}
+        lo, hi = (self.marks + [0.0, 1e30])[:2] if len(self.marks) >= 2 else (0.0, 1e30)
+        inside = [s for s in self.samples if lo <= s[0] <= hi]
+        where = "timed region"
+        if len(inside) < 3:  # a very short timed region: fall back to warm-up + timed region
+            inside, where = self.samples, "warm-up + timed region"
+        reasons = set()
+        for _, _, r in inside:
+            for bit, name in self.REASONS.items():
+                if r & bit:
                     reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None,
-                "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        return {"sm_mhz": statistics.median(s[1] for s in inside), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(reasons), "samples": len(inside), "sampled_over": where,
+                "source": "NVML in-process, %.0f ms period" % (self.period * 1e3)}
 
 
 def algorithmic_bytes(stage, N, I, P, T, rows=0, tiles_x=120):
@@ -122,6 +144,38 @@ def algorithmic_bytes(stage, N, I, P, T, rows=0, tiles_x=120):
         "raster_bwd": P * 24 + N * 48 + I * 4 + N * 36,
         "project_bwd": N * 188,
     }[stage]
+
+
+def useful_pairs(sc, kw):
+    """U_f = sum_p max(0, final_idx[p] + 1 - tile_bins[tile(p)].x), from the outputs of
+    one forward (outside every timed region)."""
+    import ctypes
+
+    import torch
+
+    from jaxsplat_b200 import _lib, _ops
+    H, W = sc.img_shape
+    bs = sc.block_size
+    n = sc.means3d.shape[0]
+    outs, _tok = _ops.render_fwd(sc.means3d, sc.scales, sc.quats, sc.viewmat, sc.colors, sc.opacities,
+                                 sc.background, num_points=n, img_shape=sc.img_shape, f=sc.f, c=sc.c,
+                                 glob_scale=sc.glob_scale, clip_thresh=sc.clip_thresh, block_width=bs)
+    final_idx = outs[7].view(H, W).long()
+    tx, ty = (W + bs - 1) // bs, (H + bs - 1) // bs
+    bins = torch.zeros((tx * ty, 2), dtype=torch.int32, device=final_idx.device)
+    got = _lib.lib().jsb200_debug_binning(ctypes.c_void_p(torch.cuda.current_stream().cuda_stream),
+                                          None, None, ctypes.c_void_p(bins.data_ptr()), None)
+    torch.cuda.synchronize()
+    if got < 0:
+        _lib.lib().jsb200_clear_error()
+        return None
+    first = bins[:, 0].long().view(ty, tx)
+    count = (bins[:, 1] - bins[:, 0]).long().view(ty, tx)
+    first_px = first.repeat_interleave(bs, 0).repeat_interleave(bs, 1)[:H, :W]
+    count_px = count.repeat_interleave(bs, 0).repeat_interleave(bs, 1)[:H, :W]
+    u = (final_idx + 1 - first_px).clamp(min=0)
+    u = torch.where(count_px > 0, u, torch.zeros_like(u))
+    return int(u.sum().item())
 
 
 def main():
@@ -178,12 +232,10 @@ def main():
         for key in ("bwdpk", "fwdpk"):  # packed FP32x2 rasterisers (A/B: tools/gpu_pk.sh)
             if os.environ.get("JSB_" + key.upper()) == "0":
                 _lib.set_option(key, 0)
-        if os.environ.get("JSB_FWD1BAR") == "1":  # experimental one-barrier forward rasteriser
-            _lib.set_option("fwd1bar", 1)
-        if os.environ.get("JSB_BWD1BAR") == "1":  # experimental one-barrier backward rasteriser
-            _lib.set_option("bwd1bar", 1)
-        if os.environ.get("JSB_SORTLIVE") == "1":  # experimental live-bit depth sort
-            _lib.set_option("sortlive", 1)
+        if os.environ.get("JSB_BWDHITS") == "0":  # per-tile batch backward instead of the hit-driven one
+            _lib.set_option("bwdhits", 0)
+        if os.environ.get("JSB_SORT1K") == "0":  # four onesweep passes instead of the resident sort
+            _lib.set_option("sort1k", 0)
         if os.environ.get("JSB_FUSED") == "0":
             jsb.set_fused_render(False)
     # N > 1: the five gradients are packed into one flat symmetric buffer so the all-reduce is a
@@ -222,9 +274,10 @@ def main():
         ev_side.record()
         _lib.set_raster_bwd_event(ev_app)
 
-    # JSB_BENCH_NATIVE_LOSS=1 (experimental, not yet run on a GPU, off by default): the MSE and its
-    # cotangent from one kernel of the library (csrc/loss.cu) instead of three torch kernels
-    native_loss = args.impl == "ours" and os.environ.get("JSB_BENCH_NATIVE_LOSS") == "1"
+    # the MSE and its cotangent come from one kernel of the library (csrc/loss.cu: 0.841 vs 0.859 ms
+    # per step, profiles/r02a_bench_nativeloss.json); JSB_BENCH_NATIVE_LOSS=0 = three torch kernels
+    # (the reference arm always uses those: its library has no loss kernel)
+    native_loss = args.impl == "ours" and os.environ.get("JSB_BENCH_NATIVE_LOSS") != "0"
     if native_loss:
         from jaxsplat_b200 import losses
 
@@ -236,7 +289,7 @@ def main():
         img = jsb.render(*params, **k)
         # MSE and its gradient written out by hand (sub, dot, scale instead of the 9 kernels that
         # autograd launches for ((img - tgt) ** 2).mean()); the render backward is autograd's
-        if native_loss:  # (EXPERIMENTAL switch: loss + cotangent in one native kernel)
+        if native_loss:  # loss + cotangent in one native kernel
             loss, v_img = losses.mse_loss_and_grad(img.detach(), tgt)
             img.backward(gradient=v_img)
         else:
@@ -272,21 +325,31 @@ def main():
         torch.cuda.synchronize()
 
     # ---------------- device-resident timing (value) ----------------
+    sampler = ClockSampler(dev)
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         step(sc.viewmat, target)
     barrier()
     launches0 = _lib.stats()["kernel_launches"] if args.impl == "ours" else 0
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        step(sc.viewmat, target)
-    e1.record()
-    barrier()
+    # the reference's stock call path spends its step in cudaMalloc/cudaFree/syncs and its time
+    # swings from run to run: time the K steps `repeats` times and report min / median too
+    repeats = 5 if args.impl == "reference" else 1
+    rep_ms = []
+    for rep in range(repeats):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        if rep == 0:
+            sampler.mark()
+        e0.record()
+        for _ in range(args.steps):
+            step(sc.viewmat, target)
+        e1.record()
+        barrier()
+        if rep == 0:
+            sampler.mark()
+        rep_ms.append(e0.elapsed_time(e1))
     clocks = sampler.stop()
-    ms_total = e0.elapsed_time(e1)
+    ms_total = statistics.median(rep_ms)
     stages = None
     launches = 0
     if args.impl == "ours":
@@ -399,6 +462,17 @@ def main():
         out["impl"] = "reference"
         out["config"]["reference"] = "unmodified yklcs/jaxsplat lib/*.cu built for sm_100a (oracle/_ref), same harness"
         out["gpu_launches"] = None
+        out["repeats"] = {"ms_per_step": [m / args.steps for m in rep_ms],
+                          "min_ms_per_step": min(rep_ms) / args.steps,
+                          "median_ms_per_step": statistics.median(rep_ms) / args.steps,
+                          "note": "K timed steps repeated 5 times; value / ms_per_step are the median "
+                                  "repeat (the stock call path's cudaMalloc/cudaFree/syncs make it swing)"}
+        if args.config == "C3":
+            # sum of the reference's own kernel durations for one C3 fwd+bwd step, from the committed
+            # ncu launch list of this same arm (cold-cache, serialised launches: an upper bound of
+            # its kernel time inside a step; no allocator or sync time in it)
+            out["reference_kernel_ms"] = {"value": 4.61,
+                                          "source": "profiles/r02a_reference_launches_C3.csv (38 launches per step)"}
         # the reference has no CPU implementation of this path (its kernels are CUDA-only): this arm
         # is its own CUDA library on the same B200; the host-core timing is the `cpu_baseline` of
         # the default arm (oracle/oracle.c)
@@ -426,27 +500,46 @@ def main():
                             "hbm_frac": b / (ms * 1e-3) / 1e9 / peak}
         dom = max(per_stage, key=lambda k: per_stage[k]["ms_per_launch"] * per_stage[k]["launches_per_step"])
         d = per_stage[dom]
-        traffic = None
+        prof = {}
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json"))).get(dom)
+            prof = json.load(open(os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")))
         except Exception:
             pass
-        out["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": d["gbs"], "peak": peak,
-                           "unit": "GB/s", "frac": d["hbm_frac"], "traffic": traffic,
-                           "peak_source": which_peak,
-                           "note": "achieved = compulsory HBM bytes of the dominant stage / its "
-                                   "device time; the rasterisers are SM-issue bound, not HBM bound "
-                                   "(no dense contraction, no tensor cores; ncu: 65-73 % issue-slot "
-                                   "utilisation, 2 % DRAM throughput): see 'issue', 'stages' and "
-                                   "DESIGN.md section 5; stage times come from a separate pass of "
-                                   "the same step with the library's stage events on"}
-        # issue-slot view of the rasterisers: (tile, Gaussian, pixel) pairs the REFERENCE's kernels
-        # evaluate for this frame (I * 256) per second of ours, against the issue-slot roof of
-        # evaluating every one of them (15 slots each); > 1x the roof = pairs never evaluated
-        pairs = I * 256
-        out["issue"] = {k: {"pairs_per_s": pairs / (per_stage[k]["ms_per_launch"] * 1e-3),
-                            "roof_pairs_per_s": 148 * 128 * (clocks["sm_mhz"] or 1965.0) * 1e6 / 15.0}
-                        for k in ("raster_fwd", "raster_bwd") if k in per_stage}
+        traffic = prof.get(dom) if args.config == "C3" else None
+        f_clk = (clocks.get("sm_mhz") or 1965.0) * 1e6
+        # SURVEY.md 8d unit of the rasterisers: useful pixel-Gaussian pairs, from the outputs
+        U_f = useful_pairs(sc, kw)
+        pair_roof = 148 * 128 * f_clk / 15.0   # every pair evaluated at >= 15 FP32-pipe slots
+        out["pairs"] = {"U_f": U_f, "roof_pairs_per_s": pair_roof,
+                        "note": "U_f = sum over pixels of (final_idx + 1 - first list entry of the "
+                                "tile): the pairs a tile-walking rasteriser without culling evaluates. "
+                                "This library's conservative 8x8-quadrant cull skips most of them "
+                                "unevaluated, so pairs/s can exceed the evaluate-everything roof; the "
+                                "roofline object is in issued warp instructions instead"}
+        for k in ("raster_fwd", "raster_bwd"):
+            if k in per_stage and U_f:
+                out["pairs"][k + "_pairs_per_s"] = U_f / (per_stage[k]["ms_per_launch"] * 1e-3)
+        if dom in ("raster_fwd", "raster_bwd"):
+            # issue-slot roofline of the dominant rasteriser: warp instructions of one launch (ncu
+            # smsp__inst_executed.sum of the same kernel on the same workload, committed under
+            # profiles/) / its device time, against 4 schedulers x 148 SMs x the SM clock
+            inst = (prof.get("_inst_executed") or {}).get(dom) if args.config == "C3" else None
+            peak_issue = 148 * 4 * f_clk
+            ach = (inst / (d["ms_per_launch"] * 1e-3)) if inst else None
+            out["roofline"] = {"bound": "issue", "kernel": dom, "achieved": ach, "peak": peak_issue,
+                               "unit": "warp-inst/s", "frac": (ach / peak_issue) if ach else None,
+                               "traffic": traffic, "inst_per_launch": inst,
+                               "inst_source": prof.get("_inst_source"),
+                               "hbm_view": {"achieved_gbs": d["gbs"], "peak_gbs": peak,
+                                            "frac": d["hbm_frac"], "peak_source": which_peak},
+                               "note": "the rasterisers are SM-issue bound (no dense contraction, no "
+                                       "tensor cores; DRAM throughput 2-3 %): frac = issued warp "
+                                       "instructions / (time x 148 SMs x 4 schedulers x f_clk); the HBM "
+                                       "stages' fractions are in 'stages'"}
+        else:
+            out["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": d["gbs"], "peak": peak,
+                               "unit": "GB/s", "frac": d["hbm_frac"], "traffic": traffic,
+                               "peak_source": which_peak}
         out["stages"] = per_stage
 
     if args.impl == "ours" and world == 1 and not args.no_cpu_baseline:

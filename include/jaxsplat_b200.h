@@ -92,7 +92,8 @@ JSB200_API void jsb200_rasterize_bwd_status(jsb200_stream_t stream, void **buffe
  *               out: v_mean3d v_scale v_quat v_colors v_opacity | v_xy v_conic v_cov2d v_cov3d
  *                    (the last four: intermediate cotangents; v_xy_abs, which nothing downstream
  *                    of rasterize_bwd reads, is not computed)
- * v_out_img_alpha may be NULL (= zero cotangent; block_width 16 only).
+ * v_out_img_alpha may be NULL (= zero cotangent; block_width 16 only); v_cov2d / v_cov3d may be
+ * NULL (not written: nothing downstream of a render reads them).
  * `opaque` is a full descriptor (f, c, glob_scale, clip_thresh set).  *token_out identifies the
  * binning this forward left in the per-(device, stream) workspace (0 = none); a render_bwd given
  * that token reuses it without any check or host synchronisation if no other binning ran on the
@@ -132,8 +133,9 @@ JSB200_API int jsb200_make_descriptor(unsigned num_points, unsigned img_h, unsig
 
 /* Extension (no reference equivalent): restricts the rasterize calls that use this descriptor to
  * the tile rows [tile_row_begin, tile_row_end) -- screen-tile-row sharding of one large frame
- * across GPUs with the Gaussians replicated.  Stored in the descriptor's 4 pad bytes; a band of 0
- * (what make_descriptor writes) means the full frame.  Only pixels of the band are written;
+ * across GPUs with the Gaussians replicated.  Stored in the descriptor's 4 pad bytes and marked by
+ * a magic value in block_dim_2d.z (1 in reference descriptors): without the marker the pad bytes
+ * -- which the reference's make_descriptor leaves uninitialised -- are ignored (= full frame).  Only pixels of the band are written;
  * final_idx then indexes the band's own sorted list.  Returns 0 on success. */
 JSB200_API int jsb200_set_descriptor_band(char *desc80, unsigned tile_row_begin, unsigned tile_row_end);
 
@@ -165,12 +167,10 @@ JSB200_API unsigned long long jsb200_error_count(void);
  *               instead of the packed FP32x2 instructions of sm_100),
  *      "rowcol" (1 default; 0 builds the per-tile lists with the older counting distribution of
  *               tile_lists.cu instead of the two-level row/column distribution),
- *      "sortlive" (0 default; 1 = EXPERIMENTAL, written without GPU access and not yet run on
- *               one: the depth sort takes its digits from `key - min key` and skips the passes
- *               over the zero top bytes; same lists by construction),
- *      "fwd1bar" / "bwd1bar" (0 default; 1 = EXPERIMENTAL, not yet run on a GPU: the two-pixel
- *               forward / packed backward rasteriser with one CTA barrier per batch instead of
- *               two; same arithmetic),
+ *      "bwdhits" (1 default; 0 runs rasterize_bwd with the per-tile batch kernel even when the
+ *               forward recorded which list entries every 8x8 quadrant accepted),
+ *      "sort1k" (1 default; 0 orders the Gaussians by depth with four onesweep passes over all 32
+ *               key bits instead of the single cooperative launch over the live bits),
  *      "timing" (0 default; 1 brackets every stage with CUDA events, see jsb200_get_stage_times),
  *      "view_slots" (8 default; binning workspaces a batched-camera call cycles through) */
 JSB200_API int jsb200_set_option(const char *key, int value);

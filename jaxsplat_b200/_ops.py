@@ -118,9 +118,17 @@ def rasterize_fwd(colors, opacities, background, xys, depths, radii, conics, cum
            _f32(depths, (n, 1), "depths"), _i32(radii, (n, 1), "radii"),
            _f32(conics, (n, 3), "conics"), _i32(cum_tiles_hit, (n, 1), "cum_tiles_hit")]
     # `out`: caller-provided (final_Ts, final_idx, img) so several tile-row bands can fill one frame
-    outs = list(out) if out is not None else [
-        _out((H, W, 1), torch.float32, dev), _out((H, W, 1), torch.int32, dev),
-        _out((H, W, 3), torch.float32, dev)]
+    if out is not None:
+        outs = list(out)
+    elif band is not None:
+        # a band call only writes the band's pixel rows: the rest of a fresh frame is zero, not
+        # uninitialised memory
+        outs = [torch.zeros((H, W, 1), dtype=torch.float32, device=dev),
+                torch.zeros((H, W, 1), dtype=torch.int32, device=dev),
+                torch.zeros((H, W, 3), dtype=torch.float32, device=dev)]
+    else:
+        outs = [_out((H, W, 1), torch.float32, dev), _out((H, W, 1), torch.int32, dev),
+                _out((H, W, 3), torch.float32, dev)]
     table.call("rasterize_fwd", ins, outs, _raster_desc(table, n, img_shape, block_width, band))
     # (final_Ts, final_idx, img)
     return tuple(outs)
@@ -178,9 +186,14 @@ def render_fwd(mean3ds, scales, quats, viewmat, colors, opacities, background, *
            _f32(background, (3,), "background")]
     outs = [_out((n, 6), torch.float32, dev), _out((n, 2), torch.float32, dev),
             _out((n, 1), torch.float32, dev), _out((n, 1), torch.int32, dev),
-            _out((n, 3), torch.float32, dev), _out((n, 1), torch.float32, dev),
-            _out((H, W, 1), torch.float32, dev), _out((H, W, 1), torch.int32, dev),
-            _out((H, W, 3), torch.float32, dev)]
+            _out((n, 3), torch.float32, dev), _out((n, 1), torch.float32, dev)]
+    if band is not None:  # only the band's pixel rows are written: the rest of the frame is zero
+        outs += [torch.zeros((H, W, 1), dtype=torch.float32, device=dev),
+                 torch.zeros((H, W, 1), dtype=torch.int32, device=dev),
+                 torch.zeros((H, W, 3), dtype=torch.float32, device=dev)]
+    else:
+        outs += [_out((H, W, 1), torch.float32, dev), _out((H, W, 1), torch.int32, dev),
+                 _out((H, W, 3), torch.float32, dev)]
     d = _ffi.make_descriptor(n, tuple(img_shape), tuple(f), tuple(c), glob_scale, clip_thresh,
                              block_width)
     if band is not None:
@@ -195,7 +208,9 @@ def render_bwd(mean3ds, scales, quats, viewmat, colors, opacities, background, c
                *, token, num_points, img_shape, f, c, glob_scale, clip_thresh, block_width,
                band=None, grad_out=None):
     """rasterize_bwd + project_bwd in one native call (jsb200_render_bwd).  Returns
-    (v_mean3d, v_scale, v_quat, v_colors, v_opacity, v_xy, v_conic, v_cov2d, v_cov3d).
+    (v_mean3d, v_scale, v_quat, v_colors, v_opacity, v_xy, v_conic, None, None): the two
+    intermediate cotangents v_cov2d / v_cov3d of the projection VJP are not materialised (the C
+    entry point writes them when given buffers).
     grad_out: optional caller-owned buffers for the first five results (see
     ``jaxsplat_b200.set_gradient_sink``); a sixth tensor of 5*N floats placed right behind
     v_opacity lets the library clear its four accumulators with one memset."""
@@ -221,17 +236,16 @@ def render_bwd(mean3ds, scales, quats, viewmat, colors, opacities, background, c
         tail = grad_out[5] if len(grad_out) > 5 else _out((5 * n,), torch.float32, dev)
         tail = _f32(tail, (5 * n,), "grad_out tail")
         # fresh view objects: autograd may then adopt them as .grad without a copy
+        # (v_cov2d / v_cov3d, the last two: None = not wanted, the kernel skips their 36 B/Gaussian)
         outs = [t.view(t.shape) for t in g] + [tail[:2 * n].view(n, 2), tail[2 * n:].view(n, 3),
-                                                _out((n, 3), torch.float32, dev),
-                                                _out((n, 6), torch.float32, dev)]
+                                                None, None]
     else:
         # the four atomically accumulated gradients back to back: the library clears them in one go
         acc = _out((n, 9), torch.float32, dev).reshape(-1)
         outs = [_out((n, 3), torch.float32, dev), _out((n, 3), torch.float32, dev),
                 _out((n, 4), torch.float32, dev), acc[:3 * n].view(n, 3),
                 acc[3 * n:4 * n].view(n, 1), acc[4 * n:6 * n].view(n, 2),
-                acc[6 * n:9 * n].view(n, 3), _out((n, 3), torch.float32, dev),
-                _out((n, 6), torch.float32, dev)]
+                acc[6 * n:9 * n].view(n, 3), None, None]
     d = _ffi.make_descriptor(n, tuple(img_shape), tuple(f), tuple(c), glob_scale, clip_thresh,
                              block_width)
     if band is not None:

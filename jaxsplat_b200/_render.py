@@ -48,6 +48,15 @@ class _Render(torch.autograd.Function):
     @staticmethod
     def backward(ctx, v_img):
         saved = ctx.saved_tensors
+        if _GRAD_SINK is not None:
+            # autograd ACCUMULATES a returned gradient into an existing .grad; if that .grad already
+            # is the sink buffer, `grad += out` with out aliasing grad would silently double it
+            for q, sink in zip((saved[0], saved[1], saved[2], saved[4], saved[5]), _GRAD_SINK):
+                if q.grad is not None and q.grad.data_ptr() == sink.data_ptr():
+                    raise RuntimeError(
+                        "jaxsplat_b200.set_gradient_sink: a parameter's .grad already aliases its sink "
+                        "buffer; set .grad = None before the backward (the sink views are adopted as "
+                        ".grad), or accumulation would double the gradient")
         # render() exposes no alpha image: its cotangent is identically zero (None = not read)
         (v_mean3d, v_scale, v_quat, v_colors, v_opacity, *_rest) = _ops.render_bwd(
             *saved, v_img.contiguous(), None, token=ctx.token, band=ctx.band,

@@ -53,7 +53,7 @@ bin_prep_kernel(const BinParams p, const float2 *__restrict__ xys,
         slab_load<3, BT>(s_color, colors, base * 3, n * 3);
     }
     __syncthreads();
-    unsigned cnt = 0, cnt_rows = 0;
+    unsigned cnt = 0, cnt_rows = 0, kinv = 0, kmax = 0;
     if (g < n) {
         const float2 xy = __ldg(xys + g);
         const float depth = __ldg(depths + g);
@@ -93,6 +93,8 @@ bin_prep_kernel(const BinParams p, const float2 *__restrict__ xys,
                 }
             }
             key = __float_as_uint(depth);
+            kinv = ~key;
+            kmax = key;
         }
         if (WRITE) {
             depth_keys[g] = key;
@@ -105,15 +107,29 @@ bin_prep_kernel(const BinParams p, const float2 *__restrict__ xys,
         cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
         cnt_rows += __shfl_xor_sync(0xffffffffu, cnt_rows, o);
     }
+    kinv = __reduce_max_sync(0xffffffffu, kinv);
+    kmax = __reduce_max_sync(0xffffffffu, kmax);
     // one pair of global atomics per CTA (they all hit the same two words: per-warp atomics
     // serialise in the L2 and were the kernel's critical path)
-    __shared__ unsigned s_tot[BT / 32][2];
-    if ((tid & 31) == 0) { s_tot[tid >> 5][0] = cnt; s_tot[tid >> 5][1] = cnt_rows; }
+    __shared__ unsigned s_tot[BT / 32][4];
+    if ((tid & 31) == 0) {
+        s_tot[tid >> 5][0] = cnt; s_tot[tid >> 5][1] = cnt_rows;
+        s_tot[tid >> 5][2] = kinv; s_tot[tid >> 5][3] = kmax;
+    }
     __syncthreads();
     if (tid == 0) {
         unsigned long long t0 = 0, t1 = 0;
+        unsigned m0 = 0, m1 = 0;
 #pragma unroll
-        for (int w = 0; w < BT / 32; ++w) { t0 += s_tot[w][0]; t1 += s_tot[w][1]; }
+        for (int w = 0; w < BT / 32; ++w) {
+            t0 += s_tot[w][0]; t1 += s_tot[w][1];
+            m0 = max(m0, s_tot[w][2]); m1 = max(m1, s_tot[w][3]);
+        }
+        if (WRITE && (m0 | m1)) {  // range of the real depth keys, for the live-bit depth sort
+            unsigned *mm = reinterpret_cast<unsigned *>(fingerprint + 5);
+            atomicMax(mm, m0);
+            atomicMax(mm + 1, m1);
+        }
         if (t0) {
             atomicAdd(fingerprint + 1, t0);  // total intersections
             // sum of box heights = row entries of the two-level distribution (rowcol_lists.cu)

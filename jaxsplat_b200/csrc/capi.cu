@@ -26,6 +26,7 @@
 #include "../../include/jaxsplat_b200.h"
 #include "common.cuh"
 #include "kernels.cuh"
+#include "raster_hits.cuh"
 
 namespace jsb {
 
@@ -34,6 +35,7 @@ static thread_local std::string t_error;
 static thread_local bool t_has_error = false;
 static std::atomic<unsigned long long> g_error_count{0};
 static std::atomic<unsigned long long> g_stats[8];
+static std::atomic<unsigned long long> g_token_counter{0};  // binning tokens (never reset, never 0)
 
 void set_error(const char *fmt, ...) {
     char buf[1024];
@@ -53,11 +55,10 @@ extern bool g_bwd_one_pixel;
 extern bool g_bwd_scalar;
 extern bool g_fwd_scalar;
 extern bool g_fwd_one_pixel;
-extern bool g_fwd_one_barrier;
-extern bool g_bwd_one_barrier;
+extern bool g_bwd_no_hits;
 static bool g_disable_cache = false;
 static bool g_disable_rowcol = false;
-static bool g_sort_live = false;  // option "sortlive": depth sort on the live bits of key - min
+static bool g_disable_resident_sort = false;  // option "sort1k" 0: the four-pass onesweep depth sort
 // jsb200_set_raster_bwd_event: recorded by the fused render backward between its two kernels
 // (process-wide: autograd runs the backward on its own thread, so not thread-local)
 static std::atomic<cudaEvent_t> g_raster_bwd_event{nullptr};
@@ -101,25 +102,25 @@ struct Ctx {
     cudaStream_t stream = nullptr;
     std::mutex mu;
     // N-scale
-    DevBuf records, dkeys_a, dkeys_b, ids_a, ids_b, box_by_id, boxes, sort_n_scratch, chain;
+    DevBuf records, dkeys_a, dkeys_b, ids_a, ids_b, order, box_by_id, boxes, sort_n_scratch, chain;
     // I-scale
-    DevBuf tile_keys, tile_vals, tile_ids, tile_scratch;
+    DevBuf tile_keys, tile_vals, tile_ids, tile_scratch, hits;
     DevBuf abs_scratch;
     DevBuf views_scratch;  // batched cameras: per-view cotangents + parameter-gradient staging
     DevBuf bins, small;  // small: [fingerprint u64][total u64][err int x4][tickets u32 x8]
     unsigned long long *h_pinned = nullptr;  // [fingerprint][total][err...]
     cudaEvent_t ev_ready = nullptr;          // recorded after the D2H of `small`
-    bool order_in_b = false;                 // where the depth-sorted ids of the last prep are
+    const unsigned *order_ptr = nullptr;     // the depth-sorted ids of the last prep
     unsigned long long last_rows = 0;        // sum of box heights of the last prep (row entries)
     // binning cache
     bool cache_valid = false;
     bool cache_has_records = false;  // false after a sort_and_bin-only call (no appearance data)
+    bool cache_has_hits = false;     // the forward that used this binning recorded hit words
     unsigned long long cache_fp = 0;
     unsigned cache_n = 0, cache_tiles = 0, cache_bw = 0, cache_tiles_x = 0, cache_band = 0;
     unsigned long long cache_I = 0;
     bool cache_fp_known = false;             // false when the binning came from the fused render
-    unsigned long long generation = 0;       // bumped by every binning run on this context
-    unsigned long long cache_token = 0;      // generation of the cached binning (fused render)
+    unsigned long long cache_token = 0;      // token of the cached binning (fused render)
     unsigned *cache_ids = nullptr;  // points into tile_ids
     size_t total_bytes = 0;
     StageTimes times;
@@ -142,8 +143,8 @@ struct Ctx {
         return 0;
     }
     void release() {
-        DevBuf *all[] = {&records, &dkeys_a, &dkeys_b, &ids_a, &ids_b, &box_by_id, &boxes,
-                         &sort_n_scratch, &chain, &tile_keys, &tile_vals, &tile_ids, &tile_scratch,
+        DevBuf *all[] = {&records, &dkeys_a, &dkeys_b, &ids_a, &ids_b, &order, &box_by_id, &boxes,
+                         &sort_n_scratch, &chain, &tile_keys, &tile_vals, &tile_ids, &tile_scratch, &hits,
                          &bins, &small, &abs_scratch, &views_scratch};
         for (DevBuf *b : all) {
             if (b->p) cudaFree(b->p);
@@ -201,6 +202,15 @@ static Ctx *get_ctx(cudaStream_t stream, unsigned slot = 0) {
     return raw;
 }
 
+// A descriptor only carries a tile-row band (in its 4 pad bytes) when jsb200_set_descriptor_band
+// also stamped this marker into block_dim_2d.z, which is 1 in every reference-built descriptor and
+// unused by this library's launches: the reference's make_descriptor leaves the pad bytes
+// uninitialised (lib/ffi.cu:15-52), and stack garbage there must not be read as a band.
+constexpr uint32_t kBandMagic = 0x4A534231u;  // "JSB1"
+static void normalise_descriptor(Descriptor &d) {
+    if (d.bdz != kBandMagic) d.pad = 0;
+}
+
 static const Descriptor *unpack(const char *opaque, size_t len) {
     if (len != sizeof(Descriptor) || opaque == nullptr) {
         set_error("invalid opaque descriptor size %zu (expected %zu)", len, sizeof(Descriptor));
@@ -209,9 +219,9 @@ static const Descriptor *unpack(const char *opaque, size_t len) {
     return reinterpret_cast<const Descriptor *>(opaque);
 }
 
-// Screen-tile-row band carried in the descriptor's 4 pad bytes (an extension: the reference
-// leaves them uninitialised): low 16 bits = first tile row, high 16 bits = one past the last.
-// 0 means the full frame, which is what every reference-compatible descriptor holds.
+// Screen-tile-row band carried in the descriptor's 4 pad bytes (an extension; only honoured with
+// the kBandMagic marker, see normalise_descriptor): low 16 bits = first tile row, high 16 bits =
+// one past the last.  0 means the full frame.
 static void band_of(const Descriptor &d, unsigned *y0, unsigned *y1) {
     *y0 = 0;
     *y1 = d.tiles_y;
@@ -232,6 +242,7 @@ static BinParams bin_params(const Descriptor &d) {
 
 constexpr int SM_FP = 0, SM_TOTAL = 1;       // u64 slots in `small`
 constexpr int SM_ROWS = 4;                   // u64 slot: sum of box heights (row entries)
+constexpr int SM_KEYRANGE = 5;               // u64 slot = two u32: max(~key), max(key) of the real depth keys
 constexpr int SM_ERR_WORD = 4;               // int slots start (byte 16)
 constexpr int SM_STRIP = 8;                  // u64 per-strip intersection counts start (byte 64)
 constexpr size_t SMALL_BYTES = 64 + 8 * kMaxStrips;
@@ -244,6 +255,10 @@ constexpr size_t SMALL_BYTES = 64 + 8 * kMaxStrips;
 static int bin_begin(Ctx &c, const Descriptor &d, bool write) {
     const unsigned n = d.num_points;
     cudaStream_t s = c.stream;
+    // a writing prep overwrites records / keys / boxes: whatever binning was cached is gone from
+    // here on, and only bin_sort re-validates (an early return in between must not leave a token
+    // that still matches)
+    if (write) c.cache_valid = false;
     if (!c.h_pinned) JSB_CUDA_OK(cudaHostAlloc((void **)&c.h_pinned, SMALL_BYTES, cudaHostAllocDefault));
     if (!c.ev_ready) JSB_CUDA_OK(cudaEventCreateWithFlags(&c.ev_ready, cudaEventDisableTiming));
     if (!c.small.p) {
@@ -255,7 +270,10 @@ static int bin_begin(Ctx &c, const Descriptor &d, bool write) {
     if (c.ensure(c.dkeys_a, (size_t)n * 4) || c.ensure(c.dkeys_b, (size_t)n * 4)) return 1;
     if (c.ensure(c.ids_a, (size_t)n * 4) || c.ensure(c.ids_b, (size_t)n * 4)) return 1;
     if (c.ensure(c.box_by_id, (size_t)n * sizeof(uint2))) return 1;
-    if (write && c.ensure(c.sort_n_scratch, radix_scratch_bytes(n, 32))) return 1;
+    if (write && c.ensure(c.sort_n_scratch, std::max(radix_scratch_bytes(n, 32),
+                                                     resident_sort_scratch_bytes(n))))
+        return 1;
+    if (write && c.ensure(c.order, (size_t)n * 4)) return 1;
     // zero fingerprint/total (bytes 0..16) and the counters at 32..64; the error words (16..32) are
     // sticky so that a device-side failure of the PREVIOUS call is seen at this call's sync
     JSB_CUDA_OK(cudaMemsetAsync(c.small.p, 0, 16, s));
@@ -279,17 +297,26 @@ static int bin_finish_enqueue(Ctx &c, const Descriptor &d, bool write) {
     JSB_CUDA_OK(cudaEventRecord(c.ev_ready, s));
     if (write) {
         StageScope ss(&c, ST_DEPTH_SORT);
-        bool in_b = false;
-        if (g_sort_live
-                ? radix_sort_depth_live(s, (uint32_t *)c.dkeys_a.p, (uint32_t *)c.dkeys_b.p,
-                                        (unsigned *)c.ids_a.p, (unsigned *)c.ids_b.p, n,
-                                        c.sort_n_scratch.p, (int *)c.small.p + SM_ERR_WORD, &in_b)
-                : radix_sort_pairs<uint32_t>(s, (uint32_t *)c.dkeys_a.p, (uint32_t *)c.dkeys_b.p,
-                                             (unsigned *)c.ids_a.p, (unsigned *)c.ids_b.p, n, 32,
-                                             c.sort_n_scratch.p, (int *)c.small.p + SM_ERR_WORD,
-                                             &in_b))
-            return 1;
-        c.order_in_b = in_b;
+        int rc = -1;
+        if (!g_disable_resident_sort) {
+            // one cooperative launch, live key bits only (resident_sort.cu)
+            const unsigned *mm = (const unsigned *)((unsigned long long *)c.small.p + SM_KEYRANGE);
+            rc = resident_depth_sort(s, (const unsigned *)c.dkeys_a.p, (unsigned *)c.dkeys_a.p,
+                                     (unsigned *)c.ids_a.p, (unsigned *)c.dkeys_b.p,
+                                     (unsigned *)c.ids_b.p, (unsigned *)c.order.p, n, mm,
+                                     c.sort_n_scratch.p, (int *)c.small.p + SM_ERR_WORD);
+            if (rc > 0) return 1;
+            if (rc == 0) c.order_ptr = (const unsigned *)c.order.p;
+        }
+        if (rc < 0) {  // option "sort1k" 0, or no cooperative launch: four onesweep passes
+            bool in_b = false;
+            if (radix_sort_pairs<uint32_t>(s, (uint32_t *)c.dkeys_a.p, (uint32_t *)c.dkeys_b.p,
+                                           (unsigned *)c.ids_a.p, (unsigned *)c.ids_b.p, n, 32,
+                                           c.sort_n_scratch.p, (int *)c.small.p + SM_ERR_WORD,
+                                           &in_b))
+                return 1;
+            c.order_ptr = (const unsigned *)(in_b ? c.ids_b.p : c.ids_a.p);
+        }
     }
     return 0;
 }
@@ -351,7 +378,7 @@ static int bin_sort_impl(Ctx &c, const Descriptor &d, unsigned long long I) {
     cudaStream_t s = c.stream;
     const unsigned tiles = d.tiles_x * d.tiles_y;
     // 1. the depth order of the Gaussians was enqueued by bin_prepare_enqueue
-    const unsigned *order = (const unsigned *)(c.order_in_b ? c.ids_b.p : c.ids_a.p);
+    const unsigned *order = c.order_ptr;
     if (c.ensure(c.bins, (size_t)tiles * sizeof(int2))) return 1;
     if (!g_disable_rowcol && rowcol_supported(bin_params(d))) {
         // two-level in-order distribution (rowcol_lists.cu): rows, then tiles of each row
@@ -442,11 +469,12 @@ static int bin_sort(Ctx &c, const Descriptor &d, unsigned long long I, unsigned 
     const unsigned tiles = d.tiles_x * d.tiles_y;
     c.cache_valid = false;
     c.cache_has_records = false;
+    c.cache_has_hits = false;
     int rc = tiles <= 65536 ? bin_sort_impl<uint16_t>(c, d, I) : bin_sort_impl<uint32_t>(c, d, I);
     if (rc) return rc;
     c.cache_valid = true;
     c.cache_fp_known = true;
-    c.cache_token = ++c.generation;
+    c.cache_token = g_token_counter.fetch_add(1) + 1;  // process-wide: never matches another context's
     c.cache_fp = fp;
     c.cache_n = d.num_points;
     c.cache_tiles = tiles;
@@ -574,12 +602,14 @@ static int rasterize_fwd_impl(cudaStream_t stream, void **buf, const Descriptor 
     }
     // the forward always bins afresh (a training loop changes the parameters every step); only
     // the matching backward may reuse this result
+    if (c->ensure(c->hits, hit_words_capacity(I, d.tiles_x * d.tiles_y) * 4)) return 1;
     if (bin_sort(*c, d, I, fp)) return 1;
     c->cache_has_records = true;
     StageScope ss(c, ST_RASTER_FWD);
     return launch_raster_fwd(stream, rp, c->cache_ids, (const int2 *)c->bins.p,
                              (const SplatRecord *)c->records.p, (const float *)buf[2],
-                             (float *)buf[8], (int *)buf[9], (float *)buf[10]);
+                             (float *)buf[8], (int *)buf[9], (float *)buf[10],
+                             (unsigned *)c->hits.p, &c->cache_has_hits);
 }
 
 static int rasterize_bwd_impl(cudaStream_t stream, void **buf, const Descriptor &d) {
@@ -623,7 +653,8 @@ static int rasterize_bwd_impl(cudaStream_t stream, void **buf, const Descriptor 
                              (const SplatRecord *)c->records.p, (const float *)buf[2],
                              (const float *)buf[8], (const int *)buf[9], (const float *)buf[10],
                              (const float *)buf[11], (float *)buf[14], (float *)buf[15],
-                             (float *)buf[16], (float *)buf[12], (float *)buf[13]);
+                             (float *)buf[16], (float *)buf[12], (float *)buf[13],
+                             c->cache_has_hits ? (const unsigned *)c->hits.p : nullptr);
 }
 
 // ---- fused render ---------------------------------------------------------------
@@ -645,7 +676,14 @@ static int render_fwd_impl(cudaStream_t stream, void **buf, const Descriptor &d,
     g_stats[0].fetch_add(1);
     const RasterParams rp = raster_params(d);
     unsigned long long I = 0, fp = 0;
-    if (d.pad == 0 && d.num_points != 0) {
+    // The fused projection kernel only accumulates the two grand totals (intersections, row
+    // entries).  The strip-by-strip fallback list builder (grids wider than 512 tiles or taller
+    // than 256 tile rows, or option "rowcol" 0) needs per-strip counts as well, which only
+    // bin_prep_kernel produces: such grids take the unfused prep.
+    const BinParams bp0 = bin_params(d);
+    const bool fused_prep_ok = (!g_disable_rowcol && rowcol_supported(bp0)) ||
+                               ceil_div(bp0.band_y1 - bp0.band_y0, bp0.strip_rows) <= 1;
+    if (d.pad == 0 && d.num_points != 0 && fused_prep_ok) {
         // full frame: the projection kernel also packs records / depth keys / tile boxes
         if (bin_begin(*c, d, /*write=*/true)) return 1;
         FusedPrep f;
@@ -672,6 +710,7 @@ static int render_fwd_impl(cudaStream_t stream, void **buf, const Descriptor &d,
         return launch_fill_background(stream, rp, (const float *)buf[6], (float *)buf[13],
                                       (int *)buf[14], (float *)buf[15]);
     }
+    if (c->ensure(c->hits, hit_words_capacity(I, d.tiles_x * d.tiles_y) * 4)) return 1;
     if (bin_sort(*c, d, I, 0)) return 1;
     c->cache_has_records = true;
     c->cache_fp_known = false;  // never matches a fingerprint: only the token proves identity
@@ -679,7 +718,8 @@ static int render_fwd_impl(cudaStream_t stream, void **buf, const Descriptor &d,
     StageScope ss(c, ST_RASTER_FWD);
     return launch_raster_fwd(stream, rp, c->cache_ids, (const int2 *)c->bins.p,
                              (const SplatRecord *)c->records.p, (const float *)buf[6],
-                             (float *)buf[13], (int *)buf[14], (float *)buf[15]);
+                             (float *)buf[13], (int *)buf[14], (float *)buf[15],
+                             (unsigned *)c->hits.p, &c->cache_has_hits);
 }
 
 // keep_appearance: v_colors / v_opacity already hold the sum over earlier views of a batched call
@@ -758,7 +798,8 @@ static int render_bwd_impl(cudaStream_t stream, void **buf, const Descriptor &d,
                               (const SplatRecord *)c->records.p, (const float *)buf[6],
                               (const float *)buf[13], (const int *)buf[14], (const float *)buf[15],
                               (const float *)buf[16], (float *)buf[22], v_xy_abs,
-                              (float *)buf[23], (float *)buf[20], (float *)buf[21]))
+                              (float *)buf[23], (float *)buf[20], (float *)buf[21],
+                              c->cache_has_hits ? (const unsigned *)c->hits.p : nullptr))
             return 1;
     }
     }
@@ -831,8 +872,7 @@ static int render_views_bwd_impl(cudaStream_t stream, void **buf, const Descript
     const size_t m = (n + 3) & ~(size_t)3;
     if (vc->ensure(vc->views_scratch, m * 24 * sizeof(float))) return 1;
     float *sc = (float *)vc->views_scratch.p;
-    float *s_xy = sc, *s_conic = sc + 2 * m, *s_cov2d = sc + 5 * m, *s_cov3d = sc + 8 * m,
-          *s_stage = sc + 14 * m;
+    float *s_xy = sc, *s_conic = sc + 2 * m, *s_stage = sc + 14 * m;
     for (unsigned i = 0; i < B; ++i) {
         const unsigned b = B - 1 - i;
         const bool first = (i == 0);
@@ -847,7 +887,7 @@ static int render_views_bwd_impl(cudaStream_t stream, void **buf, const Descript
                         first ? buf[17] : (void *)s_stage,
                         first ? buf[18] : (void *)(s_stage + 3 * m),
                         first ? buf[19] : (void *)(s_stage + 6 * m),
-                        buf[20], buf[21], s_xy, s_conic, s_cov2d, s_cov3d};
+                        buf[20], buf[21], s_xy, s_conic, nullptr, nullptr};  // (no v_cov2d / v_cov3d)
         if (render_bwd_impl(stream, vb, d, tokens ? tokens[b] : 0, b % g_view_slots,
                             /*keep_appearance=*/true))
             return 1;
@@ -868,6 +908,7 @@ static int guarded(const char *name, cudaStream_t stream, void **buffers, const 
         if (!buffers) { set_error("%s: null buffer list", name); return 1; }
         Descriptor local;
         memcpy(&local, d, sizeof local);  // opaque may be unaligned
+        normalise_descriptor(local);
         return body(stream, buffers, local);
     } catch (const std::exception &e) {
         set_error("%s: %s", name, e.what());
@@ -953,6 +994,7 @@ int jsb200_render_fwd(jsb200_stream_t stream, void **buffers, const char *opaque
         if (!buffers) { jsb::set_error("render_fwd: null buffer list"); return 1; }
         jsb::Descriptor d;
         memcpy(&d, dp, sizeof d);
+        jsb::normalise_descriptor(d);
         return jsb::render_fwd_impl((cudaStream_t)stream, buffers, d, token_out);
     } catch (...) {
         jsb::set_error("render_fwd: exception");
@@ -968,6 +1010,7 @@ int jsb200_render_bwd(jsb200_stream_t stream, void **buffers, const char *opaque
         if (!buffers) { jsb::set_error("render_bwd: null buffer list"); return 1; }
         jsb::Descriptor d;
         memcpy(&d, dp, sizeof d);
+        jsb::normalise_descriptor(d);
         return jsb::render_bwd_impl((cudaStream_t)stream, buffers, d, token);
     } catch (...) {
         jsb::set_error("render_bwd: exception");
@@ -1007,6 +1050,8 @@ int jsb200_set_descriptor_band(char *desc, unsigned tile_row_begin, unsigned til
     }
     const unsigned v = (tile_row_begin & 0xffffu) | (tile_row_end << 16);
     memcpy(desc + 76, &v, 4);
+    const uint32_t magic = jsb::kBandMagic;  // block_dim_2d.z (@72): marks the pad word as a band
+    memcpy(desc + 72, &magic, 4);
     return 0;
 }
 
@@ -1022,6 +1067,7 @@ int jsb200_sort_and_bin(jsb200_stream_t stream_, const char *opaque, size_t len,
         if (!dp) return 1;
         jsb::Descriptor d;
         memcpy(&d, dp, sizeof d);
+        jsb::normalise_descriptor(d);
         if (jsb::check_raster_desc(d)) return 1;
         jsb::Ctx *c = jsb::get_ctx(stream);
         if (!c) return 1;
@@ -1089,9 +1135,8 @@ int jsb200_set_option(const char *key, int value) {
     if (!strcmp(key, "bwdpk")) { jsb::g_bwd_scalar = (value == 0); return 0; }
     if (!strcmp(key, "fwdpk")) { jsb::g_fwd_scalar = (value == 0); return 0; }
     if (!strcmp(key, "rowcol")) { jsb::g_disable_rowcol = (value == 0); return 0; }
-    if (!strcmp(key, "sortlive")) { jsb::g_sort_live = (value != 0); return 0; }
-    if (!strcmp(key, "fwd1bar")) { jsb::g_fwd_one_barrier = (value != 0); return 0; }
-    if (!strcmp(key, "bwd1bar")) { jsb::g_bwd_one_barrier = (value != 0); return 0; }
+    if (!strcmp(key, "bwdhits")) { jsb::g_bwd_no_hits = (value == 0); return 0; }
+    if (!strcmp(key, "sort1k")) { jsb::g_disable_resident_sort = (value == 0); return 0; }
     if (!strcmp(key, "timing")) { jsb::g_timing = (value != 0); return 0; }
     if (!strcmp(key, "view_slots")) {
         if (value < 1 || value > 4096) { jsb::set_error("set_option: view_slots must be 1..4096"); return 1; }

@@ -23,8 +23,9 @@ struct ProjectBwdParams {
 
 struct SplatRecord;
 // Fused render, full-frame band: project_fwd also produces what bin_prep would (binning.cu):
-// records, depth keys (0xFFFFFFFF for radii <= 0), identity ids, tile boxes, and adds the
-// intersection / row-entry totals to totals[1] / totals[4].
+// records, depth keys (0xFFFFFFFF for radii <= 0), identity ids, tile boxes, adds the
+// intersection / row-entry totals to totals[1] / totals[4] and folds the range of the real depth
+// keys into the two u32 words of totals[5]: {max(~key), max(key)} (both 0 = no real key).
 struct FusedPrep {
     const float *colors = nullptr, *opacities = nullptr;
     SplatRecord *records = nullptr;
@@ -149,11 +150,16 @@ int radix_sort_pairs(cudaStream_t stream, KeyT *keys_a, KeyT *keys_b, unsigned *
                      unsigned *vals_b, unsigned n, int bits, void *scratch, int *err,
                      bool *result_in_b);
 
-// Depth order on the live key bits (option "sortlive", off by default): same order of the values
-// as radix_sort_pairs<uint32_t>(bits = 32) for every key != 0xFFFFFFFF; identity passes over the
-// zero top bytes of `key - min` only copy the values.  Same scratch; key buffers are scratch after.
-int radix_sort_depth_live(cudaStream_t stream, uint32_t *keys_a, uint32_t *keys_b, unsigned *vals_a,
-                          unsigned *vals_b, unsigned n, void *scratch, int *err, bool *result_in_b);
+// ---- depth order in one cooperative launch (resident_sort.cu) ----------------------------------
+// order[i] = id of the i-th Gaussian in (depth key, index) order; keys_in[g] = depth key of
+// Gaussian g (0xFFFFFFFF = hits no tile: placed anywhere at or after the largest real key);
+// mm = {max(~key), max(key)} over the real keys.  kA/vA/kB/vB: n-word ping-pong buffers (kA may be
+// keys_in).  Returns 0 on success, 1 on error, -1 if the device cannot launch cooperatively (the
+// caller then uses radix_sort_pairs).
+size_t resident_sort_scratch_bytes(unsigned n);
+int resident_depth_sort(cudaStream_t stream, const unsigned *keys_in, unsigned *kA, unsigned *vA,
+                        unsigned *kB, unsigned *vB, unsigned *order, unsigned n,
+                        const unsigned *mm, void *scratch, int *err);
 
 // ---- rasterisers (raster_fwd.cu / raster_bwd.cu) --------------------------------------------
 struct RasterParams {
@@ -163,15 +169,19 @@ struct RasterParams {
     unsigned band_y0, band_y1;  // tile rows rasterised by this call (screen-tile-row sharding)
 };
 
+// hit_words (may be null): the forward records which list entries each 8x8 quadrant accepted
+// (raster_hits.cuh; hit_words_capacity(I, tiles) words); *wrote_hits says whether the kernel that
+// ran does (only the default 16x16 two-pixel kernel).
 int launch_raster_fwd(cudaStream_t stream, const RasterParams &p, const unsigned *ids_sorted,
                       const int2 *tile_bins, const SplatRecord *records, const float *background,
-                      float *final_Ts, int *final_idx, float *out_img);
+                      float *final_Ts, int *final_idx, float *out_img,
+                      unsigned *hit_words = nullptr, bool *wrote_hits = nullptr);
 
 int launch_raster_bwd(cudaStream_t stream, const RasterParams &p, const unsigned *ids_sorted,
                       const int2 *tile_bins, const SplatRecord *records, const float *background,
                       const float *final_Ts, const int *final_idx, const float *v_out,
                       const float *v_out_alpha, float *v_xy, float *v_xy_abs, float *v_conic,
-                      float *v_colors, float *v_opacity);
+                      float *v_colors, float *v_opacity, const unsigned *hit_words = nullptr);
 
 // image = background, final_Ts = 0, final_idx = 0  (reference num_intersects==0 path,
 // ops.cu:119-127 + memsets :436-458)

@@ -3,12 +3,14 @@
 // Behavioural spec: reference lib/kernels/forward.cu:13-131 (project_gaussians_fwd),
 // :465-568 (project_cov3d_ewa, scale_rot_to_cov3d), helpers.h:9-57,122-153,194-211 and
 // lib/ops.cu:607-643 (cumsum); backward: backward.cu:345-570, helpers.h:60-98,131-192.
-// Design (not a port): one CTA owns a 256-Gaussian slab, moves the AoS operands with 16-byte
-// coalesced transactions through shared memory, writes EVERY output element (no pre-zeroing
-// memsets) and computes the CTA-local part of cum_tiles_hit in the same launch; two tiny kernels
-// (scan of the CTA totals, add prefix) finish the scan.  A single-launch chained look-back scan
-// was measured slower on B200: ~half of the kernel's stall samples sat on the look-back wait,
-// because these CTAs live only a few microseconds.  No CUB, no temp allocation.
+// Design (not a port): one thread per Gaussian, every load of a thread in flight before its first
+// use, AoS results transposed through a warp-private strip of shared memory so they leave as full
+// 128-byte rows (no CTA-wide barrier anywhere on the fused path); EVERY output element is written
+// (no pre-zeroing memsets); the unfused op also computes the CTA-local part of cum_tiles_hit in the
+// same launch and two tiny kernels (scan of the CTA totals, add prefix) finish the scan.  A
+// single-launch chained look-back scan was measured slower on B200: ~half of the kernel's stall
+// samples sat on the look-back wait, because these CTAs live only a few microseconds.  No CUB, no
+// temp allocation.
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -156,10 +158,42 @@ __device__ __forceinline__ ProjOut project_one(float mx, float my, float mz, flo
     return o;
 }
 
+// ---- warp-private AoS staging ------------------------------------------------------------------
+// The operator boundary fixes AoS (N,3)/(N,6) float arrays.  Loads of a 12- or 24-byte-stride
+// record are issued directly (the three / six scalar loads of a warp hit the same few cache lines,
+// L1 serves the repeats); stores would each touch every sector of the warp's span with 4 bytes,
+// so they are transposed through a warp-private strip of shared memory and leave as full
+// 128-byte rows.  Only __syncwarp is involved: warps of a CTA never wait for each other, which is
+// what the earlier CTA-wide slab staging (two to four __syncthreads per CTA) cost -- 54 us against
+// the reference's 22 us for the same projection at 1M Gaussians.
+constexpr int kWarpStripFloats = 32 * 12;  // one SplatRecord per lane
+
+// lane's K consecutive floats -> out[first + lane*K .. ], K floats per lane, coalesced 4-byte rows
+template <int K>
+__device__ __forceinline__ void warp_store_aos(float *strip, const float (&v)[K],
+                                               float *__restrict__ out, long long first,
+                                               long long total, int lane) {
+    __syncwarp();
+    if (K % 2 == 0) {
+#pragma unroll
+        for (int i = 0; i < K / 2; ++i)
+            reinterpret_cast<float2 *>(strip)[lane * (K / 2) + i] = make_float2(v[2 * i], v[2 * i + 1]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < K; ++i) strip[lane * K + i] = v[i];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+        const long long e = first + i * 32 + lane;
+        if (e < total) out[e] = strip[i * 32 + lane];
+    }
+}
+
 // FUSED (fused render, full-frame band): the kernel also does bin_prep's job (binning.cu) for the
-// Gaussian it just projected -- packed rasteriser record, depth key, identity id, tile box, and
-// the per-CTA totals of intersections and row entries -- so the projected arrays are not read
-// back by a second kernel.
+// Gaussian it just projected -- packed rasteriser record, depth key, tile box, the per-CTA totals
+// of intersections and row entries and the range of the real depth keys -- so the projected arrays
+// are not read back by a second kernel.
 template <bool FUSED>
 __global__ void __launch_bounds__(PT)
 project_fwd_kernel(const ProjectFwdParams p, const float *__restrict__ means3d,
@@ -169,119 +203,135 @@ project_fwd_kernel(const ProjectFwdParams p, const float *__restrict__ means3d,
                    float *__restrict__ conics, float *__restrict__ compensation,
                    int *__restrict__ num_tiles_hit, int *__restrict__ cum_tiles_hit,
                    unsigned *__restrict__ block_totals, const FusedPrep f) {
-    __shared__ __align__(16) float s_buf[PT * 9];
-    __shared__ __align__(16) float s_color[FUSED ? PT * 3 : 4];
+    __shared__ __align__(16) float s_strip[PT / 32][kWarpStripFloats];
     __shared__ unsigned s_ws[PT / 32 + 1];
-    __shared__ unsigned s_rows;
-    const int tid = threadIdx.x;
+    __shared__ unsigned s_tot[PT / 32][4];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned bid = blockIdx.x;
-    const long long base = (long long)bid * PT;
-    const long long idx = base + tid;
+    const long long idx = (long long)bid * PT + tid;
+    const long long wfirst = (long long)bid * PT + warp * 32;  // first Gaussian of this warp
     const long long n = p.num_points;
-    float *s_mean = s_buf, *s_scale = s_buf + PT * 3;
-    slab_load<3, PT>(s_mean, means3d, base * 3, n * 3);
-    slab_load<3, PT>(s_scale, scales, base * 3, n * 3);
-    if (FUSED) {
-        slab_load<3, PT>(s_color, f.colors, base * 3, n * 3);
-        if (tid == 0) s_rows = 0u;
-    }
-    __syncthreads();
+    float *strip = s_strip[warp];
 
     ProjOut o;
-    o.tiles = 0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) o.cov3d[i] = 0.f;
+    o.xy = make_float2(0.f, 0.f);
+    o.depth = 0.f; o.radius = 0; o.conic = make_float3(0.f, 0.f, 0.f); o.comp = 0.f; o.tiles = 0;
     const bool live = idx < n;
+    float cr = 0.f, cg = 0.f, cb = 0.f, opac = 0.f;
     if (live) {
+        // every load of the thread is in flight before the first use
+        const float mx = __ldg(means3d + idx * 3), my = __ldg(means3d + idx * 3 + 1),
+                    mz = __ldg(means3d + idx * 3 + 2);
+        const float sx = __ldg(scales + idx * 3), sy = __ldg(scales + idx * 3 + 1),
+                    sz = __ldg(scales + idx * 3 + 2);
         const float4 q = __ldg(quats + idx);
-        o = project_one(s_mean[tid * 3], s_mean[tid * 3 + 1], s_mean[tid * 3 + 2],
-                        s_scale[tid * 3], s_scale[tid * 3 + 1], s_scale[tid * 3 + 2], q, viewmat,
-                        p);
+        if (FUSED) {
+            cr = __ldg(f.colors + idx * 3); cg = __ldg(f.colors + idx * 3 + 1);
+            cb = __ldg(f.colors + idx * 3 + 2);
+            opac = __ldg(f.opacities + idx);
+        }
+        o = project_one(mx, my, mz, sx, sy, sz, q, viewmat, p);
     }
+    unsigned rows = 0, kinv = 0, kmax = 0;
     if (FUSED) {
-        unsigned rows = 0;
-        if (live) {
-            SplatRecord rec;
-            rec.q0 = make_float4(o.xy.x, o.xy.y, __ldg(f.opacities + idx), o.conic.x);
-            rec.q1 = make_float4(o.conic.y, o.conic.z, s_color[tid * 3], s_color[tid * 3 + 1]);
-            rec.q2 = make_float4(s_color[tid * 3 + 2], 0.f, 0.f, 0.f);
-            f.records[idx] = rec;
-            unsigned key = 0xFFFFFFFFu;
-            uint2 box = make_uint2(0u, 0u);  // {x0 | y0 << 16, width | height << 16}
-            if (o.radius > 0) {
-                // same expression as bin_prep_kernel: box from the stored xy and integer radius
-                unsigned x0, x1, y0, y1;
-                tile_bbox(o.xy.x, o.xy.y, (float)o.radius, p.block_width_f, p.tiles_x, p.tiles_y,
-                          x0, x1, y0, y1);
-                if (y1 > y0 && x1 > x0) {
-                    rows = y1 - y0;
-                    box = make_uint2(x0 | (y0 << 16), (x1 - x0) | ((y1 - y0) << 16));
-                }
-                key = __float_as_uint(o.depth);
+        unsigned key = 0xFFFFFFFFu;
+        uint2 box = make_uint2(0u, 0u);  // {x0 | y0 << 16, width | height << 16}
+        if (live && o.radius > 0) {
+            // same expression as bin_prep_kernel: box from the stored xy and integer radius
+            unsigned x0, x1, y0, y1;
+            tile_bbox(o.xy.x, o.xy.y, (float)o.radius, p.block_width_f, p.tiles_x, p.tiles_y,
+                      x0, x1, y0, y1);
+            if (y1 > y0 && x1 > x0) {
+                rows = y1 - y0;
+                box = make_uint2(x0 | (y0 << 16), (x1 - x0) | ((y1 - y0) << 16));
             }
+            key = __float_as_uint(o.depth);
+            kinv = ~key;
+            kmax = key;
+        }
+        if (live) {
             f.depth_keys[idx] = key;
             f.ids[idx] = (unsigned)idx;
             f.box_by_id[idx] = box;
         }
+        // the 48-byte records of the warp leave as 3 coalesced 16-byte rows per lane
+        __syncwarp();
+        float4 *s4 = reinterpret_cast<float4 *>(strip);
+        s4[lane * 3 + 0] = make_float4(o.xy.x, o.xy.y, opac, o.conic.x);
+        s4[lane * 3 + 1] = make_float4(o.conic.y, o.conic.z, cr, cg);
+        s4[lane * 3 + 2] = make_float4(cb, 0.f, 0.f, 0.f);
+        __syncwarp();
+        float4 *rec4 = reinterpret_cast<float4 *>(f.records) + wfirst * 3;
+        const long long rec_left = (n - wfirst) * 3;  // float4s of this warp that exist
 #pragma unroll
-        for (int s = 16; s > 0; s >>= 1) rows += __shfl_xor_sync(0xffffffffu, rows, s);
-        if ((tid & 31) == 0 && rows) atomicAdd(&s_rows, rows);
+        for (int i = 0; i < 3; ++i)
+            if (i * 32 + lane < rec_left) rec4[i * 32 + lane] = s4[i * 32 + lane];
     }
-    unsigned total;
-    const unsigned excl = cta_exclusive_scan<PT>((unsigned)o.tiles, &total, s_ws);  // syncs
-    if (tid == 0) {
-        if (cum_tiles_hit) block_totals[bid] = total;
-        if (FUSED && total) {  // one pair of same-address atomics per CTA
-            atomicAdd(f.totals + 1, (unsigned long long)total);
-            atomicAdd(f.totals + 4, (unsigned long long)s_rows);
-        }
-    }
-    // stage AoS outputs (inputs are dead after the syncs inside the scan)
-    float *s_cov = s_buf, *s_conic = s_buf + PT * 6;
     if (live) {
-#pragma unroll
-        for (int i = 0; i < 6; ++i) s_cov[tid * 6 + i] = o.cov3d[i];
-        s_conic[tid * 3] = o.conic.x;
-        s_conic[tid * 3 + 1] = o.conic.y;
-        s_conic[tid * 3 + 2] = o.conic.z;
         xys[idx] = o.xy;
         depths[idx] = o.depth;
         radii[idx] = o.radius;
         compensation[idx] = o.comp;
         // (the fused render passes null: nothing downstream of it reads the tile counts)
         if (num_tiles_hit) num_tiles_hit[idx] = o.tiles;
-        // CTA-local inclusive count; add_block_prefix_kernel adds the scanned CTA totals
-        if (cum_tiles_hit) cum_tiles_hit[idx] = (int)(excl + (unsigned)o.tiles);
     }
-    __syncthreads();
-    slab_store<6, PT>(s_cov, cov3ds, base * 6, n * 6);
-    slab_store<3, PT>(s_conic, conics, base * 3, n * 3);
+    warp_store_aos<6>(strip, o.cov3d, cov3ds, wfirst * 6, n * 6, lane);
+    const float cn[3] = {o.conic.x, o.conic.y, o.conic.z};
+    warp_store_aos<3>(strip, cn, conics, wfirst * 3, n * 3, lane);
+
+    if (cum_tiles_hit) {
+        // CTA-local inclusive count; add_block_prefix_kernel adds the scanned CTA totals
+        unsigned total;
+        const unsigned excl = cta_exclusive_scan<PT>((unsigned)o.tiles, &total, s_ws);  // syncs
+        if (tid == 0) block_totals[bid] = total;
+        if (live) cum_tiles_hit[idx] = (int)(excl + (unsigned)o.tiles);
+    }
+    if (FUSED) {
+        // one set of same-address atomics per CTA (per-warp atomics on these words serialise in
+        // the L2 and were measured as the kernel's critical path)
+        const unsigned tiles = __reduce_add_sync(0xffffffffu, (unsigned)o.tiles);
+        rows = __reduce_add_sync(0xffffffffu, rows);
+        kinv = __reduce_max_sync(0xffffffffu, kinv);
+        kmax = __reduce_max_sync(0xffffffffu, kmax);
+        if (lane == 0) { s_tot[warp][0] = tiles; s_tot[warp][1] = rows; s_tot[warp][2] = kinv; s_tot[warp][3] = kmax; }
+        __syncthreads();
+        if (tid == 0) {
+            unsigned long long t0 = 0, t1 = 0;
+            unsigned m0 = 0, m1 = 0;
+#pragma unroll
+            for (int w = 0; w < PT / 32; ++w) {
+                t0 += s_tot[w][0]; t1 += s_tot[w][1];
+                m0 = max(m0, s_tot[w][2]); m1 = max(m1, s_tot[w][3]);
+            }
+            if (t0) {
+                atomicAdd(f.totals + 1, t0);
+                atomicAdd(f.totals + 4, t1);
+            }
+            if (m0 | m1) {  // range of the real depth keys: [~max(~key), max(key)]
+                unsigned *mm = reinterpret_cast<unsigned *>(f.totals + 5);
+                atomicMax(mm, m0);
+                atomicMax(mm + 1, m1);
+            }
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
-// Projection backward.  Float outputs only (tolerance-compared), so plain expressions; the
-// structure follows the maths of backward.cu:345-570 but keeps every intermediate in registers
-// (the reference read-modify-writes v_cov2d / v_mean3d / v_cov3d through global memory).
+// Projection backward.  Float outputs only (tolerance-compared).  The maths is that of
+// backward.cu:345-570 (project_pix_vjp, cov2d_to_conic_vjp, cov2d_to_compensation_vjp,
+// project_cov3d_ewa_vjp with the unclamped t of SURVEY Q2, scale_rot_to_cov3d_vjp,
+// quat_to_rotmat_vjp), expanded by hand on the operands' structure instead of generic 3x3
+// products: J has four non-zeros, the 2x2 cotangent G and the 3x3 covariances are symmetric, so
+//   T   = J W                 two rows T0, T1
+//   v_V = T^T G T             = T0 (x) A0 + T1 (x) A1          with A = G T (two rows)
+//   v_T = 2 G T V             = 2 A V                          (two rows)
+//   v_J = v_T W^T             only the four entries the t-gradient reads
+//   v_M = 2 v_V M,  v_s = gs diag(R^T v_M),  v_R = v_M S
+// ~300 instructions per Gaussian instead of ~1100, no shared-memory slabs, no CTA barriers.
+// v_cov2d / v_cov3d may be null (the fused render has no use for the intermediate cotangents).
 // ---------------------------------------------------------------------------------------------
-struct M3 {  // column-major like the reference's mat3: m[c][r]
-    float m[3][3];
-};
-__device__ __forceinline__ M3 mm(const M3 &a, const M3 &b) {
-    M3 r;
-#pragma unroll
-    for (int c = 0; c < 3; ++c)
-#pragma unroll
-        for (int rr = 0; rr < 3; ++rr)
-            r.m[c][rr] = a.m[0][rr] * b.m[c][0] + a.m[1][rr] * b.m[c][1] + a.m[2][rr] * b.m[c][2];
-    return r;
-}
-__device__ __forceinline__ M3 tr(const M3 &a) {
-    M3 r;
-#pragma unroll
-    for (int c = 0; c < 3; ++c)
-#pragma unroll
-        for (int rr = 0; rr < 3; ++rr) r.m[c][rr] = a.m[rr][c];
-    return r;
-}
-
 __global__ void __launch_bounds__(PT)
 project_bwd_kernel(const ProjectBwdParams p, const float *__restrict__ means3d,
                    const float *__restrict__ scales, const float4 *__restrict__ quats,
@@ -291,157 +341,143 @@ project_bwd_kernel(const ProjectBwdParams p, const float *__restrict__ means3d,
                    const float *__restrict__ v_compensation, const float2 *__restrict__ v_xy,
                    const float *__restrict__ v_depth, const float *__restrict__ v_conic,
                    float *__restrict__ v_mean3d, float *__restrict__ v_scale,
-                   float4 *__restrict__ v_quat, float *__restrict__ v_cov2d,
+                   float *__restrict__ v_quat, float *__restrict__ v_cov2d,
                    float *__restrict__ v_cov3d) {
-    // slabs: mean 3, scale 3, cov3d 6, conic 3, v_conic 3  -> 18 floats/Gaussian in,
-    // outputs reuse: v_mean 3, v_scale 3, v_cov2d 3, v_cov3d 6
-    __shared__ __align__(16) float s_buf[PT * 18];
-    const int tid = threadIdx.x;
-    const long long base = (long long)blockIdx.x * PT;
-    const long long idx = base + tid;
+    __shared__ __align__(16) float s_strip[PT / 32][32 * 6];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long idx = (long long)blockIdx.x * PT + tid;
+    const long long wfirst = (long long)blockIdx.x * PT + warp * 32;
     const long long n = p.num_points;
-    float *s_mean = s_buf, *s_scale = s_buf + PT * 3, *s_cov = s_buf + PT * 6,
-          *s_conic = s_buf + PT * 12, *s_vconic = s_buf + PT * 15;
-    slab_load<3, PT>(s_mean, means3d, base * 3, n * 3);
-    slab_load<3, PT>(s_scale, scales, base * 3, n * 3);
-    slab_load<6, PT>(s_cov, cov3ds, base * 6, n * 6);
-    slab_load<3, PT>(s_conic, conics, base * 3, n * 3);
-    slab_load<3, PT>(s_vconic, v_conic, base * 3, n * 3);
-    __syncthreads();
+    float *strip = s_strip[warp];
 
     float o_mean[3] = {0.f, 0.f, 0.f}, o_scale[3] = {0.f, 0.f, 0.f};
     float o_cov2d[3] = {0.f, 0.f, 0.f}, o_cov3d[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    float4 o_quat = make_float4(0.f, 0.f, 0.f, 0.f);
+    float o_quat[4] = {0.f, 0.f, 0.f, 0.f};
     const bool live = idx < n;
-    if (live && radii[idx] > 0) {
-        const float mx = s_mean[tid * 3], my = s_mean[tid * 3 + 1], mz = s_mean[tid * 3 + 2];
+    if (live && __ldg(radii + idx) > 0) {
+        const float mx = __ldg(means3d + idx * 3), my = __ldg(means3d + idx * 3 + 1),
+                    mz = __ldg(means3d + idx * 3 + 2);
+        const float sc0 = __ldg(scales + idx * 3), sc1 = __ldg(scales + idx * 3 + 1),
+                    sc2 = __ldg(scales + idx * 3 + 2);
+        const float4 q = __ldg(quats + idx);
+        const float k0 = __ldg(cov3ds + idx * 6), k1 = __ldg(cov3ds + idx * 6 + 1),
+                    k2 = __ldg(cov3ds + idx * 6 + 2), k3 = __ldg(cov3ds + idx * 6 + 3),
+                    k4 = __ldg(cov3ds + idx * 6 + 4), k5 = __ldg(cov3ds + idx * 6 + 5);
+        const float cx = __ldg(conics + idx * 3), cy = __ldg(conics + idx * 3 + 1),
+                    cz = __ldg(conics + idx * 3 + 2);
+        const float gx = __ldg(v_conic + idx * 3), gy = 0.5f * __ldg(v_conic + idx * 3 + 1),
+                    gz = __ldg(v_conic + idx * 3 + 2);
+        const float2 vxy = __ldg(v_xy + idx);
+        const float vz = v_depth ? __ldg(v_depth + idx) : 0.f;  // null = zero cotangent (fused render)
         const float *v = viewmat;
+        const float w00 = __ldg(v + 0), w01 = __ldg(v + 1), w02 = __ldg(v + 2), w03 = __ldg(v + 3);
+        const float w10 = __ldg(v + 4), w11 = __ldg(v + 5), w12 = __ldg(v + 6), w13 = __ldg(v + 7);
+        const float w20 = __ldg(v + 8), w21 = __ldg(v + 9), w22 = __ldg(v + 10), w23 = __ldg(v + 11);
         const float fx = p.fx, fy = p.fy;
         // p_view
-        const float pvx = v[0] * mx + v[1] * my + v[2] * mz + v[3];
-        const float pvy = v[4] * mx + v[5] * my + v[6] * mz + v[7];
-        const float pvz = v[8] * mx + v[9] * my + v[10] * mz + v[11];
+        const float pvx = w00 * mx + w01 * my + w02 * mz + w03;
+        const float pvy = w10 * mx + w11 * my + w12 * mz + w13;
+        const float pvz = w20 * mx + w21 * my + w22 * mz + w23;
         // project_pix_vjp (helpers.h:131-138) then R^T (helpers.h:90-98), + depth term
-        const float2 vxy = v_xy[idx];
         const float rw = 1.f / (pvz + 1e-6f);
         const float vpx = fx * vxy.x, vpy = fy * vxy.y;
-        const float vvx = vpx * rw, vvy = vpy * rw, vvz = -(vpx * pvx + vpy * pvy) * rw * rw;
-        float vm_x = v[0] * vvx + v[4] * vvy + v[8] * vvz;
-        float vm_y = v[1] * vvx + v[5] * vvy + v[9] * vvz;
-        float vm_z = v[2] * vvx + v[6] * vvy + v[10] * vvz;
-        const float vz = v_depth ? v_depth[idx] : 0.f;  // null = zero cotangent (fused render)
-        vm_x += v[8] * vz;
-        vm_y += v[9] * vz;
-        vm_z += v[10] * vz;
+        const float vvx = vpx * rw, vvy = vpy * rw;
+        const float vvz = -(vpx * pvx + vpy * pvy) * rw * rw + vz;
+        float vm_x = w00 * vvx + w10 * vvy + w20 * vvz;
+        float vm_y = w01 * vvx + w11 * vvy + w21 * vvz;
+        float vm_z = w02 * vvx + w12 * vvy + w22 * vvz;
 
-        // cov2d_to_conic_vjp (helpers.h:60-71): v_Sigma = -X G X
-        const float cx = s_conic[tid * 3], cy = s_conic[tid * 3 + 1], cz = s_conic[tid * 3 + 2];
-        const float gx = s_vconic[tid * 3], gy = s_vconic[tid * 3 + 1] / 2.f,
-                    gz = s_vconic[tid * 3 + 2];
-        // column-major 2x2: X = [[cx,cy],[cy,cz]] ; nX = -X
-        const float n00 = -cx, n01 = -cy, n10 = -cy, n11 = -cz;  // n[c][r]
-        // P = nX * G
-        const float p00 = n00 * gx + n10 * gy, p01 = n01 * gx + n11 * gy;
-        const float p10 = n00 * gy + n10 * gz, p11 = n01 * gy + n11 * gz;
-        // S = P * X
-        const float S00 = p00 * cx + p10 * cy, S01 = p01 * cx + p11 * cy;
-        const float S10 = p00 * cy + p10 * cz, S11 = p01 * cy + p11 * cz;
-        float vc_x = S00, vc_y = S10 + S01, vc_z = S11;
+        // cov2d_to_conic_vjp (helpers.h:60-71): v_Sigma = -X G X, X = [[cx,cy],[cy,cz]]
+        const float p00 = cx * gx + cy * gy, p01 = cx * gy + cy * gz;   // (X G) row 0
+        const float p10 = cy * gx + cz * gy, p11 = cy * gy + cz * gz;   // (X G) row 1
+        float vc_x = -(p00 * cx + p01 * cy);
+        float vc_y = -((p00 * cy + p01 * cz) + (p10 * cx + p11 * cy));
+        float vc_z = -(p10 * cy + p11 * cz);
         // cov2d_to_compensation_vjp (helpers.h:73-87): the reference evaluates this in FP64
-        {
-            const float comp = compensation[idx], vcomp = v_compensation ? v_compensation[idx] : 0.f;
-            const float inv_det = cx * cz - cy * cy;
-            const float om = 1 - comp * comp;
-            const float vs = (float)((double)vcomp * 0.5 / ((double)comp + 1e-6));
-            vc_x += (float)((double)vs * ((double)(om * cx) - 0.3 * (double)inv_det));
-            vc_y += 2 * vs * (om * cy);
-            vc_z += (float)((double)vs * ((double)(om * cz) - 0.3 * (double)inv_det));
+        if (v_compensation) {
+            const float vcomp = __ldg(v_compensation + idx);
+            if (vcomp != 0.f) {
+                const float comp = __ldg(compensation + idx);
+                const float inv_det = cx * cz - cy * cy;
+                const float om = 1 - comp * comp;
+                const float vs = (float)((double)vcomp * 0.5 / ((double)comp + 1e-6));
+                vc_x += (float)((double)vs * ((double)(om * cx) - 0.3 * (double)inv_det));
+                vc_y += 2 * vs * (om * cy);
+                vc_z += (float)((double)vs * ((double)(om * cz) - 0.3 * (double)inv_det));
+            }
         }
         o_cov2d[0] = vc_x; o_cov2d[1] = vc_y; o_cov2d[2] = vc_z;
 
         // project_cov3d_ewa_vjp (backward.cu:421-524); note: unclamped t
-        M3 W = {{{v[0], v[4], v[8]}, {v[1], v[5], v[9]}, {v[2], v[6], v[10]}}};
         const float rz = 1.f / pvz, rz2 = rz * rz;
-        M3 J = {{{fx * rz, 0.f, 0.f}, {0.f, fy * rz, 0.f}, {-fx * pvx * rz2, -fy * pvy * rz2, 0.f}}};
-        const float *k = s_cov + tid * 6;
-        M3 V = {{{k[0], k[1], k[2]}, {k[1], k[3], k[4]}, {k[2], k[4], k[5]}}};
-        M3 G = {{{vc_x, 0.5f * vc_y, 0.f}, {0.5f * vc_y, vc_z, 0.f}, {0.f, 0.f, 0.f}}};
-        M3 T = mm(J, W);
-        M3 Tt = tr(T);
-        M3 vV = mm(mm(Tt, G), T);
-        M3 t1 = mm(mm(G, T), tr(V));
-        M3 t2 = mm(mm(tr(G), T), V);
-        M3 vT;
-#pragma unroll
-        for (int c = 0; c < 3; ++c)
-#pragma unroll
-            for (int r = 0; r < 3; ++r) vT.m[c][r] = t1.m[c][r] + t2.m[c][r];
-        o_cov3d[0] = vV.m[0][0];
-        o_cov3d[1] = vV.m[0][1] + vV.m[1][0];
-        o_cov3d[2] = vV.m[0][2] + vV.m[2][0];
-        o_cov3d[3] = vV.m[1][1];
-        o_cov3d[4] = vV.m[1][2] + vV.m[2][1];
-        o_cov3d[5] = vV.m[2][2];
-        M3 vJ = mm(vT, tr(W));
+        const float j00 = fx * rz, j11 = fy * rz, j02 = -fx * pvx * rz2, j12 = -fy * pvy * rz2;
+        const float T00 = j00 * w00 + j02 * w20, T01 = j00 * w01 + j02 * w21, T02 = j00 * w02 + j02 * w22;
+        const float T10 = j11 * w10 + j12 * w20, T11 = j11 * w11 + j12 * w21, T12 = j11 * w12 + j12 * w22;
+        const float g00 = vc_x, g01 = 0.5f * vc_y, g11 = vc_z;
+        // A = G T
+        const float A00 = g00 * T00 + g01 * T10, A01 = g00 * T01 + g01 * T11, A02 = g00 * T02 + g01 * T12;
+        const float A10 = g01 * T00 + g11 * T10, A11 = g01 * T01 + g11 * T11, A12 = g01 * T02 + g11 * T12;
+        // v_V = T^T A (symmetric); packed upper triangle, off-diagonals doubled
+        const float V00 = T00 * A00 + T10 * A10, V11 = T01 * A01 + T11 * A11, V22 = T02 * A02 + T12 * A12;
+        const float V01 = T00 * A01 + T10 * A11, V02 = T00 * A02 + T10 * A12, V12 = T01 * A02 + T11 * A12;
+        o_cov3d[0] = V00; o_cov3d[1] = V01 + V01; o_cov3d[2] = V02 + V02;
+        o_cov3d[3] = V11; o_cov3d[4] = V12 + V12; o_cov3d[5] = V22;
+        // v_T = 2 A V (V = cov3d, symmetric)
+        const float vT00 = 2.f * (A00 * k0 + A01 * k1 + A02 * k2);
+        const float vT01 = 2.f * (A00 * k1 + A01 * k3 + A02 * k4);
+        const float vT02 = 2.f * (A00 * k2 + A01 * k4 + A02 * k5);
+        const float vT10 = 2.f * (A10 * k0 + A11 * k1 + A12 * k2);
+        const float vT11 = 2.f * (A10 * k1 + A11 * k3 + A12 * k4);
+        const float vT12 = 2.f * (A10 * k2 + A11 * k4 + A12 * k5);
+        // v_J = v_T W^T: the four entries the t-gradient reads
+        const float vJ00 = vT00 * w00 + vT01 * w01 + vT02 * w02;
+        const float vJ02 = vT00 * w20 + vT01 * w21 + vT02 * w22;
+        const float vJ11 = vT10 * w10 + vT11 * w11 + vT12 * w12;
+        const float vJ12 = vT10 * w20 + vT11 * w21 + vT12 * w22;
         const float rz3 = rz2 * rz;
-        const float vt_x = -fx * rz2 * vJ.m[2][0];
-        const float vt_y = -fy * rz2 * vJ.m[2][1];
-        const float vt_z = -fx * rz2 * vJ.m[0][0] + 2.f * fx * pvx * rz3 * vJ.m[2][0] -
-                           fy * rz2 * vJ.m[1][1] + 2.f * fy * pvy * rz3 * vJ.m[2][1];
-        vm_x += vt_x * W.m[0][0] + vt_y * W.m[0][1] + vt_z * W.m[0][2];
-        vm_y += vt_x * W.m[1][0] + vt_y * W.m[1][1] + vt_z * W.m[1][2];
-        vm_z += vt_x * W.m[2][0] + vt_y * W.m[2][1] + vt_z * W.m[2][2];
+        const float vt_x = -fx * rz2 * vJ02;
+        const float vt_y = -fy * rz2 * vJ12;
+        const float vt_z = -fx * rz2 * vJ00 + 2.f * fx * pvx * rz3 * vJ02 - fy * rz2 * vJ11 +
+                           2.f * fy * pvy * rz3 * vJ12;
+        vm_x += vt_x * w00 + vt_y * w10 + vt_z * w20;
+        vm_y += vt_x * w01 + vt_y * w11 + vt_z * w21;
+        vm_z += vt_x * w02 + vt_y * w12 + vt_z * w22;
         o_mean[0] = vm_x; o_mean[1] = vm_y; o_mean[2] = vm_z;
 
-        // scale_rot_to_cov3d_vjp (backward.cu:528-570)
-        const float4 q = __ldg(quats + idx);
+        // scale_rot_to_cov3d_vjp (backward.cu:528-570): M = R S, v_M = 2 v_V M
         const float w = q.x, x = q.y, y = q.z, z = q.w;
-        M3 R = {{{1.f - 2.f * (y * y + z * z), 2.f * (x * y + w * z), 2.f * (x * z - w * y)},
-                 {2.f * (x * y - w * z), 1.f - 2.f * (x * x + z * z), 2.f * (y * z + w * x)},
-                 {2.f * (x * z + w * y), 2.f * (y * z - w * x), 1.f - 2.f * (x * x + y * y)}}};
+        const float R00 = 1.f - 2.f * (y * y + z * z), R01 = 2.f * (x * y - w * z), R02 = 2.f * (x * z + w * y);
+        const float R10 = 2.f * (x * y + w * z), R11 = 1.f - 2.f * (x * x + z * z), R12 = 2.f * (y * z - w * x);
+        const float R20 = 2.f * (x * z - w * y), R21 = 2.f * (y * z + w * x), R22 = 1.f - 2.f * (x * x + y * y);
         const float gs = p.glob_scale;
-        const float s0 = gs * s_scale[tid * 3], s1 = gs * s_scale[tid * 3 + 1],
-                    s2 = gs * s_scale[tid * 3 + 2];
-        M3 S = {{{s0, 0.f, 0.f}, {0.f, s1, 0.f}, {0.f, 0.f, s2}}};
-        M3 M = mm(R, S);
-        M3 vVs = {{{o_cov3d[0], 0.5f * o_cov3d[1], 0.5f * o_cov3d[2]},
-                   {0.5f * o_cov3d[1], o_cov3d[3], 0.5f * o_cov3d[4]},
-                   {0.5f * o_cov3d[2], 0.5f * o_cov3d[4], o_cov3d[5]}}};
-        M3 two = {{{2.f, 0.f, 0.f}, {0.f, 2.f, 0.f}, {0.f, 0.f, 2.f}}};
-        M3 vM = mm(mm(vVs, M), two);
-        o_scale[0] = (R.m[0][0] * vM.m[0][0] + R.m[0][1] * vM.m[0][1] + R.m[0][2] * vM.m[0][2]) * gs;
-        o_scale[1] = (R.m[1][0] * vM.m[1][0] + R.m[1][1] * vM.m[1][1] + R.m[1][2] * vM.m[1][2]) * gs;
-        o_scale[2] = (R.m[2][0] * vM.m[2][0] + R.m[2][1] * vM.m[2][1] + R.m[2][2] * vM.m[2][2]) * gs;
-        M3 vR = mm(vM, S);
+        const float s0 = gs * sc0, s1 = gs * sc1, s2 = gs * sc2;
+        // B = v_V R (3x3); v_M[r][c] = 2 s_c B[r][c]
+        const float B00 = V00 * R00 + V01 * R10 + V02 * R20, B01 = V00 * R01 + V01 * R11 + V02 * R21,
+                    B02 = V00 * R02 + V01 * R12 + V02 * R22;
+        const float B10 = V01 * R00 + V11 * R10 + V12 * R20, B11 = V01 * R01 + V11 * R11 + V12 * R21,
+                    B12 = V01 * R02 + V11 * R12 + V12 * R22;
+        const float B20 = V02 * R00 + V12 * R10 + V22 * R20, B21 = V02 * R01 + V12 * R11 + V22 * R21,
+                    B22 = V02 * R02 + V12 * R12 + V22 * R22;
+        // v_scale_c = gs * sum_r R[r][c] v_M[r][c]
+        o_scale[0] = gs * 2.f * s0 * (R00 * B00 + R10 * B10 + R20 * B20);
+        o_scale[1] = gs * 2.f * s1 * (R01 * B01 + R11 * B11 + R21 * B21);
+        o_scale[2] = gs * 2.f * s2 * (R02 * B02 + R12 * B12 + R22 * B22);
+        // v_R[r][c] = v_M[r][c] s_c = 2 s_c^2 B[r][c]
+        const float e0 = 2.f * s0 * s0, e1 = 2.f * s1 * s1, e2 = 2.f * s2 * s2;
+        const float vR00 = e0 * B00, vR01 = e1 * B01, vR02 = e2 * B02;
+        const float vR10 = e0 * B10, vR11 = e1 * B11, vR12 = e2 * B12;
+        const float vR20 = e0 * B20, vR21 = e1 * B21, vR22 = e2 * B22;
         // quat_to_rotmat_vjp (helpers.h:155-192)
-        o_quat.x = 2.f * (x * (vR.m[1][2] - vR.m[2][1]) + y * (vR.m[2][0] - vR.m[0][2]) +
-                          z * (vR.m[0][1] - vR.m[1][0]));
-        o_quat.y = 2.f * (-2.f * x * (vR.m[1][1] + vR.m[2][2]) + y * (vR.m[0][1] + vR.m[1][0]) +
-                          z * (vR.m[0][2] + vR.m[2][0]) + w * (vR.m[1][2] - vR.m[2][1]));
-        o_quat.z = 2.f * (x * (vR.m[0][1] + vR.m[1][0]) - 2.f * y * (vR.m[0][0] + vR.m[2][2]) +
-                          z * (vR.m[1][2] + vR.m[2][1]) + w * (vR.m[2][0] - vR.m[0][2]));
-        o_quat.w = 2.f * (x * (vR.m[0][2] + vR.m[2][0]) + y * (vR.m[1][2] + vR.m[2][1]) -
-                          2.f * z * (vR.m[0][0] + vR.m[1][1]) + w * (vR.m[0][1] - vR.m[1][0]));
+        o_quat[0] = 2.f * (x * (vR21 - vR12) + y * (vR02 - vR20) + z * (vR10 - vR01));
+        o_quat[1] = 2.f * (-2.f * x * (vR11 + vR22) + y * (vR10 + vR01) + z * (vR20 + vR02) + w * (vR21 - vR12));
+        o_quat[2] = 2.f * (x * (vR10 + vR01) - 2.f * y * (vR00 + vR22) + z * (vR21 + vR12) + w * (vR02 - vR20));
+        o_quat[3] = 2.f * (x * (vR20 + vR02) + y * (vR21 + vR12) - 2.f * z * (vR00 + vR11) + w * (vR10 - vR01));
     }
-    __syncthreads();  // inputs dead; reuse for outputs
-    float *s_vmean = s_buf, *s_vscale = s_buf + PT * 3, *s_vcov2d = s_buf + PT * 6,
-          *s_vcov3d = s_buf + PT * 9;
-    if (live) {
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            s_vmean[tid * 3 + i] = o_mean[i];
-            s_vscale[tid * 3 + i] = o_scale[i];
-            s_vcov2d[tid * 3 + i] = o_cov2d[i];
-        }
-#pragma unroll
-        for (int i = 0; i < 6; ++i) s_vcov3d[tid * 6 + i] = o_cov3d[i];
-        v_quat[idx] = o_quat;
-    }
-    __syncthreads();
-    slab_store<3, PT>(s_vmean, v_mean3d, base * 3, n * 3);
-    slab_store<3, PT>(s_vscale, v_scale, base * 3, n * 3);
-    slab_store<3, PT>(s_vcov2d, v_cov2d, base * 3, n * 3);
-    slab_store<6, PT>(s_vcov3d, v_cov3d, base * 6, n * 6);
+    warp_store_aos<3>(strip, o_mean, v_mean3d, wfirst * 3, n * 3, lane);
+    warp_store_aos<3>(strip, o_scale, v_scale, wfirst * 3, n * 3, lane);
+    warp_store_aos<4>(strip, o_quat, v_quat, wfirst * 4, n * 4, lane);
+    if (v_cov2d) warp_store_aos<3>(strip, o_cov2d, v_cov2d, wfirst * 3, n * 3, lane);
+    if (v_cov3d) warp_store_aos<6>(strip, o_cov3d, v_cov3d, wfirst * 6, n * 6, lane);
 }
 
 // batched cameras: adds one view's staged v_mean3d (3n) / v_scale (3n) / v_quat (4n) to the sums
@@ -509,7 +545,7 @@ int launch_project_bwd(cudaStream_t stream, const ProjectBwdParams &p, const flo
     project_bwd_kernel<<<blocks, PT, 0, stream>>>(
         p, means3d, scales, reinterpret_cast<const float4 *>(quats), viewmat, cov3ds, radii,
         conics, compensation, v_compensation, reinterpret_cast<const float2 *>(v_xy), v_depth,
-        v_conic, v_mean3d, v_scale, reinterpret_cast<float4 *>(v_quat), v_cov2d, v_cov3d);
+        v_conic, v_mean3d, v_scale, v_quat, v_cov2d, v_cov3d);
     JSB_CUDA_OK(cudaGetLastError());
     note_launch();
     return 0;

@@ -84,98 +84,18 @@ __global__ void __launch_bounds__(256) radix_hist_scan_kernel(unsigned *__restri
     h[threadIdx.x] = e;
 }
 
-// ---- live-bit depth sort: range of the real keys ---------------------------------------------
-// Depth keys are the float bits of view-space depths; a scene's depths span a small part of the
-// float range, so the top byte(s) of `key - min` are zero and the passes over them are identities
-// (C3: depths 5..11 -> 0x40A00000..0x41300000, span < 2^24 -> three passes instead of four).
-// Gaussians that hit no tile carry kDepthSentinel; they are left out of the range and re-based to
-// `span` (their place in the order does not matter: they emit nothing).
-constexpr unsigned kDepthSentinel = 0xFFFFFFFFu;
-// mm[0] = max over real keys of ~key (= ~min), mm[1] = max over real keys; zero = no real key yet
-__device__ __forceinline__ void live_range(const unsigned *__restrict__ mm, unsigned &kmin,
-                                           unsigned &span) {
-    const unsigned inv_min = __ldg(mm), kmax = __ldg(mm + 1);
-    kmin = ~inv_min;
-    span = (kmax >= kmin) ? kmax - kmin : 0u;  // no real key at all: everything re-bases to 0
-}
-__device__ __forceinline__ unsigned live_rebase(unsigned key, unsigned kmin, unsigned span) {
-    return (key == kDepthSentinel) ? span : key - kmin;
-}
-
-__global__ void __launch_bounds__(256)
-radix_minmax_kernel(const unsigned *__restrict__ keys, unsigned n, unsigned *__restrict__ mm) {
-    __shared__ unsigned s_mm[2];
-    if (threadIdx.x < 2) s_mm[threadIdx.x] = 0;
-    __syncthreads();
-    unsigned inv_min = 0, kmax = 0;
-    auto take = [&](unsigned k) {
-        if (k != kDepthSentinel) { inv_min = max(inv_min, ~k); kmax = max(kmax, k); }
-    };
-    const unsigned nvec = n / 4;
-    const unsigned stride = gridDim.x * 256u;
-    for (unsigned v = blockIdx.x * 256u + threadIdx.x; v < nvec; v += stride) {
-        const uint4 q = __ldg(reinterpret_cast<const uint4 *>(keys) + v);
-        take(q.x); take(q.y); take(q.z); take(q.w);
-    }
-    if (blockIdx.x == 0)
-        for (unsigned i = nvec * 4 + threadIdx.x; i < n; i += 256) take(keys[i]);
-    inv_min = __reduce_max_sync(0xffffffffu, inv_min);
-    kmax = __reduce_max_sync(0xffffffffu, kmax);
-    if ((threadIdx.x & 31) == 0) { atomicMax(&s_mm[0], inv_min); atomicMax(&s_mm[1], kmax); }
-    __syncthreads();
-    if (threadIdx.x < 2 && s_mm[threadIdx.x]) atomicMax(&mm[threadIdx.x], s_mm[threadIdx.x]);
-}
-
-// radix_hist_kernel<uint32_t> on the re-based keys (all four passes)
-__global__ void __launch_bounds__(256)
-radix_hist_live_kernel(const unsigned *__restrict__ keys, unsigned n,
-                       const unsigned *__restrict__ mm, unsigned *__restrict__ ghist /*[4][256]*/) {
-    __shared__ unsigned s_h[MAX_PASSES * RADIX];
-    for (int i = threadIdx.x; i < MAX_PASSES * RADIX; i += 256) s_h[i] = 0;
-    __syncthreads();
-    unsigned kmin, span;
-    live_range(mm, kmin, span);
-    // identity passes need no histogram -- and theirs would be the worst one to build: every key
-    // increments the same shared-memory word (bin 0)
-    int live_passes = 0;
-    while (live_passes < MAX_PASSES && (span >> (8 * live_passes)) != 0u) ++live_passes;
-    auto count = [&](unsigned k) {
-        const unsigned r = live_rebase(k, kmin, span);
-#pragma unroll
-        for (int ps = 0; ps < MAX_PASSES; ++ps)
-            if (ps < live_passes) atomicAdd(&s_h[ps * RADIX + ((r >> (8 * ps)) & 255u)], 1u);
-    };
-    const unsigned nvec = n / 4;
-    const unsigned stride = gridDim.x * 256u;
-    for (unsigned v = blockIdx.x * 256u + threadIdx.x; v < nvec; v += stride) {
-        const uint4 q = __ldg(reinterpret_cast<const uint4 *>(keys) + v);
-        count(q.x); count(q.y); count(q.z); count(q.w);
-    }
-    if (blockIdx.x == 0)
-        for (unsigned i = nvec * 4 + threadIdx.x; i < n; i += 256) count(keys[i]);
-    __syncthreads();
-    for (int i = threadIdx.x; i < MAX_PASSES * RADIX; i += 256) {
-        const unsigned c = s_h[i];
-        if (c) atomicAdd(&ghist[i], c);
-    }
-}
-
 // ---- one onesweep pass ------------------------------------------------------------------------
 // CHAIN = true : onesweep (tile order from a ticket, cross-tile digit offsets by chained look-back)
 // CHAIN = false: downsweep of the upsweep/scan/downsweep variant: `status` holds, digit-major
 //                [256][tiles], the row-exclusive tile offsets and `gbase` the 256 row totals; no
 //                inter-CTA dependency, no spinning.
-// LIVE (live-bit depth sort, below): 1 = first pass, re-bases every key to `key - min` as it is
-//                loaded (the re-based keys are what this pass writes and later passes read);
-//                2 = later pass.  Either way a pass whose digit is 0 for every key -- (max - min)
-//                >> shift == 0, read from `mm` -- is the identity and only copies the values.
-template <typename KeyT, int RS_ITEMS, bool CHAIN, int LIVE = 0>
+template <typename KeyT, int RS_ITEMS, bool CHAIN>
 __global__ void __launch_bounds__(RS_THREADS)
 onesweep_pass_kernel(const KeyT *__restrict__ keys_in, const unsigned *__restrict__ vals_in,
                      KeyT *__restrict__ keys_out, unsigned *__restrict__ vals_out, unsigned n,
                      int shift, int live_bits, const unsigned *__restrict__ gbase /*[256]*/,
                      unsigned *__restrict__ status, unsigned *__restrict__ ticket,
-                     int *__restrict__ err, const unsigned *__restrict__ mm = nullptr) {
+                     int *__restrict__ err) {
     __shared__ unsigned s_whist[RS_WARPS * RADIX];  // per-warp digit counts -> exclusive over warps
     __shared__ unsigned s_binstart[RADIX];          // exclusive scan of the CTA histogram
     __shared__ unsigned s_goff[RADIX];              // global offset minus s_binstart (wraps)
@@ -186,17 +106,6 @@ onesweep_pass_kernel(const KeyT *__restrict__ keys_in, const unsigned *__restric
     __shared__ unsigned s_vals[RS_TILE];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    unsigned live_min = 0, live_span = 0;
-    if constexpr (LIVE != 0) {
-        live_range(mm, live_min, live_span);
-        if ((live_span >> shift) == 0) {  // uniform over the grid: nobody waits on a look-back
-            const unsigned base = blockIdx.x * (unsigned)(RS_THREADS * RS_ITEMS);
-            const unsigned cnt = min((unsigned)(RS_THREADS * RS_ITEMS), n - base);
-            for (unsigned pos = tid; pos < cnt; pos += RS_THREADS)
-                vals_out[base + pos] = vals_in[base + pos];
-            return;
-        }
-    }
     if (CHAIN && tid == 0) s_tile = atomicAdd(ticket, 1u);
     for (int i = tid; i < RS_WARPS * RADIX; i += RS_THREADS) s_whist[i] = 0;
     __syncthreads();
@@ -214,9 +123,6 @@ onesweep_pass_kernel(const KeyT *__restrict__ keys_in, const unsigned *__restric
         const unsigned o = wbase + i * 32;
         key[i] = (o < count) ? keys_in[tile_base + o] : (KeyT)~(KeyT)0;
         val[i] = (o < count) ? vals_in[tile_base + o] : 0u;
-        if constexpr (LIVE == 1) {
-            if (o < count) key[i] = (KeyT)live_rebase((unsigned)key[i], live_min, live_span);
-        }
     }
 
     // stable ranking inside the warp's chunk: memory order == (item, lane) order.
@@ -457,51 +363,6 @@ int radix_sort_pairs(cudaStream_t stream, KeyT *keys_a, KeyT *keys_b, unsigned *
         JSB_CUDA_OK(cudaGetLastError());
     note_launch();
         KeyT *tk = kin; kin = kout; kout = tk;
-        unsigned *tv = vin; vin = vout; vout = tv;
-        *result_in_b = !*result_in_b;
-    }
-    return 0;
-}
-
-// Depth order of the Gaussians on the live key bits only (option "sortlive"): one extra pass over
-// the keys finds min / max of the real keys, every digit is taken from `key - min`, and passes
-// whose digit is zero for all keys degenerate to a copy of the values.  The order of the values is
-// the one radix_sort_pairs<uint32_t>(bits = 32) produces for every Gaussian that hits a tile; the
-// key buffers are scratch afterwards (they hold re-based keys, unsorted after an identity pass).
-int radix_sort_depth_live(cudaStream_t stream, uint32_t *keys_a, uint32_t *keys_b, unsigned *vals_a,
-                          unsigned *vals_b, unsigned n, void *scratch, int *err, bool *result_in_b) {
-    if (n >= kChainFreeMin)  // (the chain-free path re-reads its keys per pass: not re-based yet)
-        return radix_sort_pairs<uint32_t>(stream, keys_a, keys_b, vals_a, vals_b, n, 32, scratch,
-                                          err, result_in_b);
-    *result_in_b = false;
-    if (n == 0) return 0;
-    const unsigned tiles = num_tiles_of(n);
-    unsigned *ghist = reinterpret_cast<unsigned *>(scratch);
-    unsigned *tickets = ghist + MAX_PASSES * RADIX;
-    unsigned *mm = tickets + 8;  // two of the twelve spare words behind the four tickets
-    unsigned *status = tickets + 16;
-    JSB_CUDA_OK(cudaMemsetAsync(scratch, 0, radix_scratch_bytes(n, 32), stream));
-    const unsigned blocks = min(ceil_div(n, 256u * 32u), 148u * 8u);
-    radix_minmax_kernel<<<blocks, 256, 0, stream>>>(keys_a, n, mm);
-    JSB_CUDA_OK(cudaGetLastError());
-    radix_hist_live_kernel<<<blocks, 256, 0, stream>>>(keys_a, n, mm, ghist);
-    JSB_CUDA_OK(cudaGetLastError());
-    radix_hist_scan_kernel<<<MAX_PASSES, 256, 0, stream>>>(ghist);
-    JSB_CUDA_OK(cudaGetLastError());
-    note_launch(3);
-    uint32_t *kin = keys_a, *kout = keys_b;
-    unsigned *vin = vals_a, *vout = vals_b;
-    for (int ps = 0; ps < MAX_PASSES; ++ps) {
-        if (ps == 0)
-            onesweep_pass_kernel<uint32_t, JSB_RADIX_ITEMS, true, 1><<<tiles, RS_THREADS, 0, stream>>>(
-                kin, vin, kout, vout, n, 0, 8, ghist, status, tickets, err, mm);
-        else
-            onesweep_pass_kernel<uint32_t, JSB_RADIX_ITEMS, true, 2><<<tiles, RS_THREADS, 0, stream>>>(
-                kin, vin, kout, vout, n, 8 * ps, 8, ghist + ps * RADIX,
-                status + (size_t)ps * tiles * RADIX, tickets + ps, err, mm);
-        JSB_CUDA_OK(cudaGetLastError());
-        note_launch();
-        uint32_t *tk = kin; kin = kout; kout = tk;
         unsigned *tv = vin; vin = vout; vout = tv;
         *result_in_b = !*result_in_b;
     }

@@ -20,6 +20,7 @@
 #include "common.cuh"
 #include "kernels.cuh"
 #include "raster_cull.cuh"
+#include "raster_hits.cuh"
 
 namespace jsb {
 namespace {
@@ -693,45 +694,57 @@ raster_bwd16x2p_kernel(const RasterParams p, const unsigned *__restrict__ ids_so
     }
 }
 
-// ---- packed two-pixel backward, ONE CTA barrier per batch (option "bwd1bar", experimental) ----
-// raster_bwd16x2p_kernel with the staging re-ordered like raster_fwd16x2s_kernel (raster_fwd.cu):
-// the cull masks of batch b+1 are computed by each thread right after it has walked batch b, and
-// a single barrier then means both "batch b is free" and "batch b+1 is visible".  Shared memory
-// is one struct per buffer.  The walk and all arithmetic are the default kernel's text.
-template <bool CULL, bool ABS>
-__global__ void __launch_bounds__(RB2, JSB_BWD_CTAS)
-raster_bwd16x2ps_kernel(const RasterParams p, const unsigned *__restrict__ ids_sorted,
+// ---- hit-driven backward: one independent warp per 8x8 quadrant ---------------------------------
+// The forward rasteriser (raster_fwd16x2_kernel) records, per quadrant warp and per group of 32
+// list entries, a bitmask of the entries for which at least one of the warp's 64 pixels passed the
+// accept test (hit_words layout: raster_hits.cuh).  Every (pixel, Gaussian) pair the backward has
+// to differentiate lies in such an entry, so this kernel
+//   * never stages or cull-tests an entry its warp does not visit (the batch kernels above stage
+//     and mask every entry of the tile from the top down: ~500 per tile at C3, of which a warp
+//     visits ~40),
+//   * needs no CTA: a CTA IS one warp = one quadrant (4 per tile), there is no barrier anywhere,
+//     and a quadrant with few visits frees its slot instead of waiting for the tile's slowest,
+//   * walks a DENSE array of visits (no find-first-set walk over candidate masks).
+// Per span of 32 hit words (1024 list entries) the lanes expand their word into a list of visit
+// positions in shared memory (newest first); visits are then staged 32 at a time -- lane j gathers
+// the sorted id and the 48-byte record of visit j (cp.async, double buffered, ids one sub-chunk
+// further ahead) -- and replayed with exactly the arithmetic of raster_bwd16x2p_kernel, including
+// the deferred cross-lane reduction.
+constexpr int HB_SPAN = 32;  // hit words expanded at a time
+#ifndef JSB_BWDH_CTAS
+#define JSB_BWDH_CTAS 20     // resident one-warp CTAs per SM the register allocation is bounded for
+#endif
+
+struct HbStage {      // one sub-chunk of <= 32 visits
+    float4 A[32];     // x, y, opac, conic.x
+    float4 B[32];     // conic.y, conic.z, r, g
+    float4 C[32];     // b, Gaussian id (bits), sorted index (bits), -
+};
+
+template <bool ABS>
+__global__ void __launch_bounds__(32, JSB_BWDH_CTAS)
+raster_bwd_hits_kernel(const RasterParams p, const unsigned *__restrict__ ids_sorted,
                        const int2 *__restrict__ tile_bins, const SplatRecord *__restrict__ records,
+                       const unsigned *__restrict__ hit_words,
                        const float *__restrict__ background, const float *__restrict__ final_Ts,
                        const int *__restrict__ final_idx, const float *__restrict__ v_out_img,
                        const float *__restrict__ v_out_alpha_img, float *__restrict__ v_xy,
                        float *__restrict__ v_xy_abs, float *__restrict__ v_conic,
                        float *__restrict__ v_colors, float *__restrict__ v_opacity) {
     constexpr int NV = ABS ? 11 : 9;
-    constexpr int EPT = JSB_BWD_EPT;      // staged entries per thread and batch
-    constexpr int BATCH = RB2 * EPT;
-    // one struct per buffer: every shared address of a batch is one base register + a constant
-    struct Stage {
-        float4 A[BATCH];          // x, y, opac, conic.x      (cp.async staging)
-        float4 B[BATCH];          // conic.y, conic.z, r, g
-        float C[BATCH];           // b
-        unsigned Id[BATCH];       // Gaussian id
-        unsigned char M[BATCH];   // quadrant cull mask
-    };
-    __shared__ Stage st[2];
-    __shared__ int s_max[RB2 / 32];
-    __shared__ __align__(16) float sRed[(RB2 / 32) * NV * RED_STRIDE];
+    __shared__ HbStage st[2];
+    __shared__ unsigned short s_list[HB_SPAN * 32];
+    __shared__ __align__(16) float red[NV * RED_STRIDE];
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    float *red = sRed + warp * NV * RED_STRIDE;
-    const unsigned tile = p.band_y0 * p.tiles_x + blockIdx.x;
+    const int lane = threadIdx.x;
+    const unsigned quad = blockIdx.x & 3u, tile_local = blockIdx.x >> 2;
+    const unsigned tile = p.band_y0 * p.tiles_x + tile_local;
     const unsigned tile_y = tile / p.tiles_x, tile_x = tile - tile_y * p.tiles_x;
-    const unsigned j = tile_x * 16 + (warp & 1) * 8 + (lane & 7);
-    const unsigned i0 = tile_y * 16 + (warp >> 1) * 8 + (lane >> 3), i1 = i0 + 4;
+    const unsigned j = tile_x * 16 + (quad & 1) * 8 + (lane & 7);
+    const unsigned i0 = tile_y * 16 + (quad >> 1) * 8 + (lane >> 3), i1 = i0 + 4;
     const float px = (float)j + 0.5f, py0 = (float)i0 + 0.5f, py1 = (float)i1 + 0.5f;
     const bool in0 = (i0 < p.img_h) && (j < p.img_w), in1 = (i1 < p.img_h) && (j < p.img_w);
     const int2 range = tile_bins[tile];
-    const int qbit = (warp & 1) + 4 * (warp >> 1);
 
     float Tf0 = 1.f, Tf1 = 1.f, voa0 = 0.f, voa1 = 0.f;
     float3 vo0 = make_float3(0.f, 0.f, 0.f), vo1 = vo0;
@@ -750,8 +763,11 @@ raster_bwd16x2ps_kernel(const RasterParams p, const unsigned *__restrict__ ids_s
         vo1 = make_float3(v_out_img[pix * 3], v_out_img[pix * 3 + 1], v_out_img[pix * 3 + 2]);
         voa1 = v_out_alpha_img ? v_out_alpha_img[pix] : 0.f;
     }
+    const int wmax = __reduce_max_sync(0xffffffffu, max(bf0, bf1));
+    const int top = min(range.y - 1, wmax);
+    if (top < range.x) return;  // nothing in this quadrant was composited (warp-uniform)
+
     const float3 bg = make_float3(__ldg(background), __ldg(background + 1), __ldg(background + 2));
-    // per-pixel constants as {pixel 0, pixel 1} pairs
     const float2 tfc2 = f2(Tf0 * (voa0 - (vo0.x * bg.x + vo0.y * bg.y + vo0.z * bg.z)),
                            Tf1 * (voa1 - (vo1.x * bg.x + vo1.y * bg.y + vo1.z * bg.z)));
     const float2 vox2 = f2(vo0.x, vo1.x), voy2 = f2(vo0.y, vo1.y), voz2 = f2(vo0.z, vo1.z);
@@ -760,19 +776,7 @@ raster_bwd16x2ps_kernel(const RasterParams p, const unsigned *__restrict__ ids_s
     float2 T2 = f2(Tf0, Tf1);
     float2 bufx2 = f2(0.f, 0.f), bufy2 = bufx2, bufz2 = bufx2;
 
-    int wmax = max(bf0, bf1);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
-    if (lane == 0) s_max[warp] = wmax;
-    __syncthreads();
-    int tmax = s_max[0];
-#pragma unroll
-    for (int w = 1; w < RB2 / 32; ++w) tmax = max(tmax, s_max[w]);
-    const int top = min(range.y - 1, tmax);
-    if (top < range.x) return;  // nothing in this tile was composited (uniform across the CTA)
-    const int num_batches = (top - range.x + BATCH) / BATCH;
-    const float tile_x0 = (float)(tile_x * 16), tile_y0 = (float)(tile_y * 16);
-
+    // lane L (even, L/2 < NV) owns output row L/2 of the reduced gradient
     const int slot = lane >> 1;
     float *out_base;
     int out_stride;
@@ -783,53 +787,6 @@ raster_bwd16x2ps_kernel(const RasterParams p, const unsigned *__restrict__ ids_s
     else { out_base = v_xy_abs + (slot - 9); out_stride = 2; }
     const bool writer = ((lane & 1) == 0) && slot < NV;
 
-    auto load_id = [&](int bb, int h) -> unsigned {
-        const int idx = top - BATCH * bb - (tid + h * RB2);
-        return (bb < num_batches && idx >= range.x) ? ids_sorted[idx] : 0u;
-    };
-    auto issue = [&](int bb, int h, unsigned g) {
-        const int t = tid + h * RB2;
-        if (top - BATCH * bb - t >= range.x) {
-            const SplatRecord *r = records + g;
-            cp_async16(&st[bb & 1].A[t], &r->q0);
-            cp_async16(&st[bb & 1].B[t], &r->q1);
-            cp_async4(&st[bb & 1].C[t], &r->q2);
-            st[bb & 1].Id[t] = g;
-        }
-    };
-    // cull masks of this thread's entries of batch bb (its own cp.async data has been waited for)
-    auto stage_mask = [&](int bb) {
-#pragma unroll
-        for (int h = 0; h < EPT; ++h) {
-            const int t = tid + h * RB2;
-            unsigned mask = 0;
-            if (top - BATCH * bb - t >= range.x) {
-                const float4 q0 = st[bb & 1].A[t];
-                const float2 q1 = *reinterpret_cast<const float2 *>(&st[bb & 1].B[t]);
-                mask = CULL ? cull_mask16(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, tile_x0, tile_y0) : 0xFFu;
-            }
-            st[bb & 1].M[t] = (unsigned char)(mask | (mask >> 2));
-        }
-    };
-    unsigned gn[EPT];
-#pragma unroll
-    for (int h = 0; h < EPT; ++h) issue(0, h, load_id(0, h));
-#pragma unroll
-    for (int h = 0; h < EPT; ++h) gn[h] = load_id(1, h);
-    cp_async_wait_all();
-    stage_mask(0);
-    __syncthreads();  // records, ids and masks of batch 0 are visible
-    if (1 < num_batches) {
-#pragma unroll
-        for (int h = 0; h < EPT; ++h) issue(1, h, gn[h]);
-    }
-#pragma unroll
-    for (int h = 0; h < EPT; ++h) gn[h] = load_id(2, h);
-
-    // The cross-lane reduction of a visit is deferred into the NEXT visit: its shared-memory reads,
-    // adds, shuffle and RED have nothing to do with that visit's sigma / alpha arithmetic, so in
-    // one straight-line block the scheduler overlaps the two latency chains (the reduction tail
-    // held 27 % of the kernel's stall samples when it ran at the end of its own visit).
     bool pend = false;       // `red` holds the partials of a visit that is not reduced yet
     unsigned pend_id = 0;    // its Gaussian
     const float4 *red_row = reinterpret_cast<const float4 *>(
@@ -846,21 +803,72 @@ raster_bwd16x2ps_kernel(const RasterParams p, const unsigned *__restrict__ ids_s
         return u0.x + u0.y;
     };
 
-    for (int b = 0; b < num_batches; ++b) {
-        const int batch_end = top - BATCH * b;  // slot t holds sorted index batch_end - t
-        const Stage &S = st[b & 1];
+    const unsigned *hw = hit_words + hit_quadrant_offset(range, tile_local, quad);
+    const int rel_top = top - range.x;
+    for (int gs = rel_top >> 5; gs >= 0; gs -= HB_SPAN) {
+        // ---- expand this span's hit words into visit positions, newest first -------------------
+        const int g = gs - lane;  // lane's group (32 list entries) of this span
+        unsigned w = g >= 0 ? __ldg(hw + g) : 0u;
+        if (g == (rel_top >> 5)) w &= (2u << (rel_top & 31)) - 1u;  // entries above `top`
+        const int cnt = __popc(w);
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int tt = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += tt;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        if (total == 0) continue;  // warp-uniform
+        __syncwarp();              // every lane is done reading the previous span's list
+        {
+            int pos = incl - cnt;
+            while (w) {
+                const int b = 31 - __clz(w);
+                w &= ~(1u << b);
+                s_list[pos++] = (unsigned short)((lane << 5) | b);  // (group offset in span, bit)
+            }
+        }
+        __syncwarp();
+        // list entry e -> sorted index: group gs - (e >> 5), bit e & 31
+        auto sorted_index = [&](int o) -> int {
+            const unsigned e = s_list[o];
+            return range.x + ((gs - (int)(e >> 5)) << 5) + (int)(e & 31u);
+        };
+        auto issue = [&](int s, int sidx, unsigned gid) {  // lane's visit of sub-chunk s
+            if (s * 32 + lane < total) {
+                HbStage &S = st[s & 1];
+                const SplatRecord *r = records + gid;
+                cp_async16(&S.A[lane], &r->q0);
+                cp_async16(&S.B[lane], &r->q1);
+                cp_async4(&S.C[lane].x, &r->q2);
+                S.C[lane].y = __uint_as_float(gid);
+                S.C[lane].z = __int_as_float(sidx);
+            }
+        };
+        const int nsub = (total + 31) >> 5;
+        int sidx_n = lane < total ? sorted_index(lane) : 0;
+        unsigned gid_n = lane < total ? ids_sorted[sidx_n] : 0u;
+        issue(0, sidx_n, gid_n);
+        sidx_n = 32 + lane < total ? sorted_index(32 + lane) : 0;
+        gid_n = 32 + lane < total ? ids_sorted[sidx_n] : 0u;
+
+        for (int s = 0; s < nsub; ++s) {
+            cp_async_wait_all();
+            __syncwarp();  // sub-chunk s landed; every lane is done with sub-chunk s - 1
+            if (s + 1 < nsub) issue(s + 1, sidx_n, gid_n);
+            {
+                const int o = (s + 2) * 32 + lane;
+                sidx_n = o < total ? sorted_index(o) : 0;
+                gid_n = o < total ? ids_sorted[sidx_n] : 0u;
+            }
+            const HbStage &S = st[s & 1];
+            const int cs = min(32, total - s * 32);
 #pragma unroll 1
-        for (int k = 0; k < BATCH / 32; ++k) {
-            // entries newer than the warp's largest final index cannot be valid for any lane
-            if (batch_end - (k * 32 + 31) > wmax) continue;
-            const unsigned m = S.M[k * 32 + lane];
-            unsigned bits = __ballot_sync(0xffffffffu, (m >> qbit) & 1u);
-            while (bits) {
-                const int t = k * 32 + __ffs(bits) - 1;
-                bits &= bits - 1;
+            for (int t = 0; t < cs; ++t) {
                 const float4 a = S.A[t];    // {x, y, opacity, cx}
                 const float4 bq = S.B[t];   // {cy, cz, r, g}
-                float total = reduce_rows();  // previous visit's partials (stale rows if !pend)
+                const float4 cq = S.C[t];   // {b, id, sorted index, -}
+                float total_r = reduce_rows();  // previous visit's partials (stale rows if !pend)
                 // conic_sigma (common.cuh) lane by lane, in the reference's operation order
                 const float dx = fsub(a.x, px);
                 const float2 dy2 = __fadd2_rn(bc(a.y), npy2);
@@ -875,25 +883,25 @@ raster_bwd16x2ps_kernel(const RasterParams p, const unsigned *__restrict__ ids_s
                 const float vis0 = ex2_approx(x2.x), vis1 = ex2_approx(x2.y);
                 const float2 ar2 = __fmul2_rn(bc(a.z), f2(vis0, vis1));  // opacity * vis
                 const float al0 = fminf(ar2.x, 0.99f), al1 = fminf(ar2.y, 0.99f);
-                const int sidx = batch_end - t;
+                const int sidx = __float_as_int(cq.z);
                 const bool ok0 = in0 && (sidx <= bf0) && !(sg2.x < 0.f) && !(al0 < kAlphaMin);
                 const bool ok1 = in1 && (sidx <= bf1) && !(sg2.y < 0.f) && !(al1 < kAlphaMin);
-                total += __shfl_xor_sync(0xffffffffu, total, 1);
-                if (writer && pend) atomicAdd(out_base + pend_id * (unsigned)out_stride, total);
+                total_r += __shfl_xor_sync(0xffffffffu, total_r, 1);
+                if (writer && pend) atomicAdd(out_base + pend_id * (unsigned)out_stride, total_r);
                 pend = false;
                 if (!__any_sync(0xffffffffu, ok0 || ok1)) continue;
 
-                // invalid pixels: alpha = opacity*vis = 0 and ra = 1 make every partial exactly 0
-                // and leave T and the colour buffer unchanged
-                const float2 al2 = f2(ok0 ? al0 : 0.f, ok1 ? al1 : 0.f);
-                const float2 av2 = f2(ok0 ? ar2.x : 0.f, ok1 ? ar2.y : 0.f);   // opacity * vis
+                // invalid pixels: vis = 0 makes alpha = 0, ra = rcp(1) = 1 and every partial
+                // exactly 0, and leaves T and the colour buffer unchanged
                 const float2 vis2 = f2(ok0 ? vis0 : 0.f, ok1 ? vis1 : 0.f);
+                const float2 av2 = __fmul2_rn(bc(a.z), vis2);                  // opacity * vis
+                const float2 al2 = f2(fminf(av2.x, 0.99f), fminf(av2.y, 0.99f));
                 const float2 om2 = __ffma2_rn(al2, bc(-1.f), bc(1.f));         // 1 - alpha
                 float r0, r1;
                 asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(om2.x));
                 asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(om2.y));
-                const float2 ra2 = f2(ok0 ? r0 : 1.f, ok1 ? r1 : 1.f);
-                const float cb = S.C[t];
+                const float2 ra2 = f2(r0, r1);
+                const float cb = cq.x;
                 T2 = __fmul2_rn(T2, ra2);
                 const float2 fac2 = __fmul2_rn(al2, T2);
                 // v_alpha = sum_c v_out_c (T c_c - buf_c ra) + tfc ra
@@ -936,26 +944,14 @@ raster_bwd16x2ps_kernel(const RasterParams p, const unsigned *__restrict__ ids_s
                 for (int r = 0; r < NV; ++r) red[r * RED_STRIDE + lane] = v[r];
                 __syncwarp();
                 pend = true;
-                pend_id = S.Id[t];
+                pend_id = __float_as_uint(cq.y);
             }
         }
-        if (b + 1 >= num_batches) break;
-        // this thread's entries of batch b+1 have landed: their masks; then the ONE barrier of the
-        // batch -- every warp is done with batch b (its buffers are free) and batch b+1 is visible
-        cp_async_wait_all();
-        stage_mask(b + 1);
-        __syncthreads();
-        if (b + 2 < num_batches) {
-#pragma unroll
-            for (int h = 0; h < EPT; ++h) issue(b + 2, h, gn[h]);
-        }
-#pragma unroll
-        for (int h = 0; h < EPT; ++h) gn[h] = load_id(b + 3, h);
     }
     if (pend) {  // warp-uniform: the last visit of this warp
-        float total = reduce_rows();
-        total += __shfl_xor_sync(0xffffffffu, total, 1);
-        if (writer) atomicAdd(out_base + pend_id * (unsigned)out_stride, total);
+        float total_r = reduce_rows();
+        total_r += __shfl_xor_sync(0xffffffffu, total_r, 1);
+        if (writer) atomicAdd(out_base + pend_id * (unsigned)out_stride, total_r);
     }
 }
 
@@ -1014,7 +1010,7 @@ __global__ void raster_bwd_generic_kernel(
 extern bool g_disable_cull;
 bool g_bwd_one_pixel = false;  // option "bwd2px" = 0: the one-pixel-per-thread kernel
 bool g_bwd_scalar = false;     // option "bwdpk" = 0: the two-pixel kernel with scalar FP32 math
-bool g_bwd_one_barrier = false;  // option "bwd1bar" = 1 (experimental): one barrier per batch
+bool g_bwd_no_hits = false;    // option "bwdhits" = 0: the batch kernels even when hit words exist
 
 template <bool CULL, bool ABS>
 static void launch_x2(cudaStream_t stream, unsigned tiles, const RasterParams &p,
@@ -1022,11 +1018,7 @@ static void launch_x2(cudaStream_t stream, unsigned tiles, const RasterParams &p
                       const float *background, const float *final_Ts, const int *final_idx,
                       const float *v_out, const float *v_out_alpha, float *v_xy, float *v_xy_abs,
                       float *v_conic, float *v_colors, float *v_opacity) {
-    if (g_bwd_one_barrier && !g_bwd_scalar)
-        raster_bwd16x2ps_kernel<CULL, ABS><<<tiles, RB2, 0, stream>>>(
-            p, ids_sorted, tile_bins, records, background, final_Ts, final_idx, v_out, v_out_alpha,
-            v_xy, v_xy_abs, v_conic, v_colors, v_opacity);
-    else if (g_bwd_scalar)
+    if (g_bwd_scalar)
         raster_bwd16x2_kernel<CULL, ABS><<<tiles, RB2, 0, stream>>>(
             p, ids_sorted, tile_bins, records, background, final_Ts, final_idx, v_out, v_out_alpha,
             v_xy, v_xy_abs, v_conic, v_colors, v_opacity);
@@ -1041,10 +1033,20 @@ int launch_raster_bwd(cudaStream_t stream, const RasterParams &p, const unsigned
                       const int2 *tile_bins, const SplatRecord *records, const float *background,
                       const float *final_Ts, const int *final_idx, const float *v_out,
                       const float *v_out_alpha, float *v_xy, float *v_xy_abs, float *v_conic,
-                      float *v_colors, float *v_opacity) {
+                      float *v_colors, float *v_opacity, const unsigned *hit_words) {
     const unsigned tiles = p.tiles_x * (p.band_y1 - p.band_y0);
     if (tiles == 0) return 0;
-    if (p.block_width == 16 && !(g_bwd_one_pixel && v_xy_abs)) {
+    if (p.block_width == 16 && hit_words && !g_bwd_no_hits && !g_bwd_one_pixel && !g_bwd_scalar) {
+        // one independent warp per quadrant, driven by the forward's hit words
+        if (v_xy_abs)
+            raster_bwd_hits_kernel<true><<<tiles * 4, 32, 0, stream>>>(
+                p, ids_sorted, tile_bins, records, hit_words, background, final_Ts, final_idx, v_out,
+                v_out_alpha, v_xy, v_xy_abs, v_conic, v_colors, v_opacity);
+        else
+            raster_bwd_hits_kernel<false><<<tiles * 4, 32, 0, stream>>>(
+                p, ids_sorted, tile_bins, records, hit_words, background, final_Ts, final_idx, v_out,
+                v_out_alpha, v_xy, v_xy_abs, v_conic, v_colors, v_opacity);
+    } else if (p.block_width == 16 && !(g_bwd_one_pixel && v_xy_abs)) {
         if (v_xy_abs) {
             if (g_disable_cull)
                 launch_x2<false, true>(stream, tiles, p, ids_sorted, tile_bins, records, background, final_Ts, final_idx, v_out, v_out_alpha, v_xy, v_xy_abs, v_conic, v_colors, v_opacity);

@@ -25,6 +25,7 @@
 #include "common.cuh"
 #include "kernels.cuh"
 #include "raster_cull.cuh"
+#include "raster_hits.cuh"
 
 namespace jsb {
 namespace {
@@ -160,7 +161,8 @@ __global__ void __launch_bounds__(RF2, JSB_FWD_CTAS)
 raster_fwd16x2_kernel(const RasterParams p, const unsigned *__restrict__ ids_sorted,
                       const int2 *__restrict__ tile_bins, const SplatRecord *__restrict__ records,
                       const float *__restrict__ background, float *__restrict__ final_Ts,
-                      int *__restrict__ final_idx, float *__restrict__ out_img) {
+                      int *__restrict__ final_idx, float *__restrict__ out_img,
+                      unsigned *__restrict__ hit_words) {
     constexpr int EPT = JSB_FWD_EPT;      // staged entries per thread and batch
     constexpr int BATCH = RF2 * EPT;
     __shared__ float4 sA[2][BATCH];
@@ -185,6 +187,9 @@ raster_fwd16x2_kernel(const RasterParams p, const unsigned *__restrict__ ids_sor
     float T0 = 1.f, T1 = 1.f;
     int cur0 = 0, cur1 = 0;
     float r0 = 0.f, g0 = 0.f, b0 = 0.f, r1 = 0.f, g1 = 0.f, b1 = 0.f;
+    // this quadrant's hit words (raster_hits.cuh): which entries the backward has to replay
+    unsigned *hw = hit_words ? hit_words + hit_quadrant_offset(range, blockIdx.x, (unsigned)warp)
+                             : nullptr;
 
     auto load_id = [&](int b, int h) -> unsigned {
         const int idx = range.x + BATCH * b + tid + h * RF2;
@@ -237,9 +242,12 @@ raster_fwd16x2_kernel(const RasterParams p, const unsigned *__restrict__ ids_sor
             if (warp_done) continue;
             const unsigned m = sMask[k * 32 + lane];
             unsigned bits = __ballot_sync(0xffffffffu, (m >> qbit) & 1u);
+            unsigned hit = 0;  // entries of this group some pixel of this lane accepted
             while (bits) {
                 const int t = k * 32 + __ffs(bits) - 1;
-                bits &= bits - 1;
+                const unsigned rest = bits & (bits - 1);
+                const unsigned low = bits ^ rest;  // the bit of entry t
+                bits = rest;
                 const float4 a = sA[buf][t];
                 const float4 bq = sB[buf][t];
                 const float dx = fsub(a.x, px);
@@ -272,6 +280,7 @@ raster_fwd16x2_kernel(const RasterParams p, const unsigned *__restrict__ ids_sor
                 const bool ok0 = !done0 && !(sg0 < 0.f) && !(al0 < kAlphaMin);
                 const bool ok1 = !done1 && !(sg1 < 0.f) && !(al1 < kAlphaMin);
                 if (ok0 || ok1) {
+                    hit |= low;
                     const float cb = sC[buf][t];
                     if (ok0) {
                         const float next_T = fmul(T0, fsub(1.f, al0));
@@ -301,190 +310,12 @@ raster_fwd16x2_kernel(const RasterParams p, const unsigned *__restrict__ ids_sor
                     }
                 }
             }
+            if (hw) {  // one word per (quadrant, group of 32 entries) the warp entered
+                hit = __reduce_or_sync(0xffffffffu, hit);
+                if (lane == 0) hw[b * (BATCH / 32) + k] = hit;
+            }
             warp_done = __all_sync(0xffffffffu, done0 && done1);
         }
-    }
-    cp_async_wait_all();
-
-    const float bg0 = __ldg(background), bg1 = __ldg(background + 1), bg2 = __ldg(background + 2);
-    if (in0) {
-        const size_t pix = (size_t)i0 * p.img_w + j;
-        final_Ts[pix] = T0;
-        final_idx[pix] = cur0;
-        out_img[pix * 3 + 0] = ffma(T0, bg0, r0);
-        out_img[pix * 3 + 1] = ffma(T0, bg1, g0);
-        out_img[pix * 3 + 2] = ffma(T0, bg2, b0);
-    }
-    if (in1) {
-        const size_t pix = (size_t)i1 * p.img_w + j;
-        final_Ts[pix] = T1;
-        final_idx[pix] = cur1;
-        out_img[pix * 3 + 0] = ffma(T1, bg0, r1);
-        out_img[pix * 3 + 1] = ffma(T1, bg1, g1);
-        out_img[pix * 3 + 2] = ffma(T1, bg2, b1);
-    }
-}
-
-// ---- two pixels per thread, ONE CTA barrier per batch (option "fwd1bar", experimental) --------
-// Same arithmetic, same walk, same outputs as raster_fwd16x2_kernel<CULL, true>; only the staging
-// is re-ordered.  There, a batch costs two barriers (records landed / masks written) and the cull
-// masks are computed between them while nothing else can run.  Here every thread computes the
-// mask of ITS entry of batch b+1 right after it has finished walking batch b (its own cp.async
-// data is visible to itself after the wait, no barrier needed), and one barrier then says both
-// "everyone is done with batch b" and "records and masks of batch b+1 are visible": warps that
-// finish a batch early spend the wait on the mask work instead of idling through it twice.
-template <bool CULL>
-__global__ void __launch_bounds__(RF2, JSB_FWD_CTAS)
-raster_fwd16x2s_kernel(const RasterParams p, const unsigned *__restrict__ ids_sorted,
-                       const int2 *__restrict__ tile_bins, const SplatRecord *__restrict__ records,
-                       const float *__restrict__ background, float *__restrict__ final_Ts,
-                       int *__restrict__ final_idx, float *__restrict__ out_img) {
-    constexpr int BATCH = RF2;
-    constexpr bool PACKED = true;
-    // one struct per buffer: every shared address of a batch is one base register + a constant
-    struct Stage {
-        float4 A[BATCH];          // x, y, opac, conic.x
-        float4 B[BATCH];          // conic.y, conic.z, r, g
-        float C[BATCH];           // b
-        unsigned char M[BATCH];   // quadrant cull mask
-    };
-    __shared__ Stage st[2];
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const unsigned tile = p.band_y0 * p.tiles_x + blockIdx.x;
-    const unsigned tile_y = tile / p.tiles_x, tile_x = tile - tile_y * p.tiles_x;
-    const unsigned j = tile_x * 16 + (warp & 1) * 8 + (lane & 7);
-    const unsigned i0 = tile_y * 16 + (warp >> 1) * 8 + (lane >> 3), i1 = i0 + 4;
-    const float px = (float)j + 0.5f, py0 = (float)i0 + 0.5f, py1 = (float)i1 + 0.5f;
-    const bool in0 = (i0 < p.img_h) && (j < p.img_w), in1 = (i1 < p.img_h) && (j < p.img_w);
-    // (32-bit flags: as `bool` they live as bytes and cost two extra instructions per visit)
-    unsigned done0 = in0 ? 0u : 1u, done1 = in1 ? 0u : 1u;
-    const int qbit = (warp & 1) + 4 * (warp >> 1);  // quadrant bit of the row-folded cull mask
-
-    const int2 range = tile_bins[tile];
-    const int num_batches = (range.y - range.x + BATCH - 1) / BATCH;
-    const float tile_x0 = (float)(tile_x * 16), tile_y0 = (float)(tile_y * 16);
-
-    float T0 = 1.f, T1 = 1.f;
-    int cur0 = 0, cur1 = 0;
-    float r0 = 0.f, g0 = 0.f, b0 = 0.f, r1 = 0.f, g1 = 0.f, b1 = 0.f;
-
-    auto load_id = [&](int b) -> unsigned {
-        const int idx = range.x + BATCH * b + tid;
-        return (b < num_batches && idx < range.y) ? ids_sorted[idx] : 0u;
-    };
-    auto issue = [&](int b, unsigned g) {  // this thread's record of batch b -> buffer b & 1
-        if (range.x + BATCH * b + tid < range.y) {
-            const SplatRecord *r = records + g;
-            cp_async16(&st[b & 1].A[tid], &r->q0);
-            cp_async16(&st[b & 1].B[tid], &r->q1);
-            cp_async4(&st[b & 1].C[tid], &r->q2);
-        }
-    };
-    auto stage_mask = [&](int b) {  // after this thread's cp.async of batch b has been waited for
-        unsigned mask = 0;
-        if (range.x + BATCH * b + tid < range.y) {
-            const float4 q0 = st[b & 1].A[tid];
-            const float2 q1 = *reinterpret_cast<const float2 *>(&st[b & 1].B[tid]);
-            mask = CULL ? cull_mask16(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, tile_x0, tile_y0) : 0xFFu;
-        }
-        st[b & 1].M[tid] = (unsigned char)(mask | (mask >> 2));
-    };
-    unsigned gn = 0;
-    if (num_batches > 0) {
-        issue(0, load_id(0));
-        gn = load_id(1);
-        cp_async_wait_all();
-        stage_mask(0);
-        __syncthreads();  // records and masks of batch 0 are visible
-        if (1 < num_batches) issue(1, gn);
-        gn = load_id(2);
-    }
-
-    for (int b = 0; b < num_batches; ++b) {
-        const int batch_start = range.x + BATCH * b;
-        const Stage &S = st[b & 1];
-        bool warp_done = __all_sync(0xffffffffu, (done0 & done1) != 0u);
-#pragma unroll
-        for (int k = 0; k < BATCH / 32; ++k) {
-            if (warp_done) continue;
-            const unsigned m = S.M[k * 32 + lane];
-            unsigned bits = __ballot_sync(0xffffffffu, (m >> qbit) & 1u);
-            while (bits) {
-                const int t = k * 32 + __ffs(bits) - 1;
-                bits &= bits - 1;
-                const float4 a = S.A[t];
-                const float4 bq = S.B[t];
-                const float dx = fsub(a.x, px);
-                float sg0, sg1, al0, al1;
-                if (PACKED) {
-                    // conic_sigma (common.cuh) for both pixels at once with FMUL2 / FFMA2 / FADD2
-                    // (one issue slot, two FP32 lanes, each rounding like the scalar form), the
-                    // per-Gaussian operands as scalar broadcasts: same operation order per pixel,
-                    // so the outputs stay bit-identical to the scalar path
-                    const float2 dy2 = __fadd2_rn(make_float2(a.y, a.y), make_float2(-py0, -py1));
-                    const float ca = fmul(a.w, dx);                                   // cx dx
-                    const float ce = fmul(bq.x, dx);                                  // cy dx
-                    const float2 b2 = __fmul2_rn(make_float2(bq.y, bq.y), dy2);       // cz dy
-                    const float2 c2 = __fmul2_rn(dy2, b2);
-                    float2 s2 = __ffma2_rn(make_float2(dx, dx), make_float2(ca, ca), c2);
-                    s2 = __fmul2_rn(s2, make_float2(0.5f, 0.5f));
-                    const float2 sg2 = __ffma2_rn(make_float2(ce, ce), dy2, s2);
-                    const float2 x2 = __fmul2_rn(sg2, make_float2(kNegLog2e, kNegLog2e));
-                    const float2 ar2 = __fmul2_rn(make_float2(a.z, a.z),
-                                                  make_float2(ex2_approx(x2.x), ex2_approx(x2.y)));
-                    sg0 = sg2.x; sg1 = sg2.y;
-                    al0 = fminf(ar2.x, 0.999f); al1 = fminf(ar2.y, 0.999f);
-                } else {
-                    const float dy0 = fsub(a.y, py0), dy1 = fsub(a.y, py1);
-                    sg0 = conic_sigma(a.w, bq.x, bq.y, dx, dy0);
-                    sg1 = conic_sigma(a.w, bq.x, bq.y, dx, dy1);
-                    al0 = fminf(fmul(a.z, ex2_approx(fmul(sg0, kNegLog2e))), 0.999f);
-                    al1 = fminf(fmul(a.z, ex2_approx(fmul(sg1, kNegLog2e))), 0.999f);
-                }
-                const bool ok0 = (done0 == 0u) && !(sg0 < 0.f) && !(al0 < kAlphaMin);
-                const bool ok1 = (done1 == 0u) && !(sg1 < 0.f) && !(al1 < kAlphaMin);
-                if (ok0 || ok1) {
-                    const float cb = S.C[t];
-                    if (ok0) {
-                        const float next_T = fmul(T0, fsub(1.f, al0));
-                        if (next_T <= kTmin) {
-                            done0 = 1u;  // this Gaussian is not composited
-                        } else {
-                            const float vis = fmul(T0, al0);
-                            r0 = ffma(vis, bq.z, r0);
-                            g0 = ffma(vis, bq.w, g0);
-                            b0 = ffma(vis, cb, b0);
-                            T0 = next_T;
-                            cur0 = batch_start + t;
-                        }
-                    }
-                    if (ok1) {
-                        const float next_T = fmul(T1, fsub(1.f, al1));
-                        if (next_T <= kTmin) {
-                            done1 = 1u;
-                        } else {
-                            const float vis = fmul(T1, al1);
-                            r1 = ffma(vis, bq.z, r1);
-                            g1 = ffma(vis, bq.w, g1);
-                            b1 = ffma(vis, cb, b1);
-                            T1 = next_T;
-                            cur1 = batch_start + t;
-                        }
-                    }
-                }
-            }
-            warp_done = __all_sync(0xffffffffu, (done0 & done1) != 0u);
-        }
-
-        if (b + 1 >= num_batches) break;
-        // my entry of batch b+1 has landed: its mask; then the one barrier of the batch -- everyone
-        // has finished walking batch b (its buffers are free again) and batch b+1 is visible
-        cp_async_wait_all();
-        stage_mask(b + 1);
-        if (__syncthreads_count((done0 & done1) != 0u) >= RF2) break;
-        if (b + 2 < num_batches) issue(b + 2, gn);
-        gn = load_id(b + 3);
     }
     cp_async_wait_all();
 
@@ -591,23 +422,18 @@ __global__ void fill_background_kernel(const float *__restrict__ background, siz
 bool g_disable_cull = false;  // test hook (capi: jsb200_set_option)
 bool g_fwd_scalar = false;  // option "fwdpk" = 0: scalar FP32 math in the two-pixel kernel
 bool g_fwd_one_pixel = false;  // option "fwd2px" = 0: the one-pixel-per-thread kernel
-bool g_fwd_one_barrier = false;  // option "fwd1bar" = 1 (experimental): one barrier per batch
 
 int launch_raster_fwd(cudaStream_t stream, const RasterParams &p, const unsigned *ids_sorted,
                       const int2 *tile_bins, const SplatRecord *records, const float *background,
-                      float *final_Ts, int *final_idx, float *out_img) {
+                      float *final_Ts, int *final_idx, float *out_img, unsigned *hit_words,
+                      bool *wrote_hits) {
     const unsigned tiles = p.tiles_x * (p.band_y1 - p.band_y0);
+    if (wrote_hits) *wrote_hits = false;
     if (tiles == 0) return 0;
-    if (p.block_width == 16 && !g_fwd_one_pixel && g_fwd_one_barrier && !g_fwd_scalar) {
-        if (g_disable_cull)
-            raster_fwd16x2s_kernel<false><<<tiles, RF2, 0, stream>>>(
-                p, ids_sorted, tile_bins, records, background, final_Ts, final_idx, out_img);
-        else
-            raster_fwd16x2s_kernel<true><<<tiles, RF2, 0, stream>>>(
-                p, ids_sorted, tile_bins, records, background, final_Ts, final_idx, out_img);
-    } else if (p.block_width == 16 && !g_fwd_one_pixel) {
+    if (p.block_width == 16 && !g_fwd_one_pixel) {
+        if (wrote_hits) *wrote_hits = hit_words != nullptr;
 #define JSB_FWD2(C, P) raster_fwd16x2_kernel<C, P><<<tiles, RF2, 0, stream>>>( \
-        p, ids_sorted, tile_bins, records, background, final_Ts, final_idx, out_img)
+        p, ids_sorted, tile_bins, records, background, final_Ts, final_idx, out_img, hit_words)
         if (g_disable_cull) { if (g_fwd_scalar) JSB_FWD2(false, false); else JSB_FWD2(false, true); }
         else { if (g_fwd_scalar) JSB_FWD2(true, false); else JSB_FWD2(true, true); }
 #undef JSB_FWD2

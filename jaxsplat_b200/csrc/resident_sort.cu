@@ -1,0 +1,330 @@
+// Depth order of the Gaussians in ONE kernel launch, for sm_100a.
+//
+// Replaces (together with rowcol_lists.cu) the reference's cub::DeviceRadixSort::SortPairs over
+// 64-bit (tile | depth) keys (lib/ops.cu:722-757): here only the N Gaussians are ordered by their
+// 32-bit depth keys -- stable, ties keep index order -- and the per-tile lists are distributed
+// from that order.
+//
+// Why a new kernel: at N = 1M a 4-pass onesweep (ours or CUB's, measured on the same box:
+// 91 vs 92 us, profiles/r02a_depth_sort_vs_cub.json) moves 16 MB per pass, ~3 us of HBM time, and
+// spends the other ~16 us of every pass on launch ramp and the chained look-back through ~245
+// tiles.  This kernel is launched once, cooperatively, with at most one CTA per SM; a pass is
+//   A. rank the CTA's keys by digit (stable, per-warp ballots), publish 512 digit counts
+//      and group the tile by digit in shared memory
+//   -- grid barrier --
+//   B. every CTA sums the counts of the CTAs before it (16-byte loads, all independent), scans
+//      the digit totals and scatters its tile
+//   -- grid barrier --
+// so the cross-CTA dependency is two flag barriers instead of a serial chain, nothing is
+// launched between passes, and for N <= 148 x 8192 the keys never leave registers between A and B.
+// Only the live bits are sorted: the digits come from `key - min` (min / max of the real keys
+// arrive from the projection kernel), 9 bits per pass, so a scene whose far/near ratio is below
+// 2^8 sorts in THREE passes (27 live bits) and most synthetic ones (C3: 24 bits) too.  The first
+// pass makes up the ids (no identity array is read), the last pass writes only the ids.
+// Algorithmic HBM bytes per Gaussian: 4 + (passes - 1) * 16 + 4.
+#include <algorithm>
+
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace jsb {
+namespace {
+
+constexpr int DS_THREADS = 512;
+constexpr int DS_WARPS = DS_THREADS / 32;
+constexpr int DS_IPT = 16;                       // items per thread and tile, at most
+constexpr int DS_TILE = DS_THREADS * DS_IPT;     // 8192
+constexpr int DS_BITS = 9;
+constexpr int DS_BINS = 1 << DS_BITS;            // == DS_THREADS: thread d owns digit d
+static_assert(DS_BINS == DS_THREADS, "one thread per digit");
+constexpr unsigned kSentinelKey = 0xFFFFFFFFu;   // Gaussians that hit no tile
+
+struct DsParams {
+    const unsigned *keys_in;  // depth keys as the projection wrote them
+    unsigned *kA, *vA, *kB, *vB;  // ping-pong (kA may be keys_in itself)
+    unsigned *order;          // out: Gaussian ids in (depth, index) order
+    unsigned n;
+    const unsigned *mm;       // {max(~key), max(key)} over the real keys; {0, 0} = none
+    unsigned *hist;           // [grid][DS_BINS]
+    unsigned *flags;          // [grid] barrier epochs, zero at launch
+    int *err;
+    unsigned tile_items;      // multiple of 512, <= DS_TILE
+    unsigned subtiles;        // tiles per CTA
+};
+
+struct DsSmem {
+    unsigned whist[DS_WARPS][DS_BINS];  // per-warp digit counts -> exclusive over the warps
+    unsigned keys[DS_TILE];
+    unsigned vals[DS_TILE];
+    unsigned binstart[DS_BINS];         // exclusive scan of the tile's digit counts
+    unsigned goff[DS_BINS];             // global offset of the digit's run minus binstart
+    uint4 part_before[4][DS_BINS / 4];  // prefix partial sums: [row phase][digit group of 4]
+    uint4 part_all[4][DS_BINS / 4];
+    unsigned ws[DS_WARPS + 1];
+};
+
+__device__ __forceinline__ unsigned ld_acquire(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ void st_release(unsigned *p, unsigned v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Barrier over the co-resident grid.  CTA c publishes flags[c] = epoch (one plain release store:
+// no same-address atomics queueing up in the L2) and thread t polls flags[t], so a CTA sees all
+// arrivals one L2 round trip after the last one.
+__device__ __forceinline__ void grid_barrier(unsigned *flags, unsigned G, unsigned c, unsigned epoch,
+                                             int *err) {
+    __syncthreads();  // every store of this CTA happens-before thread 0's release
+    if (threadIdx.x == 0) st_release(flags + c, epoch);
+    for (unsigned t = threadIdx.x; t < G; t += DS_THREADS) {
+        int spins = 0;
+        while (ld_acquire(flags + t) < epoch) {
+            if (++spins > kSpinLimit) { *err = 3; break; }  // a scheduling bug becomes an error
+        }
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(DS_THREADS, 1) resident_depth_sort_kernel(const DsParams P) {
+    extern __shared__ __align__(16) unsigned char ds_raw[];
+    DsSmem &S = *reinterpret_cast<DsSmem *>(ds_raw);
+    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const unsigned G = gridDim.x, c = blockIdx.x;
+
+    const unsigned inv_min = __ldg(P.mm), kmax = __ldg(P.mm + 1);
+    const unsigned kmin = ~inv_min;
+    const unsigned span = (kmax >= kmin) ? kmax - kmin : 0u;
+    const int bits = span ? 32 - __clz(span) : 0;
+    const int passes = (bits + DS_BITS - 1) / DS_BITS;
+    const unsigned cta_items = P.tile_items * P.subtiles;
+    if (passes == 0) {  // one depth (or no real key at all): index order is the stable order
+        const unsigned b0 = c * cta_items;
+        for (unsigned i = tid; i < cta_items && b0 + i < P.n; i += DS_THREADS) P.order[b0 + i] = b0 + i;
+        return;
+    }
+    const int width = (bits + passes - 1) / passes;  // <= 9 live bits per pass
+    const unsigned ipt = P.tile_items / DS_THREADS;  // <= DS_IPT
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const bool single = P.subtiles == 1;
+    unsigned epoch = 0;
+
+    unsigned key[DS_IPT], val[DS_IPT];
+    unsigned short rank[DS_IPT];
+    unsigned cta_count = 0, binstart = 0;
+
+    for (int ps = 0; ps < passes; ++ps) {
+        const int shift = ps * width;
+        const int w = min(width, bits - shift);
+        const unsigned dmask = (1u << w) - 1u;
+        const bool last = ps + 1 == passes;
+        const unsigned *ksrc = ps == 0 ? P.keys_in : ((ps & 1) ? P.kB : P.kA);
+        const unsigned *vsrc = (ps & 1) ? P.vB : P.vA;
+        unsigned *kdst = (ps & 1) ? P.kA : P.kB, *vdst = last ? P.order : ((ps & 1) ? P.vA : P.vB);
+
+        // loads the tile into registers (warp-striped: memory order == (warp, item, lane) order)
+        auto load_tile = [&](unsigned tile, bool with_vals) -> unsigned {
+            const unsigned base = tile * P.tile_items;
+            const unsigned count = base < P.n ? min(P.tile_items, P.n - base) : 0u;
+            const unsigned wbase = warp * (ipt * 32u) + lane;
+#pragma unroll
+            for (int i = 0; i < DS_IPT; ++i) {
+                const unsigned o = wbase + i * 32u;
+                if ((unsigned)i < ipt && o < count) {
+                    unsigned k = __ldcg(ksrc + base + o);
+                    if (ps == 0) k = (k == kSentinelKey) ? span : k - kmin;  // live bits only
+                    key[i] = k;
+                    if (with_vals) val[i] = ps == 0 ? base + o : __ldcg(vsrc + base + o);
+                }
+            }
+            return count;
+        };
+        // stable rank of every item inside its warp's chunk + per-warp digit counts; leaves the
+        // exclusive-over-warps counts in S.whist, the tile's digit count of digit `tid` in
+        // cta_count and its exclusive scan over the digits in binstart / S.binstart
+        auto rank_tile = [&](unsigned count) {
+            for (unsigned i = tid; i < DS_WARPS * DS_BINS; i += DS_THREADS) (&S.whist[0][0])[i] = 0u;
+            __syncthreads();
+            unsigned *wh = S.whist[warp];
+            const unsigned wbase = warp * (ipt * 32u) + lane;
+#pragma unroll
+            for (int i = 0; i < DS_IPT; ++i) {
+                if ((unsigned)i >= ipt) break;  // warp-uniform
+                const bool valid = (wbase + i * 32u) < count;
+                const unsigned d = valid ? ((key[i] >> shift) & dmask) : 0u;
+                // peers = lanes holding the same digit: one ballot per live digit bit (the native
+                // MATCH.ANY is data dependent on B200 and slower when most lanes differ)
+                unsigned peers = __ballot_sync(0xffffffffu, valid);
+                peers = valid ? peers : ~peers;
+#pragma unroll
+                for (int b = 0; b < DS_BITS; ++b) {
+                    if (b < w) {
+                        const unsigned m = __ballot_sync(0xffffffffu, (d >> b) & 1u);
+                        peers &= ((d >> b) & 1u) ? m : ~m;
+                    }
+                }
+                const unsigned lower = peers & lt_mask;
+                unsigned pre = 0;
+                if (valid) pre = wh[d];
+                __syncwarp();
+                if (valid && lower == 0) wh[d] = pre + __popc(peers);
+                __syncwarp();
+                rank[i] = (unsigned short)(pre + __popc(lower));
+            }
+            __syncthreads();
+            cta_count = 0;
+#pragma unroll
+            for (int ww = 0; ww < DS_WARPS; ++ww) {
+                const unsigned cc = S.whist[ww][tid];
+                S.whist[ww][tid] = cta_count;
+                cta_count += cc;
+            }
+            unsigned total;
+            binstart = cta_exclusive_scan<DS_THREADS>(cta_count, &total, S.ws);
+            S.binstart[tid] = binstart;
+            __syncthreads();
+        };
+
+        // tile in registers -> shared memory, grouped by digit, in stable order
+        auto reorder_tile = [&](unsigned count) {
+            const unsigned *wh = S.whist[warp];
+            const unsigned wbase = warp * (ipt * 32u) + lane;
+#pragma unroll
+            for (int i = 0; i < DS_IPT; ++i) {
+                if ((unsigned)i < ipt && (wbase + i * 32u) < count) {
+                    const unsigned d = (key[i] >> shift) & dmask;
+                    const unsigned pos = S.binstart[d] + wh[d] + rank[i];
+                    S.keys[pos] = key[i];
+                    S.vals[pos] = val[i];
+                }
+            }
+        };
+
+        // ---- A: digit counts of this CTA's tiles ------------------------------------------------
+        unsigned count = 0, cta_total = 0;
+        for (unsigned st = 0; st < P.subtiles; ++st) {
+            count = load_tile(c * P.subtiles + st, single);
+            rank_tile(count);
+            cta_total += cta_count;
+        }
+        P.hist[(size_t)c * DS_BINS + tid] = cta_total;
+        // (single tile: the reorder needs nothing from the other CTAs -- done under the barrier)
+        if (single) reorder_tile(count);
+        grid_barrier(P.flags, G, c, ++epoch, P.err);
+
+        // ---- B: offsets, scatter ------------------------------------------------------------------
+        // Column sums of the G x 512 count matrix: rows before this CTA and all rows.  Thread
+        // (phase, dg) takes every 4th row of digits 4 dg .. 4 dg + 3 with 16-byte loads, all of
+        // them independent (one or two L2 round trips instead of G / 8).
+        {
+            const unsigned phase = tid >> 7, dg = tid & 127u;
+            const uint4 *h4 = reinterpret_cast<const uint4 *>(P.hist);
+            uint4 before = make_uint4(0u, 0u, 0u, 0u), all = before;
+            for (unsigned r0 = phase; r0 < G; r0 += 4 * 13) {
+                uint4 h[13];
+#pragma unroll
+                for (int u = 0; u < 13; ++u) {
+                    const unsigned r = r0 + 4 * u;
+                    h[u] = r < G ? __ldcg(h4 + (size_t)r * (DS_BINS / 4) + dg) : make_uint4(0u, 0u, 0u, 0u);
+                }
+#pragma unroll
+                for (int u = 0; u < 13; ++u) {
+                    all.x += h[u].x; all.y += h[u].y; all.z += h[u].z; all.w += h[u].w;
+                    if (r0 + 4 * u < c) {
+                        before.x += h[u].x; before.y += h[u].y; before.z += h[u].z; before.w += h[u].w;
+                    }
+                }
+            }
+            S.part_before[phase][dg] = before;
+            S.part_all[phase][dg] = all;
+        }
+        __syncthreads();
+        unsigned before = 0, all = 0;
+#pragma unroll
+        for (int ph = 0; ph < 4; ++ph) {
+            before += reinterpret_cast<const unsigned *>(S.part_before[ph])[tid];
+            all += reinterpret_cast<const unsigned *>(S.part_all[ph])[tid];
+        }
+        unsigned grand;
+        const unsigned dbase = cta_exclusive_scan<DS_THREADS>(all, &grand, S.ws);
+        unsigned run = dbase + before;  // next global slot of digit `tid` for this CTA
+        for (unsigned st = 0; st < P.subtiles; ++st) {
+            if (!single) {
+                count = load_tile(c * P.subtiles + st, true);
+                rank_tile(count);
+                reorder_tile(count);
+            }
+            S.goff[tid] = run - binstart;
+            run += cta_count;
+            __syncthreads();
+            // consecutive positions of one digit go to consecutive addresses
+            for (unsigned pos = tid; pos < count; pos += DS_THREADS) {
+                const unsigned k = S.keys[pos];
+                const unsigned o = pos + S.goff[(k >> shift) & dmask];
+                if (!last) kdst[o] = k;
+                vdst[o] = S.vals[pos];
+            }
+            __syncthreads();
+        }
+        if (!last) grid_barrier(P.flags, G, c, ++epoch, P.err);
+    }
+}
+
+struct DeviceFacts {
+    bool known = false, cooperative = false;
+    int max_ctas = 0;
+};
+DeviceFacts g_facts[64];
+
+}  // namespace
+
+size_t resident_sort_scratch_bytes(unsigned n) {
+    (void)n;
+    return (size_t)(1024 + 4) * DS_BINS * sizeof(unsigned);  // hist rows (grid <= 1024) + barrier flags
+}
+
+// returns 0 on success, 1 on error, -1 if this device cannot run it (caller falls back)
+int resident_depth_sort(cudaStream_t stream, const unsigned *keys_in, unsigned *kA, unsigned *vA,
+                        unsigned *kB, unsigned *vB, unsigned *order, unsigned n,
+                        const unsigned *mm, void *scratch, int *err) {
+    if (n == 0) return 0;
+    int dev = 0;
+    JSB_CUDA_OK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return -1;
+    DeviceFacts &F = g_facts[dev];
+    if (!F.known) {
+        int coop = 0, sms = 0, per_sm = 0;
+        JSB_CUDA_OK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+        JSB_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        JSB_CUDA_OK(cudaFuncSetAttribute(resident_depth_sort_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)sizeof(DsSmem)));
+        JSB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+            &per_sm, resident_depth_sort_kernel, DS_THREADS, sizeof(DsSmem)));
+        F.cooperative = coop != 0 && per_sm > 0;
+        F.max_ctas = std::min(sms, 1024);  // one CTA per SM is all the parallelism a pass needs
+        F.known = true;
+    }
+    if (!F.cooperative) return -1;
+    DsParams P;
+    P.keys_in = keys_in; P.kA = kA; P.vA = vA; P.kB = kB; P.vB = vB; P.order = order;
+    P.n = n; P.mm = mm; P.err = err;
+    P.hist = reinterpret_cast<unsigned *>(scratch);
+    P.flags = P.hist + (size_t)1024 * DS_BINS;
+    const unsigned G0 = (unsigned)F.max_ctas;
+    P.subtiles = std::max(1u, ceil_div(n, G0 * (unsigned)DS_TILE));
+    const unsigned per_tile = ceil_div(n, G0 * P.subtiles);
+    P.tile_items = std::min((unsigned)DS_TILE, std::max(512u, ceil_div(per_tile, 512u) * 512u));
+    const unsigned grid = ceil_div(n, P.tile_items * P.subtiles);
+    JSB_CUDA_OK(cudaMemsetAsync(P.flags, 0, 1024 * sizeof(unsigned), stream));
+    void *args[] = {(void *)&P};
+    JSB_CUDA_OK(cudaLaunchCooperativeKernel((const void *)resident_depth_sort_kernel, dim3(grid),
+                                            dim3(DS_THREADS), args, sizeof(DsSmem), stream));
+    note_launch();
+    return 0;
+}
+
+}  // namespace jsb

@@ -125,7 +125,11 @@ def test_product_never_imports_the_oracle():
 def test_descriptor_band_extension():
     d = _ffi.make_descriptor(10, (1080, 1920), (1.0, 1.0), (0.0, 0.0), 1.0, 0.01, 16)
     b = _ffi.with_band(d, 17, 34)
-    assert b[:76] == d[:76]
+    # the band lives in the 4 pad bytes and is marked by a magic block_dim_2d.z (1 in a reference
+    # descriptor, whose pad bytes are uninitialised and must therefore never be read as a band)
+    assert b[:72] == d[:72]
+    assert struct.unpack("<I", d[72:76])[0] == 1
+    assert struct.unpack("<I", b[72:76])[0] == 0x4A534231
     assert struct.unpack("<I", b[76:])[0] == (17 | (34 << 16))
     with pytest.raises(RuntimeError):
         _ffi.with_band(d, 5, 5)

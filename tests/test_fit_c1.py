@@ -94,8 +94,6 @@ def test_config1_fit_with_the_native_adam_step():
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(__import__("os").environ.get("JSB_EXPERIMENTAL") != "1",
-                    reason="experimental kernel, not yet verified on a GPU")
 def test_native_mse_loss_and_gradient_match_torch():
     """losses.mse_loss_and_grad (one kernel) against the eager expressions: the cotangent bit for
     bit, the loss to float tolerance; sizes that are and are not multiples of 4, a misaligned view"""

@@ -243,6 +243,17 @@ def _bw8_scene():
     return s
 
 
+def _tall_grid_scene():
+    """> 256 tile rows (and > 8192 tiles): the grid is binned strip by strip by the fallback list
+    builder, which needs per-strip intersection counts the fused projection kernel does not
+    produce -- the fused render must take the unfused prep here (it used to fail with "strip
+    intersection counts sum to 0")"""
+    s = synthetic.benchmark_scene(20000, (2200, 260), scale_max=0.3, seed=17)
+    s.block_size = 8
+    s.f = (130.0, 1100.0)
+    return s
+
+
 def _grads_of(scene, target, fused):
     jsb.set_fused_render(fused)
     try:
@@ -254,7 +265,8 @@ def _grads_of(scene, target, fused):
 @pytest.mark.parametrize("scene_fn", [lambda: synthetic.make_config("C1"),
                                       lambda: synthetic.make_config("C2", num_points=40000),
                                       lambda: synthetic.benchmark_scene(0 + 513, (40, 72), seed=2),
-                                      lambda: _bw8_scene()])
+                                      lambda: _bw8_scene(),
+                                      lambda: _tall_grid_scene()])
 def test_fused_render_equals_the_two_op_chain(scene_fn):
     """jsb200_render_fwd/bwd (one call per direction) vs project -> rasterize through autograd"""
     s = scene_fn()
@@ -309,3 +321,31 @@ def test_fused_render_empty_frame():
     img.sum().backward()
     for p in ps:
         assert torch.count_nonzero(p.grad) == 0
+
+
+def test_reference_style_descriptor_with_garbage_pad_bytes_renders_the_full_frame():
+    """the reference's make_descriptor leaves the 4 pad bytes uninitialised (lib/ffi.cu:15-52); a
+    descriptor whose pad holds stack garbage must NOT be read as a tile-row band: only
+    jsb200_set_descriptor_band (which also stamps a marker) selects one"""
+    g = synthetic.make_config("C2", num_points=20000)
+    inp = G.scene_inputs(g)
+    kw, rkw = G.scene_kw(g)
+    P = G.project_fwd(inp, kw)
+    want = G.rasterize_fwd(inp, P, rkw)
+
+    class GarbagePad:
+        def __init__(self, table):
+            self.t = table
+
+        def make_descriptor(self, *a):
+            d = bytearray(self.t.make_descriptor(*a))
+            d[76:80] = (3 | (7 << 16)).to_bytes(4, "little")  # would be the band [3, 7) if honoured
+            return bytes(d)
+
+        def call(self, *a, **k):
+            return self.t.call(*a, **k)
+
+    from jaxsplat_b200 import _ffi
+    got = G.rasterize_fwd(inp, P, rkw, table=GarbagePad(_ffi.native_table()))
+    assert torch.equal(got["final_idx"], want["final_idx"])
+    assert torch.equal(got["img"].view(torch.int32), want["img"].view(torch.int32))

@@ -263,6 +263,8 @@ def _binning_of(scene, band=None):
     H, W = scene.img_shape
     bw = scene.block_size
     tiles = ((W + bw - 1) // bw) * ((H + bw - 1) // bw)
+    if I == 0:  # nothing visible: no binning is kept (the forward only fills the background)
+        return 0, np.zeros(0, np.int32), np.zeros((tiles, 2), np.int32), [G.npy(o) for o in outs]
     got, ids, bins, _ = G.debug_binning(I, tiles)
     return I, G.npy(ids), G.npy(bins), [G.npy(o) for o in outs]
 
@@ -387,46 +389,48 @@ def test_packed_fp32x2_backward_equals_the_scalar_kernel(scene_fn):
         assert ok, (k, err, scale)
 
 
-# Written in a session without GPU access and not yet run on one: kept out of the default GPU
-# suite until its first run (JSB_EXPERIMENTAL=1 python -m pytest tests -m gpu -k live_bit).
-_experimental = pytest.mark.skipif(os.environ.get("JSB_EXPERIMENTAL") != "1",
-                                   reason="experimental option, not yet verified on a GPU")
-
-
-@_experimental
 @pytest.mark.parametrize("case", ["C1", "C2_30k", "one_depth", "wide_depth_range", "all_culled",
-                                  "ragged", "band"])
-def test_live_bit_depth_sort_builds_the_same_lists(case):
-    """option "sortlive": the depth sort takes its digits from `key - min key` and skips the
-    identity passes over the zero top bytes; sorted ids, tile bins and every forward output must
-    equal the default four-pass sort bit for bit"""
+                                  "ragged", "band", "two_tiles_per_cta", "many_equal_depths"])
+def test_resident_depth_sort_builds_the_same_lists(case):
+    """option "sort1k" (default): the depth order from ONE cooperative launch over the live bits of
+    `key - min` (resident_sort.cu) against four onesweep passes over all 32 key bits: sorted ids,
+    tile bins and every forward output must be equal bit for bit -- including one depth for
+    everything (no pass at all), a depth range with > 27 live bits (four passes), nothing visible
+    (only sentinel keys), and more Gaussians than one tile per CTA holds"""
     band = None
     if case == "C1":
         s = synthetic.make_config("C1")
     elif case == "C2_30k":
         s = synthetic.make_config("C2", num_points=30000)
-    elif case == "one_depth":       # every key equal: all four passes are identities
+    elif case == "one_depth":
         s = synthetic.benchmark_scene(5000, (160, 208), scale_max=0.3, seed=12)
         s.means3d[:, 2] = 0.25
-    elif case == "wide_depth_range":  # depths 0.1 .. 108: no zero top byte, nothing skipped
+    elif case == "wide_depth_range":  # depths 0.02 .. 3000: 28+ live bits
         s = synthetic.benchmark_scene(8000, (160, 208), scale_max=0.3, seed=13)
-        s.means3d[:, 2] = torch.linspace(-7.9, 100.0, 8000)[torch.randperm(
-            8000, generator=torch.Generator().manual_seed(1))]
+        z = torch.logspace(-1.7, 3.5, 8000)[torch.randperm(8000, generator=torch.Generator().manual_seed(1))]
+        s.means3d[:, 2] = z - 8.0
+        s.means3d[:, :2] *= (z / 8.0).unsqueeze(1)
+        s.scales *= (z / 8.0).unsqueeze(1)
     elif case == "all_culled":      # everything behind the camera: only sentinel keys
         s = synthetic.benchmark_scene(3000, (96, 128), scale_max=0.3, seed=14)
         s.means3d[:, 2] = -20.0
     elif case == "ragged":
         s = synthetic.benchmark_scene(777, (90, 50), scale_max=0.4, seed=6)
-    else:
+    elif case == "band":
         s = synthetic.benchmark_scene(20000, (320, 256), scale_max=0.4, seed=8)
         band = (5, 13)
+    elif case == "two_tiles_per_cta":  # > 148 x 8192 Gaussians: the kernel re-reads its tiles
+        s = synthetic.benchmark_scene(1_300_000, (128, 160), scale_max=0.01, seed=15)
+    else:  # depth ties across many Gaussians: stability decides the order
+        s = synthetic.benchmark_scene(40000, (160, 208), scale_max=0.2, seed=16)
+        s.means3d[:, 2] = torch.round(s.means3d[:, 2] * 4.0) / 4.0
     try:
-        _lib.set_option("sortlive", 1)
+        _lib.set_option("sort1k", 1)
         Ia, ids_a, bins_a, outs_a = _binning_of(s, band)
-        _lib.set_option("sortlive", 0)
+        _lib.set_option("sort1k", 0)
         Ib, ids_b, bins_b, outs_b = _binning_of(s, band)
     finally:
-        _lib.set_option("sortlive", 0)
+        _lib.set_option("sort1k", 1)
     assert Ia == Ib and (Ia > 0 or case == "all_culled")
     assert np.array_equal(bins_a, bins_b)
     assert np.array_equal(ids_a, ids_b)
@@ -435,42 +439,24 @@ def test_live_bit_depth_sort_builds_the_same_lists(case):
             assert np.array_equal(a, b)
 
 
-@_experimental
-@pytest.mark.parametrize("scene_fn", [_adversarial_scene, lambda: synthetic.make_config("C2", num_points=30000),
+def _long_list_scene():
+    """tile lists longer than one span of 32 hit words (1024 entries) that do not saturate: small
+    opacities, many splats per tile"""
+    s = synthetic.benchmark_scene(60000, (64, 96), scale_max=0.25, seed=31)
+    s.opacities *= 0.02
+    return s
+
+
+@pytest.mark.parametrize("scene_fn", [_adversarial_scene, _long_list_scene,
+                                      lambda: synthetic.make_config("C2", num_points=30000),
                                       lambda: synthetic.benchmark_scene(9000, (200, 120), scale_max=0.2, seed=21),
                                       lambda: synthetic.benchmark_scene(60, (40, 40), scale_max=0.3, seed=3),
-                                      lambda: synthetic.make_config("C1")])
-def test_one_barrier_forward_is_bit_identical(scene_fn):
-    """option "fwd1bar": raster_fwd16x2s_kernel (cull masks of batch b+1 computed after the walk of
-    batch b, one CTA barrier per batch) against the default two-barrier kernel: same arithmetic in
-    the same order, so not a bit may differ -- with and without culling"""
-    s = scene_fn()
-    inp = G.scene_inputs(s)
-    kw, rkw = G.scene_kw(s)
-    P = G.project_fwd(inp, kw)
-    for cull in (1, 0):
-        try:
-            _lib.set_option("cull", cull)
-            _lib.set_option("fwd1bar", 1)
-            a = G.rasterize_fwd(inp, P, rkw)
-            _lib.set_option("fwd1bar", 0)
-            b = G.rasterize_fwd(inp, P, rkw)
-        finally:
-            _lib.set_option("fwd1bar", 0)
-            _lib.set_option("cull", 1)
-        assert torch.equal(a["final_idx"], b["final_idx"])
-        assert torch.equal(a["final_Ts"].view(torch.int32), b["final_Ts"].view(torch.int32))
-        assert torch.equal(a["img"].view(torch.int32), b["img"].view(torch.int32))
-
-
-@_experimental
-@pytest.mark.parametrize("scene_fn", [_adversarial_scene, lambda: synthetic.make_config("C2", num_points=30000),
-                                      lambda: synthetic.benchmark_scene(9000, (200, 120), scale_max=0.2, seed=21),
-                                      lambda: synthetic.benchmark_scene(60, (40, 40), scale_max=0.3, seed=3)])
-def test_one_barrier_backward_equals_the_default_kernel(scene_fn):
-    """option "bwd1bar": raster_bwd16x2ps_kernel (one CTA barrier per batch) against the default
-    packed kernel: the same visits with the same arithmetic, so the only difference left is the
-    order in which the atomics of different tiles land (the reference's own run-to-run noise)"""
+                                      lambda: synthetic.benchmark_scene(3000, (70, 90), scale_max=0.01, seed=5)])
+def test_hit_driven_backward_equals_the_batch_kernel(scene_fn):
+    """option "bwdhits" (default): one warp per 8x8 quadrant replaying only the list entries the
+    forward marked as accepted (raster_bwd_hits_kernel) against the per-tile batch kernel that
+    stages and cull-tests every entry: the same pairs with the same arithmetic, so only the order of
+    the atomics differs (the reference's own run-to-run noise) -- all five outputs, v_xy_abs too"""
     s = scene_fn()
     inp = G.scene_inputs(s)
     kw, rkw = G.scene_kw(s)
@@ -478,12 +464,37 @@ def test_one_barrier_backward_equals_the_default_kernel(scene_fn):
     target = np.random.RandomState(2).rand(H, W, 3).astype(np.float32)
     v_alpha = np.random.RandomState(3).rand(H, W, 1).astype(np.float32) * 1e-3
     try:
-        _lib.set_option("bwd1bar", 1)
+        _lib.set_option("bwdhits", 1)
         a = _full_gpu(inp, kw, rkw, target, v_alpha)
-        _lib.set_option("bwd1bar", 0)
+        _lib.set_option("bwdhits", 0)
         b = _full_gpu(inp, kw, rkw, target, v_alpha)
     finally:
-        _lib.set_option("bwd1bar", 0)
+        _lib.set_option("bwdhits", 1)
     for k in ("v_colors", "v_opacity", "v_xy", "v_xy_abs", "v_conic"):
         ok, err, scale = grad_close(a[k], b[k], rel=2e-5)
         assert ok, (k, err, scale)
+
+
+def test_hit_driven_backward_through_the_fused_render_and_bands():
+    """the fused render (no v_xy_abs, token-validated binning) and a tile-row band with hit words"""
+    import jaxsplat_b200 as jsb
+    s = synthetic.make_config("C2", num_points=40000)
+    sc = s.to(G.DEV)
+    H, W = s.img_shape
+    target = torch.rand((H, W, 3), generator=torch.Generator().manual_seed(9)).to(G.DEV)
+    res = {}
+    for hits in (1, 0):
+        try:
+            _lib.set_option("bwdhits", hits)
+            for rows in (None, (5, 19)):
+                params = [p.clone().requires_grad_(True) for p in sc.params()]
+                img = jsb.render(*params, tile_rows=rows, **sc.render_kwargs())
+                y0, y1 = (0, H) if rows is None else (rows[0] * 16, min(H, rows[1] * 16))
+                (((img[y0:y1] - target[y0:y1]) ** 2).sum() / (H * W * 3)).backward()
+                res[(hits, rows)] = [G.npy(p.grad) for p in params]
+        finally:
+            _lib.set_option("bwdhits", 1)
+    for rows in (None, (5, 19)):
+        for a, b in zip(res[(1, rows)], res[(0, rows)]):
+            ok, err, scale = grad_close(a, b, rel=2e-5)
+            assert ok, (rows, err, scale)

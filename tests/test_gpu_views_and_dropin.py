@@ -182,8 +182,6 @@ def test_gradient_sink_receives_the_gradients_in_place():
     assert ok, (err, scale)
 
 
-@pytest.mark.skipif(os.environ.get("JSB_EXPERIMENTAL") != "1",
-                    reason="experimental hook, not yet verified on a GPU")
 def test_raster_bwd_event_marks_final_appearance_gradients():
     """jsb200_set_raster_bwd_event: the fused render backward records the event between its two
     kernels; a side stream that waits on it sees the final v_colors / v_opacity (they are not
