@@ -232,6 +232,8 @@ def main():
         for key in ("bwdpk", "fwdpk"):  # packed FP32x2 rasterisers (A/B: tools/gpu_pk.sh)
             if os.environ.get("JSB_" + key.upper()) == "0":
                 _lib.set_option(key, 0)
+        if os.environ.get("JSB_SPEC") == "0":  # every forward waits for the intersection count first
+            _lib.set_option("spec", 0)
         if os.environ.get("JSB_BWDHITS") == "0":  # per-tile batch backward instead of the hit-driven one
             _lib.set_option("bwdhits", 0)
         if os.environ.get("JSB_SORT1K") == "0":  # four onesweep passes instead of the resident sort

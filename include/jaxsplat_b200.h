@@ -167,6 +167,8 @@ JSB200_API unsigned long long jsb200_error_count(void);
  *               instead of the packed FP32x2 instructions of sm_100),
  *      "rowcol" (1 default; 0 builds the per-tile lists with the older counting distribution of
  *               tile_lists.cu instead of the two-level row/column distribution),
+ *      "spec" (1 default; 0 makes every forward wait for the frame's intersection count before it
+ *               launches the list builders, instead of sizing them from the previous frame),
  *      "bwdhits" (1 default; 0 runs rasterize_bwd with the per-tile batch kernel even when the
  *               forward recorded which list entries every 8x8 quadrant accepted),
  *      "sort1k" (1 default; 0 orders the Gaussians by depth with four onesweep passes over all 32
@@ -180,6 +182,11 @@ JSB200_API int jsb200_set_option(const char *key, int value);
  * Returns num_intersects, or -1 on error. */
 JSB200_API long long jsb200_debug_binning(jsb200_stream_t stream, const float *depths, int *ids_sorted,
                                int *tile_bins, long long *keys64_sorted);
+/* Copies the hit words the most recent forward rasterisation on `stream` recorded for its backward
+ * (layout: csrc/raster_hits.cuh) into a caller device buffer of max_words words.  Returns the
+ * number of words that exist, or -1 (no forward with hit words cached). */
+JSB200_API long long jsb200_debug_hit_words(jsb200_stream_t stream, unsigned *out_words,
+                                            size_t max_words);
 /* Per-stage device time, measured with CUDA events on `stream` while option "timing" is 1.
  * Synchronises the stream.  Stage order: project_fwd, bin_prep, depth_sort, emit, tile_scatter,
  * tile_offsets, raster_fwd, raster_bwd, project_bwd.  ms_out9 / calls_out9 receive accumulated
@@ -190,6 +197,11 @@ JSB200_API int jsb200_get_stage_times(jsb200_stream_t stream, double *ms_out9,
  * [3] binning cache hits, [4] last num_intersects, [5] workspace bytes, [6] kernel launches,
  * [7] last row-entry count (sum of tile-box heights) */
 JSB200_API void jsb200_get_stats(unsigned long long *out8);
+/* Forward rasterisations whose list builders + rasteriser were launched before the host knew the
+ * frame's intersection count (buffers sized from the previous frame of the same shape; option
+ * "spec", 1 default): out2[0] = launches that held, out2[1] = frames that outgrew the buffers and
+ * were rebuilt with exact sizes (same results either way). */
+JSB200_API void jsb200_get_speculation_stats(unsigned long long *out2);
 /* releases every workspace (all devices/streams). */
 JSB200_API void jsb200_release(void);
 

@@ -36,8 +36,10 @@ EXPORTS = (
     "jsb200_error_count",
     "jsb200_set_option",
     "jsb200_debug_binning",
+    "jsb200_debug_hit_words",
     "jsb200_get_stage_times",
     "jsb200_get_stats",
+    "jsb200_get_speculation_stats",
     "jsb200_release",
     "jsb200_set_raster_bwd_event",
     "jsb200_multimem_allreduce_f32",
@@ -102,11 +104,15 @@ def lib() -> ctypes.CDLL:
     L.jsb200_set_option.restype = i
     L.jsb200_debug_binning.argtypes = [vp, vp, vp, vp, vp]
     L.jsb200_debug_binning.restype = ctypes.c_longlong
+    L.jsb200_debug_hit_words.argtypes = [vp, vp, sz]
+    L.jsb200_debug_hit_words.restype = ctypes.c_longlong
     L.jsb200_get_stage_times.argtypes = [vp, ctypes.POINTER(ctypes.c_double),
                                          ctypes.POINTER(ctypes.c_ulonglong), i]
     L.jsb200_get_stage_times.restype = i
     L.jsb200_get_stats.argtypes = [ctypes.POINTER(ctypes.c_ulonglong)]
     L.jsb200_get_stats.restype = None
+    L.jsb200_get_speculation_stats.argtypes = [ctypes.POINTER(ctypes.c_ulonglong)]
+    L.jsb200_get_speculation_stats.restype = None
     L.jsb200_release.argtypes = []
     L.jsb200_release.restype = None
     L.jsb200_set_raster_bwd_event.argtypes = [vp]
@@ -137,6 +143,12 @@ def stats() -> dict:
     keys = ("rasterize_fwd_calls", "rasterize_bwd_calls", "binning_runs", "binning_cache_hits",
             "last_num_intersects", "workspace_bytes", "kernel_launches", "last_row_entries")
     return dict(zip(keys, [int(x) for x in out]))
+
+
+def speculation_stats() -> dict:
+    out = (ctypes.c_ulonglong * 2)()
+    lib().jsb200_get_speculation_stats(out)
+    return {"held": int(out[0]), "rebuilt": int(out[1])}
 
 
 def set_option(key: str, value: int) -> None:

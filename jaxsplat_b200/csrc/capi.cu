@@ -35,6 +35,8 @@ static thread_local std::string t_error;
 static thread_local bool t_has_error = false;
 static std::atomic<unsigned long long> g_error_count{0};
 static std::atomic<unsigned long long> g_stats[8];
+static std::atomic<unsigned long long> g_stats_spec_hits{0};  // forwards whose speculative launch held
+static std::atomic<unsigned long long> g_stats_spec_redo{0};  // ... and those that outgrew it (rebuilt)
 static std::atomic<unsigned long long> g_token_counter{0};  // binning tokens (never reset, never 0)
 
 void set_error(const char *fmt, ...) {
@@ -56,6 +58,7 @@ extern bool g_bwd_scalar;
 extern bool g_fwd_scalar;
 extern bool g_fwd_one_pixel;
 extern bool g_bwd_no_hits;
+extern bool g_bwd_all_entries;
 static bool g_disable_cache = false;
 static bool g_disable_rowcol = false;
 static bool g_disable_resident_sort = false;  // option "sort1k" 0: the four-pass onesweep depth sort
@@ -111,6 +114,11 @@ struct Ctx {
     unsigned long long *h_pinned = nullptr;  // [fingerprint][total][err...]
     cudaEvent_t ev_ready = nullptr;          // recorded after the D2H of `small`
     const unsigned *order_ptr = nullptr;     // the depth-sorted ids of the last prep
+    // counts of the last forward binning of this shape: the next forward sizes its buffers from
+    // them and launches the list builders + rasteriser BEFORE the host has this frame's counts
+    bool plan_valid = false;
+    unsigned plan_n = 0, plan_tiles_x = 0, plan_tiles_y = 0, plan_bw = 0, plan_band = 0;
+    unsigned long long plan_I = 0, plan_E = 0;
     unsigned long long last_rows = 0;        // sum of box heights of the last prep (row entries)
     // binning cache
     bool cache_valid = false;
@@ -461,6 +469,8 @@ static int bin_sort_impl(Ctx &c, const Descriptor &d, unsigned long long I) {
     return 0;
 }
 
+static void commit_binning(Ctx &c, const Descriptor &d, unsigned long long I, unsigned long long fp);
+
 static int bin_sort(Ctx &c, const Descriptor &d, unsigned long long I, unsigned long long fp) {
     if (I >= (1ull << 30)) {
         set_error("num_intersects=%llu exceeds the supported 2^30", I);
@@ -472,6 +482,13 @@ static int bin_sort(Ctx &c, const Descriptor &d, unsigned long long I, unsigned 
     c.cache_has_hits = false;
     int rc = tiles <= 65536 ? bin_sort_impl<uint16_t>(c, d, I) : bin_sort_impl<uint32_t>(c, d, I);
     if (rc) return rc;
+    commit_binning(c, d, I, fp);
+    return 0;
+}
+
+// the per-tile lists of `d` (I intersections) now sit in tile_ids / bins: make them the cache
+static void commit_binning(Ctx &c, const Descriptor &d, unsigned long long I, unsigned long long fp) {
+    const unsigned tiles = d.tiles_x * d.tiles_y;
     c.cache_valid = true;
     c.cache_fp_known = true;
     c.cache_token = g_token_counter.fetch_add(1) + 1;  // process-wide: never matches another context's
@@ -485,7 +502,6 @@ static int bin_sort(Ctx &c, const Descriptor &d, unsigned long long I, unsigned 
     g_stats[2].fetch_add(1);
     g_stats[4].store(I);
     g_stats[7].store(c.last_rows);
-    return 0;
 }
 
 static bool cache_hit(const Ctx &c, const Descriptor &d, unsigned long long I,
@@ -494,6 +510,99 @@ static bool cache_hit(const Ctx &c, const Descriptor &d, unsigned long long I,
            c.cache_fp == fp && c.cache_I == I &&
            c.cache_n == d.num_points && c.cache_tiles == d.tiles_x * d.tiles_y &&
            c.cache_tiles_x == d.tiles_x && c.cache_bw == d.block_width && c.cache_band == d.pad;
+}
+
+// ---- forward: lists + rasteriser, speculatively sized ------------------------------------------
+// Called with the prep (+ fingerprint) kernel, the 64-byte D2H copy, ev_ready and the depth sort
+// already enqueued.  The host needs this frame's intersection count only to size buffers; when the
+// previous frame of the same shape left its counts (training loops render the same scene over and
+// over), the buffers are sized for 1.25x those counts and the list builders and the rasteriser are
+// enqueued BEFORE the host waits for the counts -- the GPU never idles while the host wakes up and
+// issues a dozen launches (a ~30 us depth sort no longer hides that).  Kernels that touch the
+// I- / E-scale buffers check the device-side counts against the capacities first (ListGuard); if
+// the frame outgrew them nothing was written and the host falls back to the exactly sized path.
+static bool g_disable_spec = false;  // option "spec" 0: always wait for the counts first
+static RasterParams raster_params(const Descriptor &d);
+
+static int forward_lists_and_raster(Ctx &c, const Descriptor &d, const float *background,
+                                    float *final_Ts, int *final_idx, float *out_img,
+                                    bool fp_known, unsigned long long *token) {
+    cudaStream_t s = c.stream;
+    RasterParams rp = raster_params(d);
+    const BinParams bp = bin_params(d);
+    const unsigned tiles = d.tiles_x * d.tiles_y;
+    if (token) *token = 0;
+    unsigned long long Ip = 0, Ep = 0;
+    bool speculated = false, spec_hits = false;
+    if (!g_disable_spec && c.plan_valid && c.plan_I > 0 && d.num_points != 0 &&
+        c.plan_n == d.num_points && c.plan_tiles_x == d.tiles_x && c.plan_tiles_y == d.tiles_y &&
+        c.plan_bw == d.block_width && c.plan_band == d.pad && d.block_width == 16 &&
+        !g_fwd_one_pixel && !g_disable_rowcol && rowcol_supported(bp)) {
+        Ip = c.plan_I + c.plan_I / 4 + 4096;
+        Ep = c.plan_E + c.plan_E / 4 + 4096;
+        if (Ip < (1ull << 30)) {
+            if (c.ensure(c.bins, (size_t)tiles * sizeof(int2)) || c.ensure(c.tile_ids, (size_t)Ip * 4) ||
+                c.ensure(c.tile_scratch, rowcol_scratch_bytes(bp, Ep, Ip)) ||
+                c.ensure(c.hits, hit_words_capacity(Ip, tiles) * 4))
+                return 1;
+            ListGuard guard;
+            guard.totals = (const unsigned long long *)c.small.p;
+            guard.cap_intersects = Ip;
+            guard.cap_row_entries = Ep;
+            c.cache_valid = false;
+            if ((bp.band_y1 - bp.band_y0) != d.tiles_y)
+                JSB_CUDA_OK(cudaMemsetAsync(c.bins.p, 0, (size_t)tiles * sizeof(int2), s));
+            const Stage stage_of[3] = {ST_EMIT, ST_BIN_EDGES, ST_TILE_SORT};
+            for (int phase = 0; phase < 3; ++phase) {
+                StageScope ss(&c, stage_of[phase]);
+                if (launch_rowcol_lists(s, bp, c.order_ptr, (const uint2 *)c.box_by_id.p, Ep, Ip,
+                                        (unsigned *)c.tile_scratch.p, (unsigned *)c.tile_ids.p,
+                                        (int2 *)c.bins.p, phase, guard))
+                    return 1;
+            }
+            {
+                StageScope ss(&c, ST_RASTER_FWD);
+                rp.guard = guard;
+                if (launch_raster_fwd(s, rp, (const unsigned *)c.tile_ids.p, (const int2 *)c.bins.p,
+                                      (const SplatRecord *)c.records.p, background, final_Ts,
+                                      final_idx, out_img, (unsigned *)c.hits.p, &spec_hits))
+                    return 1;
+                rp.guard = ListGuard{};
+            }
+            speculated = true;
+        }
+    }
+    unsigned long long I = 0, fp = 0;
+    if (bin_prepare_wait(c, d, &I, &fp)) return 1;
+    c.plan_valid = true;
+    c.plan_n = d.num_points; c.plan_tiles_x = d.tiles_x; c.plan_tiles_y = d.tiles_y;
+    c.plan_bw = d.block_width; c.plan_band = d.pad;
+    c.plan_I = I; c.plan_E = c.last_rows;
+    if (I == 0) {
+        c.cache_valid = false;
+        g_stats[4].store(0);
+        return launch_fill_background(s, rp, background, final_Ts, final_idx, out_img);
+    }
+    if (speculated && I <= Ip && c.last_rows <= Ep) {
+        c.cache_ids = (unsigned *)c.tile_ids.p;
+        c.cache_has_records = false;
+        commit_binning(c, d, I, fp);
+        c.cache_has_hits = spec_hits;
+        g_stats_spec_hits.fetch_add(1);
+    } else {
+        if (speculated) g_stats_spec_redo.fetch_add(1);
+        if (c.ensure(c.hits, hit_words_capacity(I, tiles) * 4)) return 1;
+        if (bin_sort(c, d, I, fp)) return 1;
+        StageScope ss(&c, ST_RASTER_FWD);
+        if (launch_raster_fwd(s, rp, c.cache_ids, (const int2 *)c.bins.p,
+                              (const SplatRecord *)c.records.p, background, final_Ts, final_idx,
+                              out_img, (unsigned *)c.hits.p, &c.cache_has_hits))
+            return 1;
+    }
+    c.cache_has_records = true;
+    c.cache_fp_known = fp_known;  // fused render: only the token proves identity
+    if (token) *token = c.cache_token;
+    return 0;
 }
 
 // ---- op bodies ---------------------------------------------------------------------------------
@@ -589,27 +698,14 @@ static int rasterize_fwd_impl(cudaStream_t stream, void **buf, const Descriptor 
     if (!c) return 1;
     std::lock_guard<std::mutex> lk(c->mu);
     g_stats[0].fetch_add(1);
-    const RasterParams rp = raster_params(d);
-    unsigned long long I = 0, fp = 0;
-    if (bin_prepare(*c, d, (const float *)buf[3], (const float *)buf[4], (const int *)buf[5],
-                    (const float *)buf[6], (const float *)buf[1], (const float *)buf[0], &I, &fp))
+    if (bin_prepare_enqueue(*c, d, (const float *)buf[3], (const float *)buf[4],
+                            (const int *)buf[5], (const float *)buf[6], (const float *)buf[1],
+                            (const float *)buf[0]))
         return 1;
-    if (I == 0) {
-        c->cache_valid = false;
-        g_stats[4].store(0);
-        return launch_fill_background(stream, rp, (const float *)buf[2], (float *)buf[8],
-                                      (int *)buf[9], (float *)buf[10]);
-    }
     // the forward always bins afresh (a training loop changes the parameters every step); only
     // the matching backward may reuse this result
-    if (c->ensure(c->hits, hit_words_capacity(I, d.tiles_x * d.tiles_y) * 4)) return 1;
-    if (bin_sort(*c, d, I, fp)) return 1;
-    c->cache_has_records = true;
-    StageScope ss(c, ST_RASTER_FWD);
-    return launch_raster_fwd(stream, rp, c->cache_ids, (const int2 *)c->bins.p,
-                             (const SplatRecord *)c->records.p, (const float *)buf[2],
-                             (float *)buf[8], (int *)buf[9], (float *)buf[10],
-                             (unsigned *)c->hits.p, &c->cache_has_hits);
+    return forward_lists_and_raster(*c, d, (const float *)buf[2], (float *)buf[8], (int *)buf[9],
+                                    (float *)buf[10], /*fp_known=*/true, nullptr);
 }
 
 static int rasterize_bwd_impl(cudaStream_t stream, void **buf, const Descriptor &d) {
@@ -674,8 +770,6 @@ static int render_fwd_impl(cudaStream_t stream, void **buf, const Descriptor &d,
     if (!c) return 1;
     std::lock_guard<std::mutex> lk(c->mu);
     g_stats[0].fetch_add(1);
-    const RasterParams rp = raster_params(d);
-    unsigned long long I = 0, fp = 0;
     // The fused projection kernel only accumulates the two grand totals (intersections, row
     // entries).  The strip-by-strip fallback list builder (grids wider than 512 tiles or taller
     // than 256 tile rows, or option "rowcol" 0) needs per-strip counts as well, which only
@@ -703,23 +797,8 @@ static int render_fwd_impl(cudaStream_t stream, void **buf, const Descriptor &d,
                                 (const float *)buf[4], /*write=*/true, /*fingerprint=*/false))
             return 1;
     }
-    if (bin_prepare_wait(*c, d, &I, &fp)) return 1;
-    if (I == 0) {
-        c->cache_valid = false;
-        g_stats[4].store(0);
-        return launch_fill_background(stream, rp, (const float *)buf[6], (float *)buf[13],
-                                      (int *)buf[14], (float *)buf[15]);
-    }
-    if (c->ensure(c->hits, hit_words_capacity(I, d.tiles_x * d.tiles_y) * 4)) return 1;
-    if (bin_sort(*c, d, I, 0)) return 1;
-    c->cache_has_records = true;
-    c->cache_fp_known = false;  // never matches a fingerprint: only the token proves identity
-    if (token) *token = c->cache_token;
-    StageScope ss(c, ST_RASTER_FWD);
-    return launch_raster_fwd(stream, rp, c->cache_ids, (const int2 *)c->bins.p,
-                             (const SplatRecord *)c->records.p, (const float *)buf[6],
-                             (float *)buf[13], (int *)buf[14], (float *)buf[15],
-                             (unsigned *)c->hits.p, &c->cache_has_hits);
+    return forward_lists_and_raster(*c, d, (const float *)buf[6], (float *)buf[13],
+                                    (int *)buf[14], (float *)buf[15], /*fp_known=*/false, token);
 }
 
 // keep_appearance: v_colors / v_opacity already hold the sum over earlier views of a batched call
@@ -1135,7 +1214,12 @@ int jsb200_set_option(const char *key, int value) {
     if (!strcmp(key, "bwdpk")) { jsb::g_bwd_scalar = (value == 0); return 0; }
     if (!strcmp(key, "fwdpk")) { jsb::g_fwd_scalar = (value == 0); return 0; }
     if (!strcmp(key, "rowcol")) { jsb::g_disable_rowcol = (value == 0); return 0; }
-    if (!strcmp(key, "bwdhits")) { jsb::g_bwd_no_hits = (value == 0); return 0; }
+    if (!strcmp(key, "spec")) { jsb::g_disable_spec = (value == 0); return 0; }
+    if (!strcmp(key, "bwdhits")) {
+        jsb::g_bwd_no_hits = (value == 0);
+        jsb::g_bwd_all_entries = (value == 2);
+        return 0;
+    }
     if (!strcmp(key, "sort1k")) { jsb::g_disable_resident_sort = (value == 0); return 0; }
     if (!strcmp(key, "timing")) { jsb::g_timing = (value != 0); return 0; }
     if (!strcmp(key, "view_slots")) {
@@ -1163,6 +1247,26 @@ long long jsb200_debug_binning(jsb200_stream_t stream_, const float *depths, int
             if (jsb::launch_rebuild_keys64(stream, (const int2 *)c->bins.p, c->cache_tiles, c->cache_ids, depths, keys64_sorted)) return -1;
         }
         return (long long)I;
+    } catch (...) {
+        return -1;
+    }
+}
+
+long long jsb200_debug_hit_words(jsb200_stream_t stream_, unsigned *out_words, size_t max_words) {
+    try {
+        cudaStream_t stream = (cudaStream_t)stream_;
+        jsb::Ctx *c = jsb::get_ctx(stream);
+        if (!c) return -1;
+        std::lock_guard<std::mutex> lk(c->mu);
+        if (!c->cache_valid || !c->cache_has_hits) {
+            jsb::set_error("debug_hit_words: no hit words cached on this stream");
+            return -1;
+        }
+        const size_t words = jsb::hit_words_capacity(c->cache_I, c->cache_tiles);
+        if (out_words && cudaMemcpyAsync(out_words, c->hits.p, std::min(words, max_words) * 4,
+                                         cudaMemcpyDeviceToDevice, stream) != cudaSuccess)
+            return -1;
+        return (long long)words;
     } catch (...) {
         return -1;
     }
@@ -1202,6 +1306,12 @@ int jsb200_get_stage_times(jsb200_stream_t stream_, double *ms_out9, unsigned lo
         jsb::set_error("get_stage_times: exception");
         return 1;
     }
+}
+
+void jsb200_get_speculation_stats(unsigned long long *out2) {
+    if (!out2) return;
+    out2[0] = jsb::g_stats_spec_hits.load();
+    out2[1] = jsb::g_stats_spec_redo.load();
 }
 
 void jsb200_get_stats(unsigned long long *out8) {

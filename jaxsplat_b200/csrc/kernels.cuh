@@ -60,6 +60,21 @@ struct __align__(16) SplatRecord {
     float4 q0, q1, q2;
 };
 
+// Speculative launches (capi.cu): the list builders and the forward rasteriser may be enqueued
+// before the host knows this frame's intersection / row-entry counts, with buffers sized from the
+// previous frame's counts.  The kernels that touch those buffers first compare the counts the
+// prep kernel left on the device (totals[1] = intersections, totals[4] = row entries) with the
+// capacities they were launched for, and do nothing at all if either is exceeded -- the host then
+// rebuilds with exact sizes.  totals == nullptr: no check.
+struct ListGuard {
+    const unsigned long long *totals = nullptr;
+    unsigned long long cap_intersects = 0, cap_row_entries = 0;
+};
+__device__ __forceinline__ bool guard_trips(const ListGuard &g) {
+    return g.totals != nullptr &&
+           (__ldg(g.totals + 1) > g.cap_intersects || __ldg(g.totals + 4) > g.cap_row_entries);
+}
+
 struct BinParams {
     unsigned num_points;
     float block_width_f;
@@ -134,7 +149,7 @@ size_t rowcol_scratch_bytes(const BinParams &p, unsigned long long row_entries,
 int launch_rowcol_lists(cudaStream_t stream, const BinParams &p, const unsigned *order,
                         const uint2 *box_by_id, unsigned long long row_entries,
                         unsigned long long num_intersects, unsigned *scratch, unsigned *ids_sorted,
-                        int2 *tile_bins, int phase);
+                        int2 *tile_bins, int phase, const ListGuard &guard = ListGuard{});
 
 // optional debug/parity helper: rebuild the reference's sorted 64-bit keys (tile<<32 | depth bits)
 int launch_rebuild_keys64(cudaStream_t stream, const int2 *tile_bins, unsigned num_tiles,
@@ -167,6 +182,7 @@ struct RasterParams {
     unsigned tiles_x, tiles_y;
     unsigned block_width;
     unsigned band_y0, band_y1;  // tile rows rasterised by this call (screen-tile-row sharding)
+    ListGuard guard;            // forward only: speculative launch (see ListGuard)
 };
 
 // hit_words (may be null): the forward records which list entries each 8x8 quadrant accepted

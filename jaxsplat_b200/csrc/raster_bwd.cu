@@ -710,7 +710,10 @@ raster_bwd16x2p_kernel(const RasterParams p, const unsigned *__restrict__ ids_so
 // the sorted id and the 48-byte record of visit j (cp.async, double buffered, ids one sub-chunk
 // further ahead) -- and replayed with exactly the arithmetic of raster_bwd16x2p_kernel, including
 // the deferred cross-lane reduction.
-constexpr int HB_SPAN = 32;  // hit words expanded at a time
+#ifndef JSB_BWDH_SPAN
+#define JSB_BWDH_SPAN 32
+#endif
+constexpr int HB_SPAN = JSB_BWDH_SPAN;  // hit words expanded at a time (<= 32)
 #ifndef JSB_BWDH_CTAS
 #define JSB_BWDH_CTAS 20     // resident one-warp CTAs per SM the register allocation is bounded for
 #endif
@@ -725,7 +728,7 @@ template <bool ABS>
 __global__ void __launch_bounds__(32, JSB_BWDH_CTAS)
 raster_bwd_hits_kernel(const RasterParams p, const unsigned *__restrict__ ids_sorted,
                        const int2 *__restrict__ tile_bins, const SplatRecord *__restrict__ records,
-                       const unsigned *__restrict__ hit_words,
+                       const unsigned *__restrict__ hit_words, const bool all_entries,
                        const float *__restrict__ background, const float *__restrict__ final_Ts,
                        const int *__restrict__ final_idx, const float *__restrict__ v_out_img,
                        const float *__restrict__ v_out_alpha_img, float *__restrict__ v_xy,
@@ -808,7 +811,7 @@ raster_bwd_hits_kernel(const RasterParams p, const unsigned *__restrict__ ids_so
     for (int gs = rel_top >> 5; gs >= 0; gs -= HB_SPAN) {
         // ---- expand this span's hit words into visit positions, newest first -------------------
         const int g = gs - lane;  // lane's group (32 list entries) of this span
-        unsigned w = g >= 0 ? __ldg(hw + g) : 0u;
+        unsigned w = (g >= 0 && lane < HB_SPAN) ? (all_entries ? 0xFFFFFFFFu : __ldg(hw + g)) : 0u;
         if (g == (rel_top >> 5)) w &= (2u << (rel_top & 31)) - 1u;  // entries above `top`
         const int cnt = __popc(w);
         int incl = cnt;
@@ -1011,6 +1014,7 @@ extern bool g_disable_cull;
 bool g_bwd_one_pixel = false;  // option "bwd2px" = 0: the one-pixel-per-thread kernel
 bool g_bwd_scalar = false;     // option "bwdpk" = 0: the two-pixel kernel with scalar FP32 math
 bool g_bwd_no_hits = false;    // option "bwdhits" = 0: the batch kernels even when hit words exist
+bool g_bwd_all_entries = false;  // option "bwdhits" = 2 (test hook): the hit-driven kernel replays EVERY entry
 
 template <bool CULL, bool ABS>
 static void launch_x2(cudaStream_t stream, unsigned tiles, const RasterParams &p,
@@ -1040,11 +1044,11 @@ int launch_raster_bwd(cudaStream_t stream, const RasterParams &p, const unsigned
         // one independent warp per quadrant, driven by the forward's hit words
         if (v_xy_abs)
             raster_bwd_hits_kernel<true><<<tiles * 4, 32, 0, stream>>>(
-                p, ids_sorted, tile_bins, records, hit_words, background, final_Ts, final_idx, v_out,
+                p, ids_sorted, tile_bins, records, hit_words, g_bwd_all_entries, background, final_Ts, final_idx, v_out,
                 v_out_alpha, v_xy, v_xy_abs, v_conic, v_colors, v_opacity);
         else
             raster_bwd_hits_kernel<false><<<tiles * 4, 32, 0, stream>>>(
-                p, ids_sorted, tile_bins, records, hit_words, background, final_Ts, final_idx, v_out,
+                p, ids_sorted, tile_bins, records, hit_words, g_bwd_all_entries, background, final_Ts, final_idx, v_out,
                 v_out_alpha, v_xy, v_xy_abs, v_conic, v_colors, v_opacity);
     } else if (p.block_width == 16 && !(g_bwd_one_pixel && v_xy_abs)) {
         if (v_xy_abs) {

@@ -180,6 +180,7 @@ raster_fwd16x2_kernel(const RasterParams p, const unsigned *__restrict__ ids_sor
     bool done0 = !in0, done1 = !in1;
     const int qbit = (warp & 1) + 4 * (warp >> 1);  // quadrant bit of the row-folded cull mask
 
+    if (guard_trips(p.guard)) return;  // speculative launch whose lists were not built
     const int2 range = tile_bins[tile];
     const int num_batches = (range.y - range.x + BATCH - 1) / BATCH;
     const float tile_x0 = (float)(tile_x * 16), tile_y0 = (float)(tile_y * 16);
@@ -188,8 +189,8 @@ raster_fwd16x2_kernel(const RasterParams p, const unsigned *__restrict__ ids_sor
     int cur0 = 0, cur1 = 0;
     float r0 = 0.f, g0 = 0.f, b0 = 0.f, r1 = 0.f, g1 = 0.f, b1 = 0.f;
     // this quadrant's hit words (raster_hits.cuh): which entries the backward has to replay
-    unsigned *hw = hit_words ? hit_words + hit_quadrant_offset(range, blockIdx.x, (unsigned)warp)
-                             : nullptr;
+    // (kept as a 32-bit word index: the kernel runs at its register cap)
+    const unsigned hw_off = (unsigned)hit_quadrant_offset(range, blockIdx.x, (unsigned)warp);
 
     auto load_id = [&](int b, int h) -> unsigned {
         const int idx = range.x + BATCH * b + tid + h * RF2;
@@ -245,9 +246,7 @@ raster_fwd16x2_kernel(const RasterParams p, const unsigned *__restrict__ ids_sor
             unsigned hit = 0;  // entries of this group some pixel of this lane accepted
             while (bits) {
                 const int t = k * 32 + __ffs(bits) - 1;
-                const unsigned rest = bits & (bits - 1);
-                const unsigned low = bits ^ rest;  // the bit of entry t
-                bits = rest;
+                bits &= bits - 1;
                 const float4 a = sA[buf][t];
                 const float4 bq = sB[buf][t];
                 const float dx = fsub(a.x, px);
@@ -280,7 +279,7 @@ raster_fwd16x2_kernel(const RasterParams p, const unsigned *__restrict__ ids_sor
                 const bool ok0 = !done0 && !(sg0 < 0.f) && !(al0 < kAlphaMin);
                 const bool ok1 = !done1 && !(sg1 < 0.f) && !(al1 < kAlphaMin);
                 if (ok0 || ok1) {
-                    hit |= low;
+                    hit |= __funnelshift_l(0u, 1u, (unsigned)t);  // 1 << (t & 31), one SHF
                     const float cb = sC[buf][t];
                     if (ok0) {
                         const float next_T = fmul(T0, fsub(1.f, al0));
@@ -310,9 +309,12 @@ raster_fwd16x2_kernel(const RasterParams p, const unsigned *__restrict__ ids_sor
                     }
                 }
             }
-            if (hw) {  // one word per (quadrant, group of 32 entries) the warp entered
+            // one word per (quadrant, group of 32 entries) the warp entered -- only for groups
+            // that exist: the batch's trailing groups beyond the end of the list belong to the
+            // next quadrant's (or tile's) slice
+            if (hit_words && batch_start + 32 * k < range.y) {
                 hit = __reduce_or_sync(0xffffffffu, hit);
-                if (lane == 0) hw[b * (BATCH / 32) + k] = hit;
+                if (lane == 0) hit_words[hw_off + b * (BATCH / 32) + k] = hit;
             }
             warp_done = __all_sync(0xffffffffu, done0 && done1);
         }

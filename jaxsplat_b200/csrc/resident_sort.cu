@@ -9,14 +9,18 @@
 // 91 vs 92 us, profiles/r02a_depth_sort_vs_cub.json) moves 16 MB per pass, ~3 us of HBM time, and
 // spends the other ~16 us of every pass on launch ramp and the chained look-back through ~245
 // tiles.  This kernel is launched once, cooperatively, with at most one CTA per SM; a pass is
-//   A. rank the CTA's keys by digit (stable, per-warp ballots), publish 512 digit counts
-//      and group the tile by digit in shared memory
+//   A.  rank the CTA's keys by digit (stable, per-warp ballots), publish its 512 digit counts,
+//       and group the tile by digit in shared memory
 //   -- grid barrier --
-//   B. every CTA sums the counts of the CTAs before it (16-byte loads, all independent), scans
-//      the digit totals and scatters its tile
+//   B1. CTA c scans, over all CTAs, the counts of the few digits it owns (512 / grid of them)
+//       and publishes every CTA's exclusive prefix for those digits (each count is read ONCE;
+//       letting every CTA sum the rows before it costs grid^2 x 2 KB = 40 MB of L2 reads a pass)
 //   -- grid barrier --
-// so the cross-CTA dependency is two flag barriers instead of a serial chain, nothing is
-// launched between passes, and for N <= 148 x 8192 the keys never leave registers between A and B.
+//   B2. every CTA reads its own row of prefixes and the digit totals, scans the totals and
+//       scatters its tile
+//   -- grid barrier --
+// so the cross-CTA dependency is three barriers instead of a serial chain, nothing is launched
+// between passes, and for N <= 148 x 8192 the keys never leave the SM between A and B2.
 // Only the live bits are sorted: the digits come from `key - min` (min / max of the real keys
 // arrive from the projection kernel), 9 bits per pass, so a scene whose far/near ratio is below
 // 2^8 sorts in THREE passes (27 live bits) and most synthetic ones (C3: 24 bits) too.  The first
@@ -38,6 +42,8 @@ constexpr int DS_BITS = 9;
 constexpr int DS_BINS = 1 << DS_BITS;            // == DS_THREADS: thread d owns digit d
 static_assert(DS_BINS == DS_THREADS, "one thread per digit");
 constexpr unsigned kSentinelKey = 0xFFFFFFFFu;   // Gaussians that hit no tile
+constexpr int DS_MAXG = 256;                     // CTAs (= SMs used) at most
+constexpr int DS_MAXK = 16;                      // digits one CTA scans at most (grid > 32)
 
 struct DsParams {
     const unsigned *keys_in;  // depth keys as the projection wrote them
@@ -45,8 +51,10 @@ struct DsParams {
     unsigned *order;          // out: Gaussian ids in (depth, index) order
     unsigned n;
     const unsigned *mm;       // {max(~key), max(key)} over the real keys; {0, 0} = none
-    unsigned *hist;           // [grid][DS_BINS]
-    unsigned *flags;          // [grid] barrier epochs, zero at launch
+    unsigned *hist;           // [grid][DS_BINS] digit counts of every CTA
+    unsigned *pre;            // [grid][DS_BINS] their exclusive prefix over the CTAs
+    unsigned *tot;            // [DS_BINS] digit totals
+    unsigned *bar;            // grid barrier counter, zero at launch
     int *err;
     unsigned tile_items;      // multiple of 512, <= DS_TILE
     unsigned subtiles;        // tiles per CTA
@@ -58,33 +66,29 @@ struct DsSmem {
     unsigned vals[DS_TILE];
     unsigned binstart[DS_BINS];         // exclusive scan of the tile's digit counts
     unsigned goff[DS_BINS];             // global offset of the digit's run minus binstart
-    uint4 part_before[4][DS_BINS / 4];  // prefix partial sums: [row phase][digit group of 4]
-    uint4 part_all[4][DS_BINS / 4];
+    unsigned colcnt[DS_MAXK][DS_MAXG];  // B1: counts of the digits this CTA scans, per CTA
     unsigned ws[DS_WARPS + 1];
 };
 
-__device__ __forceinline__ unsigned ld_acquire(const unsigned *p) {
+// (relaxed: an acquire load compiles to LDG + CCTL.IVALL, i.e. every poll of a spin loop would
+// invalidate the whole L1; one fence after the loop does it once)
+__device__ __forceinline__ unsigned ld_relaxed_gpu(const unsigned *p) {
     unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
 
-__device__ __forceinline__ void st_release(unsigned *p, unsigned v) {
-    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
-// Barrier over the co-resident grid.  CTA c publishes flags[c] = epoch (one plain release store:
-// no same-address atomics queueing up in the L2) and thread t polls flags[t], so a CTA sees all
-// arrivals one L2 round trip after the last one.
-__device__ __forceinline__ void grid_barrier(unsigned *flags, unsigned G, unsigned c, unsigned epoch,
-                                             int *err) {
-    __syncthreads();  // every store of this CTA happens-before thread 0's release
-    if (threadIdx.x == 0) st_release(flags + c, epoch);
-    for (unsigned t = threadIdx.x; t < G; t += DS_THREADS) {
+// all CTAs of the (co-resident) grid; `target` = arrivals after which this barrier opens
+__device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned target, int *err) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(bar, 1u);
         int spins = 0;
-        while (ld_acquire(flags + t) < epoch) {
+        while (ld_relaxed_gpu(bar) < target) {
             if (++spins > kSpinLimit) { *err = 3; break; }  // a scheduling bug becomes an error
         }
+        __threadfence();
     }
     __syncthreads();
 }
@@ -110,7 +114,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) resident_depth_sort_kernel(cons
     const unsigned ipt = P.tile_items / DS_THREADS;  // <= DS_IPT
     const unsigned lt_mask = (1u << lane) - 1u;
     const bool single = P.subtiles == 1;
-    unsigned epoch = 0;
+    unsigned arrivals = 0;
 
     unsigned key[DS_IPT], val[DS_IPT];
     unsigned short rank[DS_IPT];
@@ -130,14 +134,20 @@ __global__ void __launch_bounds__(DS_THREADS, 1) resident_depth_sort_kernel(cons
             const unsigned base = tile * P.tile_items;
             const unsigned count = base < P.n ? min(P.tile_items, P.n - base) : 0u;
             const unsigned wbase = warp * (ipt * 32u) + lane;
+            // every load of the thread in flight before the first use (the profile of the first
+            // version showed load -> use -> load: 16 exposed latencies per pass)
 #pragma unroll
             for (int i = 0; i < DS_IPT; ++i) {
                 const unsigned o = wbase + i * 32u;
-                if ((unsigned)i < ipt && o < count) {
-                    unsigned k = __ldcg(ksrc + base + o);
-                    if (ps == 0) k = (k == kSentinelKey) ? span : k - kmin;  // live bits only
-                    key[i] = k;
-                    if (with_vals) val[i] = ps == 0 ? base + o : __ldcg(vsrc + base + o);
+                const bool have = (unsigned)i < ipt && o < count;
+                key[i] = have ? __ldcg(ksrc + base + o) : 0u;
+                if (with_vals && ps != 0) val[i] = have ? __ldcg(vsrc + base + o) : 0u;
+            }
+            if (ps == 0) {
+#pragma unroll
+                for (int i = 0; i < DS_IPT; ++i) {
+                    key[i] = (key[i] == kSentinelKey) ? span : key[i] - kmin;  // live bits only
+                    val[i] = base + wbase + i * 32u;
                 }
             }
             return count;
@@ -213,40 +223,54 @@ __global__ void __launch_bounds__(DS_THREADS, 1) resident_depth_sort_kernel(cons
         P.hist[(size_t)c * DS_BINS + tid] = cta_total;
         // (single tile: the reorder needs nothing from the other CTAs -- done under the barrier)
         if (single) reorder_tile(count);
-        grid_barrier(P.flags, G, c, ++epoch, P.err);
+        arrivals += G;
+        grid_barrier(P.bar, arrivals, P.err);
 
         // ---- B: offsets, scatter ------------------------------------------------------------------
-        // Column sums of the G x 512 count matrix: rows before this CTA and all rows.  Thread
-        // (phase, dg) takes every 4th row of digits 4 dg .. 4 dg + 3 with 16-byte loads, all of
-        // them independent (one or two L2 round trips instead of G / 8).
-        {
-            const unsigned phase = tid >> 7, dg = tid & 127u;
-            const uint4 *h4 = reinterpret_cast<const uint4 *>(P.hist);
-            uint4 before = make_uint4(0u, 0u, 0u, 0u), all = before;
-            for (unsigned r0 = phase; r0 < G; r0 += 4 * 13) {
-                uint4 h[13];
-#pragma unroll
-                for (int u = 0; u < 13; ++u) {
-                    const unsigned r = r0 + 4 * u;
-                    h[u] = r < G ? __ldcg(h4 + (size_t)r * (DS_BINS / 4) + dg) : make_uint4(0u, 0u, 0u, 0u);
-                }
-#pragma unroll
-                for (int u = 0; u < 13; ++u) {
-                    all.x += h[u].x; all.y += h[u].y; all.z += h[u].z; all.w += h[u].w;
-                    if (r0 + 4 * u < c) {
-                        before.x += h[u].x; before.y += h[u].y; before.z += h[u].z; before.w += h[u].w;
-                    }
-                }
-            }
-            S.part_before[phase][dg] = before;
-            S.part_all[phase][dg] = all;
-        }
-        __syncthreads();
         unsigned before = 0, all = 0;
+        if (G <= 32u) {
+            // a small grid: every CTA sums the rows before it itself (at most 32 loads a thread)
+            for (unsigned r = 0; r < G; ++r) {
+                const unsigned h = __ldcg(P.hist + (size_t)r * DS_BINS + tid);
+                all += h;
+                if (r < c) before += h;
+            }
+        } else {
+        // B1: this CTA scans digits [c K, c K + K) over the G CTAs (K = ceil(512 / G) <= 16)
+        {
+            const unsigned K = (DS_BINS + G - 1) / G;
+            const unsigned tpd = DS_THREADS / DS_MAXK;           // threads per digit while loading
+            const unsigned k = tid / tpd, r0 = tid % tpd;
+            const unsigned d = c * K + k;
+            if (k < K && d < DS_BINS)
+                for (unsigned r = r0; r < G; r += tpd) S.colcnt[k][r] = __ldcg(P.hist + (size_t)r * DS_BINS + d);
+            __syncthreads();
+            if (warp < K && c * K + warp < DS_BINS) {  // one warp per digit: lane owns a run of rows
+                const unsigned dd = c * K + warp;
+                const unsigned per = (G + 31u) / 32u;
+                const unsigned b0 = min(G, lane * per), b1 = min(G, b0 + per);
+                unsigned sum = 0;
+                for (unsigned r = b0; r < b1; ++r) sum += S.colcnt[warp][r];
+                unsigned incl = sum;
 #pragma unroll
-        for (int ph = 0; ph < 4; ++ph) {
-            before += reinterpret_cast<const unsigned *>(S.part_before[ph])[tid];
-            all += reinterpret_cast<const unsigned *>(S.part_all[ph])[tid];
+                for (int o = 1; o < 32; o <<= 1) {
+                    const unsigned tt = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= (unsigned)o) incl += tt;
+                }
+                unsigned runp = incl - sum;
+                for (unsigned r = b0; r < b1; ++r) {
+                    P.pre[(size_t)r * DS_BINS + dd] = runp;
+                    runp += S.colcnt[warp][r];
+                }
+                if (lane == 31) P.tot[dd] = incl;
+            }
+        }
+        arrivals += G;
+        grid_barrier(P.bar, arrivals, P.err);
+
+        // B2: own row of prefixes + digit totals
+        before = __ldcg(P.pre + (size_t)c * DS_BINS + tid);
+        all = __ldcg(P.tot + tid);
         }
         unsigned grand;
         const unsigned dbase = cta_exclusive_scan<DS_THREADS>(all, &grand, S.ws);
@@ -269,7 +293,10 @@ __global__ void __launch_bounds__(DS_THREADS, 1) resident_depth_sort_kernel(cons
             }
             __syncthreads();
         }
-        if (!last) grid_barrier(P.flags, G, c, ++epoch, P.err);
+        if (!last) {
+            arrivals += G;
+            grid_barrier(P.bar, arrivals, P.err);
+        }
     }
 }
 
@@ -283,7 +310,7 @@ DeviceFacts g_facts[64];
 
 size_t resident_sort_scratch_bytes(unsigned n) {
     (void)n;
-    return (size_t)(1024 + 4) * DS_BINS * sizeof(unsigned);  // hist rows (grid <= 1024) + barrier flags
+    return (size_t)(2 * DS_MAXG + 2) * DS_BINS * sizeof(unsigned);  // hist + pre rows, totals, barrier
 }
 
 // returns 0 on success, 1 on error, -1 if this device cannot run it (caller falls back)
@@ -305,7 +332,7 @@ int resident_depth_sort(cudaStream_t stream, const unsigned *keys_in, unsigned *
         JSB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
             &per_sm, resident_depth_sort_kernel, DS_THREADS, sizeof(DsSmem)));
         F.cooperative = coop != 0 && per_sm > 0;
-        F.max_ctas = std::min(sms, 1024);  // one CTA per SM is all the parallelism a pass needs
+        F.max_ctas = std::min(sms, DS_MAXG);  // one CTA per SM is all the parallelism a pass needs
         F.known = true;
     }
     if (!F.cooperative) return -1;
@@ -313,13 +340,15 @@ int resident_depth_sort(cudaStream_t stream, const unsigned *keys_in, unsigned *
     P.keys_in = keys_in; P.kA = kA; P.vA = vA; P.kB = kB; P.vB = vB; P.order = order;
     P.n = n; P.mm = mm; P.err = err;
     P.hist = reinterpret_cast<unsigned *>(scratch);
-    P.flags = P.hist + (size_t)1024 * DS_BINS;
+    P.pre = P.hist + (size_t)DS_MAXG * DS_BINS;
+    P.tot = P.pre + (size_t)DS_MAXG * DS_BINS;
+    P.bar = P.tot + DS_BINS;
     const unsigned G0 = (unsigned)F.max_ctas;
     P.subtiles = std::max(1u, ceil_div(n, G0 * (unsigned)DS_TILE));
     const unsigned per_tile = ceil_div(n, G0 * P.subtiles);
     P.tile_items = std::min((unsigned)DS_TILE, std::max(512u, ceil_div(per_tile, 512u) * 512u));
     const unsigned grid = ceil_div(n, P.tile_items * P.subtiles);
-    JSB_CUDA_OK(cudaMemsetAsync(P.flags, 0, 1024 * sizeof(unsigned), stream));
+    JSB_CUDA_OK(cudaMemsetAsync(P.bar, 0, 64, stream));
     void *args[] = {(void *)&P};
     JSB_CUDA_OK(cudaLaunchCooperativeKernel((const void *)resident_depth_sort_kernel, dim3(grid),
                                             dim3(DS_THREADS), args, sizeof(DsSmem), stream));

@@ -49,6 +49,7 @@ struct RcParams {
     unsigned n1;         // level-1 chunks = ceil(n / k1)
     unsigned n1s;        // row stride of the level-1 count matrix (n1 rounded up to 4)
     unsigned n2max;      // upper bound of the level-2 chunk count
+    ListGuard guard;     // speculative launch: capacities the E- / I-scale buffers were sized for
 };
 
 // word offsets inside the scratch buffer
@@ -243,6 +244,7 @@ __global__ void __launch_bounds__(32 * RC_CC_WARPS)
 rc_col_count_kernel(const RcParams p, const uint4 *__restrict__ chunk_info,
                     const uint2 *__restrict__ entries, unsigned *__restrict__ m) {
     __shared__ unsigned s_diff_all[RC_CC_WARPS][512 + 32];
+    if (guard_trips(p.guard)) return;  // (the row entries were not written)
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned *s_diff = s_diff_all[warp];
     const unsigned c = blockIdx.x * RC_CC_WARPS + warp;
@@ -432,6 +434,7 @@ rc_row_scatter_kernel(const RcParams p, const unsigned *__restrict__ order,
                       const uint2 *__restrict__ box_by_id, const unsigned *__restrict__ l1m,
                       const unsigned *__restrict__ row_start, uint2 *__restrict__ entries) {
     extern __shared__ __align__(16) unsigned char rc_smem[];
+    if (guard_trips(p.guard)) return;  // more row entries than the buffer holds: host rebuilds
     const DistSmem<uint2, RC_STAGE1> S(rc_smem, p.rows);
     const unsigned lane = threadIdx.x, chunk = blockIdx.x;
     unsigned lo[8], len[8];
@@ -477,6 +480,7 @@ rc_col_scatter_kernel(const RcParams p, const uint4 *__restrict__ chunk_info,
                       const uint2 *__restrict__ entries, const unsigned *__restrict__ m,
                       const unsigned *__restrict__ tile_base, unsigned *__restrict__ out_ids) {
     extern __shared__ __align__(16) unsigned char rc_smem[];
+    if (guard_trips(p.guard)) return;  // more intersections than the list buffer holds
     const DistSmem<unsigned, RC_STAGE2> S(rc_smem, p.cols);
     const unsigned lane = threadIdx.x, c = blockIdx.x;
     const uint4 info = __ldg(chunk_info + c);
@@ -551,7 +555,7 @@ size_t rowcol_scratch_bytes(const BinParams &bp, unsigned long long row_entries,
 int launch_rowcol_lists(cudaStream_t stream, const BinParams &bp, const unsigned *order,
                         const uint2 *box_by_id, unsigned long long row_entries,
                         unsigned long long num_intersects, unsigned *scratch, unsigned *ids_sorted,
-                        int2 *tile_bins, int phase) {
+                        int2 *tile_bins, int phase, const ListGuard &guard) {
     if (bp.num_points == 0 || num_intersects == 0) return 0;
     if (!rowcol_supported(bp)) {
         set_error("rowcol_lists: band of %u rows x %u tiles not supported", bp.band_y1 - bp.band_y0,
@@ -563,7 +567,8 @@ int launch_rowcol_lists(cudaStream_t stream, const BinParams &bp, const unsigned
                   num_intersects);
         return 1;
     }
-    const RcParams p = rc_params(bp, row_entries, num_intersects);
+    RcParams p = rc_params(bp, row_entries, num_intersects);
+    p.guard = guard;
     const RcLayout L = rc_layout(p, row_entries);
     unsigned *l1m = scratch + L.l1m, *row_tot = scratch + L.row_tot;
     unsigned *row_start = scratch + L.row_start, *chunk_base = scratch + L.chunk_base;
