@@ -90,8 +90,11 @@ JSB200_API void jsb200_rasterize_bwd_status(jsb200_stream_t stream, void **buffe
  *   render_bwd  in : means3d scales quats viewmat colors opacities background cov3ds xys depths
  *                    radii conics compensation final_Ts final_idx v_out_img v_out_img_alpha
  *               out: v_mean3d v_scale v_quat v_colors v_opacity | v_xy v_conic v_cov2d v_cov3d
- *                    (the last four: intermediate cotangents; v_xy_abs, which nothing downstream
- *                    of rasterize_bwd reads, is not computed)
+ *                    (v_xy (N,2) and v_conic (N,3) are accumulation scratch of the library: their
+ *                    contents on return are unspecified -- the rasteriser backward may leave raw
+ *                    moments there that the projection backward consumes; v_cov2d / v_cov3d are
+ *                    the projection VJP's intermediate cotangents; v_xy_abs, which nothing
+ *                    downstream of rasterize_bwd reads, is not computed)
  * v_out_img_alpha may be NULL (= zero cotangent; block_width 16 only); v_cov2d / v_cov3d may be
  * NULL (not written: nothing downstream of a render reads them).
  * `opaque` is a full descriptor (f, c, glob_scale, clip_thresh set).  *token_out identifies the
@@ -167,8 +170,12 @@ JSB200_API unsigned long long jsb200_error_count(void);
  *               instead of the packed FP32x2 instructions of sm_100),
  *      "rowcol" (1 default; 0 builds the per-tile lists with the older counting distribution of
  *               tile_lists.cu instead of the two-level row/column distribution),
- *      "spec" (1 default; 0 makes every forward wait for the frame's intersection count before it
- *               launches the list builders, instead of sizing them from the previous frame),
+ *      "bwdmom" (1 default; 0 makes the fused render's hit-driven rasteriser backward accumulate
+ *               finished v_xy / v_conic / v_opacity instead of raw moments that the projection
+ *               backward finishes),
+ *      "spec" (0 default; 1 lets a forward launch the list builders and the rasteriser before the
+ *               host knows the frame's intersection count, with buffers sized from the previous
+ *               frame of the same shape and device-side guards; measured neutral to slower),
  *      "bwdhits" (1 default; 0 runs rasterize_bwd with the per-tile batch kernel even when the
  *               forward recorded which list entries every 8x8 quadrant accepted),
  *      "sort1k" (1 default; 0 orders the Gaussians by depth with four onesweep passes over all 32
@@ -199,7 +206,7 @@ JSB200_API int jsb200_get_stage_times(jsb200_stream_t stream, double *ms_out9,
 JSB200_API void jsb200_get_stats(unsigned long long *out8);
 /* Forward rasterisations whose list builders + rasteriser were launched before the host knew the
  * frame's intersection count (buffers sized from the previous frame of the same shape; option
- * "spec", 1 default): out2[0] = launches that held, out2[1] = frames that outgrew the buffers and
+ * "spec", off by default): out2[0] = launches that held, out2[1] = frames that outgrew the buffers and
  * were rebuilt with exact sizes (same results either way). */
 JSB200_API void jsb200_get_speculation_stats(unsigned long long *out2);
 /* releases every workspace (all devices/streams). */

@@ -12,6 +12,7 @@ reference's own capsules, so both libraries run under one harness.
 from __future__ import annotations
 
 import ctypes
+import functools
 from typing import Dict, Sequence
 
 from . import _lib
@@ -24,7 +25,15 @@ _CALL_T = ctypes.CFUNCTYPE(None, ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p
 
 def make_descriptor(num_points: int, img_shape, f, c, glob_scale: float, clip_thresh: float,
                     block_width: int) -> bytes:
-    """reference lib/ffi.cu:15-52; img_shape is (H, W)."""
+    """reference lib/ffi.cu:15-52; img_shape is (H, W).  (Cached: a training loop asks for the same
+    80 bytes every step.)"""
+    return _make_descriptor_cached(int(num_points), (int(img_shape[0]), int(img_shape[1])),
+                                   (float(f[0]), float(f[1])), (float(c[0]), float(c[1])),
+                                   float(glob_scale), float(clip_thresh), int(block_width))
+
+
+@functools.lru_cache(maxsize=256)
+def _make_descriptor_cached(num_points, img_shape, f, c, glob_scale, clip_thresh, block_width) -> bytes:
     buf = ctypes.create_string_buffer(80)
     rc = _lib.lib().jsb200_make_descriptor(int(num_points), int(img_shape[0]), int(img_shape[1]),
                                            float(f[0]), float(f[1]), float(c[0]), float(c[1]),

@@ -59,6 +59,7 @@ extern bool g_fwd_scalar;
 extern bool g_fwd_one_pixel;
 extern bool g_bwd_no_hits;
 extern bool g_bwd_all_entries;
+extern bool g_bwd_no_moments;
 static bool g_disable_cache = false;
 static bool g_disable_rowcol = false;
 static bool g_disable_resident_sort = false;  // option "sort1k" 0: the four-pass onesweep depth sort
@@ -521,7 +522,9 @@ static bool cache_hit(const Ctx &c, const Descriptor &d, unsigned long long I,
 // issues a dozen launches (a ~30 us depth sort no longer hides that).  Kernels that touch the
 // I- / E-scale buffers check the device-side counts against the capacities first (ListGuard); if
 // the frame outgrew them nothing was written and the host falls back to the exactly sized path.
-static bool g_disable_spec = false;  // option "spec" 0: always wait for the counts first
+// OFF by default: measured neutral at C3 (0.767 vs 0.760 ms) and worse at C2 (0.411 vs 0.348 ms,
+// profiles/r02g_*): with a 40-60 us depth sort enqueued before the wait the host is hidden anyway.
+static bool g_disable_spec = true;  // option "spec" 1: launch before the counts are known
 static RasterParams raster_params(const Descriptor &d);
 
 static int forward_lists_and_raster(Ctx &c, const Descriptor &d, const float *background,
@@ -637,7 +640,10 @@ static int project_fwd_impl(cudaStream_t stream, void **buf, const Descriptor &d
     return project_fwd_locked(c, stream, buf, d, nullptr);
 }
 
-static int project_bwd_impl(cudaStream_t stream, void **buf, const Descriptor &d) {
+// moment_opacity != null (fused render): v_xy / v_conic / moment_opacity hold the rasteriser's raw
+// moments, finished into gradients by the projection backward (project.cu: FINISH_MOMENTS)
+static int project_bwd_impl2(cudaStream_t stream, void **buf, const Descriptor &d,
+                             const float *opacities, float *moment_opacity) {
     if (d.num_points == 0) return 0;
     Ctx *c = get_ctx(stream);
     if (!c) return 1;
@@ -653,7 +659,11 @@ static int project_bwd_impl(cudaStream_t stream, void **buf, const Descriptor &d
                               (const float *)buf[9], (const float *)buf[10],
                               (const float *)buf[11], (const float *)buf[12], (float *)buf[13],
                               (float *)buf[14], (float *)buf[15], (float *)buf[16],
-                              (float *)buf[17]);
+                              (float *)buf[17], opacities, moment_opacity);
+}
+
+static int project_bwd_impl(cudaStream_t stream, void **buf, const Descriptor &d) {
+    return project_bwd_impl2(stream, buf, d, nullptr, nullptr);
 }
 
 static RasterParams raster_params(const Descriptor &d) {
@@ -815,6 +825,7 @@ static int render_bwd_impl(cudaStream_t stream, void **buf, const Descriptor &d,
     if (check_raster_desc(d)) return 1;
     const size_t n = d.num_points;
     if (n == 0) return 0;
+    bool moments_flag = false;  // the rasteriser left raw moments for the projection backward
     {
     Ctx *c = get_ctx(stream, slot);
     if (!c) return 1;
@@ -853,7 +864,7 @@ static int render_bwd_impl(cudaStream_t stream, void **buf, const Descriptor &d,
                      c->cache_token == token && c->cache_n == d.num_points &&
                      c->cache_tiles == d.tiles_x * d.tiles_y && c->cache_tiles_x == d.tiles_x &&
                      c->cache_bw == d.block_width && c->cache_band == d.pad;
-    bool empty = false;
+    bool empty = false, moments = false;
     if (hit) {
         g_stats[3].fetch_add(1);
     } else {
@@ -878,9 +889,13 @@ static int render_bwd_impl(cudaStream_t stream, void **buf, const Descriptor &d,
                               (const float *)buf[13], (const int *)buf[14], (const float *)buf[15],
                               (const float *)buf[16], (float *)buf[22], v_xy_abs,
                               (float *)buf[23], (float *)buf[20], (float *)buf[21],
-                              c->cache_has_hits ? (const unsigned *)c->hits.p : nullptr))
+                              c->cache_has_hits ? (const unsigned *)c->hits.p : nullptr,
+                              // (raw moments leave v_opacity unfinished until project_bwd: not
+                              // when it accumulates over views or a driver reduces it early)
+                              (keep_appearance || g_raster_bwd_event.load()) ? nullptr : &moments))
             return 1;
     }
+    moments_flag = moments;
     }
     // v_colors / v_opacity are final from here on (project_bwd only produces the other three): a
     // data-parallel driver may start reducing them on another stream under project_bwd
@@ -890,7 +905,8 @@ static int render_bwd_impl(cudaStream_t stream, void **buf, const Descriptor &d,
     // project_bwd with zero cotangents for depth and compensation (render uses neither)
     void *pbuf[18] = {buf[0], buf[1], buf[2], buf[3], buf[7], buf[8], buf[10], buf[11], buf[12],
                       nullptr, buf[22], nullptr, buf[23], buf[17], buf[18], buf[19], buf[24], buf[25]};
-    return project_bwd_impl(stream, pbuf, d);
+    return project_bwd_impl2(stream, pbuf, d, moments_flag ? (const float *)buf[5] : nullptr,
+                             moments_flag ? (float *)buf[21] : nullptr);
 }
 
 
@@ -1214,6 +1230,7 @@ int jsb200_set_option(const char *key, int value) {
     if (!strcmp(key, "bwdpk")) { jsb::g_bwd_scalar = (value == 0); return 0; }
     if (!strcmp(key, "fwdpk")) { jsb::g_fwd_scalar = (value == 0); return 0; }
     if (!strcmp(key, "rowcol")) { jsb::g_disable_rowcol = (value == 0); return 0; }
+    if (!strcmp(key, "bwdmom")) { jsb::g_bwd_no_moments = (value == 0); return 0; }
     if (!strcmp(key, "spec")) { jsb::g_disable_spec = (value == 0); return 0; }
     if (!strcmp(key, "bwdhits")) {
         jsb::g_bwd_no_hits = (value == 0);

@@ -46,7 +46,10 @@ int launch_project_bwd(cudaStream_t stream, const ProjectBwdParams &p, const flo
                        const float *cov3ds, const int *radii, const float *conics,
                        const float *compensation, const float *v_compensation, const float *v_xy,
                        const float *v_depth, const float *v_conic, float *v_mean3d,
-                       float *v_scale, float *v_quat, float *v_cov2d, float *v_cov3d);
+                       float *v_scale, float *v_quat, float *v_cov2d, float *v_cov3d,
+                       const float *opacities = nullptr, float *moment_opacity = nullptr);
+// opacities + moment_opacity != null: v_xy / v_conic / moment_opacity hold the rasteriser's raw
+// moments; they are turned into gradients on the fly and moment_opacity[i] becomes v_opacity[i].
 
 // batched cameras: v_mean3d / v_scale / v_quat += one view's staged arrays (3n / 3n / 4n floats)
 int launch_accumulate_param_grads(cudaStream_t stream, size_t n, const float *s_mean,
@@ -197,7 +200,11 @@ int launch_raster_bwd(cudaStream_t stream, const RasterParams &p, const unsigned
                       const int2 *tile_bins, const SplatRecord *records, const float *background,
                       const float *final_Ts, const int *final_idx, const float *v_out,
                       const float *v_out_alpha, float *v_xy, float *v_xy_abs, float *v_conic,
-                      float *v_colors, float *v_opacity, const unsigned *hit_words = nullptr);
+                      float *v_colors, float *v_opacity, const unsigned *hit_words = nullptr,
+                      bool *moments_out = nullptr);
+// moments_out (fused render; may be null): if the hit-driven kernel ran without v_xy_abs it left RAW
+// MOMENTS in v_opacity / v_xy / v_conic (raster_bwd.cu: MOMENTS) and sets *moments_out; the caller
+// must then run launch_project_bwd with finish_moments (which also finalises v_opacity).
 
 // image = background, final_Ts = 0, final_idx = 0  (reference num_intersects==0 path,
 // ops.cu:119-127 + memsets :436-458)

@@ -332,6 +332,12 @@ project_fwd_kernel(const ProjectFwdParams p, const float *__restrict__ means3d,
 // ~300 instructions per Gaussian instead of ~1100, no shared-memory slabs, no CTA barriers.
 // v_cov2d / v_cov3d may be null (the fused render has no use for the intermediate cotangents).
 // ---------------------------------------------------------------------------------------------
+// FINISH_MOMENTS (fused render after the hit-driven rasteriser backward, raster_bwd.cu: MOMENTS):
+// v_xy / v_conic / moment_opacity hold raw moments (Mx, My) / (Mxx, Mxy, Myy) / M0 of
+// opacity * vis * v_alpha; with the conic and the opacity at hand they become
+//   v_xy = -(cx Mx + cy My, cy Mx + cz My), v_conic = -(Mxx / 2, Mxy, Myy / 2), v_opacity = M0 / opacity
+// here, and moment_opacity[i] is overwritten with v_opacity.
+template <bool FINISH_MOMENTS>
 __global__ void __launch_bounds__(PT)
 project_bwd_kernel(const ProjectBwdParams p, const float *__restrict__ means3d,
                    const float *__restrict__ scales, const float4 *__restrict__ quats,
@@ -342,7 +348,8 @@ project_bwd_kernel(const ProjectBwdParams p, const float *__restrict__ means3d,
                    const float *__restrict__ v_depth, const float *__restrict__ v_conic,
                    float *__restrict__ v_mean3d, float *__restrict__ v_scale,
                    float *__restrict__ v_quat, float *__restrict__ v_cov2d,
-                   float *__restrict__ v_cov3d) {
+                   float *__restrict__ v_cov3d, const float *__restrict__ opacities,
+                   float *__restrict__ moment_opacity) {
     __shared__ __align__(16) float s_strip[PT / 32][32 * 6];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long idx = (long long)blockIdx.x * PT + tid;
@@ -365,9 +372,18 @@ project_bwd_kernel(const ProjectBwdParams p, const float *__restrict__ means3d,
                     k4 = __ldg(cov3ds + idx * 6 + 4), k5 = __ldg(cov3ds + idx * 6 + 5);
         const float cx = __ldg(conics + idx * 3), cy = __ldg(conics + idx * 3 + 1),
                     cz = __ldg(conics + idx * 3 + 2);
-        const float gx = __ldg(v_conic + idx * 3), gy = 0.5f * __ldg(v_conic + idx * 3 + 1),
-                    gz = __ldg(v_conic + idx * 3 + 2);
-        const float2 vxy = __ldg(v_xy + idx);
+        float gx = __ldg(v_conic + idx * 3), gy = 0.5f * __ldg(v_conic + idx * 3 + 1),
+              gz = __ldg(v_conic + idx * 3 + 2);
+        float2 vxy = __ldg(v_xy + idx);
+        if (FINISH_MOMENTS) {
+            const float mx = vxy.x, my = vxy.y;
+            vxy = make_float2(-(cx * mx + cy * my), -(cy * mx + cz * my));
+            gx *= -0.5f;   // v_conic.x = -Mxx / 2
+            gy = -gy;      // v_conic.y / 2 = -Mxy / 2
+            gz *= -0.5f;   // v_conic.z = -Myy / 2
+            const float m0 = moment_opacity[idx];
+            moment_opacity[idx] = m0 != 0.f ? m0 / __ldg(opacities + idx) : 0.f;
+        }
         const float vz = v_depth ? __ldg(v_depth + idx) : 0.f;  // null = zero cotangent (fused render)
         const float *v = viewmat;
         const float w00 = __ldg(v + 0), w01 = __ldg(v + 1), w02 = __ldg(v + 2), w03 = __ldg(v + 3);
@@ -539,13 +555,20 @@ int launch_project_bwd(cudaStream_t stream, const ProjectBwdParams &p, const flo
                        const float *cov3ds, const int *radii, const float *conics,
                        const float *compensation, const float *v_compensation, const float *v_xy,
                        const float *v_depth, const float *v_conic, float *v_mean3d,
-                       float *v_scale, float *v_quat, float *v_cov2d, float *v_cov3d) {
+                       float *v_scale, float *v_quat, float *v_cov2d, float *v_cov3d,
+                       const float *opacities, float *moment_opacity) {
     if (p.num_points == 0) return 0;
     const unsigned blocks = ceil_div(p.num_points, PT);
-    project_bwd_kernel<<<blocks, PT, 0, stream>>>(
-        p, means3d, scales, reinterpret_cast<const float4 *>(quats), viewmat, cov3ds, radii,
-        conics, compensation, v_compensation, reinterpret_cast<const float2 *>(v_xy), v_depth,
-        v_conic, v_mean3d, v_scale, v_quat, v_cov2d, v_cov3d);
+    if (opacities && moment_opacity)
+        project_bwd_kernel<true><<<blocks, PT, 0, stream>>>(
+            p, means3d, scales, reinterpret_cast<const float4 *>(quats), viewmat, cov3ds, radii,
+            conics, compensation, v_compensation, reinterpret_cast<const float2 *>(v_xy), v_depth,
+            v_conic, v_mean3d, v_scale, v_quat, v_cov2d, v_cov3d, opacities, moment_opacity);
+    else
+        project_bwd_kernel<false><<<blocks, PT, 0, stream>>>(
+            p, means3d, scales, reinterpret_cast<const float4 *>(quats), viewmat, cov3ds, radii,
+            conics, compensation, v_compensation, reinterpret_cast<const float2 *>(v_xy), v_depth,
+            v_conic, v_mean3d, v_scale, v_quat, v_cov2d, v_cov3d, nullptr, nullptr);
     JSB_CUDA_OK(cudaGetLastError());
     note_launch();
     return 0;

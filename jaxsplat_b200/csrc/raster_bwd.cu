@@ -724,7 +724,14 @@ struct HbStage {      // one sub-chunk of <= 32 visits
     float4 C[32];     // b, Gaussian id (bits), sorted index (bits), -
 };
 
-template <bool ABS>
+// MOMENTS (fused render only, no v_xy_abs): the nine reduced rows are rgb(3) and the raw moments
+//   M0 = sum a v, Mx = sum dx a v, My = sum dy a v, Mxx = sum dx^2 a v, Mxy = sum dx dy a v,
+//   Myy = sum dy^2 a v          (a = opacity * vis, v = v_alpha, dx / dy = mean - pixel)
+// accumulated into v_opacity / v_xy / v_conic in that order; the projection backward, which has
+// the conic and the opacity of the Gaussian in registers anyway, turns them into the gradients
+//   v_opacity = M0 / opacity, v_xy = -(cx Mx + cy My, cy Mx + cz My), v_conic = -(Mxx/2, Mxy, Myy/2)
+// (project.cu: FINISH_MOMENTS) -- five packed multiplies per visit instead of eleven.
+template <bool ABS, bool MOMENTS>
 __global__ void __launch_bounds__(32, JSB_BWDH_CTAS)
 raster_bwd_hits_kernel(const RasterParams p, const unsigned *__restrict__ ids_sorted,
                        const int2 *__restrict__ tile_bins, const SplatRecord *__restrict__ records,
@@ -774,16 +781,23 @@ raster_bwd_hits_kernel(const RasterParams p, const unsigned *__restrict__ ids_so
     const float2 tfc2 = f2(Tf0 * (voa0 - (vo0.x * bg.x + vo0.y * bg.y + vo0.z * bg.z)),
                            Tf1 * (voa1 - (vo1.x * bg.x + vo1.y * bg.y + vo1.z * bg.z)));
     const float2 vox2 = f2(vo0.x, vo1.x), voy2 = f2(vo0.y, vo1.y), voz2 = f2(vo0.z, vo1.z);
-    const float2 nvox2 = f2(-vo0.x, -vo1.x), nvoy2 = f2(-vo0.y, -vo1.y), nvoz2 = f2(-vo0.z, -vo1.z);
     const float2 npy2 = f2(-py0, -py1);
     float2 T2 = f2(Tf0, Tf1);
-    float2 bufx2 = f2(0.f, 0.f), bufy2 = bufx2, bufz2 = bufx2;
+    // <v_out, colour composited behind the current entry>: the only way the colour buffer of
+    // the reference (backward.cu:283-291) enters the gradient, so it is carried as ONE scalar per
+    // pixel instead of three channels
+    float2 S2 = f2(0.f, 0.f);
 
     // lane L (even, L/2 < NV) owns output row L/2 of the reduced gradient
     const int slot = lane >> 1;
     float *out_base;
     int out_stride;
     if (slot < 3) { out_base = v_colors + slot; out_stride = 3; }
+    else if (MOMENTS) {
+        if (slot < 4) { out_base = v_opacity; out_stride = 1; }
+        else if (slot < 6) { out_base = v_xy + (slot - 4); out_stride = 2; }
+        else { out_base = v_conic + min(slot - 6, 2); out_stride = 3; }
+    }
     else if (slot < 6) { out_base = v_conic + (slot - 3); out_stride = 3; }
     else if (slot < 8) { out_base = v_xy + (slot - 6); out_stride = 2; }
     else if (slot < 9) { out_base = v_opacity; out_stride = 1; }
@@ -912,28 +926,34 @@ raster_bwd_hits_kernel(const RasterParams p, const unsigned *__restrict__ ids_so
                 float2 P2 = __fmul2_rn(vox2, bc(bq.z));
                 P2 = __ffma2_rn(voy2, bc(bq.w), P2);
                 P2 = __ffma2_rn(voz2, bc(cb), P2);
-                float2 Q2 = __ffma2_rn(nvox2, bufx2, tfc2);
-                Q2 = __ffma2_rn(nvoy2, bufy2, Q2);
-                Q2 = __ffma2_rn(nvoz2, bufz2, Q2);
+                const float2 Q2 = __fadd2_rn(tfc2, f2(-S2.x, -S2.y));
                 const float2 va2 = __ffma2_rn(ra2, Q2, __fmul2_rn(T2, P2));
-                bufx2 = __ffma2_rn(fac2, bc(bq.z), bufx2);
-                bufy2 = __ffma2_rn(fac2, bc(bq.w), bufy2);
-                bufz2 = __ffma2_rn(fac2, bc(cb), bufz2);
-                // v_sigma = -opacity vis v_alpha
-                const float2 pv2 = __fmul2_rn(av2, va2);
-                const float2 vs2 = __fmul2_rn(pv2, bc(-1.f));
-                const float2 hs2 = __fmul2_rn(pv2, bc(-0.5f));
-                const float2 dxv2 = __fmul2_rn(bc(dx), vs2);    // dx v_sigma
+                S2 = __ffma2_rn(fac2, P2, S2);
+                const float2 pv2 = __fmul2_rn(av2, va2);        // -v_sigma = opacity vis v_alpha
                 float2 o2[9];
                 o2[0] = __fmul2_rn(vox2, fac2);
                 o2[1] = __fmul2_rn(voy2, fac2);
                 o2[2] = __fmul2_rn(voz2, fac2);
-                o2[3] = __fmul2_rn(bc(dx * dx), hs2);
-                o2[4] = __fmul2_rn(dy2, dxv2);
-                o2[5] = __fmul2_rn(dy2, __fmul2_rn(dy2, hs2));
-                o2[6] = __ffma2_rn(__fmul2_rn(dy2, bc(bq.x)), vs2, __fmul2_rn(bc(ca), vs2));  // (cx dx + cy dy) v_sigma
-                o2[7] = __fmul2_rn(__fadd2_rn(bc(ce), b2), vs2);                               // (cy dx + cz dy) v_sigma
-                o2[8] = __fmul2_rn(vis2, va2);
+                if (MOMENTS) {
+                    const float2 mx2 = __fmul2_rn(bc(dx), pv2);
+                    const float2 my2 = __fmul2_rn(dy2, pv2);
+                    o2[3] = pv2;                        // M0  -> v_opacity
+                    o2[4] = mx2;                        // Mx  -> v_xy.x
+                    o2[5] = my2;                        // My  -> v_xy.y
+                    o2[6] = __fmul2_rn(bc(dx), mx2);    // Mxx -> v_conic.x
+                    o2[7] = __fmul2_rn(dy2, mx2);       // Mxy -> v_conic.y
+                    o2[8] = __fmul2_rn(dy2, my2);       // Myy -> v_conic.z
+                } else {
+                    const float2 vs2 = __fmul2_rn(pv2, bc(-1.f));
+                    const float2 hs2 = __fmul2_rn(pv2, bc(-0.5f));
+                    const float2 dxv2 = __fmul2_rn(bc(dx), vs2);    // dx v_sigma
+                    o2[3] = __fmul2_rn(bc(dx * dx), hs2);
+                    o2[4] = __fmul2_rn(dy2, dxv2);
+                    o2[5] = __fmul2_rn(dy2, __fmul2_rn(dy2, hs2));
+                    o2[6] = __ffma2_rn(__fmul2_rn(dy2, bc(bq.x)), vs2, __fmul2_rn(bc(ca), vs2));  // (cx dx + cy dy) v_sigma
+                    o2[7] = __fmul2_rn(__fadd2_rn(bc(ce), b2), vs2);                               // (cy dx + cz dy) v_sigma
+                    o2[8] = __fmul2_rn(vis2, va2);
+                }
                 float v[NV];
 #pragma unroll
                 for (int r = 0; r < 9; ++r) v[r] = o2[r].x + o2[r].y;
@@ -1014,6 +1034,7 @@ extern bool g_disable_cull;
 bool g_bwd_one_pixel = false;  // option "bwd2px" = 0: the one-pixel-per-thread kernel
 bool g_bwd_scalar = false;     // option "bwdpk" = 0: the two-pixel kernel with scalar FP32 math
 bool g_bwd_no_hits = false;    // option "bwdhits" = 0: the batch kernels even when hit words exist
+bool g_bwd_no_moments = false;  // option "bwdmom" = 0: the fused backward emits finished gradients, not moments
 bool g_bwd_all_entries = false;  // option "bwdhits" = 2 (test hook): the hit-driven kernel replays EVERY entry
 
 template <bool CULL, bool ABS>
@@ -1037,19 +1058,27 @@ int launch_raster_bwd(cudaStream_t stream, const RasterParams &p, const unsigned
                       const int2 *tile_bins, const SplatRecord *records, const float *background,
                       const float *final_Ts, const int *final_idx, const float *v_out,
                       const float *v_out_alpha, float *v_xy, float *v_xy_abs, float *v_conic,
-                      float *v_colors, float *v_opacity, const unsigned *hit_words) {
+                      float *v_colors, float *v_opacity, const unsigned *hit_words,
+                      bool *moments_out) {
     const unsigned tiles = p.tiles_x * (p.band_y1 - p.band_y0);
+    if (moments_out) *moments_out = false;
     if (tiles == 0) return 0;
+    if (g_bwd_no_moments) moments_out = nullptr;
     if (p.block_width == 16 && hit_words && !g_bwd_no_hits && !g_bwd_one_pixel && !g_bwd_scalar) {
         // one independent warp per quadrant, driven by the forward's hit words
         if (v_xy_abs)
-            raster_bwd_hits_kernel<true><<<tiles * 4, 32, 0, stream>>>(
+            raster_bwd_hits_kernel<true, false><<<tiles * 4, 32, 0, stream>>>(
+                p, ids_sorted, tile_bins, records, hit_words, g_bwd_all_entries, background, final_Ts, final_idx, v_out,
+                v_out_alpha, v_xy, v_xy_abs, v_conic, v_colors, v_opacity);
+        else if (moments_out)
+            raster_bwd_hits_kernel<false, true><<<tiles * 4, 32, 0, stream>>>(
                 p, ids_sorted, tile_bins, records, hit_words, g_bwd_all_entries, background, final_Ts, final_idx, v_out,
                 v_out_alpha, v_xy, v_xy_abs, v_conic, v_colors, v_opacity);
         else
-            raster_bwd_hits_kernel<false><<<tiles * 4, 32, 0, stream>>>(
+            raster_bwd_hits_kernel<false, false><<<tiles * 4, 32, 0, stream>>>(
                 p, ids_sorted, tile_bins, records, hit_words, g_bwd_all_entries, background, final_Ts, final_idx, v_out,
                 v_out_alpha, v_xy, v_xy_abs, v_conic, v_colors, v_opacity);
+        if (moments_out) *moments_out = !v_xy_abs;
     } else if (p.block_width == 16 && !(g_bwd_one_pixel && v_xy_abs)) {
         if (v_xy_abs) {
             if (g_disable_cull)

@@ -29,13 +29,23 @@
 namespace jsb {
 namespace {
 
-constexpr int RC_ITEMS = 256;    // items per chunk (8 register groups of 32)
+// register groups of 32 items per chunk and staged outputs per chunk, level 1 / level 2: smaller
+// chunks halve a CTA's shared memory (the single-warp scatter CTAs are limited by it: 13-14 per SM
+// at 8 groups) at the price of more fixed work per output
+#ifndef JSB_RC_GROUPS1
+#define JSB_RC_GROUPS1 8
+#endif
+#ifndef JSB_RC_GROUPS2
+#define JSB_RC_GROUPS2 4
+#endif
 #ifndef JSB_RC_STAGE1
-#define JSB_RC_STAGE1 1024
+#define JSB_RC_STAGE1 (128 * JSB_RC_GROUPS1)
 #endif
 #ifndef JSB_RC_STAGE2
-#define JSB_RC_STAGE2 1536
+#define JSB_RC_STAGE2 (192 * JSB_RC_GROUPS2)
 #endif
+constexpr int RC_G1 = JSB_RC_GROUPS1, RC_G2 = JSB_RC_GROUPS2;
+constexpr int RC_ITEMS = 256;    // items per chunk of the COUNT kernels (8 register groups of 32)
 constexpr int RC_STAGE1 = JSB_RC_STAGE1;  // staged 8-byte row entries per level-1 chunk
 constexpr int RC_STAGE2 = JSB_RC_STAGE2;  // staged 4-byte ids per level-2 chunk
 
@@ -347,7 +357,7 @@ rc_tile_scan_bins_kernel(const RcParams p, unsigned *__restrict__ tile_cnt,
 // Shared memory per warp (nbp = bins + 1 rounded up to 32):
 //   mask u32[8][nbp] | off u32[nbp] | gbase u32[nbp] | stage Payload[STAGE] | pre u16[8][nbp] |
 //   bin u16[STAGE]
-template <typename Payload, int STAGE>
+template <typename Payload, int STAGE, int GROUPS>
 struct DistSmem {
     Payload *stage;
     unsigned *mask, *off, *gbase;
@@ -357,27 +367,27 @@ struct DistSmem {
         nbp = (nb + 1 + 31) & ~31u;
         stage = reinterpret_cast<Payload *>(base);
         mask = reinterpret_cast<unsigned *>(base + (size_t)STAGE * sizeof(Payload));
-        off = mask + 8 * nbp;
+        off = mask + GROUPS * nbp;
         gbase = off + nbp;
         pre = reinterpret_cast<unsigned short *>(gbase + nbp);
-        bin = pre + 8 * nbp;
+        bin = pre + GROUPS * nbp;
     }
     static size_t bytes(unsigned nb) {
         const size_t nbp = (nb + 1 + 31) & ~31u;
-        return (size_t)STAGE * sizeof(Payload) + 10 * nbp * 4 + 8 * nbp * 2 + (size_t)STAGE * 2;
+        return (size_t)STAGE * sizeof(Payload) + (GROUPS + 2) * nbp * 4 + GROUPS * nbp * 2 + (size_t)STAGE * 2;
     }
 };
 
 // steps 1 + 2; returns the number of (item, bin) pairs of the chunk (warp-uniform)
-template <typename Payload, int STAGE>
-__device__ __forceinline__ unsigned distribute_rank(const unsigned (&lo)[8], const unsigned (&len)[8],
-                                                    unsigned nb, const DistSmem<Payload, STAGE> &S) {
+template <typename Payload, int STAGE, int GROUPS>
+__device__ __forceinline__ unsigned distribute_rank(const unsigned (&lo)[GROUPS], const unsigned (&len)[GROUPS],
+                                                    unsigned nb, const DistSmem<Payload, STAGE, GROUPS> &S) {
     const unsigned lane = threadIdx.x, mine = 1u << lane, nbp = S.nbp;
     uint4 *mz = reinterpret_cast<uint4 *>(S.mask);
-    for (unsigned i = lane; i < 2 * nbp; i += 32) mz[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (unsigned i = lane; i < (GROUPS / 4) * nbp; i += 32) mz[i] = make_uint4(0u, 0u, 0u, 0u);
     __syncwarp();
 #pragma unroll
-    for (int q = 0; q < 8; ++q)
+    for (int q = 0; q < GROUPS; ++q)
         for (unsigned k = 0; k < len[q]; ++k) atomicOr(&S.mask[q * nbp + lo[q] + k], mine);
     __syncwarp();
     unsigned carry = 0;
@@ -386,7 +396,7 @@ __device__ __forceinline__ unsigned distribute_rank(const unsigned (&lo)[8], con
         unsigned run = 0;
         if (b < nb) {
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
+            for (int q = 0; q < GROUPS; ++q) {
                 S.pre[q * nbp + b] = (unsigned short)run;
                 run += __popc(S.mask[q * nbp + b]);
             }
@@ -400,14 +410,14 @@ __device__ __forceinline__ unsigned distribute_rank(const unsigned (&lo)[8], con
 }
 
 // steps 3 + 4 (S.gbase[b] = global index of the first element of the (chunk, bin) run)
-template <typename Payload, int STAGE>
-__device__ __forceinline__ void distribute_place(const unsigned (&lo)[8], const unsigned (&len)[8],
-                                                 const Payload (&pay)[8], unsigned pairs,
-                                                 const DistSmem<Payload, STAGE> &S,
+template <typename Payload, int STAGE, int GROUPS>
+__device__ __forceinline__ void distribute_place(const unsigned (&lo)[GROUPS], const unsigned (&len)[GROUPS],
+                                                 const Payload (&pay)[GROUPS], unsigned pairs,
+                                                 const DistSmem<Payload, STAGE, GROUPS> &S,
                                                  Payload *__restrict__ out) {
     const unsigned lane = threadIdx.x, below = (1u << lane) - 1u, nbp = S.nbp;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
+    for (int q = 0; q < GROUPS; ++q) {
         for (unsigned k = 0; k < len[q]; ++k) {
             const unsigned b = lo[q] + k;
             const unsigned rank = S.pre[q * nbp + b] + __popc(S.mask[q * nbp + b] & below);
@@ -435,20 +445,20 @@ rc_row_scatter_kernel(const RcParams p, const unsigned *__restrict__ order,
                       const unsigned *__restrict__ row_start, uint2 *__restrict__ entries) {
     extern __shared__ __align__(16) unsigned char rc_smem[];
     if (guard_trips(p.guard)) return;  // more row entries than the buffer holds: host rebuilds
-    const DistSmem<uint2, RC_STAGE1> S(rc_smem, p.rows);
+    const DistSmem<uint2, RC_STAGE1, RC_G1> S(rc_smem, p.rows);
     const unsigned lane = threadIdx.x, chunk = blockIdx.x;
-    unsigned lo[8], len[8];
-    uint2 pay[8];
-    unsigned gid[8];
-    bool have[8];
+    unsigned lo[RC_G1], len[RC_G1];
+    uint2 pay[RC_G1];
+    unsigned gid[RC_G1];
+    bool have[RC_G1];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {  // 8 independent loads of the depth order ...
+    for (int q = 0; q < RC_G1; ++q) {  // independent loads of the depth order ...
         const unsigned item = q * 32 + lane, pos = chunk * p.k1 + item;
         have[q] = item < p.k1 && pos < p.n;
         gid[q] = have[q] ? order[pos] : 0u;
     }
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {  // ... then 8 independent gathers of the boxes
+    for (int q = 0; q < RC_G1; ++q) {  // ... then independent gathers of the boxes
         uint2 b = make_uint2(0u, 0u);
         if (have[q]) b = __ldg(box_by_id + gid[q]);
         const unsigned w = b.y & 0xffffu, h = b.y >> 16;
@@ -469,9 +479,9 @@ rc_row_scatter_kernel(const RcParams p, const unsigned *__restrict__ order,
         const unsigned r = lane + 32u * i;
         if (r < p.rows) S.gbase[r] = gb[i];
     }
-    const unsigned pairs = distribute_rank<uint2, RC_STAGE1>(lo, len, p.rows, S);
+    const unsigned pairs = distribute_rank<uint2, RC_STAGE1, RC_G1>(lo, len, p.rows, S);
     if (pairs == 0) return;  // warp-uniform
-    distribute_place<uint2, RC_STAGE1>(lo, len, pay, pairs, S, entries);
+    distribute_place<uint2, RC_STAGE1, RC_G1>(lo, len, pay, pairs, S, entries);
 }
 
 // ---- level 2: row entries -> per-tile id lists -----------------------------------------------------
@@ -481,7 +491,7 @@ rc_col_scatter_kernel(const RcParams p, const uint4 *__restrict__ chunk_info,
                       const unsigned *__restrict__ tile_base, unsigned *__restrict__ out_ids) {
     extern __shared__ __align__(16) unsigned char rc_smem[];
     if (guard_trips(p.guard)) return;  // more intersections than the list buffer holds
-    const DistSmem<unsigned, RC_STAGE2> S(rc_smem, p.cols);
+    const DistSmem<unsigned, RC_STAGE2, RC_G2> S(rc_smem, p.cols);
     const unsigned lane = threadIdx.x, c = blockIdx.x;
     const uint4 info = __ldg(chunk_info + c);
     const unsigned r = info.x, ebeg = info.y, eend = info.z;
@@ -495,9 +505,9 @@ rc_col_scatter_kernel(const RcParams p, const uint4 *__restrict__ chunk_info,
         const unsigned x = lane + 32u * i;
         gb[i] = x < p.cols ? __ldg(tb + x) + __ldg(mrow + x) : 0u;
     }
-    unsigned lo[8], len[8], pay[8];
+    unsigned lo[RC_G2], len[RC_G2], pay[RC_G2];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
+    for (int q = 0; q < RC_G2; ++q) {
         const unsigned e = ebeg + q * 32 + lane;
         uint2 v = make_uint2(0u, 0u);
         if (q * 32 + lane < p.k2 && e < eend) v = entries[e];
@@ -510,18 +520,19 @@ rc_col_scatter_kernel(const RcParams p, const uint4 *__restrict__ chunk_info,
         const unsigned x = lane + 32u * i;
         if (x < p.cols) S.gbase[x] = gb[i];
     }
-    const unsigned pairs = distribute_rank<unsigned, RC_STAGE2>(lo, len, p.cols, S);
+    const unsigned pairs = distribute_rank<unsigned, RC_STAGE2, RC_G2>(lo, len, p.cols, S);
     if (pairs == 0) return;
-    distribute_place<unsigned, RC_STAGE2>(lo, len, pay, pairs, S, out_ids);
+    distribute_place<unsigned, RC_STAGE2, RC_G2>(lo, len, pay, pairs, S, out_ids);
 }
 
-static unsigned pick_items(unsigned long long produced, unsigned long long items, unsigned stage) {
+static unsigned pick_items(unsigned long long produced, unsigned long long items, unsigned stage,
+                           unsigned max_items) {
     // items per chunk such that the expected output of a chunk fills ~3/4 of the staging area
-    if (produced == 0 || items == 0) return RC_ITEMS;
+    if (produced == 0 || items == 0) return max_items;
     unsigned long long k = (unsigned long long)stage * 3ull * items / (4ull * produced);
     k &= ~31ull;
     if (k < 32) k = 32;
-    if (k > (unsigned)RC_ITEMS) k = RC_ITEMS;
+    if (k > max_items) k = max_items;
     return (unsigned)k;
 }
 
@@ -532,8 +543,8 @@ static RcParams rc_params(const BinParams &bp, unsigned long long row_entries,
     p.rows = bp.band_y1 - bp.band_y0;
     p.cols = bp.tiles_x;
     p.band_y0 = bp.band_y0;
-    p.k1 = pick_items(row_entries, bp.num_points, RC_STAGE1);
-    p.k2 = pick_items(num_intersects, row_entries, RC_STAGE2);
+    p.k1 = pick_items(row_entries, bp.num_points, RC_STAGE1, 32 * RC_G1);
+    p.k2 = pick_items(num_intersects, row_entries, RC_STAGE2, 32 * RC_G2);
     p.n1 = ceil_div(p.n, p.k1);
     p.n1s = (p.n1 + 3u) & ~3u;
     p.n2max = (unsigned)(row_entries / p.k2) + p.rows;
@@ -576,8 +587,8 @@ int launch_rowcol_lists(cudaStream_t stream, const BinParams &bp, const unsigned
     unsigned *tile_cnt = scratch + L.tile_cnt;
     unsigned *m = scratch + L.m;
     uint2 *entries = reinterpret_cast<uint2 *>(scratch + L.entries);
-    const size_t smem1 = DistSmem<uint2, RC_STAGE1>::bytes(p.rows);
-    const size_t smem2 = DistSmem<unsigned, RC_STAGE2>::bytes(p.cols);
+    const size_t smem1 = DistSmem<uint2, RC_STAGE1, RC_G1>::bytes(p.rows);
+    const size_t smem2 = DistSmem<unsigned, RC_STAGE2, RC_G2>::bytes(p.cols);
 
     if (phase == 0) {  // level 1: row lists
         rc_row_count_kernel<<<ceil_div(p.n1, (unsigned)RC_RC_WARPS), 32 * RC_RC_WARPS, 0, stream>>>(

@@ -483,18 +483,23 @@ def test_hit_driven_backward_through_the_fused_render_and_bands():
     H, W = s.img_shape
     target = torch.rand((H, W, 3), generator=torch.Generator().manual_seed(9)).to(G.DEV)
     res = {}
-    for hits in (1, 0):
+    # (hit-driven, raw moments finished by the projection backward) / (hit-driven, finished
+    # gradients from the rasteriser) / (batch kernel)
+    for mode in ((1, 1), (1, 0), (0, 1)):
         try:
-            _lib.set_option("bwdhits", hits)
+            _lib.set_option("bwdhits", mode[0])
+            _lib.set_option("bwdmom", mode[1])
             for rows in (None, (5, 19)):
                 params = [p.clone().requires_grad_(True) for p in sc.params()]
                 img = jsb.render(*params, tile_rows=rows, **sc.render_kwargs())
                 y0, y1 = (0, H) if rows is None else (rows[0] * 16, min(H, rows[1] * 16))
                 (((img[y0:y1] - target[y0:y1]) ** 2).sum() / (H * W * 3)).backward()
-                res[(hits, rows)] = [G.npy(p.grad) for p in params]
+                res[(mode, rows)] = [G.npy(p.grad) for p in params]
         finally:
             _lib.set_option("bwdhits", 1)
+            _lib.set_option("bwdmom", 1)
     for rows in (None, (5, 19)):
-        for a, b in zip(res[(1, rows)], res[(0, rows)]):
-            ok, err, scale = grad_close(a, b, rel=2e-5)
-            assert ok, (rows, err, scale)
+        for mode in ((1, 1), (1, 0)):
+            for a, b in zip(res[(mode, rows)], res[((0, 1), rows)]):
+                ok, err, scale = grad_close(a, b, rel=2e-5)
+                assert ok, (mode, rows, err, scale)

@@ -90,6 +90,14 @@ def main():
     args = parse()
     real_stdout = os.fdopen(os.dup(1), "w")
     os.dup2(2, 1)  # NCCL banners go to stderr: stdout carries the one JSON line
+    out = run(args)
+    if out is not None:
+        print(json.dumps(out), file=real_stdout, flush=True)
+
+
+def run(args):
+    """the measurement itself; returns the result dict on rank 0 (None elsewhere).  bench.py calls
+    this for `--config C4` / `--config C5` with an argparse-like namespace."""
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -217,9 +225,11 @@ def main():
         out.update(extra)
         if cuda:
             out["workspace_bytes"] = _lib.stats()["workspace_bytes"]
-        print(json.dumps(out), file=real_stdout, flush=True)
+    else:
+        out = None
     if world > 1:
         dist.destroy_process_group()
+    return out
 
 
 if __name__ == "__main__":
