@@ -19,8 +19,6 @@ symmetric buffer (jaxsplat_b200.set_gradient_sink) that is summed with one all-r
   e2e    : same step, but the step's host inputs (8-bit target image + camera, pinned) are copied H2D
            and the loss is read back D2H inside the timed region (wall clock around K steps);
            the copy of step k+1 runs on a copy stream under step k
-  JSB_BENCH_OVERLAP=1 (N > 1, experimental, off by default): the appearance gradients' share of
-           the all-reduce runs on a side stream under the projection backward
   --impl reference : the UNMODIFIED reference CUDA library (oracle/_ref, built from
            /root/reference/lib by oracle/Makefile) driven through the same harness on rank 0.
 """
@@ -257,15 +255,6 @@ def main():
     if args.impl == "ours":
         if os.environ.get("JSB_ROWCOL") == "0":
             _lib.set_option("rowcol", 0)
-        if os.environ.get("JSB_FWD2PX") == "0":
-            _lib.set_option("fwd2px", 0)
-        if os.environ.get("JSB_BWD2PX") == "0":
-            _lib.set_option("bwd2px", 0)
-        for key in ("bwdpk", "fwdpk"):  # packed FP32x2 rasterisers (A/B: tools/gpu_pk.sh)
-            if os.environ.get("JSB_" + key.upper()) == "0":
-                _lib.set_option(key, 0)
-        if os.environ.get("JSB_SPEC") == "1":  # lists + rasteriser launched before the counts are known
-            _lib.set_option("spec", 1)
         if os.environ.get("JSB_BWDMOM") == "0":  # hit-driven backward emits finished gradients
             _lib.set_option("bwdmom", 0)
         if os.environ.get("JSB_BWDHITS") == "0":  # per-tile batch backward instead of the hit-driven one
@@ -297,19 +286,6 @@ def main():
             off += q.numel()
         jsb.set_gradient_sink(sink_views + [flat_scratch])
     sink_ok = [False]
-    # EXPERIMENTAL (JSB_BENCH_OVERLAP=1, written without GPU access, not yet run on GPUs): the
-    # appearance gradients (colors + opacities: the last 4N of the 14N floats) are final when the
-    # rasteriser backward ends, so their share of the all-reduce runs on a side stream under the
-    # projection backward; the library records `ev_app` between its two backward kernels
-    overlap = (use_dist and reducer is not None and sink_views is not None
-               and os.environ.get("JSB_BENCH_OVERLAP") == "1" and N % 4 == 0)
-    if overlap:
-        side = torch.cuda.Stream(device=dev)
-        ev_app, ev_side = torch.cuda.Event(), torch.cuda.Event()
-        ev_app.record()   # materialises the CUDA handle
-        ev_side.record()
-        _lib.set_raster_bwd_event(ev_app)
-
     # the MSE and its cotangent come from one kernel of the library (csrc/loss.cu: 0.841 vs 0.859 ms
     # per step, profiles/r02a_bench_nativeloss.json); JSB_BENCH_NATIVE_LOSS=0 = three torch kernels
     # (the reference arm always uses those: its library has no loss kernel)
@@ -341,15 +317,7 @@ def main():
                     q.grad.data_ptr() == v.data_ptr() for q, v in zip(params, sink_views))
             if not sink_ok[0]:
                 torch.cat([q.grad.reshape(-1) for q in params], out=flat_g)
-            if overlap and sink_ok[0]:
-                main = torch.cuda.current_stream()
-                side.wait_event(ev_app)          # recorded inside the backward, after raster_bwd
-                with torch.cuda.stream(side):
-                    reducer.all_reduce_range(10 * N, 4 * N, channel=1)
-                    ev_side.record(side)
-                reducer.all_reduce_range(0, 10 * N, channel=0)   # after project_bwd, main stream
-                main.wait_event(ev_side)         # the step ends when both halves are reduced
-            elif reducer is not None:
+            if reducer is not None:
                 reducer.all_reduce()
             else:
                 dist.all_reduce(flat_g)
@@ -487,9 +455,7 @@ def main():
                    "num_intersects": I, "parallelism": (f"view-parallel dp{world}, gradient all-reduce: "
                                    f"{reducer.mode if reducer is not None else 'nccl'}, gradients "
                                    f"{'written in place into' if sink_ok[0] else 'packed (torch.cat) into'} "
-                                   "the reduced buffer"
-                                   + (", appearance gradients reduced on a side stream under project_bwd"
-                                      if world > 1 and overlap else "")) if world > 1 else "single GPU",
+                                   "the reduced buffer") if world > 1 else "single GPU",
                    "l2": "per-step working set ~0.5 GB (keys/ids ping-pong 0.2 GB, records, images, "
                          "parameters, gradients) exceeds the 126 MB L2; no explicit flush",
                    "timing": "CUDA events around exactly K steps, barrier+synchronize both sides, max over ranks"},
@@ -580,7 +546,9 @@ def main():
                                "peak_source": which_peak}
         out["stages"] = per_stage
 
-    if args.impl == "ours" and world == 1 and not args.no_cpu_baseline:
+    # (the CPU oracle is timed on the configurations it finishes in seconds; C3b's 2.6e8
+    # intersections would take minutes per view)
+    if args.impl == "ours" and world == 1 and not args.no_cpu_baseline and args.config in ("C1", "C2", "C3", "C3s"):
         from oracle import cpu
         s_np = cpu.scene_to_numpy(scene)
         tgt_np = (target_host.to(torch.float32) / 255.0).numpy()

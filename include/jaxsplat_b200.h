@@ -164,10 +164,6 @@ JSB200_API unsigned long long jsb200_error_count(void);
 /* Test / measurement hooks (no reference equivalent). */
 /* key: "cull" (1 default; 0 disables the conservative warp-rectangle pre-filter),
  *      "cache" (1 default; 0 forces rasterize_bwd to re-bin instead of reusing the forward's),
- *      "fwd2px" / "bwd2px" (1 default; 0 runs rasterize_fwd / rasterize_bwd with one pixel per
- *               thread instead of two),
- *      "fwdpk" / "bwdpk" (1 default; 0 runs the two-pixel rasterisers with scalar FP32 math
- *               instead of the packed FP32x2 instructions of sm_100),
  *      "rowcol" (1 default; 0 builds the per-tile lists with the older counting distribution of
  *               tile_lists.cu instead of the two-level row/column distribution),
  *      "bwdmom" (1 default; 0 makes the fused render's hit-driven rasteriser backward accumulate
@@ -211,13 +207,6 @@ JSB200_API void jsb200_get_stats(unsigned long long *out8);
 JSB200_API void jsb200_get_speculation_stats(unsigned long long *out2);
 /* releases every workspace (all devices/streams). */
 JSB200_API void jsb200_release(void);
-
-/* Registers a CUDA event (cudaEvent_t, or NULL to clear) that jsb200_render_bwd records on its
- * stream between its two kernels, i.e. at the point where v_colors and v_opacity are final and
- * only the projection backward is left: a data-parallel driver can wait on it from a second stream
- * and reduce those two gradients across GPUs while the projection backward still runs.
- * Process-wide (one process drives one GPU); the batched-camera calls do not record it. */
-JSB200_API int jsb200_set_raster_bwd_event(void *cuda_event);
 
 /* ---- multi-GPU (no reference equivalent: yklcs/jaxsplat is single-device) ----
  * In-place sum of n_floats floats across the `world` ranks of one NVSwitch node, in ONE kernel:

@@ -41,7 +41,6 @@ EXPORTS = (
     "jsb200_get_stats",
     "jsb200_get_speculation_stats",
     "jsb200_release",
-    "jsb200_set_raster_bwd_event",
     "jsb200_multimem_allreduce_f32",
     "jsb200_adam_step",
     "jsb200_mse_loss_grad",
@@ -115,8 +114,6 @@ def lib() -> ctypes.CDLL:
     L.jsb200_get_speculation_stats.restype = None
     L.jsb200_release.argtypes = []
     L.jsb200_release.restype = None
-    L.jsb200_set_raster_bwd_event.argtypes = [vp]
-    L.jsb200_set_raster_bwd_event.restype = i
     L.jsb200_multimem_allreduce_f32.argtypes = [vp, vp, ctypes.POINTER(vp), sz, sz, i, i, u]
     L.jsb200_multimem_allreduce_f32.restype = i
     L.jsb200_adam_step.argtypes = [vp, vp, vp, vp, vp, sz, f, f, f, f, ctypes.c_ulonglong]
@@ -154,15 +151,6 @@ def speculation_stats() -> dict:
 def set_option(key: str, value: int) -> None:
     if lib().jsb200_set_option(key.encode(), int(value)) != 0:
         check_error("set_option")
-
-
-def set_raster_bwd_event(event) -> None:
-    """``event``: a ``torch.cuda.Event`` that has been recorded at least once (its CUDA handle
-    exists only then), or None.  The fused render backward records it between its two kernels
-    (include/jaxsplat_b200.h: jsb200_set_raster_bwd_event)."""
-    handle = None if event is None else ctypes.c_void_p(int(event.cuda_event))
-    if lib().jsb200_set_raster_bwd_event(handle) != 0:
-        check_error("set_raster_bwd_event")
 
 
 STAGES = ("project_fwd", "bin_prep", "depth_sort", "emit", "tile_scatter", "tile_offsets", "raster_fwd",

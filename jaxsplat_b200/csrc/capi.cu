@@ -53,19 +53,12 @@ void set_error(const char *fmt, ...) {
 void note_launch(int n) { g_stats[6].fetch_add((unsigned long long)n); }
 
 extern bool g_disable_cull;
-extern bool g_bwd_one_pixel;
-extern bool g_bwd_scalar;
-extern bool g_fwd_scalar;
-extern bool g_fwd_one_pixel;
 extern bool g_bwd_no_hits;
 extern bool g_bwd_all_entries;
 extern bool g_bwd_no_moments;
 static bool g_disable_cache = false;
 static bool g_disable_rowcol = false;
 static bool g_disable_resident_sort = false;  // option "sort1k" 0: the four-pass onesweep depth sort
-// jsb200_set_raster_bwd_event: recorded by the fused render backward between its two kernels
-// (process-wide: autograd runs the backward on its own thread, so not thread-local)
-static std::atomic<cudaEvent_t> g_raster_bwd_event{nullptr};
 static unsigned g_view_slots = 8;  // binning workspaces a batched-camera call cycles through
 
 // ---- optional per-stage device timing (jsb200_set_option("timing", 1)) -------------------------
@@ -540,7 +533,7 @@ static int forward_lists_and_raster(Ctx &c, const Descriptor &d, const float *ba
     if (!g_disable_spec && c.plan_valid && c.plan_I > 0 && d.num_points != 0 &&
         c.plan_n == d.num_points && c.plan_tiles_x == d.tiles_x && c.plan_tiles_y == d.tiles_y &&
         c.plan_bw == d.block_width && c.plan_band == d.pad && d.block_width == 16 &&
-        !g_fwd_one_pixel && !g_disable_rowcol && rowcol_supported(bp)) {
+        !g_disable_rowcol && rowcol_supported(bp)) {
         Ip = c.plan_I + c.plan_I / 4 + 4096;
         Ep = c.plan_E + c.plan_E / 4 + 4096;
         if (Ip < (1ull << 30)) {
@@ -891,16 +884,11 @@ static int render_bwd_impl(cudaStream_t stream, void **buf, const Descriptor &d,
                               (float *)buf[23], (float *)buf[20], (float *)buf[21],
                               c->cache_has_hits ? (const unsigned *)c->hits.p : nullptr,
                               // (raw moments leave v_opacity unfinished until project_bwd: not
-                              // when it accumulates over views or a driver reduces it early)
-                              (keep_appearance || g_raster_bwd_event.load()) ? nullptr : &moments))
+                              // when it accumulates over the views of a batched call)
+                              keep_appearance ? nullptr : &moments))
             return 1;
     }
     moments_flag = moments;
-    }
-    // v_colors / v_opacity are final from here on (project_bwd only produces the other three): a
-    // data-parallel driver may start reducing them on another stream under project_bwd
-    if (slot == 0 && !keep_appearance) {
-        if (cudaEvent_t ev = g_raster_bwd_event.load()) JSB_CUDA_OK(cudaEventRecord(ev, stream));
     }
     // project_bwd with zero cotangents for depth and compensation (render uses neither)
     void *pbuf[18] = {buf[0], buf[1], buf[2], buf[3], buf[7], buf[8], buf[10], buf[11], buf[12],
@@ -1216,19 +1204,10 @@ const char *jsb200_last_error(void) { return jsb::t_has_error ? jsb::t_error.c_s
 void jsb200_clear_error(void) { jsb::t_has_error = false; jsb::t_error.clear(); }
 unsigned long long jsb200_error_count(void) { return jsb::g_error_count.load(); }
 
-int jsb200_set_raster_bwd_event(void *cuda_event) {
-    jsb::g_raster_bwd_event.store((cudaEvent_t)cuda_event);
-    return 0;
-}
-
 int jsb200_set_option(const char *key, int value) {
     if (!key) return 1;
     if (!strcmp(key, "cull")) { jsb::g_disable_cull = (value == 0); return 0; }
     if (!strcmp(key, "cache")) { jsb::g_disable_cache = (value == 0); return 0; }
-    if (!strcmp(key, "fwd2px")) { jsb::g_fwd_one_pixel = (value == 0); return 0; }
-    if (!strcmp(key, "bwd2px")) { jsb::g_bwd_one_pixel = (value == 0); return 0; }
-    if (!strcmp(key, "bwdpk")) { jsb::g_bwd_scalar = (value == 0); return 0; }
-    if (!strcmp(key, "fwdpk")) { jsb::g_fwd_scalar = (value == 0); return 0; }
     if (!strcmp(key, "rowcol")) { jsb::g_disable_rowcol = (value == 0); return 0; }
     if (!strcmp(key, "bwdmom")) { jsb::g_bwd_no_moments = (value == 0); return 0; }
     if (!strcmp(key, "spec")) { jsb::g_disable_spec = (value == 0); return 0; }

@@ -6,15 +6,17 @@
 // 0.99 here (0.999 in the forward) and the clamp is treated as identity.
 //
 // Design (not a port):
-//   * same CTA/warp-rectangle layout, staging and conservative culling as raster_fwd.cu, so a
-//     warp only replays Gaussians that can reach its 8x4 pixels;
-//   * the CTA starts at the batch holding the largest final_idx of the tile instead of the end
-//     of the tile's list;
-//   * the 11 per-pixel partial gradients are reduced across the warp through a per-warp shared
-//     transpose (11 conflict-free STS, then 22 lanes each sum half a row with 4 LDS.128 + 15 FADD,
-//     one shuffle joins the halves) instead of 11 full butterflies (55 SHFL + 55 FADD); the 11
-//     totals end up in 11 different lanes which issue ONE predicated RED.ADD.F32 instruction
-//     instead of 11 serial ones from lane 0;
+//   * the default kernel (raster_bwd_hits_kernel) is driven by the forward's hit words: one
+//     independent warp per 8x8 quadrant replays only the list entries the forward marked as
+//     accepted, from a dense staged array, with no CTA barrier anywhere;
+//   * the batch kernel (raster_bwd16x2p_kernel) is what runs when no hit words exist (the binning
+//     was rebuilt by the backward itself): same CTA/quadrant layout, staging and conservative
+//     culling as raster_fwd.cu, starting at the batch holding the largest final_idx of the tile;
+//   * both: two pixels per lane in packed FP32x2 registers; the per-pixel partial gradients are
+//     reduced across the warp through a per-warp shared transpose (conflict-free STS, then 18
+//     lanes each sum half a row with 4 LDS.128 + 7 FADD2, one shuffle joins the halves) instead of
+//     full butterflies, and the totals end up in different lanes which issue ONE predicated
+//     RED.ADD.F32 instruction; the reduction of a visit is deferred into the next visit;
 //   * invalid lanes are not branched around: their alpha and visibility are forced to 0, which
 //     makes every partial exactly 0 and leaves T and the colour buffer unchanged.
 #include "common.cuh"
@@ -25,12 +27,7 @@
 namespace jsb {
 namespace {
 
-constexpr int RB = 256;
 constexpr int RED_STRIDE = 36;  // floats per transposed row: 16-byte phases of LDS.128 conflict-free
-
-struct PixelGrad {
-    float v[11];  // rgb(3) conic(3) xy(2) xy_abs(2) opacity(1)
-};
 
 // per-pixel gradient of one valid (pixel, Gaussian) pair; updates T and the colour buffer
 __device__ __forceinline__ void pair_grad(bool valid, float alpha, float vis, float opac, float dx, float dy,
@@ -71,138 +68,13 @@ __device__ __forceinline__ void pair_grad(bool valid, float alpha, float vis, fl
     o[10] = vis * va;
 }
 
-template <bool CULL>
-__global__ void __launch_bounds__(RB, 4)
-raster_bwd16_kernel(const RasterParams p, const unsigned *__restrict__ ids_sorted,
-                    const int2 *__restrict__ tile_bins, const SplatRecord *__restrict__ records,
-                    const float *__restrict__ background, const float *__restrict__ final_Ts,
-                    const int *__restrict__ final_idx, const float *__restrict__ v_out_img,
-                    const float *__restrict__ v_out_alpha_img, float *__restrict__ v_xy,
-                    float *__restrict__ v_xy_abs, float *__restrict__ v_conic,
-                    float *__restrict__ v_colors, float *__restrict__ v_opacity) {
-    __shared__ float4 sA[RB];
-    __shared__ float4 sB[RB];
-    __shared__ float sC[RB];
-    __shared__ unsigned sId[RB];
-    __shared__ unsigned char sMask[RB];
-    __shared__ int s_max[RB / 32];
-    __shared__ __align__(16) float sRed[(RB / 32) * 11 * RED_STRIDE];
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    float *red = sRed + warp * 11 * RED_STRIDE;
-    const unsigned tile = p.band_y0 * p.tiles_x + blockIdx.x;
-    const unsigned tile_y = tile / p.tiles_x, tile_x = tile - tile_y * p.tiles_x;
-    const unsigned j = tile_x * 16 + (warp & 1) * kRectW + (lane & 7);
-    const unsigned i = tile_y * 16 + (warp >> 1) * kRectH + (lane >> 3);
-    const float px = (float)j + 0.5f, py = (float)i + 0.5f;
-    const bool inside = (i < p.img_h) && (j < p.img_w);
-    const int2 range = tile_bins[tile];
-
-    float T_final = 1.f, v_oa = 0.f;
-    float3 v_out = make_float3(0.f, 0.f, 0.f);
-    int bin_final = -1;
-    if (inside) {
-        const size_t pix = (size_t)i * p.img_w + j;
-        T_final = final_Ts[pix];
-        bin_final = final_idx[pix];
-        v_out = make_float3(v_out_img[pix * 3], v_out_img[pix * 3 + 1], v_out_img[pix * 3 + 2]);
-        v_oa = v_out_alpha_img[pix];
-    }
-    const float3 bg = make_float3(__ldg(background), __ldg(background + 1), __ldg(background + 2));
-    float T = T_final;
-    float3 buf = make_float3(0.f, 0.f, 0.f);
-
-    // largest final index of the warp and of the tile
-    int wmax = bin_final;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
-    if (lane == 0) s_max[warp] = wmax;
-    __syncthreads();
-    int tmax = s_max[0];
-#pragma unroll
-    for (int w = 1; w < RB / 32; ++w) tmax = max(tmax, s_max[w]);
-    const int top = min(range.y - 1, tmax);
-    if (top < range.x) return;  // nothing in this tile was composited (uniform across the CTA)
-    const int num_batches = (top - range.x + RB) / RB;
-    const float tile_x0 = (float)(tile_x * 16), tile_y0 = (float)(tile_y * 16);
-
-    // lane L (even, L/2 < 11) owns output slot L/2 of the reduced gradient
-    const int slot = lane >> 1;
-    float *out_base;
-    int out_stride;
-    if (slot < 3) { out_base = v_colors + slot; out_stride = 3; }
-    else if (slot < 6) { out_base = v_conic + (slot - 3); out_stride = 3; }
-    else if (slot < 8) { out_base = v_xy + (slot - 6); out_stride = 2; }
-    else if (slot < 10) { out_base = v_xy_abs + (slot - 8); out_stride = 2; }
-    else { out_base = v_opacity; out_stride = 1; }
-    const bool writer = ((lane & 1) == 0) && slot < 11;
-
-    for (int b = 0; b < num_batches; ++b) {
-        if (b) __syncthreads();
-        const int batch_end = top - RB * b;  // slot t holds sorted index batch_end - t
-        const int idx = batch_end - tid;
-        unsigned mask = 0;
-        if (idx >= range.x) {
-            const unsigned g = ids_sorted[idx];
-            const float4 q0 = __ldg(&records[g].q0);
-            const float4 q1 = __ldg(&records[g].q1);
-            const float4 q2 = __ldg(&records[g].q2);
-            sA[tid] = q0;
-            sB[tid] = q1;
-            sC[tid] = q2.x;
-            sId[tid] = g;
-            mask = CULL ? cull_mask16(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, tile_x0, tile_y0) : 0xFFu;
-        }
-        sMask[tid] = (unsigned char)mask;
-        __syncthreads();
-
-#pragma unroll 1
-        for (int k = 0; k < RB / 32; ++k) {
-            // entries newer than the warp's largest final index cannot be valid for any lane
-            if (batch_end - (k * 32 + 31) > wmax) continue;
-            const unsigned m = sMask[k * 32 + lane];
-            unsigned bits = __ballot_sync(0xffffffffu, (m >> warp) & 1u);
-            while (bits) {
-                const int t = k * 32 + __ffs(bits) - 1;
-                bits &= bits - 1;
-                const float4 a = sA[t];
-                const float4 bq = sB[t];
-                const float dx = fsub(a.x, px), dy = fsub(a.y, py);
-                const float sigma = conic_sigma(a.w, bq.x, bq.y, dx, dy);
-                const float vis = ex2_approx(fmul(sigma, kNegLog2e));
-                const float alpha = fminf(fmul(a.z, vis), 0.99f);
-                const bool valid = inside && (batch_end - t <= bin_final) && !(sigma < 0.f) &&
-                                   !(alpha < kAlphaMin);
-                if (!__any_sync(0xffffffffu, valid)) continue;
-                float v[11];
-                pair_grad(valid, alpha, vis, a.z, dx, dy, a.w, bq.x, bq.y, bq.z, bq.w, sC[t], v_out,
-                          v_oa, T_final, bg, T, buf, v);
-                // transpose through shared memory: row k = value k of the 32 lanes
-                __syncwarp();
-#pragma unroll
-                for (int k = 0; k < 11; ++k) red[k * RED_STRIDE + lane] = v[k];
-                __syncwarp();
-                float total = 0.f;
-                if (lane < 22) {
-                    const float4 *row = reinterpret_cast<const float4 *>(red + (lane >> 1) * RED_STRIDE + (lane & 1) * 16);
-                    const float4 p0 = row[0], p1 = row[1], p2 = row[2], p3 = row[3];
-                    total = ((p0.x + p0.y) + (p0.z + p0.w)) + ((p1.x + p1.y) + (p1.z + p1.w)) +
-                            (((p2.x + p2.y) + (p2.z + p2.w)) + ((p3.x + p3.y) + (p3.z + p3.w)));
-                }
-                total += __shfl_xor_sync(0xffffffffu, total, 1);
-                if (writer) atomicAdd(out_base + sId[t] * (unsigned)out_stride, total);
-            }
-        }
-    }
-}
-
-// ---- two pixels per thread -------------------------------------------------------------------
-// Same algorithm, but a CTA is 4 warps and each warp owns an 8x8 quadrant of the tile: lane l
-// replays pixels (x, y) and (x, y + 4).  The two pixels' partial gradients are added in registers
-// before the cross-lane reduction, so the transpose / 22-lane sums / RED (a third of the
-// instructions of a visit) and the candidate bookkeeping are paid once per 64 pixels instead of
-// once per 32.  ABS = false (fused render: nothing consumes v_xy_abs) drops two of the eleven rows.
-// Row order of the reduction: rgb(3) conic(3) xy(2) opacity(1) xy_abs(2).
+// ---- two pixels per thread ---------------------------------------------------------------------
+// A CTA is 4 warps and each warp owns an 8x8 quadrant of the tile: lane l replays pixels (x, y) and
+// (x, y + 4).  The two pixels' partial gradients are added in registers before the cross-lane
+// reduction, so the transpose / half-row sums / RED (a third of the instructions of a visit) and
+// the candidate bookkeeping are paid once per 64 pixels.  ABS = false (fused render: nothing
+// consumes v_xy_abs) drops two of the eleven rows.  Row order of the reduction: rgb(3) conic(3)
+// xy(2) opacity(1) xy_abs(2).
 constexpr int RB2 = 128;
 // tuning knobs of the packed kernel (A/B builds: make EXTRA=-DJSB_BWD_CTAS=5 ...)
 #ifndef JSB_BWD_CTAS
@@ -211,228 +83,6 @@ constexpr int RB2 = 128;
 #ifndef JSB_BWD_EPT
 #define JSB_BWD_EPT 2    // staged entries per thread and batch (batch = 128 * EPT entries)
 #endif
-
-// tfc = T_final * (v_out_alpha - <v_out, background>): the two background/alpha terms of the
-// reference's v_alpha (backward.cu:283-291) are both proportional to T_final * ra, so they fold
-// into one FMA per pair with a per-pixel constant.
-template <bool ABS, bool ACC>
-__device__ __forceinline__ void pair_grad2(bool valid, float alpha, float vis, float opac, float dx,
-                                           float dy, float cx, float cy, float cz, float r, float g,
-                                           float b, const float3 v_out, float tfc, float &T,
-                                           float3 &buf, float *o) {
-    alpha = valid ? alpha : 0.f;
-    vis = valid ? vis : 0.f;
-    float ra;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ra) : "f"(1.f - alpha));
-    ra = valid ? ra : 1.f;
-    T = T * ra;
-    const float fac = alpha * T;
-    float va = v_out.x * (T * r - buf.x * ra);
-    va = fmaf(v_out.y, T * g - buf.y * ra, va);
-    va = fmaf(v_out.z, T * b - buf.z * ra, va);
-    va = fmaf(tfc, ra, va);
-    buf.x = fmaf(fac, r, buf.x);
-    buf.y = fmaf(fac, g, buf.y);
-    buf.z = fmaf(fac, b, buf.z);
-    const float v_sigma = (vis * (-opac)) * va;
-    const float hs = v_sigma * 0.5f;
-    const float gx = fmaf(dy, cy, dx * cx) * v_sigma, gy = fmaf(dy, cz, dx * cy) * v_sigma;
-    if (ACC) {
-        o[0] = fmaf(v_out.x, fac, o[0]);
-        o[1] = fmaf(v_out.y, fac, o[1]);
-        o[2] = fmaf(v_out.z, fac, o[2]);
-        o[3] = fmaf(dx, dx * hs, o[3]);
-        o[4] = fmaf(dy, dx * v_sigma, o[4]);
-        o[5] = fmaf(dy, dy * hs, o[5]);
-        o[6] += gx;
-        o[7] += gy;
-        o[8] = fmaf(vis, va, o[8]);
-        if (ABS) { o[9] += fabsf(gx); o[10] += fabsf(gy); }
-    } else {
-        o[0] = v_out.x * fac;
-        o[1] = v_out.y * fac;
-        o[2] = v_out.z * fac;
-        o[3] = dx * (dx * hs);
-        o[4] = dy * (dx * v_sigma);
-        o[5] = dy * (dy * hs);
-        o[6] = gx;
-        o[7] = gy;
-        o[8] = vis * va;
-        if (ABS) { o[9] = fabsf(gx); o[10] = fabsf(gy); }
-    }
-}
-
-template <bool CULL, bool ABS>
-__global__ void __launch_bounds__(RB2, 6)
-raster_bwd16x2_kernel(const RasterParams p, const unsigned *__restrict__ ids_sorted,
-                      const int2 *__restrict__ tile_bins, const SplatRecord *__restrict__ records,
-                      const float *__restrict__ background, const float *__restrict__ final_Ts,
-                      const int *__restrict__ final_idx, const float *__restrict__ v_out_img,
-                      const float *__restrict__ v_out_alpha_img, float *__restrict__ v_xy,
-                      float *__restrict__ v_xy_abs, float *__restrict__ v_conic,
-                      float *__restrict__ v_colors, float *__restrict__ v_opacity) {
-    constexpr int NV = ABS ? 11 : 9;
-    constexpr int BATCH = 256;  // two staged entries per thread
-    __shared__ float4 sA2[2][BATCH];  // double-buffered batches (cp.async staging)
-    __shared__ float4 sB2[2][BATCH];
-    __shared__ float sC2[2][BATCH];
-    __shared__ unsigned sId2[2][BATCH];
-    __shared__ unsigned char sMask[BATCH];
-    __shared__ int s_max[RB2 / 32];
-    __shared__ __align__(16) float sRed[(RB2 / 32) * NV * RED_STRIDE];
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    float *red = sRed + warp * NV * RED_STRIDE;
-    const unsigned tile = p.band_y0 * p.tiles_x + blockIdx.x;
-    const unsigned tile_y = tile / p.tiles_x, tile_x = tile - tile_y * p.tiles_x;
-    const unsigned j = tile_x * 16 + (warp & 1) * 8 + (lane & 7);
-    const unsigned i0 = tile_y * 16 + (warp >> 1) * 8 + (lane >> 3), i1 = i0 + 4;
-    const float px = (float)j + 0.5f, py0 = (float)i0 + 0.5f, py1 = (float)i1 + 0.5f;
-    const bool in0 = (i0 < p.img_h) && (j < p.img_w), in1 = (i1 < p.img_h) && (j < p.img_w);
-    const int2 range = tile_bins[tile];
-    // quadrant bit inside the 8-rectangle cull mask after folding rows: (m | m >> 2) has the
-    // quadrant's two 8x4 rectangles ORed at bit (warp & 1) + 4 * (warp >> 1)
-    const int qbit = (warp & 1) + 4 * (warp >> 1);
-
-    float Tf0 = 1.f, Tf1 = 1.f, voa0 = 0.f, voa1 = 0.f;
-    float3 vo0 = make_float3(0.f, 0.f, 0.f), vo1 = vo0;
-    int bf0 = -1, bf1 = -1;
-    if (in0) {
-        const size_t pix = (size_t)i0 * p.img_w + j;
-        Tf0 = final_Ts[pix];
-        bf0 = final_idx[pix];
-        vo0 = make_float3(v_out_img[pix * 3], v_out_img[pix * 3 + 1], v_out_img[pix * 3 + 2]);
-        voa0 = v_out_alpha_img ? v_out_alpha_img[pix] : 0.f;
-    }
-    if (in1) {
-        const size_t pix = (size_t)i1 * p.img_w + j;
-        Tf1 = final_Ts[pix];
-        bf1 = final_idx[pix];
-        vo1 = make_float3(v_out_img[pix * 3], v_out_img[pix * 3 + 1], v_out_img[pix * 3 + 2]);
-        voa1 = v_out_alpha_img ? v_out_alpha_img[pix] : 0.f;
-    }
-    const float3 bg = make_float3(__ldg(background), __ldg(background + 1), __ldg(background + 2));
-    const float tfc0 = Tf0 * (voa0 - (vo0.x * bg.x + vo0.y * bg.y + vo0.z * bg.z));
-    const float tfc1 = Tf1 * (voa1 - (vo1.x * bg.x + vo1.y * bg.y + vo1.z * bg.z));
-    float T0 = Tf0, T1 = Tf1;
-    float3 buf0 = make_float3(0.f, 0.f, 0.f), buf1 = buf0;
-
-    int wmax = max(bf0, bf1);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
-    if (lane == 0) s_max[warp] = wmax;
-    __syncthreads();
-    int tmax = s_max[0];
-#pragma unroll
-    for (int w = 1; w < RB2 / 32; ++w) tmax = max(tmax, s_max[w]);
-    const int top = min(range.y - 1, tmax);
-    if (top < range.x) return;  // nothing in this tile was composited (uniform across the CTA)
-    const int num_batches = (top - range.x + BATCH) / BATCH;
-    const float tile_x0 = (float)(tile_x * 16), tile_y0 = (float)(tile_y * 16);
-
-    // lane L (even, L/2 < NV) owns output row L/2 of the reduced gradient
-    const int slot = lane >> 1;
-    float *out_base;
-    int out_stride;
-    if (slot < 3) { out_base = v_colors + slot; out_stride = 3; }
-    else if (slot < 6) { out_base = v_conic + (slot - 3); out_stride = 3; }
-    else if (slot < 8) { out_base = v_xy + (slot - 6); out_stride = 2; }
-    else if (slot < 9) { out_base = v_opacity; out_stride = 1; }
-    else { out_base = v_xy_abs + (slot - 9); out_stride = 2; }
-    const bool writer = ((lane & 1) == 0) && slot < NV;
-
-    // Software pipeline (as in raster_fwd.cu): records of batch b+1 by cp.async into the other
-    // buffer and sorted ids of batch b+2 into registers while batch b is replayed.
-    auto load_id = [&](int bb, int h) -> unsigned {
-        const int idx = top - BATCH * bb - (tid + h * RB2);
-        return (bb < num_batches && idx >= range.x) ? ids_sorted[idx] : 0u;
-    };
-    auto issue = [&](int bb, int h, unsigned g) {
-        const int t = tid + h * RB2;
-        if (top - BATCH * bb - t >= range.x) {
-            const SplatRecord *r = records + g;
-            cp_async16(&sA2[bb & 1][t], &r->q0);
-            cp_async16(&sB2[bb & 1][t], &r->q1);
-            cp_async4(&sC2[bb & 1][t], &r->q2);
-            sId2[bb & 1][t] = g;
-        }
-    };
-    issue(0, 0, load_id(0, 0));
-    issue(0, 1, load_id(0, 1));
-    unsigned gn0 = load_id(1, 0), gn1 = load_id(1, 1);
-
-    for (int b = 0; b < num_batches; ++b) {
-        cp_async_wait_all();
-        __syncthreads();  // batch b landed; every warp is done with batch b-1
-        const int batch_end = top - BATCH * b;  // slot t holds sorted index batch_end - t
-        const int buf = b & 1;
-        const float4 *sA = sA2[buf];
-        const float4 *sB = sB2[buf];
-        const float *sC = sC2[buf];
-        const unsigned *sId = sId2[buf];
-        if (b + 1 < num_batches) { issue(b + 1, 0, gn0); issue(b + 1, 1, gn1); }
-        gn0 = load_id(b + 2, 0);
-        gn1 = load_id(b + 2, 1);
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int t = tid + h * RB2;
-            unsigned mask = 0;
-            if (batch_end - t >= range.x) {
-                const float4 q0 = sA[t];
-                const float2 q1 = *reinterpret_cast<const float2 *>(&sB[t]);
-                mask = CULL ? cull_mask16(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, tile_x0, tile_y0) : 0xFFu;
-            }
-            sMask[t] = (unsigned char)(mask | (mask >> 2));
-        }
-        __syncthreads();
-
-#pragma unroll 1
-        for (int k = 0; k < BATCH / 32; ++k) {
-            // entries newer than the warp's largest final index cannot be valid for any lane
-            if (batch_end - (k * 32 + 31) > wmax) continue;
-            const unsigned m = sMask[k * 32 + lane];
-            unsigned bits = __ballot_sync(0xffffffffu, (m >> qbit) & 1u);
-            while (bits) {
-                const int t = k * 32 + __ffs(bits) - 1;
-                bits &= bits - 1;
-                const float4 a = sA[t];
-                const float4 bq = sB[t];
-                const float dx = fsub(a.x, px);
-                const float dy0 = fsub(a.y, py0), dy1 = fsub(a.y, py1);
-                const float sg0 = conic_sigma(a.w, bq.x, bq.y, dx, dy0);
-                const float sg1 = conic_sigma(a.w, bq.x, bq.y, dx, dy1);
-                const float vis0 = ex2_approx(fmul(sg0, kNegLog2e));
-                const float vis1 = ex2_approx(fmul(sg1, kNegLog2e));
-                const float al0 = fminf(fmul(a.z, vis0), 0.99f);
-                const float al1 = fminf(fmul(a.z, vis1), 0.99f);
-                const int sidx = batch_end - t;
-                const bool ok0 = in0 && (sidx <= bf0) && !(sg0 < 0.f) && !(al0 < kAlphaMin);
-                const bool ok1 = in1 && (sidx <= bf1) && !(sg1 < 0.f) && !(al1 < kAlphaMin);
-                if (!__any_sync(0xffffffffu, ok0 || ok1)) continue;
-                float v[NV];
-                const float cb = sC[t];
-                pair_grad2<ABS, false>(ok0, al0, vis0, a.z, dx, dy0, a.w, bq.x, bq.y, bq.z, bq.w, cb,
-                                       vo0, tfc0, T0, buf0, v);
-                pair_grad2<ABS, true>(ok1, al1, vis1, a.z, dx, dy1, a.w, bq.x, bq.y, bq.z, bq.w, cb,
-                                      vo1, tfc1, T1, buf1, v);
-                // transpose through shared memory: row r = value r of the 32 lanes
-                __syncwarp();
-#pragma unroll
-                for (int r = 0; r < NV; ++r) red[r * RED_STRIDE + lane] = v[r];
-                __syncwarp();
-                float total = 0.f;
-                if (lane < 2 * NV) {
-                    const float4 *row = reinterpret_cast<const float4 *>(red + (lane >> 1) * RED_STRIDE + (lane & 1) * 16);
-                    const float4 p0 = row[0], p1 = row[1], p2 = row[2], p3 = row[3];
-                    total = ((p0.x + p0.y) + (p0.z + p0.w)) + ((p1.x + p1.y) + (p1.z + p1.w)) +
-                            (((p2.x + p2.y) + (p2.z + p2.w)) + ((p3.x + p3.y) + (p3.z + p3.w)));
-                }
-                total += __shfl_xor_sync(0xffffffffu, total, 1);
-                if (writer) atomicAdd(out_base + sId[t] * (unsigned)out_stride, total);
-            }
-        }
-    }
-}
 
 // ---- two pixels per thread, packed FP32x2 math -------------------------------------------------
 // sm_100 adds FFMA2 / FMUL2 / FADD2: one issue slot, two FP32 lanes of a 64-bit register pair
@@ -1031,8 +681,6 @@ __global__ void raster_bwd_generic_kernel(
 }  // namespace
 
 extern bool g_disable_cull;
-bool g_bwd_one_pixel = false;  // option "bwd2px" = 0: the one-pixel-per-thread kernel
-bool g_bwd_scalar = false;     // option "bwdpk" = 0: the two-pixel kernel with scalar FP32 math
 bool g_bwd_no_hits = false;    // option "bwdhits" = 0: the batch kernels even when hit words exist
 bool g_bwd_no_moments = false;  // option "bwdmom" = 0: the fused backward emits finished gradients, not moments
 bool g_bwd_all_entries = false;  // option "bwdhits" = 2 (test hook): the hit-driven kernel replays EVERY entry
@@ -1043,14 +691,9 @@ static void launch_x2(cudaStream_t stream, unsigned tiles, const RasterParams &p
                       const float *background, const float *final_Ts, const int *final_idx,
                       const float *v_out, const float *v_out_alpha, float *v_xy, float *v_xy_abs,
                       float *v_conic, float *v_colors, float *v_opacity) {
-    if (g_bwd_scalar)
-        raster_bwd16x2_kernel<CULL, ABS><<<tiles, RB2, 0, stream>>>(
-            p, ids_sorted, tile_bins, records, background, final_Ts, final_idx, v_out, v_out_alpha,
-            v_xy, v_xy_abs, v_conic, v_colors, v_opacity);
-    else
-        raster_bwd16x2p_kernel<CULL, ABS><<<tiles, RB2, 0, stream>>>(
-            p, ids_sorted, tile_bins, records, background, final_Ts, final_idx, v_out, v_out_alpha,
-            v_xy, v_xy_abs, v_conic, v_colors, v_opacity);
+    raster_bwd16x2p_kernel<CULL, ABS><<<tiles, RB2, 0, stream>>>(
+        p, ids_sorted, tile_bins, records, background, final_Ts, final_idx, v_out, v_out_alpha,
+        v_xy, v_xy_abs, v_conic, v_colors, v_opacity);
 }
 
 // v_xy_abs == nullptr: not computed (fused render; block_width 16 only)
@@ -1064,7 +707,7 @@ int launch_raster_bwd(cudaStream_t stream, const RasterParams &p, const unsigned
     if (moments_out) *moments_out = false;
     if (tiles == 0) return 0;
     if (g_bwd_no_moments) moments_out = nullptr;
-    if (p.block_width == 16 && hit_words && !g_bwd_no_hits && !g_bwd_one_pixel && !g_bwd_scalar) {
+    if (p.block_width == 16 && hit_words && !g_bwd_no_hits) {
         // one independent warp per quadrant, driven by the forward's hit words
         if (v_xy_abs)
             raster_bwd_hits_kernel<true, false><<<tiles * 4, 32, 0, stream>>>(
@@ -1079,7 +722,7 @@ int launch_raster_bwd(cudaStream_t stream, const RasterParams &p, const unsigned
                 p, ids_sorted, tile_bins, records, hit_words, g_bwd_all_entries, background, final_Ts, final_idx, v_out,
                 v_out_alpha, v_xy, v_xy_abs, v_conic, v_colors, v_opacity);
         if (moments_out) *moments_out = !v_xy_abs;
-    } else if (p.block_width == 16 && !(g_bwd_one_pixel && v_xy_abs)) {
+    } else if (p.block_width == 16) {
         if (v_xy_abs) {
             if (g_disable_cull)
                 launch_x2<false, true>(stream, tiles, p, ids_sorted, tile_bins, records, background, final_Ts, final_idx, v_out, v_out_alpha, v_xy, v_xy_abs, v_conic, v_colors, v_opacity);
@@ -1091,15 +734,6 @@ int launch_raster_bwd(cudaStream_t stream, const RasterParams &p, const unsigned
             else
                 launch_x2<true, false>(stream, tiles, p, ids_sorted, tile_bins, records, background, final_Ts, final_idx, v_out, v_out_alpha, v_xy, v_xy_abs, v_conic, v_colors, v_opacity);
         }
-    } else if (p.block_width == 16) {
-        if (g_disable_cull)
-            raster_bwd16_kernel<false><<<tiles, RB, 0, stream>>>(
-                p, ids_sorted, tile_bins, records, background, final_Ts, final_idx, v_out,
-                v_out_alpha, v_xy, v_xy_abs, v_conic, v_colors, v_opacity);
-        else
-            raster_bwd16_kernel<true><<<tiles, RB, 0, stream>>>(
-                p, ids_sorted, tile_bins, records, background, final_Ts, final_idx, v_out,
-                v_out_alpha, v_xy, v_xy_abs, v_conic, v_colors, v_opacity);
     } else {
         if (!v_xy_abs) {
             set_error("raster_bwd: block_width %u needs a v_xy_abs buffer", p.block_width);

@@ -8,20 +8,23 @@
 // (common.cuh), so final_idx is bit-exact and the image is bit-identical.
 //
 // Design (not a port):
-//   * one CTA = one tile; its 8 warps own 8x4-pixel rectangles (not 16x2 rows) so a warp's
-//     footprint is compact;
-//   * batches of 256 Gaussians are staged once per CTA from the packed 48-byte SplatRecord table
-//     with 16-byte loads; the staging thread also computes a conservative 8-bit mask saying which
-//     warp rectangles the Gaussian can reach (raster_cull.cuh);
-//   * each warp turns the masks into a 256-bit register bitmap with 8 ballots and only visits
-//     its own candidates (find-first-set walk): pairs that cannot pass the alpha test are never
-//     evaluated, which is where most of the reference's issue slots go;
-//   * per candidate the warp does 1 LDS.128 + 1 LDS.64 (broadcast) instead of 6 scalar LDS, and
-//     colours come from shared memory instead of three dependent global loads;
+//   * one CTA = one tile = 4 warps; each warp owns an 8x8 quadrant and each lane two pixels,
+//     (x, y) and (x, y + 4), held as packed FP32x2 register pairs (FMUL2 / FFMA2 / FADD2: one issue
+//     slot for both pixels, each lane rounding like the scalar instruction);
+//   * batches of 128 Gaussians are staged once per CTA from the packed 48-byte SplatRecord table;
+//     the staging thread also computes a conservative mask saying which quadrants the Gaussian can
+//     reach (raster_cull.cuh);
+//   * each warp turns the masks into candidate bitmaps with ballots and only visits its own
+//     candidates (find-first-set walk): pairs that cannot pass the alpha test are never evaluated,
+//     which is where most of the reference's issue slots go;
+//   * per candidate the warp does 2 broadcast LDS.128, and colours come from shared memory instead
+//     of three dependent global loads;
 //   * warps retire independently (ballot on `done`), the CTA retires on __syncthreads_count;
 //   * the staging is software-pipelined: the records of batch b+1 arrive by cp.async (LDGSTS,
 //     double-buffered shared memory) and the sorted ids of batch b+2 by a register prefetch while
-//     batch b is composited.
+//     batch b is composited;
+//   * every warp records, per group of 32 list entries, which entries some pixel of its quadrant
+//     accepted (raster_hits.cuh): the backward replays exactly those.
 #include "common.cuh"
 #include "kernels.cuh"
 #include "raster_cull.cuh"
@@ -30,116 +33,7 @@
 namespace jsb {
 namespace {
 
-constexpr int RB = 256;  // batch size == threads per CTA
-
-template <bool CULL>
-__global__ void __launch_bounds__(RB, 5)
-raster_fwd16_kernel(const RasterParams p, const unsigned *__restrict__ ids_sorted,
-                    const int2 *__restrict__ tile_bins, const SplatRecord *__restrict__ records,
-                    const float *__restrict__ background, float *__restrict__ final_Ts,
-                    int *__restrict__ final_idx, float *__restrict__ out_img) {
-    __shared__ float4 sA[2][RB];     // x, y, opac, conic.x      (double-buffered batches)
-    __shared__ float4 sB[2][RB];     // conic.y, conic.z, r, g
-    __shared__ float sC[2][RB];      // b
-    __shared__ unsigned char sMask[RB];
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const unsigned tile = p.band_y0 * p.tiles_x + blockIdx.x;
-    const unsigned tile_y = tile / p.tiles_x, tile_x = tile - tile_y * p.tiles_x;
-    const unsigned j = tile_x * 16 + (warp & 1) * kRectW + (lane & 7);   // pixel column
-    const unsigned i = tile_y * 16 + (warp >> 1) * kRectH + (lane >> 3); // pixel row
-    const float px = (float)j + 0.5f, py = (float)i + 0.5f;
-    const bool inside = (i < p.img_h) && (j < p.img_w);
-    bool done = !inside;
-
-    const int2 range = tile_bins[tile];
-    const int num_batches = (range.y - range.x + RB - 1) / RB;
-    const float tile_x0 = (float)(tile_x * 16), tile_y0 = (float)(tile_y * 16);
-
-    float T = 1.f;
-    int cur_idx = 0;
-    float acc_r = 0.f, acc_g = 0.f, acc_b = 0.f;
-
-    // Software pipeline: while batch b is composited, the records of batch b+1 travel global ->
-    // shared (cp.async) and the sorted ids of batch b+2 travel to a register, so the two dependent
-    // gathers of the staging (id, then record) are off the critical path.
-    auto issue = [&](int b, unsigned g) {  // this thread's record of batch b -> buffer b & 1
-        if (range.x + RB * b + tid < range.y) {
-            const SplatRecord *r = records + g;
-            cp_async16(&sA[b & 1][tid], &r->q0);
-            cp_async16(&sB[b & 1][tid], &r->q1);
-            cp_async4(&sC[b & 1][tid], &r->q2);
-        }
-    };
-    auto load_id = [&](int b) -> unsigned {
-        const int idx = range.x + RB * b + tid;
-        return (b < num_batches && idx < range.y) ? ids_sorted[idx] : 0u;
-    };
-    if (num_batches > 0) issue(0, load_id(0));
-    unsigned g_next = load_id(1);
-
-    for (int b = 0; b < num_batches; ++b) {
-        cp_async_wait_all();
-        // batch b has landed; also the barrier that protects the previous batch's shared data
-        if (__syncthreads_count(done) >= RB) break;
-        const int batch_start = range.x + RB * b;
-        const int buf = b & 1;
-        if (b + 1 < num_batches) issue(b + 1, g_next);
-        g_next = load_id(b + 2);
-        unsigned mask = 0;
-        if (batch_start + tid < range.y) {
-            const float4 q0 = sA[buf][tid];
-            const float2 q1 = *reinterpret_cast<const float2 *>(&sB[buf][tid]);
-            mask = CULL ? cull_mask16(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, tile_x0, tile_y0) : 0xFFu;
-        }
-        sMask[tid] = (unsigned char)mask;
-        __syncthreads();
-
-        bool warp_done = __all_sync(0xffffffffu, done);
-#pragma unroll
-        for (int k = 0; k < RB / 32; ++k) {
-            if (warp_done) continue;
-            const unsigned m = sMask[k * 32 + lane];
-            unsigned bits = __ballot_sync(0xffffffffu, (m >> warp) & 1u);
-            while (bits) {
-                const int t = k * 32 + __ffs(bits) - 1;
-                bits &= bits - 1;
-                const float4 a = sA[buf][t];
-                const float2 cyz = *reinterpret_cast<const float2 *>(&sB[buf][t]);
-                const float dx = fsub(a.x, px), dy = fsub(a.y, py);
-                const float sigma = conic_sigma(a.w, cyz.x, cyz.y, dx, dy);
-                const float vis_e = ex2_approx(fmul(sigma, kNegLog2e));
-                const float alpha = fminf(fmul(a.z, vis_e), 0.999f);
-                if (!done && !(sigma < 0.f) && !(alpha < kAlphaMin)) {
-                    const float next_T = fmul(T, fsub(1.f, alpha));
-                    if (next_T <= kTmin) {
-                        done = true;  // this Gaussian is not composited
-                    } else {
-                        const float vis = fmul(T, alpha);
-                        const float2 rg = *reinterpret_cast<const float2 *>(&sB[buf][t].z);
-                        acc_r = ffma(vis, rg.x, acc_r);
-                        acc_g = ffma(vis, rg.y, acc_g);
-                        acc_b = ffma(vis, sC[buf][t], acc_b);
-                        T = next_T;
-                        cur_idx = batch_start + t;
-                    }
-                }
-            }
-            warp_done = __all_sync(0xffffffffu, done);
-        }
-    }
-    cp_async_wait_all();
-
-    if (inside) {
-        const size_t pix = (size_t)i * p.img_w + j;
-        final_Ts[pix] = T;
-        final_idx[pix] = cur_idx;
-        const float bg0 = __ldg(background), bg1 = __ldg(background + 1), bg2 = __ldg(background + 2);
-        out_img[pix * 3 + 0] = ffma(T, bg0, acc_r);
-        out_img[pix * 3 + 1] = ffma(T, bg1, acc_g);
-        out_img[pix * 3 + 2] = ffma(T, bg2, acc_b);
-    }
-}
+constexpr int RB = 256;  // staging slots of the generic (any block_width) kernel
 
 // ---- two pixels per thread -------------------------------------------------------------------
 // A CTA is 4 warps and each warp owns an 8x8 quadrant of the tile: lane l composites pixels (x, y)
@@ -156,7 +50,7 @@ constexpr int RF2 = 128;
 #define JSB_FWD_EPT 1    // staged entries per thread and batch (batch = 128 * EPT entries)
 #endif
 
-template <bool CULL, bool PACKED>
+template <bool CULL>
 __global__ void __launch_bounds__(RF2, JSB_FWD_CTAS)
 raster_fwd16x2_kernel(const RasterParams p, const unsigned *__restrict__ ids_sorted,
                       const int2 *__restrict__ tile_bins, const SplatRecord *__restrict__ records,
@@ -250,32 +144,23 @@ raster_fwd16x2_kernel(const RasterParams p, const unsigned *__restrict__ ids_sor
                 const float4 a = sA[buf][t];
                 const float4 bq = sB[buf][t];
                 const float dx = fsub(a.x, px);
-                float sg0, sg1, al0, al1;
-                if (PACKED) {
-                    // conic_sigma (common.cuh) for both pixels at once with FMUL2 / FFMA2 / FADD2
-                    // (one issue slot, two FP32 lanes, each rounding like the scalar form), the
-                    // per-Gaussian operands as scalar broadcasts: same operation order per pixel,
-                    // so the outputs stay bit-identical to the scalar path
-                    const float2 dy2 = __fadd2_rn(make_float2(a.y, a.y), make_float2(-py0, -py1));
-                    const float ca = fmul(a.w, dx);                                   // cx dx
-                    const float ce = fmul(bq.x, dx);                                  // cy dx
-                    const float2 b2 = __fmul2_rn(make_float2(bq.y, bq.y), dy2);       // cz dy
-                    const float2 c2 = __fmul2_rn(dy2, b2);
-                    float2 s2 = __ffma2_rn(make_float2(dx, dx), make_float2(ca, ca), c2);
-                    s2 = __fmul2_rn(s2, make_float2(0.5f, 0.5f));
-                    const float2 sg2 = __ffma2_rn(make_float2(ce, ce), dy2, s2);
-                    const float2 x2 = __fmul2_rn(sg2, make_float2(kNegLog2e, kNegLog2e));
-                    const float2 ar2 = __fmul2_rn(make_float2(a.z, a.z),
-                                                  make_float2(ex2_approx(x2.x), ex2_approx(x2.y)));
-                    sg0 = sg2.x; sg1 = sg2.y;
-                    al0 = fminf(ar2.x, 0.999f); al1 = fminf(ar2.y, 0.999f);
-                } else {
-                    const float dy0 = fsub(a.y, py0), dy1 = fsub(a.y, py1);
-                    sg0 = conic_sigma(a.w, bq.x, bq.y, dx, dy0);
-                    sg1 = conic_sigma(a.w, bq.x, bq.y, dx, dy1);
-                    al0 = fminf(fmul(a.z, ex2_approx(fmul(sg0, kNegLog2e))), 0.999f);
-                    al1 = fminf(fmul(a.z, ex2_approx(fmul(sg1, kNegLog2e))), 0.999f);
-                }
+                // conic_sigma (common.cuh) for both pixels at once with FMUL2 / FFMA2 / FADD2 (one
+                // issue slot, two FP32 lanes, each rounding like the scalar form), the per-Gaussian
+                // operands as scalar broadcasts: same operation order per pixel as the reference's
+                // compiled code, so the outputs stay bit-identical
+                const float2 dy2 = __fadd2_rn(make_float2(a.y, a.y), make_float2(-py0, -py1));
+                const float ca = fmul(a.w, dx);                                   // cx dx
+                const float ce = fmul(bq.x, dx);                                  // cy dx
+                const float2 b2 = __fmul2_rn(make_float2(bq.y, bq.y), dy2);       // cz dy
+                const float2 c2 = __fmul2_rn(dy2, b2);
+                float2 s2 = __ffma2_rn(make_float2(dx, dx), make_float2(ca, ca), c2);
+                s2 = __fmul2_rn(s2, make_float2(0.5f, 0.5f));
+                const float2 sg2 = __ffma2_rn(make_float2(ce, ce), dy2, s2);
+                const float2 x2 = __fmul2_rn(sg2, make_float2(kNegLog2e, kNegLog2e));
+                const float2 ar2 = __fmul2_rn(make_float2(a.z, a.z),
+                                              make_float2(ex2_approx(x2.x), ex2_approx(x2.y)));
+                const float sg0 = sg2.x, sg1 = sg2.y;
+                const float al0 = fminf(ar2.x, 0.999f), al1 = fminf(ar2.y, 0.999f);
                 const bool ok0 = !done0 && !(sg0 < 0.f) && !(al0 < kAlphaMin);
                 const bool ok1 = !done1 && !(sg1 < 0.f) && !(al1 < kAlphaMin);
                 if (ok0 || ok1) {
@@ -422,8 +307,6 @@ __global__ void fill_background_kernel(const float *__restrict__ background, siz
 }  // namespace
 
 bool g_disable_cull = false;  // test hook (capi: jsb200_set_option)
-bool g_fwd_scalar = false;  // option "fwdpk" = 0: scalar FP32 math in the two-pixel kernel
-bool g_fwd_one_pixel = false;  // option "fwd2px" = 0: the one-pixel-per-thread kernel
 
 int launch_raster_fwd(cudaStream_t stream, const RasterParams &p, const unsigned *ids_sorted,
                       const int2 *tile_bins, const SplatRecord *records, const float *background,
@@ -432,22 +315,14 @@ int launch_raster_fwd(cudaStream_t stream, const RasterParams &p, const unsigned
     const unsigned tiles = p.tiles_x * (p.band_y1 - p.band_y0);
     if (wrote_hits) *wrote_hits = false;
     if (tiles == 0) return 0;
-    if (p.block_width == 16 && !g_fwd_one_pixel) {
+    if (p.block_width == 16) {
         if (wrote_hits) *wrote_hits = hit_words != nullptr;
-#define JSB_FWD2(C, P) raster_fwd16x2_kernel<C, P><<<tiles, RF2, 0, stream>>>( \
-        p, ids_sorted, tile_bins, records, background, final_Ts, final_idx, out_img, hit_words)
-        if (g_disable_cull) { if (g_fwd_scalar) JSB_FWD2(false, false); else JSB_FWD2(false, true); }
-        else { if (g_fwd_scalar) JSB_FWD2(true, false); else JSB_FWD2(true, true); }
-#undef JSB_FWD2
-    } else if (p.block_width == 16) {
         if (g_disable_cull)
-            raster_fwd16_kernel<false><<<tiles, RB, 0, stream>>>(p, ids_sorted, tile_bins, records,
-                                                                 background, final_Ts, final_idx,
-                                                                 out_img);
+            raster_fwd16x2_kernel<false><<<tiles, RF2, 0, stream>>>(
+                p, ids_sorted, tile_bins, records, background, final_Ts, final_idx, out_img, hit_words);
         else
-            raster_fwd16_kernel<true><<<tiles, RB, 0, stream>>>(p, ids_sorted, tile_bins, records,
-                                                                background, final_Ts, final_idx,
-                                                                out_img);
+            raster_fwd16x2_kernel<true><<<tiles, RF2, 0, stream>>>(
+                p, ids_sorted, tile_bins, records, background, final_Ts, final_idx, out_img, hit_words);
     } else {
         dim3 grid(p.tiles_x, p.band_y1 - p.band_y0), block(p.block_width, p.block_width);
         raster_fwd_generic_kernel<<<grid, block, 0, stream>>>(p, ids_sorted, tile_bins, records,

@@ -92,7 +92,6 @@ class SwitchReducedBuffer:
         self.numel = int(numel)
         self.mode = "single"
         self._epoch = 0
-        self._range_epochs = {}
         self._hdl = None
         distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
         if distributed:
@@ -106,7 +105,11 @@ class SwitchReducedBuffer:
                 g = group if group is not None else dist.group.WORLD
                 raw = symm_mem.empty(total + self.FLAG_BYTES // 4, dtype=torch.float32, device=device)
                 hdl = symm_mem.rendezvous(raw, g.group_name)
-                if hdl.multicast_ptr and hdl.world_size <= 16:
+                # (two ranks: NCCL's direct exchange is faster than a trip through the switch,
+                # 0.129 vs 0.164 ms for 56 MB, profiles/r02m_allreduce_2gpu_switch_vs_nccl.json)
+                import os
+                min_world = 2 if os.environ.get("JSB_SWITCH_ALLREDUCE") == "1" else 3
+                if hdl.multicast_ptr and min_world <= hdl.world_size <= 16:
                     raw.zero_()
                     hdl.barrier(channel=0)
                     self._raw, self._hdl = raw, hdl
@@ -140,44 +143,6 @@ class SwitchReducedBuffer:
             ctypes.c_void_p(torch.cuda.current_stream().cuda_stream),
             ctypes.c_void_p(int(hdl.multicast_ptr) + delta), peers, self._padded,
             self._flags_off, hdl.rank, hdl.world_size, self._epoch)
-        if rc != 0:
-            _lib.check_error("multimem_allreduce")
-
-    # flag blocks inside the FLAG_BYTES tail: block 0 belongs to all_reduce(), blocks 1.. to ranges
-    _FLAG_BLOCK = 256
-
-    def all_reduce_range(self, offset: int, numel: int, channel: int = 0):
-        """in-place sum over the ranks of ``tensor[offset:offset + numel]`` only, enqueued on the
-        current stream.  Reductions that may be in flight at the same time (different streams)
-        must use different ``channel`` s (each has its own cross-GPU flag block and epoch), e.g.
-        the appearance gradients on a side stream under ``project_bwd`` (channel 1) and the
-        geometry gradients on the main stream after it (channel 0).  ``offset`` and ``numel`` must
-        be multiples of 4 floats (16-byte vectors)."""
-        offset, numel, channel = int(offset), int(numel), int(channel)
-        if offset < 0 or numel < 0 or offset + numel > self.numel:
-            raise ValueError(f"all_reduce_range: [{offset}, {offset + numel}) outside [0, {self.numel})")
-        if self.mode == "single" or numel == 0:
-            return
-        if self._hdl is None:
-            dist.all_reduce(self.tensor[offset:offset + numel], group=self._group)
-            return
-        if offset % 4 or numel % 4:
-            raise ValueError("all_reduce_range: offset and numel must be multiples of 4 floats")
-        if not 0 <= channel < self.FLAG_BYTES // self._FLAG_BLOCK - 1:
-            raise ValueError("all_reduce_range: no such channel")
-        import ctypes
-
-        from . import _lib
-        hdl, raw = self._hdl, self._raw
-        delta = raw.data_ptr() - int(hdl.buffer_ptrs[hdl.rank]) + offset * 4
-        peers = (ctypes.c_void_p * hdl.world_size)(*[int(p) + delta for p in hdl.buffer_ptrs])
-        epoch = self._range_epochs.get(channel, 0) + 1
-        self._range_epochs[channel] = epoch
-        flags_off = self._flags_off - offset * 4 + (channel + 1) * self._FLAG_BLOCK
-        rc = _lib.lib().jsb200_multimem_allreduce_f32(
-            ctypes.c_void_p(torch.cuda.current_stream().cuda_stream),
-            ctypes.c_void_p(int(hdl.multicast_ptr) + delta), peers, numel, flags_off, hdl.rank,
-            hdl.world_size, epoch)
         if rc != 0:
             _lib.check_error("multimem_allreduce")
 

@@ -202,8 +202,3 @@ def test_adam_rejects_host_tensors_and_mismatched_gradient_buffers():
         Adam([torch.zeros(4)])
     with pytest.raises((TypeError, ValueError)):
         Adam([], grads=[torch.zeros(4)])
-
-
-def test_raster_bwd_event_can_be_cleared_without_a_gpu():
-    """jsb200_set_raster_bwd_event(NULL) only stores a pointer: callable on a CPU-only box"""
-    _lib.set_raster_bwd_event(None)

@@ -302,93 +302,6 @@ def test_row_column_lists_equal_the_counting_distribution(case):
             assert np.array_equal(a, b)
 
 
-@pytest.mark.parametrize("scene_fn", [_adversarial_scene, lambda: synthetic.make_config("C2", num_points=30000),
-                                      lambda: synthetic.benchmark_scene(9000, (200, 120), scale_max=0.2, seed=21)])
-def test_two_pixels_per_thread_backward_equals_one_pixel_per_thread(scene_fn):
-    """raster_bwd16x2_kernel (two pixels per thread, default) vs raster_bwd16_kernel"""
-    s = scene_fn()
-    inp = G.scene_inputs(s)
-    kw, rkw = G.scene_kw(s)
-    H, W = s.img_shape
-    target = np.random.RandomState(2).rand(H, W, 3).astype(np.float32)
-    v_alpha = np.random.RandomState(3).rand(H, W, 1).astype(np.float32) * 1e-3
-    try:
-        _lib.set_option("bwd2px", 1)
-        a = _full_gpu(inp, kw, rkw, target, v_alpha)
-        _lib.set_option("bwd2px", 0)
-        b = _full_gpu(inp, kw, rkw, target, v_alpha)
-    finally:
-        _lib.set_option("bwd2px", 1)
-    for k in ("v_colors", "v_opacity", "v_xy", "v_xy_abs", "v_conic"):
-        ok, err, scale = grad_close(a[k], b[k], rel=1e-4)
-        assert ok, (k, err, scale)
-
-
-@pytest.mark.parametrize("scene_fn", [_adversarial_scene, lambda: synthetic.make_config("C2", num_points=30000),
-                                      lambda: synthetic.benchmark_scene(9000, (200, 120), scale_max=0.2, seed=21)])
-def test_two_pixels_per_thread_forward_is_bit_identical(scene_fn):
-    """raster_fwd16x2_kernel (two pixels per thread, default) vs raster_fwd16_kernel"""
-    s = scene_fn()
-    inp = G.scene_inputs(s)
-    kw, rkw = G.scene_kw(s)
-    P = G.project_fwd(inp, kw)
-    try:
-        _lib.set_option("fwd2px", 1)
-        a = G.rasterize_fwd(inp, P, rkw)
-        _lib.set_option("fwd2px", 0)
-        b = G.rasterize_fwd(inp, P, rkw)
-    finally:
-        _lib.set_option("fwd2px", 1)
-    assert torch.equal(a["final_idx"], b["final_idx"])
-    assert torch.equal(a["final_Ts"].view(torch.int32), b["final_Ts"].view(torch.int32))
-    assert torch.equal(a["img"].view(torch.int32), b["img"].view(torch.int32))
-
-
-@pytest.mark.parametrize("scene_fn", [_adversarial_scene, lambda: synthetic.make_config("C2", num_points=30000),
-                                      lambda: synthetic.benchmark_scene(9000, (200, 120), scale_max=0.2, seed=21)])
-def test_packed_fp32x2_forward_is_bit_identical_to_the_scalar_kernel(scene_fn):
-    """raster_fwd16x2_kernel with FMUL2 / FFMA2 / FADD2 over the two pixels (default) vs the same
-    kernel with scalar FP32 math (option fwdpk = 0): every lane of a packed instruction rounds
-    like the scalar one and nothing is re-contracted, so not a bit may differ"""
-    s = scene_fn()
-    inp = G.scene_inputs(s)
-    kw, rkw = G.scene_kw(s)
-    P = G.project_fwd(inp, kw)
-    try:
-        _lib.set_option("fwdpk", 1)
-        a = G.rasterize_fwd(inp, P, rkw)
-        _lib.set_option("fwdpk", 0)
-        b = G.rasterize_fwd(inp, P, rkw)
-    finally:
-        _lib.set_option("fwdpk", 1)
-    assert torch.equal(a["final_idx"], b["final_idx"])
-    assert torch.equal(a["final_Ts"].view(torch.int32), b["final_Ts"].view(torch.int32))
-    assert torch.equal(a["img"].view(torch.int32), b["img"].view(torch.int32))
-
-
-@pytest.mark.parametrize("scene_fn", [_adversarial_scene, lambda: synthetic.make_config("C2", num_points=30000),
-                                      lambda: synthetic.benchmark_scene(9000, (200, 120), scale_max=0.2, seed=21)])
-def test_packed_fp32x2_backward_equals_the_scalar_kernel(scene_fn):
-    """raster_bwd16x2p_kernel (packed math, regrouped v_alpha, deferred reduction; default) vs
-    raster_bwd16x2_kernel (option bwdpk = 0): same accept decisions, gradients to tolerance"""
-    s = scene_fn()
-    inp = G.scene_inputs(s)
-    kw, rkw = G.scene_kw(s)
-    H, W = s.img_shape
-    target = np.random.RandomState(2).rand(H, W, 3).astype(np.float32)
-    v_alpha = np.random.RandomState(3).rand(H, W, 1).astype(np.float32) * 1e-3
-    try:
-        _lib.set_option("bwdpk", 1)
-        a = _full_gpu(inp, kw, rkw, target, v_alpha)
-        _lib.set_option("bwdpk", 0)
-        b = _full_gpu(inp, kw, rkw, target, v_alpha)
-    finally:
-        _lib.set_option("bwdpk", 1)
-    for k in ("v_colors", "v_opacity", "v_xy", "v_xy_abs", "v_conic"):
-        ok, err, scale = grad_close(a[k], b[k], rel=1e-4)
-        assert ok, (k, err, scale)
-
-
 @pytest.mark.parametrize("case", ["C1", "C2_30k", "one_depth", "wide_depth_range", "all_culled",
                                   "ragged", "band", "two_tiles_per_cta", "many_equal_depths"])
 def test_resident_depth_sort_builds_the_same_lists(case):

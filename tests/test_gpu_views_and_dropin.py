@@ -180,28 +180,3 @@ def test_gradient_sink_receives_the_gradients_in_place():
     grads(views2)
     ok, err, scale = grad_close(G.npy(flat2), G.npy(flat[:14 * n]), rel=1e-4)
     assert ok, (err, scale)
-
-
-def test_raster_bwd_event_marks_final_appearance_gradients():
-    """jsb200_set_raster_bwd_event: the fused render backward records the event between its two
-    kernels; a side stream that waits on it sees the final v_colors / v_opacity (they are not
-    touched by the projection backward that is still running on the main stream)"""
-    s = synthetic.make_config("C2", num_points=40000).to("cuda")
-    params = [p.clone().requires_grad_(True) for p in s.params()]
-    target = torch.rand((s.img_shape[0], s.img_shape[1], 3), device="cuda")
-    ev = torch.cuda.Event()
-    ev.record()
-    side = torch.cuda.Stream()
-    try:
-        _lib.set_raster_bwd_event(ev)
-        img = jsb.render(*params, **s.render_kwargs())
-        ((img - target) ** 2).mean().backward()
-        side.wait_event(ev)
-        with torch.cuda.stream(side):
-            early_c, early_o = params[3].grad.clone(), params[4].grad.clone()
-        side.synchronize()
-    finally:
-        _lib.set_raster_bwd_event(None)
-    torch.cuda.synchronize()
-    assert torch.equal(early_c, params[3].grad) and torch.equal(early_o, params[4].grad)
-    assert float(params[3].grad.abs().sum()) > 0

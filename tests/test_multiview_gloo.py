@@ -207,31 +207,9 @@ def test_multigpu_bench_tool_dry_run_shards_consistently():
     assert two["bands"][0][0] == 0 and two["bands"][-1][1] == 3 and len(two["bands"]) == 2
 
 
-def _range_worker(rank, world, port, out):
-    os.environ["MASTER_ADDR"] = "127.0.0.1"
-    os.environ["MASTER_PORT"] = str(port)
-    dist.init_process_group("gloo", rank=rank, world_size=world)
-    n = 12
-    buf = multiview.SwitchReducedBuffer(14 * n, "cpu", scratch_numel=5 * n)
-    buf.tensor.copy_(torch.arange(14 * n, dtype=torch.float32) * (rank + 1))
-    buf.scratch.fill_(7.0 + rank)
-    # the split the overlapped step uses: appearance tail on one channel, geometry head on another
-    buf.all_reduce_range(10 * n, 4 * n, channel=1)
-    buf.all_reduce_range(0, 10 * n, channel=0)
-    if rank == 0:
-        torch.save({"t": buf.tensor.clone(), "s": buf.scratch.clone(), "mode": buf.mode}, out)
-    dist.destroy_process_group()
-
-
-def test_two_rank_range_reductions_add_up_to_the_full_all_reduce(tmp_path):
-    """SwitchReducedBuffer.all_reduce_range over [10n, 14n) and [0, 10n) (the appearance /
-    geometry split of the overlapped data-parallel step) equals one all-reduce of the whole
-    buffer; the per-rank scratch tail is not touched"""
-    out = str(tmp_path / "range.pt")
-    mp.spawn(_range_worker, args=(2, _free_port(), out), nprocs=2, join=True)
-    got = torch.load(out)
-    assert got["mode"] == "gloo"
-    assert torch.equal(got["t"], torch.arange(14 * 12, dtype=torch.float32) * 3.0)
-    assert torch.equal(got["s"], torch.full((60,), 7.0))
-    with pytest.raises(ValueError):
-        multiview.SwitchReducedBuffer(16, "cpu").all_reduce_range(8, 12)
+def test_flat_adam_argument_checks():
+    from jaxsplat_b200.optim import Adam
+    with pytest.raises(TypeError):
+        Adam([torch.zeros(4)])
+    with pytest.raises((TypeError, ValueError)):
+        Adam([], grads=[torch.zeros(4)])

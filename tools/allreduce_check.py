@@ -15,6 +15,7 @@ torch.cuda.set_device(lr)
 dev = torch.device("cuda", lr)
 dist.init_process_group("nccl", device_id=dev)
 n = 14 * int(sys.argv[1]) if len(sys.argv) > 1 else 14 * 1000 * 1000
+os.environ["JSB_SWITCH_ALLREDUCE"] = "1"  # the kernel under test, also at two ranks (NCCL is the default there)
 buf = SwitchReducedBuffer(n, dev)
 out = {"world": world, "floats": n, "mode": buf.mode}
 g = torch.Generator(device=dev).manual_seed(100 + rank)

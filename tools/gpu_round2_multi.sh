@@ -11,7 +11,7 @@ mkdir -p $OUT
 RUN="python -m torch.distributed.run --nnodes=1 --nproc-per-node $G --master-addr 127.0.0.1"
 nvidia-smi --query-gpu=name,clocks.max.sm --format=csv,noheader | head -2 > $OUT/${TAG}_${G}gpu_info.txt
 timeout 600 $RUN --master-port 29501 bench.py --gpus $G --steps 200 --warmup 20 > $OUT/${TAG}_bench_C3_${G}gpu.json 2> $OUT/${TAG}_bench_C3_${G}gpu.err
-JSB_BENCH_OVERLAP=1 timeout 600 $RUN --master-port 29504 bench.py --gpus $G --steps 200 --warmup 20 > $OUT/${TAG}_bench_C3_overlap_${G}gpu.json 2> $OUT/${TAG}_bench_C3_overlap_${G}gpu.err
+
 timeout 300 $RUN --master-port 29505 tools/allreduce_check.py 1000000 > $OUT/${TAG}_allreduce_${G}gpu.json 2> $OUT/${TAG}_allreduce_${G}gpu.err
 timeout 600 $RUN --master-port 29502 bench.py --gpus $G --config C4 --steps 3 --warmup 3 > $OUT/${TAG}_bench_C4_${G}gpu.json 2> $OUT/${TAG}_bench_C4_${G}gpu.err
 timeout 600 $RUN --master-port 29503 bench.py --gpus $G --config C5 --steps 5 --warmup 3 > $OUT/${TAG}_bench_C5_${G}gpu.json 2> $OUT/${TAG}_bench_C5_${G}gpu.err
