@@ -129,7 +129,9 @@ def algorithmic_bytes(stage, N, I, P, T, rows=0, tiles_x=120):
     return {
         "project_fwd": N * 108,
         "bin_prep": N * (44 + 48 + 4 + 4 + 8),
-        "depth_sort": N * (4 + 4 * 2 * 8),
+        # resident sort, three passes over the live bits: keys read, (passes - 1) x (keys + ids
+        # written and read back), ids written
+        "depth_sort": N * (4 + 2 * 16 + 4),
         # level 1: order + box gathered twice (count, scatter), one 8-byte entry per covered row
         "emit": N * (4 + 8) * 2 + rows * 8,
         # level-2 counts: entries read once, count matrix written, scanned in place, tile bins
@@ -140,7 +142,9 @@ def algorithmic_bytes(stage, N, I, P, T, rows=0, tiles_x=120):
         # once, every gradient word once); the per-(tile, Gaussian) staging traffic is L2 hits
         "raster_fwd": P * 20 + N * 48 + I * 4,
         "raster_bwd": P * 24 + N * 48 + I * 4 + N * 36,
-        "project_bwd": N * 188,
+        # 188 B per Gaussian through the four-op API; the fused render neither writes v_cov2d /
+        # v_cov3d nor reads the compensation, and finishes the opacity moment in place: 152 B
+        "project_bwd": N * 152,
     }[stage]
 
 
@@ -502,6 +506,12 @@ def main():
             per_stage[k] = {"ms_per_launch": ms, "launches_per_step": v["calls"] / stage_steps,
                             "algorithmic_bytes": b, "gbs": b / (ms * 1e-3) / 1e9,
                             "hbm_frac": b / (ms * 1e-3) / 1e9 / peak}
+            if k == "project_fwd":
+                # SURVEY 8d's 108 B per Gaussian is the projection alone; the fused kernel also reads
+                # colours + opacities and writes the rasteriser records, depth keys, ids and tile
+                # boxes (what bin_prep would): 180 B per Gaussian actually moved
+                per_stage[k]["moved_bytes"] = N * 180
+                per_stage[k]["moved_hbm_frac"] = N * 180 / (ms * 1e-3) / 1e9 / peak
         dom = max(per_stage, key=lambda k: per_stage[k]["ms_per_launch"] * per_stage[k]["launches_per_step"])
         d = per_stage[dom]
         prof = {}
@@ -524,22 +534,27 @@ def main():
             if k in per_stage and U_f:
                 out["pairs"][k + "_pairs_per_s"] = U_f / (per_stage[k]["ms_per_launch"] * 1e-3)
         if dom in ("raster_fwd", "raster_bwd"):
-            # issue-slot roofline of the dominant rasteriser: warp instructions of one launch (ncu
-            # smsp__inst_executed.sum of the same kernel on the same workload, committed under
-            # profiles/) / its device time, against 4 schedulers x 148 SMs x the SM clock
+            # issue-slot roofline of the dominant rasteriser in SURVEY 8d's unit: useful pixel-
+            # Gaussian pairs per second against 148 SMs x 128 FP32 lanes x f_clk / 15 slots per pair
+            # (frac <= 1 by construction: U_f counts every pair of the walked list prefixes, the
+            # kernel evaluates a subset of them).  Beside it the raw issue-slot view: warp
+            # instructions of one launch (ncu smsp__inst_executed.sum of the same kernel on the same
+            # workload, committed under profiles/) / its device time, against 4 schedulers x 148 SMs.
             inst = (prof.get("_inst_executed") or {}).get(dom) if args.config == "C3" else None
             peak_issue = 148 * 4 * f_clk
-            ach = (inst / (d["ms_per_launch"] * 1e-3)) if inst else None
-            out["roofline"] = {"bound": "issue", "kernel": dom, "achieved": ach, "peak": peak_issue,
-                               "unit": "warp-inst/s", "frac": (ach / peak_issue) if ach else None,
-                               "traffic": traffic, "inst_per_launch": inst,
-                               "inst_source": prof.get("_inst_source"),
+            ach_i = (inst / (d["ms_per_launch"] * 1e-3)) if inst else None
+            ach_p = (U_f / (d["ms_per_launch"] * 1e-3)) if U_f else None
+            out["roofline"] = {"bound": "issue", "kernel": dom, "achieved": ach_p, "peak": pair_roof,
+                               "unit": "pairs/s", "frac": (ach_p / pair_roof) if ach_p else None,
+                               "traffic": traffic,
+                               "issue_slots": {"inst_per_launch": inst, "achieved": ach_i, "peak": peak_issue,
+                                               "unit": "warp-inst/s", "frac": (ach_i / peak_issue) if ach_i else None,
+                                               "inst_source": prof.get("_inst_source")},
                                "hbm_view": {"achieved_gbs": d["gbs"], "peak_gbs": peak,
                                             "frac": d["hbm_frac"], "peak_source": which_peak},
                                "note": "the rasterisers are SM-issue bound (no dense contraction, no "
-                                       "tensor cores; DRAM throughput 2-3 %): frac = issued warp "
-                                       "instructions / (time x 148 SMs x 4 schedulers x f_clk); the HBM "
-                                       "stages' fractions are in 'stages'"}
+                                       "tensor cores; DRAM throughput 2-4 %); the HBM stages' fractions "
+                                       "are in 'stages'"}
         else:
             out["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": d["gbs"], "peak": peak,
                                "unit": "GB/s", "frac": d["hbm_frac"], "traffic": traffic,
