@@ -259,10 +259,14 @@ def main():
     if args.impl == "ours":
         if os.environ.get("JSB_ROWCOL") == "0":
             _lib.set_option("rowcol", 0)
+        if os.environ.get("JSB_FWDWARP") == "0":  # per-CTA batch forward instead of the barrier-free one
+            _lib.set_option("fwdwarp", 0)
         if os.environ.get("JSB_BWDMOM") == "0":  # hit-driven backward emits finished gradients
             _lib.set_option("bwdmom", 0)
         if os.environ.get("JSB_BWDHITS") == "0":  # per-tile batch backward instead of the hit-driven one
             _lib.set_option("bwdhits", 0)
+        if os.environ.get("JSB_SORTMSD") == "0":  # global LSD passes only in the one-launch depth sort
+            _lib.set_option("sortmsd", 0)
         if os.environ.get("JSB_SORT1K") == "0":  # four onesweep passes instead of the resident sort
             _lib.set_option("sort1k", 0)
         if os.environ.get("JSB_FUSED") == "0":

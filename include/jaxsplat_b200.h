@@ -166,6 +166,8 @@ JSB200_API unsigned long long jsb200_error_count(void);
  *      "cache" (1 default; 0 forces rasterize_bwd to re-bin instead of reusing the forward's),
  *      "rowcol" (1 default; 0 builds the per-tile lists with the older counting distribution of
  *               tile_lists.cu instead of the two-level row/column distribution),
+ *      "fwdwarp" (1 default; 0 runs rasterize_fwd with the per-CTA batch kernel (two CTA barriers
+ *               per batch of 128 entries) instead of four independent quadrant warps per tile),
  *      "bwdmom" (1 default; 0 makes the fused render's hit-driven rasteriser backward accumulate
  *               finished v_xy / v_conic / v_opacity instead of raw moments that the projection
  *               backward finishes),
@@ -174,6 +176,8 @@ JSB200_API unsigned long long jsb200_error_count(void);
  *               frame of the same shape and device-side guards; measured neutral to slower),
  *      "bwdhits" (1 default; 0 runs rasterize_bwd with the per-tile batch kernel even when the
  *               forward recorded which list entries every 8x8 quadrant accepted),
+ *      "sortmsd" (1 default; 0 makes the one-launch depth sort do one global pass per 9 live key
+ *               bits instead of one global pass on the top 9 bits followed by CTA-local passes),
  *      "sort1k" (1 default; 0 orders the Gaussians by depth with four onesweep passes over all 32
  *               key bits instead of the single cooperative launch over the live bits),
  *      "timing" (0 default; 1 brackets every stage with CUDA events, see jsb200_get_stage_times),

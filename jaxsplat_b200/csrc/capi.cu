@@ -53,11 +53,13 @@ void set_error(const char *fmt, ...) {
 void note_launch(int n) { g_stats[6].fetch_add((unsigned long long)n); }
 
 extern bool g_disable_cull;
+extern bool g_fwd_batch;
 extern bool g_bwd_no_hits;
 extern bool g_bwd_all_entries;
 extern bool g_bwd_no_moments;
 static bool g_disable_cache = false;
 static bool g_disable_rowcol = false;
+static bool g_sort_lsd_only = false;  // option "sortmsd" 0: three global LSD passes, no MSD-first attempt
 static bool g_disable_resident_sort = false;  // option "sort1k" 0: the four-pass onesweep depth sort
 static unsigned g_view_slots = 8;  // binning workspaces a batched-camera call cycles through
 
@@ -306,7 +308,8 @@ static int bin_finish_enqueue(Ctx &c, const Descriptor &d, bool write) {
             rc = resident_depth_sort(s, (const unsigned *)c.dkeys_a.p, (unsigned *)c.dkeys_a.p,
                                      (unsigned *)c.ids_a.p, (unsigned *)c.dkeys_b.p,
                                      (unsigned *)c.ids_b.p, (unsigned *)c.order.p, n, mm,
-                                     c.sort_n_scratch.p, (int *)c.small.p + SM_ERR_WORD);
+                                     c.sort_n_scratch.p, (int *)c.small.p + SM_ERR_WORD,
+                                     g_sort_lsd_only);
             if (rc > 0) return 1;
             if (rc == 0) c.order_ptr = (const unsigned *)c.order.p;
         }
@@ -1209,6 +1212,7 @@ int jsb200_set_option(const char *key, int value) {
     if (!strcmp(key, "cull")) { jsb::g_disable_cull = (value == 0); return 0; }
     if (!strcmp(key, "cache")) { jsb::g_disable_cache = (value == 0); return 0; }
     if (!strcmp(key, "rowcol")) { jsb::g_disable_rowcol = (value == 0); return 0; }
+    if (!strcmp(key, "fwdwarp")) { jsb::g_fwd_batch = (value == 0); return 0; }
     if (!strcmp(key, "bwdmom")) { jsb::g_bwd_no_moments = (value == 0); return 0; }
     if (!strcmp(key, "spec")) { jsb::g_disable_spec = (value == 0); return 0; }
     if (!strcmp(key, "bwdhits")) {
@@ -1216,6 +1220,7 @@ int jsb200_set_option(const char *key, int value) {
         jsb::g_bwd_all_entries = (value == 2);
         return 0;
     }
+    if (!strcmp(key, "sortmsd")) { jsb::g_sort_lsd_only = (value == 0); return 0; }
     if (!strcmp(key, "sort1k")) { jsb::g_disable_resident_sort = (value == 0); return 0; }
     if (!strcmp(key, "timing")) { jsb::g_timing = (value != 0); return 0; }
     if (!strcmp(key, "view_slots")) {

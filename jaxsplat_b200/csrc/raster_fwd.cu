@@ -225,6 +225,183 @@ raster_fwd16x2_kernel(const RasterParams p, const unsigned *__restrict__ ids_sor
     }
 }
 
+// ---- barrier-free forward: four independent quadrant warps per tile -----------------------------
+// The counterpart of the hit-driven backward.  raster_fwd16x2_kernel above stages every batch once
+// per CTA behind two __syncthreads and lets one thread compute the cull masks of all eight 8x4
+// rectangles of its entry; its warps then wait for each other at every batch.  Here a warp walks
+// the tile's list on its own, 32 entries at a time:
+//   * lane l gathers entry 32 g + l (sorted id, then the 48-byte record; the next group's records
+//     and the ids of the group after are in flight while this group is composited -- the four
+//     warps of a tile share an SM, so three of the four gathers hit L1),
+//   * tests it against the warp's OWN 8x8 quadrant only (one conservative rectangle test),
+//   * the candidates are compacted into a dense array in the warp's shared memory (ballot prefix)
+//     and replayed in order: no find-first-set walk, no CTA barrier, and a quadrant whose pixels
+//     are all saturated simply stops.
+// Per-visit arithmetic is the text of raster_fwd16x2_kernel: same rounding order, bit-identical.
+struct FwSlot {          // one compacted candidate
+    float4 A;            // x, y, opac, conic.x
+    float4 B;            // conic.y, conic.z, r, g
+};
+
+template <bool CULL>
+__global__ void __launch_bounds__(RF2, JSB_FWD_CTAS)
+raster_fwd_warp_kernel(const RasterParams p, const unsigned *__restrict__ ids_sorted,
+                       const int2 *__restrict__ tile_bins, const SplatRecord *__restrict__ records,
+                       const float *__restrict__ background, float *__restrict__ final_Ts,
+                       int *__restrict__ final_idx, float *__restrict__ out_img,
+                       unsigned *__restrict__ hit_words) {
+    __shared__ FwSlot s_slot[RF2 / 32][32];
+    __shared__ float2 s_c[RF2 / 32][32];  // b, sorted index (bits)
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned tile = p.band_y0 * p.tiles_x + blockIdx.x;
+    const unsigned tile_y = tile / p.tiles_x, tile_x = tile - tile_y * p.tiles_x;
+    const unsigned j = tile_x * 16 + (warp & 1) * 8 + (lane & 7);
+    const unsigned i0 = tile_y * 16 + (warp >> 1) * 8 + (lane >> 3), i1 = i0 + 4;
+    const float px = (float)j + 0.5f, py0 = (float)i0 + 0.5f, py1 = (float)i1 + 0.5f;
+    const bool in0 = (i0 < p.img_h) && (j < p.img_w), in1 = (i1 < p.img_h) && (j < p.img_w);
+    bool done0 = !in0, done1 = !in1;
+    if (guard_trips(p.guard)) return;  // speculative launch whose lists were not built
+    const int2 range = tile_bins[tile];
+    const int ngroups = (range.y - range.x + 31) >> 5;
+    const float tile_x0 = (float)(tile_x * 16), tile_y0 = (float)(tile_y * 16);
+    const float quad_x0 = tile_x0 + (float)((warp & 1) * 8), quad_y0 = tile_y0 + (float)((warp >> 1) * 8);
+    const unsigned hw_off = (unsigned)hit_quadrant_offset(range, blockIdx.x, (unsigned)warp);
+    const unsigned lt_mask = (1u << lane) - 1u;
+    FwSlot *slot = s_slot[warp];
+    float2 *sc = s_c[warp];
+
+    float T0 = 1.f, T1 = 1.f;
+    int cur0 = 0, cur1 = 0;
+    float r0 = 0.f, g0 = 0.f, b0 = 0.f, r1 = 0.f, g1 = 0.f, b1 = 0.f;
+
+    // software pipeline: records of group g in registers, records of g + 1 and ids of g + 2 in flight
+    auto load_id = [&](int g) -> unsigned {
+        const int idx = range.x + 32 * g + lane;
+        return (g < ngroups && idx < range.y) ? ids_sorted[idx] : 0xFFFFFFFFu;
+    };
+    float4 qa = make_float4(0.f, 0.f, 0.f, 0.f), qb = qa;
+    float qc = 0.f;
+    auto load_rec = [&](unsigned id) {
+        if (id != 0xFFFFFFFFu) {
+            const SplatRecord *r = records + id;
+            qa = __ldg(&r->q0);
+            qb = __ldg(&r->q1);
+            qc = __ldg(&r->q2).x;
+        }
+    };
+    unsigned id_cur = load_id(0);
+    unsigned id_next = load_id(1);
+    load_rec(id_cur);
+
+    bool warp_done = __all_sync(0xffffffffu, done0 && done1);
+    for (int g = 0; g < ngroups && !warp_done; ++g) {
+        // this group's record (arrived) -> candidate test
+        const float4 a_me = qa, b_me = qb;
+        const float c_me = qc;
+        bool may = id_cur != 0xFFFFFFFFu;
+        if (CULL && may) {
+            const CullGauss c = cull_setup(a_me.x, a_me.y, a_me.z, a_me.w, b_me.x, b_me.y, tile_x0,
+                                           tile_y0, 16.f, 16.f);
+            may = !c.never && (c.always || cull_rect_may_hit(c, quad_x0, quad_y0, 8.f, 8.f));
+        }
+        // next group's gathers go out before this group is composited
+        id_cur = id_next;
+        id_next = load_id(g + 2);
+        load_rec(id_cur);
+
+        const unsigned bits = __ballot_sync(0xffffffffu, may);
+        unsigned hit = 0;
+        if (bits) {
+            if (may) {
+                const int pos = __popc(bits & lt_mask);
+                slot[pos].A = a_me;
+                slot[pos].B = b_me;
+                sc[pos] = make_float2(c_me, __int_as_float(range.x + 32 * g + lane));
+            }
+            __syncwarp();
+            const int cnt = __popc(bits);
+#pragma unroll 1
+            for (int t = 0; t < cnt; ++t) {
+                const float4 a = slot[t].A;
+                const float4 bq = slot[t].B;
+                const float dx = fsub(a.x, px);
+                // conic_sigma (common.cuh) for both pixels at once: same operation order per pixel
+                // as the reference's compiled code, so the outputs stay bit-identical
+                const float2 dy2 = __fadd2_rn(make_float2(a.y, a.y), make_float2(-py0, -py1));
+                const float ca = fmul(a.w, dx);                                   // cx dx
+                const float ce = fmul(bq.x, dx);                                  // cy dx
+                const float2 b2 = __fmul2_rn(make_float2(bq.y, bq.y), dy2);       // cz dy
+                const float2 c2 = __fmul2_rn(dy2, b2);
+                float2 s2 = __ffma2_rn(make_float2(dx, dx), make_float2(ca, ca), c2);
+                s2 = __fmul2_rn(s2, make_float2(0.5f, 0.5f));
+                const float2 sg2 = __ffma2_rn(make_float2(ce, ce), dy2, s2);
+                const float2 x2 = __fmul2_rn(sg2, make_float2(kNegLog2e, kNegLog2e));
+                const float2 ar2 = __fmul2_rn(make_float2(a.z, a.z),
+                                              make_float2(ex2_approx(x2.x), ex2_approx(x2.y)));
+                const float al0 = fminf(ar2.x, 0.999f), al1 = fminf(ar2.y, 0.999f);
+                const bool ok0 = !done0 && !(sg2.x < 0.f) && !(al0 < kAlphaMin);
+                const bool ok1 = !done1 && !(sg2.y < 0.f) && !(al1 < kAlphaMin);
+                if (ok0 || ok1) {
+                    const float2 cq = sc[t];
+                    const int sidx = __float_as_int(cq.y);
+                    hit |= __funnelshift_l(0u, 1u, (unsigned)(sidx - range.x));  // 1 << (rel & 31)
+                    if (ok0) {
+                        const float next_T = fmul(T0, fsub(1.f, al0));
+                        if (next_T <= kTmin) {
+                            done0 = true;  // this Gaussian is not composited
+                        } else {
+                            const float vis = fmul(T0, al0);
+                            r0 = ffma(vis, bq.z, r0);
+                            g0 = ffma(vis, bq.w, g0);
+                            b0 = ffma(vis, cq.x, b0);
+                            T0 = next_T;
+                            cur0 = sidx;
+                        }
+                    }
+                    if (ok1) {
+                        const float next_T = fmul(T1, fsub(1.f, al1));
+                        if (next_T <= kTmin) {
+                            done1 = true;
+                        } else {
+                            const float vis = fmul(T1, al1);
+                            r1 = ffma(vis, bq.z, r1);
+                            g1 = ffma(vis, bq.w, g1);
+                            b1 = ffma(vis, cq.x, b1);
+                            T1 = next_T;
+                            cur1 = sidx;
+                        }
+                    }
+                }
+            }
+            __syncwarp();  // the slots are free again
+        }
+        if (hit_words) {
+            hit = __reduce_or_sync(0xffffffffu, hit);
+            if (lane == 0) hit_words[hw_off + g] = hit;
+        }
+        warp_done = __all_sync(0xffffffffu, done0 && done1);
+    }
+
+    const float bg0 = __ldg(background), bg1 = __ldg(background + 1), bg2 = __ldg(background + 2);
+    if (in0) {
+        const size_t pix = (size_t)i0 * p.img_w + j;
+        final_Ts[pix] = T0;
+        final_idx[pix] = cur0;
+        out_img[pix * 3 + 0] = ffma(T0, bg0, r0);
+        out_img[pix * 3 + 1] = ffma(T0, bg1, g0);
+        out_img[pix * 3 + 2] = ffma(T0, bg2, b0);
+    }
+    if (in1) {
+        const size_t pix = (size_t)i1 * p.img_w + j;
+        final_Ts[pix] = T1;
+        final_idx[pix] = cur1;
+        out_img[pix * 3 + 0] = ffma(T1, bg0, r1);
+        out_img[pix * 3 + 1] = ffma(T1, bg1, g1);
+        out_img[pix * 3 + 2] = ffma(T1, bg2, b1);
+    }
+}
+
 // Any block_width in [1,16]: one CTA of bw*bw threads per tile, thread (ty,tx) = pixel, same
 // staging, no culling.  Semantics only; block_size 16 is the tuned case.
 __global__ void raster_fwd_generic_kernel(const RasterParams p,
@@ -307,6 +484,7 @@ __global__ void fill_background_kernel(const float *__restrict__ background, siz
 }  // namespace
 
 bool g_disable_cull = false;  // test hook (capi: jsb200_set_option)
+bool g_fwd_batch = false;     // option "fwdwarp" = 0: the per-CTA batch kernel instead of the barrier-free one
 
 int launch_raster_fwd(cudaStream_t stream, const RasterParams &p, const unsigned *ids_sorted,
                       const int2 *tile_bins, const SplatRecord *records, const float *background,
@@ -315,7 +493,15 @@ int launch_raster_fwd(cudaStream_t stream, const RasterParams &p, const unsigned
     const unsigned tiles = p.tiles_x * (p.band_y1 - p.band_y0);
     if (wrote_hits) *wrote_hits = false;
     if (tiles == 0) return 0;
-    if (p.block_width == 16) {
+    if (p.block_width == 16 && !g_fwd_batch) {
+        if (wrote_hits) *wrote_hits = hit_words != nullptr;
+        if (g_disable_cull)
+            raster_fwd_warp_kernel<false><<<tiles, RF2, 0, stream>>>(
+                p, ids_sorted, tile_bins, records, background, final_Ts, final_idx, out_img, hit_words);
+        else
+            raster_fwd_warp_kernel<true><<<tiles, RF2, 0, stream>>>(
+                p, ids_sorted, tile_bins, records, background, final_Ts, final_idx, out_img, hit_words);
+    } else if (p.block_width == 16) {
         if (wrote_hits) *wrote_hits = hit_words != nullptr;
         if (g_disable_cull)
             raster_fwd16x2_kernel<false><<<tiles, RF2, 0, stream>>>(

@@ -58,6 +58,7 @@ struct DsParams {
     int *err;
     unsigned tile_items;      // multiple of 512, <= DS_TILE
     unsigned subtiles;        // tiles per CTA
+    int lsd_only;             // 1: skip the MSD-first attempt (A/B switch, tests)
 };
 
 struct DsSmem {
@@ -67,6 +68,7 @@ struct DsSmem {
     unsigned binstart[DS_BINS];         // exclusive scan of the tile's digit counts
     unsigned goff[DS_BINS];             // global offset of the digit's run minus binstart
     unsigned colcnt[DS_MAXK][DS_MAXG];  // B1: counts of the digits this CTA scans, per CTA
+    unsigned bstart[DS_BINS + 1];       // MSD: first output position of every top-digit bucket
     unsigned ws[DS_WARPS + 1];
 };
 
@@ -93,6 +95,18 @@ __device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned target, int
     __syncthreads();
 }
 
+// how a pass reads its digit from a re-based key (the sentinel stays 0xFFFFFFFF: all-ones in
+// every LSD digit, bucket 511 -- which no real key reaches -- in the MSD pass)
+struct Digit {
+    int shift;
+    unsigned mask;
+    int w;      // live bits (ballots)
+    bool msd;
+    __device__ __forceinline__ unsigned operator()(unsigned k) const {
+        return msd ? (k == kSentinelKey ? (unsigned)(DS_BINS - 1) : (k >> shift)) : ((k >> shift) & mask);
+    }
+};
+
 __global__ void __launch_bounds__(DS_THREADS, 1) resident_depth_sort_kernel(const DsParams P) {
     extern __shared__ __align__(16) unsigned char ds_raw[];
     DsSmem &S = *reinterpret_cast<DsSmem *>(ds_raw);
@@ -110,8 +124,6 @@ __global__ void __launch_bounds__(DS_THREADS, 1) resident_depth_sort_kernel(cons
         for (unsigned i = tid; i < cta_items && b0 + i < P.n; i += DS_THREADS) P.order[b0 + i] = b0 + i;
         return;
     }
-    const int width = (bits + passes - 1) / passes;  // <= 9 live bits per pass
-    const unsigned ipt = P.tile_items / DS_THREADS;  // <= DS_IPT
     const unsigned lt_mask = (1u << lane) - 1u;
     const bool single = P.subtiles == 1;
     unsigned arrivals = 0;
@@ -120,109 +132,109 @@ __global__ void __launch_bounds__(DS_THREADS, 1) resident_depth_sort_kernel(cons
     unsigned short rank[DS_IPT];
     unsigned cta_count = 0, binstart = 0;
 
-    for (int ps = 0; ps < passes; ++ps) {
-        const int shift = ps * width;
-        const int w = min(width, bits - shift);
-        const unsigned dmask = (1u << w) - 1u;
-        const bool last = ps + 1 == passes;
-        const unsigned *ksrc = ps == 0 ? P.keys_in : ((ps & 1) ? P.kB : P.kA);
-        const unsigned *vsrc = (ps & 1) ? P.vB : P.vA;
-        unsigned *kdst = (ps & 1) ? P.kA : P.kB, *vdst = last ? P.order : ((ps & 1) ? P.vA : P.vB);
+    // `count` elements starting at `base` into registers, warp-striped over ipt items per thread
+    // (memory order == (warp, item, lane) order).  first: the keys are the projection's (re-base
+    // them, make up the ids).  Every load of the thread is in flight before the first use.
+    auto load_items = [&](const unsigned *ksrc, const unsigned *vsrc, unsigned base, unsigned count,
+                          unsigned ipt, bool first, bool with_vals) {
+        const unsigned wbase = warp * (ipt * 32u) + lane;
+#pragma unroll
+        for (int i = 0; i < DS_IPT; ++i) {
+            const unsigned o = wbase + i * 32u;
+            const bool have = (unsigned)i < ipt && o < count;
+            key[i] = have ? __ldcg(ksrc + base + o) : 0u;
+            if (with_vals && !first) val[i] = have ? __ldcg(vsrc + base + o) : 0u;
+        }
+        if (first) {
+#pragma unroll
+            for (int i = 0; i < DS_IPT; ++i) {
+                key[i] = (key[i] == kSentinelKey) ? kSentinelKey : key[i] - kmin;  // live bits only
+                val[i] = base + wbase + i * 32u;
+            }
+        }
+    };
+    // stable rank of every item inside its warp's chunk + per-warp digit counts; leaves the
+    // exclusive-over-warps counts in S.whist, the tile's digit count of digit `tid` in
+    // cta_count and its exclusive scan over the digits in binstart / S.binstart
+    auto rank_tile = [&](unsigned count, unsigned ipt, const Digit dg) {
+        for (unsigned i = tid; i < DS_WARPS * DS_BINS; i += DS_THREADS) (&S.whist[0][0])[i] = 0u;
+        __syncthreads();
+        unsigned *wh = S.whist[warp];
+        const unsigned wbase = warp * (ipt * 32u) + lane;
+#pragma unroll
+        for (int i = 0; i < DS_IPT; ++i) {
+            if ((unsigned)i >= ipt) break;  // warp-uniform
+            const bool valid = (wbase + i * 32u) < count;
+            const unsigned d = valid ? dg(key[i]) : 0u;
+            // peers = lanes holding the same digit: one ballot per live digit bit (the native
+            // MATCH.ANY is data dependent on B200 and slower when most lanes differ)
+            unsigned peers = __ballot_sync(0xffffffffu, valid);
+            peers = valid ? peers : ~peers;
+#pragma unroll
+            for (int b = 0; b < DS_BITS; ++b) {
+                if (b < dg.w) {
+                    const unsigned m = __ballot_sync(0xffffffffu, (d >> b) & 1u);
+                    peers &= ((d >> b) & 1u) ? m : ~m;
+                }
+            }
+            const unsigned lower = peers & lt_mask;
+            unsigned pre = 0;
+            if (valid) pre = wh[d];
+            __syncwarp();
+            if (valid && lower == 0) wh[d] = pre + __popc(peers);
+            __syncwarp();
+            rank[i] = (unsigned short)(pre + __popc(lower));
+        }
+        __syncthreads();
+        cta_count = 0;
+#pragma unroll
+        for (int ww = 0; ww < DS_WARPS; ++ww) {
+            const unsigned cc = S.whist[ww][tid];
+            S.whist[ww][tid] = cta_count;
+            cta_count += cc;
+        }
+        unsigned total;
+        binstart = cta_exclusive_scan<DS_THREADS>(cta_count, &total, S.ws);
+        S.binstart[tid] = binstart;
+        __syncthreads();
+    };
+    // tile in registers -> shared memory, grouped by digit, in stable order
+    auto reorder_tile = [&](unsigned count, unsigned ipt, const Digit dg) {
+        const unsigned *wh = S.whist[warp];
+        const unsigned wbase = warp * (ipt * 32u) + lane;
+#pragma unroll
+        for (int i = 0; i < DS_IPT; ++i) {
+            if ((unsigned)i < ipt && (wbase + i * 32u) < count) {
+                const unsigned d = dg(key[i]);
+                const unsigned pos = S.binstart[d] + wh[d] + rank[i];
+                S.keys[pos] = key[i];
+                S.vals[pos] = val[i];
+            }
+        }
+    };
 
-        // loads the tile into registers (warp-striped: memory order == (warp, item, lane) order)
-        auto load_tile = [&](unsigned tile, bool with_vals) -> unsigned {
+    // One GLOBAL pass: the keys of (ksrc, vsrc) leave grouped by digit, stable, into (kdst, vdst).
+    // check_buckets (MSD pass): give up -- nothing written -- if a real bucket exceeds one tile;
+    // the digit totals' exclusive scan is left in S.bstart for the local phase.  Returns false then.
+    auto global_pass = [&](const Digit dg, const unsigned *ksrc, const unsigned *vsrc, unsigned *kdst,
+                           unsigned *vdst, bool first, bool write_keys, bool check_buckets) -> bool {
+        const unsigned ipt = P.tile_items / DS_THREADS;
+        auto tile_count = [&](unsigned tile) -> unsigned {
             const unsigned base = tile * P.tile_items;
-            const unsigned count = base < P.n ? min(P.tile_items, P.n - base) : 0u;
-            const unsigned wbase = warp * (ipt * 32u) + lane;
-            // every load of the thread in flight before the first use (the profile of the first
-            // version showed load -> use -> load: 16 exposed latencies per pass)
-#pragma unroll
-            for (int i = 0; i < DS_IPT; ++i) {
-                const unsigned o = wbase + i * 32u;
-                const bool have = (unsigned)i < ipt && o < count;
-                key[i] = have ? __ldcg(ksrc + base + o) : 0u;
-                if (with_vals && ps != 0) val[i] = have ? __ldcg(vsrc + base + o) : 0u;
-            }
-            if (ps == 0) {
-#pragma unroll
-                for (int i = 0; i < DS_IPT; ++i) {
-                    key[i] = (key[i] == kSentinelKey) ? span : key[i] - kmin;  // live bits only
-                    val[i] = base + wbase + i * 32u;
-                }
-            }
-            return count;
+            return base < P.n ? min(P.tile_items, P.n - base) : 0u;
         };
-        // stable rank of every item inside its warp's chunk + per-warp digit counts; leaves the
-        // exclusive-over-warps counts in S.whist, the tile's digit count of digit `tid` in
-        // cta_count and its exclusive scan over the digits in binstart / S.binstart
-        auto rank_tile = [&](unsigned count) {
-            for (unsigned i = tid; i < DS_WARPS * DS_BINS; i += DS_THREADS) (&S.whist[0][0])[i] = 0u;
-            __syncthreads();
-            unsigned *wh = S.whist[warp];
-            const unsigned wbase = warp * (ipt * 32u) + lane;
-#pragma unroll
-            for (int i = 0; i < DS_IPT; ++i) {
-                if ((unsigned)i >= ipt) break;  // warp-uniform
-                const bool valid = (wbase + i * 32u) < count;
-                const unsigned d = valid ? ((key[i] >> shift) & dmask) : 0u;
-                // peers = lanes holding the same digit: one ballot per live digit bit (the native
-                // MATCH.ANY is data dependent on B200 and slower when most lanes differ)
-                unsigned peers = __ballot_sync(0xffffffffu, valid);
-                peers = valid ? peers : ~peers;
-#pragma unroll
-                for (int b = 0; b < DS_BITS; ++b) {
-                    if (b < w) {
-                        const unsigned m = __ballot_sync(0xffffffffu, (d >> b) & 1u);
-                        peers &= ((d >> b) & 1u) ? m : ~m;
-                    }
-                }
-                const unsigned lower = peers & lt_mask;
-                unsigned pre = 0;
-                if (valid) pre = wh[d];
-                __syncwarp();
-                if (valid && lower == 0) wh[d] = pre + __popc(peers);
-                __syncwarp();
-                rank[i] = (unsigned short)(pre + __popc(lower));
-            }
-            __syncthreads();
-            cta_count = 0;
-#pragma unroll
-            for (int ww = 0; ww < DS_WARPS; ++ww) {
-                const unsigned cc = S.whist[ww][tid];
-                S.whist[ww][tid] = cta_count;
-                cta_count += cc;
-            }
-            unsigned total;
-            binstart = cta_exclusive_scan<DS_THREADS>(cta_count, &total, S.ws);
-            S.binstart[tid] = binstart;
-            __syncthreads();
-        };
-
-        // tile in registers -> shared memory, grouped by digit, in stable order
-        auto reorder_tile = [&](unsigned count) {
-            const unsigned *wh = S.whist[warp];
-            const unsigned wbase = warp * (ipt * 32u) + lane;
-#pragma unroll
-            for (int i = 0; i < DS_IPT; ++i) {
-                if ((unsigned)i < ipt && (wbase + i * 32u) < count) {
-                    const unsigned d = (key[i] >> shift) & dmask;
-                    const unsigned pos = S.binstart[d] + wh[d] + rank[i];
-                    S.keys[pos] = key[i];
-                    S.vals[pos] = val[i];
-                }
-            }
-        };
-
         // ---- A: digit counts of this CTA's tiles ------------------------------------------------
         unsigned count = 0, cta_total = 0;
         for (unsigned st = 0; st < P.subtiles; ++st) {
-            count = load_tile(c * P.subtiles + st, single);
-            rank_tile(count);
+            const unsigned tile = c * P.subtiles + st;
+            count = tile_count(tile);
+            load_items(ksrc, vsrc, tile * P.tile_items, count, ipt, first, single);
+            rank_tile(count, ipt, dg);
             cta_total += cta_count;
         }
         P.hist[(size_t)c * DS_BINS + tid] = cta_total;
         // (single tile: the reorder needs nothing from the other CTAs -- done under the barrier)
-        if (single) reorder_tile(count);
+        if (single) reorder_tile(count, ipt, dg);
         arrivals += G;
         grid_barrier(P.bar, arrivals, P.err);
 
@@ -236,50 +248,60 @@ __global__ void __launch_bounds__(DS_THREADS, 1) resident_depth_sort_kernel(cons
                 if (r < c) before += h;
             }
         } else {
-        // B1: this CTA scans digits [c K, c K + K) over the G CTAs (K = ceil(512 / G) <= 16)
-        {
-            const unsigned K = (DS_BINS + G - 1) / G;
-            const unsigned tpd = DS_THREADS / DS_MAXK;           // threads per digit while loading
-            const unsigned k = tid / tpd, r0 = tid % tpd;
-            const unsigned d = c * K + k;
-            if (k < K && d < DS_BINS)
-                for (unsigned r = r0; r < G; r += tpd) S.colcnt[k][r] = __ldcg(P.hist + (size_t)r * DS_BINS + d);
-            __syncthreads();
-            if (warp < K && c * K + warp < DS_BINS) {  // one warp per digit: lane owns a run of rows
-                const unsigned dd = c * K + warp;
-                const unsigned per = (G + 31u) / 32u;
-                const unsigned b0 = min(G, lane * per), b1 = min(G, b0 + per);
-                unsigned sum = 0;
-                for (unsigned r = b0; r < b1; ++r) sum += S.colcnt[warp][r];
-                unsigned incl = sum;
+            // B1: this CTA scans digits [c K, c K + K) over the G CTAs (K = ceil(512 / G) <= 16)
+            {
+                const unsigned K = (DS_BINS + G - 1) / G;
+                const unsigned tpd = DS_THREADS / DS_MAXK;  // threads per digit while loading
+                const unsigned k = tid / tpd, r0 = tid % tpd;
+                const unsigned d = c * K + k;
+                if (k < K && d < DS_BINS)
+                    for (unsigned r = r0; r < G; r += tpd) S.colcnt[k][r] = __ldcg(P.hist + (size_t)r * DS_BINS + d);
+                __syncthreads();
+                if (warp < K && c * K + warp < DS_BINS) {  // one warp per digit: lane owns a run of rows
+                    const unsigned dd = c * K + warp;
+                    const unsigned per = (G + 31u) / 32u;
+                    const unsigned b0 = min(G, lane * per), b1 = min(G, b0 + per);
+                    unsigned sum = 0;
+                    for (unsigned r = b0; r < b1; ++r) sum += S.colcnt[warp][r];
+                    unsigned incl = sum;
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const unsigned tt = __shfl_up_sync(0xffffffffu, incl, o);
-                    if (lane >= (unsigned)o) incl += tt;
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const unsigned tt = __shfl_up_sync(0xffffffffu, incl, o);
+                        if (lane >= (unsigned)o) incl += tt;
+                    }
+                    unsigned runp = incl - sum;
+                    for (unsigned r = b0; r < b1; ++r) {
+                        P.pre[(size_t)r * DS_BINS + dd] = runp;
+                        runp += S.colcnt[warp][r];
+                    }
+                    if (lane == 31) P.tot[dd] = incl;
                 }
-                unsigned runp = incl - sum;
-                for (unsigned r = b0; r < b1; ++r) {
-                    P.pre[(size_t)r * DS_BINS + dd] = runp;
-                    runp += S.colcnt[warp][r];
-                }
-                if (lane == 31) P.tot[dd] = incl;
             }
-        }
-        arrivals += G;
-        grid_barrier(P.bar, arrivals, P.err);
-
-        // B2: own row of prefixes + digit totals
-        before = __ldcg(P.pre + (size_t)c * DS_BINS + tid);
-        all = __ldcg(P.tot + tid);
+            arrivals += G;
+            grid_barrier(P.bar, arrivals, P.err);
+            // B2: own row of prefixes + digit totals
+            before = __ldcg(P.pre + (size_t)c * DS_BINS + tid);
+            all = __ldcg(P.tot + tid);
         }
         unsigned grand;
         const unsigned dbase = cta_exclusive_scan<DS_THREADS>(all, &grand, S.ws);
+        if (check_buckets) {
+            // every CTA sees the same totals, so the decision is the same everywhere
+            const bool too_big = tid < DS_BINS - 1 && all > (unsigned)DS_TILE;
+            const int any_big = __syncthreads_or(too_big);
+            S.bstart[tid] = dbase;
+            if (tid == 0) S.bstart[DS_BINS] = grand;
+            __syncthreads();
+            if (any_big) return false;
+        }
         unsigned run = dbase + before;  // next global slot of digit `tid` for this CTA
         for (unsigned st = 0; st < P.subtiles; ++st) {
             if (!single) {
-                count = load_tile(c * P.subtiles + st, true);
-                rank_tile(count);
-                reorder_tile(count);
+                const unsigned tile = c * P.subtiles + st;
+                count = tile_count(tile);
+                load_items(ksrc, vsrc, tile * P.tile_items, count, ipt, first, true);
+                rank_tile(count, ipt, dg);
+                reorder_tile(count, ipt, dg);
             }
             S.goff[tid] = run - binstart;
             run += cta_count;
@@ -287,12 +309,113 @@ __global__ void __launch_bounds__(DS_THREADS, 1) resident_depth_sort_kernel(cons
             // consecutive positions of one digit go to consecutive addresses
             for (unsigned pos = tid; pos < count; pos += DS_THREADS) {
                 const unsigned k = S.keys[pos];
-                const unsigned o = pos + S.goff[(k >> shift) & dmask];
-                if (!last) kdst[o] = k;
+                const unsigned o = pos + S.goff[dg(k)];
+                if (write_keys) kdst[o] = k;
                 vdst[o] = S.vals[pos];
             }
             __syncthreads();
         }
+        return true;
+    };
+
+    // ---- MSD first: ONE global pass on the top 9 live bits, then CTA-local passes ----------------
+    // After a stable distribution by the top digit every bucket is a contiguous, complete range of
+    // the output, so the remaining low bits can be sorted bucket by bucket without any further
+    // cross-CTA exchange: a CTA takes the buckets that start in its share of the positions, packs
+    // as many complete buckets as fit one tile, and sorts them in shared memory on
+    // (bucket - first bucket, low bits).  Needs every real bucket to fit one tile (8192 keys):
+    // depth distributions too skewed for that fall through to the LSD passes below.
+    if (passes >= 2 && !P.lsd_only) {
+        int top_shift = bits - DS_BITS;
+        if ((span >> top_shift) >= (unsigned)(DS_BINS - 1)) ++top_shift;  // bucket 511 = sentinels only
+        const Digit top{top_shift, 0u, DS_BITS, true};
+        if (global_pass(top, P.keys_in, nullptr, P.kB, P.vB, /*first=*/true, /*write_keys=*/true,
+                        /*check_buckets=*/true)) {
+            arrivals += G;
+            grid_barrier(P.bar, arrivals, P.err);
+            // the sentinel bucket needs no order: its ids go out as they are (all CTAs share it)
+            const unsigned s0 = S.bstart[DS_BINS - 1];
+            for (unsigned i = s0 + c * DS_THREADS + tid; i < P.n; i += G * DS_THREADS)
+                P.order[i] = __ldcg(P.vB + i);
+            // buckets that START in this CTA's share of the real positions
+            const unsigned share = (s0 + G - 1) / G;  // (s0 = number of real keys)
+            unsigned d = 0;
+            {   // first bucket whose start is >= c * share: binary search over the 512 starts
+                unsigned lo = 0, hi = DS_BINS - 1;  // answer in [0, 511]
+                const unsigned want = c * share;
+                while (lo < hi) {
+                    const unsigned mid = (lo + hi) >> 1;
+                    if (S.bstart[mid] >= want) hi = mid; else lo = mid + 1;
+                }
+                d = lo;
+            }
+            const unsigned limit = (c + 1 == G) ? s0 : min(s0, (c + 1) * share);
+            const unsigned low_mask = (1u << top_shift) - 1u;
+            while (d < (unsigned)(DS_BINS - 1) && S.bstart[d] < limit) {
+                // group [d, de) of complete buckets, at most one tile of keys
+                unsigned de = d + 1;
+                while (de < (unsigned)(DS_BINS - 1) && S.bstart[de] < limit &&
+                       S.bstart[de + 1] - S.bstart[d] <= (unsigned)DS_TILE)
+                    ++de;
+                const unsigned base = S.bstart[d], m = S.bstart[de] - base;
+                if (m > 0) {
+                    const unsigned ipt = (m + DS_THREADS - 1) / DS_THREADS;
+                    load_items(P.kB, P.vB, base, m, ipt, false, true);
+                    // local key: (bucket - d) above the low bits
+#pragma unroll
+                    for (int i = 0; i < DS_IPT; ++i)
+                        key[i] = (((key[i] >> top_shift) - d) << top_shift) | (key[i] & low_mask);
+                    const int lbits = top_shift + (32 - __clz(de - d - 1 > 0 ? de - d - 1 : 0) );
+                    const int lbits_eff = (de - d) > 1 ? lbits : top_shift;
+                    const int lpasses = (lbits_eff + DS_BITS - 1) / DS_BITS;
+                    const int lwidth = lpasses ? (lbits_eff + lpasses - 1) / lpasses : 0;
+                    for (int lp = 0; lp < lpasses; ++lp) {
+                        const int sh = lp * lwidth;
+                        const int w = min(lwidth, lbits_eff - sh);
+                        const Digit dg{sh, (1u << w) - 1u, w, false};
+                        rank_tile(m, ipt, dg);
+                        reorder_tile(m, ipt, dg);
+                        __syncthreads();
+                        if (lp + 1 < lpasses) {  // back into registers in tile order
+                            const unsigned wbase = warp * (ipt * 32u) + lane;
+#pragma unroll
+                            for (int i = 0; i < DS_IPT; ++i) {
+                                const unsigned o = wbase + i * 32u;
+                                if ((unsigned)i < ipt && o < m) { key[i] = S.keys[o]; val[i] = S.vals[o]; }
+                            }
+                            __syncthreads();
+                        }
+                    }
+                    if (lpasses == 0) {  // (one bucket of equal keys: already in index order)
+                        const unsigned wbase = warp * (ipt * 32u) + lane;
+#pragma unroll
+                        for (int i = 0; i < DS_IPT; ++i) {
+                            const unsigned o = wbase + i * 32u;
+                            if ((unsigned)i < ipt && o < m) S.vals[o] = val[i];
+                        }
+                        __syncthreads();
+                    }
+                    for (unsigned pos = tid; pos < m; pos += DS_THREADS) P.order[base + pos] = S.vals[pos];
+                    __syncthreads();
+                }
+                d = de;
+            }
+            return;
+        }
+        // (fall through: the LSD passes restart from the projection's keys)
+    }
+
+    // ---- LSD: one global pass per 9 live bits ------------------------------------------------------
+    const int width = (bits + passes - 1) / passes;  // <= 9 live bits per pass
+    for (int ps = 0; ps < passes; ++ps) {
+        const int shift = ps * width;
+        const int w = min(width, bits - shift);
+        const Digit dg{shift, (1u << w) - 1u, w, false};
+        const bool last = ps + 1 == passes;
+        const unsigned *ksrc = ps == 0 ? P.keys_in : ((ps & 1) ? P.kB : P.kA);
+        const unsigned *vsrc = (ps & 1) ? P.vB : P.vA;
+        unsigned *kdst = (ps & 1) ? P.kA : P.kB, *vdst = last ? P.order : ((ps & 1) ? P.vA : P.vB);
+        global_pass(dg, ksrc, vsrc, kdst, vdst, ps == 0, !last, false);
         if (!last) {
             arrivals += G;
             grid_barrier(P.bar, arrivals, P.err);
@@ -316,7 +439,7 @@ size_t resident_sort_scratch_bytes(unsigned n) {
 // returns 0 on success, 1 on error, -1 if this device cannot run it (caller falls back)
 int resident_depth_sort(cudaStream_t stream, const unsigned *keys_in, unsigned *kA, unsigned *vA,
                         unsigned *kB, unsigned *vB, unsigned *order, unsigned n,
-                        const unsigned *mm, void *scratch, int *err) {
+                        const unsigned *mm, void *scratch, int *err, bool lsd_only) {
     if (n == 0) return 0;
     int dev = 0;
     JSB_CUDA_OK(cudaGetDevice(&dev));
@@ -339,6 +462,7 @@ int resident_depth_sort(cudaStream_t stream, const unsigned *keys_in, unsigned *
     DsParams P;
     P.keys_in = keys_in; P.kA = kA; P.vA = vA; P.kB = kB; P.vB = vB; P.order = order;
     P.n = n; P.mm = mm; P.err = err;
+    P.lsd_only = lsd_only ? 1 : 0;
     P.hist = reinterpret_cast<unsigned *>(scratch);
     P.pre = P.hist + (size_t)DS_MAXG * DS_BINS;
     P.tot = P.pre + (size_t)DS_MAXG * DS_BINS;

@@ -303,10 +303,12 @@ def test_row_column_lists_equal_the_counting_distribution(case):
 
 
 @pytest.mark.parametrize("case", ["C1", "C2_30k", "one_depth", "wide_depth_range", "all_culled",
-                                  "ragged", "band", "two_tiles_per_cta", "many_equal_depths"])
+                                  "ragged", "band", "two_tiles_per_cta", "many_equal_depths",
+                                  "skewed_depths", "half_culled"])
 def test_resident_depth_sort_builds_the_same_lists(case):
     """option "sort1k" (default): the depth order from ONE cooperative launch over the live bits of
-    `key - min` (resident_sort.cu) against four onesweep passes over all 32 key bits: sorted ids,
+    `key - min` (resident_sort.cu; with and without its MSD-first path, option "sortmsd") against
+    four onesweep passes over all 32 key bits: sorted ids,
     tile bins and every forward output must be equal bit for bit -- including one depth for
     everything (no pass at all), a depth range with > 27 live bits (four passes), nothing visible
     (only sentinel keys), and more Gaussians than one tile per CTA holds"""
@@ -334,22 +336,33 @@ def test_resident_depth_sort_builds_the_same_lists(case):
         band = (5, 13)
     elif case == "two_tiles_per_cta":  # > 148 x 8192 Gaussians: the kernel re-reads its tiles
         s = synthetic.benchmark_scene(1_300_000, (128, 160), scale_max=0.01, seed=15)
-    else:  # depth ties across many Gaussians: stability decides the order
+    elif case == "many_equal_depths":  # depth ties across many Gaussians: stability decides the order
         s = synthetic.benchmark_scene(40000, (160, 208), scale_max=0.2, seed=16)
         s.means3d[:, 2] = torch.round(s.means3d[:, 2] * 4.0) / 4.0
+    elif case == "skewed_depths":  # 90 % of the keys inside 1/4000 of the depth range: one top-digit
+        # bucket holds far more than a tile, the MSD-first attempt has to give way to the LSD passes
+        s = synthetic.benchmark_scene(60000, (160, 208), scale_max=0.05, seed=18)
+        g = torch.Generator().manual_seed(19)
+        s.means3d[:54000, 2] = 1.0 + torch.rand(54000, generator=g) * 0.002
+    else:  # half of the scene behind the camera: a large sentinel bucket next to the real ones
+        s = synthetic.benchmark_scene(50000, (160, 208), scale_max=0.1, seed=20)
+        s.means3d[::2, 2] = -30.0
     try:
-        _lib.set_option("sort1k", 1)
-        Ia, ids_a, bins_a, outs_a = _binning_of(s, band)
-        _lib.set_option("sort1k", 0)
+        _lib.set_option("sort1k", 0)           # four onesweep passes over all 32 key bits
         Ib, ids_b, bins_b, outs_b = _binning_of(s, band)
+        _lib.set_option("sort1k", 1)
+        for msd in (1, 0):                     # MSD pass + CTA-local passes / global LSD passes
+            _lib.set_option("sortmsd", msd)
+            Ia, ids_a, bins_a, outs_a = _binning_of(s, band)
+            assert Ia == Ib and (Ia > 0 or case == "all_culled")
+            assert np.array_equal(bins_a, bins_b), msd
+            assert np.array_equal(ids_a, ids_b), msd
+            if band is None:
+                for a, b in zip(outs_a, outs_b):
+                    assert np.array_equal(a, b), msd
     finally:
         _lib.set_option("sort1k", 1)
-    assert Ia == Ib and (Ia > 0 or case == "all_culled")
-    assert np.array_equal(bins_a, bins_b)
-    assert np.array_equal(ids_a, ids_b)
-    if band is None:
-        for a, b in zip(outs_a, outs_b):
-            assert np.array_equal(a, b)
+        _lib.set_option("sortmsd", 1)
 
 
 def _long_list_scene():
@@ -416,3 +429,45 @@ def test_hit_driven_backward_through_the_fused_render_and_bands():
             for a, b in zip(res[(mode, rows)], res[((0, 1), rows)]):
                 ok, err, scale = grad_close(a, b, rel=2e-5)
                 assert ok, (mode, rows, err, scale)
+
+
+@pytest.mark.parametrize("scene_fn", [_adversarial_scene, _long_list_scene,
+                                      lambda: synthetic.make_config("C2", num_points=30000),
+                                      lambda: synthetic.benchmark_scene(9000, (200, 120), scale_max=0.2, seed=21),
+                                      lambda: synthetic.benchmark_scene(60, (40, 40), scale_max=0.3, seed=3),
+                                      lambda: synthetic.make_config("C1")])
+def test_barrier_free_forward_is_bit_identical_to_the_batch_kernel(scene_fn):
+    """option "fwdwarp" (default): four independent quadrant warps per tile, each gathering,
+    cull-testing and compacting the list on its own (raster_fwd_warp_kernel), against the per-CTA
+    batch kernel: the same pairs in the same rounding order, so final_idx, final_Ts and the image
+    may not differ in a bit -- with and without culling -- and the hit words they leave drive the
+    backward to the same gradients"""
+    s = scene_fn()
+    inp = G.scene_inputs(s)
+    kw, rkw = G.scene_kw(s)
+    H, W = s.img_shape
+    P = G.project_fwd(inp, kw)
+    target = np.random.RandomState(2).rand(H, W, 3).astype(np.float32)
+    for cull in (1, 0):
+        try:
+            _lib.set_option("cull", cull)
+            _lib.set_option("fwdwarp", 1)
+            a = G.rasterize_fwd(inp, P, rkw)
+            _lib.set_option("fwdwarp", 0)
+            b = G.rasterize_fwd(inp, P, rkw)
+        finally:
+            _lib.set_option("fwdwarp", 1)
+            _lib.set_option("cull", 1)
+        assert torch.equal(a["final_idx"], b["final_idx"])
+        assert torch.equal(a["final_Ts"].view(torch.int32), b["final_Ts"].view(torch.int32))
+        assert torch.equal(a["img"].view(torch.int32), b["img"].view(torch.int32))
+    try:
+        _lib.set_option("fwdwarp", 1)
+        ga = _full_gpu(inp, kw, rkw, target)
+        _lib.set_option("fwdwarp", 0)
+        gb = _full_gpu(inp, kw, rkw, target)
+    finally:
+        _lib.set_option("fwdwarp", 1)
+    for k in ("v_colors", "v_opacity", "v_xy", "v_xy_abs", "v_conic"):
+        ok, err, scale = grad_close(ga[k], gb[k], rel=2e-5)
+        assert ok, (k, err, scale)
