@@ -265,8 +265,6 @@ def main():
             _lib.set_option("bwdmom", 0)
         if os.environ.get("JSB_BWDHITS") == "0":  # per-tile batch backward instead of the hit-driven one
             _lib.set_option("bwdhits", 0)
-        if os.environ.get("JSB_SORTMSD") == "0":  # global LSD passes only in the one-launch depth sort
-            _lib.set_option("sortmsd", 0)
         if os.environ.get("JSB_SORT1K") == "0":  # four onesweep passes instead of the resident sort
             _lib.set_option("sort1k", 0)
         if os.environ.get("JSB_FUSED") == "0":

@@ -177,7 +177,7 @@ int radix_sort_pairs(cudaStream_t stream, KeyT *keys_a, KeyT *keys_b, unsigned *
 size_t resident_sort_scratch_bytes(unsigned n);
 int resident_depth_sort(cudaStream_t stream, const unsigned *keys_in, unsigned *kA, unsigned *vA,
                         unsigned *kB, unsigned *vB, unsigned *order, unsigned n,
-                        const unsigned *mm, void *scratch, int *err, bool lsd_only = false);
+                        const unsigned *mm, void *scratch, int *err);
 
 // ---- rasterisers (raster_fwd.cu / raster_bwd.cu) --------------------------------------------
 struct RasterParams {

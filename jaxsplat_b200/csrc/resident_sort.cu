@@ -58,7 +58,6 @@ struct DsParams {
     int *err;
     unsigned tile_items;      // multiple of 512, <= DS_TILE
     unsigned subtiles;        // tiles per CTA
-    int lsd_only;             // 1: skip the MSD-first attempt (A/B switch, tests)
 };
 
 struct DsSmem {
@@ -68,7 +67,6 @@ struct DsSmem {
     unsigned binstart[DS_BINS];         // exclusive scan of the tile's digit counts
     unsigned goff[DS_BINS];             // global offset of the digit's run minus binstart
     unsigned colcnt[DS_MAXK][DS_MAXG];  // B1: counts of the digits this CTA scans, per CTA
-    unsigned bstart[DS_BINS + 1];       // MSD: first output position of every top-digit bucket
     unsigned ws[DS_WARPS + 1];
 };
 
@@ -96,15 +94,12 @@ __device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned target, int
 }
 
 // how a pass reads its digit from a re-based key (the sentinel stays 0xFFFFFFFF: all-ones in
-// every LSD digit, bucket 511 -- which no real key reaches -- in the MSD pass)
+// every digit, so it sorts last)
 struct Digit {
     int shift;
     unsigned mask;
     int w;      // live bits (ballots)
-    bool msd;
-    __device__ __forceinline__ unsigned operator()(unsigned k) const {
-        return msd ? (k == kSentinelKey ? (unsigned)(DS_BINS - 1) : (k >> shift)) : ((k >> shift) & mask);
-    }
+    __device__ __forceinline__ unsigned operator()(unsigned k) const { return (k >> shift) & mask; }
 };
 
 __global__ void __launch_bounds__(DS_THREADS, 1) resident_depth_sort_kernel(const DsParams P) {
@@ -214,10 +209,8 @@ __global__ void __launch_bounds__(DS_THREADS, 1) resident_depth_sort_kernel(cons
     };
 
     // One GLOBAL pass: the keys of (ksrc, vsrc) leave grouped by digit, stable, into (kdst, vdst).
-    // check_buckets (MSD pass): give up -- nothing written -- if a real bucket exceeds one tile;
-    // the digit totals' exclusive scan is left in S.bstart for the local phase.  Returns false then.
     auto global_pass = [&](const Digit dg, const unsigned *ksrc, const unsigned *vsrc, unsigned *kdst,
-                           unsigned *vdst, bool first, bool write_keys, bool check_buckets) -> bool {
+                           unsigned *vdst, bool first, bool write_keys) {
         const unsigned ipt = P.tile_items / DS_THREADS;
         auto tile_count = [&](unsigned tile) -> unsigned {
             const unsigned base = tile * P.tile_items;
@@ -285,15 +278,6 @@ __global__ void __launch_bounds__(DS_THREADS, 1) resident_depth_sort_kernel(cons
         }
         unsigned grand;
         const unsigned dbase = cta_exclusive_scan<DS_THREADS>(all, &grand, S.ws);
-        if (check_buckets) {
-            // every CTA sees the same totals, so the decision is the same everywhere
-            const bool too_big = tid < DS_BINS - 1 && all > (unsigned)DS_TILE;
-            const int any_big = __syncthreads_or(too_big);
-            S.bstart[tid] = dbase;
-            if (tid == 0) S.bstart[DS_BINS] = grand;
-            __syncthreads();
-            if (any_big) return false;
-        }
         unsigned run = dbase + before;  // next global slot of digit `tid` for this CTA
         for (unsigned st = 0; st < P.subtiles; ++st) {
             if (!single) {
@@ -315,107 +299,19 @@ __global__ void __launch_bounds__(DS_THREADS, 1) resident_depth_sort_kernel(cons
             }
             __syncthreads();
         }
-        return true;
     };
-
-    // ---- MSD first: ONE global pass on the top 9 live bits, then CTA-local passes ----------------
-    // After a stable distribution by the top digit every bucket is a contiguous, complete range of
-    // the output, so the remaining low bits can be sorted bucket by bucket without any further
-    // cross-CTA exchange: a CTA takes the buckets that start in its share of the positions, packs
-    // as many complete buckets as fit one tile, and sorts them in shared memory on
-    // (bucket - first bucket, low bits).  Needs every real bucket to fit one tile (8192 keys):
-    // depth distributions too skewed for that fall through to the LSD passes below.
-    if (passes >= 2 && !P.lsd_only) {
-        int top_shift = bits - DS_BITS;
-        if ((span >> top_shift) >= (unsigned)(DS_BINS - 1)) ++top_shift;  // bucket 511 = sentinels only
-        const Digit top{top_shift, 0u, DS_BITS, true};
-        if (global_pass(top, P.keys_in, nullptr, P.kB, P.vB, /*first=*/true, /*write_keys=*/true,
-                        /*check_buckets=*/true)) {
-            arrivals += G;
-            grid_barrier(P.bar, arrivals, P.err);
-            // the sentinel bucket needs no order: its ids go out as they are (all CTAs share it)
-            const unsigned s0 = S.bstart[DS_BINS - 1];
-            for (unsigned i = s0 + c * DS_THREADS + tid; i < P.n; i += G * DS_THREADS)
-                P.order[i] = __ldcg(P.vB + i);
-            // buckets that START in this CTA's share of the real positions
-            const unsigned share = (s0 + G - 1) / G;  // (s0 = number of real keys)
-            unsigned d = 0;
-            {   // first bucket whose start is >= c * share: binary search over the 512 starts
-                unsigned lo = 0, hi = DS_BINS - 1;  // answer in [0, 511]
-                const unsigned want = c * share;
-                while (lo < hi) {
-                    const unsigned mid = (lo + hi) >> 1;
-                    if (S.bstart[mid] >= want) hi = mid; else lo = mid + 1;
-                }
-                d = lo;
-            }
-            const unsigned limit = (c + 1 == G) ? s0 : min(s0, (c + 1) * share);
-            const unsigned low_mask = (1u << top_shift) - 1u;
-            while (d < (unsigned)(DS_BINS - 1) && S.bstart[d] < limit) {
-                // group [d, de) of complete buckets, at most one tile of keys
-                unsigned de = d + 1;
-                while (de < (unsigned)(DS_BINS - 1) && S.bstart[de] < limit &&
-                       S.bstart[de + 1] - S.bstart[d] <= (unsigned)DS_TILE)
-                    ++de;
-                const unsigned base = S.bstart[d], m = S.bstart[de] - base;
-                if (m > 0) {
-                    const unsigned ipt = (m + DS_THREADS - 1) / DS_THREADS;
-                    load_items(P.kB, P.vB, base, m, ipt, false, true);
-                    // local key: (bucket - d) above the low bits
-#pragma unroll
-                    for (int i = 0; i < DS_IPT; ++i)
-                        key[i] = (((key[i] >> top_shift) - d) << top_shift) | (key[i] & low_mask);
-                    const int lbits = top_shift + (32 - __clz(de - d - 1 > 0 ? de - d - 1 : 0) );
-                    const int lbits_eff = (de - d) > 1 ? lbits : top_shift;
-                    const int lpasses = (lbits_eff + DS_BITS - 1) / DS_BITS;
-                    const int lwidth = lpasses ? (lbits_eff + lpasses - 1) / lpasses : 0;
-                    for (int lp = 0; lp < lpasses; ++lp) {
-                        const int sh = lp * lwidth;
-                        const int w = min(lwidth, lbits_eff - sh);
-                        const Digit dg{sh, (1u << w) - 1u, w, false};
-                        rank_tile(m, ipt, dg);
-                        reorder_tile(m, ipt, dg);
-                        __syncthreads();
-                        if (lp + 1 < lpasses) {  // back into registers in tile order
-                            const unsigned wbase = warp * (ipt * 32u) + lane;
-#pragma unroll
-                            for (int i = 0; i < DS_IPT; ++i) {
-                                const unsigned o = wbase + i * 32u;
-                                if ((unsigned)i < ipt && o < m) { key[i] = S.keys[o]; val[i] = S.vals[o]; }
-                            }
-                            __syncthreads();
-                        }
-                    }
-                    if (lpasses == 0) {  // (one bucket of equal keys: already in index order)
-                        const unsigned wbase = warp * (ipt * 32u) + lane;
-#pragma unroll
-                        for (int i = 0; i < DS_IPT; ++i) {
-                            const unsigned o = wbase + i * 32u;
-                            if ((unsigned)i < ipt && o < m) S.vals[o] = val[i];
-                        }
-                        __syncthreads();
-                    }
-                    for (unsigned pos = tid; pos < m; pos += DS_THREADS) P.order[base + pos] = S.vals[pos];
-                    __syncthreads();
-                }
-                d = de;
-            }
-            return;
-        }
-        // (fall through: the LSD passes restart from the projection's keys)
-    }
 
     // ---- LSD: one global pass per 9 live bits ------------------------------------------------------
     const int width = (bits + passes - 1) / passes;  // <= 9 live bits per pass
     for (int ps = 0; ps < passes; ++ps) {
         const int shift = ps * width;
         const int w = min(width, bits - shift);
-        const Digit dg{shift, (1u << w) - 1u, w, false};
+        const Digit dg{shift, (1u << w) - 1u, w};
         const bool last = ps + 1 == passes;
         const unsigned *ksrc = ps == 0 ? P.keys_in : ((ps & 1) ? P.kB : P.kA);
         const unsigned *vsrc = (ps & 1) ? P.vB : P.vA;
         unsigned *kdst = (ps & 1) ? P.kA : P.kB, *vdst = last ? P.order : ((ps & 1) ? P.vA : P.vB);
-        global_pass(dg, ksrc, vsrc, kdst, vdst, ps == 0, !last, false);
+        global_pass(dg, ksrc, vsrc, kdst, vdst, ps == 0, !last);
         if (!last) {
             arrivals += G;
             grid_barrier(P.bar, arrivals, P.err);
@@ -439,7 +335,7 @@ size_t resident_sort_scratch_bytes(unsigned n) {
 // returns 0 on success, 1 on error, -1 if this device cannot run it (caller falls back)
 int resident_depth_sort(cudaStream_t stream, const unsigned *keys_in, unsigned *kA, unsigned *vA,
                         unsigned *kB, unsigned *vB, unsigned *order, unsigned n,
-                        const unsigned *mm, void *scratch, int *err, bool lsd_only) {
+                        const unsigned *mm, void *scratch, int *err) {
     if (n == 0) return 0;
     int dev = 0;
     JSB_CUDA_OK(cudaGetDevice(&dev));
@@ -462,7 +358,6 @@ int resident_depth_sort(cudaStream_t stream, const unsigned *keys_in, unsigned *
     DsParams P;
     P.keys_in = keys_in; P.kA = kA; P.vA = vA; P.kB = kB; P.vB = vB; P.order = order;
     P.n = n; P.mm = mm; P.err = err;
-    P.lsd_only = lsd_only ? 1 : 0;
     P.hist = reinterpret_cast<unsigned *>(scratch);
     P.pre = P.hist + (size_t)DS_MAXG * DS_BINS;
     P.tot = P.pre + (size_t)DS_MAXG * DS_BINS;

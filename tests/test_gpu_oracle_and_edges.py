@@ -307,7 +307,7 @@ def test_row_column_lists_equal_the_counting_distribution(case):
                                   "skewed_depths", "half_culled"])
 def test_resident_depth_sort_builds_the_same_lists(case):
     """option "sort1k" (default): the depth order from ONE cooperative launch over the live bits of
-    `key - min` (resident_sort.cu; with and without its MSD-first path, option "sortmsd") against
+    `key - min` (resident_sort.cu) against
     four onesweep passes over all 32 key bits: sorted ids,
     tile bins and every forward output must be equal bit for bit -- including one depth for
     everything (no pass at all), a depth range with > 27 live bits (four passes), nothing visible
@@ -339,8 +339,7 @@ def test_resident_depth_sort_builds_the_same_lists(case):
     elif case == "many_equal_depths":  # depth ties across many Gaussians: stability decides the order
         s = synthetic.benchmark_scene(40000, (160, 208), scale_max=0.2, seed=16)
         s.means3d[:, 2] = torch.round(s.means3d[:, 2] * 4.0) / 4.0
-    elif case == "skewed_depths":  # 90 % of the keys inside 1/4000 of the depth range: one top-digit
-        # bucket holds far more than a tile, the MSD-first attempt has to give way to the LSD passes
+    elif case == "skewed_depths":  # 90 % of the keys inside 1/4000 of the depth range
         s = synthetic.benchmark_scene(60000, (160, 208), scale_max=0.05, seed=18)
         g = torch.Generator().manual_seed(19)
         s.means3d[:54000, 2] = 1.0 + torch.rand(54000, generator=g) * 0.002
@@ -351,18 +350,15 @@ def test_resident_depth_sort_builds_the_same_lists(case):
         _lib.set_option("sort1k", 0)           # four onesweep passes over all 32 key bits
         Ib, ids_b, bins_b, outs_b = _binning_of(s, band)
         _lib.set_option("sort1k", 1)
-        for msd in (1, 0):                     # MSD pass + CTA-local passes / global LSD passes
-            _lib.set_option("sortmsd", msd)
-            Ia, ids_a, bins_a, outs_a = _binning_of(s, band)
-            assert Ia == Ib and (Ia > 0 or case == "all_culled")
-            assert np.array_equal(bins_a, bins_b), msd
-            assert np.array_equal(ids_a, ids_b), msd
-            if band is None:
-                for a, b in zip(outs_a, outs_b):
-                    assert np.array_equal(a, b), msd
+        Ia, ids_a, bins_a, outs_a = _binning_of(s, band)
+        assert Ia == Ib and (Ia > 0 or case == "all_culled")
+        assert np.array_equal(bins_a, bins_b)
+        assert np.array_equal(ids_a, ids_b)
+        if band is None:
+            for a, b in zip(outs_a, outs_b):
+                assert np.array_equal(a, b)
     finally:
         _lib.set_option("sort1k", 1)
-        _lib.set_option("sortmsd", 1)
 
 
 def _long_list_scene():
