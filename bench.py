@@ -159,15 +159,20 @@ def useful_pairs(sc, kw):
     H, W = sc.img_shape
     bs = sc.block_size
     n = sc.means3d.shape[0]
-    outs, _tok = _ops.render_fwd(sc.means3d, sc.scales, sc.quats, sc.viewmat, sc.colors, sc.opacities,
-                                 sc.background, num_points=n, img_shape=sc.img_shape, f=sc.f, c=sc.c,
-                                 glob_scale=sc.glob_scale, clip_thresh=sc.clip_thresh, block_width=bs)
-    final_idx = outs[7].view(H, W).long()
-    tx, ty = (W + bs - 1) // bs, (H + bs - 1) // bs
-    bins = torch.zeros((tx * ty, 2), dtype=torch.int32, device=final_idx.device)
-    got = _lib.lib().jsb200_debug_binning(ctypes.c_void_p(torch.cuda.current_stream().cuda_stream),
-                                          None, None, ctypes.c_void_p(bins.data_ptr()), None)
-    torch.cuda.synchronize()
+    # (with the exact per-tile lists: final_idx of the super-column lists counts other tiles' entries)
+    _lib.set_option("supercols", 0)
+    try:
+        outs, _tok = _ops.render_fwd(sc.means3d, sc.scales, sc.quats, sc.viewmat, sc.colors, sc.opacities,
+                                     sc.background, num_points=n, img_shape=sc.img_shape, f=sc.f, c=sc.c,
+                                     glob_scale=sc.glob_scale, clip_thresh=sc.clip_thresh, block_width=bs)
+        final_idx = outs[7].view(H, W).long()
+        tx, ty = (W + bs - 1) // bs, (H + bs - 1) // bs
+        bins = torch.zeros((tx * ty, 2), dtype=torch.int32, device=final_idx.device)
+        got = _lib.lib().jsb200_debug_binning(ctypes.c_void_p(torch.cuda.current_stream().cuda_stream),
+                                              None, None, ctypes.c_void_p(bins.data_ptr()), None)
+        torch.cuda.synchronize()
+    finally:
+        _lib.set_option("supercols", int(os.environ.get("JSB_SUPERCOLS", "2")))
     if got < 0:
         _lib.lib().jsb200_clear_error()
         return None
@@ -265,6 +270,8 @@ def main():
             _lib.set_option("bwdmom", 0)
         if os.environ.get("JSB_BWDHITS") == "0":  # per-tile batch backward instead of the hit-driven one
             _lib.set_option("bwdhits", 0)
+        if os.environ.get("JSB_SUPERCOLS"):  # tiles per super-column of the fused render's lists (log2; 0 = exact lists)
+            _lib.set_option("supercols", int(os.environ["JSB_SUPERCOLS"]))
         if os.environ.get("JSB_SORT1K") == "0":  # four onesweep passes instead of the resident sort
             _lib.set_option("sort1k", 0)
         if os.environ.get("JSB_FUSED") == "0":

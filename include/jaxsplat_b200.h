@@ -171,13 +171,12 @@ JSB200_API unsigned long long jsb200_error_count(void);
  *      "bwdmom" (1 default; 0 makes the fused render's hit-driven rasteriser backward accumulate
  *               finished v_xy / v_conic / v_opacity instead of raw moments that the projection
  *               backward finishes),
- *      "spec" (0 default; 1 lets a forward launch the list builders and the rasteriser before the
- *               host knows the frame's intersection count, with buffers sized from the previous
- *               frame of the same shape and device-side guards; measured neutral to slower),
+ *      "supercols" (2 default; k > 0: the fused render (block_width 16) lists the 8-byte row
+ *               entries per super-column of 2^k tiles and its rasterisers keep the entries whose
+ *               tile columns cover their tile; 0: the exact per-tile id lists everywhere.  Must
+ *               not change between a render_fwd and its render_bwd),
  *      "bwdhits" (1 default; 0 runs rasterize_bwd with the per-tile batch kernel even when the
  *               forward recorded which list entries every 8x8 quadrant accepted),
- *      "sortmsd" (1 default; 0 makes the one-launch depth sort do one global pass per 9 live key
- *               bits instead of one global pass on the top 9 bits followed by CTA-local passes),
  *      "sort1k" (1 default; 0 orders the Gaussians by depth with four onesweep passes over all 32
  *               key bits instead of the single cooperative launch over the live bits),
  *      "timing" (0 default; 1 brackets every stage with CUDA events, see jsb200_get_stage_times),
@@ -204,11 +203,6 @@ JSB200_API int jsb200_get_stage_times(jsb200_stream_t stream, double *ms_out9,
  * [3] binning cache hits, [4] last num_intersects, [5] workspace bytes, [6] kernel launches,
  * [7] last row-entry count (sum of tile-box heights) */
 JSB200_API void jsb200_get_stats(unsigned long long *out8);
-/* Forward rasterisations whose list builders + rasteriser were launched before the host knew the
- * frame's intersection count (buffers sized from the previous frame of the same shape; option
- * "spec", off by default): out2[0] = launches that held, out2[1] = frames that outgrew the buffers and
- * were rebuilt with exact sizes (same results either way). */
-JSB200_API void jsb200_get_speculation_stats(unsigned long long *out2);
 /* releases every workspace (all devices/streams). */
 JSB200_API void jsb200_release(void);
 

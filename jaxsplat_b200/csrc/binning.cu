@@ -53,7 +53,7 @@ bin_prep_kernel(const BinParams p, const float2 *__restrict__ xys,
         slab_load<3, BT>(s_color, colors, base * 3, n * 3);
     }
     __syncthreads();
-    unsigned cnt = 0, cnt_rows = 0, kinv = 0, kmax = 0;
+    unsigned cnt = 0, cnt_rows = 0, cnt_sup = 0, kinv = 0, kmax = 0;
     if (g < n) {
         const float2 xy = __ldg(xys + g);
         const float depth = __ldg(depths + g);
@@ -82,6 +82,7 @@ bin_prep_kernel(const BinParams p, const float2 *__restrict__ xys,
             if (y1 > y0 && x1 > x0) {
                 cnt = (x1 - x0) * (y1 - y0);
                 cnt_rows = y1 - y0;
+                cnt_sup = cnt_rows * (((x1 - 1u) >> p.sc_shift) - (x0 >> p.sc_shift) + 1u);
                 box = make_uint2(x0 | (y0 << 16), (x1 - x0) | ((y1 - y0) << 16));
                 if (WRITE && nstrips > 1) {  // tiles per strip (the strips are binned one by one)
                     for (unsigned st = (y0 - p.band_y0) / p.strip_rows; st < nstrips; ++st) {
@@ -106,23 +107,25 @@ bin_prep_kernel(const BinParams p, const float2 *__restrict__ xys,
     for (int o = 16; o > 0; o >>= 1) {
         cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
         cnt_rows += __shfl_xor_sync(0xffffffffu, cnt_rows, o);
+        cnt_sup += __shfl_xor_sync(0xffffffffu, cnt_sup, o);
     }
     kinv = __reduce_max_sync(0xffffffffu, kinv);
     kmax = __reduce_max_sync(0xffffffffu, kmax);
     // one pair of global atomics per CTA (they all hit the same two words: per-warp atomics
     // serialise in the L2 and were the kernel's critical path)
-    __shared__ unsigned s_tot[BT / 32][4];
+    __shared__ unsigned s_tot[BT / 32][5];
     if ((tid & 31) == 0) {
         s_tot[tid >> 5][0] = cnt; s_tot[tid >> 5][1] = cnt_rows;
         s_tot[tid >> 5][2] = kinv; s_tot[tid >> 5][3] = kmax;
+        s_tot[tid >> 5][4] = cnt_sup;
     }
     __syncthreads();
     if (tid == 0) {
-        unsigned long long t0 = 0, t1 = 0;
+        unsigned long long t0 = 0, t1 = 0, t2 = 0;
         unsigned m0 = 0, m1 = 0;
 #pragma unroll
         for (int w = 0; w < BT / 32; ++w) {
-            t0 += s_tot[w][0]; t1 += s_tot[w][1];
+            t0 += s_tot[w][0]; t1 += s_tot[w][1]; t2 += s_tot[w][4];
             m0 = max(m0, s_tot[w][2]); m1 = max(m1, s_tot[w][3]);
         }
         if (WRITE && (m0 | m1)) {  // range of the real depth keys, for the live-bit depth sort
@@ -133,7 +136,10 @@ bin_prep_kernel(const BinParams p, const float2 *__restrict__ xys,
         if (t0) {
             atomicAdd(fingerprint + 1, t0);  // total intersections
             // sum of box heights = row entries of the two-level distribution (rowcol_lists.cu)
-            if (WRITE) atomicAdd(fingerprint + 4, t1);
+            if (WRITE) {
+                atomicAdd(fingerprint + 4, t1);
+                atomicAdd(fingerprint + 6, t2);  // (row entry, super-column) pairs
+            }
         }
     }
     if (WRITE && nstrips > 1) {

@@ -36,8 +36,6 @@ static thread_local std::string t_error;
 static thread_local bool t_has_error = false;
 static std::atomic<unsigned long long> g_error_count{0};
 static std::atomic<unsigned long long> g_stats[8];
-static std::atomic<unsigned long long> g_stats_spec_hits{0};  // forwards whose speculative launch held
-static std::atomic<unsigned long long> g_stats_spec_redo{0};  // ... and those that outgrew it (rebuilt)
 static std::atomic<unsigned long long> g_token_counter{0};  // binning tokens (never reset, never 0)
 
 void set_error(const char *fmt, ...) {
@@ -61,6 +59,11 @@ extern bool g_bwd_no_moments;
 static bool g_disable_cache = false;
 static bool g_disable_rowcol = false;
 static bool g_disable_resident_sort = false;  // option "sort1k" 0: the four-pass onesweep depth sort
+// Fused render, block_width 16: level 2 of the list build distributes the row entries into
+// super-columns of 2^g_sc_shift tiles (rowcol_lists.cu) and the rasterisers filter by column;
+// option "supercols" (0 = the exact per-tile lists everywhere).  The four-op API always builds the
+// exact lists: its final_idx / sorted ids are the reference's.
+static unsigned g_sc_shift = 2;
 static unsigned g_view_slots = 8;  // binning workspaces a batched-camera call cycles through
 
 // ---- optional per-stage device timing (jsb200_set_option("timing", 1)) -------------------------
@@ -106,16 +109,13 @@ struct Ctx {
     DevBuf tile_keys, tile_vals, tile_ids, tile_scratch, hits;
     DevBuf abs_scratch;
     DevBuf views_scratch;  // batched cameras: per-view cotangents + parameter-gradient staging
+    DevBuf sbins;  // super-column list ranges (band-local rows x cols2)
     DevBuf bins, small;  // small: [fingerprint u64][total u64][err int x4][tickets u32 x8]
     unsigned long long *h_pinned = nullptr;  // [fingerprint][total][err...]
     cudaEvent_t ev_ready = nullptr;          // recorded after the D2H of `small`
     const unsigned *order_ptr = nullptr;     // the depth-sorted ids of the last prep
-    // counts of the last forward binning of this shape: the next forward sizes its buffers from
-    // them and launches the list builders + rasteriser BEFORE the host has this frame's counts
-    bool plan_valid = false;
-    unsigned plan_n = 0, plan_tiles_x = 0, plan_tiles_y = 0, plan_bw = 0, plan_band = 0;
-    unsigned long long plan_I = 0, plan_E = 0;
     unsigned long long last_rows = 0;        // sum of box heights of the last prep (row entries)
+    unsigned long long last_super = 0;       // (row entry, super-column) pairs of the last prep
     // binning cache
     bool cache_valid = false;
     bool cache_has_records = false;  // false after a sort_and_bin-only call (no appearance data)
@@ -123,6 +123,9 @@ struct Ctx {
     unsigned long long cache_fp = 0;
     unsigned cache_n = 0, cache_tiles = 0, cache_bw = 0, cache_tiles_x = 0, cache_band = 0;
     unsigned long long cache_I = 0;
+    unsigned cache_sc_shift = 0;             // > 0: the cached lists are super-column lists
+    unsigned long long cache_entries = 0;    // their entry count
+    const int2 *cache_bins = nullptr;        // bins (tile lists) or sbins (super-column lists)
     bool cache_fp_known = false;             // false when the binning came from the fused render
     unsigned long long cache_token = 0;      // token of the cached binning (fused render)
     unsigned *cache_ids = nullptr;  // points into tile_ids
@@ -149,7 +152,7 @@ struct Ctx {
     void release() {
         DevBuf *all[] = {&records, &dkeys_a, &dkeys_b, &ids_a, &ids_b, &order, &box_by_id, &boxes,
                          &sort_n_scratch, &chain, &tile_keys, &tile_vals, &tile_ids, &tile_scratch, &hits,
-                         &bins, &small, &abs_scratch, &views_scratch};
+                         &bins, &sbins, &small, &abs_scratch, &views_scratch};
         for (DevBuf *b : all) {
             if (b->p) cudaFree(b->p);
             b->p = nullptr;
@@ -245,6 +248,7 @@ static void band_of(const Descriptor &d, unsigned *y0, unsigned *y1) {
 
 static BinParams bin_params(const Descriptor &d) {
     BinParams bp{d.num_points, (float)(int)d.block_width, d.tiles_x, d.tiles_y, 0, 0, 1};
+    bp.sc_shift = g_sc_shift;
     band_of(d, &bp.band_y0, &bp.band_y1);
     bp.strip_rows = tile_strip_rows(d.tiles_x);
     if (bp.strip_rows == 0) bp.strip_rows = 1;  // (rejected by check_raster_desc)
@@ -254,6 +258,7 @@ static BinParams bin_params(const Descriptor &d) {
 
 constexpr int SM_FP = 0, SM_TOTAL = 1;       // u64 slots in `small`
 constexpr int SM_ROWS = 4;                   // u64 slot: sum of box heights (row entries)
+constexpr int SM_SUPER = 6;                  // u64 slot: (row entry, super-column) pairs
 constexpr int SM_KEYRANGE = 5;               // u64 slot = two u32: max(~key), max(key) of the real depth keys
 constexpr int SM_ERR_WORD = 4;               // int slots start (byte 16)
 constexpr int SM_STRIP = 8;                  // u64 per-strip intersection counts start (byte 64)
@@ -361,11 +366,13 @@ static int bin_prepare_wait(Ctx &c, const Descriptor &d, unsigned long long *I,
     *I = 0;
     *fp = 0;
     c.last_rows = 0;
+    c.last_super = 0;
     if (d.num_points == 0) return 0;
     JSB_CUDA_OK(cudaEventSynchronize(c.ev_ready));
     *fp = c.h_pinned[SM_FP];
     *I = c.h_pinned[SM_TOTAL];
     c.last_rows = c.h_pinned[SM_ROWS];
+    c.last_super = c.h_pinned[SM_SUPER];
     const int *e = (const int *)c.h_pinned + SM_ERR_WORD;
     if (e[0] | e[1] | e[2] | e[3]) {
         set_error("device-side look-back spin limit tripped in an earlier call (flags %d %d %d %d)",
@@ -384,14 +391,42 @@ static int bin_prepare(Ctx &c, const Descriptor &d, const float *xys, const floa
     return bin_prepare_wait(c, d, I, fp);
 }
 
+// the fused render's lists: super-columns of 2^sc tiles (0: not for this descriptor / these options)
+static unsigned want_super(const Descriptor &d) {
+    if (g_sc_shift == 0 || d.block_width != 16 || g_disable_rowcol || g_fwd_batch || g_bwd_no_hits)
+        return 0;
+    return supercols_supported(bin_params(d), g_sc_shift) ? g_sc_shift : 0;
+}
+
 template <typename TileKey>
-static int bin_sort_impl(Ctx &c, const Descriptor &d, unsigned long long I) {
+static int bin_sort_impl(Ctx &c, const Descriptor &d, unsigned long long I, unsigned sc) {
     const unsigned n = d.num_points;
     cudaStream_t s = c.stream;
     const unsigned tiles = d.tiles_x * d.tiles_y;
     // 1. the depth order of the Gaussians was enqueued by bin_prepare_enqueue
     const unsigned *order = c.order_ptr;
+    if (sc) {
+        // two-level distribution into super-column lists of 8-byte row entries
+        const BinParams bp = bin_params(d);
+        const unsigned long long rows = c.last_rows, E = c.last_super;
+        const unsigned supers = (bp.band_y1 - bp.band_y0) * (((d.tiles_x - 1u) >> sc) + 1u);
+        if (c.ensure(c.sbins, (size_t)supers * sizeof(int2))) return 1;
+        if (c.ensure(c.tile_ids, (size_t)E * 8)) return 1;
+        if (c.ensure(c.tile_scratch, rowcol_scratch_bytes(bp, rows, E, sc))) return 1;
+        const Stage stage_of[3] = {ST_EMIT, ST_BIN_EDGES, ST_TILE_SORT};
+        for (int phase = 0; phase < 3; ++phase) {
+            StageScope ss(&c, stage_of[phase]);
+            if (launch_rowcol_lists(s, bp, order, (const uint2 *)c.box_by_id.p, rows, E,
+                                    (unsigned *)c.tile_scratch.p, c.tile_ids.p, (int2 *)c.sbins.p,
+                                    phase, sc))
+                return 1;
+        }
+        c.cache_ids = (unsigned *)c.tile_ids.p;
+        c.cache_bins = (const int2 *)c.sbins.p;
+        return 0;
+    }
     if (c.ensure(c.bins, (size_t)tiles * sizeof(int2))) return 1;
+    c.cache_bins = (const int2 *)c.bins.p;
     if (!g_disable_rowcol && rowcol_supported(bin_params(d))) {
         // two-level in-order distribution (rowcol_lists.cu): rows, then tiles of each row
         const BinParams bp = bin_params(d);
@@ -475,7 +510,8 @@ static int bin_sort_impl(Ctx &c, const Descriptor &d, unsigned long long I) {
 
 static void commit_binning(Ctx &c, const Descriptor &d, unsigned long long I, unsigned long long fp);
 
-static int bin_sort(Ctx &c, const Descriptor &d, unsigned long long I, unsigned long long fp) {
+static int bin_sort(Ctx &c, const Descriptor &d, unsigned long long I, unsigned long long fp,
+                    unsigned sc = 0) {
     if (I >= (1ull << 30)) {
         set_error("num_intersects=%llu exceeds the supported 2^30", I);
         return 1;
@@ -484,9 +520,11 @@ static int bin_sort(Ctx &c, const Descriptor &d, unsigned long long I, unsigned 
     c.cache_valid = false;
     c.cache_has_records = false;
     c.cache_has_hits = false;
-    int rc = tiles <= 65536 ? bin_sort_impl<uint16_t>(c, d, I) : bin_sort_impl<uint32_t>(c, d, I);
+    int rc = tiles <= 65536 ? bin_sort_impl<uint16_t>(c, d, I, sc) : bin_sort_impl<uint32_t>(c, d, I, sc);
     if (rc) return rc;
     commit_binning(c, d, I, fp);
+    c.cache_sc_shift = sc;
+    c.cache_entries = sc ? c.last_super : I;
     return 0;
 }
 
@@ -503,6 +541,8 @@ static void commit_binning(Ctx &c, const Descriptor &d, unsigned long long I, un
     c.cache_bw = d.block_width;
     c.cache_band = d.pad;
     c.cache_I = I;
+    c.cache_sc_shift = 0;
+    c.cache_entries = I;
     g_stats[2].fetch_add(1);
     g_stats[4].store(I);
     g_stats[7].store(c.last_rows);
@@ -511,96 +551,50 @@ static void commit_binning(Ctx &c, const Descriptor &d, unsigned long long I, un
 static bool cache_hit(const Ctx &c, const Descriptor &d, unsigned long long I,
                       unsigned long long fp) {
     return !g_disable_cache && c.cache_valid && c.cache_has_records && c.cache_fp_known &&
-           c.cache_fp == fp && c.cache_I == I &&
+           c.cache_sc_shift == 0 && c.cache_fp == fp && c.cache_I == I &&
            c.cache_n == d.num_points && c.cache_tiles == d.tiles_x * d.tiles_y &&
            c.cache_tiles_x == d.tiles_x && c.cache_bw == d.block_width && c.cache_band == d.pad;
 }
 
-// ---- forward: lists + rasteriser, speculatively sized ------------------------------------------
+// ---- forward: lists + rasteriser ----------------------------------------------------------------
 // Called with the prep (+ fingerprint) kernel, the 64-byte D2H copy, ev_ready and the depth sort
-// already enqueued.  The host needs this frame's intersection count only to size buffers; when the
-// previous frame of the same shape left its counts (training loops render the same scene over and
-// over), the buffers are sized for 1.25x those counts and the list builders and the rasteriser are
-// enqueued BEFORE the host waits for the counts -- the GPU never idles while the host wakes up and
-// issues a dozen launches (a ~30 us depth sort no longer hides that).  Kernels that touch the
-// I- / E-scale buffers check the device-side counts against the capacities first (ListGuard); if
-// the frame outgrew them nothing was written and the host falls back to the exactly sized path.
-// OFF by default: measured neutral at C3 (0.767 vs 0.760 ms) and worse at C2 (0.411 vs 0.348 ms,
-// profiles/r02g_*): with a 40-60 us depth sort enqueued before the wait the host is hidden anyway.
-static bool g_disable_spec = true;  // option "spec" 1: launch before the counts are known
+// already enqueued: the host needs this frame's counts only to size buffers, and the N-scale depth
+// sort keeps the GPU busy while it waits for them.
 static RasterParams raster_params(const Descriptor &d);
+
+// the cached lists' view of a descriptor's raster parameters
+static RasterParams cached_raster_params(const Ctx &c, const Descriptor &d) {
+    RasterParams rp = raster_params(d);
+    rp.sc_shift = c.cache_sc_shift;
+    rp.cols2 = c.cache_sc_shift ? ((d.tiles_x - 1u) >> c.cache_sc_shift) + 1u : 0u;
+    return rp;
+}
 
 static int forward_lists_and_raster(Ctx &c, const Descriptor &d, const float *background,
                                     float *final_Ts, int *final_idx, float *out_img,
-                                    bool fp_known, unsigned long long *token) {
+                                    bool fp_known, unsigned long long *token, bool allow_super) {
     cudaStream_t s = c.stream;
     RasterParams rp = raster_params(d);
     const BinParams bp = bin_params(d);
     const unsigned tiles = d.tiles_x * d.tiles_y;
     if (token) *token = 0;
-    unsigned long long Ip = 0, Ep = 0;
-    bool speculated = false, spec_hits = false;
-    if (!g_disable_spec && c.plan_valid && c.plan_I > 0 && d.num_points != 0 &&
-        c.plan_n == d.num_points && c.plan_tiles_x == d.tiles_x && c.plan_tiles_y == d.tiles_y &&
-        c.plan_bw == d.block_width && c.plan_band == d.pad && d.block_width == 16 &&
-        !g_disable_rowcol && rowcol_supported(bp)) {
-        Ip = c.plan_I + c.plan_I / 4 + 4096;
-        Ep = c.plan_E + c.plan_E / 4 + 4096;
-        if (Ip < (1ull << 30)) {
-            if (c.ensure(c.bins, (size_t)tiles * sizeof(int2)) || c.ensure(c.tile_ids, (size_t)Ip * 4) ||
-                c.ensure(c.tile_scratch, rowcol_scratch_bytes(bp, Ep, Ip)) ||
-                c.ensure(c.hits, hit_words_capacity(Ip, tiles) * 4))
-                return 1;
-            ListGuard guard;
-            guard.totals = (const unsigned long long *)c.small.p;
-            guard.cap_intersects = Ip;
-            guard.cap_row_entries = Ep;
-            c.cache_valid = false;
-            if ((bp.band_y1 - bp.band_y0) != d.tiles_y)
-                JSB_CUDA_OK(cudaMemsetAsync(c.bins.p, 0, (size_t)tiles * sizeof(int2), s));
-            const Stage stage_of[3] = {ST_EMIT, ST_BIN_EDGES, ST_TILE_SORT};
-            for (int phase = 0; phase < 3; ++phase) {
-                StageScope ss(&c, stage_of[phase]);
-                if (launch_rowcol_lists(s, bp, c.order_ptr, (const uint2 *)c.box_by_id.p, Ep, Ip,
-                                        (unsigned *)c.tile_scratch.p, (unsigned *)c.tile_ids.p,
-                                        (int2 *)c.bins.p, phase, guard))
-                    return 1;
-            }
-            {
-                StageScope ss(&c, ST_RASTER_FWD);
-                rp.guard = guard;
-                if (launch_raster_fwd(s, rp, (const unsigned *)c.tile_ids.p, (const int2 *)c.bins.p,
-                                      (const SplatRecord *)c.records.p, background, final_Ts,
-                                      final_idx, out_img, (unsigned *)c.hits.p, &spec_hits))
-                    return 1;
-                rp.guard = ListGuard{};
-            }
-            speculated = true;
-        }
-    }
+    const unsigned sc = allow_super ? want_super(d) : 0;
     unsigned long long I = 0, fp = 0;
     if (bin_prepare_wait(c, d, &I, &fp)) return 1;
-    c.plan_valid = true;
-    c.plan_n = d.num_points; c.plan_tiles_x = d.tiles_x; c.plan_tiles_y = d.tiles_y;
-    c.plan_bw = d.block_width; c.plan_band = d.pad;
-    c.plan_I = I; c.plan_E = c.last_rows;
     if (I == 0) {
         c.cache_valid = false;
         g_stats[4].store(0);
         return launch_fill_background(s, rp, background, final_Ts, final_idx, out_img);
     }
-    if (speculated && I <= Ip && c.last_rows <= Ep) {
-        c.cache_ids = (unsigned *)c.tile_ids.p;
-        c.cache_has_records = false;
-        commit_binning(c, d, I, fp);
-        c.cache_has_hits = spec_hits;
-        g_stats_spec_hits.fetch_add(1);
-    } else {
-        if (speculated) g_stats_spec_redo.fetch_add(1);
-        if (c.ensure(c.hits, hit_words_capacity(I, tiles) * 4)) return 1;
-        if (bin_sort(c, d, I, fp)) return 1;
+    {
+        const size_t hit_words =
+            sc ? hit_words_capacity_super(c.last_super, (bp.band_y1 - bp.band_y0) * (((d.tiles_x - 1u) >> sc) + 1u), sc)
+               : hit_words_capacity(I, tiles);
+        if (c.ensure(c.hits, hit_words * 4)) return 1;
+        if (bin_sort(c, d, I, fp, sc)) return 1;
+        rp = cached_raster_params(c, d);
         StageScope ss(&c, ST_RASTER_FWD);
-        if (launch_raster_fwd(s, rp, c.cache_ids, (const int2 *)c.bins.p,
+        if (launch_raster_fwd(s, rp, c.cache_ids, c.cache_bins,
                               (const SplatRecord *)c.records.p, background, final_Ts, final_idx,
                               out_img, (unsigned *)c.hits.p, &c.cache_has_hits))
             return 1;
@@ -626,6 +620,7 @@ static int project_fwd_locked(Ctx *c, cudaStream_t stream, void **buf, const Des
     p.clip_thresh = d.clip_thresh;
     p.block_width_f = (float)(int)d.block_width;
     p.tiles_x = d.tiles_x; p.tiles_y = d.tiles_y;
+    p.sc_shift = g_sc_shift;
     const size_t chain_bytes = (size_t)ceil_div(n, 256) * 8 + 64;
     if (c->ensure(c->chain, chain_bytes)) return 1;
     StageScope ss(c, ST_PROJECT_FWD);
@@ -718,7 +713,7 @@ static int rasterize_fwd_impl(cudaStream_t stream, void **buf, const Descriptor 
     // the forward always bins afresh (a training loop changes the parameters every step); only
     // the matching backward may reuse this result
     return forward_lists_and_raster(*c, d, (const float *)buf[2], (float *)buf[8], (int *)buf[9],
-                                    (float *)buf[10], /*fp_known=*/true, nullptr);
+                                    (float *)buf[10], /*fp_known=*/true, nullptr, /*allow_super=*/false);
 }
 
 static int rasterize_bwd_impl(cudaStream_t stream, void **buf, const Descriptor &d) {
@@ -758,7 +753,7 @@ static int rasterize_bwd_impl(cudaStream_t stream, void **buf, const Descriptor 
         c->cache_has_records = true;
     }
     StageScope ss(c, ST_RASTER_BWD);
-    return launch_raster_bwd(stream, raster_params(d), c->cache_ids, (const int2 *)c->bins.p,
+    return launch_raster_bwd(stream, cached_raster_params(*c, d), c->cache_ids, c->cache_bins,
                              (const SplatRecord *)c->records.p, (const float *)buf[2],
                              (const float *)buf[8], (const int *)buf[9], (const float *)buf[10],
                              (const float *)buf[11], (float *)buf[14], (float *)buf[15],
@@ -811,7 +806,8 @@ static int render_fwd_impl(cudaStream_t stream, void **buf, const Descriptor &d,
             return 1;
     }
     return forward_lists_and_raster(*c, d, (const float *)buf[6], (float *)buf[13],
-                                    (int *)buf[14], (float *)buf[15], /*fp_known=*/false, token);
+                                    (int *)buf[14], (float *)buf[15], /*fp_known=*/false, token,
+                                    /*allow_super=*/true);
 }
 
 // keep_appearance: v_colors / v_opacity already hold the sum over earlier views of a batched call
@@ -880,14 +876,15 @@ static int render_bwd_impl(cudaStream_t stream, void **buf, const Descriptor &d,
         if (I == 0) {
             empty = true;  // rasterizer gradients stay zero; project_bwd still runs on them
         } else {
-            if (bin_sort(*c, d, I, 0)) return 1;
+            // (the forward's final_idx are positions in the lists want_super() chose: same here)
+            if (bin_sort(*c, d, I, 0, want_super(d))) return 1;
             c->cache_has_records = true;
             c->cache_fp_known = false;
         }
     }
     if (!empty) {
         StageScope ss(c, ST_RASTER_BWD);
-        if (launch_raster_bwd(stream, raster_params(d), c->cache_ids, (const int2 *)c->bins.p,
+        if (launch_raster_bwd(stream, cached_raster_params(*c, d), c->cache_ids, c->cache_bins,
                               (const SplatRecord *)c->records.p, (const float *)buf[6],
                               (const float *)buf[13], (const int *)buf[14], (const float *)buf[15],
                               (const float *)buf[16], (float *)buf[22], v_xy_abs,
@@ -1221,7 +1218,11 @@ int jsb200_set_option(const char *key, int value) {
     if (!strcmp(key, "rowcol")) { jsb::g_disable_rowcol = (value == 0); return 0; }
     if (!strcmp(key, "fwdwarp")) { jsb::g_fwd_batch = (value == 0); return 0; }
     if (!strcmp(key, "bwdmom")) { jsb::g_bwd_no_moments = (value == 0); return 0; }
-    if (!strcmp(key, "spec")) { jsb::g_disable_spec = (value == 0); return 0; }
+    if (!strcmp(key, "supercols")) {
+        if (value < 0 || value > 6) { jsb::set_error("set_option: supercols must be 0..6"); return 1; }
+        jsb::g_sc_shift = (unsigned)value;
+        return 0;
+    }
     if (!strcmp(key, "bwdhits")) {
         jsb::g_bwd_no_hits = (value == 0);
         jsb::g_bwd_all_entries = (value == 2);
@@ -1246,6 +1247,7 @@ long long jsb200_debug_binning(jsb200_stream_t stream_, const float *depths, int
         if (!c) return -1;
         std::lock_guard<std::mutex> lk(c->mu);
         if (!c->cache_valid) { jsb::set_error("debug_binning: no binning cached on this stream"); return -1; }
+        if (c->cache_sc_shift) { jsb::set_error("debug_binning: the cached lists are super-column lists (option supercols)"); return -1; }
         const size_t I = c->cache_I;
         if (ids_sorted && cudaMemcpyAsync(ids_sorted, c->cache_ids, I * 4, cudaMemcpyDeviceToDevice, stream) != cudaSuccess) return -1;
         if (tile_bins && cudaMemcpyAsync(tile_bins, c->bins.p, (size_t)c->cache_tiles * 8, cudaMemcpyDeviceToDevice, stream) != cudaSuccess) return -1;
@@ -1269,6 +1271,7 @@ long long jsb200_debug_hit_words(jsb200_stream_t stream_, unsigned *out_words, s
             jsb::set_error("debug_hit_words: no hit words cached on this stream");
             return -1;
         }
+        if (c->cache_sc_shift) { jsb::set_error("debug_hit_words: the cached lists are super-column lists (option supercols)"); return -1; }
         const size_t words = jsb::hit_words_capacity(c->cache_I, c->cache_tiles);
         if (out_words && cudaMemcpyAsync(out_words, c->hits.p, std::min(words, max_words) * 4,
                                          cudaMemcpyDeviceToDevice, stream) != cudaSuccess)
@@ -1313,12 +1316,6 @@ int jsb200_get_stage_times(jsb200_stream_t stream_, double *ms_out9, unsigned lo
         jsb::set_error("get_stage_times: exception");
         return 1;
     }
-}
-
-void jsb200_get_speculation_stats(unsigned long long *out2) {
-    if (!out2) return;
-    out2[0] = jsb::g_stats_spec_hits.load();
-    out2[1] = jsb::g_stats_spec_redo.load();
 }
 
 void jsb200_get_stats(unsigned long long *out8) {

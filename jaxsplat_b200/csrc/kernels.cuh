@@ -13,6 +13,7 @@ struct ProjectFwdParams {
     float clip_thresh;
     float block_width_f;  // (float)(int)block_width
     unsigned tiles_x, tiles_y;
+    unsigned sc_shift = 0;  // fused prep: log2 of the tiles per super-column counted into totals[6]
 };
 
 struct ProjectBwdParams {
@@ -24,8 +25,9 @@ struct ProjectBwdParams {
 struct SplatRecord;
 // Fused render, full-frame band: project_fwd also produces what bin_prep would (binning.cu):
 // records, depth keys (0xFFFFFFFF for radii <= 0), identity ids, tile boxes, adds the
-// intersection / row-entry totals to totals[1] / totals[4] and folds the range of the real depth
-// keys into the two u32 words of totals[5]: {max(~key), max(key)} (both 0 = no real key).
+// intersection / row-entry totals to totals[1] / totals[4], the (row entry, super-column) pairs to
+// totals[6], and folds the range of the real depth keys into the two u32 words of totals[5]:
+// {max(~key), max(key)} (both 0 = no real key).
 struct FusedPrep {
     const float *colors = nullptr, *opacities = nullptr;
     SplatRecord *records = nullptr;
@@ -63,27 +65,13 @@ struct __align__(16) SplatRecord {
     float4 q0, q1, q2;
 };
 
-// Speculative launches (capi.cu): the list builders and the forward rasteriser may be enqueued
-// before the host knows this frame's intersection / row-entry counts, with buffers sized from the
-// previous frame's counts.  The kernels that touch those buffers first compare the counts the
-// prep kernel left on the device (totals[1] = intersections, totals[4] = row entries) with the
-// capacities they were launched for, and do nothing at all if either is exceeded -- the host then
-// rebuilds with exact sizes.  totals == nullptr: no check.
-struct ListGuard {
-    const unsigned long long *totals = nullptr;
-    unsigned long long cap_intersects = 0, cap_row_entries = 0;
-};
-__device__ __forceinline__ bool guard_trips(const ListGuard &g) {
-    return g.totals != nullptr &&
-           (__ldg(g.totals + 1) > g.cap_intersects || __ldg(g.totals + 4) > g.cap_row_entries);
-}
-
 struct BinParams {
     unsigned num_points;
     float block_width_f;
     unsigned tiles_x, tiles_y;
     unsigned band_y0, band_y1;  // tile rows [band_y0, band_y1) this call owns (full frame: 0, tiles_y)
     unsigned strip_rows;        // the band is binned in strips of this many tile rows (tile_lists.cu)
+    unsigned sc_shift = 0;      // prep: log2 of the tiles per super-column counted into fingerprint[6]
 };
 
 constexpr unsigned kMaxStrips = 256;
@@ -146,13 +134,18 @@ int launch_tile_scatter(cudaStream_t stream, const BinParams &p, unsigned chunks
 // Same result as box_gather + emit + tile_offsets + tile_scatter for bands of <= 256 tile rows
 // and <= 512 tiles per row.  row_entries = sum of the band-clamped box heights (bin_prep counts
 // it), phase 0 = row lists, 1 = run starts + tile_bins of the band, 2 = ids_sorted.
+// sc_shift > 0 (fused render, super-column lists): level 2 distributes the 8-byte row entries
+// {id, x0 | w << 16} into super-columns of 2^sc_shift tiles instead of ids into tiles;
+// num_intersects is then the number of (row entry, super-column) pairs, ids_sorted a uint2 array
+// of that many entries and tile_bins a band-local (rows x ceil(tiles_x / 2^sc_shift)) array.
 bool rowcol_supported(const BinParams &p);
+bool supercols_supported(const BinParams &p, unsigned sc_shift);
 size_t rowcol_scratch_bytes(const BinParams &p, unsigned long long row_entries,
-                            unsigned long long num_intersects);
+                            unsigned long long num_intersects, unsigned sc_shift = 0);
 int launch_rowcol_lists(cudaStream_t stream, const BinParams &p, const unsigned *order,
                         const uint2 *box_by_id, unsigned long long row_entries,
-                        unsigned long long num_intersects, unsigned *scratch, unsigned *ids_sorted,
-                        int2 *tile_bins, int phase, const ListGuard &guard = ListGuard{});
+                        unsigned long long num_intersects, unsigned *scratch, void *ids_sorted,
+                        int2 *tile_bins, int phase, unsigned sc_shift = 0);
 
 // optional debug/parity helper: rebuild the reference's sorted 64-bit keys (tile<<32 | depth bits)
 int launch_rebuild_keys64(cudaStream_t stream, const int2 *tile_bins, unsigned num_tiles,
@@ -185,18 +178,22 @@ struct RasterParams {
     unsigned tiles_x, tiles_y;
     unsigned block_width;
     unsigned band_y0, band_y1;  // tile rows rasterised by this call (screen-tile-row sharding)
-    ListGuard guard;            // forward only: speculative launch (see ListGuard)
+    // sc_shift > 0 (fused render, block_width 16): `ids_sorted` is a uint2 array of row entries
+    // {id, x0 | w << 16} listed per super-column of 2^sc_shift tiles, `tile_bins` the band-local
+    // (rows x cols2) ranges of those lists (rowcol_lists.cu), final_idx positions in them, and the
+    // hit words follow hit_quadrant_offset_super; a tile keeps the entries whose columns cover it
+    unsigned sc_shift = 0, cols2 = 0;
 };
 
 // hit_words (may be null): the forward records which list entries each 8x8 quadrant accepted
 // (raster_hits.cuh; hit_words_capacity(I, tiles) words); *wrote_hits says whether the kernel that
 // ran does (only the default 16x16 two-pixel kernel).
-int launch_raster_fwd(cudaStream_t stream, const RasterParams &p, const unsigned *ids_sorted,
+int launch_raster_fwd(cudaStream_t stream, const RasterParams &p, const void *ids_sorted,
                       const int2 *tile_bins, const SplatRecord *records, const float *background,
                       float *final_Ts, int *final_idx, float *out_img,
                       unsigned *hit_words = nullptr, bool *wrote_hits = nullptr);
 
-int launch_raster_bwd(cudaStream_t stream, const RasterParams &p, const unsigned *ids_sorted,
+int launch_raster_bwd(cudaStream_t stream, const RasterParams &p, const void *ids_sorted,
                       const int2 *tile_bins, const SplatRecord *records, const float *background,
                       const float *final_Ts, const int *final_idx, const float *v_out,
                       const float *v_out_alpha, float *v_xy, float *v_xy_abs, float *v_conic,

@@ -205,7 +205,7 @@ project_fwd_kernel(const ProjectFwdParams p, const float *__restrict__ means3d,
                    unsigned *__restrict__ block_totals, const FusedPrep f) {
     __shared__ __align__(16) float s_strip[PT / 32][kWarpStripFloats];
     __shared__ unsigned s_ws[PT / 32 + 1];
-    __shared__ unsigned s_tot[PT / 32][4];
+    __shared__ unsigned s_tot[PT / 32][5];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned bid = blockIdx.x;
     const long long idx = (long long)bid * PT + tid;
@@ -234,7 +234,7 @@ project_fwd_kernel(const ProjectFwdParams p, const float *__restrict__ means3d,
         }
         o = project_one(mx, my, mz, sx, sy, sz, q, viewmat, p);
     }
-    unsigned rows = 0, kinv = 0, kmax = 0;
+    unsigned rows = 0, sup = 0, kinv = 0, kmax = 0;
     if (FUSED) {
         unsigned key = 0xFFFFFFFFu;
         uint2 box = make_uint2(0u, 0u);  // {x0 | y0 << 16, width | height << 16}
@@ -245,6 +245,8 @@ project_fwd_kernel(const ProjectFwdParams p, const float *__restrict__ means3d,
                       x0, x1, y0, y1);
             if (y1 > y0 && x1 > x0) {
                 rows = y1 - y0;
+                // (row entry, super-column) pairs: the level-2 output of the super-column lists
+                sup = rows * (((x1 - 1u) >> p.sc_shift) - (x0 >> p.sc_shift) + 1u);
                 box = make_uint2(x0 | (y0 << 16), (x1 - x0) | ((y1 - y0) << 16));
             }
             key = __float_as_uint(o.depth);
@@ -293,21 +295,26 @@ project_fwd_kernel(const ProjectFwdParams p, const float *__restrict__ means3d,
         // the L2 and were measured as the kernel's critical path)
         const unsigned tiles = __reduce_add_sync(0xffffffffu, (unsigned)o.tiles);
         rows = __reduce_add_sync(0xffffffffu, rows);
+        sup = __reduce_add_sync(0xffffffffu, sup);
         kinv = __reduce_max_sync(0xffffffffu, kinv);
         kmax = __reduce_max_sync(0xffffffffu, kmax);
-        if (lane == 0) { s_tot[warp][0] = tiles; s_tot[warp][1] = rows; s_tot[warp][2] = kinv; s_tot[warp][3] = kmax; }
+        if (lane == 0) {
+            s_tot[warp][0] = tiles; s_tot[warp][1] = rows; s_tot[warp][2] = kinv; s_tot[warp][3] = kmax;
+            s_tot[warp][4] = sup;
+        }
         __syncthreads();
         if (tid == 0) {
-            unsigned long long t0 = 0, t1 = 0;
+            unsigned long long t0 = 0, t1 = 0, t2 = 0;
             unsigned m0 = 0, m1 = 0;
 #pragma unroll
             for (int w = 0; w < PT / 32; ++w) {
-                t0 += s_tot[w][0]; t1 += s_tot[w][1];
+                t0 += s_tot[w][0]; t1 += s_tot[w][1]; t2 += s_tot[w][4];
                 m0 = max(m0, s_tot[w][2]); m1 = max(m1, s_tot[w][3]);
             }
             if (t0) {
                 atomicAdd(f.totals + 1, t0);
                 atomicAdd(f.totals + 4, t1);
+                atomicAdd(f.totals + 6, t2);
             }
             if (m0 | m1) {  // range of the real depth keys: [~max(~key), max(key)]
                 unsigned *mm = reinterpret_cast<unsigned *>(f.totals + 5);

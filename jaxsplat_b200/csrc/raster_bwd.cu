@@ -381,9 +381,11 @@ struct HbStage {      // one sub-chunk of <= 32 visits
 // the conic and the opacity of the Gaussian in registers anyway, turns them into the gradients
 //   v_opacity = M0 / opacity, v_xy = -(cx Mx + cy My, cy Mx + cz My), v_conic = -(Mxx/2, Mxy, Myy/2)
 // (project.cu: FINISH_MOMENTS) -- five packed multiplies per visit instead of eleven.
-template <bool ABS, bool MOMENTS>
+// SUPER: super-column lists (RasterParams::sc_shift); with all_entries the entries whose tile
+// columns do not cover the tile are skipped like the forward skips them.
+template <bool ABS, bool MOMENTS, bool SUPER>
 __global__ void __launch_bounds__(32, JSB_BWDH_CTAS)
-raster_bwd_hits_kernel(const RasterParams p, const unsigned *__restrict__ ids_sorted,
+raster_bwd_hits_kernel(const RasterParams p, const void *__restrict__ list,
                        const int2 *__restrict__ tile_bins, const SplatRecord *__restrict__ records,
                        const unsigned *__restrict__ hit_words, const bool all_entries,
                        const float *__restrict__ background, const float *__restrict__ final_Ts,
@@ -404,7 +406,10 @@ raster_bwd_hits_kernel(const RasterParams p, const unsigned *__restrict__ ids_so
     const unsigned i0 = tile_y * 16 + (quad >> 1) * 8 + (lane >> 3), i1 = i0 + 4;
     const float px = (float)j + 0.5f, py0 = (float)i0 + 0.5f, py1 = (float)i1 + 0.5f;
     const bool in0 = (i0 < p.img_h) && (j < p.img_w), in1 = (i1 < p.img_h) && (j < p.img_w);
-    const int2 range = tile_bins[tile];
+    const unsigned *ids_sorted = reinterpret_cast<const unsigned *>(list);
+    const uint2 *ents = reinterpret_cast<const uint2 *>(list);
+    const unsigned super_local = (tile_y - p.band_y0) * p.cols2 + (tile_x >> p.sc_shift);
+    const int2 range = tile_bins[SUPER ? super_local : tile];
 
     float Tf0 = 1.f, Tf1 = 1.f, voa0 = 0.f, voa1 = 0.f;
     float3 vo0 = make_float3(0.f, 0.f, 0.f), vo1 = vo0;
@@ -470,7 +475,9 @@ raster_bwd_hits_kernel(const RasterParams p, const unsigned *__restrict__ ids_so
         return u0.x + u0.y;
     };
 
-    const unsigned *hw = hit_words + hit_quadrant_offset(range, tile_local, quad);
+    const unsigned *hw = hit_words + (SUPER
+        ? hit_quadrant_offset_super(range, super_local, tile_x & ((1u << p.sc_shift) - 1u), quad, p.sc_shift)
+        : hit_quadrant_offset(range, tile_local, quad));
     const int rel_top = top - range.x;
     for (int gs = rel_top >> 5; gs >= 0; gs -= HB_SPAN) {
         // ---- expand this span's hit words into visit positions, newest first -------------------
@@ -513,21 +520,33 @@ raster_bwd_hits_kernel(const RasterParams p, const unsigned *__restrict__ ids_so
             }
         };
         const int nsub = (total + 31) >> 5;
-        int sidx_n = lane < total ? sorted_index(lane) : 0;
-        unsigned gid_n = lane < total ? ids_sorted[sidx_n] : 0u;
+        // visit o of the span: its sorted index and Gaussian id (a super-column entry that does not
+        // cover this tile -- only met when every entry is replayed -- gets an index no pixel reaches)
+        int sidx_n = 0;
+        unsigned gid_n = 0u;
+        auto fetch = [&](int o) {
+            sidx_n = 0;
+            gid_n = 0u;
+            if (o < total) {
+                sidx_n = sorted_index(o);
+                if (SUPER) {
+                    const uint2 e = __ldg(ents + sidx_n);
+                    gid_n = e.x;
+                    if (all_entries && !((tile_x - (e.y & 0xffffu)) < (e.y >> 16))) sidx_n = 0x7fffffff;
+                } else {
+                    gid_n = ids_sorted[sidx_n];
+                }
+            }
+        };
+        fetch(lane);
         issue(0, sidx_n, gid_n);
-        sidx_n = 32 + lane < total ? sorted_index(32 + lane) : 0;
-        gid_n = 32 + lane < total ? ids_sorted[sidx_n] : 0u;
+        fetch(32 + lane);
 
         for (int s = 0; s < nsub; ++s) {
             cp_async_wait_all();
             __syncwarp();  // sub-chunk s landed; every lane is done with sub-chunk s - 1
             if (s + 1 < nsub) issue(s + 1, sidx_n, gid_n);
-            {
-                const int o = (s + 2) * 32 + lane;
-                sidx_n = o < total ? sorted_index(o) : 0;
-                gid_n = o < total ? ids_sorted[sidx_n] : 0u;
-            }
+            fetch((s + 2) * 32 + lane);
             const HbStage &S = st[s & 1];
             const int cs = min(32, total - s * 32);
 #pragma unroll 1
@@ -697,29 +716,52 @@ static void launch_x2(cudaStream_t stream, unsigned tiles, const RasterParams &p
 }
 
 // v_xy_abs == nullptr: not computed (fused render; block_width 16 only)
-int launch_raster_bwd(cudaStream_t stream, const RasterParams &p, const unsigned *ids_sorted,
+int launch_raster_bwd(cudaStream_t stream, const RasterParams &p, const void *list,
                       const int2 *tile_bins, const SplatRecord *records, const float *background,
                       const float *final_Ts, const int *final_idx, const float *v_out,
                       const float *v_out_alpha, float *v_xy, float *v_xy_abs, float *v_conic,
                       float *v_colors, float *v_opacity, const unsigned *hit_words,
                       bool *moments_out) {
     const unsigned tiles = p.tiles_x * (p.band_y1 - p.band_y0);
+    const unsigned *ids_sorted = reinterpret_cast<const unsigned *>(list);
     if (moments_out) *moments_out = false;
     if (tiles == 0) return 0;
     if (g_bwd_no_moments) moments_out = nullptr;
-    if (p.block_width == 16 && hit_words && !g_bwd_no_hits) {
-        // one independent warp per quadrant, driven by the forward's hit words
+    if (p.sc_shift && p.block_width != 16) {
+        set_error("raster_bwd: super-column lists need block_width 16");
+        return 1;
+    }
+    if (p.sc_shift) {
+        // super-column lists (fused render): always the hit-driven kernel; without hit words (the
+        // backward rebuilt the lists itself) it replays every entry of the quadrant's range
+        const bool all = g_bwd_all_entries || hit_words == nullptr;
+        const unsigned *hw = hit_words ? hit_words : reinterpret_cast<const unsigned *>(list);  // (not read)
         if (v_xy_abs)
-            raster_bwd_hits_kernel<true, false><<<tiles * 4, 32, 0, stream>>>(
-                p, ids_sorted, tile_bins, records, hit_words, g_bwd_all_entries, background, final_Ts, final_idx, v_out,
+            raster_bwd_hits_kernel<true, false, true><<<tiles * 4, 32, 0, stream>>>(
+                p, list, tile_bins, records, hw, all, background, final_Ts, final_idx, v_out,
                 v_out_alpha, v_xy, v_xy_abs, v_conic, v_colors, v_opacity);
         else if (moments_out)
-            raster_bwd_hits_kernel<false, true><<<tiles * 4, 32, 0, stream>>>(
-                p, ids_sorted, tile_bins, records, hit_words, g_bwd_all_entries, background, final_Ts, final_idx, v_out,
+            raster_bwd_hits_kernel<false, true, true><<<tiles * 4, 32, 0, stream>>>(
+                p, list, tile_bins, records, hw, all, background, final_Ts, final_idx, v_out,
                 v_out_alpha, v_xy, v_xy_abs, v_conic, v_colors, v_opacity);
         else
-            raster_bwd_hits_kernel<false, false><<<tiles * 4, 32, 0, stream>>>(
-                p, ids_sorted, tile_bins, records, hit_words, g_bwd_all_entries, background, final_Ts, final_idx, v_out,
+            raster_bwd_hits_kernel<false, false, true><<<tiles * 4, 32, 0, stream>>>(
+                p, list, tile_bins, records, hw, all, background, final_Ts, final_idx, v_out,
+                v_out_alpha, v_xy, v_xy_abs, v_conic, v_colors, v_opacity);
+        if (moments_out) *moments_out = !v_xy_abs;
+    } else if (p.block_width == 16 && hit_words && !g_bwd_no_hits) {
+        // one independent warp per quadrant, driven by the forward's hit words
+        if (v_xy_abs)
+            raster_bwd_hits_kernel<true, false, false><<<tiles * 4, 32, 0, stream>>>(
+                p, list, tile_bins, records, hit_words, g_bwd_all_entries, background, final_Ts, final_idx, v_out,
+                v_out_alpha, v_xy, v_xy_abs, v_conic, v_colors, v_opacity);
+        else if (moments_out)
+            raster_bwd_hits_kernel<false, true, false><<<tiles * 4, 32, 0, stream>>>(
+                p, list, tile_bins, records, hit_words, g_bwd_all_entries, background, final_Ts, final_idx, v_out,
+                v_out_alpha, v_xy, v_xy_abs, v_conic, v_colors, v_opacity);
+        else
+            raster_bwd_hits_kernel<false, false, false><<<tiles * 4, 32, 0, stream>>>(
+                p, list, tile_bins, records, hit_words, g_bwd_all_entries, background, final_Ts, final_idx, v_out,
                 v_out_alpha, v_xy, v_xy_abs, v_conic, v_colors, v_opacity);
         if (moments_out) *moments_out = !v_xy_abs;
     } else if (p.block_width == 16) {

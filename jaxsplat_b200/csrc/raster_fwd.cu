@@ -74,7 +74,6 @@ raster_fwd16x2_kernel(const RasterParams p, const unsigned *__restrict__ ids_sor
     bool done0 = !in0, done1 = !in1;
     const int qbit = (warp & 1) + 4 * (warp >> 1);  // quadrant bit of the row-folded cull mask
 
-    if (guard_trips(p.guard)) return;  // speculative launch whose lists were not built
     const int2 range = tile_bins[tile];
     const int num_batches = (range.y - range.x + BATCH - 1) / BATCH;
     const float tile_x0 = (float)(tile_x * 16), tile_y0 = (float)(tile_y * 16);
@@ -243,9 +242,11 @@ struct FwSlot {          // one compacted candidate
     float4 B;            // conic.y, conic.z, r, g
 };
 
-template <bool CULL>
+// SUPER: the list is a super-column's (RasterParams::sc_shift): 8-byte row entries, of which the
+// tile keeps those whose tile columns cover it -- exactly the tile's own list, in the same order.
+template <bool CULL, bool SUPER>
 __global__ void __launch_bounds__(RF2, JSB_FWD_CTAS)
-raster_fwd_warp_kernel(const RasterParams p, const unsigned *__restrict__ ids_sorted,
+raster_fwd_warp_kernel(const RasterParams p, const void *__restrict__ list,
                        const int2 *__restrict__ tile_bins, const SplatRecord *__restrict__ records,
                        const float *__restrict__ background, float *__restrict__ final_Ts,
                        int *__restrict__ final_idx, float *__restrict__ out_img,
@@ -261,24 +262,35 @@ raster_fwd_warp_kernel(const RasterParams p, const unsigned *__restrict__ ids_so
     const float px = (float)j + 0.5f, py0 = (float)i0 + 0.5f, py1 = (float)i1 + 0.5f;
     const bool in0 = (i0 < p.img_h) && (j < p.img_w), in1 = (i1 < p.img_h) && (j < p.img_w);
     bool done0 = !in0, done1 = !in1;
-    if (guard_trips(p.guard)) return;  // speculative launch whose lists were not built
-    const int2 range = tile_bins[tile];
+    const unsigned *ids_sorted = reinterpret_cast<const unsigned *>(list);
+    const uint2 *ents = reinterpret_cast<const uint2 *>(list);
+    const unsigned super_local = (tile_y - p.band_y0) * p.cols2 + (tile_x >> p.sc_shift);
+    const int2 range = tile_bins[SUPER ? super_local : tile];
     const int ngroups = (range.y - range.x + 31) >> 5;
     const float tile_x0 = (float)(tile_x * 16), tile_y0 = (float)(tile_y * 16);
     const float quad_x0 = tile_x0 + (float)((warp & 1) * 8), quad_y0 = tile_y0 + (float)((warp >> 1) * 8);
-    const unsigned hw_off = (unsigned)hit_quadrant_offset(range, blockIdx.x, (unsigned)warp);
+    const unsigned hw_off = SUPER
+        ? (unsigned)hit_quadrant_offset_super(range, super_local, tile_x & ((1u << p.sc_shift) - 1u),
+                                              (unsigned)warp, p.sc_shift)
+        : (unsigned)hit_quadrant_offset(range, blockIdx.x, (unsigned)warp);
     const unsigned lt_mask = (1u << lane) - 1u;
     FwSlot *slot = s_slot[warp];
     float2 *sc = s_c[warp];
 
-    float T0 = 1.f, T1 = 1.f;
+    // {pixel 0, pixel 1} pairs: transmittance and the three colour sums
+    float2 T2 = make_float2(1.f, 1.f);
+    float2 R2 = make_float2(0.f, 0.f), G2 = R2, B2 = R2;
     int cur0 = 0, cur1 = 0;
-    float r0 = 0.f, g0 = 0.f, b0 = 0.f, r1 = 0.f, g1 = 0.f, b1 = 0.f;
 
     // software pipeline: records of group g in registers, records of g + 1 and ids of g + 2 in flight
     auto load_id = [&](int g) -> unsigned {
         const int idx = range.x + 32 * g + lane;
-        return (g < ngroups && idx < range.y) ? ids_sorted[idx] : 0xFFFFFFFFu;
+        if (!(g < ngroups && idx < range.y)) return 0xFFFFFFFFu;
+        if (SUPER) {  // the entry's tile columns [x0, x0 + w) must cover this tile
+            const uint2 e = __ldg(ents + idx);
+            return (tile_x - (e.y & 0xffffu)) < (e.y >> 16) ? e.x : 0xFFFFFFFFu;
+        }
+        return ids_sorted[idx];
     };
     float4 qa = make_float4(0.f, 0.f, 0.f, 0.f), qb = qa;
     float qc = 0.f;
@@ -339,40 +351,35 @@ raster_fwd_warp_kernel(const RasterParams p, const unsigned *__restrict__ ids_so
                 const float2 x2 = __fmul2_rn(sg2, make_float2(kNegLog2e, kNegLog2e));
                 const float2 ar2 = __fmul2_rn(make_float2(a.z, a.z),
                                               make_float2(ex2_approx(x2.x), ex2_approx(x2.y)));
-                const float al0 = fminf(ar2.x, 0.999f), al1 = fminf(ar2.y, 0.999f);
-                const bool ok0 = !done0 && !(sg2.x < 0.f) && !(al0 < kAlphaMin);
-                const bool ok1 = !done1 && !(sg2.y < 0.f) && !(al1 < kAlphaMin);
-                if (ok0 || ok1) {
-                    const float2 cq = sc[t];
-                    const int sidx = __float_as_int(cq.y);
-                    hit |= __funnelshift_l(0u, 1u, (unsigned)(sidx - range.x));  // 1 << (rel & 31)
-                    if (ok0) {
-                        const float next_T = fmul(T0, fsub(1.f, al0));
-                        if (next_T <= kTmin) {
-                            done0 = true;  // this Gaussian is not composited
-                        } else {
-                            const float vis = fmul(T0, al0);
-                            r0 = ffma(vis, bq.z, r0);
-                            g0 = ffma(vis, bq.w, g0);
-                            b0 = ffma(vis, cq.x, b0);
-                            T0 = next_T;
-                            cur0 = sidx;
-                        }
-                    }
-                    if (ok1) {
-                        const float next_T = fmul(T1, fsub(1.f, al1));
-                        if (next_T <= kTmin) {
-                            done1 = true;
-                        } else {
-                            const float vis = fmul(T1, al1);
-                            r1 = ffma(vis, bq.z, r1);
-                            g1 = ffma(vis, bq.w, g1);
-                            b1 = ffma(vis, cq.x, b1);
-                            T1 = next_T;
-                            cur1 = sidx;
-                        }
-                    }
-                }
+                const float2 al2 = make_float2(fminf(ar2.x, 0.999f), fminf(ar2.y, 0.999f));
+                const bool ok0 = !done0 && !(sg2.x < 0.f) && !(al2.x < kAlphaMin);
+                const bool ok1 = !done1 && !(sg2.y < 0.f) && !(al2.y < kAlphaMin);
+                // Branch-free compositing of both pixels (the four nested data-dependent branches
+                // of the scalar form cost more issue slots in BSSY / BSYNC / BRA than the work they
+                // skip): next_T = T (1 - alpha) and vis = T alpha are evaluated for every lane with
+                // the reference's operations (1 - alpha as fma(alpha, -1, 1): one rounding of the
+                // exact difference, like the subtraction), and a pixel that does not composite
+                // this Gaussian -- rejected, saturated, or stopped by it -- gets
+                // vis = 0, which leaves its sums unchanged to the bit, and keeps its T.
+                const float2 cq = sc[t];
+                const int sidx = __float_as_int(cq.y);
+                const float2 om2 = __ffma2_rn(al2, make_float2(-1.f, -1.f), make_float2(1.f, 1.f));
+                const float2 nT2 = __fmul2_rn(T2, om2);
+                float2 vis2 = __fmul2_rn(T2, al2);
+                const bool stop0 = ok0 && (nT2.x <= kTmin), stop1 = ok1 && (nT2.y <= kTmin);
+                const bool upd0 = ok0 && !(nT2.x <= kTmin), upd1 = ok1 && !(nT2.y <= kTmin);
+                vis2.x = upd0 ? vis2.x : 0.f;
+                vis2.y = upd1 ? vis2.y : 0.f;
+                R2 = __ffma2_rn(vis2, make_float2(bq.z, bq.z), R2);
+                G2 = __ffma2_rn(vis2, make_float2(bq.w, bq.w), G2);
+                B2 = __ffma2_rn(vis2, make_float2(cq.x, cq.x), B2);
+                T2.x = upd0 ? nT2.x : T2.x;
+                T2.y = upd1 ? nT2.y : T2.y;
+                cur0 = upd0 ? sidx : cur0;
+                cur1 = upd1 ? sidx : cur1;
+                done0 = done0 || stop0;
+                done1 = done1 || stop1;
+                hit |= (ok0 || ok1) ? __funnelshift_l(0u, 1u, (unsigned)(sidx - range.x)) : 0u;  // 1 << (rel & 31)
             }
             __syncwarp();  // the slots are free again
         }
@@ -386,19 +393,19 @@ raster_fwd_warp_kernel(const RasterParams p, const unsigned *__restrict__ ids_so
     const float bg0 = __ldg(background), bg1 = __ldg(background + 1), bg2 = __ldg(background + 2);
     if (in0) {
         const size_t pix = (size_t)i0 * p.img_w + j;
-        final_Ts[pix] = T0;
+        final_Ts[pix] = T2.x;
         final_idx[pix] = cur0;
-        out_img[pix * 3 + 0] = ffma(T0, bg0, r0);
-        out_img[pix * 3 + 1] = ffma(T0, bg1, g0);
-        out_img[pix * 3 + 2] = ffma(T0, bg2, b0);
+        out_img[pix * 3 + 0] = ffma(T2.x, bg0, R2.x);
+        out_img[pix * 3 + 1] = ffma(T2.x, bg1, G2.x);
+        out_img[pix * 3 + 2] = ffma(T2.x, bg2, B2.x);
     }
     if (in1) {
         const size_t pix = (size_t)i1 * p.img_w + j;
-        final_Ts[pix] = T1;
+        final_Ts[pix] = T2.y;
         final_idx[pix] = cur1;
-        out_img[pix * 3 + 0] = ffma(T1, bg0, r1);
-        out_img[pix * 3 + 1] = ffma(T1, bg1, g1);
-        out_img[pix * 3 + 2] = ffma(T1, bg2, b1);
+        out_img[pix * 3 + 0] = ffma(T2.y, bg0, R2.y);
+        out_img[pix * 3 + 1] = ffma(T2.y, bg1, G2.y);
+        out_img[pix * 3 + 2] = ffma(T2.y, bg2, B2.y);
     }
 }
 
@@ -486,21 +493,34 @@ __global__ void fill_background_kernel(const float *__restrict__ background, siz
 bool g_disable_cull = false;  // test hook (capi: jsb200_set_option)
 bool g_fwd_batch = false;     // option "fwdwarp" = 0: the per-CTA batch kernel instead of the barrier-free one
 
-int launch_raster_fwd(cudaStream_t stream, const RasterParams &p, const unsigned *ids_sorted,
+int launch_raster_fwd(cudaStream_t stream, const RasterParams &p, const void *list,
                       const int2 *tile_bins, const SplatRecord *records, const float *background,
                       float *final_Ts, int *final_idx, float *out_img, unsigned *hit_words,
                       bool *wrote_hits) {
     const unsigned tiles = p.tiles_x * (p.band_y1 - p.band_y0);
+    const unsigned *ids_sorted = reinterpret_cast<const unsigned *>(list);
     if (wrote_hits) *wrote_hits = false;
     if (tiles == 0) return 0;
-    if (p.block_width == 16 && !g_fwd_batch) {
+    if (p.sc_shift && (p.block_width != 16 || g_fwd_batch)) {
+        set_error("raster_fwd: super-column lists need the block_width 16 warp kernel");
+        return 1;
+    }
+    if (p.sc_shift) {
         if (wrote_hits) *wrote_hits = hit_words != nullptr;
         if (g_disable_cull)
-            raster_fwd_warp_kernel<false><<<tiles, RF2, 0, stream>>>(
-                p, ids_sorted, tile_bins, records, background, final_Ts, final_idx, out_img, hit_words);
+            raster_fwd_warp_kernel<false, true><<<tiles, RF2, 0, stream>>>(
+                p, list, tile_bins, records, background, final_Ts, final_idx, out_img, hit_words);
         else
-            raster_fwd_warp_kernel<true><<<tiles, RF2, 0, stream>>>(
-                p, ids_sorted, tile_bins, records, background, final_Ts, final_idx, out_img, hit_words);
+            raster_fwd_warp_kernel<true, true><<<tiles, RF2, 0, stream>>>(
+                p, list, tile_bins, records, background, final_Ts, final_idx, out_img, hit_words);
+    } else if (p.block_width == 16 && !g_fwd_batch) {
+        if (wrote_hits) *wrote_hits = hit_words != nullptr;
+        if (g_disable_cull)
+            raster_fwd_warp_kernel<false, false><<<tiles, RF2, 0, stream>>>(
+                p, list, tile_bins, records, background, final_Ts, final_idx, out_img, hit_words);
+        else
+            raster_fwd_warp_kernel<true, false><<<tiles, RF2, 0, stream>>>(
+                p, list, tile_bins, records, background, final_Ts, final_idx, out_img, hit_words);
     } else if (p.block_width == 16) {
         if (wrote_hits) *wrote_hits = hit_words != nullptr;
         if (g_disable_cull)

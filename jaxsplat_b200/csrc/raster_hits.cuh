@@ -30,4 +30,21 @@ __device__ __forceinline__ size_t hit_quadrant_offset(const int2 range, unsigned
     return 4 * ((size_t)g0 + tile_local) + (size_t)quad * cap;
 }
 
+// Super-column lists (fused render): the list belongs to a super-column of T = 2^shift tiles of
+// one tile row, and each of its T tiles keeps its own four quadrant slices of the same length:
+// super-tile s (band-local index) with list range [x, y) owns 4 T cap words starting at word
+// 4 T ((x >> 5) + s); tile t of the super-column, quadrant q: [(4 t + q) cap, (4 t + q) cap + cap).
+__host__ __device__ inline size_t hit_words_capacity_super(unsigned long long entries, unsigned supers,
+                                                           unsigned shift) {
+    return (size_t)(4u << shift) * ((size_t)(entries >> 5) + supers + 1);
+}
+
+__device__ __forceinline__ size_t hit_quadrant_offset_super(const int2 range, unsigned super_local,
+                                                            unsigned tile_in_super, unsigned quad,
+                                                            unsigned shift) {
+    const unsigned g0 = (unsigned)range.x >> 5;
+    const unsigned cap = ((unsigned)range.y >> 5) - g0 + 1u;
+    return (size_t)(4u << shift) * ((size_t)g0 + super_local) + (size_t)(4u * tile_in_super + quad) * cap;
+}
+
 }  // namespace jsb

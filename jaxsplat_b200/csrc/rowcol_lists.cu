@@ -23,6 +23,8 @@
 // in shared memory) and a column scan; the count matrices are (chunks x rows) and
 // (row chunks x tile columns): a few MB instead of the (chunks x tiles) matrix of tile_lists.cu.
 // HBM traffic per intersection: the 4-byte id, once.  Per row entry: 8 B written, 8 B read twice.
+#include <type_traits>
+
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -44,22 +46,31 @@ namespace {
 #ifndef JSB_RC_STAGE2
 #define JSB_RC_STAGE2 (192 * JSB_RC_GROUPS2)
 #endif
-constexpr int RC_G1 = JSB_RC_GROUPS1, RC_G2 = JSB_RC_GROUPS2;
+// super-column level 2 (fused render): 8-byte entries into a few wide bins per row
+#ifndef JSB_RC_GROUPS2S
+#define JSB_RC_GROUPS2S 8
+#endif
+#ifndef JSB_RC_STAGE2S
+#define JSB_RC_STAGE2S (80 * JSB_RC_GROUPS2S)
+#endif
+constexpr int RC_G1 = JSB_RC_GROUPS1, RC_G2 = JSB_RC_GROUPS2, RC_G2S = JSB_RC_GROUPS2S;
 constexpr int RC_ITEMS = 256;    // items per chunk of the COUNT kernels (8 register groups of 32)
 constexpr int RC_STAGE1 = JSB_RC_STAGE1;  // staged 8-byte row entries per level-1 chunk
 constexpr int RC_STAGE2 = JSB_RC_STAGE2;  // staged 4-byte ids per level-2 chunk
+constexpr int RC_STAGE2S = JSB_RC_STAGE2S;  // staged 8-byte entries per super-column level-2 chunk
 
 struct RcParams {
     unsigned n;          // Gaussians
     unsigned rows;       // R: tile rows of the band
     unsigned cols;       // X: tiles per row
+    unsigned sc_shift;   // level-2 bins are super-columns of 2^sc_shift tiles (0: the tiles themselves)
+    unsigned cols2;      // level-2 bins per row = ceil(cols / 2^sc_shift)
     unsigned band_y0;    // first tile row of the band
     unsigned k1;         // depth positions per level-1 chunk (multiple of 32, <= 256)
     unsigned k2;         // row entries per level-2 chunk (multiple of 32, <= 256)
     unsigned n1;         // level-1 chunks = ceil(n / k1)
     unsigned n1s;        // row stride of the level-1 count matrix (n1 rounded up to 4)
     unsigned n2max;      // upper bound of the level-2 chunk count
-    ListGuard guard;     // speculative launch: capacities the E- / I-scale buffers were sized for
 };
 
 // word offsets inside the scratch buffer
@@ -69,8 +80,8 @@ struct RcLayout {
     size_t row_start;   // [rows + 1]
     size_t chunk_base;  // [rows + 1]
     size_t chunk_row;   // uint4 [n2max]: {row, first entry, one past last entry, 0} of every level-2 chunk
-    size_t tile_cnt;    // [rows * cols] -> exclusive scan (tile bases)
-    size_t m;           // [n2max][cols] level-2 counts -> exclusive prefix per (row, col)
+    size_t tile_cnt;    // [rows * cols2] -> exclusive scan (bin bases)
+    size_t m;           // [n2max][cols2] level-2 counts -> exclusive prefix per (row, bin)
     size_t entries;     // uint2 [entries] (8-byte aligned)
     size_t end;
 };
@@ -85,8 +96,8 @@ static RcLayout rc_layout(const RcParams &p, unsigned long long row_entries) {
     L.row_start = o;  o += up4(p.rows + 1);
     L.chunk_base = o; o += up4(p.rows + 1);
     L.chunk_row = o;  o += 4 * (size_t)p.n2max;
-    L.tile_cnt = o;   o += up4((size_t)p.rows * p.cols + 1);
-    L.m = o;          o += up4((size_t)p.n2max * p.cols);
+    L.tile_cnt = o;   o += up4((size_t)p.rows * p.cols2 + 1);
+    L.m = o;          o += up4((size_t)p.n2max * p.cols2);
     L.entries = o;    o += up4(2 * (size_t)row_entries + 4);
     L.end = o;
     return L;
@@ -246,6 +257,13 @@ rc_chunk_rows_kernel(const RcParams p, const unsigned *__restrict__ row_tot,
     chunk_info[ch] = info;
 }
 
+// level-2 bins [lo, lo + len) covered by a row entry's tile columns x0 .. x0 + w - 1
+__device__ __forceinline__ void entry_bins(unsigned xw, unsigned shift, unsigned &lo, unsigned &len) {
+    const unsigned x0 = xw & 0xffffu, w = xw >> 16;
+    lo = x0 >> shift;
+    len = w ? ((x0 + w - 1u) >> shift) - lo + 1u : 0u;
+}
+
 // ---- level 2 counts: tile columns covered by each chunk of k2 row entries -------------------------
 // One warp per chunk (8 chunks per CTA, no CTA-wide barrier): difference array in the warp's own
 // shared memory, 8 entries per lane, then a prefix over the columns.
@@ -254,7 +272,6 @@ __global__ void __launch_bounds__(32 * RC_CC_WARPS)
 rc_col_count_kernel(const RcParams p, const uint4 *__restrict__ chunk_info,
                     const uint2 *__restrict__ entries, unsigned *__restrict__ m) {
     __shared__ unsigned s_diff_all[RC_CC_WARPS][512 + 32];
-    if (guard_trips(p.guard)) return;  // (the row entries were not written)
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned *s_diff = s_diff_all[warp];
     const unsigned c = blockIdx.x * RC_CC_WARPS + warp;
@@ -262,7 +279,7 @@ rc_col_count_kernel(const RcParams p, const uint4 *__restrict__ chunk_info,
     const uint4 info = __ldg(chunk_info + c);
     const unsigned ebeg = info.y, eend = info.z;
     if (ebeg >= eend) return;
-    for (unsigned i = lane; i <= p.cols; i += 32) s_diff[i] = 0u;
+    for (unsigned i = lane; i <= p.cols2; i += 32) s_diff[i] = 0u;
     unsigned xw[8];
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
@@ -272,20 +289,21 @@ rc_col_count_kernel(const RcParams p, const uint4 *__restrict__ chunk_info,
     __syncwarp();
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-        const unsigned x0 = xw[q] & 0xffffu, w = xw[q] >> 16;
-        if (w) {
-            atomicAdd(&s_diff[x0], 1u);
-            atomicAdd(&s_diff[x0 + w], 0xffffffffu);
+        unsigned lo, len;
+        entry_bins(xw[q], p.sc_shift, lo, len);
+        if (len) {
+            atomicAdd(&s_diff[lo], 1u);
+            atomicAdd(&s_diff[lo + len], 0xffffffffu);
         }
     }
     __syncwarp();
-    unsigned *mrow = m + (size_t)c * p.cols;
+    unsigned *mrow = m + (size_t)c * p.cols2;
     unsigned carry = 0;
-    for (unsigned base = 0; base < p.cols; base += 32) {
+    for (unsigned base = 0; base < p.cols2; base += 32) {
         const unsigned i = base + lane;
-        const unsigned cnt = warp_inclusive_scan(i < p.cols ? s_diff[i] : 0u, lane) + carry;
+        const unsigned cnt = warp_inclusive_scan(i < p.cols2 ? s_diff[i] : 0u, lane) + carry;
         carry = __shfl_sync(0xffffffffu, cnt, 31);
-        if (i < p.cols) mrow[i] = cnt;
+        if (i < p.cols2) mrow[i] = cnt;
     }
 }
 
@@ -301,11 +319,11 @@ rc_col_scan_kernel(const RcParams p, const unsigned *__restrict__ chunk_base,
     const unsigned cb = chunk_base[r], ce = chunk_base[r + 1];
     const unsigned per = (ce - cb + RC_CS_WARPS - 1) / RC_CS_WARPS;
     const unsigned c0 = min(ce, cb + warp * per), c1 = min(ce, c0 + per);
-    const bool live = col < p.cols;
+    const bool live = col < p.cols2;
     unsigned sum = 0;
     if (live) {
 #pragma unroll 8
-        for (unsigned c = c0; c < c1; ++c) sum += m[(size_t)c * p.cols + col];
+        for (unsigned c = c0; c < c1; ++c) sum += m[(size_t)c * p.cols2 + col];
     }
     s_part[warp][lane] = sum;
     __syncthreads();
@@ -321,14 +339,14 @@ rc_col_scan_kernel(const RcParams p, const unsigned *__restrict__ chunk_base,
         for (unsigned c = c0; c < c1; c += U) {
             unsigned v[U];
 #pragma unroll
-            for (int u = 0; u < U; ++u) v[u] = (c + u < c1) ? m[(size_t)(c + u) * p.cols + col] : 0u;
+            for (int u = 0; u < U; ++u) v[u] = (c + u < c1) ? m[(size_t)(c + u) * p.cols2 + col] : 0u;
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                if (c + u < c1) m[(size_t)(c + u) * p.cols + col] = run;
+                if (c + u < c1) m[(size_t)(c + u) * p.cols2 + col] = run;
                 run += v[u];
             }
         }
-        if (warp == 0) tile_cnt[(size_t)r * p.cols + col] = total;
+        if (warp == 0) tile_cnt[(size_t)r * p.cols2 + col] = total;
     }
 }
 
@@ -336,8 +354,9 @@ rc_col_scan_kernel(const RcParams p, const unsigned *__restrict__ chunk_base,
 __global__ void __launch_bounds__(1024)
 rc_tile_scan_bins_kernel(const RcParams p, unsigned *__restrict__ tile_cnt,
                          int2 *__restrict__ tile_bins) {
-    int2 *bins = tile_bins + (size_t)p.band_y0 * p.cols;
-    cta32_exclusive_scan_inplace(tile_cnt, p.rows * p.cols, [bins](unsigned t, unsigned base, unsigned v) {
+    // (super-column bins are a band-local array of the library's own; tile bins index the frame)
+    int2 *bins = p.sc_shift ? tile_bins : tile_bins + (size_t)p.band_y0 * p.cols;
+    cta32_exclusive_scan_inplace(tile_cnt, p.rows * p.cols2, [bins](unsigned t, unsigned base, unsigned v) {
         // tiles without intersections stay (0,0) like the reference's memset + edge detection
         bins[t] = v ? make_int2((int)base, (int)(base + v)) : make_int2(0, 0);
     });
@@ -444,7 +463,6 @@ rc_row_scatter_kernel(const RcParams p, const unsigned *__restrict__ order,
                       const uint2 *__restrict__ box_by_id, const unsigned *__restrict__ l1m,
                       const unsigned *__restrict__ row_start, uint2 *__restrict__ entries) {
     extern __shared__ __align__(16) unsigned char rc_smem[];
-    if (guard_trips(p.guard)) return;  // more row entries than the buffer holds: host rebuilds
     const DistSmem<uint2, RC_STAGE1, RC_G1> S(rc_smem, p.rows);
     const unsigned lane = threadIdx.x, chunk = blockIdx.x;
     unsigned lo[RC_G1], len[RC_G1];
@@ -485,44 +503,52 @@ rc_row_scatter_kernel(const RcParams p, const unsigned *__restrict__ order,
 }
 
 // ---- level 2: row entries -> per-tile id lists -----------------------------------------------------
+// SUPER: the bins are super-columns of 2^sc_shift tiles and the payload is the whole 8-byte row
+// entry {id, x0 | w << 16}: the rasterisers of the fused render walk a super-column's list and
+// keep the entries whose tile columns cover their own tile (a third of the pairs of the exact
+// lists at 8 tiles per super-column, and 16 bins per row instead of 120 to rank over).
+template <bool SUPER>
 __global__ void __launch_bounds__(32)
 rc_col_scatter_kernel(const RcParams p, const uint4 *__restrict__ chunk_info,
                       const uint2 *__restrict__ entries, const unsigned *__restrict__ m,
-                      const unsigned *__restrict__ tile_base, unsigned *__restrict__ out_ids) {
+                      const unsigned *__restrict__ tile_base, void *__restrict__ out_list) {
+    using Payload = typename std::conditional<SUPER, uint2, unsigned>::type;
+    constexpr int STAGE = SUPER ? RC_STAGE2S : RC_STAGE2;
+    constexpr int G = SUPER ? RC_G2S : RC_G2;
     extern __shared__ __align__(16) unsigned char rc_smem[];
-    if (guard_trips(p.guard)) return;  // more intersections than the list buffer holds
-    const DistSmem<unsigned, RC_STAGE2, RC_G2> S(rc_smem, p.cols);
+    const DistSmem<Payload, STAGE, G> S(rc_smem, p.cols2);
     const unsigned lane = threadIdx.x, c = blockIdx.x;
     const uint4 info = __ldg(chunk_info + c);
     const unsigned r = info.x, ebeg = info.y, eend = info.z;
     if (ebeg >= eend) return;
     // run starts of this chunk: all loads in flight before the first dependent store
-    const unsigned *mrow = m + (size_t)c * p.cols;
-    const unsigned *tb = tile_base + (size_t)r * p.cols;
-    unsigned gb[16];  // cols <= 512
+    const unsigned *mrow = m + (size_t)c * p.cols2;
+    const unsigned *tb = tile_base + (size_t)r * p.cols2;
+    constexpr int NB = SUPER ? 4 : 16;  // bins <= 512 (exact) / <= 128 (super-columns)
+    unsigned gb[NB];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
+    for (int i = 0; i < NB; ++i) {
         const unsigned x = lane + 32u * i;
-        gb[i] = x < p.cols ? __ldg(tb + x) + __ldg(mrow + x) : 0u;
+        gb[i] = x < p.cols2 ? __ldg(tb + x) + __ldg(mrow + x) : 0u;
     }
-    unsigned lo[RC_G2], len[RC_G2], pay[RC_G2];
+    unsigned lo[G], len[G];
+    Payload pay[G];
 #pragma unroll
-    for (int q = 0; q < RC_G2; ++q) {
+    for (int q = 0; q < G; ++q) {
         const unsigned e = ebeg + q * 32 + lane;
         uint2 v = make_uint2(0u, 0u);
         if (q * 32 + lane < p.k2 && e < eend) v = entries[e];
-        pay[q] = v.x;
-        lo[q] = v.y & 0xffffu;
-        len[q] = v.y >> 16;
+        if constexpr (SUPER) pay[q] = v; else pay[q] = v.x;
+        entry_bins(v.y, p.sc_shift, lo[q], len[q]);
     }
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
+    for (int i = 0; i < NB; ++i) {
         const unsigned x = lane + 32u * i;
-        if (x < p.cols) S.gbase[x] = gb[i];
+        if (x < p.cols2) S.gbase[x] = gb[i];
     }
-    const unsigned pairs = distribute_rank<unsigned, RC_STAGE2, RC_G2>(lo, len, p.cols, S);
+    const unsigned pairs = distribute_rank<Payload, STAGE, G>(lo, len, p.cols2, S);
     if (pairs == 0) return;
-    distribute_place<unsigned, RC_STAGE2, RC_G2>(lo, len, pay, pairs, S, out_ids);
+    distribute_place<Payload, STAGE, G>(lo, len, pay, pairs, S, reinterpret_cast<Payload *>(out_list));
 }
 
 static unsigned pick_items(unsigned long long produced, unsigned long long items, unsigned stage,
@@ -536,15 +562,19 @@ static unsigned pick_items(unsigned long long produced, unsigned long long items
     return (unsigned)k;
 }
 
+// num_intersects: level-2 outputs (intersections; super-column entries when sc_shift > 0)
 static RcParams rc_params(const BinParams &bp, unsigned long long row_entries,
-                          unsigned long long num_intersects) {
+                          unsigned long long num_intersects, unsigned sc_shift) {
     RcParams p;
     p.n = bp.num_points;
     p.rows = bp.band_y1 - bp.band_y0;
     p.cols = bp.tiles_x;
+    p.sc_shift = sc_shift;
+    p.cols2 = ((bp.tiles_x - 1u) >> sc_shift) + 1u;
     p.band_y0 = bp.band_y0;
     p.k1 = pick_items(row_entries, bp.num_points, RC_STAGE1, 32 * RC_G1);
-    p.k2 = pick_items(num_intersects, row_entries, RC_STAGE2, 32 * RC_G2);
+    p.k2 = sc_shift ? pick_items(num_intersects, row_entries, RC_STAGE2S, 32 * RC_G2S)
+                    : pick_items(num_intersects, row_entries, RC_STAGE2, 32 * RC_G2);
     p.n1 = ceil_div(p.n, p.k1);
     p.n1s = (p.n1 + 3u) & ~3u;
     p.n2max = (unsigned)(row_entries / p.k2) + p.rows;
@@ -557,16 +587,20 @@ bool rowcol_supported(const BinParams &bp) {
     return bp.band_y1 > bp.band_y0 && bp.band_y1 - bp.band_y0 <= 256u && bp.tiles_x <= 512u;
 }
 
+bool supercols_supported(const BinParams &bp, unsigned sc_shift) {
+    return rowcol_supported(bp) && sc_shift >= 1 && sc_shift <= 6 && (((bp.tiles_x - 1u) >> sc_shift) + 1u) <= 128u;
+}
+
 size_t rowcol_scratch_bytes(const BinParams &bp, unsigned long long row_entries,
-                            unsigned long long num_intersects) {
-    const RcParams p = rc_params(bp, row_entries, num_intersects);
+                            unsigned long long num_intersects, unsigned sc_shift) {
+    const RcParams p = rc_params(bp, row_entries, num_intersects, sc_shift);
     return rc_layout(p, row_entries).end * sizeof(unsigned);
 }
 
 int launch_rowcol_lists(cudaStream_t stream, const BinParams &bp, const unsigned *order,
                         const uint2 *box_by_id, unsigned long long row_entries,
-                        unsigned long long num_intersects, unsigned *scratch, unsigned *ids_sorted,
-                        int2 *tile_bins, int phase, const ListGuard &guard) {
+                        unsigned long long num_intersects, unsigned *scratch, void *ids_sorted,
+                        int2 *tile_bins, int phase, unsigned sc_shift) {
     if (bp.num_points == 0 || num_intersects == 0) return 0;
     if (!rowcol_supported(bp)) {
         set_error("rowcol_lists: band of %u rows x %u tiles not supported", bp.band_y1 - bp.band_y0,
@@ -578,8 +612,11 @@ int launch_rowcol_lists(cudaStream_t stream, const BinParams &bp, const unsigned
                   num_intersects);
         return 1;
     }
-    RcParams p = rc_params(bp, row_entries, num_intersects);
-    p.guard = guard;
+    if (sc_shift && !supercols_supported(bp, sc_shift)) {
+        set_error("rowcol_lists: super-columns of 2^%u tiles not supported for %u tiles per row", sc_shift, bp.tiles_x);
+        return 1;
+    }
+    RcParams p = rc_params(bp, row_entries, num_intersects, sc_shift);
     const RcLayout L = rc_layout(p, row_entries);
     unsigned *l1m = scratch + L.l1m, *row_tot = scratch + L.row_tot;
     unsigned *row_start = scratch + L.row_start, *chunk_base = scratch + L.chunk_base;
@@ -588,7 +625,8 @@ int launch_rowcol_lists(cudaStream_t stream, const BinParams &bp, const unsigned
     unsigned *m = scratch + L.m;
     uint2 *entries = reinterpret_cast<uint2 *>(scratch + L.entries);
     const size_t smem1 = DistSmem<uint2, RC_STAGE1, RC_G1>::bytes(p.rows);
-    const size_t smem2 = DistSmem<unsigned, RC_STAGE2, RC_G2>::bytes(p.cols);
+    const size_t smem2 = sc_shift ? DistSmem<uint2, RC_STAGE2S, RC_G2S>::bytes(p.cols2)
+                                  : DistSmem<unsigned, RC_STAGE2, RC_G2>::bytes(p.cols2);
 
     if (phase == 0) {  // level 1: row lists
         rc_row_count_kernel<<<ceil_div(p.n1, (unsigned)RC_RC_WARPS), 32 * RC_RC_WARPS, 0, stream>>>(
@@ -606,15 +644,19 @@ int launch_rowcol_lists(cudaStream_t stream, const BinParams &bp, const unsigned
         rc_col_count_kernel<<<ceil_div(p.n2max, (unsigned)RC_CC_WARPS), 32 * RC_CC_WARPS, 0, stream>>>(
             p, chunk_info, entries, m);
         JSB_CUDA_OK(cudaGetLastError());
-        rc_col_scan_kernel<<<dim3(ceil_div(p.cols, 32u), p.rows), 32 * RC_CS_WARPS, 0, stream>>>(
+        rc_col_scan_kernel<<<dim3(ceil_div(p.cols2, 32u), p.rows), 32 * RC_CS_WARPS, 0, stream>>>(
             p, chunk_base, m, tile_cnt);
         JSB_CUDA_OK(cudaGetLastError());
         rc_tile_scan_bins_kernel<<<1, 1024, 0, stream>>>(p, tile_cnt, tile_bins);
         JSB_CUDA_OK(cudaGetLastError());
         note_launch(3);
     } else {  // level 2: the lists
-        rc_col_scatter_kernel<<<p.n2max, 32, smem2, stream>>>(p, chunk_info, entries, m, tile_cnt,
-                                                              ids_sorted);
+        if (sc_shift)
+            rc_col_scatter_kernel<true><<<p.n2max, 32, smem2, stream>>>(p, chunk_info, entries, m, tile_cnt,
+                                                                        ids_sorted);
+        else
+            rc_col_scatter_kernel<false><<<p.n2max, 32, smem2, stream>>>(p, chunk_info, entries, m, tile_cnt,
+                                                                         ids_sorted);
         JSB_CUDA_OK(cudaGetLastError());
         note_launch();
     }

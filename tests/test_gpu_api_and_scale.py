@@ -356,45 +356,3 @@ def test_reference_style_descriptor_with_garbage_pad_bytes_renders_the_full_fram
     got = G.rasterize_fwd(inp, P, rkw, table=GarbagePad(_ffi.native_table()))
     assert torch.equal(got["final_idx"], want["final_idx"])
     assert torch.equal(got["img"].view(torch.int32), want["img"].view(torch.int32))
-
-
-def test_speculative_forward_holds_on_a_repeated_frame_and_rebuilds_when_the_frame_outgrows_it():
-    """option "spec" (off by default): from the second forward of a shape on, the list builders and the rasteriser
-    are launched before the host knows the intersection count, with buffers sized from the previous
-    frame.  Same results as the waiting path; a frame with far more intersections than planned
-    trips the device-side guard, nothing is written, and the host rebuilds with exact sizes."""
-    from jaxsplat_b200 import _lib
-    small = synthetic.benchmark_scene(20000, (256, 320), scale_max=0.05, seed=41).to(G.DEV)
-    big = synthetic.benchmark_scene(20000, (256, 320), scale_max=0.6, seed=42).to(G.DEV)   # same shape
-    t = torch.rand((256, 320, 3), generator=torch.Generator().manual_seed(5)).to(G.DEV)
-
-    def run(sc):
-        ps = [p.clone().requires_grad_(True) for p in sc.params()]
-        img = jsb.render(*ps, **sc.render_kwargs())
-        ((img - t) ** 2).mean().backward()
-        return img.detach().clone(), [p.grad.clone() for p in ps]
-
-    _lib.set_option("spec", 0)
-    ref_small, ref_big = run(small), run(big)
-    _lib.lib().jsb200_release()          # forget every plan
-    try:
-        _lib.set_option("spec", 1)
-        s0 = _lib.speculation_stats()
-        a = run(small)                       # no plan yet: waits
-        b = run(small)                       # planned from a: holds
-        s1 = _lib.speculation_stats()
-        assert s1["held"] == s0["held"] + 1 and s1["rebuilt"] == s0["rebuilt"]
-        c = run(big)                         # same shape, ~50x the intersections: guard trips
-        s2 = _lib.speculation_stats()
-        assert s2["rebuilt"] == s1["rebuilt"] + 1
-        d = run(big)                         # planned from c: holds
-        e = run(small)                       # a smaller frame inside a bigger plan: holds
-        s3 = _lib.speculation_stats()
-        assert s3["held"] == s2["held"] + 2
-    finally:
-        _lib.set_option("spec", 0)           # the default
-    for got, ref in ((a, ref_small), (b, ref_small), (c, ref_big), (d, ref_big), (e, ref_small)):
-        assert torch.equal(got[0], ref[0])
-        for x, y in zip(got[1], ref[1]):
-            ok, err, scale = grad_close(G.npy(x), G.npy(y), rel=1e-4)
-            assert ok, (err, scale)

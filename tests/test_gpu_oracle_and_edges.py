@@ -467,3 +467,62 @@ def test_barrier_free_forward_is_bit_identical_to_the_batch_kernel(scene_fn):
     for k in ("v_colors", "v_opacity", "v_xy", "v_xy_abs", "v_conic"):
         ok, err, scale = grad_close(ga[k], gb[k], rel=2e-5)
         assert ok, (k, err, scale)
+
+
+@pytest.mark.parametrize("case", ["C2_30k", "wide_boxes", "ragged", "band", "narrow_grid", "tiny",
+                                  "long_lists", "adversarial"])
+def test_super_column_lists_render_the_same_image_and_gradients(case):
+    """option "supercols" (default 2): the fused render's level 2 distributes 8-byte row entries
+    into super-columns of 2^k tiles and the rasterisers keep the entries whose tile columns cover
+    their tile -- the tile's own list in the same order, so the image may not differ in a bit from
+    the exact per-tile lists (supercols 0) for any k, and the gradients only by atomic order; also
+    when the backward has to rebuild the lists itself (cache off: it replays every entry)"""
+    import jaxsplat_b200 as jsb
+    rows = None
+    if case == "C2_30k":
+        s = synthetic.make_config("C2", num_points=30000)
+    elif case == "wide_boxes":   # boxes spanning several super-columns
+        s = synthetic.benchmark_scene(20000, (272, 400), scale_max=1.5, seed=9)
+    elif case == "ragged":
+        s = synthetic.benchmark_scene(777, (90, 50), scale_max=0.4, seed=6)
+    elif case == "band":
+        s = synthetic.benchmark_scene(20000, (320, 256), scale_max=0.4, seed=8)
+        rows = (5, 13)
+    elif case == "narrow_grid":  # four tiles per row: one super-column at k >= 2
+        s = synthetic.benchmark_scene(4000, (1024, 64), scale_max=2.0, seed=10)
+    elif case == "tiny":
+        s = synthetic.benchmark_scene(60, (40, 40), scale_max=0.3, seed=3)
+    elif case == "long_lists":
+        s = _long_list_scene()
+    else:
+        s = _adversarial_scene()
+    sc = s.to(G.DEV)
+    H, W = s.img_shape
+    target = torch.rand((H, W, 3), generator=torch.Generator().manual_seed(9)).to(G.DEV)
+    y0, y1 = (0, H) if rows is None else (rows[0] * 16, min(H, rows[1] * 16))
+
+    def run():
+        params = [p.clone().requires_grad_(True) for p in sc.params()]
+        img = jsb.render(*params, tile_rows=rows, **sc.render_kwargs())
+        (((img[y0:y1] - target[y0:y1]) ** 2).sum() / (H * W * 3)).backward()
+        return img[y0:y1].detach().clone(), [G.npy(p.grad) for p in params]
+
+    try:
+        _lib.set_option("supercols", 0)
+        img0, g0 = run()
+        # atomic-order noise of the exact lists themselves (needle-thin splats amplify it through
+        # the conic VJP of the projection backward): the yardstick for the comparison below
+        _img0b, g0b = run()
+        noise = [float(np.abs(a.astype(np.float64) - b.astype(np.float64)).max()) for a, b in zip(g0, g0b)]
+        for k in (1, 2, 3, 5):
+            _lib.set_option("supercols", k)
+            for cache in (1, 0):
+                _lib.set_option("cache", cache)
+                img, g = run()
+                assert torch.equal(img.view(torch.int32), img0.view(torch.int32)), (k, cache)
+                for a, b, nz in zip(g, g0, noise):
+                    ok, err, scale = grad_close(a, b, rel=2e-5)
+                    assert ok or err <= 8.0 * nz, (k, cache, err, scale, nz)
+    finally:
+        _lib.set_option("supercols", 2)
+        _lib.set_option("cache", 1)
