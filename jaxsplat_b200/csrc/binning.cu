@@ -15,6 +15,7 @@
 // and 6 passes.
 #include "common.cuh"
 #include "kernels.cuh"
+#include "raster_cull.cuh"
 
 namespace jsb {
 namespace {
@@ -67,7 +68,7 @@ bin_prep_kernel(const BinParams p, const float2 *__restrict__ xys,
                 SplatRecord rec;
                 rec.q0 = make_float4(xy.x, xy.y, opac, cx);
                 rec.q1 = make_float4(cy, cz, r, gr);
-                rec.q2 = make_float4(b, 0.f, 0.f, 0.f);
+                rec.q2 = make_float4(b, cull_record_thresh(opac, cx, cy, cz, (float)radius, p.block_width_f), 0.f, 0.f);
                 records[g] = rec;
             }
         }

@@ -60,7 +60,9 @@ int launch_accumulate_param_grads(cudaStream_t stream, size_t n, const float *s_
 
 // ---- binning (binning.cu) -------------------------------------------------------------------
 // Per-Gaussian record gathered by the rasterisers: 3 x float4 = 48 B, one 16-B aligned line.
-//   q0 = {x, y, opacity, conic.x}   q1 = {conic.y, conic.z, r, g}   q2 = {b, 0, 0, 0}
+//   q0 = {x, y, opacity, conic.x}   q1 = {conic.y, conic.z, r, g}   q2 = {b, cull threshold, 0, 0}
+// (cull threshold: raster_cull.cuh, cull_record_thresh -- the per-Gaussian part of the conservative
+// quadrant pre-filter, so the rasterisers do not redo it for every tile the Gaussian is listed in)
 struct __align__(16) SplatRecord {
     float4 q0, q1, q2;
 };

@@ -13,6 +13,7 @@
 // temp allocation.
 #include "common.cuh"
 #include "kernels.cuh"
+#include "raster_cull.cuh"
 
 namespace jsb {
 
@@ -263,7 +264,8 @@ project_fwd_kernel(const ProjectFwdParams p, const float *__restrict__ means3d,
         float4 *s4 = reinterpret_cast<float4 *>(strip);
         s4[lane * 3 + 0] = make_float4(o.xy.x, o.xy.y, opac, o.conic.x);
         s4[lane * 3 + 1] = make_float4(o.conic.y, o.conic.z, cr, cg);
-        s4[lane * 3 + 2] = make_float4(cb, 0.f, 0.f, 0.f);
+        s4[lane * 3 + 2] = make_float4(cb, cull_record_thresh(opac, o.conic.x, o.conic.y, o.conic.z, (float)o.radius,
+                                                            p.block_width_f), 0.f, 0.f);
         __syncwarp();
         float4 *rec4 = reinterpret_cast<float4 *>(f.records) + wfirst * 3;
         const long long rec_left = (n - wfirst) * 3;  // float4s of this warp that exist

@@ -44,7 +44,38 @@ __device__ __forceinline__ CullGauss cull_setup(float gx, float gy, float opac, 
     return c;
 }
 
+// The Gaussian-only part of the set-up, evaluated once per Gaussian by the prep kernels and kept
+// in its record (SplatRecord::q2.y): ln(255 opac) + margins, with the relative margin taken over
+// every pixel of every tile the Gaussian's box covers (|d| <= radius + tile width per axis, so it
+// bounds the per-tile value of cull_setup); -inf when no pixel can accept (`never`), +inf when the
+// conic is not safely positive definite (`always`: never cull).
+__host__ __device__ __forceinline__ float cull_record_thresh(float opac, float cx, float cy, float cz,
+                                                             float radius, float tile_w) {
+    if (opac < kAlphaMin * 0.9999f) return -INFINITY;
+    const float det = cx * cz - cy * cy;
+    if (!(det > 0.f && cx > 0.f && cz > 0.f && det < 3.0e38f)) return INFINITY;
+    const float dm = radius + tile_w;
+    const float amax = 0.5f * (cx + cz) * dm * dm;
+    const float t = logf(255.f * fmaxf(opac, 1e-30f)) + kCullAbsMargin + kCullRelMargin * amax;
+    if (!(t == t) || !(amax < 3.0e38f)) return INFINITY;
+    return t;
+}
+
+// set-up from a record that carries cull_record_thresh
+__device__ __forceinline__ CullGauss cull_from_record(float gx, float gy, float cx, float cy, float cz,
+                                                      float thresh) {
+    CullGauss c;
+    c.gx = gx; c.gy = gy; c.cx = cx; c.cy = cy; c.cz = cz;
+    c.never = false;   // (both folded into thresh)
+    c.always = false;
+    c.icx = __fdividef(1.f, cx);
+    c.icz = __fdividef(1.f, cz);
+    c.thresh = thresh;
+    return c;
+}
+
 // may any pixel centre in [x0+0.5, x0+w-0.5] x [y0+0.5, y0+h-0.5] pass the exact test?
+// (written as !(min > thresh): a NaN from a degenerate conic never culls)
 __device__ __forceinline__ bool cull_rect_may_hit(const CullGauss &c, float x0, float y0, float w,
                                                   float h) {
     // delta = g - p ranges over [dx_lo, dx_hi] x [dy_lo, dy_hi]
@@ -58,7 +89,7 @@ __device__ __forceinline__ bool cull_rect_may_hit(const CullGauss &c, float x0, 
     const float xb = fminf(fmaxf(-c.cy * Y * c.icx, dx_lo), dx_hi);
     const float qa = 0.5f * (c.cx * X * X + c.cz * ya * ya) + c.cy * X * ya;
     const float qb = 0.5f * (c.cx * xb * xb + c.cz * Y * Y) + c.cy * xb * Y;
-    return fminf(qa, qb) <= c.thresh;
+    return !(fminf(qa, qb) > c.thresh);
 }
 
 // 8-bit mask over the 2x4 warp rectangles of a 16x16 tile (bit = wy*2 + wx)

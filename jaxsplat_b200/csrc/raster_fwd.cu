@@ -293,13 +293,13 @@ raster_fwd_warp_kernel(const RasterParams p, const void *__restrict__ list,
         return ids_sorted[idx];
     };
     float4 qa = make_float4(0.f, 0.f, 0.f, 0.f), qb = qa;
-    float qc = 0.f;
+    float2 qc = make_float2(0.f, 0.f);  // b, cull threshold
     auto load_rec = [&](unsigned id) {
         if (id != 0xFFFFFFFFu) {
             const SplatRecord *r = records + id;
             qa = __ldg(&r->q0);
             qb = __ldg(&r->q1);
-            qc = __ldg(&r->q2).x;
+            qc = __ldg(reinterpret_cast<const float2 *>(&r->q2));
         }
     };
     unsigned id_cur = load_id(0);
@@ -310,12 +310,11 @@ raster_fwd_warp_kernel(const RasterParams p, const void *__restrict__ list,
     for (int g = 0; g < ngroups && !warp_done; ++g) {
         // this group's record (arrived) -> candidate test
         const float4 a_me = qa, b_me = qb;
-        const float c_me = qc;
+        const float c_me = qc.x;
         bool may = id_cur != 0xFFFFFFFFu;
-        if (CULL && may) {
-            const CullGauss c = cull_setup(a_me.x, a_me.y, a_me.z, a_me.w, b_me.x, b_me.y, tile_x0,
-                                           tile_y0, 16.f, 16.f);
-            may = !c.never && (c.always || cull_rect_may_hit(c, quad_x0, quad_y0, 8.f, 8.f));
+        if (CULL && may) {  // the record carries the per-Gaussian part of the test (cull_record_thresh)
+            const CullGauss c = cull_from_record(a_me.x, a_me.y, a_me.w, b_me.x, b_me.y, qc.y);
+            may = cull_rect_may_hit(c, quad_x0, quad_y0, 8.f, 8.f);
         }
         // next group's gathers go out before this group is composited
         id_cur = id_next;
