@@ -235,6 +235,12 @@ JSB200_API int jsb200_adam_step(jsb200_stream_t stream, float *param, const floa
  * per CTA, so its last bits depend on the order in which the CTAs finish).  Returns 0 on success. */
 JSB200_API int jsb200_mse_loss_grad(jsb200_stream_t stream, const float *img, const float *target,
                                     size_t n, float scale, float *v_img, float *loss);
+/* The same with an 8-bit target image (what a data loader delivers): element i is decoded as
+ * float(target[i]) * (1 / 255) inside the kernel -- the value a separate u8 -> f32 decode pass would
+ * have stored -- so the image never exists as floats in memory. */
+JSB200_API int jsb200_mse_loss_grad_u8(jsb200_stream_t stream, const float *img,
+                                       const unsigned char *target, size_t n, float scale,
+                                       float *v_img, float *loss);
 
 #ifdef __cplusplus
 }

@@ -43,6 +43,7 @@ EXPORTS = (
     "jsb200_multimem_allreduce_f32",
     "jsb200_adam_step",
     "jsb200_mse_loss_grad",
+    "jsb200_mse_loss_grad_u8",
 )
 
 _lib = None
@@ -117,6 +118,8 @@ def lib() -> ctypes.CDLL:
     L.jsb200_adam_step.restype = i
     L.jsb200_mse_loss_grad.argtypes = [vp, vp, vp, sz, f, vp, vp]
     L.jsb200_mse_loss_grad.restype = i
+    L.jsb200_mse_loss_grad_u8.argtypes = [vp, vp, vp, sz, f, vp, vp]
+    L.jsb200_mse_loss_grad_u8.restype = i
     _lib = L
     return L
 

@@ -19,8 +19,24 @@ __device__ __forceinline__ float sq_diff(float a, float b, float scale, float &v
     return d * d;
 }
 
+// target element i as float: float targets as they are, 8-bit ones as float(t) * (1 / 255) -- the
+// decode an eager pipeline runs as its own kernel (u8 -> f32 copy, scale) before the loss
+__device__ __forceinline__ float target_at(const float *t, size_t i) { return t[i]; }
+__device__ __forceinline__ float target_at(const unsigned char *t, size_t i) {
+    return __fmul_rn((float)t[i], 1.0f / 255.0f);
+}
+__device__ __forceinline__ float4 target4_at(const float *t, size_t i) {
+    return __ldg(reinterpret_cast<const float4 *>(t) + i);
+}
+__device__ __forceinline__ float4 target4_at(const unsigned char *t, size_t i) {
+    const uchar4 q = __ldg(reinterpret_cast<const uchar4 *>(t) + i);
+    return make_float4(__fmul_rn((float)q.x, 1.0f / 255.0f), __fmul_rn((float)q.y, 1.0f / 255.0f),
+                       __fmul_rn((float)q.z, 1.0f / 255.0f), __fmul_rn((float)q.w, 1.0f / 255.0f));
+}
+
+template <typename TargetT>
 __global__ void __launch_bounds__(256)
-mse_loss_grad_kernel(const float *__restrict__ img, const float *__restrict__ target, size_t n,
+mse_loss_grad_kernel(const float *__restrict__ img, const TargetT *__restrict__ target, size_t n,
                      float scale, float inv_n, float *__restrict__ v_img, float *__restrict__ loss,
                      bool vec) {
     __shared__ float s_part[256 / 32];
@@ -32,7 +48,7 @@ mse_loss_grad_kernel(const float *__restrict__ img, const float *__restrict__ ta
         const size_t nv = n >> 2;
         for (size_t i = tid; i < nv; i += stride) {
             const float4 a = __ldg(reinterpret_cast<const float4 *>(img) + i);
-            const float4 b = __ldg(reinterpret_cast<const float4 *>(target) + i);
+            const float4 b = target4_at(target, i);
             float4 v;
             acc += sq_diff(a.x, b.x, scale, v.x);
             acc += sq_diff(a.y, b.y, scale, v.y);
@@ -44,7 +60,7 @@ mse_loss_grad_kernel(const float *__restrict__ img, const float *__restrict__ ta
     }
     for (size_t i = done + tid; i < n; i += stride) {
         float v;
-        acc += sq_diff(img[i], target[i], scale, v);
+        acc += sq_diff(img[i], target_at(target, i), scale, v);
         v_img[i] = v;
     }
 #pragma unroll
@@ -62,24 +78,37 @@ mse_loss_grad_kernel(const float *__restrict__ img, const float *__restrict__ ta
 }  // namespace
 }  // namespace jsb
 
-extern "C" int jsb200_mse_loss_grad(jsb200_stream_t stream_, const float *img, const float *target,
-                                    size_t n, float scale, float *v_img, float *loss) {
-    using namespace jsb;
-    cudaStream_t stream = (cudaStream_t)stream_;
+namespace jsb {
+template <typename TargetT>
+static int mse_loss_grad_impl(cudaStream_t stream, const float *img, const TargetT *target, size_t n,
+                              float scale, float *v_img, float *loss) {
     if (!loss || (n && (!img || !target || !v_img))) {
         set_error("mse_loss_grad: null buffer");
         return 1;
     }
     JSB_CUDA_OK(cudaMemsetAsync(loss, 0, sizeof(float), stream));
     if (n == 0) return 0;
-    const bool vec = ((reinterpret_cast<uintptr_t>(img) | reinterpret_cast<uintptr_t>(target) |
-                       reinterpret_cast<uintptr_t>(v_img)) & 15) == 0;
+    // (four elements per thread: 16-byte image / cotangent accesses, 16- or 4-byte target ones)
+    const bool vec = ((reinterpret_cast<uintptr_t>(img) | reinterpret_cast<uintptr_t>(v_img)) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(target) & (4 * sizeof(TargetT) - 1)) == 0;
     const size_t work = vec ? (n + 3) / 4 : n;
     unsigned blocks = (unsigned)((work + 255) / 256 < 148 * 8 ? (work + 255) / 256 : 148 * 8);
     if (blocks == 0) blocks = 1;
-    mse_loss_grad_kernel<<<blocks, 256, 0, stream>>>(img, target, n, scale, 1.0f / (float)n, v_img,
-                                                     loss, vec);
+    mse_loss_grad_kernel<TargetT><<<blocks, 256, 0, stream>>>(img, target, n, scale, 1.0f / (float)n,
+                                                              v_img, loss, vec);
     JSB_CUDA_OK(cudaGetLastError());
     note_launch();
     return 0;
+}
+}  // namespace jsb
+
+extern "C" int jsb200_mse_loss_grad(jsb200_stream_t stream, const float *img, const float *target,
+                                    size_t n, float scale, float *v_img, float *loss) {
+    return jsb::mse_loss_grad_impl<float>((cudaStream_t)stream, img, target, n, scale, v_img, loss);
+}
+
+extern "C" int jsb200_mse_loss_grad_u8(jsb200_stream_t stream, const float *img,
+                                       const unsigned char *target, size_t n, float scale,
+                                       float *v_img, float *loss) {
+    return jsb::mse_loss_grad_impl<unsigned char>((cudaStream_t)stream, img, target, n, scale, v_img, loss);
 }

@@ -111,3 +111,9 @@ def test_native_mse_loss_and_gradient_match_torch():
         assert torch.equal(v, diff * (2.0 / diff.numel()))
         ref = float((diff.double() ** 2).mean())
         assert abs(float(loss) - ref) <= 1e-5 * ref
+        # an 8-bit target decoded inside the kernel == the decoded float target
+        t8 = (torch.rand(n + off, generator=gen) * 256).clamp(0, 255).to(torch.uint8).cuda()[off:].view(shape)
+        loss8, v8 = mse_loss_and_grad(a, t8)
+        lossf, vf = mse_loss_and_grad(a, t8.float().mul_(1.0 / 255.0))
+        assert torch.equal(v8, vf)
+        assert abs(float(loss8) - float(lossf)) <= 1e-6 * float(lossf)
