@@ -68,8 +68,10 @@ __device__ __forceinline__ CullGauss cull_from_record(float gx, float gy, float 
     c.gx = gx; c.gy = gy; c.cx = cx; c.cy = cy; c.cz = cz;
     c.never = false;   // (both folded into thresh)
     c.always = false;
-    c.icx = __fdividef(1.f, cx);
-    c.icz = __fdividef(1.f, cz);
+    // the reciprocals only steer the clamped edge minimiser (any value keeps the test
+    // conservative): one MUFU each, without the range fix-ups of a division
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(c.icx) : "f"(cx));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(c.icz) : "f"(cz));
     c.thresh = thresh;
     return c;
 }

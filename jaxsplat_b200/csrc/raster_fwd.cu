@@ -308,28 +308,27 @@ raster_fwd_warp_kernel(const RasterParams p, const void *__restrict__ list,
 
     bool warp_done = __all_sync(0xffffffffu, done0 && done1);
     for (int g = 0; g < ngroups && !warp_done; ++g) {
-        // this group's record (arrived) -> candidate test
-        const float4 a_me = qa, b_me = qb;
-        const float c_me = qc.x;
+        // this group's record (arrived) -> candidate test -> compacted into the warp's slots
         bool may = id_cur != 0xFFFFFFFFu;
         if (CULL && may) {  // the record carries the per-Gaussian part of the test (cull_record_thresh)
-            const CullGauss c = cull_from_record(a_me.x, a_me.y, a_me.w, b_me.x, b_me.y, qc.y);
+            const CullGauss c = cull_from_record(qa.x, qa.y, qa.w, qb.x, qb.y, qc.y);
             may = cull_rect_may_hit(c, quad_x0, quad_y0, 8.f, 8.f);
         }
-        // next group's gathers go out before this group is composited
+        const unsigned bits = __ballot_sync(0xffffffffu, may);
+        if (may) {
+            const int pos = __popc(bits & lt_mask);
+            slot[pos].A = qa;
+            slot[pos].B = qb;
+            sc[pos] = make_float2(qc.x, __int_as_float(range.x + 32 * g + lane));
+        }
+        // the record registers are free again: the next group's gathers go out and fly while this
+        // group is composited
         id_cur = id_next;
         id_next = load_id(g + 2);
         load_rec(id_cur);
 
-        const unsigned bits = __ballot_sync(0xffffffffu, may);
         unsigned hit = 0;
         if (bits) {
-            if (may) {
-                const int pos = __popc(bits & lt_mask);
-                slot[pos].A = a_me;
-                slot[pos].B = b_me;
-                sc[pos] = make_float2(c_me, __int_as_float(range.x + 32 * g + lane));
-            }
             __syncwarp();
             const int cnt = __popc(bits);
 #pragma unroll 1
