@@ -226,8 +226,8 @@ def render_bwd(mean3ds, scales, quats, viewmat, colors, opacities, background, c
            _f32(conics, (n, 3), "conics"), _f32(compensation, (n, 1), "compensation"),
            _f32(final_Ts, (H, W, 1), "final_Ts"),
            _i32(final_idx, (H, W, 1), "final_idx"), _f32(v_img, (H, W, 3), "v_img"),
-           # None = zero cotangent for the alpha image (16x16 tiles only)
-           None if (v_img_alpha is None and block_width == 16) else _f32(
+           # None = zero cotangent for the alpha image (16x16 and 8x8 tiles: the tuned kernels)
+           None if (v_img_alpha is None and block_width in (8, 16)) else _f32(
                torch.zeros((H, W, 1), dtype=torch.float32, device=dev) if v_img_alpha is None
                else v_img_alpha, (H, W, 1), "v_img_alpha")]
     if grad_out is not None:
@@ -293,7 +293,7 @@ def render_views_bwd(mean3ds, scales, quats, viewmats, colors, opacities, backgr
     n, dev = num_points, mean3ds.device
     H, W = img_shape
     B = int(viewmats.shape[0])
-    if v_img_alphas is None and block_width != 16:
+    if v_img_alphas is None and block_width not in (8, 16):
         v_img_alphas = torch.zeros((B, H, W, 1), dtype=torch.float32, device=dev)
     ins = [_f32(mean3ds, (n, 3), "mean3ds"), _f32(scales, (n, 3), "scales"),
            _f32(quats, (n, 4), "quats"), _f32(viewmats, (B, 4, 4), "viewmats"),

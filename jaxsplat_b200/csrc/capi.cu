@@ -850,11 +850,12 @@ static int render_bwd_impl(cudaStream_t stream, void **buf, const Descriptor &d,
         JSB_CUDA_OK(cudaMemsetAsync(buf[23], 0, n * 3 * 4, stream));
     }
     float *v_xy_abs = nullptr;
-    if (d.block_width != 16 && !buf[16]) {
+    const bool tuned_bw = d.block_width == 16 || d.block_width == 8;
+    if (!tuned_bw && !buf[16]) {
         set_error("render_bwd: block_width %u needs a v_out_img_alpha buffer", d.block_width);
         return 1;
     }
-    if (d.block_width != 16) {  // the generic rasteriser always writes it: library scratch
+    if (!tuned_bw) {  // the generic rasteriser always writes it: library scratch
         if (c->ensure(c->abs_scratch, n * 2 * 4)) return 1;
         JSB_CUDA_OK(cudaMemsetAsync(c->abs_scratch.p, 0, n * 2 * 4, stream));
         v_xy_abs = (float *)c->abs_scratch.p;

@@ -383,7 +383,8 @@ struct HbStage {      // one sub-chunk of <= 32 visits
 // (project.cu: FINISH_MOMENTS) -- five packed multiplies per visit instead of eleven.
 // SUPER: super-column lists (RasterParams::sc_shift); with all_entries the entries whose tile
 // columns do not cover the tile are skipped like the forward skips them.
-template <bool ABS, bool MOMENTS, bool SUPER>
+// T8: block_width 8 -- the tile is the quadrant (one CTA per tile).
+template <bool ABS, bool MOMENTS, bool SUPER, bool T8 = false>
 __global__ void __launch_bounds__(32, JSB_BWDH_CTAS)
 raster_bwd_hits_kernel(const RasterParams p, const void *__restrict__ list,
                        const int2 *__restrict__ tile_bins, const SplatRecord *__restrict__ records,
@@ -399,11 +400,12 @@ raster_bwd_hits_kernel(const RasterParams p, const void *__restrict__ list,
     __shared__ __align__(16) float red[NV * RED_STRIDE];
 
     const int lane = threadIdx.x;
-    const unsigned quad = blockIdx.x & 3u, tile_local = blockIdx.x >> 2;
+    constexpr unsigned TS = T8 ? 8 : 16;  // tile size in pixels
+    const unsigned quad = T8 ? 0u : blockIdx.x & 3u, tile_local = T8 ? blockIdx.x : blockIdx.x >> 2;
     const unsigned tile = p.band_y0 * p.tiles_x + tile_local;
     const unsigned tile_y = tile / p.tiles_x, tile_x = tile - tile_y * p.tiles_x;
-    const unsigned j = tile_x * 16 + (quad & 1) * 8 + (lane & 7);
-    const unsigned i0 = tile_y * 16 + (quad >> 1) * 8 + (lane >> 3), i1 = i0 + 4;
+    const unsigned j = tile_x * TS + (quad & 1) * 8 + (lane & 7);
+    const unsigned i0 = tile_y * TS + (quad >> 1) * 8 + (lane >> 3), i1 = i0 + 4;
     const float px = (float)j + 0.5f, py0 = (float)i0 + 0.5f, py1 = (float)i1 + 0.5f;
     const bool in0 = (i0 < p.img_h) && (j < p.img_w), in1 = (i1 < p.img_h) && (j < p.img_w);
     const unsigned *ids_sorted = reinterpret_cast<const unsigned *>(list);
@@ -477,7 +479,7 @@ raster_bwd_hits_kernel(const RasterParams p, const void *__restrict__ list,
 
     const unsigned *hw = hit_words + (SUPER
         ? hit_quadrant_offset_super(range, super_local, tile_x & ((1u << p.sc_shift) - 1u), quad, p.sc_shift)
-        : hit_quadrant_offset(range, tile_local, quad));
+        : T8 ? hit_tile8_offset(range, tile_local) : hit_quadrant_offset(range, tile_local, quad));
     const int rel_top = top - range.x;
     for (int gs = rel_top >> 5; gs >= 0; gs -= HB_SPAN) {
         // ---- expand this span's hit words into visit positions, newest first -------------------
@@ -746,6 +748,24 @@ int launch_raster_bwd(cudaStream_t stream, const RasterParams &p, const void *li
                 v_out_alpha, v_xy, v_xy_abs, v_conic, v_colors, v_opacity);
         else
             raster_bwd_hits_kernel<false, false, true><<<tiles * 4, 32, 0, stream>>>(
+                p, list, tile_bins, records, hw, all, background, final_Ts, final_idx, v_out,
+                v_out_alpha, v_xy, v_xy_abs, v_conic, v_colors, v_opacity);
+        if (moments_out) *moments_out = !v_xy_abs;
+    } else if (p.block_width == 8 && !(g_bwd_no_hits && v_xy_abs)) {
+        // 8x8 tiles: the hit-driven kernel with the tile as its quadrant; without hit words (the
+        // backward rebuilt the lists itself) it replays every entry of the tile's range
+        const bool all = g_bwd_all_entries || hit_words == nullptr || g_bwd_no_hits;
+        const unsigned *hw = hit_words ? hit_words : reinterpret_cast<const unsigned *>(list);  // (not read)
+        if (v_xy_abs)
+            raster_bwd_hits_kernel<true, false, false, true><<<tiles, 32, 0, stream>>>(
+                p, list, tile_bins, records, hw, all, background, final_Ts, final_idx, v_out,
+                v_out_alpha, v_xy, v_xy_abs, v_conic, v_colors, v_opacity);
+        else if (moments_out)
+            raster_bwd_hits_kernel<false, true, false, true><<<tiles, 32, 0, stream>>>(
+                p, list, tile_bins, records, hw, all, background, final_Ts, final_idx, v_out,
+                v_out_alpha, v_xy, v_xy_abs, v_conic, v_colors, v_opacity);
+        else
+            raster_bwd_hits_kernel<false, false, false, true><<<tiles, 32, 0, stream>>>(
                 p, list, tile_bins, records, hw, all, background, final_Ts, final_idx, v_out,
                 v_out_alpha, v_xy, v_xy_abs, v_conic, v_colors, v_opacity);
         if (moments_out) *moments_out = !v_xy_abs;

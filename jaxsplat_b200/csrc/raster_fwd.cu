@@ -244,7 +244,9 @@ struct FwSlot {          // one compacted candidate
 
 // SUPER: the list is a super-column's (RasterParams::sc_shift): 8-byte row entries, of which the
 // tile keeps those whose tile columns cover it -- exactly the tile's own list, in the same order.
-template <bool CULL, bool SUPER>
+// T8: block_width 8 -- a tile IS one 8x8 quadrant, so each of the CTA's four warps takes a whole
+// tile of its own (tile 4 blockIdx + warp) and everything else is the same code.
+template <bool CULL, bool SUPER, bool T8>
 __global__ void __launch_bounds__(RF2, JSB_FWD_CTAS)
 raster_fwd_warp_kernel(const RasterParams p, const void *__restrict__ list,
                        const int2 *__restrict__ tile_bins, const SplatRecord *__restrict__ records,
@@ -255,10 +257,14 @@ raster_fwd_warp_kernel(const RasterParams p, const void *__restrict__ list,
     __shared__ float2 s_c[RF2 / 32][32];  // b, sorted index (bits)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const unsigned tile = p.band_y0 * p.tiles_x + blockIdx.x;
+    constexpr unsigned TS = T8 ? 8 : 16;  // tile size in pixels
+    const unsigned tile_local = T8 ? blockIdx.x * (RF2 / 32) + warp : blockIdx.x;
+    if (T8 && tile_local >= p.tiles_x * (p.band_y1 - p.band_y0)) return;  // (no CTA barrier below)
+    const unsigned tile = p.band_y0 * p.tiles_x + tile_local;
     const unsigned tile_y = tile / p.tiles_x, tile_x = tile - tile_y * p.tiles_x;
-    const unsigned j = tile_x * 16 + (warp & 1) * 8 + (lane & 7);
-    const unsigned i0 = tile_y * 16 + (warp >> 1) * 8 + (lane >> 3), i1 = i0 + 4;
+    const unsigned qx = T8 ? 0u : (warp & 1) * 8, qy = T8 ? 0u : (warp >> 1) * 8;  // quadrant in the tile
+    const unsigned j = tile_x * TS + qx + (lane & 7);
+    const unsigned i0 = tile_y * TS + qy + (lane >> 3), i1 = i0 + 4;
     const float px = (float)j + 0.5f, py0 = (float)i0 + 0.5f, py1 = (float)i1 + 0.5f;
     const bool in0 = (i0 < p.img_h) && (j < p.img_w), in1 = (i1 < p.img_h) && (j < p.img_w);
     bool done0 = !in0, done1 = !in1;
@@ -267,12 +273,12 @@ raster_fwd_warp_kernel(const RasterParams p, const void *__restrict__ list,
     const unsigned super_local = (tile_y - p.band_y0) * p.cols2 + (tile_x >> p.sc_shift);
     const int2 range = tile_bins[SUPER ? super_local : tile];
     const int ngroups = (range.y - range.x + 31) >> 5;
-    const float tile_x0 = (float)(tile_x * 16), tile_y0 = (float)(tile_y * 16);
-    const float quad_x0 = tile_x0 + (float)((warp & 1) * 8), quad_y0 = tile_y0 + (float)((warp >> 1) * 8);
+    const float quad_x0 = (float)(tile_x * TS + qx), quad_y0 = (float)(tile_y * TS + qy);
     const unsigned hw_off = SUPER
         ? (unsigned)hit_quadrant_offset_super(range, super_local, tile_x & ((1u << p.sc_shift) - 1u),
                                               (unsigned)warp, p.sc_shift)
-        : (unsigned)hit_quadrant_offset(range, blockIdx.x, (unsigned)warp);
+        : T8 ? (unsigned)hit_tile8_offset(range, tile_local)
+             : (unsigned)hit_quadrant_offset(range, tile_local, (unsigned)warp);
     const unsigned lt_mask = (1u << lane) - 1u;
     FwSlot *slot = s_slot[warp];
     float2 *sc = s_c[warp];
@@ -506,18 +512,28 @@ int launch_raster_fwd(cudaStream_t stream, const RasterParams &p, const void *li
     if (p.sc_shift) {
         if (wrote_hits) *wrote_hits = hit_words != nullptr;
         if (g_disable_cull)
-            raster_fwd_warp_kernel<false, true><<<tiles, RF2, 0, stream>>>(
+            raster_fwd_warp_kernel<false, true, false><<<tiles, RF2, 0, stream>>>(
                 p, list, tile_bins, records, background, final_Ts, final_idx, out_img, hit_words);
         else
-            raster_fwd_warp_kernel<true, true><<<tiles, RF2, 0, stream>>>(
+            raster_fwd_warp_kernel<true, true, false><<<tiles, RF2, 0, stream>>>(
                 p, list, tile_bins, records, background, final_Ts, final_idx, out_img, hit_words);
     } else if (p.block_width == 16 && !g_fwd_batch) {
         if (wrote_hits) *wrote_hits = hit_words != nullptr;
         if (g_disable_cull)
-            raster_fwd_warp_kernel<false, false><<<tiles, RF2, 0, stream>>>(
+            raster_fwd_warp_kernel<false, false, false><<<tiles, RF2, 0, stream>>>(
                 p, list, tile_bins, records, background, final_Ts, final_idx, out_img, hit_words);
         else
-            raster_fwd_warp_kernel<true, false><<<tiles, RF2, 0, stream>>>(
+            raster_fwd_warp_kernel<true, false, false><<<tiles, RF2, 0, stream>>>(
+                p, list, tile_bins, records, background, final_Ts, final_idx, out_img, hit_words);
+    } else if (p.block_width == 8 && !g_fwd_batch) {
+        // 8x8 tiles: one warp per tile, four tiles per CTA
+        if (wrote_hits) *wrote_hits = hit_words != nullptr;
+        const unsigned ctas = (tiles + RF2 / 32 - 1) / (RF2 / 32);
+        if (g_disable_cull)
+            raster_fwd_warp_kernel<false, false, true><<<ctas, RF2, 0, stream>>>(
+                p, list, tile_bins, records, background, final_Ts, final_idx, out_img, hit_words);
+        else
+            raster_fwd_warp_kernel<true, false, true><<<ctas, RF2, 0, stream>>>(
                 p, list, tile_bins, records, background, final_Ts, final_idx, out_img, hit_words);
     } else if (p.block_width == 16) {
         if (wrote_hits) *wrote_hits = hit_words != nullptr;

@@ -30,6 +30,12 @@ __device__ __forceinline__ size_t hit_quadrant_offset(const int2 range, unsigned
     return 4 * ((size_t)g0 + tile_local) + (size_t)quad * cap;
 }
 
+// block_width 8: a tile is one quadrant; tile t with list range [x, y) owns cap words starting at
+// word (x >> 5) + t (inside the capacity above).
+__device__ __forceinline__ size_t hit_tile8_offset(const int2 range, unsigned tile_local) {
+    return (size_t)((unsigned)range.x >> 5) + tile_local;
+}
+
 // Super-column lists (fused render): the list belongs to a super-column of T = 2^shift tiles of
 // one tile row, and each of its T tiles keeps its own four quadrant slices of the same length:
 // super-tile s (band-local index) with list range [x, y) owns 4 T cap words starting at word

@@ -529,3 +529,68 @@ def test_super_column_lists_render_the_same_image_and_gradients(case):
     finally:
         _lib.set_option("supercols", 2)
         _lib.set_option("cache", 1)
+
+
+@pytest.mark.parametrize("case", ["C2_30k", "ragged", "long_lists", "adversarial", "tiny"])
+def test_block_size_8_tuned_kernels_equal_the_generic_ones(case):
+    """block_size 8 (reference lib/ffi.cu:29-36 runs one kernel for any block width): a tile is one
+    8x8 quadrant, so the barrier-free forward and the hit-driven backward run it with one warp per
+    tile.  Against the generic one-thread-per-pixel kernels (options "fwdwarp" 0 / "bwdhits" 0):
+    final_idx, final_Ts and the image bit for bit, all five rasteriser gradients to 1e-4; and the
+    fused render (no v_xy_abs, raw moments) with and without the forward's hit
+    words (cache off: the backward rebuilds the lists and replays every entry)."""
+    import jaxsplat_b200 as jsb
+    if case == "C2_30k":
+        s = synthetic.make_config("C2", num_points=30000)
+    elif case == "ragged":
+        s = synthetic.benchmark_scene(777, (90, 50), scale_max=0.4, seed=6)
+    elif case == "long_lists":
+        s = _long_list_scene()
+    elif case == "adversarial":
+        s = _adversarial_scene()
+    else:
+        s = synthetic.benchmark_scene(60, (40, 40), scale_max=0.3, seed=3)
+    s.block_size = 8
+    inp = G.scene_inputs(s)
+    kw, rkw = G.scene_kw(s)
+    H, W = s.img_shape
+    target = np.random.RandomState(2).rand(H, W, 3).astype(np.float32)
+    v_alpha = np.random.RandomState(3).rand(H, W, 1).astype(np.float32) * 1e-3
+    try:
+        a = _full_gpu(inp, kw, rkw, target, v_alpha)
+        _lib.set_option("fwdwarp", 0)
+        _lib.set_option("bwdhits", 0)
+        b = _full_gpu(inp, kw, rkw, target, v_alpha)
+    finally:
+        _lib.set_option("fwdwarp", 1)
+        _lib.set_option("bwdhits", 1)
+    assert np.array_equal(a["final_idx"], b["final_idx"])
+    assert G.bits_equal(a["final_Ts"], b["final_Ts"]) == 0
+    assert G.bits_equal(a["img"], b["img"]) == 0
+    for k in ("v_colors", "v_opacity", "v_xy", "v_xy_abs", "v_conic"):
+        # (the generic kernel differentiates pixel by pixel in scalar arithmetic, the hit-driven one
+        # in regrouped packed arithmetic: the stated gradient tolerance, not atomic-order noise)
+        ok, err, scale = grad_close(a[k], b[k], rel=1e-4)
+        assert ok, (k, err, scale)
+    # fused render
+    sc = s.to(G.DEV)
+    tgt = torch.from_numpy(target).to(G.DEV)
+    res = {}
+    try:
+        for mode in ("tuned", "tuned_no_cache", "generic"):
+            _lib.set_option("cache", 0 if mode == "tuned_no_cache" else 1)
+            _lib.set_option("fwdwarp", 0 if mode == "generic" else 1)
+            _lib.set_option("bwdhits", 0 if mode == "generic" else 1)
+            params = [p.clone().requires_grad_(True) for p in sc.params()]
+            img = jsb.render(*params, **sc.render_kwargs())
+            ((img - tgt) ** 2).mean().backward()
+            res[mode] = (img.detach().clone(), [G.npy(p.grad) for p in params])
+    finally:
+        _lib.set_option("cache", 1)
+        _lib.set_option("fwdwarp", 1)
+        _lib.set_option("bwdhits", 1)
+    for mode in ("tuned", "tuned_no_cache"):
+        assert torch.equal(res[mode][0].view(torch.int32), res["generic"][0].view(torch.int32))
+        for x, y in zip(res[mode][1], res["generic"][1]):
+            ok, err, scale = grad_close(x, y, rel=1e-4 if case != "adversarial" else 5e-3)
+            assert ok, (mode, err, scale)
