@@ -95,8 +95,11 @@ JSB200_API void jsb200_rasterize_bwd_status(jsb200_stream_t stream, void **buffe
  *                    moments there that the projection backward consumes; v_cov2d / v_cov3d are
  *                    the projection VJP's intermediate cotangents; v_xy_abs, which nothing
  *                    downstream of rasterize_bwd reads, is not computed)
- * v_out_img_alpha may be NULL (= zero cotangent; block_width 16 only); v_cov2d / v_cov3d may be
- * NULL (not written: nothing downstream of a render reads them).
+ * v_out_img_alpha may be NULL (= zero cotangent; block_width 16 and 8 only); v_cov2d / v_cov3d may
+ * be NULL (not written: nothing downstream of a render reads them).
+ * Lean residuals: cov3ds and compensation may be NULL in render_fwd (not written) and in the
+ * matching render_bwd, which then recomputes the 3D covariance from scales and quaternions -- 28 /
+ * 24 bytes per Gaussian less.  Also valid for the per-view arrays of render_views_fwd / _bwd.
  * `opaque` is a full descriptor (f, c, glob_scale, clip_thresh set).  *token_out identifies the
  * binning this forward left in the per-(device, stream) workspace (0 = none); a render_bwd given
  * that token reuses it without any check or host synchronisation if no other binning ran on the

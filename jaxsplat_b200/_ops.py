@@ -51,6 +51,11 @@ def _f32(t: torch.Tensor, shape, name: str) -> torch.Tensor:
     return t.contiguous()
 
 
+def _f32n(t, shape, name: str):
+    """a float32 tensor of `shape`, or None (lean residuals: not produced / recomputed)"""
+    return None if t is None else _f32(t, shape, name)
+
+
 def _i32(t: torch.Tensor, shape, name: str) -> torch.Tensor:
     if t.dtype != torch.int32 or tuple(t.shape) != tuple(shape):
         raise TypeError(f"{name}: expected int32{tuple(shape)}, got {t.dtype}{tuple(t.shape)}")
@@ -172,10 +177,11 @@ def _call_native(fn_name, tensors, opaque, *extra):
 
 
 def render_fwd(mean3ds, scales, quats, viewmat, colors, opacities, background, *, num_points,
-               img_shape, f, c, glob_scale, clip_thresh, block_width, band=None):
+               img_shape, f, c, glob_scale, clip_thresh, block_width, band=None, lean=False):
     """project_fwd + binning + rasterize_fwd in one native call (jsb200_render_fwd).  Returns
     ((cov3ds, xys, depths, radii, conics, compensation, final_Ts, final_idx, img), token);
-    outputs are bit-identical to the two-op chain."""
+    outputs are bit-identical to the two-op chain.  lean=True: cov3ds / compensation are not
+    produced (None) -- ``render_bwd`` given None for cov3ds recomputes the covariance."""
     import ctypes
 
     n, dev = num_points, mean3ds.device
@@ -184,9 +190,10 @@ def render_fwd(mean3ds, scales, quats, viewmat, colors, opacities, background, *
            _f32(quats, (n, 4), "quats"), _f32(viewmat, (4, 4), "viewmat"),
            _f32(colors, (n, 3), "colors"), _f32(opacities, (n, 1), "opacities"),
            _f32(background, (3,), "background")]
-    outs = [_out((n, 6), torch.float32, dev), _out((n, 2), torch.float32, dev),
+    outs = [None if lean else _out((n, 6), torch.float32, dev), _out((n, 2), torch.float32, dev),
             _out((n, 1), torch.float32, dev), _out((n, 1), torch.int32, dev),
-            _out((n, 3), torch.float32, dev), _out((n, 1), torch.float32, dev)]
+            _out((n, 3), torch.float32, dev),
+            None if lean else _out((n, 1), torch.float32, dev)]
     if band is not None:  # only the band's pixel rows are written: the rest of the frame is zero
         outs += [torch.zeros((H, W, 1), dtype=torch.float32, device=dev),
                  torch.zeros((H, W, 1), dtype=torch.int32, device=dev),
@@ -221,9 +228,9 @@ def render_bwd(mean3ds, scales, quats, viewmat, colors, opacities, background, c
     ins = [_f32(mean3ds, (n, 3), "mean3ds"), _f32(scales, (n, 3), "scales"),
            _f32(quats, (n, 4), "quats"), _f32(viewmat, (4, 4), "viewmat"),
            _f32(colors, (n, 3), "colors"), _f32(opacities, (n, 1), "opacities"),
-           _f32(background, (3,), "background"), _f32(cov3ds, (n, 6), "cov3ds"),
+           _f32(background, (3,), "background"), _f32n(cov3ds, (n, 6), "cov3ds"),
            _f32(xys, (n, 2), "xys"), _f32(depths, (n, 1), "depths"), _i32(radii, (n, 1), "radii"),
-           _f32(conics, (n, 3), "conics"), _f32(compensation, (n, 1), "compensation"),
+           _f32(conics, (n, 3), "conics"), _f32n(compensation, (n, 1), "compensation"),
            _f32(final_Ts, (H, W, 1), "final_Ts"),
            _i32(final_idx, (H, W, 1), "final_idx"), _f32(v_img, (H, W, 3), "v_img"),
            # None = zero cotangent for the alpha image (16x16 and 8x8 tiles: the tuned kernels)
@@ -256,7 +263,7 @@ def render_bwd(mean3ds, scales, quats, viewmat, colors, opacities, background, c
 
 # ---- batched cameras: this library only ------------------------------------------
 def render_views_fwd(mean3ds, scales, quats, viewmats, colors, opacities, background, *,
-                     num_points, img_shape, f, c, glob_scale, clip_thresh, block_width):
+                     num_points, img_shape, f, c, glob_scale, clip_thresh, block_width, lean=False):
     """B cameras of the same Gaussians in one native call (jsb200_render_views_fwd).  Returns
     ((cov3ds, xys, depths, radii, conics, compensation, final_Ts, final_idx, imgs), tokens), every
     array with a leading view axis; view b is bit-identical to ``render_fwd`` with viewmats[b]."""
@@ -271,9 +278,10 @@ def render_views_fwd(mean3ds, scales, quats, viewmats, colors, opacities, backgr
            _f32(quats, (n, 4), "quats"), _f32(viewmats, (B, 4, 4), "viewmats"),
            _f32(colors, (n, 3), "colors"), _f32(opacities, (n, 1), "opacities"),
            _f32(background, (3,), "background")]
-    outs = [_out((B, n, 6), torch.float32, dev), _out((B, n, 2), torch.float32, dev),
+    outs = [None if lean else _out((B, n, 6), torch.float32, dev), _out((B, n, 2), torch.float32, dev),
             _out((B, n, 1), torch.float32, dev), _out((B, n, 1), torch.int32, dev),
-            _out((B, n, 3), torch.float32, dev), _out((B, n, 1), torch.float32, dev),
+            _out((B, n, 3), torch.float32, dev),
+            None if lean else _out((B, n, 1), torch.float32, dev),
             _out((B, H, W, 1), torch.float32, dev), _out((B, H, W, 1), torch.int32, dev),
             _out((B, H, W, 3), torch.float32, dev)]
     d = _ffi.make_descriptor(n, tuple(img_shape), tuple(f), tuple(c), glob_scale, clip_thresh,
@@ -298,10 +306,10 @@ def render_views_bwd(mean3ds, scales, quats, viewmats, colors, opacities, backgr
     ins = [_f32(mean3ds, (n, 3), "mean3ds"), _f32(scales, (n, 3), "scales"),
            _f32(quats, (n, 4), "quats"), _f32(viewmats, (B, 4, 4), "viewmats"),
            _f32(colors, (n, 3), "colors"), _f32(opacities, (n, 1), "opacities"),
-           _f32(background, (3,), "background"), _f32(cov3ds, (B, n, 6), "cov3ds"),
+           _f32(background, (3,), "background"), _f32n(cov3ds, (B, n, 6), "cov3ds"),
            _f32(xys, (B, n, 2), "xys"), _f32(depths, (B, n, 1), "depths"),
            _i32(radii, (B, n, 1), "radii"), _f32(conics, (B, n, 3), "conics"),
-           _f32(compensation, (B, n, 1), "compensation"),
+           _f32n(compensation, (B, n, 1), "compensation"),
            _f32(final_Ts, (B, H, W, 1), "final_Ts"), _i32(final_idx, (B, H, W, 1), "final_idx"),
            _f32(v_imgs, (B, H, W, 3), "v_imgs"),
            None if v_img_alphas is None else _f32(v_img_alphas, (B, H, W, 1), "v_img_alphas")]

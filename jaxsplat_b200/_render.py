@@ -38,7 +38,9 @@ class _Render(torch.autograd.Function):
                 viewmat, background):
         (cov3ds, xys, depths, radii, conics, compensation, final_Ts, final_idx,
          img), token = _ops.render_fwd(means3d, scales, quats, viewmat, colors, opacities,
-                                       background, band=band, **desc.kwargs())
+                                       background, band=band, lean=True, **desc.kwargs())
+        # (lean: cov3ds / compensation are None -- the backward recomputes the covariance from scales
+        # and quaternions instead of the forward writing and the backward reading 24 bytes per Gaussian)
         ctx.desc, ctx.band, ctx.token = desc, band, token
         ctx.save_for_backward(means3d, scales, quats, viewmat, colors, opacities, background,
                               cov3ds, xys, depths, radii, conics, compensation, final_Ts,
@@ -80,7 +82,7 @@ class _RenderViews(torch.autograd.Function):
                 background):
         (cov3ds, xys, depths, radii, conics, compensation, final_Ts, final_idx,
          imgs), tokens = _ops.render_views_fwd(means3d, scales, quats, viewmats, colors, opacities,
-                                               background, **desc.kwargs())
+                                               background, lean=True, **desc.kwargs())
         ctx.desc, ctx.tokens = desc, tokens
         ctx.save_for_backward(means3d, scales, quats, viewmats, colors, opacities, background,
                               cov3ds, xys, depths, radii, conics, compensation, final_Ts,

@@ -606,13 +606,9 @@ static int forward_lists_and_raster(Ctx &c, const Descriptor &d, const float *ba
 }
 
 // ---- op bodies ---------------------------------------------------------------------------------
-static int project_fwd_locked(Ctx *c, cudaStream_t stream, void **buf, const Descriptor &d,
-                              const FusedPrep *fused) {
-    const unsigned n = d.num_points;
-    if (n == 0) return 0;
-    if (d.block_width == 0) { set_error("block_width must be > 0"); return 1; }
+static ProjectFwdParams project_fwd_params(const Descriptor &d) {
     ProjectFwdParams p;
-    p.num_points = n;
+    p.num_points = d.num_points;
     p.glob_scale = d.glob_scale;
     p.fx = d.fx; p.fy = d.fy; p.cx = d.cx; p.cy = d.cy;
     p.tan_fovx = (float)(0.5 * (double)d.img_w / (double)d.fx);
@@ -621,6 +617,15 @@ static int project_fwd_locked(Ctx *c, cudaStream_t stream, void **buf, const Des
     p.block_width_f = (float)(int)d.block_width;
     p.tiles_x = d.tiles_x; p.tiles_y = d.tiles_y;
     p.sc_shift = g_sc_shift;
+    return p;
+}
+
+static int project_fwd_locked(Ctx *c, cudaStream_t stream, void **buf, const Descriptor &d,
+                              const FusedPrep *fused) {
+    const unsigned n = d.num_points;
+    if (n == 0) return 0;
+    if (d.block_width == 0) { set_error("block_width must be > 0"); return 1; }
+    const ProjectFwdParams p = project_fwd_params(d);
     const size_t chain_bytes = (size_t)ceil_div(n, 256) * 8 + 64;
     if (c->ensure(c->chain, chain_bytes)) return 1;
     StageScope ss(c, ST_PROJECT_FWD);
@@ -651,6 +656,7 @@ static int project_bwd_impl2(cudaStream_t stream, void **buf, const Descriptor &
     // in: 0 mean3ds 1 scales 2 quats 3 viewmat 4 cov3ds 5 xys 6 radii 7 conics 8 compensation
     //     9 v_compensation 10 v_xy 11 v_depth 12 v_conic ; out: 13 v_mean3d 14 v_scale 15 v_quat
     //     16 v_cov2d 17 v_cov3d
+    if (d.block_width == 0) { set_error("block_width must be > 0"); return 1; }
     return launch_project_bwd(stream, p, (const float *)buf[0], (const float *)buf[1],
                               (const float *)buf[2], (const float *)buf[3], (const float *)buf[4],
                               (const int *)buf[6], (const float *)buf[7], (const float *)buf[8],
@@ -770,6 +776,8 @@ static int render_fwd_impl(cudaStream_t stream, void **buf, const Descriptor &d,
     // in : 0 means3d 1 scales 2 quats 3 viewmat 4 colors 5 opacities 6 background
     // out: 7 cov3ds 8 xys 9 depths 10 radii 11 conics 12 compensation 13 final_Ts 14 final_idx
     //      15 out_img   (num_tiles_hit / cum_tiles_hit are not produced: nothing reads them)
+    // cov3ds / compensation may be NULL (lean residuals): they are then not written, and render_bwd
+    // given NULL for cov3ds recomputes the covariance from scales and quaternions
     if (token) *token = 0;
     if (check_raster_desc(d)) return 1;
     void *pbuf[12] = {buf[0], buf[1], buf[2], buf[3], buf[7], buf[8], buf[9], buf[10], buf[11],
@@ -869,8 +877,9 @@ static int render_bwd_impl(cudaStream_t stream, void **buf, const Descriptor &d,
         g_stats[3].fetch_add(1);
     } else {
         unsigned long long I = 0, fp = 0;
+        const float *conics = (const float *)buf[11];
         if (bin_prepare_enqueue(*c, d, (const float *)buf[8], (const float *)buf[9],
-                                (const int *)buf[10], (const float *)buf[11], (const float *)buf[5],
+                                (const int *)buf[10], conics, (const float *)buf[5],
                                 (const float *)buf[4], /*write=*/true, /*fingerprint=*/false))
             return 1;
         if (bin_prepare_wait(*c, d, &I, &fp)) return 1;
@@ -926,9 +935,10 @@ static int render_views_fwd_impl(cudaStream_t stream, void **buf, const Descript
     for (unsigned b = 0; b < B; ++b) {
         void *vb[16] = {buf[0], buf[1], buf[2], (float *)buf[3] + 16 * (size_t)b, buf[4], buf[5],
                         buf[6],
-                        (float *)buf[7] + b * n * 6, (float *)buf[8] + b * n * 2,
+                        buf[7] ? (void *)((float *)buf[7] + b * n * 6) : nullptr, (float *)buf[8] + b * n * 2,
                         (float *)buf[9] + b * n, (int *)buf[10] + b * n,
-                        (float *)buf[11] + b * n * 3, (float *)buf[12] + b * n,
+                        (float *)buf[11] + b * n * 3,
+                        buf[12] ? (void *)((float *)buf[12] + b * n) : nullptr,
                         (float *)buf[13] + b * px, (int *)buf[14] + b * px,
                         (float *)buf[15] + b * px * 3};
         unsigned long long tok = 0;
@@ -969,9 +979,10 @@ static int render_views_bwd_impl(cudaStream_t stream, void **buf, const Descript
         const bool first = (i == 0);
         void *vb[26] = {buf[0], buf[1], buf[2], (float *)buf[3] + 16 * (size_t)b, buf[4], buf[5],
                         buf[6],
-                        (float *)buf[7] + b * n * 6, (float *)buf[8] + b * n * 2,
+                        buf[7] ? (void *)((float *)buf[7] + b * n * 6) : nullptr, (float *)buf[8] + b * n * 2,
                         (float *)buf[9] + b * n, (int *)buf[10] + b * n,
-                        (float *)buf[11] + b * n * 3, (float *)buf[12] + b * n,
+                        (float *)buf[11] + b * n * 3,
+                        buf[12] ? (void *)((float *)buf[12] + b * n) : nullptr,
                         (float *)buf[13] + b * px, (int *)buf[14] + b * px,
                         (float *)buf[15] + b * px * 3,
                         buf[16] ? (void *)((float *)buf[16] + b * px) : nullptr,

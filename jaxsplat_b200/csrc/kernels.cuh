@@ -43,6 +43,7 @@ int launch_project_fwd(cudaStream_t stream, const ProjectFwdParams &p, const flo
                        unsigned *block_totals /* ceil(N/256) scratch words */,
                        const FusedPrep *fused = nullptr);
 
+// cov3ds == nullptr (lean residuals): the 3D covariance is recomputed from scales and quaternions.
 int launch_project_bwd(cudaStream_t stream, const ProjectBwdParams &p, const float *means3d,
                        const float *scales, const float *quats, const float *viewmat,
                        const float *cov3ds, const int *radii, const float *conics,

@@ -277,13 +277,14 @@ project_fwd_kernel(const ProjectFwdParams p, const float *__restrict__ means3d,
         xys[idx] = o.xy;
         depths[idx] = o.depth;
         radii[idx] = o.radius;
-        compensation[idx] = o.comp;
+        if (compensation) compensation[idx] = o.comp;
         // (the fused render passes null: nothing downstream of it reads the tile counts)
         if (num_tiles_hit) num_tiles_hit[idx] = o.tiles;
     }
-    warp_store_aos<6>(strip, o.cov3d, cov3ds, wfirst * 6, n * 6, lane);
+    // (null = lean residuals of the fused render: the projection backward recomputes them)
+    if (cov3ds) warp_store_aos<6>(strip, o.cov3d, cov3ds, wfirst * 6, n * 6, lane);
     const float cn[3] = {o.conic.x, o.conic.y, o.conic.z};
-    warp_store_aos<3>(strip, cn, conics, wfirst * 3, n * 3, lane);
+    if (conics) warp_store_aos<3>(strip, cn, conics, wfirst * 3, n * 3, lane);
 
     if (cum_tiles_hit) {
         // CTA-local inclusive count; add_block_prefix_kernel adds the scanned CTA totals
@@ -346,7 +347,12 @@ project_fwd_kernel(const ProjectFwdParams p, const float *__restrict__ means3d,
 // opacity * vis * v_alpha; with the conic and the opacity at hand they become
 //   v_xy = -(cx Mx + cy My, cy Mx + cz My), v_conic = -(Mxx / 2, Mxy, Myy / 2), v_opacity = M0 / opacity
 // here, and moment_opacity[i] is overwritten with v_opacity.
-template <bool FINISH_MOMENTS>
+// RECOMPUTE (lean residuals of the fused render: cov3ds == null): the 3D covariance is re-derived
+// from the rotation and the scales this kernel needs anyway (21 multiply-adds) instead of being
+// written by the forward and read back here: 24 bytes per Gaussian less in each direction.
+// (Recomputing the conic as well -- the whole EWA projection -- was measured: the forward gained
+// 4.5 us, this kernel lost 4 us; profiles/r03a_bench_C3_recompute_conic.json.)
+template <bool FINISH_MOMENTS, bool RECOMPUTE>
 __global__ void __launch_bounds__(PT)
 project_bwd_kernel(const ProjectBwdParams p, const float *__restrict__ means3d,
                    const float *__restrict__ scales, const float4 *__restrict__ quats,
@@ -376,17 +382,35 @@ project_bwd_kernel(const ProjectBwdParams p, const float *__restrict__ means3d,
         const float sc0 = __ldg(scales + idx * 3), sc1 = __ldg(scales + idx * 3 + 1),
                     sc2 = __ldg(scales + idx * 3 + 2);
         const float4 q = __ldg(quats + idx);
-        const float k0 = __ldg(cov3ds + idx * 6), k1 = __ldg(cov3ds + idx * 6 + 1),
-                    k2 = __ldg(cov3ds + idx * 6 + 2), k3 = __ldg(cov3ds + idx * 6 + 3),
-                    k4 = __ldg(cov3ds + idx * 6 + 4), k5 = __ldg(cov3ds + idx * 6 + 5);
+        // R(q), q = (w, x, y, z), and the scaled axes: also what the scale / quaternion VJP needs
+        const float w = q.x, x = q.y, y = q.z, z = q.w;
+        const float R00 = 1.f - 2.f * (y * y + z * z), R01 = 2.f * (x * y - w * z), R02 = 2.f * (x * z + w * y);
+        const float R10 = 2.f * (x * y + w * z), R11 = 1.f - 2.f * (x * x + z * z), R12 = 2.f * (y * z - w * x);
+        const float R20 = 2.f * (x * z - w * y), R21 = 2.f * (y * z + w * x), R22 = 1.f - 2.f * (x * x + y * y);
+        const float gs = p.glob_scale;
+        const float s0 = gs * sc0, s1 = gs * sc1, s2 = gs * sc2;
+        float k0, k1, k2, k3, k4, k5;
+        if (RECOMPUTE) {  // V = R S S R^T
+            const float e0 = s0 * s0, e1 = s1 * s1, e2 = s2 * s2;
+            k0 = e0 * R00 * R00 + e1 * R01 * R01 + e2 * R02 * R02;
+            k1 = e0 * R00 * R10 + e1 * R01 * R11 + e2 * R02 * R12;
+            k2 = e0 * R00 * R20 + e1 * R01 * R21 + e2 * R02 * R22;
+            k3 = e0 * R10 * R10 + e1 * R11 * R11 + e2 * R12 * R12;
+            k4 = e0 * R10 * R20 + e1 * R11 * R21 + e2 * R12 * R22;
+            k5 = e0 * R20 * R20 + e1 * R21 * R21 + e2 * R22 * R22;
+        } else {
+            k0 = __ldg(cov3ds + idx * 6); k1 = __ldg(cov3ds + idx * 6 + 1);
+            k2 = __ldg(cov3ds + idx * 6 + 2); k3 = __ldg(cov3ds + idx * 6 + 3);
+            k4 = __ldg(cov3ds + idx * 6 + 4); k5 = __ldg(cov3ds + idx * 6 + 5);
+        }
         const float cx = __ldg(conics + idx * 3), cy = __ldg(conics + idx * 3 + 1),
                     cz = __ldg(conics + idx * 3 + 2);
         float gx = __ldg(v_conic + idx * 3), gy = 0.5f * __ldg(v_conic + idx * 3 + 1),
               gz = __ldg(v_conic + idx * 3 + 2);
         float2 vxy = __ldg(v_xy + idx);
         if (FINISH_MOMENTS) {
-            const float mx = vxy.x, my = vxy.y;
-            vxy = make_float2(-(cx * mx + cy * my), -(cy * mx + cz * my));
+            const float mmx = vxy.x, mmy = vxy.y;
+            vxy = make_float2(-(cx * mmx + cy * mmy), -(cy * mmx + cz * mmy));
             gx *= -0.5f;   // v_conic.x = -Mxx / 2
             gy = -gy;      // v_conic.y / 2 = -Mxy / 2
             gz *= -0.5f;   // v_conic.z = -Myy / 2
@@ -470,12 +494,6 @@ project_bwd_kernel(const ProjectBwdParams p, const float *__restrict__ means3d,
         o_mean[0] = vm_x; o_mean[1] = vm_y; o_mean[2] = vm_z;
 
         // scale_rot_to_cov3d_vjp (backward.cu:528-570): M = R S, v_M = 2 v_V M
-        const float w = q.x, x = q.y, y = q.z, z = q.w;
-        const float R00 = 1.f - 2.f * (y * y + z * z), R01 = 2.f * (x * y - w * z), R02 = 2.f * (x * z + w * y);
-        const float R10 = 2.f * (x * y + w * z), R11 = 1.f - 2.f * (x * x + z * z), R12 = 2.f * (y * z - w * x);
-        const float R20 = 2.f * (x * z - w * y), R21 = 2.f * (y * z + w * x), R22 = 1.f - 2.f * (x * x + y * y);
-        const float gs = p.glob_scale;
-        const float s0 = gs * sc0, s1 = gs * sc1, s2 = gs * sc2;
         // B = v_V R (3x3); v_M[r][c] = 2 s_c B[r][c]
         const float B00 = V00 * R00 + V01 * R10 + V02 * R20, B01 = V00 * R01 + V01 * R11 + V02 * R21,
                     B02 = V00 * R02 + V01 * R12 + V02 * R22;
@@ -568,16 +586,28 @@ int launch_project_bwd(cudaStream_t stream, const ProjectBwdParams &p, const flo
                        const float *opacities, float *moment_opacity) {
     if (p.num_points == 0) return 0;
     const unsigned blocks = ceil_div(p.num_points, PT);
-    if (opacities && moment_opacity)
-        project_bwd_kernel<true><<<blocks, PT, 0, stream>>>(
-            p, means3d, scales, reinterpret_cast<const float4 *>(quats), viewmat, cov3ds, radii,
-            conics, compensation, v_compensation, reinterpret_cast<const float2 *>(v_xy), v_depth,
-            v_conic, v_mean3d, v_scale, v_quat, v_cov2d, v_cov3d, opacities, moment_opacity);
-    else
-        project_bwd_kernel<false><<<blocks, PT, 0, stream>>>(
-            p, means3d, scales, reinterpret_cast<const float4 *>(quats), viewmat, cov3ds, radii,
-            conics, compensation, v_compensation, reinterpret_cast<const float2 *>(v_xy), v_depth,
-            v_conic, v_mean3d, v_scale, v_quat, v_cov2d, v_cov3d, nullptr, nullptr);
+    const bool recompute = cov3ds == nullptr;
+    if (v_compensation && !compensation) {
+        set_error("project_bwd: a compensation cotangent needs the forward's compensation");
+        return 1;
+    }
+    if (!conics || !radii) {
+        set_error("project_bwd: conics / radii missing");
+        return 1;
+    }
+    const bool finish = opacities && moment_opacity;
+    const float4 *q4 = reinterpret_cast<const float4 *>(quats);
+    const float2 *vxy2 = reinterpret_cast<const float2 *>(v_xy);
+#define JSB_PBWD(F, R)                                                                              \
+    project_bwd_kernel<F, R><<<blocks, PT, 0, stream>>>(                                            \
+        p, means3d, scales, q4, viewmat, cov3ds, radii, conics, compensation, v_compensation,   \
+        vxy2, v_depth, v_conic, v_mean3d, v_scale, v_quat, v_cov2d, v_cov3d,                        \
+        finish ? opacities : nullptr, finish ? moment_opacity : nullptr)
+    if (finish && recompute) JSB_PBWD(true, true);
+    else if (finish) JSB_PBWD(true, false);
+    else if (recompute) JSB_PBWD(false, true);
+    else JSB_PBWD(false, false);
+#undef JSB_PBWD
     JSB_CUDA_OK(cudaGetLastError());
     note_launch();
     return 0;

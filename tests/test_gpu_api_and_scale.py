@@ -7,7 +7,7 @@ import torch
 from conftest import grad_close
 import gpu_util as G
 import jaxsplat_b200 as jsb
-from jaxsplat_b200 import synthetic
+from jaxsplat_b200 import _ops, synthetic
 from oracle import ref_cuda
 
 pytestmark = pytest.mark.gpu
@@ -356,3 +356,48 @@ def test_reference_style_descriptor_with_garbage_pad_bytes_renders_the_full_fram
     got = G.rasterize_fwd(inp, P, rkw, table=GarbagePad(_ffi.native_table()))
     assert torch.equal(got["final_idx"], want["final_idx"])
     assert torch.equal(got["img"].view(torch.int32), want["img"].view(torch.int32))
+
+
+def test_lean_residuals_recompute_in_the_backward():
+    """render_fwd / render_bwd with NULL cov3ds / compensation (what ``render`` passes): the
+    projection backward re-derives the 3D covariance from scales and quaternions, so the gradients
+    equal those of the full-residual call to float rounding -- full frame, a tile-row band, a
+    stale token (the backward rebuilds the lists), and batched cameras"""
+    from jaxsplat_b200 import _lib
+    s = synthetic.make_config("C2", num_points=30000)
+    sc = s.to(G.DEV)
+    H, W = s.img_shape
+    n = sc.means3d.shape[0]
+    kw = dict(num_points=n, img_shape=s.img_shape, f=s.f, c=s.c, glob_scale=s.glob_scale,
+              clip_thresh=s.clip_thresh, block_width=16)
+    v_img = torch.rand((H, W, 3), generator=torch.Generator().manual_seed(4)).to(G.DEV) * 1e-3
+    ins = (sc.means3d, sc.scales, sc.quats, sc.viewmat, sc.colors, sc.opacities, sc.background)
+    for band in (None, (3, 17)):
+        res = {}
+        for lean, stale in ((False, False), (True, False), (True, True)):
+            outs, tok = _ops.render_fwd(*ins, band=band, lean=lean, **kw)
+            assert (outs[0] is None) == lean and (outs[5] is None) == lean
+            if stale:  # another binning on the same workspace: the token no longer matches
+                _ops.render_fwd(sc.means3d * 1.01, *ins[1:], band=band, lean=lean, **kw)
+            g = _ops.render_bwd(*ins, *outs[:8], v_img, None, token=tok, band=band, **kw)
+            res[(lean, stale)] = (outs[8].clone(), [G.npy(x) for x in g[:5]])
+        for key in ((True, False), (True, True)):
+            assert torch.equal(res[key][0], res[(False, False)][0])
+            for a, b in zip(res[key][1], res[(False, False)][1]):
+                ok, err, scale = grad_close(a, b, rel=2e-5)
+                assert ok, (band, key, err, scale)
+    # batched cameras
+    vm = torch.stack([sc.viewmat, sc.viewmat.clone()])
+    vm[1, 0, 3] += 0.3
+    v_imgs = torch.stack([v_img, v_img * 0.5])
+    got = {}
+    for lean in (False, True):
+        outs, toks = _ops.render_views_fwd(sc.means3d, sc.scales, sc.quats, vm, sc.colors, sc.opacities,
+                                           sc.background, lean=lean, **kw)
+        g = _ops.render_views_bwd(sc.means3d, sc.scales, sc.quats, vm, sc.colors, sc.opacities,
+                                  sc.background, *outs[:8], v_imgs, None, tokens=toks, **kw)
+        got[lean] = (outs[8].clone(), [G.npy(x) for x in g])
+    assert torch.equal(got[True][0], got[False][0])
+    for a, b in zip(got[True][1], got[False][1]):
+        ok, err, scale = grad_close(a, b, rel=2e-5)
+        assert ok, (err, scale)
