@@ -577,7 +577,9 @@ raster_bwd_hits_kernel(const RasterParams p, const void *__restrict__ list,
                 total_r += __shfl_xor_sync(0xffffffffu, total_r, 1);
                 if (writer && pend) atomicAdd(out_base + pend_id * (unsigned)out_stride, total_r);
                 pend = false;
-                if (!__any_sync(0xffffffffu, ok0 || ok1)) continue;
+                // (a hit-driven visit has an accepting pixel by construction; only the replay of
+                // EVERY entry meets visits without one, worth a vote to skip)
+                if (all_entries && !__any_sync(0xffffffffu, ok0 || ok1)) continue;
 
                 // invalid pixels: vis = 0 makes alpha = 0, ra = rcp(1) = 1 and every partial
                 // exactly 0, and leaves T and the colour buffer unchanged
