@@ -461,8 +461,14 @@ raster_bwd_hits_kernel(const RasterParams p, const void *__restrict__ list,
     else { out_base = v_xy_abs + (slot - 9); out_stride = 2; }
     const bool writer = ((lane & 1) == 0) && slot < NV;
 
-    bool pend = false;       // `red` holds the partials of a visit that is not reduced yet
-    unsigned pend_id = 0;    // its Gaussian
+    // `red` always holds the partials of the previous visit (zeros before the first one) and
+    // pend_id its Gaussian: the reduction + atomics at the top of every visit need no flag.  Before
+    // the first visit the zeros go to the warp's own first Gaussian (not to one shared word).
+    unsigned pend_id = 0;
+    bool first_chunk = true;
+#pragma unroll
+    for (int r = 0; r < NV; ++r) red[r * RED_STRIDE + lane] = 0.f;
+    __syncwarp();
     const float4 *red_row = reinterpret_cast<const float4 *>(
         red + min(lane >> 1, NV - 1) * RED_STRIDE + (lane & 1) * 16);
     auto reduce_rows = [&]() -> float {
@@ -551,12 +557,16 @@ raster_bwd_hits_kernel(const RasterParams p, const void *__restrict__ list,
             fetch((s + 2) * 32 + lane);
             const HbStage &S = st[s & 1];
             const int cs = min(32, total - s * 32);
+            if (first_chunk) {  // warp-uniform, once per kernel
+                pend_id = __float_as_uint(S.C[0].y);
+                first_chunk = false;
+            }
 #pragma unroll 1
             for (int t = 0; t < cs; ++t) {
                 const float4 a = S.A[t];    // {x, y, opacity, cx}
                 const float4 bq = S.B[t];   // {cy, cz, r, g}
                 const float4 cq = S.C[t];   // {b, id, sorted index, -}
-                float total_r = reduce_rows();  // previous visit's partials (stale rows if !pend)
+                float total_r = reduce_rows();  // previous visit's partials
                 // conic_sigma (common.cuh) lane by lane, in the reference's operation order
                 const float dx = fsub(a.x, px);
                 const float2 dy2 = __fadd2_rn(bc(a.y), npy2);
@@ -575,17 +585,23 @@ raster_bwd_hits_kernel(const RasterParams p, const void *__restrict__ list,
                 const bool ok0 = in0 && (sidx <= bf0) && !(sg2.x < 0.f) && !(al0 < kAlphaMin);
                 const bool ok1 = in1 && (sidx <= bf1) && !(sg2.y < 0.f) && !(al1 < kAlphaMin);
                 total_r += __shfl_xor_sync(0xffffffffu, total_r, 1);
-                if (writer && pend) atomicAdd(out_base + pend_id * (unsigned)out_stride, total_r);
-                pend = false;
+                if (writer) atomicAdd(out_base + pend_id * (unsigned)out_stride, total_r);
                 // (a hit-driven visit has an accepting pixel by construction; only the replay of
-                // EVERY entry meets visits without one, worth a vote to skip)
-                if (all_entries && !__any_sync(0xffffffffu, ok0 || ok1)) continue;
+                // EVERY entry meets visits without one, worth a vote to skip -- leaving zero rows)
+                if (all_entries && !__any_sync(0xffffffffu, ok0 || ok1)) {
+                    __syncwarp();
+#pragma unroll
+                    for (int r = 0; r < NV; ++r) red[r * RED_STRIDE + lane] = 0.f;
+                    __syncwarp();
+                    continue;
+                }
 
                 // invalid pixels: vis = 0 makes alpha = 0, ra = rcp(1) = 1 and every partial
                 // exactly 0, and leaves T and the colour buffer unchanged
                 const float2 vis2 = f2(ok0 ? vis0 : 0.f, ok1 ? vis1 : 0.f);
-                const float2 av2 = __fmul2_rn(bc(a.z), vis2);                  // opacity * vis
-                const float2 al2 = f2(fminf(av2.x, 0.99f), fminf(av2.y, 0.99f));
+                // (opacity * vis and its clamp were evaluated for the accept test: selected, not redone)
+                const float2 av2 = f2(ok0 ? ar2.x : 0.f, ok1 ? ar2.y : 0.f);   // opacity * vis
+                const float2 al2 = f2(ok0 ? al0 : 0.f, ok1 ? al1 : 0.f);
                 const float2 om2 = __ffma2_rn(al2, bc(-1.f), bc(1.f));         // 1 - alpha
                 float r0, r1;
                 asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(om2.x));
@@ -639,12 +655,11 @@ raster_bwd_hits_kernel(const RasterParams p, const void *__restrict__ list,
 #pragma unroll
                 for (int r = 0; r < NV; ++r) red[r * RED_STRIDE + lane] = v[r];
                 __syncwarp();
-                pend = true;
                 pend_id = __float_as_uint(cq.y);
             }
         }
     }
-    if (pend) {  // warp-uniform: the last visit of this warp
+    if (!first_chunk) {  // warp-uniform: the last visit of this warp
         float total_r = reduce_rows();
         total_r += __shfl_xor_sync(0xffffffffu, total_r, 1);
         if (writer) atomicAdd(out_base + pend_id * (unsigned)out_stride, total_r);
