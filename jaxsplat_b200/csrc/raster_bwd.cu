@@ -384,11 +384,13 @@ struct HbStage {      // one sub-chunk of <= 32 visits
 // SUPER: super-column lists (RasterParams::sc_shift); with all_entries the entries whose tile
 // columns do not cover the tile are skipped like the forward skips them.
 // T8: block_width 8 -- the tile is the quadrant (one CTA per tile).
-template <bool ABS, bool MOMENTS, bool SUPER, bool T8 = false>
+// ALL: no hit words -- every entry of the quadrant's range is replayed (the backward rebuilt the
+// lists itself, or the test hook asked for it).
+template <bool ABS, bool MOMENTS, bool SUPER, bool T8 = false, bool ALL = false>
 __global__ void __launch_bounds__(32, JSB_BWDH_CTAS)
 raster_bwd_hits_kernel(const RasterParams p, const void *__restrict__ list,
                        const int2 *__restrict__ tile_bins, const SplatRecord *__restrict__ records,
-                       const unsigned *__restrict__ hit_words, const bool all_entries,
+                       const unsigned *__restrict__ hit_words,
                        const float *__restrict__ background, const float *__restrict__ final_Ts,
                        const int *__restrict__ final_idx, const float *__restrict__ v_out_img,
                        const float *__restrict__ v_out_alpha_img, float *__restrict__ v_xy,
@@ -490,7 +492,7 @@ raster_bwd_hits_kernel(const RasterParams p, const void *__restrict__ list,
     for (int gs = rel_top >> 5; gs >= 0; gs -= HB_SPAN) {
         // ---- expand this span's hit words into visit positions, newest first -------------------
         const int g = gs - lane;  // lane's group (32 list entries) of this span
-        unsigned w = (g >= 0 && lane < HB_SPAN) ? (all_entries ? 0xFFFFFFFFu : __ldg(hw + g)) : 0u;
+        unsigned w = (g >= 0 && lane < HB_SPAN) ? (ALL ? 0xFFFFFFFFu : __ldg(hw + g)) : 0u;
         if (g == (rel_top >> 5)) w &= (2u << (rel_top & 31)) - 1u;  // entries above `top`
         const int cnt = __popc(w);
         int incl = cnt;
@@ -540,7 +542,7 @@ raster_bwd_hits_kernel(const RasterParams p, const void *__restrict__ list,
                 if (SUPER) {
                     const uint2 e = __ldg(ents + sidx_n);
                     gid_n = e.x;
-                    if (all_entries && !((tile_x - (e.y & 0xffffu)) < (e.y >> 16))) sidx_n = 0x7fffffff;
+                    if (ALL && !((tile_x - (e.y & 0xffffu)) < (e.y >> 16))) sidx_n = 0x7fffffff;
                 } else {
                     gid_n = ids_sorted[sidx_n];
                 }
@@ -588,7 +590,7 @@ raster_bwd_hits_kernel(const RasterParams p, const void *__restrict__ list,
                 if (writer) atomicAdd(out_base + pend_id * (unsigned)out_stride, total_r);
                 // (a hit-driven visit has an accepting pixel by construction; only the replay of
                 // EVERY entry meets visits without one, worth a vote to skip -- leaving zero rows)
-                if (all_entries && !__any_sync(0xffffffffu, ok0 || ok1)) {
+                if (ALL && !__any_sync(0xffffffffu, ok0 || ok1)) {
                     __syncwarp();
 #pragma unroll
                     for (int r = 0; r < NV; ++r) red[r * RED_STRIDE + lane] = 0.f;
@@ -750,57 +752,39 @@ int launch_raster_bwd(cudaStream_t stream, const RasterParams &p, const void *li
         set_error("raster_bwd: super-column lists need block_width 16");
         return 1;
     }
+#define JSB_HITS(ABS_, MOM_, SUP_, T8_, ALL_, GRID_, HW_)                                              \
+    raster_bwd_hits_kernel<ABS_, MOM_, SUP_, T8_, ALL_><<<GRID_, 32, 0, stream>>>(                       \
+        p, list, tile_bins, records, HW_, background, final_Ts, final_idx, v_out, v_out_alpha, v_xy,     \
+        v_xy_abs, v_conic, v_colors, v_opacity)
+#define JSB_HITS_MODE(SUP_, T8_, ALL_, GRID_, HW_)                                                     \
+    do {                                                                                               \
+        if (v_xy_abs) JSB_HITS(true, false, SUP_, T8_, ALL_, GRID_, HW_);                              \
+        else if (moments_out) JSB_HITS(false, true, SUP_, T8_, ALL_, GRID_, HW_);                      \
+        else JSB_HITS(false, false, SUP_, T8_, ALL_, GRID_, HW_);                                      \
+    } while (0)
     if (p.sc_shift) {
         // super-column lists (fused render): always the hit-driven kernel; without hit words (the
         // backward rebuilt the lists itself) it replays every entry of the quadrant's range
         const bool all = g_bwd_all_entries || hit_words == nullptr;
         const unsigned *hw = hit_words ? hit_words : reinterpret_cast<const unsigned *>(list);  // (not read)
-        if (v_xy_abs)
-            raster_bwd_hits_kernel<true, false, true><<<tiles * 4, 32, 0, stream>>>(
-                p, list, tile_bins, records, hw, all, background, final_Ts, final_idx, v_out,
-                v_out_alpha, v_xy, v_xy_abs, v_conic, v_colors, v_opacity);
-        else if (moments_out)
-            raster_bwd_hits_kernel<false, true, true><<<tiles * 4, 32, 0, stream>>>(
-                p, list, tile_bins, records, hw, all, background, final_Ts, final_idx, v_out,
-                v_out_alpha, v_xy, v_xy_abs, v_conic, v_colors, v_opacity);
-        else
-            raster_bwd_hits_kernel<false, false, true><<<tiles * 4, 32, 0, stream>>>(
-                p, list, tile_bins, records, hw, all, background, final_Ts, final_idx, v_out,
-                v_out_alpha, v_xy, v_xy_abs, v_conic, v_colors, v_opacity);
+        if (all) JSB_HITS_MODE(true, false, true, tiles * 4, hw);
+        else JSB_HITS_MODE(true, false, false, tiles * 4, hw);
         if (moments_out) *moments_out = !v_xy_abs;
     } else if (p.block_width == 8 && !(g_bwd_no_hits && v_xy_abs)) {
         // 8x8 tiles: the hit-driven kernel with the tile as its quadrant; without hit words (the
         // backward rebuilt the lists itself) it replays every entry of the tile's range
         const bool all = g_bwd_all_entries || hit_words == nullptr || g_bwd_no_hits;
         const unsigned *hw = hit_words ? hit_words : reinterpret_cast<const unsigned *>(list);  // (not read)
-        if (v_xy_abs)
-            raster_bwd_hits_kernel<true, false, false, true><<<tiles, 32, 0, stream>>>(
-                p, list, tile_bins, records, hw, all, background, final_Ts, final_idx, v_out,
-                v_out_alpha, v_xy, v_xy_abs, v_conic, v_colors, v_opacity);
-        else if (moments_out)
-            raster_bwd_hits_kernel<false, true, false, true><<<tiles, 32, 0, stream>>>(
-                p, list, tile_bins, records, hw, all, background, final_Ts, final_idx, v_out,
-                v_out_alpha, v_xy, v_xy_abs, v_conic, v_colors, v_opacity);
-        else
-            raster_bwd_hits_kernel<false, false, false, true><<<tiles, 32, 0, stream>>>(
-                p, list, tile_bins, records, hw, all, background, final_Ts, final_idx, v_out,
-                v_out_alpha, v_xy, v_xy_abs, v_conic, v_colors, v_opacity);
+        if (all) JSB_HITS_MODE(false, true, true, tiles, hw);
+        else JSB_HITS_MODE(false, true, false, tiles, hw);
         if (moments_out) *moments_out = !v_xy_abs;
     } else if (p.block_width == 16 && hit_words && !g_bwd_no_hits) {
         // one independent warp per quadrant, driven by the forward's hit words
-        if (v_xy_abs)
-            raster_bwd_hits_kernel<true, false, false><<<tiles * 4, 32, 0, stream>>>(
-                p, list, tile_bins, records, hit_words, g_bwd_all_entries, background, final_Ts, final_idx, v_out,
-                v_out_alpha, v_xy, v_xy_abs, v_conic, v_colors, v_opacity);
-        else if (moments_out)
-            raster_bwd_hits_kernel<false, true, false><<<tiles * 4, 32, 0, stream>>>(
-                p, list, tile_bins, records, hit_words, g_bwd_all_entries, background, final_Ts, final_idx, v_out,
-                v_out_alpha, v_xy, v_xy_abs, v_conic, v_colors, v_opacity);
-        else
-            raster_bwd_hits_kernel<false, false, false><<<tiles * 4, 32, 0, stream>>>(
-                p, list, tile_bins, records, hit_words, g_bwd_all_entries, background, final_Ts, final_idx, v_out,
-                v_out_alpha, v_xy, v_xy_abs, v_conic, v_colors, v_opacity);
+        if (g_bwd_all_entries) JSB_HITS_MODE(false, false, true, tiles * 4, hit_words);
+        else JSB_HITS_MODE(false, false, false, tiles * 4, hit_words);
         if (moments_out) *moments_out = !v_xy_abs;
+#undef JSB_HITS_MODE
+#undef JSB_HITS
     } else if (p.block_width == 16) {
         if (v_xy_abs) {
             if (g_disable_cull)

@@ -237,6 +237,27 @@ raster_fwd16x2_kernel(const RasterParams p, const unsigned *__restrict__ ids_sor
 //     and replayed in order: no find-first-set walk, no CTA barrier, and a quadrant whose pixels
 //     are all saturated simply stops.
 // Per-visit arithmetic is the text of raster_fwd16x2_kernel: same rounding order, bit-identical.
+// Shared-memory accesses of the warp kernel by 32-bit shared address: with generic pointers the
+// compiler, at its register cap, re-derives the shared window base (S2R SR_CgaCtaId, LEA, ...) for
+// every group -- ~20 issue slots of a ~120-slot group; an opaque 32-bit address has to stay in a
+// register.
+__device__ __forceinline__ void sts128(unsigned a, const float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w));
+}
+__device__ __forceinline__ void sts64(unsigned a, const float2 v) {
+    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a), "f"(v.x), "f"(v.y));
+}
+__device__ __forceinline__ float4 lds128(unsigned a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ float2 lds64(unsigned a) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
+    return v;
+}
+
 struct FwSlot {          // one compacted candidate
     float4 A;            // x, y, opac, conic.x
     float4 B;            // conic.y, conic.z, r, g
@@ -280,8 +301,9 @@ raster_fwd_warp_kernel(const RasterParams p, const void *__restrict__ list,
         : T8 ? (unsigned)hit_tile8_offset(range, tile_local)
              : (unsigned)hit_quadrant_offset(range, tile_local, (unsigned)warp);
     const unsigned lt_mask = (1u << lane) - 1u;
-    FwSlot *slot = s_slot[warp];
-    float2 *sc = s_c[warp];
+    unsigned slot_sa = (unsigned)__cvta_generic_to_shared(s_slot[warp]);  // 32 bytes per candidate
+    unsigned sc_sa = (unsigned)__cvta_generic_to_shared(s_c[warp]);       // 8 bytes per candidate
+    asm volatile("" : "+r"(slot_sa), "+r"(sc_sa));  // opaque: kept in registers, not re-derived
 
     // {pixel 0, pixel 1} pairs: transmittance and the three colour sums
     float2 T2 = make_float2(1.f, 1.f);
@@ -322,10 +344,10 @@ raster_fwd_warp_kernel(const RasterParams p, const void *__restrict__ list,
         }
         const unsigned bits = __ballot_sync(0xffffffffu, may);
         if (may) {
-            const int pos = __popc(bits & lt_mask);
-            slot[pos].A = qa;
-            slot[pos].B = qb;
-            sc[pos] = make_float2(qc.x, __int_as_float(range.x + 32 * g + lane));
+            const unsigned pos = __popc(bits & lt_mask);
+            sts128(slot_sa + pos * 32u, qa);
+            sts128(slot_sa + pos * 32u + 16u, qb);
+            sts64(sc_sa + pos * 8u, make_float2(qc.x, __int_as_float(range.x + 32 * g + lane)));
         }
         // the record registers are free again: the next group's gathers go out and fly while this
         // group is composited
@@ -338,9 +360,10 @@ raster_fwd_warp_kernel(const RasterParams p, const void *__restrict__ list,
             __syncwarp();
             const int cnt = __popc(bits);
 #pragma unroll 1
-            for (int t = 0; t < cnt; ++t) {
-                const float4 a = slot[t].A;
-                const float4 bq = slot[t].B;
+            unsigned pa = slot_sa, pc = sc_sa;
+            for (int t = 0; t < cnt; ++t, pa += 32u, pc += 8u) {
+                const float4 a = lds128(pa);
+                const float4 bq = lds128(pa + 16u);
                 const float dx = fsub(a.x, px);
                 // conic_sigma (common.cuh) for both pixels at once: same operation order per pixel
                 // as the reference's compiled code, so the outputs stay bit-identical
@@ -365,7 +388,7 @@ raster_fwd_warp_kernel(const RasterParams p, const void *__restrict__ list,
                 // exact difference, like the subtraction), and a pixel that does not composite
                 // this Gaussian -- rejected, saturated, or stopped by it -- gets
                 // vis = 0, which leaves its sums unchanged to the bit, and keeps its T.
-                const float2 cq = sc[t];
+                const float2 cq = lds64(pc);
                 const int sidx = __float_as_int(cq.y);
                 const float2 om2 = __ffma2_rn(al2, make_float2(-1.f, -1.f), make_float2(1.f, 1.f));
                 const float2 nT2 = __fmul2_rn(T2, om2);
