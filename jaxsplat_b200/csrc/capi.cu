@@ -820,9 +820,12 @@ static int render_fwd_impl(cudaStream_t stream, void **buf, const Descriptor &d,
 
 // keep_appearance: v_colors / v_opacity already hold the sum over earlier views of a batched call
 // and keep accumulating (raster_bwd only ever adds to them)
+// raster_only (batched cameras): stop after the rasteriser backward, which leaves RAW MOMENTS in
+// v_xy / v_conic (pre-zeroed by the caller) and adds M0 to v_opacity; *moments_seen reports it did.
 static int render_bwd_impl(cudaStream_t stream, void **buf, const Descriptor &d,
                            unsigned long long token, unsigned slot = 0,
-                           bool keep_appearance = false) {
+                           bool keep_appearance = false, bool raster_only = false,
+                           bool *moments_seen = nullptr) {
     // in : 0 means3d 1 scales 2 quats 3 viewmat 4 colors 5 opacities 6 background 7 cov3ds 8 xys
     //      9 depths 10 radii 11 conics 12 compensation 13 final_Ts 14 final_idx
     //      15 v_out_img 16 v_out_img_alpha
@@ -833,6 +836,7 @@ static int render_bwd_impl(cudaStream_t stream, void **buf, const Descriptor &d,
     const size_t n = d.num_points;
     if (n == 0) return 0;
     bool moments_flag = false;  // the rasteriser left raw moments for the projection backward
+    bool empty_flag = false;    // nothing intersects: the rasteriser backward did not run
     {
     Ctx *c = get_ctx(stream, slot);
     if (!c) return 1;
@@ -841,7 +845,9 @@ static int render_bwd_impl(cudaStream_t stream, void **buf, const Descriptor &d,
     // the four accumulators are cleared with one memset when the caller laid them out back to
     // back (the torch host layer does), else one by one
     char *g0 = (char *)buf[20];
-    if (keep_appearance) {
+    if (raster_only) {
+        // (the caller cleared the per-view moment arrays in one memset)
+    } else if (keep_appearance) {
         if ((char *)buf[23] == (char *)buf[22] + n * 8) {
             JSB_CUDA_OK(cudaMemsetAsync(buf[22], 0, n * 20, stream));
         } else {
@@ -902,10 +908,15 @@ static int render_bwd_impl(cudaStream_t stream, void **buf, const Descriptor &d,
                               c->cache_has_hits ? (const unsigned *)c->hits.p : nullptr,
                               // (raw moments leave v_opacity unfinished until project_bwd: not
                               // when it accumulates over the views of a batched call)
-                              keep_appearance ? nullptr : &moments))
+                              (keep_appearance && !raster_only) ? nullptr : &moments))
             return 1;
     }
     moments_flag = moments;
+    empty_flag = empty;
+    }
+    if (raster_only) {
+        if (moments_seen) *moments_seen = moments_flag || empty_flag;
+        return 0;
     }
     // project_bwd with zero cotangents for depth and compensation (render uses neither)
     void *pbuf[18] = {buf[0], buf[1], buf[2], buf[3], buf[7], buf[8], buf[10], buf[11], buf[12],
@@ -968,9 +979,46 @@ static int render_views_bwd_impl(cudaStream_t stream, void **buf, const Descript
         JSB_CUDA_OK(cudaMemsetAsync(buf[19], 0, n * 4 * 4, stream));
         return 0;
     }
-    // scratch, every array 16-byte aligned (m = n rounded up to a multiple of 4):
-    // [v_xy 2m][v_conic 3m][v_cov2d 3m][v_cov3d 6m][staged v_mean3d 3m | v_scale 3m | v_quat 4m]
     const size_t m = (n + 3) & ~(size_t)3;
+    // One projection backward for all views (project.cu: project_bwd_views_kernel) whenever the
+    // rasteriser backward leaves raw moments -- the tuned block widths with their default options:
+    // every view's moments go to its own slice [v_xy 2m | v_conic 3m] of the scratch buffer.
+    if ((want_super(d) != 0 || d.block_width == 8) && !g_bwd_no_moments) {
+        if (vc->ensure(vc->views_scratch, (size_t)B * 5 * m * sizeof(float))) return 1;
+        float *sc = (float *)vc->views_scratch.p;
+        JSB_CUDA_OK(cudaMemsetAsync(sc, 0, (size_t)B * 5 * m * sizeof(float), stream));
+        for (unsigned i = 0; i < B; ++i) {
+            const unsigned b = B - 1 - i;  // last view first: its binning is still in its slot
+            float *s_xy = sc + (size_t)b * 5 * m, *s_conic = s_xy + 2 * m;
+            void *vb[26] = {buf[0], buf[1], buf[2], (float *)buf[3] + 16 * (size_t)b, buf[4], buf[5],
+                            buf[6],
+                            buf[7] ? (void *)((float *)buf[7] + b * n * 6) : nullptr, (float *)buf[8] + b * n * 2,
+                            (float *)buf[9] + b * n, (int *)buf[10] + b * n,
+                            (float *)buf[11] + b * n * 3,
+                            buf[12] ? (void *)((float *)buf[12] + b * n) : nullptr,
+                            (float *)buf[13] + b * px, (int *)buf[14] + b * px,
+                            (float *)buf[15] + b * px * 3,
+                            buf[16] ? (void *)((float *)buf[16] + b * px) : nullptr,
+                            nullptr, nullptr, nullptr, buf[20], buf[21], s_xy, s_conic, nullptr, nullptr};
+            bool moments = false;
+            if (render_bwd_impl(stream, vb, d, tokens ? tokens[b] : 0, b % g_view_slots,
+                                /*keep_appearance=*/true, /*raster_only=*/true, &moments))
+                return 1;
+            if (!moments) {
+                set_error("render_views_bwd: the rasteriser backward left no raw moments");
+                return 1;
+            }
+        }
+        StageScope ss(vc, ST_PROJECT_BWD);
+        const ProjectBwdParams pp{d.num_points, d.glob_scale, d.fx, d.fy};
+        return launch_project_bwd_views(stream, pp, B, (const float *)buf[0], (const float *)buf[1],
+                                        (const float *)buf[2], (const float *)buf[3],
+                                        (const int *)buf[10], (const float *)buf[11], sc, sc + 2 * m,
+                                        5 * m, (float *)buf[17], (float *)buf[18], (float *)buf[19],
+                                        (const float *)buf[5], (float *)buf[21]);
+    }
+    // (other block widths / options) scratch, every array 16-byte aligned:
+    // [v_xy 2m][v_conic 3m][v_cov2d 3m][v_cov3d 6m][staged v_mean3d 3m | v_scale 3m | v_quat 4m]
     if (vc->ensure(vc->views_scratch, m * 24 * sizeof(float))) return 1;
     float *sc = (float *)vc->views_scratch.p;
     float *s_xy = sc, *s_conic = sc + 2 * m, *s_stage = sc + 14 * m;

@@ -54,6 +54,16 @@ int launch_project_bwd(cudaStream_t stream, const ProjectBwdParams &p, const flo
 // opacities + moment_opacity != null: v_xy / v_conic / moment_opacity hold the rasteriser's raw
 // moments; they are turned into gradients on the fly and moment_opacity[i] becomes v_opacity[i].
 
+// batched cameras, one launch for all views: per-view radii (B,n), conics (B,n,3) and raw moments
+// mom_xy (view b at mom_xy + b * mom_stride floats, n float2) / mom_conic (view b at mom_conic +
+// b * mom_stride floats, 3n floats); mom_opacity (n) = sum over the views of M0, leaves as v_opacity
+int launch_project_bwd_views(cudaStream_t stream, const ProjectBwdParams &p, unsigned num_views,
+                            const float *means3d, const float *scales, const float *quats,
+                            const float *viewmats, const int *radii, const float *conics,
+                            const float *mom_xy, const float *mom_conic, size_t mom_stride,
+                            float *v_mean3d, float *v_scale, float *v_quat, const float *opacities,
+                            float *mom_opacity);
+
 // batched cameras: v_mean3d / v_scale / v_quat += one view's staged arrays (3n / 3n / 4n floats)
 int launch_accumulate_param_grads(cudaStream_t stream, size_t n, const float *s_mean,
                                   const float *s_scale, const float *s_quat, float *v_mean3d,

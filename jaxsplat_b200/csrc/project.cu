@@ -523,6 +523,140 @@ project_bwd_kernel(const ProjectBwdParams p, const float *__restrict__ means3d,
     if (v_cov3d) warp_store_aos<6>(strip, o_cov3d, v_cov3d, wfirst * 6, n * 6, lane);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Batched cameras: the projection backward of B views of the same Gaussians in ONE
+// launch.  A thread loads its Gaussian's parameters once, builds R, S and the 3D covariance once,
+// then walks the views: per view the rasteriser's raw moments (raster_bwd.cu: MOMENTS) become
+// v_xy / v_conic, the EWA VJP runs with that view's matrix, v_mean3d and the covariance cotangent
+// v_V accumulate in registers; the scale / quaternion VJP -- linear in v_V -- runs once on the sum,
+// and every gradient is written once.  Replaces, per view, a full projection backward (parameters
+// and gradients through HBM) plus the add kernel that summed the views (120 bytes per Gaussian).
+// mom_opacity holds the sum over the views of M0 and leaves as v_opacity.
+__global__ void __launch_bounds__(PT)
+project_bwd_views_kernel(const ProjectBwdParams p, const unsigned num_views,
+                         const float *__restrict__ means3d, const float *__restrict__ scales,
+                         const float4 *__restrict__ quats, const float *__restrict__ viewmats,
+                         const int *__restrict__ radii, const float *__restrict__ conics,
+                         const float2 *__restrict__ mom_xy, const float *__restrict__ mom_conic,
+                         const size_t mom_stride /* floats between two views' moment arrays / m */,
+                         float *__restrict__ v_mean3d, float *__restrict__ v_scale,
+                         float *__restrict__ v_quat, const float *__restrict__ opacities,
+                         float *__restrict__ mom_opacity) {
+    __shared__ __align__(16) float s_strip[PT / 32][32 * 6];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long idx = (long long)blockIdx.x * PT + tid;
+    const long long wfirst = (long long)blockIdx.x * PT + warp * 32;
+    const long long n = p.num_points;
+    float *strip = s_strip[warp];
+    float o_mean[3] = {0.f, 0.f, 0.f}, o_scale[3] = {0.f, 0.f, 0.f};
+    float o_quat[4] = {0.f, 0.f, 0.f, 0.f};
+    if (idx < n) {
+        const float mx = __ldg(means3d + idx * 3), my = __ldg(means3d + idx * 3 + 1),
+                    mz = __ldg(means3d + idx * 3 + 2);
+        const float sc0 = __ldg(scales + idx * 3), sc1 = __ldg(scales + idx * 3 + 1),
+                    sc2 = __ldg(scales + idx * 3 + 2);
+        const float4 q = __ldg(quats + idx);
+        const float w = q.x, x = q.y, y = q.z, z = q.w;
+        const float R00 = 1.f - 2.f * (y * y + z * z), R01 = 2.f * (x * y - w * z), R02 = 2.f * (x * z + w * y);
+        const float R10 = 2.f * (x * y + w * z), R11 = 1.f - 2.f * (x * x + z * z), R12 = 2.f * (y * z - w * x);
+        const float R20 = 2.f * (x * z - w * y), R21 = 2.f * (y * z + w * x), R22 = 1.f - 2.f * (x * x + y * y);
+        const float gs = p.glob_scale;
+        const float s0 = gs * sc0, s1 = gs * sc1, s2 = gs * sc2;
+        const float e0 = s0 * s0, e1 = s1 * s1, e2 = s2 * s2;
+        const float k0 = e0 * R00 * R00 + e1 * R01 * R01 + e2 * R02 * R02;
+        const float k1 = e0 * R00 * R10 + e1 * R01 * R11 + e2 * R02 * R12;
+        const float k2 = e0 * R00 * R20 + e1 * R01 * R21 + e2 * R02 * R22;
+        const float k3 = e0 * R10 * R10 + e1 * R11 * R11 + e2 * R12 * R12;
+        const float k4 = e0 * R10 * R20 + e1 * R11 * R21 + e2 * R12 * R22;
+        const float k5 = e0 * R20 * R20 + e1 * R21 * R21 + e2 * R22 * R22;
+        float vm_x = 0.f, vm_y = 0.f, vm_z = 0.f;
+        float V00 = 0.f, V01 = 0.f, V02 = 0.f, V11 = 0.f, V12 = 0.f, V22 = 0.f;  // sum of v_V
+        const float fx = p.fx, fy = p.fy;
+        for (unsigned b = 0; b < num_views; ++b) {
+            if (__ldg(radii + (size_t)b * n + idx) <= 0) continue;
+            const float *cn = conics + ((size_t)b * n + idx) * 3;
+            const float cx = __ldg(cn), cy = __ldg(cn + 1), cz = __ldg(cn + 2);
+            const float2 mxy = __ldg(mom_xy + (size_t)b * (mom_stride / 2) + idx);
+            const float *mc = mom_conic + (size_t)b * mom_stride + idx * 3;
+            // raw moments -> v_xy, v_conic (v_conic.y halved for the symmetric product below)
+            const float vxy_x = -(cx * mxy.x + cy * mxy.y), vxy_y = -(cy * mxy.x + cz * mxy.y);
+            const float gx = -0.5f * __ldg(mc), gy = -0.5f * __ldg(mc + 1), gz = -0.5f * __ldg(mc + 2);
+            const float *v = viewmats + 16 * (size_t)b;
+            const float w00 = __ldg(v + 0), w01 = __ldg(v + 1), w02 = __ldg(v + 2), w03 = __ldg(v + 3);
+            const float w10 = __ldg(v + 4), w11 = __ldg(v + 5), w12 = __ldg(v + 6), w13 = __ldg(v + 7);
+            const float w20 = __ldg(v + 8), w21 = __ldg(v + 9), w22 = __ldg(v + 10), w23 = __ldg(v + 11);
+            const float pvx = w00 * mx + w01 * my + w02 * mz + w03;
+            const float pvy = w10 * mx + w11 * my + w12 * mz + w13;
+            const float pvz = w20 * mx + w21 * my + w22 * mz + w23;
+            const float rw = 1.f / (pvz + 1e-6f);
+            const float vpx = fx * vxy_x, vpy = fy * vxy_y;
+            const float vvx = vpx * rw, vvy = vpy * rw;
+            const float vvz = -(vpx * pvx + vpy * pvy) * rw * rw;
+            vm_x += w00 * vvx + w10 * vvy + w20 * vvz;
+            vm_y += w01 * vvx + w11 * vvy + w21 * vvz;
+            vm_z += w02 * vvx + w12 * vvy + w22 * vvz;
+            // cov2d_to_conic_vjp
+            const float p00 = cx * gx + cy * gy, p01 = cx * gy + cy * gz;
+            const float p10 = cy * gx + cz * gy, p11 = cy * gy + cz * gz;
+            const float vc_x = -(p00 * cx + p01 * cy);
+            const float vc_y = -((p00 * cy + p01 * cz) + (p10 * cx + p11 * cy));
+            const float vc_z = -(p10 * cy + p11 * cz);
+            // project_cov3d_ewa_vjp (unclamped t)
+            const float rz = 1.f / pvz, rz2 = rz * rz;
+            const float j00 = fx * rz, j11 = fy * rz, j02 = -fx * pvx * rz2, j12 = -fy * pvy * rz2;
+            const float T00 = j00 * w00 + j02 * w20, T01 = j00 * w01 + j02 * w21, T02 = j00 * w02 + j02 * w22;
+            const float T10 = j11 * w10 + j12 * w20, T11 = j11 * w11 + j12 * w21, T12 = j11 * w12 + j12 * w22;
+            const float g00 = vc_x, g01 = 0.5f * vc_y, g11 = vc_z;
+            const float A00 = g00 * T00 + g01 * T10, A01 = g00 * T01 + g01 * T11, A02 = g00 * T02 + g01 * T12;
+            const float A10 = g01 * T00 + g11 * T10, A11 = g01 * T01 + g11 * T11, A12 = g01 * T02 + g11 * T12;
+            V00 += T00 * A00 + T10 * A10; V11 += T01 * A01 + T11 * A11; V22 += T02 * A02 + T12 * A12;
+            V01 += T00 * A01 + T10 * A11; V02 += T00 * A02 + T10 * A12; V12 += T01 * A02 + T11 * A12;
+            const float vT00 = 2.f * (A00 * k0 + A01 * k1 + A02 * k2);
+            const float vT01 = 2.f * (A00 * k1 + A01 * k3 + A02 * k4);
+            const float vT02 = 2.f * (A00 * k2 + A01 * k4 + A02 * k5);
+            const float vT10 = 2.f * (A10 * k0 + A11 * k1 + A12 * k2);
+            const float vT11 = 2.f * (A10 * k1 + A11 * k3 + A12 * k4);
+            const float vT12 = 2.f * (A10 * k2 + A11 * k4 + A12 * k5);
+            const float vJ00 = vT00 * w00 + vT01 * w01 + vT02 * w02;
+            const float vJ02 = vT00 * w20 + vT01 * w21 + vT02 * w22;
+            const float vJ11 = vT10 * w10 + vT11 * w11 + vT12 * w12;
+            const float vJ12 = vT10 * w20 + vT11 * w21 + vT12 * w22;
+            const float rz3 = rz2 * rz;
+            const float vt_x = -fx * rz2 * vJ02;
+            const float vt_y = -fy * rz2 * vJ12;
+            const float vt_z = -fx * rz2 * vJ00 + 2.f * fx * pvx * rz3 * vJ02 - fy * rz2 * vJ11 +
+                               2.f * fy * pvy * rz3 * vJ12;
+            vm_x += vt_x * w00 + vt_y * w10 + vt_z * w20;
+            vm_y += vt_x * w01 + vt_y * w11 + vt_z * w21;
+            vm_z += vt_x * w02 + vt_y * w12 + vt_z * w22;
+        }
+        o_mean[0] = vm_x; o_mean[1] = vm_y; o_mean[2] = vm_z;
+        // scale_rot_to_cov3d_vjp and quat_to_rotmat_vjp, once, on the summed v_V
+        const float B00 = V00 * R00 + V01 * R10 + V02 * R20, B01 = V00 * R01 + V01 * R11 + V02 * R21,
+                    B02 = V00 * R02 + V01 * R12 + V02 * R22;
+        const float B10 = V01 * R00 + V11 * R10 + V12 * R20, B11 = V01 * R01 + V11 * R11 + V12 * R21,
+                    B12 = V01 * R02 + V11 * R12 + V12 * R22;
+        const float B20 = V02 * R00 + V12 * R10 + V22 * R20, B21 = V02 * R01 + V12 * R11 + V22 * R21,
+                    B22 = V02 * R02 + V12 * R12 + V22 * R22;
+        o_scale[0] = gs * 2.f * s0 * (R00 * B00 + R10 * B10 + R20 * B20);
+        o_scale[1] = gs * 2.f * s1 * (R01 * B01 + R11 * B11 + R21 * B21);
+        o_scale[2] = gs * 2.f * s2 * (R02 * B02 + R12 * B12 + R22 * B22);
+        const float f0 = 2.f * e0, f1 = 2.f * e1, f2 = 2.f * e2;
+        const float vR00 = f0 * B00, vR01 = f1 * B01, vR02 = f2 * B02;
+        const float vR10 = f0 * B10, vR11 = f1 * B11, vR12 = f2 * B12;
+        const float vR20 = f0 * B20, vR21 = f1 * B21, vR22 = f2 * B22;
+        o_quat[0] = 2.f * (x * (vR21 - vR12) + y * (vR02 - vR20) + z * (vR10 - vR01));
+        o_quat[1] = 2.f * (-2.f * x * (vR11 + vR22) + y * (vR10 + vR01) + z * (vR20 + vR02) + w * (vR21 - vR12));
+        o_quat[2] = 2.f * (x * (vR10 + vR01) - 2.f * y * (vR00 + vR22) + z * (vR21 + vR12) + w * (vR02 - vR20));
+        o_quat[3] = 2.f * (x * (vR20 + vR02) + y * (vR21 + vR12) - 2.f * z * (vR00 + vR11) + w * (vR10 - vR01));
+        const float m0 = mom_opacity[idx];
+        mom_opacity[idx] = m0 != 0.f ? m0 / __ldg(opacities + idx) : 0.f;
+    }
+    warp_store_aos<3>(strip, o_mean, v_mean3d, wfirst * 3, n * 3, lane);
+    warp_store_aos<3>(strip, o_scale, v_scale, wfirst * 3, n * 3, lane);
+    warp_store_aos<4>(strip, o_quat, v_quat, wfirst * 4, n * 4, lane);
+}
+
 // batched cameras: adds one view's staged v_mean3d (3n) / v_scale (3n) / v_quat (4n) to the sums
 __global__ void __launch_bounds__(256)
 accumulate_param_grads_kernel(const float *__restrict__ s_mean, const float *__restrict__ s_scale,
@@ -608,6 +742,23 @@ int launch_project_bwd(cudaStream_t stream, const ProjectBwdParams &p, const flo
     else if (recompute) JSB_PBWD(false, true);
     else JSB_PBWD(false, false);
 #undef JSB_PBWD
+    JSB_CUDA_OK(cudaGetLastError());
+    note_launch();
+    return 0;
+}
+
+int launch_project_bwd_views(cudaStream_t stream, const ProjectBwdParams &p, unsigned num_views,
+                            const float *means3d, const float *scales, const float *quats,
+                            const float *viewmats, const int *radii, const float *conics,
+                            const float *mom_xy, const float *mom_conic, size_t mom_stride,
+                            float *v_mean3d, float *v_scale, float *v_quat, const float *opacities,
+                            float *mom_opacity) {
+    if (p.num_points == 0) return 0;
+    const unsigned blocks = ceil_div(p.num_points, PT);
+    project_bwd_views_kernel<<<blocks, PT, 0, stream>>>(
+        p, num_views, means3d, scales, reinterpret_cast<const float4 *>(quats), viewmats, radii, conics,
+        reinterpret_cast<const float2 *>(mom_xy), mom_conic, mom_stride, v_mean3d, v_scale, v_quat,
+        opacities, mom_opacity);
     JSB_CUDA_OK(cudaGetLastError());
     note_launch();
     return 0;
