@@ -121,9 +121,21 @@ class ClockSampler:
                 "source": "NVML in-process, %.0f ms period" % (self.period * 1e3)}
 
 
-def algorithmic_bytes(stage, N, I, P, T, rows=0, tiles_x=120):
+def algorithmic_bytes(stage, N, I, P, T, rows=0, tiles_x=120, E=0, shift=0):
     """DESIGN.md 'algorithmic bytes per unit' (SURVEY.md 8d), per launch of the stage.
-    rows = row entries (sum of tile-box heights) of the two-level list distribution."""
+    rows = row entries (sum of tile-box heights) of the two-level list distribution; shift > 0:
+    the lists are super-column lists of E 8-byte entries (2^shift tiles per super-column)."""
+    if shift:
+        # level 2 distributes 8-byte row entries into ceil(tiles_x / 2^shift) bins per row
+        cols2 = ((tiles_x - 1) >> shift) + 1
+        k2 = 256 if rows == 0 or E == 0 else max(32, min(256, (640 * 3 * rows // (4 * E)) & ~31))
+        chunks = rows // k2 + (T // max(tiles_x, 1))
+        lists = {"tile_offsets": rows * 8 + 3 * chunks * cols2 * 4 + (T >> shift) * (4 + 8),
+                 "tile_scatter": rows * 8 + chunks * cols2 * 4 + E * 8,
+                 "raster_fwd": P * 20 + N * 48 + E * 8,
+                 "raster_bwd": P * 24 + N * 48 + E * 8 + N * 36}
+        if stage in lists:
+            return lists[stage]
     k2 = 256 if rows == 0 or I == 0 else max(32, min(256, (1536 * 3 * rows // (4 * I)) & ~31))
     chunks = rows // k2 + (T // max(tiles_x, 1))  # level-2 chunks (upper bound the grid uses)
     return {
@@ -143,8 +155,9 @@ def algorithmic_bytes(stage, N, I, P, T, rows=0, tiles_x=120):
         "raster_fwd": P * 20 + N * 48 + I * 4,
         "raster_bwd": P * 24 + N * 48 + I * 4 + N * 36,
         # 188 B per Gaussian through the four-op API; the fused render neither writes v_cov2d /
-        # v_cov3d nor reads the compensation, and finishes the opacity moment in place: 152 B
-        "project_bwd": N * 152,
+        # v_cov3d nor reads the compensation or the 3D covariance (recomputed), and finishes the
+        # opacity moment in place: 128 B
+        "project_bwd": N * 128,
     }[stage]
 
 
@@ -459,6 +472,7 @@ def main():
 
     I = _lib.stats()["last_num_intersects"] if args.impl == "ours" else None
     rows = _lib.stats()["last_row_entries"] if args.impl == "ours" else 0
+    lst = _lib.list_stats() if args.impl == "ours" else {"super_entries": 0, "super_shift": 0}
     T = ((W + 15) // 16) * ((H + 15) // 16)
     out = {
         "metric": METRIC, "value": value, "unit": "views/s", "n_gpus": world if args.impl == "ours" else 1,
@@ -472,6 +486,8 @@ def main():
                                    f"{reducer.mode if reducer is not None else 'nccl'}, gradients "
                                    f"{'written in place into' if sink_ok[0] else 'packed (torch.cat) into'} "
                                    "the reduced buffer") if world > 1 else "single GPU",
+                   "lists": (f"super-column lists, {1 << lst['super_shift']} tiles per super-column, "
+                             f"{lst['super_entries']} 8-byte entries" if lst["super_shift"] else "exact per-tile id lists"),
                    "l2": "per-step working set ~0.5 GB (keys/ids ping-pong 0.2 GB, records, images, "
                          "parameters, gradients) exceeds the 126 MB L2; no explicit flush",
                    "timing": "CUDA events around exactly K steps, barrier+synchronize both sides, max over ranks"},
@@ -514,16 +530,17 @@ def main():
             if v["calls"] == 0:
                 continue
             ms = v["ms"] / v["calls"]
-            b = algorithmic_bytes(k, N, I, P, T, rows, (W + 15) // 16)
+            b = algorithmic_bytes(k, N, I, P, T, rows, (W + 15) // 16, lst["super_entries"], lst["super_shift"])
             per_stage[k] = {"ms_per_launch": ms, "launches_per_step": v["calls"] / stage_steps,
                             "algorithmic_bytes": b, "gbs": b / (ms * 1e-3) / 1e9,
                             "hbm_frac": b / (ms * 1e-3) / 1e9 / peak}
             if k == "project_fwd":
                 # SURVEY 8d's 108 B per Gaussian is the projection alone; the fused kernel also reads
                 # colours + opacities and writes the rasteriser records, depth keys, ids and tile
-                # boxes (what bin_prep would): 180 B per Gaussian actually moved
-                per_stage[k]["moved_bytes"] = N * 180
-                per_stage[k]["moved_hbm_frac"] = N * 180 / (ms * 1e-3) / 1e9 / peak
+                # boxes (what bin_prep would), and no longer writes cov3d / compensation (lean
+                # residuals): 152 B per Gaussian actually moved
+                per_stage[k]["moved_bytes"] = N * 152
+                per_stage[k]["moved_hbm_frac"] = N * 152 / (ms * 1e-3) / 1e9 / peak
         dom = max(per_stage, key=lambda k: per_stage[k]["ms_per_launch"] * per_stage[k]["launches_per_step"])
         d = per_stage[dom]
         prof = {}

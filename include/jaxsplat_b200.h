@@ -206,6 +206,9 @@ JSB200_API int jsb200_get_stage_times(jsb200_stream_t stream, double *ms_out9,
  * [3] binning cache hits, [4] last num_intersects, [5] workspace bytes, [6] kernel launches,
  * [7] last row-entry count (sum of tile-box heights) */
 JSB200_API void jsb200_get_stats(unsigned long long *out8);
+/* the last list build: [0] intersections, [1] row entries, [2] (row entry, super-column) pairs the
+ * prep counted, [3] log2 of the tiles per super-column the lists were built with (0 = exact lists) */
+JSB200_API void jsb200_get_list_stats(unsigned long long *out4);
 /* releases every workspace (all devices/streams). */
 JSB200_API void jsb200_release(void);
 

@@ -39,6 +39,7 @@ EXPORTS = (
     "jsb200_debug_hit_words",
     "jsb200_get_stage_times",
     "jsb200_get_stats",
+    "jsb200_get_list_stats",
     "jsb200_release",
     "jsb200_multimem_allreduce_f32",
     "jsb200_adam_step",
@@ -110,6 +111,8 @@ def lib() -> ctypes.CDLL:
     L.jsb200_get_stage_times.restype = i
     L.jsb200_get_stats.argtypes = [ctypes.POINTER(ctypes.c_ulonglong)]
     L.jsb200_get_stats.restype = None
+    L.jsb200_get_list_stats.argtypes = [ctypes.POINTER(ctypes.c_ulonglong)]
+    L.jsb200_get_list_stats.restype = None
     L.jsb200_release.argtypes = []
     L.jsb200_release.restype = None
     L.jsb200_multimem_allreduce_f32.argtypes = [vp, vp, ctypes.POINTER(vp), sz, sz, i, i, u]
@@ -140,6 +143,13 @@ def stats() -> dict:
     keys = ("rasterize_fwd_calls", "rasterize_bwd_calls", "binning_runs", "binning_cache_hits",
             "last_num_intersects", "workspace_bytes", "kernel_launches", "last_row_entries")
     return dict(zip(keys, [int(x) for x in out]))
+
+
+def list_stats() -> dict:
+    out = (ctypes.c_ulonglong * 4)()
+    lib().jsb200_get_list_stats(out)
+    return {"intersections": int(out[0]), "row_entries": int(out[1]), "super_entries": int(out[2]),
+            "super_shift": int(out[3])}
 
 
 def set_option(key: str, value: int) -> None:

@@ -64,6 +64,8 @@ static bool g_disable_resident_sort = false;  // option "sort1k" 0: the four-pas
 // option "supercols" (0 = the exact per-tile lists everywhere).  The four-op API always builds the
 // exact lists: its final_idx / sorted ids are the reference's.
 static unsigned g_sc_shift = 2;
+static std::atomic<unsigned long long> g_list_entries{0};  // (row entry, super-column) pairs of the last prep
+static std::atomic<unsigned> g_list_shift{0};              // super-column shift of the last list build (0: exact)
 static unsigned g_view_slots = 8;  // binning workspaces a batched-camera call cycles through
 
 // ---- optional per-stage device timing (jsb200_set_option("timing", 1)) -------------------------
@@ -525,6 +527,7 @@ static int bin_sort(Ctx &c, const Descriptor &d, unsigned long long I, unsigned 
     commit_binning(c, d, I, fp);
     c.cache_sc_shift = sc;
     c.cache_entries = sc ? c.last_super : I;
+    g_list_shift.store(sc);
     return 0;
 }
 
@@ -546,6 +549,7 @@ static void commit_binning(Ctx &c, const Descriptor &d, unsigned long long I, un
     g_stats[2].fetch_add(1);
     g_stats[4].store(I);
     g_stats[7].store(c.last_rows);
+    g_list_entries.store(c.last_super);
 }
 
 static bool cache_hit(const Ctx &c, const Descriptor &d, unsigned long long I,
@@ -1376,6 +1380,14 @@ int jsb200_get_stage_times(jsb200_stream_t stream_, double *ms_out9, unsigned lo
         jsb::set_error("get_stage_times: exception");
         return 1;
     }
+}
+
+void jsb200_get_list_stats(unsigned long long *out4) {
+    if (!out4) return;
+    out4[0] = jsb::g_stats[4].load();
+    out4[1] = jsb::g_stats[7].load();
+    out4[2] = jsb::g_list_entries.load();
+    out4[3] = jsb::g_list_shift.load();
 }
 
 void jsb200_get_stats(unsigned long long *out8) {
