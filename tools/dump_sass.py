@@ -12,8 +12,9 @@ LIB = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "jaxsplat_b200", 
 OUT = sys.argv[2] if len(sys.argv) > 2 else os.path.join(ROOT, "profiles", "sass")
 # kernel base name -> substring of the mangled template arguments of the default instantiation
 PREFER = {"raster_fwd16x2_kernel": "ILb1E", "raster_bwd16x2p_kernel": "ILb1ELb0E",
-          "raster_bwd_hits_kernel": "ILb0ELb1E", "project_fwd_kernel": "ILb1E",
-          "project_bwd_kernel": "ILb1E",
+          "raster_bwd_hits_kernel": "ILb0ELb1ELb1ELb0ELb0E", "project_fwd_kernel": "ILb1E",
+          "project_bwd_kernel": "ILb1ELb1E", "raster_fwd_warp_kernel": "ILb1ELb1ELb0E",
+          "rc_col_scatter_kernel": "ILb1E", "mse_loss_grad_kernel": "IhE",
           "onesweep_pass_kernel": "IjLi16ELb1E", "radix_hist_kernel": "IjE", "upsweep_kernel": "IjE"}
 
 

@@ -17,8 +17,13 @@ timeout 600 python bench.py --config C5 --steps 5 --warmup 3 > $OUT/${TAG}_bench
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv \
     --log-file $OUT/${TAG}_launches_C3.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline \
     > $OUT/${TAG}_launches_bench.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -s 28 -c 14 -o $OUT/${TAG}_ncu_full -f \
+# (the .ncu-rep of a whole step with sources is larger than what gpurun copies back: exported to
+# CSV pages here, the report itself stays on the box)
+timeout 900 ncu --set full --clock-control none --import-source on -s 28 -c 14 -o /tmp/${TAG}_ncu_full -f \
     python tools/ncu_step.py C3 4 > $OUT/${TAG}_ncu_full.log 2>&1
+ncu -i /tmp/${TAG}_ncu_full.ncu-rep --page raw --csv > $OUT/${TAG}_ncu_full_raw.csv 2>/dev/null
+ncu -i /tmp/${TAG}_ncu_full.ncu-rep --page source --csv --print-source sass -k regex:"raster_bwd_hits|raster_fwd_warp" > $OUT/${TAG}_ncu_source_rasterisers.csv 2>/dev/null
+ls -la /tmp/${TAG}_ncu_full.ncu-rep $OUT/${TAG}_ncu_*.csv
 SEL="test_super_column or test_block_size_8 or test_lean_residuals or test_render_views_equals or test_fused_render_equals or test_hit_driven_backward_through"
 timeout 1200 compute-sanitizer --tool memcheck --error-exitcode 7 --print-limit 20 \
     python -m pytest tests -m gpu -q -x -k "$SEL" > $OUT/${TAG}_sanitize_memcheck.log 2>&1

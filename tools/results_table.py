@@ -48,8 +48,11 @@ for cfg, ours, ref in (("C1", f"{tag}_bench_C1.json", f"{tag}_bench_reference_C1
         row += f" | x{r['ms_per_step'] / o['ms_per_step']:.1f}"
         if e and re:
             row += f" (e2e x{re / e:.1f})"
-        if r.get("reference_kernel_ms"):
-            row += f" | ref kernels {r['reference_kernel_ms']:.2f} ms"
+        rk = r.get("reference_kernel_ms")
+        if isinstance(rk, dict):
+            rk = rk.get("value") or rk.get("ms")
+        if isinstance(rk, (int, float)):
+            row += f" | ref kernels {rk:.2f} ms"
     if o.get("stages"):
         row += " | " + ", ".join(f"{k} {v['ms_per_launch'] * 1000:.1f}" for k, v in o["stages"].items())
     rf = o.get("roofline") or {}
