@@ -91,7 +91,7 @@ class CustomCallTable:
             if not t.is_cuda or not t.is_contiguous():
                 raise ValueError(f"{target}: every buffer must be a contiguous CUDA tensor")
         if stream is None:
-            stream = torch.cuda.current_stream().cuda_stream
+            stream = torch._C._cuda_getCurrentRawStream(torch.cuda.current_device())
         bufs = (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
         self._fns[target](ctypes.c_void_p(stream), bufs, opaque, len(opaque))
         if self._check is not None:

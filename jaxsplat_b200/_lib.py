@@ -152,6 +152,20 @@ def list_stats() -> dict:
             "super_shift": int(out[3])}
 
 
+def raw_stream(device=None) -> int:
+    """the current CUDA stream's handle of `device` (a torch.device / index; default: the current
+    device) without building a torch.cuda.Stream object (three attribute look-ups and a device query
+    per call: ~15 us of a small scene's 350 us step)"""
+    import torch
+    if device is None:
+        idx = torch.cuda.current_device()
+    elif isinstance(device, int):
+        idx = device
+    else:
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+    return torch._C._cuda_getCurrentRawStream(idx)
+
+
 def set_option(key: str, value: int) -> None:
     if lib().jsb200_set_option(key.encode(), int(value)) != 0:
         check_error("set_option")

@@ -168,7 +168,7 @@ def _call_native(fn_name, tensors, opaque, *extra):
         if t is not None and (not t.is_cuda or not t.is_contiguous()):
             raise ValueError(f"{fn_name}: every buffer must be a contiguous CUDA tensor")
     bufs = (ctypes.c_void_p * len(tensors))(*[None if t is None else t.data_ptr() for t in tensors])
-    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    stream = ctypes.c_void_p(_lib.raw_stream())  # the current device's current stream
     rc = getattr(_lib.lib(), fn_name)(stream, bufs, opaque, len(opaque), *extra)
     if rc != 0:
         _lib.check_error(fn_name)

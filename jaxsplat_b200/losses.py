@@ -31,7 +31,7 @@ def mse_loss_and_grad(img: torch.Tensor, target: torch.Tensor):
     loss = torch.empty(1, dtype=torch.float32, device=img.device)
     fn = _lib.lib().jsb200_mse_loss_grad_u8 if u8 else _lib.lib().jsb200_mse_loss_grad
     rc = fn(
-        ctypes.c_void_p(torch.cuda.current_stream().cuda_stream), ctypes.c_void_p(img.data_ptr()),
+        ctypes.c_void_p(_lib.raw_stream()), ctypes.c_void_p(img.data_ptr()),
         ctypes.c_void_p(target.data_ptr()), n, 2.0 / max(n, 1), ctypes.c_void_p(v_img.data_ptr()),
         ctypes.c_void_p(loss.data_ptr()))
     if rc != 0:
