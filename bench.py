@@ -237,6 +237,12 @@ def main():
     import torch
     import torch.distributed as dist
 
+    # The backward of a step is one chain (loss -> render): run it in the calling thread instead of
+    # handing it to autograd's worker thread and waiting for the wake-up (both arms; 40-50 us of
+    # host time per step, visible where the GPU work is shorter than the host's: C1, C2)
+    if os.environ.get("JSB_BENCH_AUTOGRAD_THREADS") != "1":
+        torch.autograd.set_multithreading_enabled(False)
+
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -490,6 +496,8 @@ def main():
                              f"{lst['super_entries']} 8-byte entries" if lst["super_shift"] else "exact per-tile id lists"),
                    "l2": "per-step working set ~0.5 GB (keys/ids ping-pong 0.2 GB, records, images, "
                          "parameters, gradients) exceeds the 126 MB L2; no explicit flush",
+                   "host": "torch autograd in the calling thread (set_multithreading_enabled(False))"
+                           if os.environ.get("JSB_BENCH_AUTOGRAD_THREADS") != "1" else "torch autograd worker thread",
                    "timing": "CUDA events around exactly K steps, barrier+synchronize both sides, max over ranks"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
         "loss": loss_host,

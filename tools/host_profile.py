@@ -29,6 +29,8 @@ def step():
     img.backward(gradient=v)
 
 
+if os.environ.get("JSB_AUTOGRAD_SINGLE_THREAD") == "1":
+    torch.autograd.set_multithreading_enabled(False)  # the backward runs in the calling thread
 for _ in range(20):
     step()
 torch.cuda.synchronize()

@@ -98,6 +98,7 @@ def main():
 def run(args):
     """the measurement itself; returns the result dict on rank 0 (None elsewhere).  bench.py calls
     this for `--config C4` / `--config C5` with an argparse-like namespace."""
+    torch.autograd.set_multithreading_enabled(False)  # (one backward chain: no worker-thread hand-off)
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
