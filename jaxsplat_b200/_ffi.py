@@ -91,7 +91,8 @@ class CustomCallTable:
             if not t.is_cuda or not t.is_contiguous():
                 raise ValueError(f"{target}: every buffer must be a contiguous CUDA tensor")
         if stream is None:
-            stream = torch._C._cuda_getCurrentRawStream(torch.cuda.current_device())
+            from . import _lib
+            stream = _lib.raw_stream()
         bufs = (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
         self._fns[target](ctypes.c_void_p(stream), bufs, opaque, len(opaque))
         if self._check is not None:

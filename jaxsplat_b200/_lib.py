@@ -163,7 +163,10 @@ def raw_stream(device=None) -> int:
         idx = device
     else:
         idx = device.index if device.index is not None else torch.cuda.current_device()
-    return torch._C._cuda_getCurrentRawStream(idx)
+    get = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+    if get is None:  # (a torch without the private accessor)
+        return torch.cuda.current_stream(idx).cuda_stream
+    return get(idx)
 
 
 def set_option(key: str, value: int) -> None:
