@@ -621,36 +621,44 @@ raster_bwd_hits_kernel(const RasterParams p, const void *__restrict__ list,
                 const float2 va2 = __ffma2_rn(ra2, Q2, __fmul2_rn(T2, P2));
                 S2 = __ffma2_rn(fac2, P2, S2);
                 const float2 pv2 = __fmul2_rn(av2, va2);        // -v_sigma = opacity vis v_alpha
-                float2 o2[9];
-                o2[0] = __fmul2_rn(vox2, fac2);
-                o2[1] = __fmul2_rn(voy2, fac2);
-                o2[2] = __fmul2_rn(voz2, fac2);
+                float v[NV];
+                {
+                    const float2 c0 = __fmul2_rn(vox2, fac2), c1 = __fmul2_rn(voy2, fac2),
+                                 c2 = __fmul2_rn(voz2, fac2);
+                    v[0] = c0.x + c0.y;
+                    v[1] = c1.x + c1.y;
+                    v[2] = c2.x + c2.y;
+                }
                 if (MOMENTS) {
-                    const float2 mx2 = __fmul2_rn(bc(dx), pv2);
+                    // the lane's two pixels share dx: the moments in dx come from the pair SUM
+                    // (scalar multiplies) instead of a packed multiply and a pair add each
+                    const float m0 = pv2.x + pv2.y;                // M0  -> v_opacity
+                    const float mx = dx * m0;                      // Mx  -> v_xy.x
                     const float2 my2 = __fmul2_rn(dy2, pv2);
-                    o2[3] = pv2;                        // M0  -> v_opacity
-                    o2[4] = mx2;                        // Mx  -> v_xy.x
-                    o2[5] = my2;                        // My  -> v_xy.y
-                    o2[6] = __fmul2_rn(bc(dx), mx2);    // Mxx -> v_conic.x
-                    o2[7] = __fmul2_rn(dy2, mx2);       // Mxy -> v_conic.y
-                    o2[8] = __fmul2_rn(dy2, my2);       // Myy -> v_conic.z
+                    const float my = my2.x + my2.y;                // My  -> v_xy.y
+                    const float2 myy2 = __fmul2_rn(dy2, my2);
+                    v[3] = m0;
+                    v[4] = mx;
+                    v[5] = my;
+                    v[6] = dx * mx;                                // Mxx -> v_conic.x
+                    v[7] = dx * my;                                // Mxy -> v_conic.y
+                    v[8] = myy2.x + myy2.y;                        // Myy -> v_conic.z
                 } else {
                     const float2 vs2 = __fmul2_rn(pv2, bc(-1.f));
                     const float2 hs2 = __fmul2_rn(pv2, bc(-0.5f));
                     const float2 dxv2 = __fmul2_rn(bc(dx), vs2);    // dx v_sigma
-                    o2[3] = __fmul2_rn(bc(dx * dx), hs2);
-                    o2[4] = __fmul2_rn(dy2, dxv2);
-                    o2[5] = __fmul2_rn(dy2, __fmul2_rn(dy2, hs2));
-                    o2[6] = __ffma2_rn(__fmul2_rn(dy2, bc(bq.x)), vs2, __fmul2_rn(bc(ca), vs2));  // (cx dx + cy dy) v_sigma
-                    o2[7] = __fmul2_rn(__fadd2_rn(bc(ce), b2), vs2);                               // (cy dx + cz dy) v_sigma
-                    o2[8] = __fmul2_rn(vis2, va2);
-                }
-                float v[NV];
-#pragma unroll
-                for (int r = 0; r < 9; ++r) v[r] = o2[r].x + o2[r].y;
-                if (ABS) {
-                    v[9] = fabsf(o2[6].x) + fabsf(o2[6].y);
-                    v[10] = fabsf(o2[7].x) + fabsf(o2[7].y);
+                    const float2 o3 = __fmul2_rn(bc(dx * dx), hs2);
+                    const float2 o4 = __fmul2_rn(dy2, dxv2);
+                    const float2 o5 = __fmul2_rn(dy2, __fmul2_rn(dy2, hs2));
+                    const float2 o6 = __ffma2_rn(__fmul2_rn(dy2, bc(bq.x)), vs2, __fmul2_rn(bc(ca), vs2));  // (cx dx + cy dy) v_sigma
+                    const float2 o7 = __fmul2_rn(__fadd2_rn(bc(ce), b2), vs2);                               // (cy dx + cz dy) v_sigma
+                    const float2 o8 = __fmul2_rn(vis2, va2);
+                    v[3] = o3.x + o3.y; v[4] = o4.x + o4.y; v[5] = o5.x + o5.y;
+                    v[6] = o6.x + o6.y; v[7] = o7.x + o7.y; v[8] = o8.x + o8.y;
+                    if (ABS) {
+                        v[9] = fabsf(o6.x) + fabsf(o6.y);
+                        v[10] = fabsf(o7.x) + fabsf(o7.y);
+                    }
                 }
                 // transpose through shared memory: row r = value r of the 32 lanes
                 __syncwarp();
