@@ -474,7 +474,10 @@ raster_bwd_hits_kernel(const RasterParams p, const void *__restrict__ list,
     const float4 *red_row = reinterpret_cast<const float4 *>(
         red + min(lane >> 1, NV - 1) * RED_STRIDE + (lane & 1) * 16);
     auto reduce_rows = [&]() -> float {
-        const float4 p0 = red_row[0], p1 = red_row[1], p2 = red_row[2], p3 = red_row[3];
+        // (only the 2 NV reducer lanes load: a quarter-warp without an active lane costs no
+        // shared-memory wavefront -- 3 instead of 4 per LDS.128, of a pipe that runs 70 % busy)
+        float4 p0 = make_float4(0.f, 0.f, 0.f, 0.f), p1 = p0, p2 = p0, p3 = p0;
+        if (lane < 2 * NV) { p0 = red_row[0]; p1 = red_row[1]; p2 = red_row[2]; p3 = red_row[3]; }
         float2 u0 = __fadd2_rn(f2(p0.x, p0.y), f2(p0.z, p0.w));
         float2 u1 = __fadd2_rn(f2(p1.x, p1.y), f2(p1.z, p1.w));
         float2 u2 = __fadd2_rn(f2(p2.x, p2.y), f2(p2.z, p2.w));
