@@ -244,6 +244,29 @@ def test_in_switch_allreduce_two_ranks():
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 
 
+def test_in_switch_allreduce_kernel_on_one_gpu():
+    """csrc/collective.cu on the ONE-GPU box the driver's tests run on: a multicast object with a team
+    of one device (driver API; tools/multicast_single.py), the kernel with world = 1 -- every
+    instruction of its data path (multimem.ld_reduce, multimem.st, arrive / depart flags), result =
+    the data itself bit for bit.  Skipped where the driver refuses a one-device multicast team
+    (measured: a one-GPU slice of an 8-GPU node answers cuMulticastCreate with INVALID_VALUE for any
+    team size or handle type, so on the driver's test box this test documents the attempt; the
+    two-rank test above is what exercises the kernel, `profiles/r03m_pytest_2gpu.log`)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "multicast_single.py"), "1048576"],
+                       capture_output=True, text=True, timeout=300)
+    line = (r.stdout.strip().splitlines() or ["{}"])[-1]
+    assert r.returncode == 0, r.stdout[-1000:] + r.stderr[-2000:]
+    import json
+    res = json.loads(line)
+    if res.get("skipped"):
+        pytest.skip(res["skipped"])
+    assert res["ok"], res
+
+
 def _bw8_scene():
     s = synthetic.benchmark_scene(5000, (100, 136), scale_max=0.3, seed=12)
     s.block_size = 8
