@@ -34,13 +34,18 @@
 namespace jsb {
 namespace {
 
-constexpr int DS_THREADS = 512;
+// threads per CTA: the register file holds one CTA per SM either way (keys, ids and ranks of a tile
+// live in registers), so more threads x fewer items each = more warps to hide the ranking chain
+#ifndef JSB_DS_THREADS
+#define JSB_DS_THREADS 512
+#endif
+constexpr int DS_THREADS = JSB_DS_THREADS;
 constexpr int DS_WARPS = DS_THREADS / 32;
-constexpr int DS_IPT = 16;                       // items per thread and tile, at most
-constexpr int DS_TILE = DS_THREADS * DS_IPT;     // 8192
+constexpr int DS_TILE = 8192;                    // keys per tile, at most
+constexpr int DS_IPT = DS_TILE / DS_THREADS;     // items per thread and tile, at most
 constexpr int DS_BITS = 9;
-constexpr int DS_BINS = 1 << DS_BITS;            // == DS_THREADS: thread d owns digit d
-static_assert(DS_BINS == DS_THREADS, "one thread per digit");
+constexpr int DS_BINS = 1 << DS_BITS;            // thread d < DS_BINS owns digit d
+static_assert(DS_THREADS >= DS_BINS && DS_THREADS % DS_BINS == 0, "one thread per digit, at least");
 constexpr unsigned kSentinelKey = 0xFFFFFFFFu;   // Gaussians that hit no tile
 constexpr int DS_MAXG = 256;                     // CTAs (= SMs used) at most
 constexpr int DS_MAXK = 16;                      // digits one CTA scans at most (grid > 32)
@@ -56,7 +61,7 @@ struct DsParams {
     unsigned *tot;            // [DS_BINS] digit totals
     unsigned *bar;            // grid barrier counter, zero at launch
     int *err;
-    unsigned tile_items;      // multiple of 512, <= DS_TILE
+    unsigned tile_items;      // multiple of DS_THREADS, <= DS_TILE
     unsigned subtiles;        // tiles per CTA
 };
 
@@ -182,15 +187,17 @@ __global__ void __launch_bounds__(DS_THREADS, 1) resident_depth_sort_kernel(cons
         }
         __syncthreads();
         cta_count = 0;
+        if (tid < (unsigned)DS_BINS) {
 #pragma unroll
-        for (int ww = 0; ww < DS_WARPS; ++ww) {
-            const unsigned cc = S.whist[ww][tid];
-            S.whist[ww][tid] = cta_count;
-            cta_count += cc;
+            for (int ww = 0; ww < DS_WARPS; ++ww) {
+                const unsigned cc = S.whist[ww][tid];
+                S.whist[ww][tid] = cta_count;
+                cta_count += cc;
+            }
         }
         unsigned total;
         binstart = cta_exclusive_scan<DS_THREADS>(cta_count, &total, S.ws);
-        S.binstart[tid] = binstart;
+        if (tid < (unsigned)DS_BINS) S.binstart[tid] = binstart;
         __syncthreads();
     };
     // tile in registers -> shared memory, grouped by digit, in stable order
@@ -225,7 +232,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) resident_depth_sort_kernel(cons
             rank_tile(count, ipt, dg);
             cta_total += cta_count;
         }
-        P.hist[(size_t)c * DS_BINS + tid] = cta_total;
+        if (tid < (unsigned)DS_BINS) P.hist[(size_t)c * DS_BINS + tid] = cta_total;
         // (single tile: the reorder needs nothing from the other CTAs -- done under the barrier)
         if (single) reorder_tile(count, ipt, dg);
         arrivals += G;
@@ -235,7 +242,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) resident_depth_sort_kernel(cons
         unsigned before = 0, all = 0;
         if (G <= 32u) {
             // a small grid: every CTA sums the rows before it itself (at most 32 loads a thread)
-            for (unsigned r = 0; r < G; ++r) {
+            for (unsigned r = 0; r < G && tid < (unsigned)DS_BINS; ++r) {
                 const unsigned h = __ldcg(P.hist + (size_t)r * DS_BINS + tid);
                 all += h;
                 if (r < c) before += h;
@@ -273,8 +280,10 @@ __global__ void __launch_bounds__(DS_THREADS, 1) resident_depth_sort_kernel(cons
             arrivals += G;
             grid_barrier(P.bar, arrivals, P.err);
             // B2: own row of prefixes + digit totals
-            before = __ldcg(P.pre + (size_t)c * DS_BINS + tid);
-            all = __ldcg(P.tot + tid);
+            if (tid < (unsigned)DS_BINS) {
+                before = __ldcg(P.pre + (size_t)c * DS_BINS + tid);
+                all = __ldcg(P.tot + tid);
+            }
         }
         unsigned grand;
         const unsigned dbase = cta_exclusive_scan<DS_THREADS>(all, &grand, S.ws);
@@ -287,7 +296,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) resident_depth_sort_kernel(cons
                 rank_tile(count, ipt, dg);
                 reorder_tile(count, ipt, dg);
             }
-            S.goff[tid] = run - binstart;
+            if (tid < (unsigned)DS_BINS) S.goff[tid] = run - binstart;
             run += cta_count;
             __syncthreads();
             // consecutive positions of one digit go to consecutive addresses
@@ -365,7 +374,7 @@ int resident_depth_sort(cudaStream_t stream, const unsigned *keys_in, unsigned *
     const unsigned G0 = (unsigned)F.max_ctas;
     P.subtiles = std::max(1u, ceil_div(n, G0 * (unsigned)DS_TILE));
     const unsigned per_tile = ceil_div(n, G0 * P.subtiles);
-    P.tile_items = std::min((unsigned)DS_TILE, std::max(512u, ceil_div(per_tile, 512u) * 512u));
+    P.tile_items = std::min((unsigned)DS_TILE, std::max((unsigned)DS_THREADS, ceil_div(per_tile, (unsigned)DS_THREADS) * (unsigned)DS_THREADS));
     const unsigned grid = ceil_div(n, P.tile_items * P.subtiles);
     JSB_CUDA_OK(cudaMemsetAsync(P.bar, 0, 64, stream));
     void *args[] = {(void *)&P};
