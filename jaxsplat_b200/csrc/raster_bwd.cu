@@ -364,6 +364,13 @@ raster_bwd16x2p_kernel(const RasterParams p, const unsigned *__restrict__ ids_so
 #define JSB_BWDH_SPAN 32
 #endif
 constexpr int HB_SPAN = JSB_BWDH_SPAN;  // hit words expanded at a time (<= 32)
+// Visits whose partial rows are reduced together (0: every visit on its own, deferred into the
+// next one).  Three visits x nine rows = 27 rows: ONE lane per row sums its 32 partials (8
+// LDS.128) and all 27 atomics leave in one instruction, behind two __syncwarp per three visits
+// instead of two per visit.
+#ifndef JSB_BWDH_BATCH
+#define JSB_BWDH_BATCH 3
+#endif
 #ifndef JSB_BWDH_CTAS
 #define JSB_BWDH_CTAS 20     // resident one-warp CTAs per SM the register allocation is bounded for
 #endif
@@ -397,9 +404,11 @@ raster_bwd_hits_kernel(const RasterParams p, const void *__restrict__ list,
                        float *__restrict__ v_xy_abs, float *__restrict__ v_conic,
                        float *__restrict__ v_colors, float *__restrict__ v_opacity) {
     constexpr int NV = ABS ? 11 : 9;
+    constexpr int VB = JSB_BWDH_BATCH == 0 ? 0 : (ABS ? 2 : JSB_BWDH_BATCH);  // rows <= 32
+    static_assert(VB * NV <= 32, "one lane per row of a batch");
     __shared__ HbStage st[2];
     __shared__ unsigned short s_list[HB_SPAN * 32];
-    __shared__ __align__(16) float red[NV * RED_STRIDE];
+    __shared__ __align__(16) float red[(VB ? VB : 1) * NV * RED_STRIDE];
 
     const int lane = threadIdx.x;
     constexpr unsigned TS = T8 ? 8 : 16;  // tile size in pixels
@@ -447,8 +456,9 @@ raster_bwd_hits_kernel(const RasterParams p, const void *__restrict__ list,
     // pixel instead of three channels
     float2 S2 = f2(0.f, 0.f);
 
-    // lane L (even, L/2 < NV) owns output row L/2 of the reduced gradient
-    const int slot = lane >> 1;
+    // per-visit reduction: lane L (even, L/2 < NV) owns output row L/2 of the reduced gradient;
+    // batched reduction: lane L < VB * NV owns row L % NV of visit L / NV of the batch
+    const int slot = VB ? lane % NV : lane >> 1;
     float *out_base;
     int out_stride;
     if (slot < 3) { out_base = v_colors + slot; out_stride = 3; }
@@ -461,16 +471,42 @@ raster_bwd_hits_kernel(const RasterParams p, const void *__restrict__ list,
     else if (slot < 8) { out_base = v_xy + (slot - 6); out_stride = 2; }
     else if (slot < 9) { out_base = v_opacity; out_stride = 1; }
     else { out_base = v_xy_abs + (slot - 9); out_stride = 2; }
-    const bool writer = ((lane & 1) == 0) && slot < NV;
+    const bool writer = VB ? lane < VB * NV : ((lane & 1) == 0) && slot < NV;
+    const int which = VB ? lane / NV : 0;  // visit of the batch this lane reduces
+    int vb = 0;                            // visits of the current batch already stored
+    unsigned bid0 = 0, bid1 = 0, bid2 = 0; // their Gaussians
+    auto flush_batch = [&]() {             // warp-uniform; rows [0, vb * NV) hold partials
+        __syncwarp();
+        if (lane < vb * NV) {
+            const float4 *row = reinterpret_cast<const float4 *>(red + lane * RED_STRIDE);
+            float2 u[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float4 q = row[i];
+                u[i] = __fadd2_rn(f2(q.x, q.y), f2(q.z, q.w));
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) u[i] = __fadd2_rn(u[i], u[i + 4]);
+            u[0] = __fadd2_rn(u[0], u[2]);
+            u[1] = __fadd2_rn(u[1], u[3]);
+            u[0] = __fadd2_rn(u[0], u[1]);
+            const unsigned id = which == 0 ? bid0 : which == 1 ? bid1 : bid2;
+            atomicAdd(out_base + id * (unsigned)out_stride, u[0].x + u[0].y);
+        }
+        __syncwarp();
+        vb = 0;
+    };
 
     // `red` always holds the partials of the previous visit (zeros before the first one) and
     // pend_id its Gaussian: the reduction + atomics at the top of every visit need no flag.  Before
     // the first visit the zeros go to the warp's own first Gaussian (not to one shared word).
     unsigned pend_id = 0;
     bool first_chunk = true;
+    if (!VB) {
 #pragma unroll
-    for (int r = 0; r < NV; ++r) red[r * RED_STRIDE + lane] = 0.f;
-    __syncwarp();
+        for (int r = 0; r < NV; ++r) red[r * RED_STRIDE + lane] = 0.f;
+        __syncwarp();
+    }
     const float4 *red_row = reinterpret_cast<const float4 *>(
         red + min(lane >> 1, NV - 1) * RED_STRIDE + (lane & 1) * 16);
     auto reduce_rows = [&]() -> float {
@@ -571,7 +607,7 @@ raster_bwd_hits_kernel(const RasterParams p, const void *__restrict__ list,
                 const float4 a = S.A[t];    // {x, y, opacity, cx}
                 const float4 bq = S.B[t];   // {cy, cz, r, g}
                 const float4 cq = S.C[t];   // {b, id, sorted index, -}
-                float total_r = reduce_rows();  // previous visit's partials
+                float total_r = VB ? 0.f : reduce_rows();  // previous visit's partials
                 // conic_sigma (common.cuh) lane by lane, in the reference's operation order
                 const float dx = fsub(a.x, px);
                 const float2 dy2 = __fadd2_rn(bc(a.y), npy2);
@@ -589,15 +625,19 @@ raster_bwd_hits_kernel(const RasterParams p, const void *__restrict__ list,
                 const int sidx = __float_as_int(cq.z);
                 const bool ok0 = in0 && (sidx <= bf0) && !(sg2.x < 0.f) && !(al0 < kAlphaMin);
                 const bool ok1 = in1 && (sidx <= bf1) && !(sg2.y < 0.f) && !(al1 < kAlphaMin);
-                total_r += __shfl_xor_sync(0xffffffffu, total_r, 1);
-                if (writer) atomicAdd(out_base + pend_id * (unsigned)out_stride, total_r);
+                if (!VB) {
+                    total_r += __shfl_xor_sync(0xffffffffu, total_r, 1);
+                    if (writer) atomicAdd(out_base + pend_id * (unsigned)out_stride, total_r);
+                }
                 // (a hit-driven visit has an accepting pixel by construction; only the replay of
                 // EVERY entry meets visits without one, worth a vote to skip -- leaving zero rows)
                 if (ALL && !__any_sync(0xffffffffu, ok0 || ok1)) {
-                    __syncwarp();
+                    if (!VB) {
+                        __syncwarp();
 #pragma unroll
-                    for (int r = 0; r < NV; ++r) red[r * RED_STRIDE + lane] = 0.f;
-                    __syncwarp();
+                        for (int r = 0; r < NV; ++r) red[r * RED_STRIDE + lane] = 0.f;
+                        __syncwarp();
+                    }
                     continue;
                 }
 
@@ -664,15 +704,25 @@ raster_bwd_hits_kernel(const RasterParams p, const void *__restrict__ list,
                     }
                 }
                 // transpose through shared memory: row r = value r of the 32 lanes
-                __syncwarp();
+                if (VB) {
 #pragma unroll
-                for (int r = 0; r < NV; ++r) red[r * RED_STRIDE + lane] = v[r];
-                __syncwarp();
-                pend_id = __float_as_uint(cq.y);
+                    for (int r = 0; r < NV; ++r) red[(vb * NV + r) * RED_STRIDE + lane] = v[r];
+                    const unsigned gid = __float_as_uint(cq.y);
+                    if (vb == 0) bid0 = gid; else if (vb == 1) bid1 = gid; else bid2 = gid;
+                    if (++vb == VB) flush_batch();
+                } else {
+                    __syncwarp();
+#pragma unroll
+                    for (int r = 0; r < NV; ++r) red[r * RED_STRIDE + lane] = v[r];
+                    __syncwarp();
+                    pend_id = __float_as_uint(cq.y);
+                }
             }
         }
     }
-    if (!first_chunk) {  // warp-uniform: the last visit of this warp
+    if (VB) {
+        if (vb > 0) flush_batch();  // warp-uniform: the last, partial batch
+    } else if (!first_chunk) {  // warp-uniform: the last visit of this warp
         float total_r = reduce_rows();
         total_r += __shfl_xor_sync(0xffffffffu, total_r, 1);
         if (writer) atomicAdd(out_base + pend_id * (unsigned)out_stride, total_r);
