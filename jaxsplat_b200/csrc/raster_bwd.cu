@@ -367,7 +367,7 @@ constexpr int HB_SPAN = JSB_BWDH_SPAN;  // hit words expanded at a time (<= 32)
 // Visits whose partial rows are reduced together (0: every visit on its own, deferred into the
 // next one).  Three visits x nine rows = 27 rows: ONE lane per row sums its 32 partials (8
 // LDS.128) and all 27 atomics leave in one instruction, behind two __syncwarp per three visits
-// instead of two per visit.
+// instead of two per visit.  More than 32 rows take another round of the same lanes.
 #ifndef JSB_BWDH_BATCH
 #define JSB_BWDH_BATCH 3
 #endif
@@ -404,8 +404,9 @@ raster_bwd_hits_kernel(const RasterParams p, const void *__restrict__ list,
                        float *__restrict__ v_xy_abs, float *__restrict__ v_conic,
                        float *__restrict__ v_colors, float *__restrict__ v_opacity) {
     constexpr int NV = ABS ? 11 : 9;
-    constexpr int VB = JSB_BWDH_BATCH == 0 ? 0 : (ABS ? 2 : JSB_BWDH_BATCH);  // rows <= 32
-    static_assert(VB * NV <= 32, "one lane per row of a batch");
+    constexpr int VB = JSB_BWDH_BATCH == 0 ? 0 : (ABS ? 2 : JSB_BWDH_BATCH);
+    static_assert(VB <= 8, "batch ids live in eight shared words");
+    __shared__ unsigned s_bid[8];  // the Gaussians of the batch's visits
     __shared__ HbStage st[2];
     __shared__ unsigned short s_list[HB_SPAN * 32];
     __shared__ __align__(16) float red[(VB ? VB : 1) * NV * RED_STRIDE];
@@ -458,40 +459,53 @@ raster_bwd_hits_kernel(const RasterParams p, const void *__restrict__ list,
 
     // per-visit reduction: lane L (even, L/2 < NV) owns output row L/2 of the reduced gradient;
     // batched reduction: lane L < VB * NV owns row L % NV of visit L / NV of the batch
-    const int slot = VB ? lane % NV : lane >> 1;
+    const int slot = VB ? 0 : lane >> 1;
+    // where row `s` (0 .. NV-1) of a visit's reduced gradient accumulates: base pointer, stride
+    auto row_target = [&](int s, float *&base, int &stride) {
+        if (s < 3) { base = v_colors + s; stride = 3; }
+        else if (MOMENTS) {
+            if (s < 4) { base = v_opacity; stride = 1; }
+            else if (s < 6) { base = v_xy + (s - 4); stride = 2; }
+            else { base = v_conic + min(s - 6, 2); stride = 3; }
+        }
+        else if (s < 6) { base = v_conic + (s - 3); stride = 3; }
+        else if (s < 8) { base = v_xy + (s - 6); stride = 2; }
+        else if (s < 9) { base = v_opacity; stride = 1; }
+        else { base = v_xy_abs + (s - 9); stride = 2; }
+    };
     float *out_base;
     int out_stride;
-    if (slot < 3) { out_base = v_colors + slot; out_stride = 3; }
-    else if (MOMENTS) {
-        if (slot < 4) { out_base = v_opacity; out_stride = 1; }
-        else if (slot < 6) { out_base = v_xy + (slot - 4); out_stride = 2; }
-        else { out_base = v_conic + min(slot - 6, 2); out_stride = 3; }
-    }
-    else if (slot < 6) { out_base = v_conic + (slot - 3); out_stride = 3; }
-    else if (slot < 8) { out_base = v_xy + (slot - 6); out_stride = 2; }
-    else if (slot < 9) { out_base = v_opacity; out_stride = 1; }
-    else { out_base = v_xy_abs + (slot - 9); out_stride = 2; }
-    const bool writer = VB ? lane < VB * NV : ((lane & 1) == 0) && slot < NV;
-    const int which = VB ? lane / NV : 0;  // visit of the batch this lane reduces
+    row_target(slot, out_base, out_stride);
+    const bool writer = ((lane & 1) == 0) && slot < NV;
+    // batched reduction: in round k lane L owns row 32 k + L of the batch = row (32 k + L) % NV of
+    // visit (32 k + L) / NV
+    constexpr int ROUNDS = VB ? (VB * NV + 31) / 32 : 0;
+    float *b_base[ROUNDS ? ROUNDS : 1];
+    int b_stride[ROUNDS ? ROUNDS : 1];
+#pragma unroll
+    for (int k = 0; k < ROUNDS; ++k) row_target((32 * k + lane) % NV, b_base[k], b_stride[k]);
     int vb = 0;                            // visits of the current batch already stored
-    unsigned bid0 = 0, bid1 = 0, bid2 = 0; // their Gaussians
     auto flush_batch = [&]() {             // warp-uniform; rows [0, vb * NV) hold partials
         __syncwarp();
-        if (lane < vb * NV) {
-            const float4 *row = reinterpret_cast<const float4 *>(red + lane * RED_STRIDE);
-            float2 u[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const float4 q = row[i];
-                u[i] = __fadd2_rn(f2(q.x, q.y), f2(q.z, q.w));
+        for (int k = 0; k < ROUNDS; ++k) {
+            const int rowi = 32 * k + lane;
+            if (rowi < vb * NV) {
+                const float4 *row = reinterpret_cast<const float4 *>(red + rowi * RED_STRIDE);
+                float2 u[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float4 q = row[i];
+                    u[i] = __fadd2_rn(f2(q.x, q.y), f2(q.z, q.w));
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) u[i] = __fadd2_rn(u[i], u[i + 4]);
+                u[0] = __fadd2_rn(u[0], u[2]);
+                u[1] = __fadd2_rn(u[1], u[3]);
+                u[0] = __fadd2_rn(u[0], u[1]);
+                const unsigned id = s_bid[rowi / NV];
+                atomicAdd(b_base[k] + id * (unsigned)b_stride[k], u[0].x + u[0].y);
             }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) u[i] = __fadd2_rn(u[i], u[i + 4]);
-            u[0] = __fadd2_rn(u[0], u[2]);
-            u[1] = __fadd2_rn(u[1], u[3]);
-            u[0] = __fadd2_rn(u[0], u[1]);
-            const unsigned id = which == 0 ? bid0 : which == 1 ? bid1 : bid2;
-            atomicAdd(out_base + id * (unsigned)out_stride, u[0].x + u[0].y);
         }
         __syncwarp();
         vb = 0;
@@ -707,8 +721,7 @@ raster_bwd_hits_kernel(const RasterParams p, const void *__restrict__ list,
                 if (VB) {
 #pragma unroll
                     for (int r = 0; r < NV; ++r) red[(vb * NV + r) * RED_STRIDE + lane] = v[r];
-                    const unsigned gid = __float_as_uint(cq.y);
-                    if (vb == 0) bid0 = gid; else if (vb == 1) bid1 = gid; else bid2 = gid;
+                    if (lane == 0) s_bid[vb] = __float_as_uint(cq.y);
                     if (++vb == VB) flush_batch();
                 } else {
                     __syncwarp();
