@@ -28,6 +28,9 @@ SEL="test_super_column or test_block_size_8 or test_lean_residuals or test_rende
 timeout 1200 compute-sanitizer --tool memcheck --error-exitcode 7 --print-limit 20 \
     python -m pytest tests -m gpu -q -x -k "$SEL" > $OUT/${TAG}_sanitize_memcheck.log 2>&1
 echo "memcheck rc=$?"; grep -E "ERROR SUMMARY|passed|failed|Invalid|out of bounds" $OUT/${TAG}_sanitize_memcheck.log | tail -6
+timeout 900 compute-sanitizer --tool racecheck --error-exitcode 7 --print-limit 10 \
+    python -m pytest tests -m gpu -q -x -k "test_super_column_lists_render_the_same_image_and_gradients and (ragged or tiny) or test_block_size_8_tuned_kernels_equal_the_generic_ones and tiny or test_hit_driven_backward_equals_the_batch_kernel and not C2" > $OUT/${TAG}_sanitize_racecheck.log 2>&1
+echo "racecheck rc=$?"; grep -E "RACECHECK SUMMARY|passed|failed" $OUT/${TAG}_sanitize_racecheck.log | tail -4
 python - <<PY
 import json, glob
 for f in sorted(glob.glob("${OUT}/${TAG}_bench*.json")):
