@@ -404,12 +404,12 @@ raster_bwd_hits_kernel(const RasterParams p, const void *__restrict__ list,
                        float *__restrict__ v_xy_abs, float *__restrict__ v_conic,
                        float *__restrict__ v_colors, float *__restrict__ v_opacity) {
     constexpr int NV = ABS ? 11 : 9;
-    constexpr int VB = JSB_BWDH_BATCH == 0 ? 0 : (ABS ? 2 : JSB_BWDH_BATCH);
-    static_assert(VB <= 8, "batch ids live in eight shared words");
+    constexpr int VB = ABS ? 2 : JSB_BWDH_BATCH;  // visits per reduction batch
+    static_assert(VB >= 1 && VB <= 8, "batch ids live in eight shared words");
     __shared__ unsigned s_bid[8];  // the Gaussians of the batch's visits
     __shared__ HbStage st[2];
     __shared__ unsigned short s_list[HB_SPAN * 32];
-    __shared__ __align__(16) float red[(VB ? VB : 1) * NV * RED_STRIDE];
+    __shared__ __align__(16) float red[VB * NV * RED_STRIDE];
 
     const int lane = threadIdx.x;
     constexpr unsigned TS = T8 ? 8 : 16;  // tile size in pixels
@@ -457,9 +457,6 @@ raster_bwd_hits_kernel(const RasterParams p, const void *__restrict__ list,
     // pixel instead of three channels
     float2 S2 = f2(0.f, 0.f);
 
-    // per-visit reduction: lane L (even, L/2 < NV) owns output row L/2 of the reduced gradient;
-    // batched reduction: lane L < VB * NV owns row L % NV of visit L / NV of the batch
-    const int slot = VB ? 0 : lane >> 1;
     // where row `s` (0 .. NV-1) of a visit's reduced gradient accumulates: base pointer, stride
     auto row_target = [&](int s, float *&base, int &stride) {
         if (s < 3) { base = v_colors + s; stride = 3; }
@@ -473,24 +470,19 @@ raster_bwd_hits_kernel(const RasterParams p, const void *__restrict__ list,
         else if (s < 9) { base = v_opacity; stride = 1; }
         else { base = v_xy_abs + (s - 9); stride = 2; }
     };
-    float *out_base;
-    int out_stride;
-    row_target(slot, out_base, out_stride);
-    const bool writer = ((lane & 1) == 0) && slot < NV;
     // batched reduction: in round k lane L owns row 32 k + L of the batch = row (32 k + L) % NV of
     // visit (32 k + L) / NV
-    constexpr int ROUNDS = VB ? (VB * NV + 31) / 32 : 0;
-    float *b_base[ROUNDS ? ROUNDS : 1];
-    int b_stride[ROUNDS ? ROUNDS : 1];
+    constexpr int ROUNDS = (VB * NV + 31) / 32;
+    float *b_base[ROUNDS];
+    int b_stride[ROUNDS];
 #pragma unroll
     for (int k = 0; k < ROUNDS; ++k) row_target((32 * k + lane) % NV, b_base[k], b_stride[k]);
-    int vb = 0;                            // visits of the current batch already stored
-    auto flush_batch = [&]() {             // warp-uniform; rows [0, vb * NV) hold partials
+    auto flush_batch = [&](const int nb) {  // warp-uniform; rows [0, nb * NV) hold partials
         __syncwarp();
 #pragma unroll
         for (int k = 0; k < ROUNDS; ++k) {
             const int rowi = 32 * k + lane;
-            if (rowi < vb * NV) {
+            if (rowi < nb * NV) {
                 const float4 *row = reinterpret_cast<const float4 *>(red + rowi * RED_STRIDE);
                 float2 u[8];
 #pragma unroll
@@ -508,34 +500,6 @@ raster_bwd_hits_kernel(const RasterParams p, const void *__restrict__ list,
             }
         }
         __syncwarp();
-        vb = 0;
-    };
-
-    // `red` always holds the partials of the previous visit (zeros before the first one) and
-    // pend_id its Gaussian: the reduction + atomics at the top of every visit need no flag.  Before
-    // the first visit the zeros go to the warp's own first Gaussian (not to one shared word).
-    unsigned pend_id = 0;
-    bool first_chunk = true;
-    if (!VB) {
-#pragma unroll
-        for (int r = 0; r < NV; ++r) red[r * RED_STRIDE + lane] = 0.f;
-        __syncwarp();
-    }
-    const float4 *red_row = reinterpret_cast<const float4 *>(
-        red + min(lane >> 1, NV - 1) * RED_STRIDE + (lane & 1) * 16);
-    auto reduce_rows = [&]() -> float {
-        // (only the 2 NV reducer lanes load: a quarter-warp without an active lane costs no
-        // shared-memory wavefront -- 3 instead of 4 per LDS.128, of a pipe that runs 70 % busy)
-        float4 p0 = make_float4(0.f, 0.f, 0.f, 0.f), p1 = p0, p2 = p0, p3 = p0;
-        if (lane < 2 * NV) { p0 = red_row[0]; p1 = red_row[1]; p2 = red_row[2]; p3 = red_row[3]; }
-        float2 u0 = __fadd2_rn(f2(p0.x, p0.y), f2(p0.z, p0.w));
-        float2 u1 = __fadd2_rn(f2(p1.x, p1.y), f2(p1.z, p1.w));
-        float2 u2 = __fadd2_rn(f2(p2.x, p2.y), f2(p2.z, p2.w));
-        float2 u3 = __fadd2_rn(f2(p3.x, p3.y), f2(p3.z, p3.w));
-        u0 = __fadd2_rn(u0, u1);
-        u2 = __fadd2_rn(u2, u3);
-        u0 = __fadd2_rn(u0, u2);
-        return u0.x + u0.y;
     };
 
     const unsigned *hw = hit_words + (SUPER
@@ -612,16 +576,12 @@ raster_bwd_hits_kernel(const RasterParams p, const void *__restrict__ list,
             fetch((s + 2) * 32 + lane);
             const HbStage &S = st[s & 1];
             const int cs = min(32, total - s * 32);
-            if (first_chunk) {  // warp-uniform, once per kernel
-                pend_id = __float_as_uint(S.C[0].y);
-                first_chunk = false;
-            }
-#pragma unroll 1
-            for (int t = 0; t < cs; ++t) {
+            // visit t of the sub-chunk; its partial rows go to slot k of the reduction batch (k is
+            // a compile-time constant in the unrolled callers: row addresses are immediates)
+            auto visit = [&](const int t, const int k) {
                 const float4 a = S.A[t];    // {x, y, opacity, cx}
                 const float4 bq = S.B[t];   // {cy, cz, r, g}
                 const float4 cq = S.C[t];   // {b, id, sorted index, -}
-                float total_r = VB ? 0.f : reduce_rows();  // previous visit's partials
                 // conic_sigma (common.cuh) lane by lane, in the reference's operation order
                 const float dx = fsub(a.x, px);
                 const float2 dy2 = __fadd2_rn(bc(a.y), npy2);
@@ -639,20 +599,13 @@ raster_bwd_hits_kernel(const RasterParams p, const void *__restrict__ list,
                 const int sidx = __float_as_int(cq.z);
                 const bool ok0 = in0 && (sidx <= bf0) && !(sg2.x < 0.f) && !(al0 < kAlphaMin);
                 const bool ok1 = in1 && (sidx <= bf1) && !(sg2.y < 0.f) && !(al1 < kAlphaMin);
-                if (!VB) {
-                    total_r += __shfl_xor_sync(0xffffffffu, total_r, 1);
-                    if (writer) atomicAdd(out_base + pend_id * (unsigned)out_stride, total_r);
-                }
+                if (lane == 0) s_bid[k] = __float_as_uint(cq.y);
                 // (a hit-driven visit has an accepting pixel by construction; only the replay of
                 // EVERY entry meets visits without one, worth a vote to skip -- leaving zero rows)
                 if (ALL && !__any_sync(0xffffffffu, ok0 || ok1)) {
-                    if (!VB) {
-                        __syncwarp();
 #pragma unroll
-                        for (int r = 0; r < NV; ++r) red[r * RED_STRIDE + lane] = 0.f;
-                        __syncwarp();
-                    }
-                    continue;
+                    for (int r = 0; r < NV; ++r) red[(k * NV + r) * RED_STRIDE + lane] = 0.f;
+                    return;
                 }
 
                 // invalid pixels: vis = 0 makes alpha = 0, ra = rcp(1) = 1 and every partial
@@ -718,27 +671,23 @@ raster_bwd_hits_kernel(const RasterParams p, const void *__restrict__ list,
                     }
                 }
                 // transpose through shared memory: row r = value r of the 32 lanes
-                if (VB) {
 #pragma unroll
-                    for (int r = 0; r < NV; ++r) red[(vb * NV + r) * RED_STRIDE + lane] = v[r];
-                    if (lane == 0) s_bid[vb] = __float_as_uint(cq.y);
-                    if (++vb == VB) flush_batch();
-                } else {
-                    __syncwarp();
+                for (int r = 0; r < NV; ++r) red[(k * NV + r) * RED_STRIDE + lane] = v[r];
+            };
+            int t0 = 0;
+#pragma unroll 1
+            for (; t0 + VB <= cs; t0 += VB) {  // full batches: VB visits, one reduction
 #pragma unroll
-                    for (int r = 0; r < NV; ++r) red[r * RED_STRIDE + lane] = v[r];
-                    __syncwarp();
-                    pend_id = __float_as_uint(cq.y);
-                }
+                for (int k = 0; k < VB; ++k) visit(t0 + k, k);
+                flush_batch(VB);
+            }
+            if (t0 < cs) {  // the sub-chunk's last, partial batch
+#pragma unroll
+                for (int k = 0; k < VB - 1; ++k)
+                    if (t0 + k < cs) visit(t0 + k, k);
+                flush_batch(cs - t0);
             }
         }
-    }
-    if (VB) {
-        if (vb > 0) flush_batch();  // warp-uniform: the last, partial batch
-    } else if (!first_chunk) {  // warp-uniform: the last visit of this warp
-        float total_r = reduce_rows();
-        total_r += __shfl_xor_sync(0xffffffffu, total_r, 1);
-        if (writer) atomicAdd(out_base + pend_id * (unsigned)out_stride, total_r);
     }
 }
 
