@@ -13,10 +13,11 @@
 //     was rebuilt by the backward itself): same CTA/quadrant layout, staging and conservative
 //     culling as raster_fwd.cu, starting at the batch holding the largest final_idx of the tile;
 //   * both: two pixels per lane in packed FP32x2 registers; the per-pixel partial gradients are
-//     reduced across the warp through a per-warp shared transpose (conflict-free STS, then 18
-//     lanes each sum half a row with 4 LDS.128 + 7 FADD2, one shuffle joins the halves) instead of
-//     full butterflies, and the totals end up in different lanes which issue ONE predicated
-//     RED.ADD.F32 instruction; the reduction of a visit is deferred into the next visit;
+//     reduced across the warp through a per-warp shared transpose (conflict-free STS, then lanes
+//     summing rows with LDS.128 + FADD2) instead of full butterflies, and the totals end up in
+//     different lanes which issue ONE RED.ADD.F32 instruction.  The hit-driven kernel reduces the
+//     rows of THREE visits together (one lane per row); the batch kernel reduces every visit on
+//     its own (18 lanes, half a row each), deferred into the next visit;
 //   * invalid lanes are not branched around: their alpha and visibility are forced to 0, which
 //     makes every partial exactly 0 and leaves T and the colour buffer unchanged.
 #include "common.cuh"
@@ -359,15 +360,16 @@ raster_bwd16x2p_kernel(const RasterParams p, const unsigned *__restrict__ ids_so
 // positions in shared memory (newest first); visits are then staged 32 at a time -- lane j gathers
 // the sorted id and the 48-byte record of visit j (cp.async, double buffered, ids one sub-chunk
 // further ahead) -- and replayed with exactly the arithmetic of raster_bwd16x2p_kernel, including
-// the deferred cross-lane reduction.
+// the cross-lane reduction (batched: see JSB_BWDH_BATCH).
 #ifndef JSB_BWDH_SPAN
 #define JSB_BWDH_SPAN 32
 #endif
 constexpr int HB_SPAN = JSB_BWDH_SPAN;  // hit words expanded at a time (<= 32)
-// Visits whose partial rows are reduced together (0: every visit on its own, deferred into the
-// next one).  Three visits x nine rows = 27 rows: ONE lane per row sums its 32 partials (8
-// LDS.128) and all 27 atomics leave in one instruction, behind two __syncwarp per three visits
-// instead of two per visit.  More than 32 rows take another round of the same lanes.
+// Visits whose partial rows are reduced together.  Three visits x nine rows = 27 rows: ONE lane
+// per row sums its 32 partials (8 LDS.128) and all 27 atomics leave in one instruction, behind two
+// __syncwarp per three visits instead of two per visit; the visits of a batch are unrolled, so the
+// batch slot is a compile-time constant.  More than 32 rows take another round of the same lanes
+// (measured slower: 2 -> 207, 3 -> 196, 5 -> 209, 7 -> 211 us at C3).
 #ifndef JSB_BWDH_BATCH
 #define JSB_BWDH_BATCH 3
 #endif
