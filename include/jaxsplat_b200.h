@@ -182,6 +182,10 @@ JSB200_API unsigned long long jsb200_error_count(void);
  *               forward recorded which list entries every 8x8 quadrant accepted),
  *      "sort1k" (1 default; 0 orders the Gaussians by depth with four onesweep passes over all 32
  *               key bits instead of the single cooperative launch over the live bits),
+ *      "pdl" (1 default; the kernels of a step that follow another kernel directly are launched
+ *               with programmatic stream serialization: they become resident while their
+ *               predecessor drains and wait for it in the kernel (griddepcontrol.wait) before
+ *               their first global access; 0: plain launches),
  *      "timing" (0 default; 1 brackets every stage with CUDA events, see jsb200_get_stage_times),
  *      "view_slots" (8 default; binning workspaces a batched-camera call cycles through) */
 JSB200_API int jsb200_set_option(const char *key, int value);

@@ -64,6 +64,9 @@ static bool g_disable_resident_sort = false;  // option "sort1k" 0: the four-pas
 // option "supercols" (0 = the exact per-tile lists everywhere).  The four-op API always builds the
 // exact lists: its final_idx / sorted ids are the reference's.
 static unsigned g_sc_shift = 2;
+// Programmatic dependent launch for the kernel-to-kernel boundaries of the step (common.cuh:
+// launch_chained / chain_wait); option "pdl".
+bool g_pdl = true;
 static std::atomic<unsigned long long> g_list_entries{0};  // (row entry, super-column) pairs of the last prep
 static std::atomic<unsigned> g_list_shift{0};              // super-column shift of the last list build (0: exact)
 static unsigned g_view_slots = 8;  // binning workspaces a batched-camera call cycles through
@@ -262,9 +265,9 @@ constexpr int SM_FP = 0, SM_TOTAL = 1;       // u64 slots in `small`
 constexpr int SM_ROWS = 4;                   // u64 slot: sum of box heights (row entries)
 constexpr int SM_SUPER = 6;                  // u64 slot: (row entry, super-column) pairs
 constexpr int SM_KEYRANGE = 5;               // u64 slot = two u32: max(~key), max(key) of the real depth keys
-constexpr int SM_ERR_WORD = 4;               // int slots start (byte 16)
 constexpr int SM_STRIP = 8;                  // u64 per-strip intersection counts start (byte 64)
-constexpr size_t SMALL_BYTES = 64 + 8 * kMaxStrips;
+constexpr int SM_ERR_WORD = (64 + 8 * kMaxStrips) / 4;  // four sticky int error words behind the strips
+constexpr size_t SMALL_BYTES = 64 + 8 * kMaxStrips + 16;
 
 // ---- binning -----------------------------------------------------------------------------------
 // Enqueues prep (+fingerprint, +totals) and the D2H of the 64 control bytes, records ev_ready and
@@ -293,10 +296,10 @@ static int bin_begin(Ctx &c, const Descriptor &d, bool write) {
                                                      resident_sort_scratch_bytes(n))))
         return 1;
     if (write && c.ensure(c.order, (size_t)n * 4)) return 1;
-    // zero fingerprint/total (bytes 0..16) and the counters at 32..64; the error words (16..32) are
-    // sticky so that a device-side failure of the PREVIOUS call is seen at this call's sync
-    JSB_CUDA_OK(cudaMemsetAsync(c.small.p, 0, 16, s));
-    JSB_CUDA_OK(cudaMemsetAsync((char *)c.small.p + 32, 0, 32, s));
+    // zero fingerprint / totals / counters (bytes 0..64) with one memset; the error words live
+    // behind the strip counts and are sticky, so that a device-side failure of the PREVIOUS call is
+    // seen at this call's sync
+    JSB_CUDA_OK(cudaMemsetAsync(c.small.p, 0, 64, s));
     const BinParams bp = bin_params(d);
     const unsigned nstrips = ceil_div(bp.band_y1 - bp.band_y0, bp.strip_rows);
     if (nstrips > 1) JSB_CUDA_OK(cudaMemsetAsync((char *)c.small.p + 64, 0, 8 * nstrips, s));
@@ -309,10 +312,8 @@ static int bin_finish_enqueue(Ctx &c, const Descriptor &d, bool write) {
     const unsigned n = d.num_points;
     cudaStream_t s = c.stream;
     if (n == 0) return 0;
-    const BinParams bp = bin_params(d);
-    const unsigned nstrips = ceil_div(bp.band_y1 - bp.band_y0, bp.strip_rows);
-    JSB_CUDA_OK(cudaMemcpyAsync(c.h_pinned, c.small.p, 64 + (nstrips > 1 ? 8 * nstrips : 0),
-                                cudaMemcpyDeviceToHost, s));
+    // (one copy of the whole block: the error words sit behind the strip counts)
+    JSB_CUDA_OK(cudaMemcpyAsync(c.h_pinned, c.small.p, SMALL_BYTES, cudaMemcpyDeviceToHost, s));
     JSB_CUDA_OK(cudaEventRecord(c.ev_ready, s));
     if (write) {
         StageScope ss(&c, ST_DEPTH_SORT);
@@ -340,7 +341,7 @@ static int bin_finish_enqueue(Ctx &c, const Descriptor &d, bool write) {
     return 0;
 }
 
-// Enqueues prep (+fingerprint, +totals), the D2H of the 64 control bytes and (writing prep) the
+// Enqueues prep (+fingerprint, +totals), the D2H of the control block and (writing prep) the
 // depth sort; bin_prepare_wait() then blocks the host until the control bytes have arrived.
 static int bin_prepare_enqueue(Ctx &c, const Descriptor &d, const float *xys, const float *depths,
                                const int *radii, const float *conics, const float *opac,
@@ -379,7 +380,7 @@ static int bin_prepare_wait(Ctx &c, const Descriptor &d, unsigned long long *I,
     if (e[0] | e[1] | e[2] | e[3]) {
         set_error("device-side look-back spin limit tripped in an earlier call (flags %d %d %d %d)",
                   e[0], e[1], e[2], e[3]);
-        JSB_CUDA_OK(cudaMemsetAsync((char *)c.small.p + 16, 0, 16, c.stream));
+        JSB_CUDA_OK(cudaMemsetAsync((char *)c.small.p + 4 * SM_ERR_WORD, 0, 16, c.stream));
         return 1;
     }
     return 0;
@@ -1292,6 +1293,7 @@ int jsb200_set_option(const char *key, int value) {
         jsb::g_bwd_all_entries = (value == 2);
         return 0;
     }
+    if (!strcmp(key, "pdl")) { jsb::g_pdl = (value != 0); return 0; }
     if (!strcmp(key, "sort1k")) { jsb::g_disable_resident_sort = (value == 0); return 0; }
     if (!strcmp(key, "timing")) { jsb::g_timing = (value != 0); return 0; }
     if (!strcmp(key, "view_slots")) {

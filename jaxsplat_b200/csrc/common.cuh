@@ -100,6 +100,40 @@ __device__ __forceinline__ void cp_async_wait_all() {
 
 __host__ __device__ inline unsigned ceil_div(unsigned a, unsigned b) { return (a + b - 1) / b; }
 
+// Programmatic dependent launch (option "pdl"): a kernel launched through launch_chained() may
+// become resident while the kernel before it in the stream drains its last wave.  Such a kernel
+// calls chain_wait() before it touches global memory (all prerequisite grids complete, their
+// writes visible) and only then lets ITS successor in (chain_release()), so at most one waiting
+// grid is resident at a time.  Both are no-ops for a kernel launched the plain way.
+__device__ __forceinline__ void chain_wait() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+extern bool g_pdl;  // capi.cu
+template <typename... KArgs, typename... Args>
+inline void launch_chained(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                           cudaStream_t stream, Args &&...args) {
+    if (!g_pdl) {
+        kernel<<<grid, block, smem, stream>>>(static_cast<KArgs>(args)...);
+        return;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...) == cudaErrorNotSupported) {
+        (void)cudaGetLastError();  // (no programmatic launches here: plain ones from now on)
+        g_pdl = false;
+        kernel<<<grid, block, smem, stream>>>(static_cast<KArgs>(args)...);
+    }
+}
+
 // tile box of a projected Gaussian; reference helpers.h:9-32 (get_tile_bbox -> get_bbox).
 // float->int conversions are cvt.rzi (truncate, saturating), exactly the reference's casts.
 __device__ __forceinline__ void tile_bbox(float px, float py, float radius, float bw,

@@ -376,6 +376,7 @@ project_bwd_kernel(const ProjectBwdParams p, const float *__restrict__ means3d,
     float o_cov2d[3] = {0.f, 0.f, 0.f}, o_cov3d[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     float o_quat[4] = {0.f, 0.f, 0.f, 0.f};
     const bool live = idx < n;
+    chain_wait();
     if (live && __ldg(radii + idx) > 0) {
         const float mx = __ldg(means3d + idx * 3), my = __ldg(means3d + idx * 3 + 1),
                     mz = __ldg(means3d + idx * 3 + 2);
@@ -733,7 +734,7 @@ int launch_project_bwd(cudaStream_t stream, const ProjectBwdParams &p, const flo
     const float4 *q4 = reinterpret_cast<const float4 *>(quats);
     const float2 *vxy2 = reinterpret_cast<const float2 *>(v_xy);
 #define JSB_PBWD(F, R)                                                                              \
-    project_bwd_kernel<F, R><<<blocks, PT, 0, stream>>>(                                            \
+    launch_chained(project_bwd_kernel<F, R>, blocks, PT, 0, stream,                                 \
         p, means3d, scales, q4, viewmat, cov3ds, radii, conics, compensation, v_compensation,   \
         vxy2, v_depth, v_conic, v_mean3d, v_scale, v_quat, v_cov2d, v_cov3d,                        \
         finish ? opacities : nullptr, finish ? moment_opacity : nullptr)

@@ -426,6 +426,7 @@ raster_bwd_hits_kernel(const RasterParams p, const void *__restrict__ list,
     const unsigned *ids_sorted = reinterpret_cast<const unsigned *>(list);
     const uint2 *ents = reinterpret_cast<const uint2 *>(list);
     const unsigned super_local = (tile_y - p.band_y0) * p.cols2 + (tile_x >> p.sc_shift);
+    chain_wait();
     const int2 range = tile_bins[SUPER ? super_local : tile];
 
     float Tf0 = 1.f, Tf1 = 1.f, voa0 = 0.f, voa1 = 0.f;
@@ -779,9 +780,9 @@ int launch_raster_bwd(cudaStream_t stream, const RasterParams &p, const void *li
         return 1;
     }
 #define JSB_HITS(ABS_, MOM_, SUP_, T8_, ALL_, GRID_, HW_)                                              \
-    raster_bwd_hits_kernel<ABS_, MOM_, SUP_, T8_, ALL_><<<GRID_, 32, 0, stream>>>(                       \
-        p, list, tile_bins, records, HW_, background, final_Ts, final_idx, v_out, v_out_alpha, v_xy,     \
-        v_xy_abs, v_conic, v_colors, v_opacity)
+    launch_chained(raster_bwd_hits_kernel<ABS_, MOM_, SUP_, T8_, ALL_>, GRID_, 32, 0, stream, p, list,  \
+                   tile_bins, records, HW_, background, final_Ts, final_idx, v_out, v_out_alpha, v_xy, \
+                   v_xy_abs, v_conic, v_colors, v_opacity)
 #define JSB_HITS_MODE(SUP_, T8_, ALL_, GRID_, HW_)                                                     \
     do {                                                                                               \
         if (v_xy_abs) JSB_HITS(true, false, SUP_, T8_, ALL_, GRID_, HW_);                              \

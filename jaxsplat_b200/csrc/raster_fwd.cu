@@ -292,6 +292,7 @@ raster_fwd_warp_kernel(const RasterParams p, const void *__restrict__ list,
     const unsigned *ids_sorted = reinterpret_cast<const unsigned *>(list);
     const uint2 *ents = reinterpret_cast<const uint2 *>(list);
     const unsigned super_local = (tile_y - p.band_y0) * p.cols2 + (tile_x >> p.sc_shift);
+    chain_wait();
     const int2 range = tile_bins[SUPER ? super_local : tile];
     const int ngroups = (range.y - range.x + 31) >> 5;
     const float quad_x0 = (float)(tile_x * TS + qx), quad_y0 = (float)(tile_y * TS + qy);
@@ -535,29 +536,23 @@ int launch_raster_fwd(cudaStream_t stream, const RasterParams &p, const void *li
     if (p.sc_shift) {
         if (wrote_hits) *wrote_hits = hit_words != nullptr;
         if (g_disable_cull)
-            raster_fwd_warp_kernel<false, true, false><<<tiles, RF2, 0, stream>>>(
-                p, list, tile_bins, records, background, final_Ts, final_idx, out_img, hit_words);
+            launch_chained(raster_fwd_warp_kernel<false, true, false>, tiles, RF2, 0, stream, p, list, tile_bins, records, background, final_Ts, final_idx, out_img, hit_words);
         else
-            raster_fwd_warp_kernel<true, true, false><<<tiles, RF2, 0, stream>>>(
-                p, list, tile_bins, records, background, final_Ts, final_idx, out_img, hit_words);
+            launch_chained(raster_fwd_warp_kernel<true, true, false>, tiles, RF2, 0, stream, p, list, tile_bins, records, background, final_Ts, final_idx, out_img, hit_words);
     } else if (p.block_width == 16 && !g_fwd_batch) {
         if (wrote_hits) *wrote_hits = hit_words != nullptr;
         if (g_disable_cull)
-            raster_fwd_warp_kernel<false, false, false><<<tiles, RF2, 0, stream>>>(
-                p, list, tile_bins, records, background, final_Ts, final_idx, out_img, hit_words);
+            launch_chained(raster_fwd_warp_kernel<false, false, false>, tiles, RF2, 0, stream, p, list, tile_bins, records, background, final_Ts, final_idx, out_img, hit_words);
         else
-            raster_fwd_warp_kernel<true, false, false><<<tiles, RF2, 0, stream>>>(
-                p, list, tile_bins, records, background, final_Ts, final_idx, out_img, hit_words);
+            launch_chained(raster_fwd_warp_kernel<true, false, false>, tiles, RF2, 0, stream, p, list, tile_bins, records, background, final_Ts, final_idx, out_img, hit_words);
     } else if (p.block_width == 8 && !g_fwd_batch) {
         // 8x8 tiles: one warp per tile, four tiles per CTA
         if (wrote_hits) *wrote_hits = hit_words != nullptr;
         const unsigned ctas = (tiles + RF2 / 32 - 1) / (RF2 / 32);
         if (g_disable_cull)
-            raster_fwd_warp_kernel<false, false, true><<<ctas, RF2, 0, stream>>>(
-                p, list, tile_bins, records, background, final_Ts, final_idx, out_img, hit_words);
+            launch_chained(raster_fwd_warp_kernel<false, false, true>, ctas, RF2, 0, stream, p, list, tile_bins, records, background, final_Ts, final_idx, out_img, hit_words);
         else
-            raster_fwd_warp_kernel<true, false, true><<<ctas, RF2, 0, stream>>>(
-                p, list, tile_bins, records, background, final_Ts, final_idx, out_img, hit_words);
+            launch_chained(raster_fwd_warp_kernel<true, false, true>, ctas, RF2, 0, stream, p, list, tile_bins, records, background, final_Ts, final_idx, out_img, hit_words);
     } else if (p.block_width == 16) {
         if (wrote_hits) *wrote_hits = hit_words != nullptr;
         if (g_disable_cull)

@@ -136,6 +136,7 @@ __global__ void __launch_bounds__(32 * RC_RC_WARPS)
 rc_row_count_kernel(const RcParams p, const unsigned *__restrict__ order,
                     const uint2 *__restrict__ box_by_id, unsigned *__restrict__ l1m) {
     __shared__ unsigned s_diff_all[RC_RC_WARPS][256 + 32];
+    chain_wait();
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned *s_diff = s_diff_all[warp];
     const unsigned chunk = blockIdx.x * RC_RC_WARPS + warp;
@@ -207,6 +208,7 @@ __device__ __forceinline__ unsigned cta32_exclusive_scan_inplace(unsigned *data,
 // ---- in-place exclusive scan of every row of the level-1 matrix (one CTA per row) -----------------
 __global__ void __launch_bounds__(1024)
 rc_row_scan_kernel(const RcParams p, unsigned *__restrict__ l1m, unsigned *__restrict__ row_tot) {
+    chain_wait();
     unsigned *row = l1m + (size_t)blockIdx.x * p.n1s;
     const unsigned total = cta32_exclusive_scan_inplace(row, p.n1, [](unsigned, unsigned, unsigned) {});
     if (threadIdx.x == 0) row_tot[blockIdx.x] = total;
@@ -223,6 +225,7 @@ rc_chunk_rows_kernel(const RcParams p, const unsigned *__restrict__ row_tot,
     __shared__ unsigned s_base[256 + 1], s_start[256 + 1];
     __shared__ unsigned s_ws[256 / 32 + 1];
     const unsigned tid = threadIdx.x;
+    chain_wait();
     const unsigned n = tid < p.rows ? row_tot[tid] : 0u;
     unsigned total;
     unsigned e = cta_exclusive_scan<256>(n, &total, s_ws);
@@ -272,6 +275,7 @@ __global__ void __launch_bounds__(32 * RC_CC_WARPS)
 rc_col_count_kernel(const RcParams p, const uint4 *__restrict__ chunk_info,
                     const uint2 *__restrict__ entries, unsigned *__restrict__ m) {
     __shared__ unsigned s_diff_all[RC_CC_WARPS][512 + 32];
+    chain_wait();
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned *s_diff = s_diff_all[warp];
     const unsigned c = blockIdx.x * RC_CC_WARPS + warp;
@@ -316,6 +320,7 @@ rc_col_scan_kernel(const RcParams p, const unsigned *__restrict__ chunk_base,
     __shared__ unsigned s_part[RC_CS_WARPS][32];
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned r = blockIdx.y, col = blockIdx.x * 32u + lane;
+    chain_wait();
     const unsigned cb = chunk_base[r], ce = chunk_base[r + 1];
     const unsigned per = (ce - cb + RC_CS_WARPS - 1) / RC_CS_WARPS;
     const unsigned c0 = min(ce, cb + warp * per), c1 = min(ce, c0 + per);
@@ -354,6 +359,7 @@ rc_col_scan_kernel(const RcParams p, const unsigned *__restrict__ chunk_base,
 __global__ void __launch_bounds__(1024)
 rc_tile_scan_bins_kernel(const RcParams p, unsigned *__restrict__ tile_cnt,
                          int2 *__restrict__ tile_bins) {
+    chain_wait();
     // (super-column bins are a band-local array of the library's own; tile bins index the frame)
     int2 *bins = p.sc_shift ? tile_bins : tile_bins + (size_t)p.band_y0 * p.cols;
     cta32_exclusive_scan_inplace(tile_cnt, p.rows * p.cols2, [bins](unsigned t, unsigned base, unsigned v) {
@@ -465,6 +471,7 @@ rc_row_scatter_kernel(const RcParams p, const unsigned *__restrict__ order,
     extern __shared__ __align__(16) unsigned char rc_smem[];
     const DistSmem<uint2, RC_STAGE1, RC_G1> S(rc_smem, p.rows);
     const unsigned lane = threadIdx.x, chunk = blockIdx.x;
+    chain_wait();
     unsigned lo[RC_G1], len[RC_G1];
     uint2 pay[RC_G1];
     unsigned gid[RC_G1];
@@ -518,6 +525,7 @@ rc_col_scatter_kernel(const RcParams p, const uint4 *__restrict__ chunk_info,
     extern __shared__ __align__(16) unsigned char rc_smem[];
     const DistSmem<Payload, STAGE, G> S(rc_smem, p.cols2);
     const unsigned lane = threadIdx.x, c = blockIdx.x;
+    chain_wait();
     const uint4 info = __ldg(chunk_info + c);
     const unsigned r = info.x, ebeg = info.y, eend = info.z;
     if (ebeg >= eend) return;
@@ -629,33 +637,30 @@ int launch_rowcol_lists(cudaStream_t stream, const BinParams &bp, const unsigned
                                   : DistSmem<unsigned, RC_STAGE2, RC_G2>::bytes(p.cols2);
 
     if (phase == 0) {  // level 1: row lists
-        rc_row_count_kernel<<<ceil_div(p.n1, (unsigned)RC_RC_WARPS), 32 * RC_RC_WARPS, 0, stream>>>(
-            p, order, box_by_id, l1m);
+        launch_chained(rc_row_count_kernel, ceil_div(p.n1, (unsigned)RC_RC_WARPS), 32 * RC_RC_WARPS, 0, stream, p, order, box_by_id, l1m);
         JSB_CUDA_OK(cudaGetLastError());
-        rc_row_scan_kernel<<<p.rows, 1024, 0, stream>>>(p, l1m, row_tot);
+        launch_chained(rc_row_scan_kernel, p.rows, 1024, 0, stream, p, l1m, row_tot);
         JSB_CUDA_OK(cudaGetLastError());
-        rc_chunk_rows_kernel<<<ceil_div(p.n2max, 256u), 256, 0, stream>>>(p, row_tot, row_start,
+        launch_chained(rc_chunk_rows_kernel, ceil_div(p.n2max, 256u), 256, 0, stream, p, row_tot, row_start,
                                                                           chunk_base, chunk_info);
         JSB_CUDA_OK(cudaGetLastError());
-        rc_row_scatter_kernel<<<p.n1, 32, smem1, stream>>>(p, order, box_by_id, l1m, row_start, entries);
+        launch_chained(rc_row_scatter_kernel, p.n1, 32, smem1, stream, p, order, box_by_id, l1m, row_start, entries);
         JSB_CUDA_OK(cudaGetLastError());
         note_launch(4);
     } else if (phase == 1) {  // level 2 run starts and tile bins
-        rc_col_count_kernel<<<ceil_div(p.n2max, (unsigned)RC_CC_WARPS), 32 * RC_CC_WARPS, 0, stream>>>(
-            p, chunk_info, entries, m);
+        launch_chained(rc_col_count_kernel, ceil_div(p.n2max, (unsigned)RC_CC_WARPS), 32 * RC_CC_WARPS, 0, stream, p, chunk_info, entries, m);
         JSB_CUDA_OK(cudaGetLastError());
-        rc_col_scan_kernel<<<dim3(ceil_div(p.cols2, 32u), p.rows), 32 * RC_CS_WARPS, 0, stream>>>(
-            p, chunk_base, m, tile_cnt);
+        launch_chained(rc_col_scan_kernel, dim3(ceil_div(p.cols2, 32u), p.rows), 32 * RC_CS_WARPS, 0, stream, p, chunk_base, m, tile_cnt);
         JSB_CUDA_OK(cudaGetLastError());
-        rc_tile_scan_bins_kernel<<<1, 1024, 0, stream>>>(p, tile_cnt, tile_bins);
+        launch_chained(rc_tile_scan_bins_kernel, 1, 1024, 0, stream, p, tile_cnt, tile_bins);
         JSB_CUDA_OK(cudaGetLastError());
         note_launch(3);
     } else {  // level 2: the lists
         if (sc_shift)
-            rc_col_scatter_kernel<true><<<p.n2max, 32, smem2, stream>>>(p, chunk_info, entries, m, tile_cnt,
+            launch_chained(rc_col_scatter_kernel<true>, p.n2max, 32, smem2, stream, p, chunk_info, entries, m, tile_cnt,
                                                                         ids_sorted);
         else
-            rc_col_scatter_kernel<false><<<p.n2max, 32, smem2, stream>>>(p, chunk_info, entries, m, tile_cnt,
+            launch_chained(rc_col_scatter_kernel<false>, p.n2max, 32, smem2, stream, p, chunk_info, entries, m, tile_cnt,
                                                                          ids_sorted);
         JSB_CUDA_OK(cudaGetLastError());
         note_launch();

@@ -16,6 +16,17 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+@pytest.fixture(scope="session", autouse=True)
+def _library_options_from_env():
+    """JSB_PDL=0|1 runs the whole GPU suite with programmatic dependent launch off / on"""
+    if os.environ.get("JSB_PDL") is not None:
+        import torch
+        if torch.cuda.is_available():
+            from jaxsplat_b200 import _lib
+            _lib.set_option("pdl", int(os.environ["JSB_PDL"]))
+    yield
+
+
 def load_golden(name):
     """fixture produced by the REFERENCE's CUDA kernels (tests/golden/make_golden.py)"""
     z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))

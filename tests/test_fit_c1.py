@@ -117,3 +117,13 @@ def test_native_mse_loss_and_gradient_match_torch():
         lossf, vf = mse_loss_and_grad(a, t8.float().mul_(1.0 / 255.0))
         assert torch.equal(v8, vf)
         assert abs(float(loss8) - float(lossf)) <= 1e-6 * float(lossf)
+        # the partial sums are added in CTA order by the CTA that draws the last ticket: the same
+        # bits on every launch, back to back without a memset, and on a second stream (own scratch)
+        again = [mse_loss_and_grad(a, b)[0] for _ in range(5)]
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            other = [mse_loss_and_grad(a, b)[0] for _ in range(3)]
+        side.synchronize()
+        for l in again + other:
+            assert torch.equal(l.view(torch.int32), loss.view(torch.int32))

@@ -534,6 +534,59 @@ def test_super_column_lists_render_the_same_image_and_gradients(case):
         _lib.set_option("cache", 1)
 
 
+@pytest.mark.parametrize("case", ["C2_30k", "wide_boxes", "tiny", "block8"])
+def test_programmatic_dependent_launch_changes_nothing(case):
+    """option "pdl": the step's kernels may become resident while their predecessor drains and wait
+    on it in the kernel (griddepcontrol.wait before the first global access).  Several steps
+    enqueued back to back without a host sync, each on perturbed parameters so that a kernel that
+    ran ahead of its inputs would see the previous step's buffers: images bit for bit, gradients to
+    atomic-order noise, against the plain launches."""
+    import os
+    import jaxsplat_b200 as jsb
+    if case == "C2_30k":
+        s = synthetic.make_config("C2", num_points=30000)
+    elif case == "wide_boxes":
+        s = synthetic.benchmark_scene(20000, (272, 400), scale_max=1.5, seed=9)
+    elif case == "block8":
+        s = synthetic.benchmark_scene(5000, (200, 120), scale_max=0.5, seed=12)
+        s.block_size = 8
+    else:
+        s = synthetic.benchmark_scene(60, (40, 40), scale_max=0.3, seed=3)
+    sc = s.to(G.DEV)
+    H, W = s.img_shape
+    target = torch.rand((H, W, 3), generator=torch.Generator().manual_seed(9)).to(G.DEV)
+    base = [p.clone() for p in sc.params()]
+    shifts = [torch.tensor([0.01 * k, -0.02 * k, 0.015 * k], device=G.DEV) for k in range(4)]
+
+    def run():
+        out = []
+        for sh in shifts:  # (no sync inside the loop)
+            params = [p.clone().requires_grad_(True) for p in base]
+            with torch.no_grad():
+                params[0] += sh
+            img = jsb.render(*params, **sc.render_kwargs())
+            (((img - target) ** 2).sum() / (H * W * 3)).backward()
+            out.append((img.detach(), [p.grad for p in params]))
+        torch.cuda.synchronize()
+        return [(i.clone(), [G.npy(g) for g in gs]) for i, gs in out]
+
+    try:
+        _lib.set_option("pdl", 0)
+        ref = run()
+        ref2 = run()
+        _lib.set_option("pdl", 1)
+        for _ in range(3):
+            got = run()
+            for (img, g), (img0, g0), (_i, g0b) in zip(got, ref, ref2):
+                assert torch.equal(img.view(torch.int32), img0.view(torch.int32))
+                for a, b, b2 in zip(g, g0, g0b):
+                    nz = float(np.abs(b.astype(np.float64) - b2.astype(np.float64)).max())
+                    ok, err, scale = grad_close(a, b, rel=2e-5)
+                    assert ok or err <= 16.0 * nz, (err, scale, nz)
+    finally:
+        _lib.set_option("pdl", int(os.environ.get("JSB_PDL", "1")))
+
+
 @pytest.mark.parametrize("case", ["C2_30k", "ragged", "long_lists", "adversarial", "tiny"])
 def test_block_size_8_tuned_kernels_equal_the_generic_ones(case):
     """block_size 8 (reference lib/ffi.cu:29-36 runs one kernel for any block width): a tile is one
