@@ -122,6 +122,7 @@ struct Ctx {
     unsigned long long last_rows = 0;        // sum of box heights of the last prep (row entries)
     unsigned long long last_super = 0;       // (row entry, super-column) pairs of the last prep
     // binning cache
+    bool small_clean = false;  // bytes 0..64 of `small` are zero on the stream (see bin_begin)
     bool cache_valid = false;
     bool cache_has_records = false;  // false after a sort_and_bin-only call (no appearance data)
     bool cache_has_hits = false;     // the forward that used this binning recorded hit words
@@ -267,7 +268,9 @@ constexpr int SM_SUPER = 6;                  // u64 slot: (row entry, super-colu
 constexpr int SM_KEYRANGE = 5;               // u64 slot = two u32: max(~key), max(key) of the real depth keys
 constexpr int SM_STRIP = 8;                  // u64 per-strip intersection counts start (byte 64)
 constexpr int SM_ERR_WORD = (64 + 8 * kMaxStrips) / 4;  // four sticky int error words behind the strips
-constexpr size_t SMALL_BYTES = 64 + 8 * kMaxStrips + 16;
+constexpr int SM_SORT_BAR = SM_ERR_WORD + 4;  // two words of the depth sort's grid barrier (it leaves them zero)
+constexpr size_t SMALL_BYTES = 64 + 8 * kMaxStrips + 16 + 16;
+constexpr size_t SMALL_COPY_BYTES = 64 + 8 * kMaxStrips + 16;  // what the host reads back
 
 // ---- binning -----------------------------------------------------------------------------------
 // Enqueues prep (+fingerprint, +totals) and the D2H of the 64 control bytes, records ev_ready and
@@ -286,6 +289,7 @@ static int bin_begin(Ctx &c, const Descriptor &d, bool write) {
     if (!c.small.p) {
         if (c.ensure(c.small, SMALL_BYTES)) return 1;
         JSB_CUDA_OK(cudaMemsetAsync(c.small.p, 0, SMALL_BYTES, s));
+        c.small_clean = true;
     }
     if (n == 0) return 0;
     if (c.ensure(c.records, (size_t)n * sizeof(SplatRecord))) return 1;
@@ -296,10 +300,12 @@ static int bin_begin(Ctx &c, const Descriptor &d, bool write) {
                                                      resident_sort_scratch_bytes(n))))
         return 1;
     if (write && c.ensure(c.order, (size_t)n * 4)) return 1;
-    // zero fingerprint / totals / counters (bytes 0..64) with one memset; the error words live
-    // behind the strip counts and are sticky, so that a device-side failure of the PREVIOUS call is
-    // seen at this call's sync
-    JSB_CUDA_OK(cudaMemsetAsync(c.small.p, 0, 64, s));
+    // fingerprint / totals / counters (bytes 0..64) start at zero: the depth sort of the previous
+    // binning cleared them behind its last reader (resident_sort.cu), else one memset does; the
+    // error words live behind the strip counts and are sticky, so that a device-side failure of
+    // the PREVIOUS call is seen at this call's sync
+    if (!c.small_clean) JSB_CUDA_OK(cudaMemsetAsync(c.small.p, 0, 64, s));
+    c.small_clean = false;
     const BinParams bp = bin_params(d);
     const unsigned nstrips = ceil_div(bp.band_y1 - bp.band_y0, bp.strip_rows);
     if (nstrips > 1) JSB_CUDA_OK(cudaMemsetAsync((char *)c.small.p + 64, 0, 8 * nstrips, s));
@@ -313,7 +319,7 @@ static int bin_finish_enqueue(Ctx &c, const Descriptor &d, bool write) {
     cudaStream_t s = c.stream;
     if (n == 0) return 0;
     // (one copy of the whole block: the error words sit behind the strip counts)
-    JSB_CUDA_OK(cudaMemcpyAsync(c.h_pinned, c.small.p, SMALL_BYTES, cudaMemcpyDeviceToHost, s));
+    JSB_CUDA_OK(cudaMemcpyAsync(c.h_pinned, c.small.p, SMALL_COPY_BYTES, cudaMemcpyDeviceToHost, s));
     JSB_CUDA_OK(cudaEventRecord(c.ev_ready, s));
     if (write) {
         StageScope ss(&c, ST_DEPTH_SORT);
@@ -324,9 +330,13 @@ static int bin_finish_enqueue(Ctx &c, const Descriptor &d, bool write) {
             rc = resident_depth_sort(s, (const unsigned *)c.dkeys_a.p, (unsigned *)c.dkeys_a.p,
                                      (unsigned *)c.ids_a.p, (unsigned *)c.dkeys_b.p,
                                      (unsigned *)c.ids_b.p, (unsigned *)c.order.p, n, mm,
-                                     c.sort_n_scratch.p, (int *)c.small.p + SM_ERR_WORD);
+                                     c.sort_n_scratch.p, (int *)c.small.p + SM_ERR_WORD,
+                                     (unsigned *)c.small.p + SM_SORT_BAR, (unsigned *)c.small.p);
             if (rc > 0) return 1;
-            if (rc == 0) c.order_ptr = (const unsigned *)c.order.p;
+            if (rc == 0) {
+                c.order_ptr = (const unsigned *)c.order.p;
+                c.small_clean = true;  // (the control block is not touched again in this binning)
+            }
         }
         if (rc < 0) {  // option "sort1k" 0, or no cooperative launch: four onesweep passes
             bool in_b = false;
@@ -380,7 +390,9 @@ static int bin_prepare_wait(Ctx &c, const Descriptor &d, unsigned long long *I,
     if (e[0] | e[1] | e[2] | e[3]) {
         set_error("device-side look-back spin limit tripped in an earlier call (flags %d %d %d %d)",
                   e[0], e[1], e[2], e[3]);
-        JSB_CUDA_OK(cudaMemsetAsync((char *)c.small.p + 4 * SM_ERR_WORD, 0, 16, c.stream));
+        // (a tripped spin limit may have left the sort's barrier words behind as well)
+        JSB_CUDA_OK(cudaMemsetAsync((char *)c.small.p + 4 * SM_ERR_WORD, 0, 32, c.stream));
+        c.small_clean = false;
         return 1;
     }
     return 0;

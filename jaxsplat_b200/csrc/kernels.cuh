@@ -178,12 +178,15 @@ int radix_sort_pairs(cudaStream_t stream, KeyT *keys_a, KeyT *keys_b, unsigned *
 // order[i] = id of the i-th Gaussian in (depth key, index) order; keys_in[g] = depth key of
 // Gaussian g (0xFFFFFFFF = hits no tile: placed anywhere at or after the largest real key);
 // mm = {max(~key), max(key)} over the real keys.  kA/vA/kB/vB: n-word ping-pong buffers (kA may be
-// keys_in).  Returns 0 on success, 1 on error, -1 if the device cannot launch cooperatively (the
-// caller then uses radix_sort_pairs).
+// keys_in).  barrier_words: two words that are zero at the launch (the kernel leaves them zero:
+// allocate once, clear once); clear_words: 16 words (may hold mm) that the last CTA out sets to
+// zero once every CTA has read mm, or null.  Returns 0 on success, 1 on error, -1 if the device
+// cannot launch cooperatively (the caller then uses radix_sort_pairs; nothing was cleared).
 size_t resident_sort_scratch_bytes(unsigned n);
 int resident_depth_sort(cudaStream_t stream, const unsigned *keys_in, unsigned *kA, unsigned *vA,
                         unsigned *kB, unsigned *vB, unsigned *order, unsigned n,
-                        const unsigned *mm, void *scratch, int *err);
+                        const unsigned *mm, void *scratch, int *err, unsigned *barrier_words,
+                        unsigned *clear_words);
 
 // ---- rasterisers (raster_fwd.cu / raster_bwd.cu) --------------------------------------------
 struct RasterParams {

@@ -221,6 +221,7 @@ project_fwd_kernel(const ProjectFwdParams p, const float *__restrict__ means3d,
     o.depth = 0.f; o.radius = 0; o.conic = make_float3(0.f, 0.f, 0.f); o.comp = 0.f; o.tiles = 0;
     const bool live = idx < n;
     float cr = 0.f, cg = 0.f, cb = 0.f, opac = 0.f;
+    chain_wait();
     if (live) {
         // every load of the thread is in flight before the first use
         const float mx = __ldg(means3d + idx * 3), my = __ldg(means3d + idx * 3 + 1),
@@ -695,12 +696,12 @@ int launch_project_fwd(cudaStream_t stream, const ProjectFwdParams &p, const flo
     if (p.num_points == 0) return 0;
     const unsigned blocks = ceil_div(p.num_points, PT);
     if (fused)
-        project_fwd_kernel<true><<<blocks, PT, 0, stream>>>(
+        launch_chained(project_fwd_kernel<true>, blocks, PT, 0, stream,
             p, means3d, scales, reinterpret_cast<const float4 *>(quats), viewmat, cov3ds,
             reinterpret_cast<float2 *>(xys), depths, radii, conics, compensation, num_tiles_hit,
             cum_tiles_hit, block_totals, *fused);
     else
-        project_fwd_kernel<false><<<blocks, PT, 0, stream>>>(
+        launch_chained(project_fwd_kernel<false>, blocks, PT, 0, stream,
             p, means3d, scales, reinterpret_cast<const float4 *>(quats), viewmat, cov3ds,
             reinterpret_cast<float2 *>(xys), depths, radii, conics, compensation, num_tiles_hit,
             cum_tiles_hit, block_totals, FusedPrep{});

@@ -59,7 +59,9 @@ struct DsParams {
     unsigned *hist;           // [grid][DS_BINS] digit counts of every CTA
     unsigned *pre;            // [grid][DS_BINS] their exclusive prefix over the CTAs
     unsigned *tot;            // [DS_BINS] digit totals
-    unsigned *bar;            // grid barrier counter, zero at launch
+    unsigned *bar;            // [0] grid barrier counter, [1] CTAs that are through: both zero at
+                              // launch, and zero again when the last CTA leaves (no memset)
+    unsigned *ctrl;           // 16 control words the last CTA out clears for the caller, or null
     int *err;
     unsigned tile_items;      // multiple of DS_THREADS, <= DS_TILE
     unsigned subtiles;        // tiles per CTA
@@ -113,6 +115,20 @@ __global__ void __launch_bounds__(DS_THREADS, 1) resident_depth_sort_kernel(cons
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const unsigned G = gridDim.x, c = blockIdx.x;
 
+    // the last CTA out (every CTA has read `mm` and left every barrier by then) puts the barrier
+    // words back to zero and clears the caller's control words for its next binning
+    auto leave = [&]() {
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            if (atomicAdd(P.bar + 1, 1u) == G - 1u) {
+                P.bar[0] = 0u;
+                P.bar[1] = 0u;
+                if (P.ctrl)
+                    for (int i = 0; i < 16; ++i) P.ctrl[i] = 0u;
+            }
+        }
+    };
     const unsigned inv_min = __ldg(P.mm), kmax = __ldg(P.mm + 1);
     const unsigned kmin = ~inv_min;
     const unsigned span = (kmax >= kmin) ? kmax - kmin : 0u;
@@ -122,6 +138,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) resident_depth_sort_kernel(cons
     if (passes == 0) {  // one depth (or no real key at all): index order is the stable order
         const unsigned b0 = c * cta_items;
         for (unsigned i = tid; i < cta_items && b0 + i < P.n; i += DS_THREADS) P.order[b0 + i] = b0 + i;
+        leave();
         return;
     }
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -326,6 +343,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) resident_depth_sort_kernel(cons
             grid_barrier(P.bar, arrivals, P.err);
         }
     }
+    leave();
 }
 
 struct DeviceFacts {
@@ -338,13 +356,14 @@ DeviceFacts g_facts[64];
 
 size_t resident_sort_scratch_bytes(unsigned n) {
     (void)n;
-    return (size_t)(2 * DS_MAXG + 2) * DS_BINS * sizeof(unsigned);  // hist + pre rows, totals, barrier
+    return (size_t)(2 * DS_MAXG + 2) * DS_BINS * sizeof(unsigned);  // hist + pre rows, totals
 }
 
 // returns 0 on success, 1 on error, -1 if this device cannot run it (caller falls back)
 int resident_depth_sort(cudaStream_t stream, const unsigned *keys_in, unsigned *kA, unsigned *vA,
                         unsigned *kB, unsigned *vB, unsigned *order, unsigned n,
-                        const unsigned *mm, void *scratch, int *err) {
+                        const unsigned *mm, void *scratch, int *err, unsigned *barrier_words,
+                        unsigned *clear_words) {
     if (n == 0) return 0;
     int dev = 0;
     JSB_CUDA_OK(cudaGetDevice(&dev));
@@ -370,13 +389,13 @@ int resident_depth_sort(cudaStream_t stream, const unsigned *keys_in, unsigned *
     P.hist = reinterpret_cast<unsigned *>(scratch);
     P.pre = P.hist + (size_t)DS_MAXG * DS_BINS;
     P.tot = P.pre + (size_t)DS_MAXG * DS_BINS;
-    P.bar = P.tot + DS_BINS;
+    P.bar = barrier_words;
+    P.ctrl = clear_words;
     const unsigned G0 = (unsigned)F.max_ctas;
     P.subtiles = std::max(1u, ceil_div(n, G0 * (unsigned)DS_TILE));
     const unsigned per_tile = ceil_div(n, G0 * P.subtiles);
     P.tile_items = std::min((unsigned)DS_TILE, std::max((unsigned)DS_THREADS, ceil_div(per_tile, (unsigned)DS_THREADS) * (unsigned)DS_THREADS));
     const unsigned grid = ceil_div(n, P.tile_items * P.subtiles);
-    JSB_CUDA_OK(cudaMemsetAsync(P.bar, 0, 64, stream));
     void *args[] = {(void *)&P};
     JSB_CUDA_OK(cudaLaunchCooperativeKernel((const void *)resident_depth_sort_kernel, dim3(grid),
                                             dim3(DS_THREADS), args, sizeof(DsSmem), stream));
