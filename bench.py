@@ -291,6 +291,8 @@ def main():
             _lib.set_option("bwdhits", 0)
         if os.environ.get("JSB_SUPERCOLS"):  # tiles per super-column of the fused render's lists (log2; 0 = exact lists)
             _lib.set_option("supercols", int(os.environ["JSB_SUPERCOLS"]))
+        if os.environ.get("JSB_PRECLEAR") == "0":  # the backward's accumulators cleared by its own memset
+            jsb.set_preclear(False)
         if os.environ.get("JSB_PDL"):  # programmatic dependent launch between the step's kernels
             _lib.set_option("pdl", int(os.environ["JSB_PDL"]))
         if os.environ.get("JSB_SORT1K") == "0":  # four onesweep passes instead of the resident sort

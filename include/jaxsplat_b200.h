@@ -109,6 +109,14 @@ JSB200_API int jsb200_render_fwd(jsb200_stream_t stream, void **buffers, const c
                                  size_t opaque_len, unsigned long long *token_out);
 JSB200_API int jsb200_render_bwd(jsb200_stream_t stream, void **buffers, const char *opaque,
                                  size_t opaque_len, unsigned long long token);
+/* jsb200_render_bwd for a caller that has already set the four atomically accumulated outputs
+ * (v_colors, v_opacity, v_xy, v_conic: 36 bytes per Gaussian) to zero, ordered before this call on
+ * `stream` -- e.g. on a side stream while the forward ran, joined with an event (the torch host
+ * layer does: jaxsplat_b200/_render.py).  The library then issues no memset in front of the
+ * rasteriser backward (36 MB at 1M Gaussians); everything else as jsb200_render_bwd. */
+JSB200_API int jsb200_render_bwd_precleared(jsb200_stream_t stream, void **buffers,
+                                            const char *opaque, size_t opaque_len,
+                                            unsigned long long token);
 
 /* Batched cameras (an API addition: the reference renders one camera per call,
  * jaxsplat/__init__.py:6-70, and a multi-view step loops over it in Python).  num_views cameras of

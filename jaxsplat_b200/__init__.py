@@ -11,7 +11,7 @@ fallback path.
 from . import _ops
 from ._project import project
 from ._rasterize import rasterize
-from ._render import render_fused, render_views, set_gradient_sink
+from ._render import render_fused, render_views, set_gradient_sink, set_preclear
 
 _FUSED = True
 
@@ -47,4 +47,4 @@ def render(means3d, scales, quats, colors, opacities, *, viewmat, background, im
 
 
 __all__ = ["render", "render_views", "project", "rasterize", "set_fused_render",
-           "set_gradient_sink"]
+           "set_gradient_sink", "set_preclear"]

@@ -25,6 +25,7 @@ EXPORTS = (
     "jsb200_rasterize_bwd_status",
     "jsb200_render_fwd",
     "jsb200_render_bwd",
+    "jsb200_render_bwd_precleared",
     "jsb200_render_views_fwd",
     "jsb200_render_views_bwd",
     "jsb200_make_descriptor",
@@ -86,6 +87,8 @@ def lib() -> ctypes.CDLL:
     L.jsb200_render_fwd.restype = i
     L.jsb200_render_bwd.argtypes = [vp, ctypes.POINTER(vp), cp, sz, ctypes.c_ulonglong]
     L.jsb200_render_bwd.restype = i
+    L.jsb200_render_bwd_precleared.argtypes = [vp, ctypes.POINTER(vp), cp, sz, ctypes.c_ulonglong]
+    L.jsb200_render_bwd_precleared.restype = i
     L.jsb200_make_descriptor.argtypes = [u, u, u, f, f, f, f, f, f, u, ctypes.c_char_p]
     L.jsb200_make_descriptor.restype = i
     L.jsb200_set_descriptor_band.argtypes = [ctypes.c_char_p, u, u]

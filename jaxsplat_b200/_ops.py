@@ -213,14 +213,17 @@ def render_fwd(mean3ds, scales, quats, viewmat, colors, opacities, background, *
 def render_bwd(mean3ds, scales, quats, viewmat, colors, opacities, background, cov3ds, xys, depths,
                radii, conics, compensation, final_Ts, final_idx, v_img, v_img_alpha,
                *, token, num_points, img_shape, f, c, glob_scale, clip_thresh, block_width,
-               band=None, grad_out=None):
+               band=None, grad_out=None, cleared_acc=None):
     """rasterize_bwd + project_bwd in one native call (jsb200_render_bwd).  Returns
     (v_mean3d, v_scale, v_quat, v_colors, v_opacity, v_xy, v_conic, None, None): the two
     intermediate cotangents v_cov2d / v_cov3d of the projection VJP are not materialised (the C
     entry point writes them when given buffers).
     grad_out: optional caller-owned buffers for the first five results (see
     ``jaxsplat_b200.set_gradient_sink``); a sixth tensor of 5*N floats placed right behind
-    v_opacity lets the library clear its four accumulators with one memset."""
+    v_opacity lets the library clear its four accumulators with one memset.
+    cleared_acc: a float32 tensor of 9*N zeros (ordered before this call on the current stream)
+    for the four atomically accumulated results; the library then issues no memset
+    (jsb200_render_bwd_precleared)."""
     import ctypes
 
     n, dev = num_points, mean3ds.device
@@ -248,7 +251,8 @@ def render_bwd(mean3ds, scales, quats, viewmat, colors, opacities, background, c
                                                 None, None]
     else:
         # the four atomically accumulated gradients back to back: the library clears them in one go
-        acc = _out((n, 9), torch.float32, dev).reshape(-1)
+        acc = (_out((n, 9), torch.float32, dev).reshape(-1) if cleared_acc is None
+               else _f32(cleared_acc, (9 * n,), "cleared_acc"))
         outs = [_out((n, 3), torch.float32, dev), _out((n, 3), torch.float32, dev),
                 _out((n, 4), torch.float32, dev), acc[:3 * n].view(n, 3),
                 acc[3 * n:4 * n].view(n, 1), acc[4 * n:6 * n].view(n, 2),
@@ -257,7 +261,9 @@ def render_bwd(mean3ds, scales, quats, viewmat, colors, opacities, background, c
                              block_width)
     if band is not None:
         d = _ffi.with_band(d, band[0], band[1])
-    _call_native("jsb200_render_bwd", ins + outs, d, ctypes.c_ulonglong(int(token)))
+    precleared = cleared_acc is not None and grad_out is None
+    _call_native("jsb200_render_bwd_precleared" if precleared else "jsb200_render_bwd", ins + outs,
+                 d, ctypes.c_ulonglong(int(token)))
     return tuple(outs)
 
 

@@ -32,10 +32,43 @@ def set_gradient_sink(buffers) -> None:
     _GRAD_SINK = None if buffers is None else list(buffers)
 
 
+# The rasteriser backward accumulates four of its results with atomics (36 bytes per Gaussian) and
+# needs them zero.  Cleared in front of it that is a 36 MB memset on the critical path at 1M
+# Gaussians; cleared on a side stream while the forward's list build and rasteriser run (both
+# issue-bound, the memory system idle) it costs nothing.  The buffer is allocated BEFORE the forward
+# is enqueued and the side stream waits for that point of the main stream, so whatever owned the
+# memory before is done with it; the backward waits for the side stream's event.
+_PRECLEAR = True
+_PRECLEAR_MIN_BYTES = 4 << 20
+_side_streams = {}
+
+
+def set_preclear(enabled: bool) -> None:
+    """Clear the backward's accumulators on a side stream during the forward (default) or leave it
+    to the backward's own memset."""
+    global _PRECLEAR
+    _PRECLEAR = bool(enabled)
+
+
+def _side_stream(dev):
+    s = _side_streams.get(dev)
+    if s is None:
+        s = _side_streams[dev] = torch.cuda.Stream(device=dev)
+    return s
+
+
 class _Render(torch.autograd.Function):
     @staticmethod
     def forward(ctx, desc: ProjectDescriptor, band, means3d, scales, quats, colors, opacities,
                 viewmat, background):
+        n = means3d.shape[0]
+        ctx.acc = ctx.acc_ready = None
+        preclear = (_PRECLEAR and _GRAD_SINK is None and any(ctx.needs_input_grad[2:7])
+                    and n * 36 >= _PRECLEAR_MIN_BYTES)
+        if preclear:
+            main = torch.cuda.current_stream(means3d.device)
+            acc = torch.empty(9 * n, dtype=torch.float32, device=means3d.device)
+            fork = main.record_event()
         (cov3ds, xys, depths, radii, conics, compensation, final_Ts, final_idx,
          img), token = _ops.render_fwd(means3d, scales, quats, viewmat, colors, opacities,
                                        background, band=band, lean=True, **desc.kwargs())
@@ -45,11 +78,25 @@ class _Render(torch.autograd.Function):
         ctx.save_for_backward(means3d, scales, quats, viewmat, colors, opacities, background,
                               cov3ds, xys, depths, radii, conics, compensation, final_Ts,
                               final_idx)
+        if preclear:
+            # (enqueued now, i.e. while the forward's later kernels run; ordered after `fork`)
+            side = _side_stream(means3d.device)
+            side.wait_event(fork)
+            with torch.cuda.stream(side):
+                acc.zero_()
+            acc.record_stream(side)
+            ctx.acc, ctx.acc_ready = acc, side.record_event()
         return img
 
     @staticmethod
     def backward(ctx, v_img):
         saved = ctx.saved_tensors
+        # (one use: a second backward through the same graph finds the accumulators dirty)
+        acc, ready, ctx.acc, ctx.acc_ready = ctx.acc, ctx.acc_ready, None, None
+        if acc is not None and _GRAD_SINK is None:
+            torch.cuda.current_stream(acc.device).wait_event(ready)
+        else:
+            acc = None
         if _GRAD_SINK is not None:
             # autograd ACCUMULATES a returned gradient into an existing .grad; if that .grad already
             # is the sink buffer, `grad += out` with out aliasing grad would silently double it
@@ -62,7 +109,7 @@ class _Render(torch.autograd.Function):
         # render() exposes no alpha image: its cotangent is identically zero (None = not read)
         (v_mean3d, v_scale, v_quat, v_colors, v_opacity, *_rest) = _ops.render_bwd(
             *saved, v_img.contiguous(), None, token=ctx.token, band=ctx.band,
-            grad_out=_GRAD_SINK, **ctx.desc.kwargs())
+            grad_out=_GRAD_SINK, cleared_acc=acc, **ctx.desc.kwargs())
         return None, None, v_mean3d, v_scale, v_quat, v_colors, v_opacity, None, None
 
 

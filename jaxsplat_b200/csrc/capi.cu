@@ -842,7 +842,9 @@ static int render_fwd_impl(cudaStream_t stream, void **buf, const Descriptor &d,
 static int render_bwd_impl(cudaStream_t stream, void **buf, const Descriptor &d,
                            unsigned long long token, unsigned slot = 0,
                            bool keep_appearance = false, bool raster_only = false,
-                           bool *moments_seen = nullptr) {
+                           bool *moments_seen = nullptr, bool precleared = false) {
+    // precleared: the caller zeroed v_colors / v_opacity / v_xy / v_conic itself, ordered before
+    // this call on `stream` (jsb200_render_bwd_precleared)
     // in : 0 means3d 1 scales 2 quats 3 viewmat 4 colors 5 opacities 6 background 7 cov3ds 8 xys
     //      9 depths 10 radii 11 conics 12 compensation 13 final_Ts 14 final_idx
     //      15 v_out_img 16 v_out_img_alpha
@@ -862,8 +864,8 @@ static int render_bwd_impl(cudaStream_t stream, void **buf, const Descriptor &d,
     // the four accumulators are cleared with one memset when the caller laid them out back to
     // back (the torch host layer does), else one by one
     char *g0 = (char *)buf[20];
-    if (raster_only) {
-        // (the caller cleared the per-view moment arrays in one memset)
+    if (raster_only || precleared) {
+        // (raster_only: the caller cleared the per-view moment arrays in one memset)
     } else if (keep_appearance) {
         if ((char *)buf[23] == (char *)buf[22] + n * 8) {
             JSB_CUDA_OK(cudaMemsetAsync(buf[22], 0, n * 20, stream));
@@ -1179,6 +1181,23 @@ int jsb200_render_bwd(jsb200_stream_t stream, void **buffers, const char *opaque
         memcpy(&d, dp, sizeof d);
         jsb::normalise_descriptor(d);
         return jsb::render_bwd_impl((cudaStream_t)stream, buffers, d, token);
+    } catch (...) {
+        jsb::set_error("render_bwd: exception");
+        return 1;
+    }
+}
+
+int jsb200_render_bwd_precleared(jsb200_stream_t stream, void **buffers, const char *opaque,
+                                 size_t len, unsigned long long token) {
+    try {
+        const jsb::Descriptor *dp = jsb::unpack(opaque, len);
+        if (!dp) return 1;
+        if (!buffers) { jsb::set_error("render_bwd: null buffer list"); return 1; }
+        jsb::Descriptor d;
+        memcpy(&d, dp, sizeof d);
+        jsb::normalise_descriptor(d);
+        return jsb::render_bwd_impl((cudaStream_t)stream, buffers, d, token, 0, false, false, nullptr,
+                                    /*precleared=*/true);
     } catch (...) {
         jsb::set_error("render_bwd: exception");
         return 1;

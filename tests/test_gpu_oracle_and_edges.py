@@ -587,6 +587,62 @@ def test_programmatic_dependent_launch_changes_nothing(case):
         _lib.set_option("pdl", int(os.environ.get("JSB_PDL", "1")))
 
 
+@pytest.mark.parametrize("case", ["C2_30k", "wide_boxes", "tiny"])
+def test_accumulators_cleared_on_a_side_stream_during_the_forward(case, monkeypatch):
+    """render()'s backward accumulates v_colors / v_opacity / v_xy / v_conic with atomics; the host
+    layer clears them on a side stream while the forward runs and calls
+    jsb200_render_bwd_precleared (no memset in front of the rasteriser backward).  Same gradients
+    as with the library's own memset (atomic-order noise), also for several steps in flight, a
+    second backward through the same graph (the accumulators are dirty then: ordinary path) and a
+    forward whose backward never runs."""
+    import jaxsplat_b200 as jsb
+    from jaxsplat_b200 import _render
+    if case == "C2_30k":
+        s = synthetic.make_config("C2", num_points=30000)
+    elif case == "wide_boxes":
+        s = synthetic.benchmark_scene(20000, (272, 400), scale_max=1.5, seed=9)
+    else:
+        s = synthetic.benchmark_scene(60, (40, 40), scale_max=0.3, seed=3)
+    monkeypatch.setattr(_render, "_PRECLEAR_MIN_BYTES", 0)
+    sc = s.to(G.DEV)
+    H, W = s.img_shape
+    target = torch.rand((H, W, 3), generator=torch.Generator().manual_seed(9)).to(G.DEV)
+
+    def run(steps=3, twice=False):
+        out = []
+        for k in range(steps):  # (no sync inside the loop)
+            params = [p.clone().requires_grad_(True) for p in sc.params()]
+            img = jsb.render(*params, **sc.render_kwargs())
+            loss = ((img - target) ** 2).sum() / (H * W * 3)
+            if twice:
+                loss.backward(retain_graph=True)
+                for p in params:
+                    p.grad = None
+            loss.backward()
+            out.append([p.grad for p in params])
+            # a forward that is never differentiated, and garbage written over freed memory
+            dead = jsb.render(*[p.clone().requires_grad_(True) for p in sc.params()], **sc.render_kwargs())
+            del dead
+            torch.full((9 * params[0].shape[0],), float("nan"), device=G.DEV)
+        torch.cuda.synchronize()
+        return [[G.npy(g) for g in gs] for gs in out]
+
+    try:
+        jsb.set_preclear(False)
+        ref = run()
+        ref2 = run()
+        jsb.set_preclear(True)
+        for twice in (False, True):
+            for gs in run(twice=twice):
+                for a, b, b2 in zip(gs, ref[0], ref2[0]):
+                    assert np.isfinite(a).all()
+                    nz = float(np.abs(b.astype(np.float64) - b2.astype(np.float64)).max())
+                    ok, err, scale = grad_close(a, b, rel=2e-5)
+                    assert ok or err <= 16.0 * nz, (twice, err, scale, nz)
+    finally:
+        jsb.set_preclear(True)
+
+
 @pytest.mark.parametrize("case", ["C2_30k", "ragged", "long_lists", "adversarial", "tiny"])
 def test_block_size_8_tuned_kernels_equal_the_generic_ones(case):
     """block_size 8 (reference lib/ffi.cu:29-36 runs one kernel for any block width): a tile is one
