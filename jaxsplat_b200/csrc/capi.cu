@@ -663,13 +663,15 @@ static int project_fwd_impl(cudaStream_t stream, void **buf, const Descriptor &d
 // moment_opacity != null (fused render): v_xy / v_conic / moment_opacity hold the rasteriser's raw
 // moments, finished into gradients by the projection backward (project.cu: FINISH_MOMENTS)
 static int project_bwd_impl2(cudaStream_t stream, void **buf, const Descriptor &d,
-                             const float *opacities, float *moment_opacity) {
+                             const float *opacities, float *moment_opacity,
+                             bool residuals_ready = false) {
     if (d.num_points == 0) return 0;
     Ctx *c = get_ctx(stream);
     if (!c) return 1;
     std::lock_guard<std::mutex> lk(c->mu);
     StageScope ss(c, ST_PROJECT_BWD);
     ProjectBwdParams p{d.num_points, d.glob_scale, d.fx, d.fy};
+    p.residuals_ready = residuals_ready;
     // in: 0 mean3ds 1 scales 2 quats 3 viewmat 4 cov3ds 5 xys 6 radii 7 conics 8 compensation
     //     9 v_compensation 10 v_xy 11 v_depth 12 v_conic ; out: 13 v_mean3d 14 v_scale 15 v_quat
     //     16 v_cov2d 17 v_cov3d
@@ -940,8 +942,11 @@ static int render_bwd_impl(cudaStream_t stream, void **buf, const Descriptor &d,
     // project_bwd with zero cotangents for depth and compensation (render uses neither)
     void *pbuf[18] = {buf[0], buf[1], buf[2], buf[3], buf[7], buf[8], buf[10], buf[11], buf[12],
                       nullptr, buf[22], nullptr, buf[23], buf[17], buf[18], buf[19], buf[24], buf[25]};
+    // (the rasteriser backward of this call sits right in front of it on the stream and writes none
+    // of the forward's residuals: project.cu loads them ahead of its wait on that kernel)
     return project_bwd_impl2(stream, pbuf, d, moments_flag ? (const float *)buf[5] : nullptr,
-                             moments_flag ? (float *)buf[21] : nullptr);
+                             moments_flag ? (float *)buf[21] : nullptr,
+                             /*residuals_ready=*/!empty_flag);
 }
 
 

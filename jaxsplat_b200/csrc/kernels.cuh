@@ -20,6 +20,10 @@ struct ProjectBwdParams {
     unsigned num_points;
     float glob_scale;
     float fx, fy;
+    // the kernel right before this one on the stream is the library's own and everything but the
+    // cotangents (parameters, radii, conics, cov3ds, viewmat, opacities) was complete before THAT
+    // kernel started: those are loaded ahead of the in-kernel wait on the predecessor
+    bool residuals_ready = false;
 };
 
 struct SplatRecord;

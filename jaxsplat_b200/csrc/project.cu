@@ -377,13 +377,34 @@ project_bwd_kernel(const ProjectBwdParams p, const float *__restrict__ means3d,
     float o_cov2d[3] = {0.f, 0.f, 0.f}, o_cov3d[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     float o_quat[4] = {0.f, 0.f, 0.f, 0.f};
     const bool live = idx < n;
-    chain_wait();
-    if (live && __ldg(radii + idx) > 0) {
-        const float mx = __ldg(means3d + idx * 3), my = __ldg(means3d + idx * 3 + 1),
-                    mz = __ldg(means3d + idx * 3 + 2);
-        const float sc0 = __ldg(scales + idx * 3), sc1 = __ldg(scales + idx * 3 + 1),
-                    sc2 = __ldg(scales + idx * 3 + 2);
-        const float4 q = __ldg(quats + idx);
+    // p.residuals_ready (the fused render's backward, right behind its own rasteriser backward):
+    // everything the FORWARD left -- parameters, radii, conics, the camera -- was complete before
+    // the predecessor started, so a CTA that became resident while the predecessor drains loads it
+    // before it waits; only the cotangents / moments are read behind the wait.
+    if (!p.residuals_ready) chain_wait();
+    const bool vis = live && __ldg(radii + idx) > 0;
+    float mx = 0.f, my = 0.f, mz = 0.f, sc0 = 0.f, sc1 = 0.f, sc2 = 0.f;
+    float4 q = make_float4(1.f, 0.f, 0.f, 0.f);
+    float cx = 0.f, cy = 0.f, cz = 0.f, opac = 1.f;
+    float k0 = 0.f, k1 = 0.f, k2 = 0.f, k3 = 0.f, k4 = 0.f, k5 = 0.f;
+    if (vis) {
+        mx = __ldg(means3d + idx * 3); my = __ldg(means3d + idx * 3 + 1); mz = __ldg(means3d + idx * 3 + 2);
+        sc0 = __ldg(scales + idx * 3); sc1 = __ldg(scales + idx * 3 + 1); sc2 = __ldg(scales + idx * 3 + 2);
+        q = __ldg(quats + idx);
+        cx = __ldg(conics + idx * 3); cy = __ldg(conics + idx * 3 + 1); cz = __ldg(conics + idx * 3 + 2);
+        if (FINISH_MOMENTS) opac = __ldg(opacities + idx);
+        if (!RECOMPUTE) {
+            k0 = __ldg(cov3ds + idx * 6); k1 = __ldg(cov3ds + idx * 6 + 1);
+            k2 = __ldg(cov3ds + idx * 6 + 2); k3 = __ldg(cov3ds + idx * 6 + 3);
+            k4 = __ldg(cov3ds + idx * 6 + 4); k5 = __ldg(cov3ds + idx * 6 + 5);
+        }
+    }
+    const float *v = viewmat;
+    const float w00 = __ldg(v + 0), w01 = __ldg(v + 1), w02 = __ldg(v + 2), w03 = __ldg(v + 3);
+    const float w10 = __ldg(v + 4), w11 = __ldg(v + 5), w12 = __ldg(v + 6), w13 = __ldg(v + 7);
+    const float w20 = __ldg(v + 8), w21 = __ldg(v + 9), w22 = __ldg(v + 10), w23 = __ldg(v + 11);
+    if (p.residuals_ready) chain_wait();
+    if (vis) {
         // R(q), q = (w, x, y, z), and the scaled axes: also what the scale / quaternion VJP needs
         const float w = q.x, x = q.y, y = q.z, z = q.w;
         const float R00 = 1.f - 2.f * (y * y + z * z), R01 = 2.f * (x * y - w * z), R02 = 2.f * (x * z + w * y);
@@ -391,7 +412,6 @@ project_bwd_kernel(const ProjectBwdParams p, const float *__restrict__ means3d,
         const float R20 = 2.f * (x * z - w * y), R21 = 2.f * (y * z + w * x), R22 = 1.f - 2.f * (x * x + y * y);
         const float gs = p.glob_scale;
         const float s0 = gs * sc0, s1 = gs * sc1, s2 = gs * sc2;
-        float k0, k1, k2, k3, k4, k5;
         if (RECOMPUTE) {  // V = R S S R^T
             const float e0 = s0 * s0, e1 = s1 * s1, e2 = s2 * s2;
             k0 = e0 * R00 * R00 + e1 * R01 * R01 + e2 * R02 * R02;
@@ -400,13 +420,7 @@ project_bwd_kernel(const ProjectBwdParams p, const float *__restrict__ means3d,
             k3 = e0 * R10 * R10 + e1 * R11 * R11 + e2 * R12 * R12;
             k4 = e0 * R10 * R20 + e1 * R11 * R21 + e2 * R12 * R22;
             k5 = e0 * R20 * R20 + e1 * R21 * R21 + e2 * R22 * R22;
-        } else {
-            k0 = __ldg(cov3ds + idx * 6); k1 = __ldg(cov3ds + idx * 6 + 1);
-            k2 = __ldg(cov3ds + idx * 6 + 2); k3 = __ldg(cov3ds + idx * 6 + 3);
-            k4 = __ldg(cov3ds + idx * 6 + 4); k5 = __ldg(cov3ds + idx * 6 + 5);
         }
-        const float cx = __ldg(conics + idx * 3), cy = __ldg(conics + idx * 3 + 1),
-                    cz = __ldg(conics + idx * 3 + 2);
         float gx = __ldg(v_conic + idx * 3), gy = 0.5f * __ldg(v_conic + idx * 3 + 1),
               gz = __ldg(v_conic + idx * 3 + 2);
         float2 vxy = __ldg(v_xy + idx);
@@ -417,13 +431,9 @@ project_bwd_kernel(const ProjectBwdParams p, const float *__restrict__ means3d,
             gy = -gy;      // v_conic.y / 2 = -Mxy / 2
             gz *= -0.5f;   // v_conic.z = -Myy / 2
             const float m0 = moment_opacity[idx];
-            moment_opacity[idx] = m0 != 0.f ? m0 / __ldg(opacities + idx) : 0.f;
+            moment_opacity[idx] = m0 != 0.f ? m0 / opac : 0.f;
         }
         const float vz = v_depth ? __ldg(v_depth + idx) : 0.f;  // null = zero cotangent (fused render)
-        const float *v = viewmat;
-        const float w00 = __ldg(v + 0), w01 = __ldg(v + 1), w02 = __ldg(v + 2), w03 = __ldg(v + 3);
-        const float w10 = __ldg(v + 4), w11 = __ldg(v + 5), w12 = __ldg(v + 6), w13 = __ldg(v + 7);
-        const float w20 = __ldg(v + 8), w21 = __ldg(v + 9), w22 = __ldg(v + 10), w23 = __ldg(v + 11);
         const float fx = p.fx, fy = p.fy;
         // p_view
         const float pvx = w00 * mx + w01 * my + w02 * mz + w03;

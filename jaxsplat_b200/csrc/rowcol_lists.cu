@@ -471,7 +471,9 @@ rc_row_scatter_kernel(const RcParams p, const unsigned *__restrict__ order,
     extern __shared__ __align__(16) unsigned char rc_smem[];
     const DistSmem<uint2, RC_STAGE1, RC_G1> S(rc_smem, p.rows);
     const unsigned lane = threadIdx.x, chunk = blockIdx.x;
-    chain_wait();
+    // (launched right behind rc_chunk_rows_kernel, which started after the depth order and the
+    // boxes were complete: a CTA that is resident while that kernel runs gathers them now and
+    // waits for the kernel only in front of the run starts)
     unsigned lo[RC_G1], len[RC_G1];
     uint2 pay[RC_G1];
     unsigned gid[RC_G1];
@@ -492,6 +494,7 @@ rc_row_scatter_kernel(const RcParams p, const unsigned *__restrict__ order,
         len[q] = ok ? h : 0u;
         pay[q] = make_uint2(gid[q], (b.x & 0xffffu) | (w << 16));
     }
+    chain_wait();
     // run starts of this chunk in every row: loads in flight before the dependent stores
     unsigned gb[8];  // rows <= 256
 #pragma unroll
@@ -525,11 +528,15 @@ rc_col_scatter_kernel(const RcParams p, const uint4 *__restrict__ chunk_info,
     extern __shared__ __align__(16) unsigned char rc_smem[];
     const DistSmem<Payload, STAGE, G> S(rc_smem, p.cols2);
     const unsigned lane = threadIdx.x, c = blockIdx.x;
-    chain_wait();
+    // (launched right behind rc_tile_scan_bins_kernel -- one CTA -- which started after the row
+    // entries, the chunk records and the run starts within the rows were complete: a CTA that is
+    // resident while it runs loads those now and waits only in front of the scanned bin starts)
     const uint4 info = __ldg(chunk_info + c);
     const unsigned r = info.x, ebeg = info.y, eend = info.z;
-    if (ebeg >= eend) return;
-    // run starts of this chunk: all loads in flight before the first dependent store
+    if (ebeg >= eend) {
+        chain_wait();
+        return;
+    }
     const unsigned *mrow = m + (size_t)c * p.cols2;
     const unsigned *tb = tile_base + (size_t)r * p.cols2;
     constexpr int NB = SUPER ? 4 : 16;  // bins <= 512 (exact) / <= 128 (super-columns)
@@ -537,7 +544,7 @@ rc_col_scatter_kernel(const RcParams p, const uint4 *__restrict__ chunk_info,
 #pragma unroll
     for (int i = 0; i < NB; ++i) {
         const unsigned x = lane + 32u * i;
-        gb[i] = x < p.cols2 ? __ldg(tb + x) + __ldg(mrow + x) : 0u;
+        gb[i] = x < p.cols2 ? __ldg(mrow + x) : 0u;
     }
     unsigned lo[G], len[G];
     Payload pay[G];
@@ -548,6 +555,13 @@ rc_col_scatter_kernel(const RcParams p, const uint4 *__restrict__ chunk_info,
         if (q * 32 + lane < p.k2 && e < eend) v = entries[e];
         if constexpr (SUPER) pay[q] = v; else pay[q] = v.x;
         entry_bins(v.y, p.sc_shift, lo[q], len[q]);
+    }
+    chain_wait();
+    // run starts of this chunk: all loads in flight before the first dependent store
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {
+        const unsigned x = lane + 32u * i;
+        if (x < p.cols2) gb[i] += __ldg(tb + x);
     }
 #pragma unroll
     for (int i = 0; i < NB; ++i) {
