@@ -473,7 +473,8 @@ rc_row_scatter_kernel(const RcParams p, const unsigned *__restrict__ order,
     const unsigned lane = threadIdx.x, chunk = blockIdx.x;
     // (launched right behind rc_chunk_rows_kernel, which started after the depth order and the
     // boxes were complete: a CTA that is resident while that kernel runs gathers them now and
-    // waits for the kernel only in front of the run starts)
+    // waits for the kernel only in front of the run starts.  ld.global.cg, not the read-only path:
+    // the compiler is free to sink invariant loads below the wait, and did)
     unsigned lo[RC_G1], len[RC_G1];
     uint2 pay[RC_G1];
     unsigned gid[RC_G1];
@@ -482,12 +483,12 @@ rc_row_scatter_kernel(const RcParams p, const unsigned *__restrict__ order,
     for (int q = 0; q < RC_G1; ++q) {  // independent loads of the depth order ...
         const unsigned item = q * 32 + lane, pos = chunk * p.k1 + item;
         have[q] = item < p.k1 && pos < p.n;
-        gid[q] = have[q] ? order[pos] : 0u;
+        gid[q] = have[q] ? __ldcg(order + pos) : 0u;
     }
 #pragma unroll
     for (int q = 0; q < RC_G1; ++q) {  // ... then independent gathers of the boxes
         uint2 b = make_uint2(0u, 0u);
-        if (have[q]) b = __ldg(box_by_id + gid[q]);
+        if (have[q]) b = __ldcg(box_by_id + gid[q]);
         const unsigned w = b.y & 0xffffu, h = b.y >> 16;
         const bool ok = w != 0u && h != 0u;
         lo[q] = ok ? (b.x >> 16) - p.band_y0 : 0u;
@@ -544,7 +545,7 @@ rc_col_scatter_kernel(const RcParams p, const uint4 *__restrict__ chunk_info,
 #pragma unroll
     for (int i = 0; i < NB; ++i) {
         const unsigned x = lane + 32u * i;
-        gb[i] = x < p.cols2 ? __ldg(mrow + x) : 0u;
+        gb[i] = x < p.cols2 ? __ldcg(mrow + x) : 0u;
     }
     unsigned lo[G], len[G];
     Payload pay[G];
@@ -552,7 +553,7 @@ rc_col_scatter_kernel(const RcParams p, const uint4 *__restrict__ chunk_info,
     for (int q = 0; q < G; ++q) {
         const unsigned e = ebeg + q * 32 + lane;
         uint2 v = make_uint2(0u, 0u);
-        if (q * 32 + lane < p.k2 && e < eend) v = entries[e];
+        if (q * 32 + lane < p.k2 && e < eend) v = __ldcg(entries + e);  // (see rc_row_scatter_kernel)
         if constexpr (SUPER) pay[q] = v; else pay[q] = v.x;
         entry_bins(v.y, p.sc_shift, lo[q], len[q]);
     }
