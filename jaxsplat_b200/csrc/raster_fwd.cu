@@ -536,23 +536,29 @@ int launch_raster_fwd(cudaStream_t stream, const RasterParams &p, const void *li
     if (p.sc_shift) {
         if (wrote_hits) *wrote_hits = hit_words != nullptr;
         if (g_disable_cull)
-            launch_chained(raster_fwd_warp_kernel<false, true, false>, tiles, RF2, 0, stream, p, list, tile_bins, records, background, final_Ts, final_idx, out_img, hit_words);
+            launch_chained(raster_fwd_warp_kernel<false, true, false>, tiles, RF2, 0, stream, p, list,
+                           tile_bins, records, background, final_Ts, final_idx, out_img, hit_words);
         else
-            launch_chained(raster_fwd_warp_kernel<true, true, false>, tiles, RF2, 0, stream, p, list, tile_bins, records, background, final_Ts, final_idx, out_img, hit_words);
+            launch_chained(raster_fwd_warp_kernel<true, true, false>, tiles, RF2, 0, stream, p, list,
+                           tile_bins, records, background, final_Ts, final_idx, out_img, hit_words);
     } else if (p.block_width == 16 && !g_fwd_batch) {
         if (wrote_hits) *wrote_hits = hit_words != nullptr;
         if (g_disable_cull)
-            launch_chained(raster_fwd_warp_kernel<false, false, false>, tiles, RF2, 0, stream, p, list, tile_bins, records, background, final_Ts, final_idx, out_img, hit_words);
+            launch_chained(raster_fwd_warp_kernel<false, false, false>, tiles, RF2, 0, stream, p, list,
+                           tile_bins, records, background, final_Ts, final_idx, out_img, hit_words);
         else
-            launch_chained(raster_fwd_warp_kernel<true, false, false>, tiles, RF2, 0, stream, p, list, tile_bins, records, background, final_Ts, final_idx, out_img, hit_words);
+            launch_chained(raster_fwd_warp_kernel<true, false, false>, tiles, RF2, 0, stream, p, list,
+                           tile_bins, records, background, final_Ts, final_idx, out_img, hit_words);
     } else if (p.block_width == 8 && !g_fwd_batch) {
         // 8x8 tiles: one warp per tile, four tiles per CTA
         if (wrote_hits) *wrote_hits = hit_words != nullptr;
         const unsigned ctas = (tiles + RF2 / 32 - 1) / (RF2 / 32);
         if (g_disable_cull)
-            launch_chained(raster_fwd_warp_kernel<false, false, true>, ctas, RF2, 0, stream, p, list, tile_bins, records, background, final_Ts, final_idx, out_img, hit_words);
+            launch_chained(raster_fwd_warp_kernel<false, false, true>, ctas, RF2, 0, stream, p, list,
+                           tile_bins, records, background, final_Ts, final_idx, out_img, hit_words);
         else
-            launch_chained(raster_fwd_warp_kernel<true, false, true>, ctas, RF2, 0, stream, p, list, tile_bins, records, background, final_Ts, final_idx, out_img, hit_words);
+            launch_chained(raster_fwd_warp_kernel<true, false, true>, ctas, RF2, 0, stream, p, list,
+                           tile_bins, records, background, final_Ts, final_idx, out_img, hit_words);
     } else if (p.block_width == 16) {
         if (wrote_hits) *wrote_hits = hit_words != nullptr;
         if (g_disable_cull)

@@ -652,31 +652,35 @@ int launch_rowcol_lists(cudaStream_t stream, const BinParams &bp, const unsigned
                                   : DistSmem<unsigned, RC_STAGE2, RC_G2>::bytes(p.cols2);
 
     if (phase == 0) {  // level 1: row lists
-        launch_chained(rc_row_count_kernel, ceil_div(p.n1, (unsigned)RC_RC_WARPS), 32 * RC_RC_WARPS, 0, stream, p, order, box_by_id, l1m);
+        launch_chained(rc_row_count_kernel, ceil_div(p.n1, (unsigned)RC_RC_WARPS), 32 * RC_RC_WARPS, 0,
+                       stream, p, order, box_by_id, l1m);
         JSB_CUDA_OK(cudaGetLastError());
         launch_chained(rc_row_scan_kernel, p.rows, 1024, 0, stream, p, l1m, row_tot);
         JSB_CUDA_OK(cudaGetLastError());
-        launch_chained(rc_chunk_rows_kernel, ceil_div(p.n2max, 256u), 256, 0, stream, p, row_tot, row_start,
-                                                                          chunk_base, chunk_info);
+        launch_chained(rc_chunk_rows_kernel, ceil_div(p.n2max, 256u), 256, 0, stream, p, row_tot,
+                       row_start, chunk_base, chunk_info);
         JSB_CUDA_OK(cudaGetLastError());
-        launch_chained(rc_row_scatter_kernel, p.n1, 32, smem1, stream, p, order, box_by_id, l1m, row_start, entries);
+        launch_chained(rc_row_scatter_kernel, p.n1, 32, smem1, stream, p, order, box_by_id, l1m,
+                       row_start, entries);
         JSB_CUDA_OK(cudaGetLastError());
         note_launch(4);
     } else if (phase == 1) {  // level 2 run starts and tile bins
-        launch_chained(rc_col_count_kernel, ceil_div(p.n2max, (unsigned)RC_CC_WARPS), 32 * RC_CC_WARPS, 0, stream, p, chunk_info, entries, m);
+        launch_chained(rc_col_count_kernel, ceil_div(p.n2max, (unsigned)RC_CC_WARPS), 32 * RC_CC_WARPS, 0,
+                       stream, p, chunk_info, entries, m);
         JSB_CUDA_OK(cudaGetLastError());
-        launch_chained(rc_col_scan_kernel, dim3(ceil_div(p.cols2, 32u), p.rows), 32 * RC_CS_WARPS, 0, stream, p, chunk_base, m, tile_cnt);
+        launch_chained(rc_col_scan_kernel, dim3(ceil_div(p.cols2, 32u), p.rows), 32 * RC_CS_WARPS, 0,
+                       stream, p, chunk_base, m, tile_cnt);
         JSB_CUDA_OK(cudaGetLastError());
         launch_chained(rc_tile_scan_bins_kernel, 1, 1024, 0, stream, p, tile_cnt, tile_bins);
         JSB_CUDA_OK(cudaGetLastError());
         note_launch(3);
     } else {  // level 2: the lists
         if (sc_shift)
-            launch_chained(rc_col_scatter_kernel<true>, p.n2max, 32, smem2, stream, p, chunk_info, entries, m, tile_cnt,
-                                                                        ids_sorted);
+            launch_chained(rc_col_scatter_kernel<true>, p.n2max, 32, smem2, stream, p, chunk_info,
+                           entries, m, tile_cnt, ids_sorted);
         else
-            launch_chained(rc_col_scatter_kernel<false>, p.n2max, 32, smem2, stream, p, chunk_info, entries, m, tile_cnt,
-                                                                         ids_sorted);
+            launch_chained(rc_col_scatter_kernel<false>, p.n2max, 32, smem2, stream, p, chunk_info,
+                           entries, m, tile_cnt, ids_sorted);
         JSB_CUDA_OK(cudaGetLastError());
         note_launch();
     }
