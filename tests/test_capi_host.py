@@ -80,6 +80,21 @@ def test_unknown_option_rejected():
         _lib.set_option("no_such_option", 1)
 
 
+def test_every_option_is_documented_in_the_header_and_accepted():
+    """the keys jsb200_set_option compares against == the keys include/jaxsplat_b200.h documents;
+    every one is accepted with its documented default (options only set host-side switches: no GPU)"""
+    src = open(os.path.join(ROOT, "jaxsplat_b200", "csrc", "capi.cu")).read()
+    body = src[src.index("int jsb200_set_option("):]
+    body = body[:body.index("\n}\n")]
+    keys = set(re.findall(r'strcmp\(key, "(\w+)"\)', body))
+    hdr = open(os.path.join(ROOT, "include", "jaxsplat_b200.h")).read()
+    doc = hdr[hdr.index("/* key:"):hdr.index("JSB200_API int jsb200_set_option")]
+    documented = dict(re.findall(r'"(\w+)" \((\d+) default', doc))
+    assert keys == set(documented), (sorted(keys), sorted(documented))
+    for key, default in documented.items():
+        _lib.set_option(key, int(default))
+
+
 def test_ops_validate_shapes_before_touching_the_gpu():
     n = 8
     z = torch.zeros
