@@ -117,6 +117,10 @@ JSB200_API int jsb200_render_bwd(jsb200_stream_t stream, void **buffers, const c
 JSB200_API int jsb200_render_bwd_precleared(jsb200_stream_t stream, void **buffers,
                                             const char *opaque, size_t opaque_len,
                                             unsigned long long token);
+/* Sets `bytes` bytes at `ptr` to zero on `stream` (cudaMemsetAsync; no kernel of a host framework):
+ * what a host layer issues on its side stream for jsb200_render_bwd_precleared.  The reference
+ * clears the same arrays with cudaMemsetAsync in front of its backward (lib/ops.cu:534-572). */
+JSB200_API int jsb200_clear_async(jsb200_stream_t stream, void *ptr, size_t bytes);
 
 /* Batched cameras (an API addition: the reference renders one camera per call,
  * jaxsplat/__init__.py:6-70, and a multi-view step loops over it in Python).  num_views cameras of

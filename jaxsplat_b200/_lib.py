@@ -26,6 +26,7 @@ EXPORTS = (
     "jsb200_render_fwd",
     "jsb200_render_bwd",
     "jsb200_render_bwd_precleared",
+    "jsb200_clear_async",
     "jsb200_render_views_fwd",
     "jsb200_render_views_bwd",
     "jsb200_make_descriptor",
@@ -89,6 +90,8 @@ def lib() -> ctypes.CDLL:
     L.jsb200_render_bwd.restype = i
     L.jsb200_render_bwd_precleared.argtypes = [vp, ctypes.POINTER(vp), cp, sz, ctypes.c_ulonglong]
     L.jsb200_render_bwd_precleared.restype = i
+    L.jsb200_clear_async.argtypes = [vp, vp, sz]
+    L.jsb200_clear_async.restype = i
     L.jsb200_make_descriptor.argtypes = [u, u, u, f, f, f, f, f, f, u, ctypes.c_char_p]
     L.jsb200_make_descriptor.restype = i
     L.jsb200_set_descriptor_band.argtypes = [ctypes.c_char_p, u, u]
@@ -138,6 +141,13 @@ def check_error(where: str) -> None:
         text = msg.decode("utf-8", "replace")
         L.jsb200_clear_error()
         raise RuntimeError(f"jaxsplat_b200 {where}: {text}")
+
+
+def clear_async(stream: int, ptr: int, nbytes: int) -> None:
+    """zero `nbytes` at device address `ptr` on the raw stream handle `stream` (cudaMemsetAsync)"""
+    if lib().jsb200_clear_async(ctypes.c_void_p(stream), ctypes.c_void_p(ptr), ctypes.c_size_t(nbytes)) != 0:
+        check_error("clear_async")
+        raise RuntimeError("jaxsplat_b200 clear_async failed")
 
 
 def stats() -> dict:

@@ -11,7 +11,7 @@ from __future__ import annotations
 
 import torch
 
-from . import _ops
+from . import _lib, _ops
 from ._project import ProjectDescriptor
 
 
@@ -82,8 +82,11 @@ class _Render(torch.autograd.Function):
             # (enqueued now, i.e. while the forward's later kernels run; ordered after `fork`)
             side = _side_stream(means3d.device)
             side.wait_event(fork)
-            with torch.cuda.stream(side):
-                acc.zero_()
+            try:  # the driver's memset on the side stream: no kernel of torch's in the step
+                _lib.clear_async(side.cuda_stream, acc.data_ptr(), acc.numel() * 4)
+            except Exception:  # (e.g. a side stream of another device than the current one)
+                with torch.cuda.stream(side):
+                    acc.zero_()
             acc.record_stream(side)
             ctx.acc, ctx.acc_ready = acc, side.record_event()
         return img

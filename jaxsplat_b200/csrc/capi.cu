@@ -1433,6 +1433,18 @@ void jsb200_get_stats(unsigned long long *out8) {
     for (int i = 0; i < 8; ++i) out8[i] = jsb::g_stats[i].load();
 }
 
+int jsb200_clear_async(jsb200_stream_t stream, void *ptr, size_t bytes) {
+    if (bytes == 0) return 0;
+    if (!ptr) { jsb::set_error("clear_async: null buffer"); return 1; }
+    const cudaError_t e = cudaMemsetAsync(ptr, 0, bytes, (cudaStream_t)stream);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();  // (not sticky: the next launch check must not see it)
+        jsb::set_error("clear_async: cudaMemsetAsync -> %s", cudaGetErrorString(e));
+        return 1;
+    }
+    return 0;
+}
+
 void jsb200_release(void) {
     std::lock_guard<std::mutex> lk(jsb::g_ctx_mu);
     for (auto &kv : jsb::g_ctx) {

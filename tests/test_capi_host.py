@@ -95,6 +95,15 @@ def test_every_option_is_documented_in_the_header_and_accepted():
         _lib.set_option(key, int(default))
 
 
+def test_clear_async_argument_checks_need_no_gpu():
+    """jsb200_clear_async: zero bytes is a no-op, a null buffer is an error that is raised and
+    cleared (the host layer's fall-back to a framework fill relies on both)"""
+    _lib.clear_async(0, 0, 0)
+    with pytest.raises(RuntimeError, match="null buffer"):
+        _lib.clear_async(0, 0, 16)
+    assert _lib.lib().jsb200_last_error() is None
+
+
 def test_ops_validate_shapes_before_touching_the_gpu():
     n = 8
     z = torch.zeros
