@@ -577,8 +577,10 @@ def main():
         if dom in ("raster_fwd", "raster_bwd"):
             # issue-slot roofline of the dominant rasteriser in SURVEY 8d's unit: useful pixel-
             # Gaussian pairs per second against 148 SMs x 128 FP32 lanes x f_clk / 15 slots per pair
-            # (frac <= 1 by construction: U_f counts every pair of the walked list prefixes, the
-            # kernel evaluates a subset of them).  Beside it the raw issue-slot view: warp
+            # (U_f counts every pair of the walked list prefixes; the kernel evaluates the subset its
+            # 8x8-quadrant pre-filter lets through, so where most pairs are skipped -- C3b's large
+            # splats -- pairs/s can pass the evaluate-everything roof: 0.47 at C3, 1.06 at C3b; the
+            # issue-slot view beside it cannot).  The raw issue-slot view: warp
             # instructions of one launch (ncu smsp__inst_executed.sum of the same kernel on the same
             # workload, committed under profiles/) / its device time, against 4 schedulers x 148 SMs.
             inst = (prof.get("_inst_executed") or {}).get(dom) if args.config == "C3" else None
@@ -596,6 +598,9 @@ def main():
                                "note": "the rasterisers are SM-issue bound (no dense contraction, no "
                                        "tensor cores; DRAM throughput 2-4 %); the HBM stages' fractions "
                                        "are in 'stages'"}
+            if ach_p and ach_p > pair_roof:
+                out["roofline"]["note"] += ("; frac > 1: U_f counts pairs the quadrant pre-filter "
+                                            "skips unevaluated (see 'pairs')")
         else:
             out["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": d["gbs"], "peak": peak,
                                "unit": "GB/s", "frac": d["hbm_frac"], "traffic": traffic,
